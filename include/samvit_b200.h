@@ -1,0 +1,105 @@
+/* samvit_b200 — C ABI of the B200-native SAM ViT image-encoder forward path.
+ *
+ * The reference has no C/FFI operator API for this path: its boundary is the Python module
+ * `sam.modeling.ImageEncoderViT` (sam/modeling/image_encoder.py:17-120) constructed by
+ * `sam/build_sam.py:60-73`.  This header is the C boundary a host binds INSTEAD of that module's
+ * forward; each entry names the reference interface it replaces.  Plain pointers and sizes only,
+ * no torch types.  Every function returns 0 on success; on failure a non-zero code, and
+ * svb_last_error() returns a thread-local message.  All device work is enqueued on the given
+ * CUDA stream; nothing synchronises unless stated.  There is NO CPU fallback.
+ */
+#ifndef SAMVIT_B200_H
+#define SAMVIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svb_encoder svb_encoder_t;
+typedef void* svb_stream_t; /* cudaStream_t */
+
+enum { SVB_MODE_BF16 = 0,      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / residual / norms  */
+       SVB_MODE_FP32 = 1 };    /* validation mode: fp32 operands, fp32 FMA accumulate (1e-4 rel-L2 bar)       */
+enum { SVB_DTYPE_F32 = 0, SVB_DTYPE_BF16 = 1 };
+
+/* Constructor arguments of ImageEncoderViT (image_encoder.py:18-36) as fixed by _build_sam (build_sam.py:60-73). */
+typedef struct svb_config {
+    int32_t img_size;          /* 1024 */
+    int32_t patch_size;        /* 16 */
+    int32_t in_chans;          /* 3 */
+    int32_t embed_dim;         /* 768 / 1024 / 1280 */
+    int32_t depth;             /* 12 / 24 / 32 */
+    int32_t num_heads;         /* 12 / 16 / 16 */
+    int32_t mlp_dim;           /* int(embed_dim * mlp_ratio) */
+    int32_t window_size;       /* 14 */
+    int32_t num_global;        /* len(global_attn_indexes) */
+    int32_t global_idx[16];    /* global_attn_indexes */
+    int32_t fpn_dims[4];       /* SimpleFPN out_dims = {128,256,512,1024} (image_encoder.py:105) */
+    float ln_eps;              /* 1e-6 */
+    float gn_eps;              /* 1e-5 */
+} svb_config_t;
+
+const char* svb_last_error(void);
+int svb_version(void);
+
+/* ---- encoder object: replaces ImageEncoderViT.__init__ / load_state_dict / forward ---- */
+int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out);
+void svb_encoder_destroy(svb_encoder_t* enc);
+
+/* Replaces nn.Module.load_state_dict for one entry: `key` is the reference state_dict key
+ * (e.g. "blocks.3.attn.qkv.weight"); `data` is a DEVICE pointer to `numel` contiguous
+ * fp32 values in the reference layout.  The data is repacked (bf16 and fp32 copies, ConvTranspose /
+ * Conv2d(k=2,s=2) weights re-laid as GEMM operands) into memory owned by the encoder.  Keys of the
+ * never-executed `orig_neck` (image_encoder.py:88-104) are accepted and ignored. */
+int svb_encoder_load_param(svb_encoder_t* enc, const char* key, const float* data, int64_t numel, svb_stream_t stream);
+/* Number of forward-path parameters not yet loaded (0 = ready). */
+int svb_encoder_missing_params(const svb_encoder_t* enc);
+
+/* Workspace the forward needs for `chunk` images processed at once (activations; no allocation inside forward). */
+size_t svb_encoder_workspace_bytes(const svb_encoder_t* enc, int chunk, int mode);
+
+/* Replaces ImageEncoderViT.forward (image_encoder.py:107-120): x is a DEVICE fp32 tensor (B,3,S,S) NCHW;
+ * res2..res5 are DEVICE output tensors NCHW of dtype `out_dtype` with shapes (B,128,S/4,S/4), (B,256,S/8,S/8),
+ * (B,512,S/16,S/16), (B,1024,S/32,S/32).  The batch is processed in chunks of `chunk` images. */
+int svb_encoder_forward(svb_encoder_t* enc, const float* x, int batch, void* res2, void* res3, void* res4, void* res5,
+                        int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
+
+/* Same call with HOST buffers (the end-to-end path): copies each chunk's input host->device, runs the forward and
+ * copies the four outputs device->host, double-buffered on internal streams; returns after everything completed.
+ * Host buffers should be pinned for full PCIe bandwidth. */
+int svb_encoder_forward_host(svb_encoder_t* enc, const float* x_host, int batch, void* res2_host, void* res3_host,
+                             void* res4_host, void* res5_host, int out_dtype, int mode, int chunk);
+
+/* Token stream (B*T, D) fp32 after the patch embedding (block = -1) or after block `block` of the LAST forward's
+ * last chunk, copied into `dst` (device).  Only valid when taps were enabled; used by the parity tests to bisect. */
+int svb_encoder_enable_taps(svb_encoder_t* enc, int enable);
+int svb_encoder_read_tap(svb_encoder_t* enc, int block, float* dst, int64_t numel, svb_stream_t stream);
+
+/* ---- single operators (the pieces of the forward; exported so each can be checked against the oracle) ---- */
+/* nn.Linear / conv-as-GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  mode BF16: A,W bf16 (tcgen05); FP32: fp32. */
+int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
+               const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats,
+               int rows_per_sample, svb_stream_t stream);
+/* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype. */
+int svb_layernorm(const float* x, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim,
+                  float eps, svb_stream_t stream);
+/* Block attention core (image_encoder.py:239-255 + 258-304 + 340-376): qkv [B*g*g, 3*D] token order ->
+ * out [B*g*g, D]; ws == g selects global attention, otherwise ws x ws windows with bias-valued pad keys.
+ * impl: 0 = fp32-math SIMT kernel (dtype f32 or bf16), 1 = tcgen05 kernel (bf16 only). */
+int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w,
+                  const float* qkv_bias, int batch, int grid, int ws, int heads, int head_dim, svb_stream_t stream);
+/* PatchEmbed im2col (image_encoder.py:402-410). */
+int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream);
+/* GroupNorm(1,C) apply from (sum,sumsq) statistics; NHWC rows -> NHWC rows, or -> NCHW with `levels` folded 2x2 stages. */
+int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
+                        int64_t rows, int C, int64_t rows_per_sample, float eps, int gelu, svb_stream_t stream);
+int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out,
+                             int out_dtype, int batch, int grid, int levels, int C, float eps, int gelu, svb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMVIT_B200_H */

@@ -10,9 +10,7 @@ from .synthetic import make_state_dict, make_images, rel_l2  # noqa: F401
 def __getattr__(name):
     # heavy / native parts are imported lazily so that `import iuvl_b200` works without a GPU
     if name in ("ImageEncoderViT", "build_encoder", "sam_encoder_registry", "install_into_reference"):
-        from . import encoder as _enc
+        import importlib
+        _enc = importlib.import_module(__name__ + ".encoder")
         return getattr(_enc, name)
-    if name in ("cabi",):
-        from . import cabi as _c
-        return _c
     raise AttributeError(name)

@@ -1,0 +1,112 @@
+// Shared declarations for the sm_100a SAM ViT encoder kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace svb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing: every C-ABI entry returns 0 on success; message via svb_last_error() ----
+void set_error(const char* fmt, ...);
+#define SVB_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            svb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+#define SVB_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            svb::set_error(__VA_ARGS__);       \
+            return 2;                          \
+        }                                      \
+    } while (0)
+
+// ---- GEMM epilogue description shared by the tcgen05 GEMM and the fp32 SIMT GEMM ----
+// out[r, c] = act(acc[r, c] + bias[c]) + resid[(resid_mod ? r % resid_mod : r), c]
+// optionally accumulating sum / sum-of-squares of (acc + bias) per sample for GroupNorm(1, C).
+struct Epilogue {
+    const float* bias = nullptr;     // [N] fp32
+    const float* resid = nullptr;    // fp32, leading dim ldr; may alias `out` when out is fp32 (in-place residual)
+    int resid_mod = 0;
+    int ldr = 0;
+    int act = 0;                     // 0 none, 1 GELU (erf form)
+    void* out = nullptr;
+    int out_bf16 = 0;                // 1: bf16 output, 0: fp32 output
+    int ldo = 0;
+    double* stats = nullptr;         // [samples][2] (sum, sumsq) or null
+    int rows_per_sample = 1;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_float<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- launchers implemented in the .cu files (all asynchronous on `stream`) ----
+// tcgen05 GEMM: C[M,N] = A[M,K] (bf16, row-major, lda) * W[N,K]^T (bf16, row-major, ldw), fp32 accumulate.
+int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,
+                 cudaStream_t stream);
+// fp32 SIMT GEMM of the validation mode, same contract with fp32 operands.
+int gemm_f32_simt(const float* A, int lda, const float* W, int ldw, int M, int N, int K, const Epilogue& ep,
+                  cudaStream_t stream);
+
+struct AttnParams {
+    const void* qkv;        // [B*grid*grid, 3*D], element type T (token order y*grid+x)
+    void* out;              // [B*grid*grid, D], element type T
+    const float* rel_h;     // [2*ws-1, hd] fp32
+    const float* rel_w;     // [2*ws-1, hd] fp32
+    const float* qkv_bias;  // [3*D] fp32: pad tokens of edge windows have k = b_k, v = b_v
+    int batch, grid, ws, heads, hd;   // ws == grid -> global attention
+};
+// fp32-math SIMT attention with decomposed rel-pos; T = float (validation) or bf16.
+int attention_simt(const AttnParams& p, bool is_bf16, cudaStream_t stream);
+// tcgen05 attention kernels (bf16 in/out).  rel tables are bf16 copies prepared at load time.
+struct AttnTcParams {
+    const bf16* qkv; bf16* out;
+    const bf16* rel_hw;     // [2][L_pad][hd] bf16: h table then w table, rows padded
+    const float* qkv_bias;
+    int batch, grid, ws, heads, hd;
+};
+int attention_tc(const AttnTcParams& p, cudaStream_t stream);
+
+// elementwise / normalisation kernels (elementwise.cu)
+int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s);
+int layernorm_rows(const float* x, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
+                   cudaStream_t s);
+int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s);
+int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,
+                    long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s);
+// final stage: GroupNorm(1,C)+GELU and (pixel-unshuffle) NHWC -> NCHW.  `levels` = number of 2x2 ConvT stages whose
+// sub-pixel index is still folded into the row index (0, 1 or 2); base grid `g` (64 or 32).
+int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
+                         int B, int g, int levels, int C, float eps, int gelu, cudaStream_t s);
+// weight packing
+int pack_cast(const float* src, void* dst, bool dst_bf16, long n, cudaStream_t s);
+int pack_convT(const float* w /*Cin,Cout,2,2*/, void* dst /*[4*Cout, Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
+int pack_conv2x2(const float* w /*Cout,Cin,2,2*/, void* dst /*[Cout, 4*Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
+int pack_bias4(const float* b, float* dst, int C, cudaStream_t s);
+
+}  // namespace svb

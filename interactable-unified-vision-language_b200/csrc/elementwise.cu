@@ -1,0 +1,307 @@
+// HBM-bound stages of the encoder: patch im2col, LayerNorm, GroupNorm(1,C) apply (+GELU, + NHWC->NCHW un-shuffle),
+// the neck's cast / 2x2 space-to-depth gather, and the one-time weight packing kernels.
+// All are sized for coalesced 16-byte accesses; their roofline is HBM bandwidth.
+#include "common.cuh"
+
+namespace svb {
+namespace {
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ void store(bf16* p, float a, float b, float c, float d) {
+        uint2 u;
+        u.x = pack_bf16x2(a, b);
+        u.y = pack_bf16x2(c, d);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// im2col for the patch embedding (PatchEmbed, image_encoder.py:379-410): x NCHW fp32 -> rows = patches (b,py,px),
+// cols = (c, ky, kx), matching patch_embed.proj.weight.reshape(D, C*p*p).  One thread = 4 consecutive kx.
+template <typename T>
+__global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int img, int patch) {
+    const int g = img / patch;
+    const int K = C * patch * patch;
+    const size_t total4 = (size_t)B * C * img * img / 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;                      // flat NCHW element index (input-major -> coalesced reads)
+        const int X = (int)(e % img);
+        const int Y = (int)((e / img) % img);
+        const int c = (int)((e / ((size_t)img * img)) % C);
+        const int b = (int)(e / ((size_t)img * img * C));
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        const int px = X / patch, kx = X % patch, py = Y / patch, ky = Y % patch;
+        const size_t row = ((size_t)b * g + py) * g + px;
+        Vec4<T>::store(out + row * K + (size_t)c * patch * patch + ky * patch + kx, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (norm1 / norm2, image_encoder.py:166,176; eps 1e-6 from build_sam.py:65).
+// fp32 residual stream in, T out.  One warp per row, row cached in registers, two-pass variance.
+constexpr int LN_MAXV = 16;   // float4 per lane -> D <= 2048
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, T* __restrict__ out,
+                 int rows, int D, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int n4 = D >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * D);
+    float4 v[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n4) {
+            v[i] = xr[idx];
+            sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n4) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            sq += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+    T* orow = out + (size_t)warp * D;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bia) + idx);
+            Vec4<T>::store(orow + 4 * idx, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                           (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Neck input staging: the SimpleFPN consumes the raw residual stream (no norm, image_encoder.py:120).  Writes
+//   xb  [B*g*g, D]      = cast(x)                        (A operand of down_4.0 / down_8.0 / down_16.0)
+//   a32 [B*(g/2)^2, 4D] = 2x2 space-to-depth gather     (A operand of the k=2,s=2 conv down_32.0, image_encoder.py:442)
+//        a32[(b,Y,X), (dy*2+dx)*D + c] = x[(b,2Y+dy,2X+dx), c]
+template <typename T>
+__global__ void cast_s2d_kernel(const float* __restrict__ x, T* __restrict__ xb, T* __restrict__ a32, int B, int g, int D) {
+    const size_t total4 = (size_t)B * g * g * D / 4;
+    const int hg = g / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;
+        const int c = (int)(e % D);
+        const size_t tok = e / D;
+        const int xx = (int)(tok % g), yy = (int)((tok / g) % g), b = (int)(tok / ((size_t)g * g));
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        if (xb) Vec4<T>::store(xb + e, v.x, v.y, v.z, v.w);
+        const size_t row = ((size_t)b * hg + (yy >> 1)) * hg + (xx >> 1);
+        const int sub = (yy & 1) * 2 + (xx & 1);
+        Vec4<T>::store(a32 + row * (size_t)(4 * D) + (size_t)sub * D + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm(1, C) apply (image_encoder.py:419-446): statistics (sum, sumsq per sample, fp64) were accumulated by the
+// producing GEMM's epilogue.  NHWC rows in, NHWC rows out (T) for the next GEMM.
+template <typename T>
+__global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, T* __restrict__ out, long rows, int C, long rows_per_sample,
+                                float eps, int gelu) {
+    const size_t total4 = (size_t)rows * C / 4;
+    const double n = (double)rows_per_sample * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;
+        const int c = (int)(e % C);
+        const long row = (long)(e / C);
+        const long sample = row / rows_per_sample;
+        const double mu = stats[2 * sample] / n;
+        const double var = fmax(stats[2 * sample + 1] / n - mu * mu, 0.0);
+        const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float a = (v.x - mean) * rstd * g4.x + b4.x, b = (v.y - mean) * rstd * g4.y + b4.y;
+        float cc = (v.z - mean) * rstd * g4.z + b4.z, d = (v.w - mean) * rstd * g4.w + b4.w;
+        if (gelu) { a = gelu_erf(a); b = gelu_erf(b); cc = gelu_erf(cc); d = gelu_erf(d); }
+        Vec4<T>::store(out + e, a, b, cc, d);
+    }
+}
+
+// Final stage of every branch: GroupNorm(1,C) + GELU, then NHWC (with `levels` folded 2x2 sub-pixel indexes in the row
+// index) -> NCHW.  Input rows are ordered (b, y, x, s_1, ..., s_levels) with s_l = dy_l*2+dx_l; output pixel
+// Y = y*2^L + sum dy_l 2^(L-l), X likewise.  32x32 (pixel x channel) tiles transposed through shared memory so both
+// the reads (along C) and the writes (along X) are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_apply_nchw_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ out, int B, int g, int levels, int C, float eps, int gelu) {
+    __shared__ float tile[32][33];
+    const int Wout = g << levels, Hout = Wout;
+    const int xt = Wout / 32;                       // 32-pixel tiles per output row
+    const int X0 = (blockIdx.x % xt) * 32;
+    const int Y = (blockIdx.x / xt) % Hout;
+    const int b = blockIdx.x / (xt * Hout);
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const long rows_per_sample = (long)g * g << (2 * levels);
+    const double n = (double)rows_per_sample * C;
+    const double mu = stats[2 * b] / n;
+    const double var = fmax(stats[2 * b + 1] / n - mu * mu, 0.0);
+    const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = ty + 8 * k;                   // pixel within the tile
+        const int X = X0 + i;
+        // source row of output pixel (Y, X)
+        long row = ((long)b * g + (Y >> levels)) * g + (X >> levels);
+        for (int l = 1; l <= levels; ++l) {
+            const int sh = levels - l;
+            row = row * 4 + (((Y >> sh) & 1) * 2 + ((X >> sh) & 1));
+        }
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (c < C) {
+            v = (x[row * C + c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+            if (gelu) v = gelu_erf(v);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cj = ty + 8 * k;
+        const int c = c0 + cj;
+        if (c < C) out[(((size_t)b * C + c) * Hout + Y) * Wout + X0 + tx] = from_float<T>(tile[tx][cj]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing (run once per load_state_dict)
+template <typename T>
+__global__ void pack_cast_kernel(const float* __restrict__ s, T* __restrict__ d, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) d[i] = from_float<T>(s[i]);
+}
+// ConvTranspose2d weight (Cin, Cout, 2, 2) -> GEMM weight [N = (dy*2+dx)*Cout + co, K = ci]
+template <typename T>
+__global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ d, int Cin, int Cout) {
+    const long n = (long)4 * Cout * Cin;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const int nrow = (int)(i / Cin);
+        const int co = nrow % Cout, sub = nrow / Cout;
+        d[i] = from_float<T>(w[((long)ci * Cout + co) * 4 + sub]);
+    }
+}
+// Conv2d k=2,s=2 weight (Cout, Cin, 2, 2) -> GEMM weight [N = co, K = (dy*2+dx)*Cin + ci]
+template <typename T>
+__global__ void pack_conv2x2_kernel(const float* __restrict__ w, T* __restrict__ d, int Cin, int Cout) {
+    const long n = (long)4 * Cout * Cin;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % (4 * Cin));
+        const int co = (int)(i / (4 * Cin));
+        const int ci = k % Cin, sub = k / Cin;
+        d[i] = from_float<T>(w[((long)co * Cin + ci) * 4 + sub]);
+    }
+}
+__global__ void pack_bias4_kernel(const float* __restrict__ b, float* __restrict__ d, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * C) d[i] = b[i % C];
+}
+
+inline int grid_for(size_t n, int block) {
+    size_t gsz = (n + block - 1) / block;
+    const size_t cap = 148 * 16;
+    return (int)(gsz < cap ? (gsz ? gsz : 1) : cap);
+}
+
+}  // namespace
+
+int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s) {
+    SVB_REQUIRE(img % patch == 0 && patch % 4 == 0, "im2col_patch: img %d / patch %d unsupported", img, patch);
+    const size_t total4 = (size_t)B * C * img * img / 4;
+    if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img, patch);
+    else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img, patch);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int layernorm_rows(const float* x, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
+                   cudaStream_t s) {
+    SVB_REQUIRE(D % 4 == 0 && D <= LN_MAXV * 128, "layernorm_rows: D=%d unsupported (multiple of 4, <= %d)", D, LN_MAXV * 128);
+    const int blocks = (rows + 7) / 8;
+    if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, w, b, (bf16*)out, rows, D, eps);
+    else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, w, b, (float*)out, rows, D, eps);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s) {
+    SVB_REQUIRE(D % 4 == 0 && grid % 2 == 0, "cast_and_space2depth: D=%d grid=%d unsupported", D, grid);
+    const size_t total4 = (size_t)B * grid * grid * D / 4;
+    if (out_bf16) cast_s2d_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)xb, (bf16*)a32, B, grid, D);
+    else cast_s2d_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)xb, (float*)a32, B, grid, D);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,
+                    long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s) {
+    SVB_REQUIRE(C % 4 == 0, "groupnorm_apply: C=%d must be a multiple of 4", C);
+    const size_t total4 = (size_t)rows * C / 4;
+    if (out_bf16)
+        gn_apply_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, rows, C, rows_per_sample, eps, gelu);
+    else
+        gn_apply_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, stats, gamma, beta, (float*)out, rows, C, rows_per_sample, eps, gelu);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
+                         int B, int g, int levels, int C, float eps, int gelu, cudaStream_t s) {
+    const int Wout = g << levels;
+    SVB_REQUIRE(Wout % 32 == 0 && levels >= 0 && levels <= 2, "groupnorm_apply_nchw: grid %d levels %d unsupported", g, levels);
+    dim3 grid((unsigned)((size_t)B * Wout * (Wout / 32)), (C + 31) / 32);
+    if (out_dtype == 1) gn_apply_nchw_kernel<bf16><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
+    else gn_apply_nchw_kernel<float><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pack_cast(const float* src, void* dst, bool dst_bf16, long n, cudaStream_t s) {
+    if (dst_bf16) pack_cast_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(src, (bf16*)dst, n);
+    else pack_cast_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(src, (float*)dst, n);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int pack_convT(const float* w, void* dst, bool dst_bf16, int Cin, int Cout, cudaStream_t s) {
+    const long n = (long)4 * Cin * Cout;
+    if (dst_bf16) pack_convT_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(w, (bf16*)dst, Cin, Cout);
+    else pack_convT_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(w, (float*)dst, Cin, Cout);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int pack_conv2x2(const float* w, void* dst, bool dst_bf16, int Cin, int Cout, cudaStream_t s) {
+    const long n = (long)4 * Cin * Cout;
+    if (dst_bf16) pack_conv2x2_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(w, (bf16*)dst, Cin, Cout);
+    else pack_conv2x2_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(w, (float*)dst, Cin, Cout);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int pack_bias4(const float* b, float* dst, int C, cudaStream_t s) {
+    pack_bias4_kernel<<<(4 * C + 255) / 256, 256, 0, s>>>(b, dst, C);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace svb

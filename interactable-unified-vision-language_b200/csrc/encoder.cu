@@ -1,0 +1,619 @@
+// Encoder object + C ABI (include/samvit_b200.h).  Host-side orchestration of the forward path
+// ImageEncoderViT.forward (image_encoder.py:107-120): PatchEmbed -> +pos_embed -> depth x Block -> SimpleFPN.
+#include "../../include/samvit_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace svb {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+enum ParamKind { P_VEC, P_GEMM_W, P_CONVT_W, P_CONVT_B, P_CONV22_W, P_IGNORED };
+
+struct Param {
+    ParamKind kind = P_VEC;
+    int64_t numel = 0;
+    int a = 0, b = 0;           // kind-specific dims: GEMM_W (N,K); CONVT_W (Cin,Cout); CONV22_W (Cin,Cout); CONVT_B (C)
+    float* f32 = nullptr;       // packed fp32 copy (all kinds)
+    bf16* b16 = nullptr;        // packed bf16 copy (GEMM operands)
+    bool loaded = false;
+};
+
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    void* alloc(size_t bytes) {
+        off = (off + 1023) & ~size_t(1023);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+};
+
+}  // namespace
+}  // namespace svb
+
+using namespace svb;
+
+struct svb_encoder {
+    svb_config_t cfg;
+    std::map<std::string, Param> params;
+    int D, depth, heads, hd, grid, T, mlp, d4, d8, d32;
+    bool taps_enabled = false;
+    float* taps = nullptr;          // [(depth+1)][T*D] fp32, first image of the last chunk
+    int attn_impl_bf16 = 0;         // 0: SIMT kernel, 1: tcgen05 kernel
+    // host path resources
+    struct HostPath {
+        int chunk = 0, mode = -1, out_dtype = -1;
+        float* xin[2] = {nullptr, nullptr};
+        void* outs[2][4] = {{nullptr}};
+        void* ws = nullptr;
+        size_t ws_bytes = 0;
+        cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+        cudaEvent_t in_done[2], comp_done[2], out_done[2];
+        bool events = false;
+    } hp;
+
+    const Param& P(const std::string& k) const { return params.at(k); }
+    bool is_global(int i) const {
+        for (int j = 0; j < cfg.num_global; ++j)
+            if (cfg.global_idx[j] == i) return true;
+        return false;
+    }
+};
+
+namespace {
+
+void add_param(svb_encoder* e, const std::string& key, ParamKind kind, int64_t numel, int a = 0, int b = 0) {
+    Param p;
+    p.kind = kind;
+    p.numel = numel;
+    p.a = a;
+    p.b = b;
+    e->params[key] = p;
+}
+
+int alloc_param_storage(Param& p) {
+    if (p.kind == P_IGNORED) return 0;
+    int64_t n = p.numel;
+    if (p.kind == P_CONVT_B) n = 4 * p.numel;
+    SVB_CHECK_CUDA(cudaMalloc(&p.f32, sizeof(float) * n));
+    if (p.kind == P_GEMM_W || p.kind == P_CONVT_W || p.kind == P_CONV22_W) SVB_CHECK_CUDA(cudaMalloc(&p.b16, sizeof(bf16) * n));
+    return 0;
+}
+
+struct Buffers {
+    void *A0, *Xn, *QKV, *O, *Hid;
+    float* X;
+    // neck
+    void *Xb, *A32, *Gn, *G2n;
+    float *G, *G2, *G3;
+    double* stats;
+    size_t total;
+};
+
+Buffers plan(const svb_encoder* e, int chunk, int mode, void* base) {
+    const size_t es = (mode == SVB_MODE_BF16) ? 2 : 4;
+    const size_t M = (size_t)chunk * e->T;
+    const int D = e->D;
+    const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
+    Buffers b;
+    Arena ar;
+    ar.base = (char*)base;
+    b.X = (float*)ar.alloc(M * D * 4);
+    b.stats = (double*)ar.alloc(sizeof(double) * 2 * 8 * chunk);
+    const size_t mark = ar.off;
+    b.A0 = ar.alloc(M * kpe * es);
+    b.Xn = ar.alloc(M * D * es);
+    b.QKV = ar.alloc(M * 3 * D * es);
+    b.O = ar.alloc(M * D * es);
+    b.Hid = ar.alloc(M * e->mlp * es);
+    const size_t trunk_end = ar.off;
+    ar.off = mark;   // the neck reuses the trunk's activation buffers
+    b.Xb = ar.alloc(M * D * es);
+    b.A32 = ar.alloc(M * D * es);
+    const size_t dmax = (size_t)(e->d4 > e->d8 ? e->d4 : e->d8);
+    size_t g_elems = M * 4 * dmax;                       // ConvT output [M, 4*d]
+    if (g_elems < M * (size_t)e->cfg.fpn_dims[2]) g_elems = M * (size_t)e->cfg.fpn_dims[2];
+    if (g_elems < (M / 4) * (size_t)e->d32) g_elems = (M / 4) * (size_t)e->d32;
+    b.G = (float*)ar.alloc(g_elems * 4);
+    b.Gn = ar.alloc(g_elems * es);
+    size_t g2_elems = 4 * M * 4 * (size_t)(e->d4 / 2);    // second ConvT output [4M, 4*d4/2]
+    if (g2_elems < 4 * M * (size_t)e->cfg.fpn_dims[1]) g2_elems = 4 * M * (size_t)e->cfg.fpn_dims[1];
+    if (g2_elems < (M / 4) * (size_t)e->cfg.fpn_dims[3]) g2_elems = (M / 4) * (size_t)e->cfg.fpn_dims[3];
+    b.G2 = (float*)ar.alloc(g2_elems * 4);
+    b.G2n = ar.alloc(g2_elems * es);
+    b.G3 = (float*)ar.alloc(16 * M * (size_t)e->cfg.fpn_dims[0] * 4);
+    b.total = (ar.off > trunk_end ? ar.off : trunk_end) + 1024;
+    return b;
+}
+
+int linear(int mode, const void* A, int lda, const Param& W, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+    if (mode == SVB_MODE_BF16) return gemm_bf16_tc((const bf16*)A, lda, W.b16, K, M, N, K, ep, st);
+    return gemm_f32_simt((const float*)A, lda, W.f32, K, M, N, K, ep, st);
+}
+
+int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], int out_dtype, int mode, const Buffers& bf,
+                  cudaStream_t st) {
+    const bool h = (mode == SVB_MODE_BF16);
+    const int D = e->D, T = e->T, g = e->grid;
+    const int M = B * T;
+    const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
+    int rc;
+    // ---- PatchEmbed (image_encoder.py:402-410) + pos_embed (:109-114), fused in the GEMM epilogue ----
+    if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size, e->cfg.patch_size, st))) return rc;
+    {
+        Epilogue ep;
+        ep.bias = e->P("patch_embed.proj.bias").f32;
+        ep.resid = e->P("pos_embed").f32;
+        ep.resid_mod = T;
+        ep.ldr = D;
+        ep.out = bf.X;
+        ep.ldo = D;
+        if ((rc = linear(mode, bf.A0, kpe, e->P("patch_embed.proj.weight"), M, D, kpe, ep, st))) return rc;
+    }
+    if (e->taps_enabled) SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
+
+    // ---- Blocks (image_encoder.py:181-197) ----
+    for (int i = 0; i < e->depth; ++i) {
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        if ((rc = layernorm_rows(bf.X, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
+            return rc;
+        {   // qkv (image_encoder.py:242)
+            Epilogue ep;
+            ep.bias = e->P(p + "attn.qkv.bias").f32;
+            ep.out = bf.QKV;
+            ep.out_bf16 = h;
+            ep.ldo = 3 * D;
+            if ((rc = linear(mode, bf.Xn, D, e->P(p + "attn.qkv.weight"), M, 3 * D, D, ep, st))) return rc;
+        }
+        {   // windowed / global attention with decomposed rel-pos (image_encoder.py:246-253, 258-304, 340-376)
+            const int ws = e->is_global(i) ? g : e->cfg.window_size;
+            if (h && e->attn_impl_bf16 == 1) {
+                AttnTcParams ap;
+                ap.qkv = (const bf16*)bf.QKV; ap.out = (bf16*)bf.O;
+                ap.rel_hw = e->P(p + "attn.rel_pos_h").b16;   // h and w tables packed back to back at load time
+                ap.qkv_bias = e->P(p + "attn.qkv.bias").f32;
+                ap.batch = B; ap.grid = g; ap.ws = ws; ap.heads = e->heads; ap.hd = e->hd;
+                if ((rc = attention_tc(ap, st))) return rc;
+            } else {
+                AttnParams ap;
+                ap.qkv = bf.QKV; ap.out = bf.O;
+                ap.rel_h = e->P(p + "attn.rel_pos_h").f32;
+                ap.rel_w = e->P(p + "attn.rel_pos_w").f32;
+                ap.qkv_bias = e->P(p + "attn.qkv.bias").f32;
+                ap.batch = B; ap.grid = g; ap.ws = ws; ap.heads = e->heads; ap.hd = e->hd;
+                if ((rc = attention_simt(ap, h, st))) return rc;
+            }
+        }
+        {   // proj + shortcut (image_encoder.py:253,194), in place on the fp32 residual stream
+            Epilogue ep;
+            ep.bias = e->P(p + "attn.proj.bias").f32;
+            ep.resid = bf.X; ep.ldr = D;
+            ep.out = bf.X; ep.ldo = D;
+            if ((rc = linear(mode, bf.O, D, e->P(p + "attn.proj.weight"), M, D, D, ep, st))) return rc;
+        }
+        if ((rc = layernorm_rows(bf.X, e->P(p + "norm2.weight").f32, e->P(p + "norm2.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
+            return rc;
+        {   // MLPBlock lin1 + GELU (common.py:25-26)
+            Epilogue ep;
+            ep.bias = e->P(p + "mlp.lin1.bias").f32;
+            ep.act = 1;
+            ep.out = bf.Hid; ep.out_bf16 = h; ep.ldo = e->mlp;
+            if ((rc = linear(mode, bf.Xn, D, e->P(p + "mlp.lin1.weight"), M, e->mlp, D, ep, st))) return rc;
+        }
+        {   // lin2 + residual (image_encoder.py:195)
+            Epilogue ep;
+            ep.bias = e->P(p + "mlp.lin2.bias").f32;
+            ep.resid = bf.X; ep.ldr = D;
+            ep.out = bf.X; ep.ldo = D;
+            if ((rc = linear(mode, bf.Hid, e->mlp, e->P(p + "mlp.lin2.weight"), M, D, e->mlp, ep, st))) return rc;
+        }
+        if (e->taps_enabled)
+            SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps + (size_t)(i + 1) * T * D, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- SimpleFPN neck (image_encoder.py:413-466).  ConvTranspose2d(k=2,s=2) and Conv2d(k=2,s=2) do not overlap, so
+    // each is one GEMM; the 2x2 sub-pixel index stays folded in the row index until the final NCHW write. ----
+    SVB_CHECK_CUDA(cudaMemsetAsync(bf.stats, 0, sizeof(double) * 2 * 8 * B, st));
+    if ((rc = cast_and_space2depth(bf.X, h ? bf.Xb : nullptr, bf.A32, h, B, g, D, st))) return rc;
+    const void* Xb = h ? bf.Xb : (const void*)bf.X;
+    const float geps = e->cfg.gn_eps;
+    const int* od = e->cfg.fpn_dims;
+    auto S = [&](int k) { return bf.stats + (size_t)2 * B * k; };
+    auto gemm_stats = [&](const void* A, int lda, const std::string& wkey, const std::string& bkey, int m, int n, int k,
+                          float* out, double* stats, int rps) {
+        Epilogue ep;
+        ep.bias = e->P(bkey).f32;
+        ep.out = out; ep.ldo = n;
+        ep.stats = stats; ep.rows_per_sample = rps;
+        return linear(mode, A, lda, e->P(wkey), m, n, k, ep, st);
+    };
+    const std::string n = "neck.";
+    // down_16: Conv1x1 -> GN -> GELU  (:435-439)
+    if ((rc = gemm_stats(Xb, D, n + "down_16.0.weight", n + "down_16.0.bias", M, od[2], D, bf.G, S(0), T))) return rc;
+    if ((rc = groupnorm_apply_nchw(bf.G, S(0), e->P(n + "down_16.1.weight").f32, e->P(n + "down_16.1.bias").f32, outs[2], out_dtype,
+                                   B, g, 0, od[2], geps, 1, st))) return rc;
+    // down_8: ConvT -> GN -> Conv1x1 -> GN -> GELU  (:428-434)
+    if ((rc = gemm_stats(Xb, D, n + "down_8.0.weight", n + "down_8.0.bias", M, 4 * e->d8, D, bf.G, S(1), T))) return rc;
+    if ((rc = groupnorm_apply(bf.G, S(1), e->P(n + "down_8.1.weight").f32, e->P(n + "down_8.1.bias").f32, bf.Gn, h, (long)4 * M, e->d8,
+                              (long)4 * T, geps, 0, st))) return rc;
+    if ((rc = gemm_stats(h ? bf.Gn : bf.Gn, e->d8, n + "down_8.2.weight", n + "down_8.2.bias", 4 * M, od[1], e->d8, bf.G2, S(2), 4 * T)))
+        return rc;
+    if ((rc = groupnorm_apply_nchw(bf.G2, S(2), e->P(n + "down_8.3.weight").f32, e->P(n + "down_8.3.bias").f32, outs[1], out_dtype, B,
+                                   g, 1, od[1], geps, 1, st))) return rc;
+    // down_4: ConvT -> GN -> GELU -> ConvT -> GN -> Conv1x1 -> GN -> GELU  (:417-426)
+    if ((rc = gemm_stats(Xb, D, n + "down_4.0.weight", n + "down_4.0.bias", M, 4 * e->d4, D, bf.G, S(3), T))) return rc;
+    if ((rc = groupnorm_apply(bf.G, S(3), e->P(n + "down_4.1.weight").f32, e->P(n + "down_4.1.bias").f32, bf.Gn, h, (long)4 * M, e->d4,
+                              (long)4 * T, geps, 1, st))) return rc;
+    if ((rc = gemm_stats(bf.Gn, e->d4, n + "down_4.3.weight", n + "down_4.3.bias", 4 * M, 4 * (e->d4 / 2), e->d4, bf.G2, S(4), 4 * T)))
+        return rc;
+    if ((rc = groupnorm_apply(bf.G2, S(4), e->P(n + "down_4.4.weight").f32, e->P(n + "down_4.4.bias").f32, bf.G2n, h, (long)16 * M,
+                              e->d4 / 2, (long)16 * T, geps, 0, st))) return rc;
+    if ((rc = gemm_stats(bf.G2n, e->d4 / 2, n + "down_4.5.weight", n + "down_4.5.bias", 16 * M, od[0], e->d4 / 2, bf.G3, S(5), 16 * T)))
+        return rc;
+    if ((rc = groupnorm_apply_nchw(bf.G3, S(5), e->P(n + "down_4.6.weight").f32, e->P(n + "down_4.6.bias").f32, outs[0], out_dtype, B,
+                                   g, 2, od[0], geps, 1, st))) return rc;
+    // down_32: Conv(k2,s2) -> GN -> Conv1x1 -> GN -> GELU  (:441-447)
+    if ((rc = gemm_stats(bf.A32, 4 * D, n + "down_32.0.weight", n + "down_32.0.bias", M / 4, e->d32, 4 * D, bf.G, S(6), T / 4))) return rc;
+    if ((rc = groupnorm_apply(bf.G, S(6), e->P(n + "down_32.1.weight").f32, e->P(n + "down_32.1.bias").f32, bf.Gn, h, (long)M / 4, e->d32,
+                              (long)T / 4, geps, 0, st))) return rc;
+    if ((rc = gemm_stats(bf.Gn, e->d32, n + "down_32.2.weight", n + "down_32.2.bias", M / 4, od[3], e->d32, bf.G2, S(7), T / 4))) return rc;
+    if ((rc = groupnorm_apply_nchw(bf.G2, S(7), e->P(n + "down_32.3.weight").f32, e->P(n + "down_32.3.bias").f32, outs[3], out_dtype, B,
+                                   g / 2, 0, od[3], geps, 1, st))) return rc;
+    return 0;
+}
+
+size_t out_elems_per_image(const svb_encoder* e, int k) {
+    const int S = e->cfg.img_size;
+    const int strides[4] = {4, 8, 16, 32};
+    const size_t hw = (size_t)(S / strides[k]) * (S / strides[k]);
+    return hw * e->cfg.fpn_dims[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* svb_last_error(void) { return g_err; }
+int svb_version(void) { return 100; }
+
+int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
+    SVB_REQUIRE(cfg && out, "svb_encoder_create: null argument");
+    SVB_REQUIRE(cfg->embed_dim % cfg->num_heads == 0, "embed_dim %d not divisible by num_heads %d", cfg->embed_dim, cfg->num_heads);
+    SVB_REQUIRE(cfg->img_size % cfg->patch_size == 0, "img_size %d not divisible by patch_size %d", cfg->img_size, cfg->patch_size);
+    SVB_REQUIRE(cfg->embed_dim % 8 == 0, "embed_dim %d must be a multiple of 8", cfg->embed_dim);
+    SVB_REQUIRE((cfg->img_size / cfg->patch_size) % 32 == 0, "token grid must be a multiple of 32 (img_size 1024, patch 16 -> 64)");
+    SVB_REQUIRE(cfg->num_global >= 0 && cfg->num_global <= 16, "num_global out of range");
+    svb_encoder* e = new svb_encoder();
+    e->cfg = *cfg;
+    e->D = cfg->embed_dim;
+    e->depth = cfg->depth;
+    e->heads = cfg->num_heads;
+    e->hd = e->D / e->heads;
+    e->grid = cfg->img_size / cfg->patch_size;
+    e->T = e->grid * e->grid;
+    e->mlp = cfg->mlp_dim;
+    // SimpleFPN widths (image_encoder.py:416,427,440)
+    e->d4 = std::max(cfg->fpn_dims[0] * 2, e->D / 2);
+    e->d8 = std::max(cfg->fpn_dims[1], e->D / 2);
+    e->d32 = std::max(cfg->fpn_dims[3], e->D * 2);
+    const int D = e->D, p = cfg->patch_size, kpe = cfg->in_chans * p * p;
+    add_param(e, "pos_embed", P_VEC, (int64_t)e->T * D);
+    add_param(e, "patch_embed.proj.weight", P_GEMM_W, (int64_t)D * kpe, D, kpe);
+    add_param(e, "patch_embed.proj.bias", P_VEC, D);
+    for (int i = 0; i < e->depth; ++i) {
+        const std::string b = "blocks." + std::to_string(i) + ".";
+        const int L = 2 * (e->is_global(i) ? e->grid : cfg->window_size) - 1;
+        add_param(e, b + "norm1.weight", P_VEC, D);
+        add_param(e, b + "norm1.bias", P_VEC, D);
+        add_param(e, b + "attn.rel_pos_h", P_VEC, (int64_t)L * e->hd);
+        add_param(e, b + "attn.rel_pos_w", P_VEC, (int64_t)L * e->hd);
+        add_param(e, b + "attn.qkv.weight", P_GEMM_W, (int64_t)3 * D * D, 3 * D, D);
+        add_param(e, b + "attn.qkv.bias", P_VEC, 3 * D);
+        add_param(e, b + "attn.proj.weight", P_GEMM_W, (int64_t)D * D, D, D);
+        add_param(e, b + "attn.proj.bias", P_VEC, D);
+        add_param(e, b + "norm2.weight", P_VEC, D);
+        add_param(e, b + "norm2.bias", P_VEC, D);
+        add_param(e, b + "mlp.lin1.weight", P_GEMM_W, (int64_t)e->mlp * D, e->mlp, D);
+        add_param(e, b + "mlp.lin1.bias", P_VEC, e->mlp);
+        add_param(e, b + "mlp.lin2.weight", P_GEMM_W, (int64_t)D * e->mlp, D, e->mlp);
+        add_param(e, b + "mlp.lin2.bias", P_VEC, D);
+    }
+    for (const char* k : {"orig_neck.0.weight", "orig_neck.1.weight", "orig_neck.1.bias", "orig_neck.2.weight", "orig_neck.3.weight",
+                          "orig_neck.3.bias"})
+        add_param(e, k, P_IGNORED, 0);
+    const int* od = cfg->fpn_dims;
+    const int d4 = e->d4, d8 = e->d8, d32 = e->d32;
+    add_param(e, "neck.down_4.0.weight", P_CONVT_W, (int64_t)D * d4 * 4, D, d4);
+    add_param(e, "neck.down_4.0.bias", P_CONVT_B, d4);
+    add_param(e, "neck.down_4.1.weight", P_VEC, d4);
+    add_param(e, "neck.down_4.1.bias", P_VEC, d4);
+    add_param(e, "neck.down_4.3.weight", P_CONVT_W, (int64_t)d4 * (d4 / 2) * 4, d4, d4 / 2);
+    add_param(e, "neck.down_4.3.bias", P_CONVT_B, d4 / 2);
+    add_param(e, "neck.down_4.4.weight", P_VEC, d4 / 2);
+    add_param(e, "neck.down_4.4.bias", P_VEC, d4 / 2);
+    add_param(e, "neck.down_4.5.weight", P_GEMM_W, (int64_t)od[0] * (d4 / 2), od[0], d4 / 2);
+    add_param(e, "neck.down_4.5.bias", P_VEC, od[0]);
+    add_param(e, "neck.down_4.6.weight", P_VEC, od[0]);
+    add_param(e, "neck.down_4.6.bias", P_VEC, od[0]);
+    add_param(e, "neck.down_8.0.weight", P_CONVT_W, (int64_t)D * d8 * 4, D, d8);
+    add_param(e, "neck.down_8.0.bias", P_CONVT_B, d8);
+    add_param(e, "neck.down_8.1.weight", P_VEC, d8);
+    add_param(e, "neck.down_8.1.bias", P_VEC, d8);
+    add_param(e, "neck.down_8.2.weight", P_GEMM_W, (int64_t)od[1] * d8, od[1], d8);
+    add_param(e, "neck.down_8.2.bias", P_VEC, od[1]);
+    add_param(e, "neck.down_8.3.weight", P_VEC, od[1]);
+    add_param(e, "neck.down_8.3.bias", P_VEC, od[1]);
+    add_param(e, "neck.down_16.0.weight", P_GEMM_W, (int64_t)od[2] * D, od[2], D);
+    add_param(e, "neck.down_16.0.bias", P_VEC, od[2]);
+    add_param(e, "neck.down_16.1.weight", P_VEC, od[2]);
+    add_param(e, "neck.down_16.1.bias", P_VEC, od[2]);
+    add_param(e, "neck.down_32.0.weight", P_CONV22_W, (int64_t)d32 * D * 4, D, d32);
+    add_param(e, "neck.down_32.0.bias", P_VEC, d32);
+    add_param(e, "neck.down_32.1.weight", P_VEC, d32);
+    add_param(e, "neck.down_32.1.bias", P_VEC, d32);
+    add_param(e, "neck.down_32.2.weight", P_GEMM_W, (int64_t)od[3] * d32, od[3], d32);
+    add_param(e, "neck.down_32.2.bias", P_VEC, od[3]);
+    add_param(e, "neck.down_32.3.weight", P_VEC, od[3]);
+    add_param(e, "neck.down_32.3.bias", P_VEC, od[3]);
+    for (auto& kv : e->params) {
+        int rc = alloc_param_storage(kv.second);
+        if (rc) { svb_encoder_destroy(e); return rc; }
+    }
+    const char* env = getenv("SVB_ATTN_IMPL");
+    if (env) e->attn_impl_bf16 = atoi(env);
+    *out = e;
+    return 0;
+}
+
+void svb_encoder_destroy(svb_encoder_t* e) {
+    if (!e) return;
+    for (auto& kv : e->params) {
+        if (kv.second.f32) cudaFree(kv.second.f32);
+        if (kv.second.b16) cudaFree(kv.second.b16);
+    }
+    if (e->taps) cudaFree(e->taps);
+    auto& hp = e->hp;
+    for (int i = 0; i < 2; ++i) {
+        if (hp.xin[i]) cudaFree(hp.xin[i]);
+        for (int k = 0; k < 4; ++k)
+            if (hp.outs[i][k]) cudaFree(hp.outs[i][k]);
+    }
+    if (hp.ws) cudaFree(hp.ws);
+    if (hp.events)
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(hp.in_done[i]); cudaEventDestroy(hp.comp_done[i]); cudaEventDestroy(hp.out_done[i]); }
+    if (hp.s_in) cudaStreamDestroy(hp.s_in);
+    if (hp.s_comp) cudaStreamDestroy(hp.s_comp);
+    if (hp.s_out) cudaStreamDestroy(hp.s_out);
+    delete e;
+}
+
+int svb_encoder_load_param(svb_encoder_t* e, const char* key, const float* data, int64_t numel, svb_stream_t stream) {
+    SVB_REQUIRE(e && key && data, "svb_encoder_load_param: null argument");
+    auto it = e->params.find(key);
+    SVB_REQUIRE(it != e->params.end(), "unexpected state_dict key '%s'", key);
+    Param& p = it->second;
+    if (p.kind == P_IGNORED) { p.loaded = true; return 0; }
+    SVB_REQUIRE(numel == p.numel, "size mismatch for '%s': got %lld elements, expected %lld", key, (long long)numel, (long long)p.numel);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    switch (p.kind) {
+        case P_VEC:
+            SVB_CHECK_CUDA(cudaMemcpyAsync(p.f32, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
+            break;
+        case P_GEMM_W:
+            SVB_CHECK_CUDA(cudaMemcpyAsync(p.f32, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
+            rc = pack_cast(data, p.b16, true, numel, st);
+            break;
+        case P_CONVT_W:
+            rc = pack_convT(data, p.f32, false, p.a, p.b, st);
+            if (!rc) rc = pack_convT(data, p.b16, true, p.a, p.b, st);
+            break;
+        case P_CONVT_B:
+            rc = pack_bias4(data, p.f32, (int)numel, st);
+            break;
+        case P_CONV22_W:
+            rc = pack_conv2x2(data, p.f32, false, p.a, p.b, st);
+            if (!rc) rc = pack_conv2x2(data, p.b16, true, p.a, p.b, st);
+            break;
+        default: break;
+    }
+    if (rc) return rc;
+    p.loaded = true;
+    return 0;
+}
+
+int svb_encoder_missing_params(const svb_encoder_t* e) {
+    int n = 0;
+    for (auto& kv : e->params)
+        if (kv.second.kind != P_IGNORED && !kv.second.loaded) ++n;
+    return n;
+}
+
+size_t svb_encoder_workspace_bytes(const svb_encoder_t* e, int chunk, int mode) {
+    if (!e || chunk <= 0) return 0;
+    return plan(e, chunk, mode, nullptr).total;
+}
+
+int svb_encoder_forward(svb_encoder_t* e, const float* x, int batch, void* res2, void* res3, void* res4, void* res5, int out_dtype,
+                        int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    SVB_REQUIRE(e && x && res2 && res3 && res4 && res5 && workspace, "svb_encoder_forward: null argument");
+    SVB_REQUIRE(mode == SVB_MODE_BF16 || mode == SVB_MODE_FP32, "svb_encoder_forward: bad mode %d", mode);
+    SVB_REQUIRE(out_dtype == SVB_DTYPE_F32 || out_dtype == SVB_DTYPE_BF16, "svb_encoder_forward: bad out_dtype %d", out_dtype);
+    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward: batch %d / chunk %d must be positive", batch, chunk);
+    const int missing = svb_encoder_missing_params(e);
+    SVB_REQUIRE(missing == 0, "svb_encoder_forward: %d parameters have not been loaded", missing);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    if (chunk > batch) chunk = batch;
+    const size_t need = plan(e, chunk, mode, nullptr).total;
+    SVB_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    const Buffers bf = plan(e, chunk, mode, workspace);
+    const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
+    const size_t in_per_img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+    char* res[4] = {(char*)res2, (char*)res3, (char*)res4, (char*)res5};
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        const int B = std::min(chunk, batch - b0);
+        void* outs[4];
+        for (int k = 0; k < 4; ++k) outs[k] = res[k] + (size_t)b0 * out_elems_per_image(e, k) * osz;
+        int rc = forward_chunk(e, x + (size_t)b0 * in_per_img, B, outs, out_dtype, mode, bf, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int svb_encoder_forward_host(svb_encoder_t* e, const float* x_host, int batch, void* res2_host, void* res3_host, void* res4_host,
+                             void* res5_host, int out_dtype, int mode, int chunk) {
+    SVB_REQUIRE(e && x_host && res2_host && res3_host && res4_host && res5_host, "svb_encoder_forward_host: null argument");
+    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward_host: batch/chunk must be positive");
+    const int missing = svb_encoder_missing_params(e);
+    SVB_REQUIRE(missing == 0, "svb_encoder_forward_host: %d parameters have not been loaded", missing);
+    if (chunk > batch) chunk = batch;
+    auto& hp = e->hp;
+    const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
+    const size_t in_per_img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+    if (hp.chunk != chunk || hp.mode != mode || hp.out_dtype != out_dtype) {
+        for (int i = 0; i < 2; ++i) {
+            if (hp.xin[i]) { cudaFree(hp.xin[i]); hp.xin[i] = nullptr; }
+            for (int k = 0; k < 4; ++k)
+                if (hp.outs[i][k]) { cudaFree(hp.outs[i][k]); hp.outs[i][k] = nullptr; }
+        }
+        if (hp.ws) { cudaFree(hp.ws); hp.ws = nullptr; }
+        for (int i = 0; i < 2; ++i) {
+            SVB_CHECK_CUDA(cudaMalloc(&hp.xin[i], sizeof(float) * in_per_img * chunk));
+            for (int k = 0; k < 4; ++k) SVB_CHECK_CUDA(cudaMalloc(&hp.outs[i][k], osz * out_elems_per_image(e, k) * chunk));
+        }
+        hp.ws_bytes = plan(e, chunk, mode, nullptr).total;
+        SVB_CHECK_CUDA(cudaMalloc(&hp.ws, hp.ws_bytes));
+        if (!hp.s_in) {
+            SVB_CHECK_CUDA(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+            SVB_CHECK_CUDA(cudaStreamCreateWithFlags(&hp.s_comp, cudaStreamNonBlocking));
+            SVB_CHECK_CUDA(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                SVB_CHECK_CUDA(cudaEventCreateWithFlags(&hp.in_done[i], cudaEventDisableTiming));
+                SVB_CHECK_CUDA(cudaEventCreateWithFlags(&hp.comp_done[i], cudaEventDisableTiming));
+                SVB_CHECK_CUDA(cudaEventCreateWithFlags(&hp.out_done[i], cudaEventDisableTiming));
+            }
+            hp.events = true;
+        }
+        hp.chunk = chunk; hp.mode = mode; hp.out_dtype = out_dtype;
+    }
+    const Buffers bf = plan(e, chunk, mode, hp.ws);
+    char* res[4] = {(char*)res2_host, (char*)res3_host, (char*)res4_host, (char*)res5_host};
+    int it = 0;
+    for (int b0 = 0; b0 < batch; b0 += chunk, ++it) {
+        const int B = std::min(chunk, batch - b0);
+        const int s = it & 1;
+        // H2D of this chunk may start once the compute that last read xin[s] (two chunks ago) has finished
+        if (it >= 2) SVB_CHECK_CUDA(cudaStreamWaitEvent(hp.s_in, hp.comp_done[s], 0));
+        SVB_CHECK_CUDA(cudaMemcpyAsync(hp.xin[s], x_host + (size_t)b0 * in_per_img, sizeof(float) * in_per_img * B, cudaMemcpyHostToDevice, hp.s_in));
+        SVB_CHECK_CUDA(cudaEventRecord(hp.in_done[s], hp.s_in));
+        SVB_CHECK_CUDA(cudaStreamWaitEvent(hp.s_comp, hp.in_done[s], 0));
+        if (it >= 2) SVB_CHECK_CUDA(cudaStreamWaitEvent(hp.s_comp, hp.out_done[s], 0));   // outs[s] drained to the host
+        int rc = forward_chunk(e, hp.xin[s], B, hp.outs[s], out_dtype, mode, bf, hp.s_comp);
+        if (rc) return rc;
+        SVB_CHECK_CUDA(cudaEventRecord(hp.comp_done[s], hp.s_comp));
+        SVB_CHECK_CUDA(cudaStreamWaitEvent(hp.s_out, hp.comp_done[s], 0));
+        for (int k = 0; k < 4; ++k) {
+            const size_t bytes = osz * out_elems_per_image(e, k);
+            SVB_CHECK_CUDA(cudaMemcpyAsync(res[k] + (size_t)b0 * bytes, hp.outs[s][k], bytes * B, cudaMemcpyDeviceToHost, hp.s_out));
+        }
+        SVB_CHECK_CUDA(cudaEventRecord(hp.out_done[s], hp.s_out));
+    }
+    SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_in));
+    SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_comp));
+    SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_out));
+    return 0;
+}
+
+int svb_encoder_enable_taps(svb_encoder_t* e, int enable) {
+    SVB_REQUIRE(e, "null encoder");
+    if (enable && !e->taps) SVB_CHECK_CUDA(cudaMalloc(&e->taps, sizeof(float) * (size_t)(e->depth + 1) * e->T * e->D));
+    e->taps_enabled = enable != 0;
+    return 0;
+}
+
+int svb_encoder_read_tap(svb_encoder_t* e, int block, float* dst, int64_t numel, svb_stream_t stream) {
+    SVB_REQUIRE(e && e->taps, "taps are not enabled");
+    SVB_REQUIRE(block >= -1 && block < e->depth, "tap index %d out of range", block);
+    SVB_REQUIRE(numel == (int64_t)e->T * e->D, "tap size mismatch: %lld vs %lld", (long long)numel, (long long)e->T * e->D);
+    SVB_CHECK_CUDA(cudaMemcpyAsync(dst, e->taps + (size_t)(block + 1) * e->T * e->D, sizeof(float) * numel, cudaMemcpyDeviceToDevice,
+                                   (cudaStream_t)stream));
+    return 0;
+}
+
+int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
+               const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats, int rows_per_sample,
+               svb_stream_t stream) {
+    SVB_REQUIRE(A && W && out, "svb_linear: null argument");
+    Epilogue ep;
+    ep.bias = bias;
+    ep.act = act_gelu ? 1 : 0;
+    ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
+    ep.out = out; ep.out_bf16 = out_dtype == SVB_DTYPE_BF16; ep.ldo = ldo;
+    ep.stats = gn_stats; ep.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+    if (mode == SVB_MODE_BF16) return gemm_bf16_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
+    if (mode == SVB_MODE_FP32) return gemm_f32_simt((const float*)A, lda, (const float*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
+    SVB_REQUIRE(false, "svb_linear: bad mode %d", mode);
+}
+
+int svb_layernorm(const float* x, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim, float eps,
+                  svb_stream_t stream) {
+    SVB_REQUIRE(x && weight && bias && out, "svb_layernorm: null argument");
+    return layernorm_rows(x, weight, bias, out, out_dtype == SVB_DTYPE_BF16, rows, dim, eps, (cudaStream_t)stream);
+}
+
+int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w, const float* qkv_bias,
+                  int batch, int grid, int ws, int heads, int head_dim, svb_stream_t stream) {
+    SVB_REQUIRE(qkv && out && rel_pos_h && rel_pos_w && qkv_bias, "svb_attention: null argument");
+    if (impl == 0) {
+        AttnParams ap;
+        ap.qkv = qkv; ap.out = out; ap.rel_h = rel_pos_h; ap.rel_w = rel_pos_w; ap.qkv_bias = qkv_bias;
+        ap.batch = batch; ap.grid = grid; ap.ws = ws; ap.heads = heads; ap.hd = head_dim;
+        return attention_simt(ap, dtype == SVB_DTYPE_BF16, (cudaStream_t)stream);
+    }
+    SVB_REQUIRE(false, "svb_attention: impl %d is not available in this build", impl);
+}
+
+int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream) {
+    SVB_REQUIRE(x && out, "svb_im2col: null argument");
+    return im2col_patch(x, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, patch, (cudaStream_t)stream);
+}
+
+int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
+                        int64_t rows, int C, int64_t rows_per_sample, float eps, int gelu, svb_stream_t stream) {
+    SVB_REQUIRE(x && stats && gamma && beta && out, "svb_groupnorm_apply: null argument");
+    return groupnorm_apply(x, stats, gamma, beta, out, out_dtype == SVB_DTYPE_BF16, (long)rows, C, (long)rows_per_sample, eps, gelu,
+                           (cudaStream_t)stream);
+}
+
+int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
+                             int batch, int grid, int levels, int C, float eps, int gelu, svb_stream_t stream) {
+    SVB_REQUIRE(x && stats && gamma && beta && out, "svb_groupnorm_apply_nchw: null argument");
+    return groupnorm_apply_nchw(x, stats, gamma, beta, out, out_dtype, batch, grid, levels, C, eps, gelu, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace svb {
+// tcgen05 attention is linked from attention_tc.cu when present; this weak default keeps the library loadable and
+// fails loudly if the tcgen05 path is selected without it.
+__attribute__((weak)) int attention_tc(const AttnTcParams&, cudaStream_t) {
+    set_error("attention_tc: the tcgen05 attention kernel is not part of this build");
+    return 3;
+}
+}  // namespace svb

@@ -1,0 +1,111 @@
+"""Drop-in boundary (CPU): constructor signature, state_dict keys / shapes / module types identical to the reference
+(fixture tests/golden/reference_state_dict_keys.json was dumped from the unmodified reference via sam.build_sam),
+C-ABI library loads and exports every symbol include/samvit_b200.h declares, and the product fails loudly
+without a GPU instead of falling back."""
+import inspect
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import iuvl_b200 as ib
+from iuvl_b200 import cabi
+from iuvl_b200.encoder import ImageEncoderViT, build_encoder
+from tests.util import GOLDEN, ROOT
+
+
+@pytest.fixture(scope="module")
+def ref_keys():
+    with open(os.path.join(GOLDEN, "reference_state_dict_keys.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("preset", ["vit_b", "vit_l", "vit_h"])
+def test_state_dict_matches_reference(preset, ref_keys):
+    with torch.device("meta"):
+        enc = build_encoder(ib.PRESETS[preset])
+    mine = [[k, list(v.shape)] for k, v in enc.state_dict().items()]
+    assert mine == ref_keys[preset]                      # same keys, same order, same shapes
+    assert [[k, list(s)] for k, s in ib.state_dict_spec(ib.PRESETS[preset])] == ref_keys[preset]
+    assert all(v.dtype == torch.float32 for v in enc.state_dict().values())
+
+
+@pytest.mark.parametrize("preset", ["vit_b", "vit_h"])
+def test_module_tree_matches_reference(preset, ref_keys):
+    """named_modules() names and leaf types: the optimizer grouping tests isinstance(LayerNorm/GroupNorm/...)
+    (trainer/xdecoder_trainer.py:61-73,103-131)."""
+    with torch.device("meta"):
+        enc = build_encoder(ib.PRESETS[preset])
+    mine = [[n, type(m).__name__] for n, m in enc.named_modules()]
+    assert mine == ref_keys[preset + "_modules"]
+
+
+def test_constructor_signature_is_the_reference_one():
+    # image_encoder.py:18-36
+    expected = ["self", "img_size", "patch_size", "in_chans", "embed_dim", "depth", "num_heads", "mlp_ratio", "out_chans",
+                "qkv_bias", "norm_layer", "act_layer", "use_abs_pos", "use_rel_pos", "rel_pos_zero_init", "window_size",
+                "global_attn_indexes"]
+    sig = inspect.signature(ImageEncoderViT.__init__)
+    assert list(sig.parameters) == expected
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["img_size"], d["patch_size"], d["in_chans"], d["embed_dim"], d["depth"], d["num_heads"]) == (1024, 16, 3, 768, 12, 12)
+    assert d["mlp_ratio"] == 4.0 and d["out_chans"] == 256 and d["window_size"] == 0 and d["global_attn_indexes"] == ()
+
+
+def test_load_state_dict_strict_and_eval_train_to():
+    cfg = ib.PRESETS["tiny64"]
+    enc = build_encoder(cfg)
+    sd = ib.make_state_dict(cfg, 3)
+    res = enc.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(enc.blocks[1].attn.rel_pos_h, sd["blocks.1.attn.rel_pos_h"])
+    assert enc.blocks[1].attn.rel_pos_h.shape[0] == 127 and enc.blocks[0].attn.rel_pos_h.shape[0] == 27
+    enc.train(); enc.eval(); enc.to("cpu")
+    assert enc.img_size == 1024
+    # SAM-style prefixed, non-strict load as in build_sam.py:96-99
+    holder = torch.nn.Module()
+    holder.image_encoder = enc
+    msg = holder.load_state_dict({"image_encoder." + k: v for k, v in sd.items()}, strict=False)
+    assert not msg.unexpected_keys
+
+
+def test_no_cpu_fallback():
+    enc = build_encoder(ib.PRESETS["tiny64"])
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        enc(torch.zeros(1, 3, 1024, 1024))
+
+
+def test_unsupported_configurations_raise():
+    with pytest.raises(NotImplementedError):
+        ImageEncoderViT(use_rel_pos=False, window_size=14)
+    with pytest.raises(NotImplementedError):
+        ImageEncoderViT(use_rel_pos=True, window_size=14, act_layer=torch.nn.ReLU)
+
+
+def test_cabi_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "samvit_b200.h")) as f:
+        hdr = f.read()
+    declared = set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(cabi.SYMBOLS), declared ^ set(cabi.SYMBOLS)
+    lib = cabi.lib()                                   # loads the .so and resolves every symbol
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.svb_version() >= 100
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "interactable-unified-vision-language_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert "sam_vit_oracle" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_flops_per_image_match_survey():
+    # 0.98682 / 2.92971 / 5.78735 TFLOP
+    for k, v in (("vit_b", 0.98682e12), ("vit_l", 2.92971e12), ("vit_h", 5.78735e12)):
+        assert abs(ib.PRESETS[k].flops_per_image() / v - 1) < 1e-5

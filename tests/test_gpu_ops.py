@@ -1,0 +1,212 @@
+"""GPU parity of the single operators, called through the C ABI, against fp64 references / the oracle's pieces."""
+import math
+
+import pytest
+import torch
+
+import iuvl_b200 as ib
+from iuvl_b200 import cabi
+from tests.util import ref_attention_core
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _linear(mode, A, W, bias=None, gelu=False, resid=None, resid_mod=0, out_dtype=torch.float32, stats=None, rps=0,
+            out=None):
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    rc = cabi.lib().svb_linear(
+        mode, A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, cabi.ptr(bias), int(gelu), cabi.ptr(resid),
+        resid.stride(0) if resid is not None else 0, resid_mod, out.data_ptr(),
+        cabi.DTYPE_BF16 if out.dtype == torch.bfloat16 else cabi.DTYPE_F32, out.stride(0), cabi.ptr(stats), rps,
+        cabi.stream_ptr())
+    cabi.check(rc, "svb_linear")
+    return out
+
+
+def _ref_linear(A, W, bias=None, gelu=False, resid=None, resid_mod=0):
+    y = A.double() @ W.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    pre = y.clone()
+    if gelu:
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2)))
+    if resid is not None:
+        r = resid.double()
+        if resid_mod:
+            r = r[torch.arange(A.shape[0], device=A.device) % resid_mod]
+        y = y + r
+    return y, pre
+
+
+SHAPES = [(128, 256, 64), (256, 512, 128), (4096, 768, 768), (4096, 2304, 768), (2048, 1280, 5120), (4096, 128, 192),
+          (1024, 1024, 2048), (200, 136, 72), (4096, 3840, 1280), (384, 96, 320), (128, 2560, 640)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tcgen05_plain(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    out = _linear(cabi.MODE_BF16, A, W)
+    torch.cuda.synchronize()
+    ref, _ = _ref_linear(A, W)
+    err = ib.rel_l2(out, ref)
+    assert err < 2e-6, err          # bf16 operands are exact inputs; only fp32 accumulation order differs
+    assert (out.double() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_tcgen05_epilogues(out_dtype):
+    M, N, K = 8192, 1280, 768
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    tol = 1e-5 if out_dtype == torch.float32 else 4e-3
+    # bias + GELU
+    out = _linear(cabi.MODE_BF16, A, W, bias=bias, gelu=True, out_dtype=out_dtype)
+    ref, _ = _ref_linear(A, W, bias, gelu=True)
+    assert ib.rel_l2(out, ref) < tol
+    # bias + broadcast residual (pos_embed style) and in-place residual, fp32 stream
+    if out_dtype == torch.float32:
+        pos = torch.randn(4096, N, generator=g).to(DEV)
+        out = _linear(cabi.MODE_BF16, A, W, bias=bias, resid=pos, resid_mod=4096)
+        ref, _ = _ref_linear(A, W, bias, resid=pos, resid_mod=4096)
+        assert ib.rel_l2(out, ref) < tol
+        X = torch.randn(M, N, generator=g).to(DEV)
+        X0 = X.clone()
+        _linear(cabi.MODE_BF16, A, W, bias=bias, resid=X, out=X)
+        ref, _ = _ref_linear(A, W, bias, resid=X0)
+        assert ib.rel_l2(X, ref) < tol
+        # GroupNorm statistics of (acc + bias), 2 samples of 4096 rows
+        stats = torch.zeros(2, 2, dtype=torch.float64, device=DEV)
+        out = _linear(cabi.MODE_BF16, A, W, bias=bias, stats=stats, rps=4096)
+        ref, pre = _ref_linear(A, W, bias)
+        s_ref = torch.stack([pre.reshape(2, -1).sum(1), (pre ** 2).reshape(2, -1).sum(1)], 1)
+        assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-2), (stats, s_ref)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (4096, 768, 768), (200, 136, 72), (1024, 128, 320)])
+def test_gemm_fp32_simt(M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    out = _linear(cabi.MODE_FP32, A, W, bias=bias, gelu=True, resid=res)
+    ref, _ = _ref_linear(A, W, bias, gelu=True, resid=res)
+    assert ib.rel_l2(out, ref) < 2e-6
+    if M % 128 == 0:
+        stats = torch.zeros(M // 128, 2, dtype=torch.float64, device=DEV)
+        _linear(cabi.MODE_FP32, A, W, bias=bias, stats=stats, rps=128)
+        _, pre = _ref_linear(A, W, bias)
+        s_ref = torch.stack([pre.reshape(M // 128, -1).sum(1), (pre ** 2).reshape(M // 128, -1).sum(1)], 1)
+        assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("D,out_dtype", [(768, torch.float32), (1280, torch.bfloat16), (160, torch.float32), (1024, torch.bfloat16)])
+def test_layernorm(D, out_dtype):
+    rows = 4096 + 3
+    x = torch.randn(rows, D, device=DEV) * 3 + 0.5
+    w, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
+    out = torch.empty(rows, D, dtype=out_dtype, device=DEV)
+    cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                        cabi.DTYPE_BF16 if out_dtype == torch.bfloat16 else cabi.DTYPE_F32, rows, D, 1e-6,
+                                        cabi.stream_ptr()))
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-6)
+    assert ib.rel_l2(out, ref) < (2e-6 if out_dtype == torch.float32 else 3e-3)
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_im2col_matches_conv(out_dtype):
+    B, C, img, p, D = 2, 3, 1024, 16, 64
+    x = torch.randn(B, C, img, img, device=DEV)
+    cols = torch.empty(B * 4096, C * p * p, dtype=out_dtype, device=DEV)
+    cabi.check(cabi.lib().svb_im2col(x.data_ptr(), cols.data_ptr(), cabi.DTYPE_BF16 if out_dtype == torch.bfloat16 else cabi.DTYPE_F32,
+                                     B, C, img, p, cabi.stream_ptr()))
+    w = torch.randn(D, C, p, p, device=DEV)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), stride=p).permute(0, 2, 3, 1).reshape(B * 4096, D)
+    got = cols.double() @ w.double().reshape(D, -1).t()
+    assert ib.rel_l2(got, ref) < (1e-6 if out_dtype == torch.float32 else 5e-3)
+    if out_dtype == torch.float32:   # pure data movement: bit exact against unfold
+        unf = torch.nn.functional.unfold(x, p, stride=p).transpose(1, 2).reshape(B * 4096, -1)
+        assert torch.equal(cols, unf)
+
+
+def _attention(dtype, qkv, rel_h, rel_w, bias, B, g, ws, heads, hd, impl=0):
+    out = torch.empty(B * g * g, heads * hd, dtype=qkv.dtype, device=DEV)
+    cabi.check(cabi.lib().svb_attention(impl, dtype, qkv.data_ptr(), out.data_ptr(), rel_h.data_ptr(), rel_w.data_ptr(),
+                                        bias.data_ptr(), B, g, ws, heads, hd, cabi.stream_ptr()), "svb_attention")
+    return out
+
+
+@pytest.mark.parametrize("ws,heads,hd,rel_std", [(14, 2, 64, 0.02), (14, 2, 80, 0.5), (64, 2, 64, 0.5), (64, 1, 80, 0.02)])
+def test_attention_simt_fp32(ws, heads, hd, rel_std):
+    B, g = 2 if ws == 14 else 1, 64
+    D = heads * hd
+    gen = torch.Generator(device="cpu").manual_seed(ws + hd)
+    qkv = torch.randn(B * g * g, 3 * D, generator=gen)
+    L = 2 * ws - 1
+    rel_h, rel_w = torch.randn(L, hd, generator=gen) * rel_std, torch.randn(L, hd, generator=gen) * rel_std
+    bias = torch.randn(3 * D, generator=gen)
+    ref = ref_attention_core(qkv, rel_h, rel_w, bias, B, g, ws, heads)
+    out = _attention(cabi.DTYPE_F32, qkv.to(DEV), rel_h.to(DEV), rel_w.to(DEV), bias.to(DEV), B, g, ws, heads, hd)
+    assert ib.rel_l2(out, ref) < 5e-6
+
+
+@pytest.mark.parametrize("ws,heads,hd", [(14, 2, 64), (64, 1, 80)])
+def test_attention_simt_bf16(ws, heads, hd):
+    B, g = 1, 64
+    D = heads * hd
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    qkv = torch.randn(B * g * g, 3 * D, generator=gen).bfloat16()
+    L = 2 * ws - 1
+    rel_h, rel_w = torch.randn(L, hd, generator=gen) * 0.1, torch.randn(L, hd, generator=gen) * 0.1
+    bias = torch.randn(3 * D, generator=gen)
+    ref = ref_attention_core(qkv.float(), rel_h, rel_w, bias.bfloat16().float(), B, g, ws, heads)
+    out = _attention(cabi.DTYPE_BF16, qkv.to(DEV), rel_h.to(DEV), rel_w.to(DEV), bias.to(DEV), B, g, ws, heads, hd)
+    assert ib.rel_l2(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("levels,g,C", [(0, 64, 512), (1, 64, 256), (2, 64, 128), (0, 32, 1024)])
+def test_groupnorm_nchw_unshuffle(levels, g, C):
+    """GroupNorm(1,C)+GELU on rows ordered (b,y,x,s1,..) -> NCHW; reference builds the NCHW tensor by explicit
+    pixel un-shuffle and calls torch group_norm."""
+    B = 2
+    rows = B * g * g * 4 ** levels
+    x = torch.randn(rows, C, device=DEV) * 2 + 0.3
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    xs = x.double().reshape(B, -1)
+    stats = torch.stack([xs.sum(1), (xs ** 2).sum(1)], 1).contiguous()
+    Wout = g << levels
+    out = torch.empty(B, C, Wout, Wout, device=DEV)
+    cabi.check(cabi.lib().svb_groupnorm_apply_nchw(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                                   cabi.DTYPE_F32, B, g, levels, C, 1e-5, 1, cabi.stream_ptr()))
+    t = x.double()
+    if levels == 0:
+        nchw = t.reshape(B, g, g, C).permute(0, 3, 1, 2)
+    elif levels == 1:
+        nchw = t.reshape(B, g, g, 2, 2, C).permute(0, 5, 1, 3, 2, 4).reshape(B, C, 2 * g, 2 * g)
+    else:
+        nchw = t.reshape(B, g, g, 2, 2, 2, 2, C).permute(0, 7, 1, 3, 5, 2, 4, 6).reshape(B, C, 4 * g, 4 * g)
+    ref = torch.nn.functional.gelu(torch.nn.functional.group_norm(nchw, 1, gamma.double(), beta.double(), 1e-5))
+    assert ib.rel_l2(out, ref) < 1e-5
+
+
+def test_groupnorm_rows():
+    B, rps, C = 2, 4096 * 4, 384
+    x = torch.randn(B * rps, C, device=DEV) + 1
+    gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    xs = x.double().reshape(B, -1)
+    stats = torch.stack([xs.sum(1), (xs ** 2).sum(1)], 1).contiguous()
+    out = torch.empty(B * rps, C, dtype=torch.bfloat16, device=DEV)
+    cabi.check(cabi.lib().svb_groupnorm_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                              cabi.DTYPE_BF16, B * rps, C, rps, 1e-5, 0, cabi.stream_ptr()))
+    mu = xs.mean(1).reshape(B, 1, 1)
+    var = xs.var(1, unbiased=False).reshape(B, 1, 1)
+    ref = (x.double().reshape(B, rps, C) - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    assert ib.rel_l2(out, ref.reshape(-1, C)) < 3e-3

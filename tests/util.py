@@ -25,3 +25,36 @@ def sampled_rel_l2(t: torch.Tensor, g: dict, key: str) -> float:
 
 def norm_ratio(t: torch.Tensor, g: dict, key: str) -> float:
     return float(t.detach().double().norm().item() / float(g[key + ".norm"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference for the attention core operating directly on a qkv tensor (uses the oracle's pieces)
+def ref_attention_core(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, qkv_bias: torch.Tensor, B: int, g: int,
+                       ws: int, heads: int) -> torch.Tensor:
+    """qkv (B*g*g, 3D) token order -> (B*g*g, D).  Windows of ws x ws with zero-padded-then-biased pad tokens
+    (image_encoder.py:183-187,258-279: the pad is applied after norm1 so pad tokens' qkv equals the bias)."""
+    from oracle import sam_vit_oracle as orc
+    D = qkv.shape[1] // 3
+    hd = D // heads
+    x = qkv.reshape(B, g, g, 3 * D).double()
+    if ws < g:
+        Hp = -(-g // ws) * ws
+        xp = qkv_bias.double().reshape(1, 1, 1, -1).expand(B, Hp, Hp, 3 * D).clone()
+        xp[:, :g, :g] = x
+        wins, pad_hw = orc.window_partition(xp, ws)
+    else:
+        wins, pad_hw = x, (g, g)
+    Bp = wins.shape[0]
+    S = ws * ws
+    q, k, v = wins.reshape(Bp, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    scores = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    Rh = orc.rel_pos_rows(ws, ws, rel_h.double())
+    Rw = orc.rel_pos_rows(ws, ws, rel_w.double())
+    q5 = q.reshape(Bp, heads, ws, ws, hd)
+    bh = torch.einsum("bnhwc,hkc->bnhwk", q5, Rh)
+    bw = torch.einsum("bnhwc,wkc->bnhwk", q5, Rw)
+    scores = (scores.reshape(Bp, heads, ws, ws, ws, ws) + bh[..., :, None] + bw[..., None, :]).reshape(Bp, heads, S, S)
+    out = (torch.softmax(scores, -1) @ v).permute(0, 2, 1, 3).reshape(Bp, ws, ws, D)
+    if ws < g:
+        out = orc.window_unpartition(out, ws, pad_hw, (g, g))
+    return out.reshape(B * g * g, D)
