@@ -99,6 +99,14 @@ int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma,
 int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out,
                              int out_dtype, int batch, int grid, int levels, int C, float eps, int gelu, svb_stream_t stream);
 
+/* ---- measurement helpers (bench.py): launch accounting and a CUDA-event profiler.  Between start and stop every kernel
+ * launch of this library is bracketed by events on its launch stream; stop synchronises the device and returns, per
+ * category {0 GEMM, 1 windowed attention, 2 global attention, 3 norms, 4 other}, the summed device milliseconds,
+ * algorithmic FLOPs, algorithmic bytes and launch counts. ---- */
+int svb_profile_start(void);
+int svb_profile_stop(double* ms5, double* flops5, double* bytes5, int64_t* launches5);
+int64_t svb_launch_count(void);   /* kernels launched by this library since it was loaded */
+
 #ifdef __cplusplus
 }
 #endif

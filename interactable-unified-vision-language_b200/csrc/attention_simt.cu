@@ -169,6 +169,10 @@ int attention_simt(const AttnParams& p, bool is_bf16, cudaStream_t stream) {
     const size_t smem = sizeof(float) * ((size_t)QT * hdp + (size_t)KT * hdp + (size_t)KT * p.hd + (size_t)QT * (KT + 1) +
                                          2 * (size_t)QT * p.ws);
     dim3 grid((S + QT - 1) / QT, p.heads, p.batch * nwin_side * nwin_side);
+    const double D_ = (double)p.heads * p.hd;
+    ProfScope prof(p.ws == p.grid ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
+                   (double)p.batch * nwin_side * nwin_side * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
+                   (double)p.batch * p.grid * p.grid * 4.0 * D_ * (is_bf16 ? 2 : 4), stream);
     if (is_bf16) {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attention_simt_kernel<bf16><<<grid, NT, smem, stream>>>(p);

@@ -65,6 +65,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- launch accounting / optional event profiler (profile.cu) ----
+enum ProfCat { PC_GEMM = 0, PC_ATTN_WIN = 1, PC_ATTN_GLOBAL = 2, PC_NORM = 3, PC_OTHER = 4, PC_COUNT = 5 };
+void count_launch(int n = 1);
+void prof_begin(int cat, double flops, double bytes, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+    cudaStream_t st;
+    ProfScope(int cat, double flops, double bytes, cudaStream_t s, int launches = 1) : st(s) {
+        count_launch(launches);
+        prof_begin(cat, flops, bytes, s);
+    }
+    ~ProfScope() { prof_end(st); }
+};
+
 // ---- launchers implemented in the .cu files (all asynchronous on `stream`) ----
 // tcgen05 GEMM: C[M,N] = A[M,K] (bf16, row-major, lda) * W[N,K]^T (bf16, row-major, ldw), fp32 accumulate.
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,

@@ -230,6 +230,7 @@ inline int grid_for(size_t n, int block) {
 int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s) {
     SVB_REQUIRE(img % patch == 0 && patch % 4 == 0, "im2col_patch: img %d / patch %d unsupported", img, patch);
     const size_t total4 = (size_t)B * C * img * img / 4;
+    ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * (4 + (out_bf16 ? 2 : 4)), s);
     if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img, patch);
     else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img, patch);
     SVB_CHECK_CUDA(cudaGetLastError());
@@ -240,6 +241,7 @@ int layernorm_rows(const float* x, const float* w, const float* b, void* out, bo
                    cudaStream_t s) {
     SVB_REQUIRE(D % 4 == 0 && D <= LN_MAXV * 128, "layernorm_rows: D=%d unsupported (multiple of 4, <= %d)", D, LN_MAXV * 128);
     const int blocks = (rows + 7) / 8;
+    ProfScope prof(PC_NORM, 0, (double)rows * D * (4 + (out_bf16 ? 2 : 4)), s);
     if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, w, b, (bf16*)out, rows, D, eps);
     else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, w, b, (float*)out, rows, D, eps);
     SVB_CHECK_CUDA(cudaGetLastError());
@@ -249,6 +251,7 @@ int layernorm_rows(const float* x, const float* w, const float* b, void* out, bo
 int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s) {
     SVB_REQUIRE(D % 4 == 0 && grid % 2 == 0, "cast_and_space2depth: D=%d grid=%d unsupported", D, grid);
     const size_t total4 = (size_t)B * grid * grid * D / 4;
+    ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * (4 + (out_bf16 ? 2 : 4) * (xb ? 2 : 1)), s);
     if (out_bf16) cast_s2d_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)xb, (bf16*)a32, B, grid, D);
     else cast_s2d_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)xb, (float*)a32, B, grid, D);
     SVB_CHECK_CUDA(cudaGetLastError());
@@ -259,6 +262,7 @@ int groupnorm_apply(const float* x, const double* stats, const float* gamma, con
                     long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s) {
     SVB_REQUIRE(C % 4 == 0, "groupnorm_apply: C=%d must be a multiple of 4", C);
     const size_t total4 = (size_t)rows * C / 4;
+    ProfScope prof(PC_NORM, 0, (double)rows * C * (4 + (out_bf16 ? 2 : 4)), s);
     if (out_bf16)
         gn_apply_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, rows, C, rows_per_sample, eps, gelu);
     else
@@ -272,6 +276,7 @@ int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma
     const int Wout = g << levels;
     SVB_REQUIRE(Wout % 32 == 0 && levels >= 0 && levels <= 2, "groupnorm_apply_nchw: grid %d levels %d unsupported", g, levels);
     dim3 grid((unsigned)((size_t)B * Wout * (Wout / 32)), (C + 31) / 32);
+    ProfScope prof(PC_NORM, 0, (double)B * Wout * Wout * C * (4 + (out_dtype == 1 ? 2 : 4)), s);
     if (out_dtype == 1) gn_apply_nchw_kernel<bf16><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
     else gn_apply_nchw_kernel<float><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
     SVB_CHECK_CUDA(cudaGetLastError());

@@ -109,6 +109,7 @@ int gemm_f32_simt(const float* A, int lda, const float* W, int ldw, int M, int N
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_f32_simt: empty problem");
     SVB_REQUIRE(!ep.stats || (ep.rows_per_sample % TM) == 0, "gemm_f32_simt: rows_per_sample must be a multiple of 128");
     dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+    ProfScope prof(PC_GEMM, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), stream);
     gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, ldw, M, N, K, ep);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -325,6 +325,7 @@ static int launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, in
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
+    ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (ep.out_bf16 ? 2.0 : 4.0) * M * N, stream);
     gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -55,7 +55,7 @@ def test_gemm_tcgen05_plain(M, N, K):
     torch.cuda.synchronize()
     ref, _ = _ref_linear(A, W)
     err = ib.rel_l2(out, ref)
-    assert err < 2e-6, err          # bf16 operands are exact inputs; only fp32 accumulation order differs
+    assert err < 2e-5, err          # bf16 operands are exact inputs; only fp32 accumulation order/rounding differs
     assert (out.double() - ref).abs().max() < 1e-4
 
 
