@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: SAM ViT-H 1024x1024 image-encoder forward, images/s (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); images are sharded data-parallel by batch, no
+collective on the data path.  A "step" = one encoder forward over one batch of synthetic images per GPU.
+Prints ONE JSON line on rank 0 (see the contract in the task statement): `value` = whole-job images/s with inputs
+resident in HBM; `e2e` = same metric through the host-buffer C-ABI call (H2D + D2H inside the timed region);
+`roofline` = dominant kernel (tcgen05 GEMM) from CUDA events around every launch; `cpu_baseline` = the oracle
+timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SAM ViT-H 1024x1024 encoder images/sec"
+UNIT = "images/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            sm_sorted = sorted(sm)
+            # median over the busy samples (top half by power) so idle samples around the region do not dilute it
+            out.update(sm_mhz=sm_sorted[len(sm_sorted) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm (oracle port; the reference itself is Python and /root/reference does
+    not exist on the GPU box) on the host CPU with all threads.  Each step = ONE ViT-H image (bounded sample)."""
+    if rank != 0:
+        return
+    import torch
+    import iuvl_b200 as ib
+    from oracle import sam_vit_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = ib.PRESETS[args.model]
+    sd = ib.make_state_dict(cfg, 1234)
+    x = ib.make_images(1, cfg, 0)
+    for _ in range(args.warmup):
+        orc.encoder_forward_cfg(sd, x, cfg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.encoder_forward_cfg(sd, x, cfg)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = 1.0 / dt
+    sample = f"1 image of the {args.model} workload per step, fp32, torch CPU ops, {torch.get_num_threads()} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": "SAM %s image-encoder forward, batch %d x 3x1024x1024 per GPU (BASELINE.json configs[3] shape), "
+                    "random-init weights" % ({"vit_b": "ViT-B", "vit_l": "ViT-L", "vit_h": "ViT-H"}[args.model], args.batch),
+        "encoder": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "image": 1024,
+        "chunk": args.chunk, "out_dtype": args.out_dtype,
+        "parallelism": f"dp{world}: images sharded by batch, no collective on the data path",
+        "l2": "per-step inputs (batch x 12.6 MB fp32) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="vit_h", choices=["vit_b", "vit_l", "vit_h"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=8, help="images per pass through the kernels")
+    ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import iuvl_b200 as ib
+    from iuvl_b200 import cabi
+    from iuvl_b200.encoder import build_encoder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = ib.PRESETS[args.model]
+    enc = build_encoder(cfg)
+    enc.load_state_dict(ib.make_state_dict(cfg, 1234))
+    enc.to(dev)
+    enc.precision = "bf16"
+    enc.out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
+    enc.max_chunk = args.chunk
+    lib = cabi.lib()
+
+    B = args.batch
+    # synthetic inputs of the workload's shape; a different seed per rank (each GPU owns its shard of the batch)
+    x_host = torch.empty(B, 3, cfg.img_size, cfg.img_size, dtype=torch.float32).pin_memory()
+    g = torch.Generator().manual_seed(1000 + rank)
+    for b in range(B):
+        x_host[b] = torch.randn(3, cfg.img_size, cfg.img_size, generator=g)
+    x_dev = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`) + live roofline ----------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = enc(x_dev)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        launches0 = lib.svb_launch_count()
+        lib.svb_profile_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = enc(x_dev)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        ms5, fl5, by5, ln5 = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
+        lib.svb_profile_stop(ms5, fl5, by5, ln5)
+        launches = lib.svb_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---------------- end to end through the host-buffer C-ABI call ----------------
+    e2e = None
+    if not args.no_e2e:
+        out_host = {f"res{k + 2}": torch.empty(B, cfg.fpn_dims[k], cfg.img_size // s, cfg.img_size // s,
+                                               dtype=enc.out_dtype).pin_memory()
+                    for k, s in enumerate((4, 8, 16, 32))}
+        with torch.no_grad():
+            enc.forward_host(x_host, out_host)          # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(1, min(args.steps, 3))
+            for _ in range(n_e2e):
+                enc.forward_host(x_host, out_host)       # synchronous: returns after the D2H copies completed
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_e2e
+        dt = max_over_ranks(dt)
+        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+               "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host.values())),
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "timer": "host perf_counter around the synchronous C-ABI call, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    flops_img = cfg.flops_per_image()
+    gemm_tflops = (fl5[0] / (ms5[0] * 1e-3) / 1e12) if ms5[0] > 0 else None
+    n_gemm = ln5[0]
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM, all linears + patch-embed + neck convs)",
+        "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None,
+        "frac_of_burst": (gemm_tflops / pk["bf16_burst"]) if gemm_tflops else None,
+        "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+        "launches": int(n_gemm), "avg_launch_ms": (ms5[0] / n_gemm) if n_gemm else None,
+        "flops_per_launch_avg": (fl5[0] / n_gemm) if n_gemm else None,
+        "traffic": None,
+        "step_share": {name: ms5[i] / (ms_total if ms_total else 1) for i, name in
+                       enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},
+        "categories": {name: {"ms_per_step": ms5[i] / args.steps, "launches_per_step": ln5[i] / args.steps,
+                              "tflops": (fl5[i] / (ms5[i] * 1e-3) / 1e12) if ms5[i] > 0 and fl5[i] > 0 else None,
+                              "gbs": (by5[i] / (ms5[i] * 1e-3) / 1e9) if ms5[i] > 0 and by5[i] > 0 else None}
+                       for i, name in enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},
+        "whole_step": {"tflops": value / world * flops_img / 1e12, "frac_of_sustained": value / world * flops_img / 1e12 / pk["bf16_sustained"],
+                       "frac_of_burst": value / world * flops_img / 1e12 / pk["bf16_burst"], "flops_per_image": flops_img},
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import sam_vit_oracle as orc       # the checker, timed as the reported CPU baseline (kind "port")
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = ib.make_state_dict(cfg, 1234)
+        x1 = x_host[:1].clone()
+        t0 = time.perf_counter()
+        orc.encoder_forward_cfg(sd, x1, cfg)
+        dt_cpu = time.perf_counter() - t0
+        cpu_baseline = {"value": 1.0 / dt_cpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"1 image of the same workload ({args.model}, fp32, torch CPU ops), single cold pass of {dt_cpu:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
