@@ -107,6 +107,12 @@ int svb_profile_start(void);
 int svb_profile_stop(double* ms5, double* flops5, double* bytes5, int64_t* launches5);
 int64_t svb_launch_count(void);   /* kernels launched by this library since it was loaded */
 
+/* ---- test hook: one CTA, K/16 tcgen05.mma with caller-supplied smem-descriptor fields; dumps the 128 x N accumulator.
+ * Pins the MN-major / 32B-swizzle descriptor encodings the attention kernel relies on (tests/test_gpu_probe.py). ---- */
+int svb_probe_mma(const void* a, const void* b, float* out, int K, int N, int a_sw, int b_sw, int b_mn_major, int a_manual,
+                  unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo, unsigned b_kstep,
+                  svb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,127 @@
+// Descriptor probe (test infrastructure, exported as svb_probe_mma): runs ONE CTA that loads an A tile [128 x K] and a
+// B tile with TMA (or writes A by hand with the 128B swizzle, the path the attention kernel uses for P), issues
+// K/16 tcgen05.mma with caller-supplied shared-memory descriptor fields, and dumps the 128 x N fp32 accumulator.
+// tests/test_gpu_probe.py uses it to pin the MN-major and 32B-swizzle descriptor encodings against torch.
+#include "../../include/samvit_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace svb {
+int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_rows, int swizzle_bytes);
+
+namespace {
+struct ProbeArgs {
+    int K, N;
+    int a_sw, b_sw;                 // swizzle bytes 128 / 32
+    int a_bytes, b_bytes;           // TMA transaction bytes
+    uint32_t a_lbo, a_sbo, a_kstep; // descriptor byte offsets, per-K=16 start-address advance (bytes)
+    uint32_t b_lbo, b_sbo, b_kstep;
+    uint32_t idesc;
+    int a_manual;                   // 1: A written by threads (row-major [128][K] in global, K = 64*n) with manual SW128
+    const bf16* a_gl;
+};
+
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, ProbeArgs pa, float* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint8_t* sA = sm;                 // up to 64 KB
+    uint8_t* sB = sm + 65536;         // up to 64 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 131072);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(sm + 131072 + 64);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        ptx::mbar_init(&bar[0], 1);
+        ptx::mbar_init(&bar[1], 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) ptx::tmem_alloc(slot, 256);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (pa.a_manual) {
+        // thread t owns row t: K-major, 64-element (128 B) atoms along K, 16-byte chunk c of row r lands at chunk c ^ (r & 7)
+        const int r = tid;
+        for (int atom = 0; atom < pa.K / 64; ++atom)
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(pa.a_gl + (size_t)r * pa.K + atom * 64 + c * 8);
+                *reinterpret_cast<uint4*>(sA + atom * 16384 + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+            }
+        ptx::fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ptx::mbar_expect_tx(&bar[0], (pa.a_manual ? 0 : pa.a_bytes) + pa.b_bytes);
+        if (!pa.a_manual) {
+            if (pa.a_sw == 128) for (int k0 = 0; k0 < pa.K; k0 += 64) ptx::tma_load_2d(sA + (k0 / 64) * 16384, &map_a, &bar[0], k0, 0);
+            else ptx::tma_load_2d(sA, &map_a, &bar[0], 0, 0);
+        }
+        ptx::tma_load_2d(sB, &map_b, &bar[0], 0, 0);
+        ptx::mbar_wait(&bar[0], 0);
+        ptx::tc_fence_after();
+        const uint32_t a_layout = pa.a_sw == 128 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW32;
+        const uint32_t b_layout = pa.b_sw == 128 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW32;
+        for (int k = 0; k < pa.K / 16; ++k) {
+            const uint32_t a_off = pa.a_sw == 128 ? (k >> 2) * 16384 + (k & 3) * pa.a_kstep : k * pa.a_kstep;
+            const uint64_t da = ptx::make_smem_desc(base + a_off, pa.a_lbo, pa.a_sbo, a_layout);
+            const uint64_t db = ptx::make_smem_desc(base + 65536 + k * pa.b_kstep, pa.b_lbo, pa.b_sbo, b_layout);
+            ptx::mma_f16_ss(tmem, da, db, pa.idesc, k ? 1u : 0u);
+        }
+        ptx::mma_commit(&bar[1]);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&bar[1], 0);
+    ptx::tc_fence_after();
+    for (int c0 = 0; c0 < pa.N; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+        ptx::tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) out[(size_t)tid * pa.N + c0 + j] = __uint_as_float(v[j]);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+}
+}  // namespace
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int svb_probe_mma(const void* a, const void* b, float* out, int K, int N, int a_sw, int b_sw, int b_mn_major,
+                             int a_manual, unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo,
+                             unsigned b_kstep, svb_stream_t stream) {
+    SVB_REQUIRE(K % 16 == 0 && N % 16 == 0 && N <= 256, "probe: bad K/N");
+    CUtensorMap ma, mb;
+    ProbeArgs pa{};
+    pa.K = K; pa.N = N; pa.a_sw = a_sw; pa.b_sw = b_sw;
+    pa.a_lbo = a_lbo; pa.a_sbo = a_sbo; pa.a_kstep = a_kstep;
+    pa.b_lbo = b_lbo; pa.b_sbo = b_sbo; pa.b_kstep = b_kstep;
+    pa.idesc = ptx::make_idesc_bf16(128, N, 0, b_mn_major);
+    pa.a_manual = a_manual; pa.a_gl = (const bf16*)a;
+    int rc;
+    // A: global [128][K] row-major; SW128 -> boxes of 64 columns (one per 64-wide atom), SW32 -> K must be 16
+    if (a_sw == 128) rc = make_tmap_2d_bf16(&ma, a, K, 128, K, 64, 128, 128);
+    else rc = make_tmap_2d_bf16(&ma, a, K, 128, K, 16, 128, 32);
+    if (rc) return rc;
+    pa.a_bytes = 128 * K * 2;
+    if (!b_mn_major) {   // B global [N][K] (K contiguous)
+        if (b_sw == 128) rc = make_tmap_2d_bf16(&mb, b, K, N, K, 64, N, 128);
+        else rc = make_tmap_2d_bf16(&mb, b, K, N, K, 16, N, 32);
+        pa.b_bytes = N * (b_sw == 128 ? 64 : 16) * 2;
+        SVB_REQUIRE(K == (b_sw == 128 ? 64 : 16), "probe: K-major B supports a single atom along K");
+    } else {             // B global [K][N] (N contiguous): box {N_inner, K rows}
+        if (b_sw == 128) rc = make_tmap_2d_bf16(&mb, b, N, K, N, 64, K, 128);
+        else rc = make_tmap_2d_bf16(&mb, b, N, K, N, 16, K, 32);
+        pa.b_bytes = K * (b_sw == 128 ? 64 : 16) * 2;
+        SVB_REQUIRE(N == (b_sw == 128 ? 64 : 16), "probe: MN-major B supports a single atom along N");
+    }
+    if (rc) return rc;
+    const int smem = 131072 + 1024 + 256;
+    SVB_CHECK_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, pa, out);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
