@@ -82,7 +82,9 @@ int svb_encoder_read_tap(svb_encoder_t* enc, int block, float* dst, int64_t nume
 /* nn.Linear / conv-as-GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  mode BF16: A,W bf16 (tcgen05); FP32: fp32. */
 int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats,
-               int rows_per_sample, svb_stream_t stream);
+               int rows_per_sample, int remap_grid, int remap_grid_pad, svb_stream_t stream);
+/* remap_grid > 0: output row r (token order, grid x grid per image) is stored at the token's row of the window-padded
+ * grid_pad x grid_pad layout — window_partition's F.pad (image_encoder.py:271-275) expressed as a store address. */
 /* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype. */
 int svb_layernorm(const float* x, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim,
                   float eps, svb_stream_t stream);
@@ -91,6 +93,19 @@ int svb_layernorm(const float* x, const float* weight, const float* bias, void* 
  * impl: 0 = fp32-math SIMT kernel (dtype f32 or bf16), 1 = tcgen05 kernel (bf16 only). */
 int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w,
                   const float* qkv_bias, int batch, int grid, int ws, int heads, int head_dim, svb_stream_t stream);
+/* tcgen05 attention core (bf16).  Same computation as svb_attention; the operands are in the layout the encoder keeps:
+ *   qkv      ws == grid: token order [B*grid*grid, 3*D];  ws == 14: window-padded [B, 70, 70, 3*D] whose pad rows hold
+ *            the qkv bias (svb_fill_pad_rows) — window_partition / window_unpartition (image_encoder.py:258-304) are
+ *            TMA box coordinates and store addresses, nothing is copied;
+ *   rel_pack bf16 [svb_rel_pack_rows(ws, grid)][head_dim] written by svb_pack_rel_table from rel_pos_h / rel_pos_w;
+ *   out      token order [B*grid*grid, D] bf16.
+ * Implemented geometry: grid 64, ws 14 or 64, head_dim 64 or 80 (everything build_sam.py:14-44 instantiates). */
+int svb_attention_tc(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
+                     svb_stream_t stream);
+int svb_rel_pack_rows(int ws, int grid);
+int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int head_dim, int is_w, svb_stream_t stream);
+int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int grid, int grid_pad, int row_len,
+                      svb_stream_t stream);
 /* PatchEmbed im2col (image_encoder.py:402-410). */
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream);
 /* GroupNorm(1,C) apply from (sum,sumsq) statistics; NHWC rows -> NHWC rows, or -> NCHW with `levels` folded 2x2 stages. */

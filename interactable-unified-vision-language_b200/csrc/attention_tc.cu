@@ -1,0 +1,801 @@
+// tcgen05 / TMEM attention with the decomposed relative-position bias built in-kernel (sm_100a, bf16 in / bf16 out).
+//
+// Restates Attention.forward + add_decomposed_rel_pos (image_encoder.py:239-255, 340-376) fused with window_partition /
+// window_unpartition (image_encoder.py:258-304) for the two geometries _build_sam instantiates (build_sam.py:60-73):
+// a 64x64 token grid with 14x14 windows (25 windows of 196 keys on the 70x70 padded grid) and global 64x64 attention.
+//
+//   * Q, K, V tiles come straight out of the qkv GEMM output by TMA (cp.async.bulk.tensor, 128B swizzle for the first
+//     64 head-dim columns, 32B swizzle for the 16-column tail of head_dim 80).  A window is ONE 4-D TMA box
+//     (64 cols x 14 x 14) of the padded [B,70,70,3D] tensor, so window_partition never materialises; the output is written
+//     at the token's own position, so window_unpartition + crop never materialise either.
+//   * S = Q K^T and O = P V run on the tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM).  P is written
+//     back to TMEM as bf16 over the S columns and fed to the second MMA as the TMEM A operand — it never touches
+//     shared or global memory.
+//   * rel-pos: bias(q,k) = q.Rh[qh-kh+ws-1] + q.Rw[qw-kw+ws-1] (unscaled q, image_encoder.py:369-374).  The products
+//     Q.Rh^T and Q.Rw^T against the rel_pos tables are two more tcgen05 MMAs per query tile; each softmax thread (one
+//     query row) pulls its own skewed slice into REGISTERS (w term) / a per-warp column of shared memory (h term) and
+//     adds it in the exp2 argument.  Neither the gathered (S,S,hd) tables nor the (S,S) bias exist anywhere.
+//   * softmax in fp32, base-2 with the scale folded in, lazy rescaling of O (only when the running bound grows by 2^8).
+//
+// Global kernel:   CTA = 256 queries (4 grid rows) of one (image, head); 8 softmax warps (2 query tiles ping-pong on the
+//                  tensor core), 1 TMA warp, 1 MMA warp; K/V tiles of 128 keys through an NST-deep ring.
+// Windowed kernel: CTA = one query tile (9 or 5 window rows) of one (image, window, head); 4 softmax warps + TMA + MMA;
+//                  2 CTAs per SM.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+
+namespace svb {
+int encode_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, int swizzle_bytes);
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays below 2^8 relative to the reference maximum
+
+__device__ __forceinline__ uint64_t desc_k128(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 1024, ptx::LAYOUT_SW128); }
+__device__ __forceinline__ uint64_t desc_k32(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 256, ptx::LAYOUT_SW32); }
+
+// D[128 x N] (+)= A[128 x HD] * B[N x HD]^T, both K-major: 64 columns in a 128B-swizzled tile (+ 16 in a 32B-swizzled tile)
+template <int HD>
+__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t a_main, uint32_t a_tail, uint32_t b_main, uint32_t b_tail,
+                                         uint32_t idesc) {
+    const uint64_t da = desc_k128(a_main), db = desc_k128(b_main);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+    if (HD > 64) ptx::mma_f16_ss(d_tmem, desc_k32(a_tail), desc_k32(b_tail), idesc, 1u);
+}
+
+// O[128 x HD] (+)= P[128 x 16*ksteps] (bf16 in TMEM, two per column) * V[keys x HD] (MN-major in smem)
+template <int HD>
+__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t v_main, uint32_t v_tail, int ksteps,
+                                         bool accumulate) {
+    constexpr uint32_t id_main = ptx::make_idesc_bf16(128, 64, 0, 1);
+    constexpr uint32_t id_tail = ptx::make_idesc_bf16(128, 16, 0, 1);
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t acc = (accumulate || k) ? 1u : 0u;
+        ptx::mma_f16_ts(o_tmem, p_tmem + 8 * k, ptx::make_smem_desc(v_main + k * 2048, 0, 1024, ptx::LAYOUT_SW128), id_main, acc);
+        if (HD > 64)
+            ptx::mma_f16_ts(o_tmem + 64, p_tmem + 8 * k, ptx::make_smem_desc(v_tail + k * 512, 0, 256, ptx::LAYOUT_SW32), id_tail, acc);
+    }
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
+    float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+        m0 = fmaxf(m0, __uint_as_float(v[e]));
+        m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[e + 2]));
+        m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+    }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
+// write HD normalised outputs of one query row
+template <int HD>
+__device__ __forceinline__ void store_row(bf16* dst, uint32_t o_tmem, float inv) {
+    uint32_t v[32];
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+        ptx::tmem_ld_x32(o_tmem + c, v);
+        ptx::tmem_ld_wait_dep(v);
+        if (dst) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+                u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+                u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+                u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+                reinterpret_cast<uint4*>(dst + c)[j] = u;
+            }
+        }
+    }
+    if (HD > 64) {
+        uint32_t w[16];
+        ptx::tmem_ld_x16(o_tmem + 64, w);
+        ptx::tmem_ld_wait_dep(w);
+        if (dst) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(w[8 * j + 0]) * inv, __uint_as_float(w[8 * j + 1]) * inv);
+                u.y = pack_bf16x2(__uint_as_float(w[8 * j + 2]) * inv, __uint_as_float(w[8 * j + 3]) * inv);
+                u.z = pack_bf16x2(__uint_as_float(w[8 * j + 4]) * inv, __uint_as_float(w[8 * j + 5]) * inv);
+                u.w = pack_bf16x2(__uint_as_float(w[8 * j + 6]) * inv, __uint_as_float(w[8 * j + 7]) * inv);
+                reinterpret_cast<uint4*>(dst + 64)[j] = u;
+            }
+        }
+    }
+}
+
+// ================================================================================================================
+//                                              GLOBAL ATTENTION (64 x 64 keys)
+// ================================================================================================================
+template <int HD, int NST_> struct GCfg {
+    static constexpr int NST = NST_;
+    static constexpr int TAIL = HD - 64;
+    static constexpr int T_MAIN = 128 * 128;                  // 128 rows x 64 bf16, 128B swizzle
+    static constexpr int T_TAIL = TAIL ? 128 * 32 : 0;        // 128 rows x 16 bf16, 32B swizzle
+    static constexpr int TILE = T_MAIN + T_TAIL;
+    static constexpr int OFF_Q = 0;                           // 2 query tiles
+    static constexpr int OFF_K = 2 * TILE;                    // NST key tiles
+    static constexpr int OFF_V = OFF_K + NST * TILE;          // NST value tiles
+    static constexpr int OFF_STG = OFF_V + NST * TILE;        // 8 warps x 8 KB: w-term staging, then the h-term columns
+    static constexpr int STG_BYTES = 8 * 8192;
+    static constexpr int OFF_RW = OFF_STG;                    // rel tables alias the staging area (dead after the bias MMAs)
+    static constexpr int RH_MAIN = 80 * 128;
+    static constexpr int RH_TAIL = TAIL ? 3072 : 0;           // 80 x 32 B rounded up to 1 KB
+    static constexpr int OFF_RH = OFF_RW + TILE;
+    static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int Q_TX = 2 * (128 * 128 + (TAIL ? 128 * 32 : 0)) + (128 * 128 + (TAIL ? 128 * 32 : 0)) +
+                                (80 * 128 + (TAIL ? 80 * 32 : 0));
+    static constexpr int KV_TX = 128 * 128 + (TAIL ? 128 * 32 : 0);
+    static_assert(OFF_RH + RH_MAIN + RH_TAIL <= OFF_STG + STG_BYTES, "rel tables must fit in the staging area");
+    static_assert(SMEM <= 232448, "shared memory budget");
+    // barrier slots
+    static constexpr int B_QFULL = 0, B_BIAS = 1, B_KFULL = 2, B_KEMPTY = B_KFULL + NST, B_VFULL = B_KEMPTY + NST,
+                         B_VEMPTY = B_VFULL + NST, B_SFULL = B_VEMPTY + NST, B_PFULL = B_SFULL + 2, B_PVDONE = B_PFULL + 2,
+                         B_COUNT = B_PVDONE + 2;
+    static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
+    // TMEM columns
+    static constexpr int TM_S = 0, TM_O = 256, TM_COLS = 512;   // S_i at 128*i (P_i aliases its first 64), O_i at 256 + 128*i
+};
+
+template <int HD, int NST>
+__global__ void __launch_bounds__(320, 1)
+attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
+                   const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
+                   const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
+                   bf16* __restrict__ out, int D, int T, float scale_log2) {
+    using C = GCfg<HD, NST>;
+    constexpr int NKT = 32;                                     // 4096 keys / 128
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * T + pair * 256;
+    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
+
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tmap(&tm_main);
+        ptx::prefetch_tmap(&tm_rw_main);
+        ptx::prefetch_tmap(&tm_rh_main);
+        if (HD > 64) { ptx::prefetch_tmap(&tm_tail); ptx::prefetch_tmap(&tm_rw_tail); ptx::prefetch_tmap(&tm_rh_tail); }
+        ptx::mbar_init(&bars[C::B_QFULL], 1);
+        ptx::mbar_init(&bars[C::B_BIAS], 1);
+        for (int s = 0; s < NST; ++s) {
+            ptx::mbar_init(&bars[C::B_KFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_KEMPTY + s], 1);
+            ptx::mbar_init(&bars[C::B_VFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_VEMPTY + s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars[C::B_SFULL + i], 1);
+            ptx::mbar_init(&bars[C::B_PFULL + i], 128);
+            ptx::mbar_init(&bars[C::B_PVDONE + i], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::Q_TX);
+            for (int i = 0; i < 2; ++i) {
+                ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE, &tm_main, &bars[C::B_QFULL], colq, row0 + 128 * i);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_QFULL], colq + 64, row0 + 128 * i);
+            }
+            ptx::tma_load_2d(sm + C::OFF_RW, &tm_rw_main, &bars[C::B_QFULL], 0, 144);
+            ptx::tma_load_2d(sm + C::OFF_RH, &tm_rh_main, &bars[C::B_QFULL], 0, 4 * pair);
+            if (HD > 64) {
+                ptx::tma_load_2d(sm + C::OFF_RW + C::T_MAIN, &tm_rw_tail, &bars[C::B_QFULL], 64, 144);
+                ptx::tma_load_2d(sm + C::OFF_RH + C::RH_MAIN, &tm_rh_tail, &bars[C::B_QFULL], 64, 4 * pair);
+            }
+            for (int j = 0; j < NKT; ++j) {
+                const int st = j % NST;
+                const uint32_t par = ((j / NST) & 1) ^ 1;
+                const int krow = b * T + j * 128;
+                ptx::mbar_wait(&bars[C::B_KEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_KFULL + st], C::KV_TX);
+                ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
+                ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::KV_TX);
+                ptx::tma_load_2d(sm + C::OFF_V + st * C::TILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_VFULL + st], colv + 64, krow);
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t id_rh = ptx::make_idesc_bf16(128, 80, 0, 0);
+            const uint32_t q_main[2] = {base + C::OFF_Q, base + C::OFF_Q + C::TILE};
+            const uint32_t q_tail[2] = {q_main[0] + C::T_MAIN, q_main[1] + C::T_MAIN};
+            ptx::mbar_wait(&bars[C::B_QFULL], 0);
+            ptx::tc_fence_after();
+            // decomposed rel-pos products: Q.Rw^T -> S_i columns, Q.Rh[4*pair ..]^T -> O_i columns
+            for (int i = 0; i < 2; ++i)
+                issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_s);
+            for (int i = 0; i < 2; ++i)
+                issue_qk<HD>(tmem + C::TM_O + 128 * i, q_main[i], q_tail[i], base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
+            ptx::mma_commit(&bars[C::B_BIAS]);
+            // S_i(0)
+            ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
+            for (int i = 0; i < 2; ++i) {
+                ptx::mbar_wait(&bars[C::B_PFULL + i], 0);          // bias products consumed: S_i / O_i columns are free
+                ptx::tc_fence_after();
+                issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_K, base + C::OFF_K + C::T_MAIN, id_s);
+                ptx::mma_commit(&bars[C::B_SFULL + i]);
+            }
+            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
+            for (int j = 0; j < NKT; ++j) {
+                const int st = j % NST, nst = (j + 1) % NST;
+                const bool more = (j + 1 < NKT);
+                ptx::mbar_wait(&bars[C::B_VFULL + st], (j / NST) & 1);
+                if (more) ptx::mbar_wait(&bars[C::B_KFULL + nst], ((j + 1) / NST) & 1);
+                for (int i = 0; i < 2; ++i) {
+                    ptx::mbar_wait(&bars[C::B_PFULL + i], (j + 1) & 1);   // P_i(j) is in TMEM
+                    ptx::tc_fence_after();
+                    issue_pv<HD>(tmem + C::TM_O + 128 * i, tmem + C::TM_S + 128 * i, base + C::OFF_V + st * C::TILE,
+                                 base + C::OFF_V + st * C::TILE + C::T_MAIN, 8, j > 0);
+                    ptx::mma_commit(&bars[C::B_PVDONE + i]);
+                    if (i == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
+                    if (more) {
+                        // in-order execution on the tensor pipe: this overwrite of S_i / P_i follows the PV above
+                        issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_K + nst * C::TILE,
+                                     base + C::OFF_K + nst * C::TILE + C::T_MAIN, id_s);
+                        ptx::mma_commit(&bars[C::B_SFULL + i]);
+                        if (i == 1) ptx::mma_commit(&bars[C::B_KEMPTY + nst]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps: 2 groups of 128 query rows =====================
+        const int i = warp >> 2;                                   // query tile of this warp group
+        const int w4 = warp & 3;                                   // TMEM lane quadrant
+        const int t = w4 * 32 + lane;                              // query row inside the tile
+        const int qr = 2 * i + (t >> 6);                           // grid row of the query inside the CTA (0..3), warp-uniform
+        const int qw = t & 63;                                     // grid column of the query
+        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + C::TM_S + 128 * i;
+        const uint32_t o_tmem = tmem + lane_off + C::TM_O + 128 * i;
+        float* stg = reinterpret_cast<float*>(sm + C::OFF_STG + warp * 8192);   // [64][32] fp32, private to this warp
+
+        // ---- rel-pos prologue: w term into registers, h term into this warp's smem column block ----
+        float bwl[64];
+        ptx::mbar_wait(&bars[C::B_BIAS], 0);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(s_tmem + 64 * p + 32 * h, v);
+                ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) stg[(32 * h + e) * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int kw = 0; kw < 64; ++kw) {
+                const int c = qw + 63 - kw;                        // table row qw - kw + 63
+                if ((c >> 6) == p) bwl[kw] = stg[(c & 63) * 32 + lane];
+            }
+            __syncwarp();
+        }
+        float bwmax = bwl[0];
+#pragma unroll
+        for (int kw = 1; kw < 64; ++kw) bwmax = fmaxf(bwmax, bwl[kw]);
+        {
+            // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
+            uint32_t v[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                ptx::tmem_ld_x32(o_tmem + c0, v);
+                ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int kh = qr + 63 - (c0 + e);
+                    if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+                }
+            }
+            uint32_t w[16];
+            ptx::tmem_ld_x16(o_tmem + 64, w);
+            ptx::tmem_ld_wait_dep(w);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int kh = qr + 63 - (64 + e);
+                if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(w[e]) * LOG2E;
+            }
+        }
+        __syncwarp();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_PFULL + i]);                   // phase 0: S_i / O_i columns may be overwritten
+
+        float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NKT; ++j) {
+            ptx::mbar_wait(&bars[C::B_SFULL + i], j & 1);
+            ptx::tc_fence_after();
+            const float bh0 = stg[(2 * j) * 32 + lane], bh1 = stg[(2 * j + 1) * 32 + lane];
+            uint32_t va[32], vb[32];
+            // ---- pass A: raw maxima of the two key rows ----
+            ptx::tmem_ld_x32(s_tmem, va);
+            ptx::tmem_ld_wait_dep(va);
+            ptx::tmem_ld_x32(s_tmem + 32, vb);
+            float sm0 = max32(va, -INFINITY);
+            ptx::tmem_ld_wait_dep(vb);
+            ptx::tmem_ld_x32(s_tmem + 64, va);
+            sm0 = max32(vb, sm0);
+            ptx::tmem_ld_wait_dep(va);
+            ptx::tmem_ld_x32(s_tmem + 96, vb);
+            float sm1 = max32(va, -INFINITY);
+            ptx::tmem_ld_wait_dep(vb);
+            ptx::tmem_ld_x32(s_tmem, va);                          // first chunk of pass B
+            sm1 = max32(vb, sm1);
+            // upper bound of the row maximum in log2 units (scale > 0)
+            const float mb = fmaxf(fmaf(sm0, scale_log2, bh0), fmaf(sm1, scale_log2, bh1)) + bwmax;
+            const bool need = mb > m_ref + RESCALE_THRESHOLD;      // always true for j == 0
+            if (__any_sync(0xffffffffu, need)) {
+                const float m_new = need ? mb : m_ref;
+                if (j > 0) {
+                    const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
+                    ptx::mbar_wait(&bars[C::B_PVDONE + i], (j - 1) & 1);   // O_i holds tiles 0..j-1
+                    ptx::tc_fence_after();
+                    uint32_t r[32];
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        ptx::tmem_ld_x32(o_tmem + c0, r);
+                        ptx::tmem_ld_wait_dep(r);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        ptx::tmem_st_x32(o_tmem + c0, r);
+                    }
+                    if (HD > 64) {
+                        uint32_t r2[16];
+                        ptx::tmem_ld_x16(o_tmem + 64, r2);
+                        ptx::tmem_ld_wait_dep(r2);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r2[e] = __float_as_uint(__uint_as_float(r2[e]) * alpha);
+                        ptx::tmem_st_x16(o_tmem + 64, r2);
+                    }
+                    l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+                }
+                m_ref = m_new;
+            }
+            const float d0 = bh0 - m_ref, d1 = bh1 - m_ref;
+            // ---- pass B: P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
+#define SVB_PASS_B(V, CHUNK)                                                                             \
+            {                                                                                            \
+                uint32_t pk[16];                                                                         \
+                const float dd = ((CHUNK) < 2) ? d0 : d1;                                                \
+                _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
+                    const int kw = 32 * ((CHUNK) & 1) + e;                                               \
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(V[e]), scale_log2, bwl[kw]) + dd);         \
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 1]), scale_log2, bwl[kw + 1]) + dd); \
+                    const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 2]), scale_log2, bwl[kw + 2]) + dd); \
+                    const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 3]), scale_log2, bwl[kw + 3]) + dd); \
+                    l0 += p0; l1 += p1; l2 += p2; l3 += p3;                                              \
+                    pk[e / 2] = pack_bf16x2(p0, p1);                                                     \
+                    pk[e / 2 + 1] = pack_bf16x2(p2, p3);                                                 \
+                }                                                                                        \
+                ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                             \
+            }
+            ptx::tmem_ld_wait_dep(va);
+            ptx::tmem_ld_x32(s_tmem + 32, vb);
+            SVB_PASS_B(va, 0)
+            ptx::tmem_ld_wait_dep(vb);
+            ptx::tmem_ld_x32(s_tmem + 64, va);
+            SVB_PASS_B(vb, 1)
+            ptx::tmem_ld_wait_dep(va);
+            ptx::tmem_ld_x32(s_tmem + 96, vb);
+            SVB_PASS_B(va, 2)
+            ptx::tmem_ld_wait_dep(vb);
+            SVB_PASS_B(vb, 3)
+#undef SVB_PASS_B
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars[C::B_PFULL + i]);
+        }
+        // ---- epilogue: O / l at the query's own token position ----
+        ptx::mbar_wait(&bars[C::B_PVDONE + i], (NKT - 1) & 1);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+        bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD;
+        store_row<HD>(dst, o_tmem, inv);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C::TM_COLS);
+    }
+}
+
+// ================================================================================================================
+//                                      WINDOWED ATTENTION (14 x 14 windows, 196 keys)
+// ================================================================================================================
+template <int HD> struct WCfg {
+    static constexpr int TAIL = HD - 64;
+    static constexpr int Q_MAIN = 128 * 128, Q_TAIL = TAIL ? 128 * 32 : 0;
+    static constexpr int K_MAIN = 208 * 128, K_TAIL = TAIL ? 7168 : 0;       // 208 x 32 B rounded up to 1 KB
+    static constexpr int R_MAIN = 64 * 128, R_TAIL = TAIL ? 64 * 32 : 0;     // rel tables: rows 0..26 h, 32..58 w
+    static constexpr int OFF_Q = 0;
+    static constexpr int OFF_K = OFF_Q + Q_MAIN + Q_TAIL;
+    static constexpr int OFF_V = OFF_K + K_MAIN + K_TAIL;
+    static constexpr int OFF_R = OFF_V + K_MAIN + K_TAIL;
+    static constexpr int OFF_BAR = OFF_R + R_MAIN + R_TAIL;
+    static constexpr int SMEM = OFF_BAR + 128 + 1024;
+    static constexpr int STG_BYTES = 4 * 4096;                               // 4 warps x [32][32] fp32, aliases the V tile
+    static_assert(STG_BYTES <= 196 * 128, "staging must not reach the zeroed V pad rows");
+    static_assert(2 * (SMEM + 1024) <= 233472, "two CTAs per SM");
+    static constexpr int QR_TX = 64 * 128 + (TAIL ? 64 * 32 : 0);            // + query rows * (128 + 32)
+    static constexpr int KV_TX = 196 * 128 + (TAIL ? 196 * 32 : 0);
+    static constexpr int B_QFULL = 0, B_BIAS = 1, B_KFULL = 2, B_VFULL = 3, B_SFULL = 4, B_PFULL = 5, B_PVDONE = 6, B_COUNT = 7;
+    static constexpr int TM_S = 0, TM_O = 112, TM_COLS = 256;                // bias product at [0,64), P at [0,104), O at [112,112+HD)
+};
+
+struct WinMaps {
+    CUtensorMap q0_main, q1_main, kv_main, r_main;     // boxes (64,14,9,1) / (64,14,5,1) / (64,14,14,1) / (64,64)
+    CUtensorMap q0_tail, q1_tail, kv_tail, r_tail;     // boxes (16, ...)
+};
+
+template <int HD>
+__global__ void __launch_bounds__(192, 2)
+attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out, int D, int g, float scale_log2) {
+    using C = WCfg<HD>;
+    constexpr int WS = 14, NWS = 5;
+    const int qt = blockIdx.x, head = blockIdx.y;
+    const int b = blockIdx.z / (NWS * NWS), win = blockIdx.z % (NWS * NWS);
+    const int wy = win / NWS, wx = win % NWS;
+    const int yi0 = qt ? 9 : 0;
+    if (wy * WS + yi0 >= g) return;                               // every query row of this tile is padding (cropped later)
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
+    const int qrows = qt ? 70 : 126;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tmap(&maps.kv_main);
+        ptx::prefetch_tmap(qt ? &maps.q1_main : &maps.q0_main);
+        ptx::prefetch_tmap(&maps.r_main);
+        for (int s = 0; s < C::B_COUNT; ++s) ptx::mbar_init(&bars[s], s == C::B_PFULL ? 128 : 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 5) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int x0 = wx * WS, y0 = wy * WS;
+            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::QR_TX + qrows * (128 + (HD > 64 ? 32 : 0)));
+            ptx::tma_load_4d(sm + C::OFF_Q, qt ? &maps.q1_main : &maps.q0_main, &bars[C::B_QFULL], colq, x0, y0 + yi0, b);
+            ptx::tma_load_2d(sm + C::OFF_R, &maps.r_main, &bars[C::B_QFULL], 0, 0);
+            if (HD > 64) {
+                ptx::tma_load_4d(sm + C::OFF_Q + C::Q_MAIN, qt ? &maps.q1_tail : &maps.q0_tail, &bars[C::B_QFULL], colq + 64, x0, y0 + yi0, b);
+                ptx::tma_load_2d(sm + C::OFF_R + C::R_MAIN, &maps.r_tail, &bars[C::B_QFULL], 64, 0);
+            }
+            ptx::mbar_expect_tx(&bars[C::B_KFULL], C::KV_TX);
+            ptx::tma_load_4d(sm + C::OFF_K, &maps.kv_main, &bars[C::B_KFULL], colk, x0, y0, b);
+            if (HD > 64) ptx::tma_load_4d(sm + C::OFF_K + C::K_MAIN, &maps.kv_tail, &bars[C::B_KFULL], colk + 64, x0, y0, b);
+            ptx::mbar_wait(&bars[C::B_PFULL], 0);                  // the staging area inside the V tile is dead
+            ptx::mbar_expect_tx(&bars[C::B_VFULL], C::KV_TX);
+            ptx::tma_load_4d(sm + C::OFF_V, &maps.kv_main, &bars[C::B_VFULL], colv, x0, y0, b);
+            if (HD > 64) ptx::tma_load_4d(sm + C::OFF_V + C::K_MAIN, &maps.kv_tail, &bars[C::B_VFULL], colv + 64, x0, y0, b);
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t id_r = ptx::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 208, 0, 0);
+            ptx::mbar_wait(&bars[C::B_QFULL], 0);
+            ptx::tc_fence_after();
+            issue_qk<HD>(tmem + C::TM_S, base + C::OFF_Q, base + C::OFF_Q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
+            ptx::mma_commit(&bars[C::B_BIAS]);
+            ptx::mbar_wait(&bars[C::B_KFULL], 0);
+            ptx::mbar_wait(&bars[C::B_PFULL], 0);                  // bias product consumed
+            ptx::tc_fence_after();
+            issue_qk<HD>(tmem + C::TM_S, base + C::OFF_Q, base + C::OFF_Q + C::Q_MAIN, base + C::OFF_K, base + C::OFF_K + C::K_MAIN, id_s);
+            ptx::mma_commit(&bars[C::B_SFULL]);
+            ptx::mbar_wait(&bars[C::B_VFULL], 0);
+            ptx::mbar_wait(&bars[C::B_PFULL], 1);                  // P is in TMEM
+            ptx::tc_fence_after();
+            issue_pv<HD>(tmem + C::TM_O, tmem + C::TM_S, base + C::OFF_V, base + C::OFF_V + C::K_MAIN, 13, false);
+            ptx::mma_commit(&bars[C::B_PVDONE]);
+        }
+    } else {
+        // ===================== softmax warps: 128 query rows =====================
+        const int t = warp * 32 + lane;
+        const int yi = yi0 + t / WS, xi = t % WS;
+        const int y = wy * WS + yi, x = wx * WS + xi;
+        const bool valid = (t < qrows) && (y < g) && (x < g);
+        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + C::TM_S;
+        const uint32_t o_tmem = tmem + lane_off + C::TM_O;
+        float* stg = reinterpret_cast<float*>(sm + C::OFF_V + warp * 4096);     // [32][32] fp32, private to this warp
+
+        // keys 196..207 of the PV contraction multiply P = 0: their V rows must be finite
+        if (t < 96) *reinterpret_cast<uint4*>(sm + C::OFF_V + 196 * 128 + t * 16) = make_uint4(0, 0, 0, 0);
+        if (HD > 64 && t < 24) *reinterpret_cast<uint4*>(sm + C::OFF_V + C::K_MAIN + 196 * 32 + t * 16) = make_uint4(0, 0, 0, 0);
+        ptx::fence_proxy_async_smem();
+
+        // ---- rel-pos prologue: both terms into registers through the per-warp staging block ----
+        float bhm[14], bwl[14];
+        ptx::mbar_wait(&bars[C::B_BIAS], 0);
+        ptx::tc_fence_after();
+        const int yc = yi < 18 ? yi : 18;                          // rows beyond the tile hold garbage; keep the reads in bounds
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(s_tmem + 32 * p, v);
+            ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) stg[e * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+            __syncwarp();
+            if (p == 0) {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) bhm[k] = stg[(yc + 13 - k) * 32 + lane];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) bwl[k] = stg[(xi + 13 - k) * 32 + lane];
+            }
+            __syncwarp();
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 0
+
+        float bmax = bhm[0], wmax = bwl[0];
+#pragma unroll
+        for (int k = 1; k < 14; ++k) { bmax = fmaxf(bmax, bhm[k]); wmax = fmaxf(wmax, bwl[k]); }
+
+        ptx::mbar_wait(&bars[C::B_SFULL], 0);
+        ptx::tc_fence_after();
+        uint32_t va[32], vb[32], vt[4];
+        // ---- pass A: raw maximum over the 196 keys ----
+        float smax = -INFINITY;
+        ptx::tmem_ld_x32(s_tmem, va);
+        ptx::tmem_ld_wait_dep(va);
+#pragma unroll
+        for (int c = 1; c < 6; ++c) {
+            if (c & 1) { ptx::tmem_ld_x32(s_tmem + 32 * c, vb); smax = max32(va, smax); ptx::tmem_ld_wait_dep(vb); }
+            else       { ptx::tmem_ld_x32(s_tmem + 32 * c, va); smax = max32(vb, smax); ptx::tmem_ld_wait_dep(va); }
+        }
+        ptx::tmem_ld_x4(s_tmem + 192, vt);
+        smax = max32(vb, smax);
+        ptx::tmem_ld_wait_dep(vt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) smax = fmaxf(smax, __uint_as_float(vt[e]));
+        const float m_ref = fmaf(smax, scale_log2, bmax + wmax);   // upper bound of the row maximum (scale > 0)
+#pragma unroll
+        for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
+        // ---- pass B ----
+        float l0 = 0.f, l1 = 0.f;
+#define SVB_WIN_B(V, CHUNK)                                                                              \
+        {                                                                                                \
+            uint32_t pk[16];                                                                             \
+            _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                          \
+                const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                            \
+                const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(V[e]), scale_log2, bwl[k0 % 14]) + bhm[k0 / 14]);     \
+                const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 1]), scale_log2, bwl[k1 % 14]) + bhm[k1 / 14]); \
+                l0 += p0; l1 += p1;                                                                      \
+                pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
+            }                                                                                            \
+            ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
+        }
+        ptx::tmem_ld_x32(s_tmem, va);
+        ptx::tmem_ld_wait_dep(va);
+        ptx::tmem_ld_x32(s_tmem + 32, vb);
+        SVB_WIN_B(va, 0)
+        ptx::tmem_ld_wait_dep(vb);
+        ptx::tmem_ld_x32(s_tmem + 64, va);
+        SVB_WIN_B(vb, 1)
+        ptx::tmem_ld_wait_dep(va);
+        ptx::tmem_ld_x32(s_tmem + 96, vb);
+        SVB_WIN_B(va, 2)
+        ptx::tmem_ld_wait_dep(vb);
+        ptx::tmem_ld_x32(s_tmem + 128, va);
+        SVB_WIN_B(vb, 3)
+        ptx::tmem_ld_wait_dep(va);
+        ptx::tmem_ld_x32(s_tmem + 160, vb);
+        SVB_WIN_B(va, 4)
+        ptx::tmem_ld_wait_dep(vb);
+        SVB_WIN_B(vb, 5)
+#undef SVB_WIN_B
+        {
+            // keys 192..195 (vt was loaded in pass A and is still live) + zero columns for keys 196..207
+            uint32_t pk[8];
+            const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]) + bhm[192 / 14]);
+            const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14]);
+            const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14]);
+            const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14]);
+            l0 += p0 + p2; l1 += p1 + p3;
+            pk[0] = pack_bf16x2(p0, p1);
+            pk[1] = pack_bf16x2(p2, p3);
+#pragma unroll
+            for (int e = 2; e < 8; ++e) pk[e] = 0u;
+            ptx::tmem_st_x8(s_tmem + 96, pk);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 1
+        // ---- epilogue ----
+        ptx::mbar_wait(&bars[C::B_PVDONE], 0);
+        ptx::tc_fence_after();
+        const float inv = 1.0f / (l0 + l1);
+        bf16* dst = valid ? out + ((size_t)b * g * g + (size_t)y * g + x) * D + head * HD : nullptr;
+        store_row<HD>(dst, o_tmem, inv);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C::TM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pad rows of the padded [B, gp, gp, ld] qkv tensor = the qkv bias (pad tokens are zero AFTER norm1, image_encoder.py:183-187,
+// 271-275, so their k / v are b_k / b_v); written once per windowed block before the attention kernel reads it.
+__global__ void fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int B, int g, int gp, int ld) {
+    const int npad = gp * gp - g * g;
+    const int v8 = ld / 8;
+    const long total = (long)B * npad * v8;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % v8);
+        const long r = i / v8;
+        const int pi = (int)(r % npad), b = (int)(r / npad);
+        // pad index -> (y, x): first the right-hand strip of the g real rows, then the full bottom rows
+        int y, x;
+        const int strip = g * (gp - g);
+        if (pi < strip) { y = pi / (gp - g); x = g + pi % (gp - g); }
+        else { y = g + (pi - strip) / gp; x = (pi - strip) % gp; }
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+        uint4 u;
+        u.x = pack_bf16x2(b0.x, b0.y); u.y = pack_bf16x2(b0.z, b0.w);
+        u.z = pack_bf16x2(b1.x, b1.y); u.w = pack_bf16x2(b1.z, b1.w);
+        *reinterpret_cast<uint4*>(qkv + (((size_t)b * gp + y) * gp + x) * ld + c8 * 8) = u;
+    }
+}
+
+// rel_pos table (L, hd) fp32 -> rows [row_off, row_off + L) of the packed bf16 table
+__global__ void pack_rel_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int L, int hd, int row_off) {
+    const int n = L * hd;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[(size_t)row_off * hd + i] = __float2bfloat16_rn(src[i]);
+}
+
+template <int HD>
+int launch_global(const AttnTcParams& p, cudaStream_t stream) {
+    constexpr int NST = (HD > 64) ? 2 : 3;
+    using C = GCfg<HD, NST>;
+    const int D = p.heads * p.hd, T = p.grid * p.grid;
+    CUtensorMap m[6];
+    int rc;
+    {
+        const uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)p.batch * T};
+        const uint64_t str[1] = {(uint64_t)3 * D * 2};
+        const uint32_t bm[2] = {64, 128}, bt[2] = {16, 128};
+        if ((rc = encode_tmap_nd_bf16(&m[0], p.qkv, 2, dims, str, bm, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&m[1], p.qkv, 2, dims, str, bt, 32))) return rc;
+        const uint64_t rd[2] = {(uint64_t)HD, 272};
+        const uint64_t rs[1] = {(uint64_t)HD * 2};
+        const uint32_t wm[2] = {64, 128}, wt[2] = {16, 128}, hm[2] = {64, 80}, ht[2] = {16, 80};
+        if ((rc = encode_tmap_nd_bf16(&m[2], p.rel_pack, 2, rd, rs, wm, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&m[3], p.rel_pack, 2, rd, rs, wt, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&m[4], p.rel_pack, 2, rd, rs, hm, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&m[5], p.rel_pack, 2, rd, rs, ht, 32))) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    const float scale_log2 = LOG2E / sqrtf((float)HD);
+    dim3 grid(T / 256, p.heads, p.batch);
+    attn_global_kernel<HD, NST><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int HD>
+int launch_window(const AttnTcParams& p, cudaStream_t stream) {
+    using C = WCfg<HD>;
+    const int D = p.heads * p.hd, gp = 70;
+    WinMaps wm;
+    int rc;
+    {
+        const uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)gp, (uint64_t)gp, (uint64_t)p.batch};
+        const uint64_t str[3] = {(uint64_t)3 * D * 2, (uint64_t)gp * 3 * D * 2, (uint64_t)gp * gp * 3 * D * 2};
+        const uint32_t q0[4] = {64, 14, 9, 1}, q1[4] = {64, 14, 5, 1}, kv[4] = {64, 14, 14, 1};
+        const uint32_t q0t[4] = {16, 14, 9, 1}, q1t[4] = {16, 14, 5, 1}, kvt[4] = {16, 14, 14, 1};
+        if ((rc = encode_tmap_nd_bf16(&wm.q0_main, p.qkv, 4, dims, str, q0, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q1_main, p.qkv, 4, dims, str, q1, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.kv_main, p.qkv, 4, dims, str, kv, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q0_tail, p.qkv, 4, dims, str, q0t, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q1_tail, p.qkv, 4, dims, str, q1t, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.kv_tail, p.qkv, 4, dims, str, kvt, 32))) return rc;
+        const uint64_t rd[2] = {(uint64_t)HD, 64};
+        const uint64_t rs[1] = {(uint64_t)HD * 2};
+        const uint32_t rm[2] = {64, 64}, rt[2] = {16, 64};
+        if ((rc = encode_tmap_nd_bf16(&wm.r_main, p.rel_pack, 2, rd, rs, rm, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.r_tail, p.rel_pack, 2, rd, rs, rt, 32))) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    const float scale_log2 = LOG2E / sqrtf((float)HD);
+    dim3 grid(2, p.heads, p.batch * 25);
+    attn_window_kernel<HD><<<grid, 192, C::SMEM, stream>>>(wm, p.out, D, p.grid, scale_log2);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int attention_tc_rel_rows(int ws, int grid) { return ws == grid ? 272 : 64; }
+
+int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream) {
+    SVB_REQUIRE(L == 27 || L == 127, "pack_rel_table: table length %d is not 27 (14x14 windows) or 127 (64x64 global)", L);
+    const int row_off = is_w ? (L == 127 ? 144 : 32) : 0;
+    pack_rel_kernel<<<(L * hd + 255) / 256, 256, 0, stream>>>(src, dst, L, hd, row_off);
+    count_launch();
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream) {
+    SVB_REQUIRE(ld % 8 == 0, "fill_pad_rows: row length must be a multiple of 8");
+    const long total = (long)B * (gp * gp - g * g) * (ld / 8);
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+    ProfScope prof(PC_OTHER, 0.0, (double)total * 16.0, stream);
+    fill_pad_rows_kernel<<<blocks, 256, 0, stream>>>(qkv, bias, B, g, gp, ld);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
+    SVB_REQUIRE(p.grid == 64, "attention_tc: the tcgen05 kernels implement the 64x64 token grid (img 1024 / patch 16), got %d", p.grid);
+    SVB_REQUIRE(p.ws == 14 || p.ws == 64, "attention_tc: window size %d is not 14 (windowed) or 64 (global)", p.ws);
+    SVB_REQUIRE(p.hd == 64 || p.hd == 80, "attention_tc: head_dim %d is not 64 or 80", p.hd);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(p.rel_pack) & 15) == 0, "attention_tc: pointers must be 16-byte aligned");
+    const double D_ = (double)p.heads * p.hd;
+    const int S = p.ws * p.ws, nwin = p.ws == 64 ? 1 : 25;
+    ProfScope prof(p.ws == p.grid ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
+                   (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
+                   (double)p.batch * p.grid * p.grid * 4.0 * D_ * 2, stream);
+    if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
+    return p.hd == 64 ? launch_window<64>(p, stream) : launch_window<80>(p, stream);
+}
+
+}  // namespace svb

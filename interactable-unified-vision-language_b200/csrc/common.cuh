@@ -42,7 +42,16 @@ struct Epilogue {
     int ldo = 0;
     double* stats = nullptr;         // [samples][2] (sum, sumsq) or null
     int rows_per_sample = 1;
+    // optional output-row remap (token grid g x g -> padded grid gp x gp, the window_partition padding of
+    // image_encoder.py:271-275 expressed as a store address): out row = (r / g^2) * gp^2 + ((r % g^2) / g) * gp + r % g
+    int remap_g = 0, remap_gp = 0;
 };
+__host__ __device__ __forceinline__ size_t epilogue_out_row(const Epilogue& ep, int row) {
+    if (ep.remap_g == 0) return (size_t)row;
+    const int t = ep.remap_g * ep.remap_g;
+    const int b = row / t, r = row % t;
+    return (size_t)b * ep.remap_gp * ep.remap_gp + (size_t)(r / ep.remap_g) * ep.remap_gp + (r % ep.remap_g);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -97,13 +106,18 @@ struct AttnParams {
 };
 // fp32-math SIMT attention with decomposed rel-pos; T = float (validation) or bf16.
 int attention_simt(const AttnParams& p, bool is_bf16, cudaStream_t stream);
-// tcgen05 attention kernels (bf16 in/out).  rel tables are bf16 copies prepared at load time.
+// tcgen05 attention kernels (bf16 in/out), attention_tc.cu.  `qkv` is the qkv GEMM output: token order [B*64*64, 3D] for
+// global attention (ws == grid), the PADDED window grid [B, 70, 70, 3D] (pad rows = qkv bias, see fill_pad_rows) for ws == 14.
+// `rel_pack` is the bf16 table block written by pack_rel_table: 64 rows (h at 0, w at 32) for windows, 272 rows (h at 0,
+// w at 144) for global attention, hd columns.
 struct AttnTcParams {
     const bf16* qkv; bf16* out;
-    const bf16* rel_hw;     // [2][L_pad][hd] bf16: h table then w table, rows padded
-    const float* qkv_bias;
+    const bf16* rel_pack;
     int batch, grid, ws, heads, hd;
 };
+int attention_tc_rel_rows(int ws, int grid);
+int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream);
+int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream);
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)

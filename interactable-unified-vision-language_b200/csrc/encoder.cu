@@ -22,7 +22,7 @@ void set_error(const char* fmt, ...) {
 
 namespace {
 
-enum ParamKind { P_VEC, P_GEMM_W, P_CONVT_W, P_CONVT_B, P_CONV22_W, P_IGNORED };
+enum ParamKind { P_VEC, P_GEMM_W, P_CONVT_W, P_CONVT_B, P_CONV22_W, P_REL_H, P_REL_W, P_IGNORED };
 
 struct Param {
     ParamKind kind = P_VEC;
@@ -56,6 +56,8 @@ struct svb_encoder {
     bool taps_enabled = false;
     float* taps = nullptr;          // [(depth+1)][T*D] fp32, first image of the last chunk
     int attn_impl_bf16 = 0;         // 0: SIMT kernel, 1: tcgen05 kernel
+    int grid_pad = 0;               // window-padded token grid (70 for 64 / 14)
+    std::vector<bf16*> relpack;     // per block: bf16 rel-pos table block of the tcgen05 attention kernel (attention_tc.cu)
     // host path resources
     struct HostPath {
         int chunk = 0, mode = -1, out_dtype = -1;
@@ -119,7 +121,8 @@ Buffers plan(const svb_encoder* e, int chunk, int mode, void* base) {
     const size_t mark = ar.off;
     b.A0 = ar.alloc(M * kpe * es);
     b.Xn = ar.alloc(M * D * es);
-    b.QKV = ar.alloc(M * 3 * D * es);
+    const size_t Mp = (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1) ? (size_t)chunk * e->grid_pad * e->grid_pad : M;
+    b.QKV = ar.alloc(Mp * 3 * D * es);
     b.O = ar.alloc(M * D * es);
     b.Hid = ar.alloc(M * e->mlp * es);
     const size_t trunk_end = ar.off;
@@ -173,21 +176,25 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         const std::string p = "blocks." + std::to_string(i) + ".";
         if ((rc = layernorm_rows(bf.X, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
             return rc;
+        const int ws = e->is_global(i) ? g : e->cfg.window_size;
+        const bool tc = h && e->attn_impl_bf16 == 1;
+        const bool padded = tc && ws != g;      // windowed blocks of the tcgen05 path keep qkv on the padded 70x70 grid
         {   // qkv (image_encoder.py:242)
             Epilogue ep;
             ep.bias = e->P(p + "attn.qkv.bias").f32;
             ep.out = bf.QKV;
             ep.out_bf16 = h;
             ep.ldo = 3 * D;
+            if (padded) { ep.remap_g = g; ep.remap_gp = e->grid_pad; }
             if ((rc = linear(mode, bf.Xn, D, e->P(p + "attn.qkv.weight"), M, 3 * D, D, ep, st))) return rc;
+            // pad tokens are zero after norm1 (image_encoder.py:183-187,271-275): their qkv rows are the bias
+            if (padded && (rc = fill_pad_rows((bf16*)bf.QKV, ep.bias, B, g, e->grid_pad, 3 * D, st))) return rc;
         }
         {   // windowed / global attention with decomposed rel-pos (image_encoder.py:246-253, 258-304, 340-376)
-            const int ws = e->is_global(i) ? g : e->cfg.window_size;
-            if (h && e->attn_impl_bf16 == 1) {
+            if (tc) {
                 AttnTcParams ap;
                 ap.qkv = (const bf16*)bf.QKV; ap.out = (bf16*)bf.O;
-                ap.rel_hw = e->P(p + "attn.rel_pos_h").b16;   // h and w tables packed back to back at load time
-                ap.qkv_bias = e->P(p + "attn.qkv.bias").f32;
+                ap.rel_pack = e->relpack[i];
                 ap.batch = B; ap.grid = g; ap.ws = ws; ap.heads = e->heads; ap.hd = e->hd;
                 if ((rc = attention_tc(ap, st))) return rc;
             } else {
@@ -321,8 +328,8 @@ int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
         const int L = 2 * (e->is_global(i) ? e->grid : cfg->window_size) - 1;
         add_param(e, b + "norm1.weight", P_VEC, D);
         add_param(e, b + "norm1.bias", P_VEC, D);
-        add_param(e, b + "attn.rel_pos_h", P_VEC, (int64_t)L * e->hd);
-        add_param(e, b + "attn.rel_pos_w", P_VEC, (int64_t)L * e->hd);
+        add_param(e, b + "attn.rel_pos_h", P_REL_H, (int64_t)L * e->hd, L, i);
+        add_param(e, b + "attn.rel_pos_w", P_REL_W, (int64_t)L * e->hd, L, i);
         add_param(e, b + "attn.qkv.weight", P_GEMM_W, (int64_t)3 * D * D, 3 * D, D);
         add_param(e, b + "attn.qkv.bias", P_VEC, 3 * D);
         add_param(e, b + "attn.proj.weight", P_GEMM_W, (int64_t)D * D, D, D);
@@ -375,8 +382,23 @@ int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
         int rc = alloc_param_storage(kv.second);
         if (rc) { svb_encoder_destroy(e); return rc; }
     }
+    // tcgen05 attention covers the geometry _build_sam instantiates (64x64 grid, 14x14 windows, head_dim 64 / 80);
+    // anything else runs the SIMT kernel.  SVB_ATTN_IMPL=0 forces the SIMT kernel (bisecting aid).
+    e->grid_pad = ((e->grid + cfg->window_size - 1) / cfg->window_size) * cfg->window_size;
+    e->attn_impl_bf16 = (e->grid == 64 && cfg->window_size == 14 && (e->hd == 64 || e->hd == 80)) ? 1 : 0;
     const char* env = getenv("SVB_ATTN_IMPL");
-    if (env) e->attn_impl_bf16 = atoi(env);
+    if (env && atoi(env) == 0) e->attn_impl_bf16 = 0;
+    if (e->attn_impl_bf16 == 1) {
+        e->relpack.assign(e->depth, nullptr);
+        for (int i = 0; i < e->depth; ++i) {
+            const size_t bytes = sizeof(bf16) * (size_t)attention_tc_rel_rows(e->is_global(i) ? e->grid : cfg->window_size, e->grid) * e->hd;
+            if (cudaMalloc(&e->relpack[i], bytes) != cudaSuccess || cudaMemset(e->relpack[i], 0, bytes) != cudaSuccess) {
+                set_error("svb_encoder_create: cannot allocate the rel-pos table block of block %d", i);
+                svb_encoder_destroy(e);
+                return 1;
+            }
+        }
+    }
     *out = e;
     return 0;
 }
@@ -388,6 +410,8 @@ void svb_encoder_destroy(svb_encoder_t* e) {
         if (kv.second.b16) cudaFree(kv.second.b16);
     }
     if (e->taps) cudaFree(e->taps);
+    for (bf16* r : e->relpack)
+        if (r) cudaFree(r);
     auto& hp = e->hp;
     for (int i = 0; i < 2; ++i) {
         if (hp.xin[i]) cudaFree(hp.xin[i]);
@@ -415,6 +439,11 @@ int svb_encoder_load_param(svb_encoder_t* e, const char* key, const float* data,
     switch (p.kind) {
         case P_VEC:
             SVB_CHECK_CUDA(cudaMemcpyAsync(p.f32, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
+            break;
+        case P_REL_H:
+        case P_REL_W:
+            SVB_CHECK_CUDA(cudaMemcpyAsync(p.f32, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
+            if (e->attn_impl_bf16 == 1) rc = pack_rel_table(data, e->relpack[p.b], p.a, e->hd, p.kind == P_REL_W, st);
             break;
         case P_GEMM_W:
             SVB_CHECK_CUDA(cudaMemcpyAsync(p.f32, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, st));
@@ -558,7 +587,7 @@ int svb_encoder_read_tap(svb_encoder_t* e, int block, float* dst, int64_t numel,
 
 int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats, int rows_per_sample,
-               svb_stream_t stream) {
+               int remap_grid, int remap_grid_pad, svb_stream_t stream) {
     SVB_REQUIRE(A && W && out, "svb_linear: null argument");
     Epilogue ep;
     ep.bias = bias;
@@ -566,6 +595,11 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
     ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
     ep.out = out; ep.out_bf16 = out_dtype == SVB_DTYPE_BF16; ep.ldo = ldo;
     ep.stats = gn_stats; ep.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+    if (remap_grid > 0) {
+        SVB_REQUIRE(remap_grid_pad >= remap_grid && M % (remap_grid * remap_grid) == 0,
+                    "svb_linear: row remap needs M to be a multiple of grid^2 and grid_pad >= grid");
+        ep.remap_g = remap_grid; ep.remap_gp = remap_grid_pad;
+    }
     if (mode == SVB_MODE_BF16) return gemm_bf16_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
     if (mode == SVB_MODE_FP32) return gemm_f32_simt((const float*)A, lda, (const float*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
     SVB_REQUIRE(false, "svb_linear: bad mode %d", mode);
@@ -589,6 +623,28 @@ int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* 
     SVB_REQUIRE(false, "svb_attention: impl %d is not available in this build", impl);
 }
 
+int svb_attention_tc(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
+                     svb_stream_t stream) {
+    SVB_REQUIRE(qkv && out && rel_pack, "svb_attention_tc: null argument");
+    AttnTcParams ap;
+    ap.qkv = (const bf16*)qkv; ap.out = (bf16*)out; ap.rel_pack = (const bf16*)rel_pack;
+    ap.batch = batch; ap.grid = grid; ap.ws = ws; ap.heads = heads; ap.hd = head_dim;
+    return attention_tc(ap, (cudaStream_t)stream);
+}
+
+int svb_rel_pack_rows(int ws, int grid) { return attention_tc_rel_rows(ws, grid); }
+
+int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int head_dim, int is_w, svb_stream_t stream) {
+    SVB_REQUIRE(table && rel_pack, "svb_pack_rel_table: null argument");
+    return pack_rel_table(table, (bf16*)rel_pack, table_len, head_dim, is_w != 0, (cudaStream_t)stream);
+}
+
+int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int grid, int grid_pad, int row_len, svb_stream_t stream) {
+    SVB_REQUIRE(qkv_padded && qkv_bias, "svb_fill_pad_rows: null argument");
+    SVB_REQUIRE(grid > 0 && grid_pad >= grid, "svb_fill_pad_rows: bad grid %d / padded grid %d", grid, grid_pad);
+    return fill_pad_rows((bf16*)qkv_padded, qkv_bias, batch, grid, grid_pad, row_len, (cudaStream_t)stream);
+}
+
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream) {
     SVB_REQUIRE(x && out, "svb_im2col: null argument");
     return im2col_patch(x, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, patch, (cudaStream_t)stream);
@@ -609,11 +665,3 @@ int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* g
 
 }  // extern "C"
 
-namespace svb {
-// tcgen05 attention is linked from attention_tc.cu when present; this weak default keeps the library loadable and
-// fails loudly if the tcgen05 path is selected without it.
-__attribute__((weak)) int attention_tc(const AttnTcParams&, cudaStream_t) {
-    set_error("attention_tc: the tcgen05 attention kernel is not part of this build");
-    return 3;
-}
-}  // namespace svb

@@ -17,8 +17,8 @@ __device__ __forceinline__ void store_out(const Epilogue& ep, int row, int col, 
         const int rr = ep.resid_mod ? (row % ep.resid_mod) : row;
         x += ep.resid[(size_t)rr * ep.ldr + col];
     }
-    if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[(size_t)row * ep.ldo + col] = __float2bfloat16_rn(x);
-    else reinterpret_cast<float*>(ep.out)[(size_t)row * ep.ldo + col] = x;
+    if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[epilogue_out_row(ep, row) * ep.ldo + col] = __float2bfloat16_rn(x);
+    else reinterpret_cast<float*>(ep.out)[epilogue_out_row(ep, row) * ep.ldo + col] = x;
 }
 
 __global__ void __launch_bounds__(256)

@@ -42,6 +42,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
     const bool full = (col0 + 32 <= N);
     if (!row_ok) return;
+    const size_t orow = epilogue_out_row(ep, row);
     if (full) {
         if (ep.bias) {
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
@@ -69,7 +70,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
             }
         }
         if (ep.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (size_t)row * ep.ldo + col0);
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 u;
@@ -80,7 +81,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
                 o[j] = u;
             }
         } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0);
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -94,8 +95,8 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
                 if (ep.stats) { s_sum += x; s_sq += x * x; }
                 if (ep.act == 1) x = gelu_erf(x);
                 if (ep.resid) x += ep.resid[(size_t)rr * ep.ldr + c];
-                if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[(size_t)row * ep.ldo + c] = __float2bfloat16_rn(x);
-                else reinterpret_cast<float*>(ep.out)[(size_t)row * ep.ldo + c] = x;
+                if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[orow * ep.ldo + c] = __float2bfloat16_rn(x);
+                else reinterpret_cast<float*>(ep.out)[orow * ep.ldo + c] = x;
             }
         }
     }

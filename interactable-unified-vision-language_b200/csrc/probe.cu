@@ -19,6 +19,7 @@ struct ProbeArgs {
     uint32_t b_lbo, b_sbo, b_kstep;
     uint32_t idesc;
     int a_manual;                   // 1: A written by threads (row-major [128][K] in global, K = 64*n) with manual SW128
+                                    // 2: A written by threads into TMEM columns [128, 128 + K/2) as packed bf16 pairs (the P path)
     const bf16* a_gl;
 };
 
@@ -42,7 +43,17 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *slot;
-    if (pa.a_manual) {
+    if (pa.a_manual == 2) {
+        // thread t owns row t = TMEM lane t: column 128 + j holds (A[t][2j], A[t][2j+1]) as one 32-bit word
+        const uint32_t* arow = reinterpret_cast<const uint32_t*>(pa.a_gl + (size_t)tid * pa.K);
+        for (int c0 = 0; c0 < pa.K / 2; c0 += 16) {
+            uint32_t w[16];
+            for (int j = 0; j < 16; ++j) w[j] = arow[c0 + j];
+            ptx::tmem_st_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 128 + c0, w);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+    } else if (pa.a_manual) {
         // thread t owns row t: K-major, 64-element (128 B) atoms along K, 16-byte chunk c of row r lands at chunk c ^ (r & 7)
         const int r = tid;
         for (int atom = 0; atom < pa.K / 64; ++atom)
@@ -54,6 +65,7 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     __syncthreads();
     if (tid == 0) {
+        ptx::tc_fence_after();
         ptx::mbar_expect_tx(&bar[0], (pa.a_manual ? 0 : pa.a_bytes) + pa.b_bytes);
         if (!pa.a_manual) {
             if (pa.a_sw == 128) for (int k0 = 0; k0 < pa.K; k0 += 64) ptx::tma_load_2d(sA + (k0 / 64) * 16384, &map_a, &bar[0], k0, 0);
@@ -68,7 +80,8 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const uint32_t a_off = pa.a_sw == 128 ? (k >> 2) * 16384 + (k & 3) * pa.a_kstep : k * pa.a_kstep;
             const uint64_t da = ptx::make_smem_desc(base + a_off, pa.a_lbo, pa.a_sbo, a_layout);
             const uint64_t db = ptx::make_smem_desc(base + 65536 + k * pa.b_kstep, pa.b_lbo, pa.b_sbo, b_layout);
-            ptx::mma_f16_ss(tmem, da, db, pa.idesc, k ? 1u : 0u);
+            if (pa.a_manual == 2) ptx::mma_f16_ts(tmem, tmem + 128 + 8 * k, db, pa.idesc, k ? 1u : 0u);
+            else ptx::mma_f16_ss(tmem, da, db, pa.idesc, k ? 1u : 0u);
         }
         ptx::mma_commit(&bar[1]);
     }

@@ -13,7 +13,7 @@ DEV = "cuda"
 
 
 def _linear(mode, A, W, bias=None, gelu=False, resid=None, resid_mod=0, out_dtype=torch.float32, stats=None, rps=0,
-            out=None):
+            out=None, remap=(0, 0)):
     M, K = A.shape
     N = W.shape[0]
     if out is None:
@@ -22,7 +22,7 @@ def _linear(mode, A, W, bias=None, gelu=False, resid=None, resid_mod=0, out_dtyp
         mode, A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, cabi.ptr(bias), int(gelu), cabi.ptr(resid),
         resid.stride(0) if resid is not None else 0, resid_mod, out.data_ptr(),
         cabi.DTYPE_BF16 if out.dtype == torch.bfloat16 else cabi.DTYPE_F32, out.stride(0), cabi.ptr(stats), rps,
-        cabi.stream_ptr())
+        remap[0], remap[1], cabi.stream_ptr())
     cabi.check(rc, "svb_linear")
     return out
 
@@ -210,3 +210,70 @@ def test_groupnorm_rows():
     var = xs.var(1, unbiased=False).reshape(B, 1, 1)
     ref = (x.double().reshape(B, rps, C) - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
     assert ib.rel_l2(out, ref.reshape(-1, C)) < 3e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tcgen05 attention (attention_tc.cu): operands in the encoder's own layouts
+def _attention_tc(qkv, rel_h, rel_w, bias, B, g, ws, heads, hd):
+    """qkv (B*g*g, 3D) bf16 token order on the device -> (B*g*g, D) bf16 through svb_attention_tc."""
+    lib = cabi.lib()
+    D = heads * hd
+    st = cabi.stream_ptr()
+    rows = lib.svb_rel_pack_rows(ws, g)
+    pack = torch.zeros(rows, hd, dtype=torch.bfloat16, device=DEV)
+    cabi.check(lib.svb_pack_rel_table(rel_h.data_ptr(), pack.data_ptr(), rel_h.shape[0], hd, 0, st), "pack h")
+    cabi.check(lib.svb_pack_rel_table(rel_w.data_ptr(), pack.data_ptr(), rel_w.shape[0], hd, 1, st), "pack w")
+    if ws != g:
+        gp = -(-g // ws) * ws
+        src = torch.full((B, gp, gp, 3 * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+        src[:, :g, :g] = qkv.reshape(B, g, g, 3 * D)
+        cabi.check(lib.svb_fill_pad_rows(src.data_ptr(), bias.data_ptr(), B, g, gp, 3 * D, st), "fill_pad_rows")
+    else:
+        src = qkv
+    out = torch.full((B * g * g, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    cabi.check(lib.svb_attention_tc(src.data_ptr(), out.data_ptr(), pack.data_ptr(), B, g, ws, heads, hd, st), "svb_attention_tc")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("ws,heads,hd,rel_std,B", [
+    (14, 2, 64, 0.02, 2), (14, 2, 80, 0.5, 2), (14, 3, 80, 0.1, 1),
+    (64, 2, 64, 0.5, 1), (64, 1, 80, 0.02, 2), (64, 2, 80, 0.5, 1)])
+def test_attention_tcgen05(ws, heads, hd, rel_std, B):
+    g = 64
+    D = heads * hd
+    gen = torch.Generator(device="cpu").manual_seed(ws * 100 + hd + heads)
+    qkv = torch.randn(B * g * g, 3 * D, generator=gen).bfloat16()
+    L = 2 * ws - 1
+    rel_h, rel_w = torch.randn(L, hd, generator=gen) * rel_std, torch.randn(L, hd, generator=gen) * rel_std
+    bias = torch.randn(3 * D, generator=gen)
+    # the kernel sees bf16 copies of the tables and of the pad rows (= bias)
+    ref = ref_attention_core(qkv.float(), rel_h.bfloat16().float(), rel_w.bfloat16().float(), bias.bfloat16().float(), B, g, ws, heads)
+    out = _attention_tc(qkv.to(DEV), rel_h.to(DEV), rel_w.to(DEV), bias.to(DEV), B, g, ws, heads, hd)
+    assert torch.isfinite(out.float()).all()
+    err = ib.rel_l2(out, ref)
+    assert err < 6e-3, err          # P and the output are rounded to bf16 (2^-9 relative)
+    # per-head error, so that a broken head / tail slice cannot hide in the average
+    o3, r3 = out.float().cpu().reshape(-1, heads, hd), ref.float().reshape(-1, heads, hd)
+    for hh in range(heads):
+        assert ib.rel_l2(o3[:, hh, :64], r3[:, hh, :64]) < 8e-3
+        if hd > 64:
+            assert ib.rel_l2(o3[:, hh, 64:], r3[:, hh, 64:]) < 8e-3
+
+
+def test_linear_remap_to_padded_grid():
+    """qkv GEMM epilogue storing token rows at their position in the window-padded 70x70 grid."""
+    g, gp, B, K, N = 64, 70, 2, 64, 256
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randn(B * g * g, K, generator=gen).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=gen) / 8).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=gen).to(DEV)
+    out = torch.zeros(B * gp * gp, N, dtype=torch.bfloat16, device=DEV)
+    _linear(cabi.MODE_BF16, A, W, bias=bias, out=out, remap=(g, gp))
+    cabi.check(cabi.lib().svb_fill_pad_rows(out.data_ptr(), bias.data_ptr(), B, g, gp, N, cabi.stream_ptr()), "fill")
+    torch.cuda.synchronize()
+    ref, _ = _ref_linear(A, W, bias=bias)
+    full = bias.double().reshape(1, 1, 1, N).expand(B, gp, gp, N).clone()
+    full[:, :g, :g] = ref.reshape(B, g, g, N)
+    assert ib.rel_l2(out.reshape(B, gp, gp, N), full) < 4e-3
+    assert torch.equal(out.reshape(B, gp, gp, N)[:, g:, :, :].float(), bias.bfloat16().float().expand(B, gp - g, gp, N))

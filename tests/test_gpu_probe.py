@@ -45,6 +45,8 @@ def test_descriptor_encodings():
         cands[f"lbo{lbo}_sbo{sbo}_k{kstep}"] = err(run(a2, bmn, 128, 64, 128, 128, 1, 0, 0, 1024, 32, lbo, sbo, kstep), ref2)
     report["mn_sw128_tma_a"] = cands
     report["mn_sw128_manual_a"] = err(run(a2, bmn, 128, 64, 128, 128, 1, 1, 0, 1024, 32, 0, 1024, 2048), ref2)
+    # 2b. A = P in TENSOR MEMORY (tcgen05.st of packed bf16 pairs, A operand taken from TMEM), K = 128, MN-major B
+    report["mn_sw128_tmem_a"] = err(run(a2, bmn, 128, 64, 128, 128, 1, 2, 0, 1024, 32, 0, 1024, 2048), ref2)
     # 3. 32B-swizzle tail, K-major both (Q K^T tail: K = 16)
     a3 = torch.randn(128, 16, generator=g).bfloat16().to(DEV)
     b3 = torch.randn(128, 16, generator=g).bfloat16().to(DEV)
@@ -60,6 +62,7 @@ def test_descriptor_encodings():
     for lbo, sbo, kstep in itertools.product((0, 256), (256, 128, 512), (512, 256)):
         c4[f"lbo{lbo}_sbo{sbo}_k{kstep}"] = err(run(a2, b4, 128, 16, 128, 32, 1, 1, 0, 1024, 32, lbo, sbo, kstep), ref4)
     report["mn_sw32"] = c4
+    report["mn_sw32_tmem_a"] = err(run(a2, b4, 128, 16, 128, 32, 1, 2, 0, 1024, 32, 0, 256, 512), ref4)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe_report.json"), "w") as f:
         json.dump(report, f, indent=1)
@@ -68,5 +71,7 @@ def test_descriptor_encodings():
     assert report["kmajor_sw128"] < 1e-5
     assert report["mn_sw128_tma_a"]["lbo0_sbo1024_k2048"] < 1e-5
     assert report["mn_sw128_manual_a"] < 1e-5
+    assert report["mn_sw128_tmem_a"] < 1e-5
+    assert report["mn_sw32_tmem_a"] < 1e-5
     assert report["kmajor_sw32"]["sbo256"] < 1e-5
     assert report["mn_sw32"]["lbo0_sbo256_k512"] < 1e-5
