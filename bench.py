@@ -49,7 +49,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -82,10 +82,11 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            sm_sorted = sorted(sm)
-            # median over the busy samples (top half by power) so idle samples around the region do not dilute it
-            out.update(sm_mhz=sm_sorted[len(sm_sorted) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons),
-                       samples=len(sm))
+            # the sampler runs from before the warm-up: keep the samples taken under load (power >= 60 % of the maximum seen)
+            busy = [c for c, w in zip(sm, pw) if w >= 0.6 * max(pw)] or sm
+            busy.sort()
+            out.update(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons),
+                       samples=len(sm), samples_under_load=len(busy))
         return out
 
 
@@ -199,14 +200,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- device-resident throughput (`value`) + live roofline ----------------
+    # ---------------- device-resident throughput (`value`): clean timed region, no per-launch events ----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # started before the warm-up: nvidia-smi needs time to spin up
     with torch.no_grad():
         for _ in range(args.warmup):
             out = enc(x_dev)
         barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         launches0 = lib.svb_launch_count()
-        lib.svb_profile_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -215,10 +215,20 @@ def main():
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
-        ms5, fl5, by5, ln5 = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
-        lib.svb_profile_stop(ms5, fl5, by5, ln5)
         launches = lib.svb_launch_count() - launches0
         clocks = sampler.stop() if sampler else None
+        # ---------------- live roofline: the same step again with CUDA events around every launch ----------------
+        prof_steps = max(1, min(args.steps, 2))
+        lib.svb_profile_start()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(prof_steps):
+            out = enc(x_dev)
+        p1.record()
+        torch.cuda.synchronize()
+        ms_prof_total = p0.elapsed_time(p1)
+        ms5, fl5, by5, ln5 = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int64 * 5)()
+        lib.svb_profile_stop(ms5, fl5, by5, ln5)
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -261,9 +271,10 @@ def main():
         "launches": int(n_gemm), "avg_launch_ms": (ms5[0] / n_gemm) if n_gemm else None,
         "flops_per_launch_avg": (fl5[0] / n_gemm) if n_gemm else None,
         "traffic": None,
-        "step_share": {name: ms5[i] / (ms_total if ms_total else 1) for i, name in
+        "profiled_steps": prof_steps, "profiled_ms_per_step": ms_prof_total / prof_steps,
+        "step_share": {name: ms5[i] / (ms_prof_total if ms_prof_total else 1) for i, name in
                        enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},
-        "categories": {name: {"ms_per_step": ms5[i] / args.steps, "launches_per_step": ln5[i] / args.steps,
+        "categories": {name: {"ms_per_step": ms5[i] / prof_steps, "launches_per_step": ln5[i] / prof_steps,
                               "tflops": (fl5[i] / (ms5[i] * 1e-3) / 1e12) if ms5[i] > 0 and fl5[i] > 0 else None,
                               "gbs": (by5[i] / (ms5[i] * 1e-3) / 1e9) if ms5[i] > 0 and by5[i] > 0 else None}
                        for i, name in enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},

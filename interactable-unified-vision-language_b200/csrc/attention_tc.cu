@@ -147,7 +147,7 @@ template <int HD, int NST_> struct GCfg {
 };
 
 template <int HD, int NST>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __maxnreg__(200)
 attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,

@@ -57,6 +57,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Exact-erf GELU for the bf16 path: erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the 2^-9 relative
+// rounding of the bf16 store that follows) with MUFU ex2 / rcp — about half the instructions of erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = p * t * exp2f(-z * z * 1.4426950408889634f);   // 1 - erf(z)
+    const float half_x = 0.5f * x;
+    // 0.5 x (1 + erf(x/sqrt2)): erf(|..|) = 1 - e; sign folded into the branch-free select
+    return x >= 0.f ? half_x * (2.0f - e) : half_x * e;
+}
+
 __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(bf16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_float(float v);

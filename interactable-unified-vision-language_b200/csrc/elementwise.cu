@@ -237,13 +237,64 @@ int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img
     return 0;
 }
 
+// D = 128 * NV exactly (768 / 1024 / 1280): no bounds tests, the row lives in NV float4 registers per lane, small blocks
+// (4 rows) at high occupancy so that enough bytes are in flight to cover the HBM latency (HBM-bound: 4 + sizeof(T) B/element).
+template <typename T, int NV>
+__global__ void __launch_bounds__(128, 8)
+layernorm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, T* __restrict__ out,
+                       int rows, float eps) {
+    constexpr int D = 128 * NV;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    T* orow = out + (size_t)row * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bia) + idx);
+        Vec4<T>::store(orow + 4 * idx, (v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                       (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    }
+}
+
+template <typename T>
+static bool launch_ln_fixed(const float* x, const float* w, const float* b, T* out, int rows, int D, float eps, cudaStream_t s) {
+    const int blocks = (rows + 3) / 4;
+    switch (D) {
+        case 768: layernorm_fixed_kernel<T, 6><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
+        case 1024: layernorm_fixed_kernel<T, 8><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
+        case 1280: layernorm_fixed_kernel<T, 10><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
+        default: return false;
+    }
+}
+
 int layernorm_rows(const float* x, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s) {
     SVB_REQUIRE(D % 4 == 0 && D <= LN_MAXV * 128, "layernorm_rows: D=%d unsupported (multiple of 4, <= %d)", D, LN_MAXV * 128);
     const int blocks = (rows + 7) / 8;
     ProfScope prof(PC_NORM, 0, (double)rows * D * (4 + (out_bf16 ? 2 : 4)), s);
-    if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, w, b, (bf16*)out, rows, D, eps);
-    else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, w, b, (float*)out, rows, D, eps);
+    const bool fixed = out_bf16 ? launch_ln_fixed<bf16>(x, w, b, (bf16*)out, rows, D, eps, s)
+                                : launch_ln_fixed<float>(x, w, b, (float*)out, rows, D, eps, s);
+    if (!fixed) {
+        if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, w, b, (bf16*)out, rows, D, eps);
+        else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, w, b, (float*)out, rows, D, eps);
+    }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

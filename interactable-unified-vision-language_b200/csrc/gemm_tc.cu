@@ -13,8 +13,10 @@
 //   warps 2..5 : epilogue      — tcgen05.ld 32x32b (one output row per thread), bias / GELU / residual /
 //                GroupNorm statistics in registers, 16-byte global stores
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace svb {
@@ -34,73 +36,6 @@ template <int BN> struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = 2 * BN;
 };
-
-__device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int col0, int M, int N, bool row_ok,
-                                               uint32_t (&raw)[32], float& s_sum, float& s_sq) {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-    const bool full = (col0 + 32 <= N);
-    if (!row_ok) return;
-    const size_t orow = epilogue_out_row(ep, row);
-    if (full) {
-        if (ep.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 b = __ldg(b4 + j);
-                v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-        }
-        if (ep.stats) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { s_sum += v[j]; s_sq += v[j] * v[j]; }
-        }
-        if (ep.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (ep.resid) {
-            const int rr = ep.resid_mod ? (row % ep.resid_mod) : row;
-            const float4* r4 = reinterpret_cast<const float4*>(ep.resid + (size_t)rr * ep.ldr + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 r = r4[j];
-                v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-        }
-        if (ep.out_bf16) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + orow * ep.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                o[j] = u;
-            }
-        } else {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow * ep.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-    } else {
-        const int rr = ep.resid ? (ep.resid_mod ? (row % ep.resid_mod) : row) : 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int c = col0 + j;
-            if (c < N) {
-                float x = v[j] + (ep.bias ? __ldg(ep.bias + c) : 0.f);
-                if (ep.stats) { s_sum += x; s_sq += x * x; }
-                if (ep.act == 1) x = gelu_erf(x);
-                if (ep.resid) x += ep.resid[(size_t)rr * ep.ldr + c];
-                if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[orow * ep.ldo + c] = __float2bfloat16_rn(x);
-                else reinterpret_cast<float*>(ep.out)[orow * ep.ldo + c] = x;
-            }
-        }
-    }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -332,6 +267,8 @@ static int launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, in
     return 0;
 }
 
+int gemm_bf16_tc_pair(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
+
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,
                  cudaStream_t stream) {
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16_tc: empty problem M=%d N=%d K=%d", M, N, K);
@@ -340,6 +277,9 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
                 "gemm_bf16_tc: operands must be 16-byte aligned");
     SVB_REQUIRE((ep.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm_bf16_tc: output must be 16-byte aligned");
     SVB_REQUIRE(!ep.stats || (ep.rows_per_sample % 32) == 0, "gemm_bf16_tc: rows_per_sample must be a multiple of 32");
+    // CTA-pair kernel (gemm_tc2.cu) by default; SVB_GEMM_IMPL=1 selects the single-CTA kernel below (A/B comparisons)
+    static const int impl = [] { const char* e = getenv("SVB_GEMM_IMPL"); return e ? atoi(e) : 2; }();
+    if (impl != 1) return gemm_bf16_tc_pair(A, lda, W, ldw, M, N, K, ep, stream);
     if (N <= 128) return launch_gemm<128>(A, lda, W, ldw, M, N, K, ep, stream);
     return launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);
 }
