@@ -25,6 +25,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace svb {
 int encode_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -147,7 +148,8 @@ template <int HD, int NST_> struct GCfg {
 };
 
 template <int HD, int NST>
-__global__ void __maxnreg__(200)
+// 10 warps are allocated as 12 (warp allocation granularity 4): the register cap is 65536 / 384 = 168 per thread
+__global__ void __launch_bounds__(320, 1)
 attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
@@ -441,10 +443,13 @@ template <int HD> struct WCfg {
     static constexpr int OFF_K = OFF_Q + Q_MAIN + Q_TAIL;
     static constexpr int OFF_V = OFF_K + K_MAIN + K_TAIL;
     static constexpr int OFF_R = OFF_V + K_MAIN + K_TAIL;
-    static constexpr int OFF_BAR = OFF_R + R_MAIN + R_TAIL;
+    // The per-warp staging blocks of the rel-pos prologue (4 warps x [32][32] fp32) reuse the rel-table area: the tables are
+    // dead once the bias MMA has committed, and no later TMA write lands there.  (Staging inside the V tile raced with the V
+    // load: generic-proxy accesses followed by an async-proxy write to the same bytes are not ordered by an mbarrier hand-off.)
+    static constexpr int STG_BYTES = 4 * 4096;
+    static constexpr int R_AREA = (R_MAIN + R_TAIL > STG_BYTES) ? (R_MAIN + R_TAIL) : STG_BYTES;
+    static constexpr int OFF_BAR = OFF_R + R_AREA;
     static constexpr int SMEM = OFF_BAR + 128 + 1024;
-    static constexpr int STG_BYTES = 4 * 4096;                               // 4 warps x [32][32] fp32, aliases the V tile
-    static_assert(STG_BYTES <= 196 * 128, "staging must not reach the zeroed V pad rows");
     static_assert(2 * (SMEM + 1024) <= 233472, "two CTAs per SM");
     static constexpr int QR_TX = 64 * 128 + (TAIL ? 64 * 32 : 0);            // + query rows * (128 + 32)
     static constexpr int KV_TX = 196 * 128 + (TAIL ? 196 * 32 : 0);
@@ -459,7 +464,7 @@ struct WinMaps {
 
 template <int HD>
 __global__ void __launch_bounds__(192, 2)
-attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out, int D, int g, float scale_log2) {
+attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out, int D, int g, float scale_log2, int dbg) {
     using C = WCfg<HD>;
     constexpr int WS = 14, NWS = 5;
     const int qt = blockIdx.x, head = blockIdx.y;
@@ -504,7 +509,6 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
             ptx::mbar_expect_tx(&bars[C::B_KFULL], C::KV_TX);
             ptx::tma_load_4d(sm + C::OFF_K, &maps.kv_main, &bars[C::B_KFULL], colk, x0, y0, b);
             if (HD > 64) ptx::tma_load_4d(sm + C::OFF_K + C::K_MAIN, &maps.kv_tail, &bars[C::B_KFULL], colk + 64, x0, y0, b);
-            ptx::mbar_wait(&bars[C::B_PFULL], 0);                  // the staging area inside the V tile is dead
             ptx::mbar_expect_tx(&bars[C::B_VFULL], C::KV_TX);
             ptx::tma_load_4d(sm + C::OFF_V, &maps.kv_main, &bars[C::B_VFULL], colv, x0, y0, b);
             if (HD > 64) ptx::tma_load_4d(sm + C::OFF_V + C::K_MAIN, &maps.kv_tail, &bars[C::B_VFULL], colv + 64, x0, y0, b);
@@ -538,7 +542,7 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
         const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
         const uint32_t s_tmem = tmem + lane_off + C::TM_S;
         const uint32_t o_tmem = tmem + lane_off + C::TM_O;
-        float* stg = reinterpret_cast<float*>(sm + C::OFF_V + warp * 4096);     // [32][32] fp32, private to this warp
+        float* stg = reinterpret_cast<float*>(sm + C::OFF_R + warp * 4096);     // [32][32] fp32, private to this warp
 
         // keys 196..207 of the PV contraction multiply P = 0: their V rows must be finite
         if (t < 96) *reinterpret_cast<uint4*>(sm + C::OFF_V + 196 * 128 + t * 16) = make_uint4(0, 0, 0, 0);
@@ -748,14 +752,16 @@ int launch_window(const AttnTcParams& p, cudaStream_t stream) {
         if ((rc = encode_tmap_nd_bf16(&wm.r_main, p.rel_pack, 2, rd, rs, rm, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.r_tail, p.rel_pack, 2, rd, rs, rt, 32))) return rc;
     }
+    const int smem = C::SMEM;
+    const int dbg = 0;
     static bool attr_set = false;
     if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     dim3 grid(2, p.heads, p.batch * 25);
-    attn_window_kernel<HD><<<grid, 192, C::SMEM, stream>>>(wm, p.out, D, p.grid, scale_log2);
+    attn_window_kernel<HD><<<grid, 192, smem, stream>>>(wm, p.out, D, p.grid, scale_log2, dbg);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -22,7 +22,8 @@ __device__ __forceinline__ void prefetch_resid(const Epilogue& ep, int row, int 
 }
 
 __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int col0, int M, int N, bool row_ok,
-                                               uint32_t (&raw)[32], float& s_sum, float& s_sq, const ResidChunk* pre = nullptr) {
+                                               uint32_t (&raw)[32], float& s_sum, float& s_sq, const ResidChunk* pre = nullptr,
+                                               uint32_t bias_smem = 0) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -34,7 +35,12 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
             const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float4 b = __ldg(b4 + j);
+                float4 b;
+                if (bias_smem) {   // this chunk's 32 bias values staged in shared memory by the epilogue warps (broadcast read)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_smem + 16 * j));
+                } else {
+                    b = __ldg(b4 + j);
+                }
                 v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
         }
@@ -44,7 +50,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
         }
         if (ep.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
         }
         if (ep.resid) {
             const int rr = ep.resid_mod ? (row % ep.resid_mod) : row;

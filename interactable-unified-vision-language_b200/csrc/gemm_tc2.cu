@@ -10,14 +10,19 @@
 //
 //   warp 0     : TMA producer (each CTA loads its own halves; completion bytes of BOTH CTAs land on the leader's barrier)
 //   warp 1     : MMA issuer (leader CTA only); tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
-//   warps 2..9 : epilogue — two warps per TMEM lane quadrant, each owning half of the tile's columns; tcgen05.ld 32x32b,
-//                bias / GELU / residual / GroupNorm statistics in registers, 16-byte global stores.
+//   warps 2..9 : epilogue — two warps per TMEM lane quadrant, each owning half of the tile's columns; tcgen05.ld 32x32b
+//                (one accumulator row per thread), bias / GELU / GroupNorm statistics in registers, then a per-warp
+//                32 x 32 transpose through swizzled shared memory so that every global access of the warp (residual
+//                loads, output stores) covers whole 128-byte lines of 4 (fp32) or 8 (bf16) rows instead of one 16-byte
+//                piece of 32 different rows (the row-per-thread pattern cost 32 LSU wavefronts per instruction and made
+//                the in-place fp32 residual epilogue of proj / lin2 the bottleneck: ncu tensor pipe 32 %).
 //   Two accumulator stages in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i + 1.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace svb {
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
@@ -36,8 +41,13 @@ template <int BN> struct Cfg2 {
     static constexpr int A_BYTES = BM_CTA * BK * 2;
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 6 : 8;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int STAGES = (BN == 256) ? 5 : 6;
+    static constexpr int BIAS_BYTES = 2 * BN * 4;                 // per accumulator stage: the tile's BN bias values
+    static constexpr int EPI_BYTES = EPI_WARPS * 4096;            // per epilogue warp: one 32 x 32 fp32 transpose tile
+    static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BIAS = OFF_BARS + 256;
+    static constexpr int OFF_EPI = OFF_BIAS + BIAS_BYTES + (1024 - (256 + BIAS_BYTES) % 1024) % 1024;
+    static constexpr int SMEM_BYTES = OFF_EPI + EPI_BYTES + 1024;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -56,7 +66,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // relaxed: only the TMEM reads must be ordered before this arrive, and tcgen05.wait::ld + fence::before_thread_sync did that;
+    // a release at cluster scope would drain the epilogue's global stores (MEMBAR.ALL.GPU + L1 invalidate) once per tile and warp
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of this CTA's tile into its own smem; the completion bytes are credited to the barrier at `bar_cluster_addr`
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
@@ -89,19 +101,20 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 }
 
 template <int BN, bool RESID>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
-                Epilogue ep) {
+                Epilogue ep, int dbg) {
     using C = Cfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* tiles = smem_raw + (base_u32 - ptx::smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::STAGES * C::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::OFF_BARS);
     uint64_t* full_bar = bars;                       // leader's copy is the one in use
     uint64_t* empty_bar = bars + C::STAGES;          // per CTA
     uint64_t* tmem_full = bars + 2 * C::STAGES;      // per CTA
     uint64_t* tmem_empty = bars + 2 * C::STAGES + 2; // leader's copy is the one in use
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* bias_s = reinterpret_cast<float*>(tiles + C::OFF_BIAS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -184,52 +197,137 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
         const int half = (warp - 2) >> 2;                     // column half of the tile
         constexpr int NCH = BN / 64;                          // 32-column chunks per warp
+        const int etid = threadIdx.x - 64;                    // 0..255 among the epilogue threads
+        const uint32_t tile_s = base_u32 + C::OFF_EPI + (warp - 2) * 4096;   // this warp's transpose tile (1024-aligned)
+        const bool out_bf16 = ep.out_bf16 != 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
             const int m0 = (t / num_n) * (2 * BM_CTA) + rank * BM_CTA;
-            const int n0 = (t % num_n) * BN + half * (BN / 2);
-            const int row = m0 + quad * 32 + lane;
+            const int nt0 = (t % num_n) * BN;
+            const int n0 = nt0 + half * (BN / 2);
+            const int r0 = m0 + quad * 32;                    // first row of this warp's 32-row slab
+            const int row = r0 + lane;
             const bool row_ok = row < M;
+            // ---- while the MMAs of this tile run: stage the tile's bias in smem, start the residual loads ----
+            float* bs = bias_s + as * BN;
+            if (ep.bias) {
+                for (int c = etid; c < BN; c += EPI_WARPS * 32) bs[c] = (nt0 + c < N) ? __ldg(ep.bias + nt0 + c) : 0.f;
+            }
+            // residual in the COALESCED mapping of the write-out: instruction i covers rows 4i..4i+3, lane -> (row 4i + lane/8,
+            // 16-byte piece lane%8); two chunks in flight
+            float4 q[2][8];
+            auto load_resid = [&](int c, float4 (&dst)[8]) {
+                const int col0 = n0 + c * 32;
+                if (col0 + 32 > N) return;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int gr = r0 + 4 * i + (lane >> 3);
+                    if (gr < M) {
+                        const int rr = ep.resid_mod ? (gr % ep.resid_mod) : gr;
+                        dst[i] = *reinterpret_cast<const float4*>(ep.resid + (size_t)rr * ep.ldr + col0 + (lane & 7) * 4);
+                    }
+                }
+            };
+            if constexpr (RESID) {
+                load_resid(0, q[0]);
+                if (NCH > 1) load_resid(1, q[1]);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // bias visible to all epilogue warps
+            const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
             ptx::mbar_wait(&tmem_full[as], aphase);
             ptx::tc_fence_after();
             float s_sum = 0.f, s_sq = 0.f;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * (BN / 2);
-            if constexpr (RESID) {
-                // residual stream (HBM latency) prefetched one chunk ahead; the accumulator load is short and waits in place
-                uint32_t ra[32];
-                ResidChunk qa, qb;
-                if (n0 < N) prefetch_resid(ep, row, n0, N, row_ok, qa);
+            // accumulator chunks: double-buffered TMEM loads, except in the residual variant where the registers go to the
+            // two residual chunks in flight (the TMEM load is short and waits in place)
+            uint32_t ra[32], rb[RESID ? 1 : 32];
+            if (!RESID && n0 < N) ptx::tmem_ld_x32(taddr, ra);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    if (n0 + c * 32 >= N) break;
-                    const bool more = (c + 1 < NCH) && (n0 + (c + 1) * 32 < N);
+            for (int c = 0; c < NCH; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= N) break;
+                const bool more = (c + 1 < NCH) && (col0 + 32 < N);
+                uint32_t (&raw)[32] = *reinterpret_cast<uint32_t (*)[32]>((!RESID && (c & 1)) ? rb : ra);
+                if constexpr (RESID) {
                     ptx::tmem_ld_x32(taddr + c * 32, ra);
-                    if (c & 1) {
-                        if (more) prefetch_resid(ep, row, n0 + (c + 1) * 32, N, row_ok, qa);
-                        ptx::tmem_ld_wait_dep(ra);
-                        epilogue_chunk(ep, row, n0 + c * 32, M, N, row_ok, ra, s_sum, s_sq, &qb);
-                    } else {
-                        if (more) prefetch_resid(ep, row, n0 + (c + 1) * 32, N, row_ok, qb);
-                        ptx::tmem_ld_wait_dep(ra);
-                        epilogue_chunk(ep, row, n0 + c * 32, M, N, row_ok, ra, s_sum, s_sq, &qa);
+                    ptx::tmem_ld_wait_dep(ra);
+                } else {
+                    ptx::tmem_ld_wait_dep(raw);
+                    if (more) ptx::tmem_ld_x32(taddr + (c + 1) * 32, *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? ra : rb));
+                }
+                if (col0 + 32 > N) {                          // ragged last chunk: element-wise path
+                    epilogue_chunk(ep, row, col0, M, N, row_ok, raw, s_sum, s_sq);
+                    continue;
+                }
+                // ---- row-per-thread math: + bias, statistics, GELU ----
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                if (ep.bias) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bsm + c * 128 + 16 * j));
+                        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                     }
                 }
-            } else {
-                uint32_t ra[32], rb[32];
-                if (n0 < N) ptx::tmem_ld_x32(taddr, ra);
+                if (ep.stats && row_ok) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    if (n0 + c * 32 >= N) break;
-                    const bool more = (c + 1 < NCH) && (n0 + (c + 1) * 32 < N);
-                    if (c & 1) {
-                        ptx::tmem_ld_wait_dep(rb);
-                        if (more) ptx::tmem_ld_x32(taddr + (c + 1) * 32, ra);
-                        epilogue_chunk(ep, row, n0 + c * 32, M, N, row_ok, rb, s_sum, s_sq);
-                    } else {
-                        ptx::tmem_ld_wait_dep(ra);
-                        if (more) ptx::tmem_ld_x32(taddr + (c + 1) * 32, rb);
-                        epilogue_chunk(ep, row, n0 + c * 32, M, N, row_ok, ra, s_sum, s_sq);
+                    for (int j = 0; j < 32; ++j) { s_sum += v[j]; s_sq += v[j] * v[j]; }
+                }
+                if (ep.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
+                }
+                if (out_bf16) {
+                    // ---- transpose tile [32 rows][64 B]: piece j of row r at physical piece j ^ ((r >> 1) & 3) ----
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t a = tile_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * j + 0], v[8 * j + 1])),
+                                     "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                                     "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {             // instruction i: rows 8i..8i+7, 4 lanes (64 B) per row
+                        const int rr = 8 * i + (lane >> 2), pc = lane & 3;
+                        uint4 u;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                     : "r"(tile_s + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4)));
+                        const int gr = r0 + rr;
+                        if (gr < M)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + epilogue_out_row(ep, gr) * ep.ldo + col0 + pc * 8) = u;
+                    }
+                    __syncwarp();
+                } else {
+                    // ---- transpose tile [32 rows][128 B]: piece j of row r at physical piece j ^ (r & 7) ----
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t a = tile_s + lane * 128 + ((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j + 0]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                                     "f"(v[4 * j + 3]) : "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {             // instruction i: rows 4i..4i+3, 8 lanes (128 B) per row
+                        const int rr = 4 * i + (lane >> 3), pc = lane & 7;
+                        float4 x;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                                     : "r"(tile_s + rr * 128 + ((pc ^ (rr & 7)) << 4)));
+                        const int gr = r0 + rr;
+                        if (gr < M) {
+                            if constexpr (RESID) {
+                                const float4 r = q[c & 1][i];
+                                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                            }
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + epilogue_out_row(ep, gr) * ep.ldo + col0 + pc * 4) = x;
+                        }
+                    }
+                    __syncwarp();
+                    if constexpr (RESID) {
+                        if (c + 2 < NCH) load_resid(c + 2, q[c & 1]);
                     }
                 }
             }
@@ -239,8 +337,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (ep.stats) {
                 s_sum = warp_sum(s_sum);
                 s_sq = warp_sum(s_sq);
-                if (lane == 0 && (m0 + quad * 32) < M && n0 < N) {
-                    const int sample = (m0 + quad * 32) / ep.rows_per_sample;
+                if (lane == 0 && r0 < M && n0 < N) {
+                    const int sample = r0 / ep.rows_per_sample;
                     atomicAdd(ep.stats + 2 * sample, (double)s_sum);
                     atomicAdd(ep.stats + 2 * sample + 1, (double)s_sq);
                 }
@@ -274,8 +372,9 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     const int tiles = ((M + 2 * BM_CTA - 1) / (2 * BM_CTA)) * ((N + BN - 1) / BN);
     const int pairs = std::min(tiles, num_sms() / 2);
     ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (ep.out_bf16 ? 2.0 : 4.0) * M * N, stream);
-    if (ep.resid) gemm_tc2_kernel<BN, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep);
-    else gemm_tc2_kernel<BN, false><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep);
+    static const int dbg = [] { const char* e = getenv("SVB_GEMM2_DBG"); return e ? atoi(e) : 0; }();   // bisecting aid: 1 no L2 prefetch, 2 no smem bias, 4 no early residual loads
+    if (ep.resid) gemm_tc2_kernel<BN, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep, dbg);
+    else gemm_tc2_kernel<BN, false><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep, dbg);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -70,7 +70,9 @@ def test_gemm_tcgen05_epilogues(out_dtype):
     # bias + GELU
     out = _linear(cabi.MODE_BF16, A, W, bias=bias, gelu=True, out_dtype=out_dtype)
     ref, _ = _ref_linear(A, W, bias, gelu=True)
-    assert ib.rel_l2(out, ref) < tol
+    # the bf16 path evaluates erf by Abramowitz-Stegun 7.1.25 (|erf error| <= 2.5e-5): visible only in an fp32 store
+    assert ib.rel_l2(out, ref) < (5e-5 if out_dtype == torch.float32 else tol)
+    assert (out.double() - ref).abs().max() < (1e-4 if out_dtype == torch.float32 else 0.05)
     # bias + broadcast residual (pos_embed style) and in-place residual, fp32 stream
     if out_dtype == torch.float32:
         pos = torch.randn(4096, N, generator=g).to(DEV)
@@ -277,3 +279,21 @@ def test_linear_remap_to_padded_grid():
     full[:, :g, :g] = ref.reshape(B, g, g, N)
     assert ib.rel_l2(out.reshape(B, gp, gp, N), full) < 4e-3
     assert torch.equal(out.reshape(B, gp, gp, N)[:, g:, :, :].float(), bias.bfloat16().float().expand(B, gp - g, gp, N))
+
+
+@pytest.mark.parametrize("ws,heads,hd,B", [(14, 16, 80, 4), (14, 12, 64, 4), (64, 4, 80, 2)])
+def test_attention_tcgen05_is_deterministic(ws, heads, hd, B):
+    """Multi-wave grids (CTAs reusing an SM's shared / tensor memory, two windowed CTAs per SM) must give bit-identical
+    results run after run: guards the cross-proxy (generic vs TMA) shared-memory reuse rules of attention_tc.cu."""
+    g = 64
+    D = heads * hd
+    gen = torch.Generator(device="cpu").manual_seed(ws + hd + B)
+    qkv = torch.randn(B * g * g, 3 * D, generator=gen).bfloat16().to(DEV)
+    L = 2 * ws - 1
+    rel_h, rel_w = (torch.randn(L, hd, generator=gen) * 0.1).to(DEV), (torch.randn(L, hd, generator=gen) * 0.1).to(DEV)
+    bias = torch.randn(3 * D, generator=gen).to(DEV)
+    first = _attention_tc(qkv, rel_h, rel_w, bias, B, g, ws, heads, hd)
+    assert torch.isfinite(first.float()).all()
+    for _ in range(12):
+        again = _attention_tc(qkv, rel_h, rel_w, bias, B, g, ws, heads, hd)
+        assert torch.equal(again, first)
