@@ -85,8 +85,10 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
                int rows_per_sample, int remap_grid, int remap_grid_pad, svb_stream_t stream);
 /* remap_grid > 0: output row r (token order, grid x grid per image) is stored at the token's row of the window-padded
  * grid_pad x grid_pad layout — window_partition's F.pad (image_encoder.py:271-275) expressed as a store address. */
-/* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype. */
-int svb_layernorm(const float* x, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim,
+/* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype.  With `add` (rows x dim, element
+ * type = out_dtype) the residual add of Block.forward (image_encoder.py:194) is fused in: x += add is written back, then
+ * out = LayerNorm(x). */
+int svb_layernorm(float* x, const void* add, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim,
                   float eps, svb_stream_t stream);
 /* Block attention core (image_encoder.py:239-255 + 258-304 + 340-376): qkv [B*g*g, 3*D] token order ->
  * out [B*g*g, D]; ws == g selects global attention, otherwise ws x ws windows with bias-valued pad keys.

@@ -44,7 +44,7 @@ SYMBOLS = {
     "svb_rel_pack_rows": (_i, [_i, _i]),
     "svb_pack_rel_table": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_fill_pad_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "svb_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "svb_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "svb_attention": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _f, _i, _vp]),

@@ -185,7 +185,8 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)
 int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s);
-int layernorm_rows(const float* x, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
+// out = LayerNorm(x [+ add]); when `add` (same element type as out) is given, x += add is written back first (fused residual)
+int layernorm_rows(float* x, const void* add, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s);
 int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s);
 int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,

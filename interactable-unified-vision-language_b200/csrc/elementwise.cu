@@ -11,6 +11,7 @@ template <> struct Vec4<float> {
     static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
         *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
     }
+    static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
 };
 template <> struct Vec4<bf16> {
     static __device__ __forceinline__ void store(bf16* p, float a, float b, float c, float d) {
@@ -18,6 +19,12 @@ template <> struct Vec4<bf16> {
         u.x = pack_bf16x2(a, b);
         u.y = pack_bf16x2(c, d);
         *reinterpret_cast<uint2*>(p) = u;
+    }
+    static __device__ __forceinline__ float4 load(const bf16* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+        return make_float4(a.x, a.y, b.x, b.y);
     }
 };
 
@@ -48,13 +55,13 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, 
 constexpr int LN_MAXV = 16;   // float4 per lane -> D <= 2048
 template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, T* __restrict__ out,
-                 int rows, int D, float eps) {
+layernorm_kernel(float* __restrict__ x, const T* __restrict__ add, const float* __restrict__ w, const float* __restrict__ bia,
+                 T* __restrict__ out, int rows, int D, float eps) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const int n4 = D >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * D);
+    float4* xr = reinterpret_cast<float4*>(x + (size_t)warp * D);
     float4 v[LN_MAXV];
     float sum = 0.f;
 #pragma unroll
@@ -62,6 +69,11 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
         const int idx = lane + 32 * i;
         if (idx < n4) {
             v[i] = xr[idx];
+            if (add) {      // fused residual add (x += add) ahead of the norm: the sum goes back to the fp32 stream
+                const float4 a = Vec4<T>::load(add + (size_t)warp * D + 4 * idx);
+                v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+                xr[idx] = v[i];
+            }
             sum += v[i].x + v[i].y + v[i].z + v[i].w;
         }
     }
@@ -241,16 +253,26 @@ int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img
 // (4 rows) at high occupancy so that enough bytes are in flight to cover the HBM latency (HBM-bound: 4 + sizeof(T) B/element).
 template <typename T, int NV>
 __global__ void __launch_bounds__(128, 8)
-layernorm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bia, T* __restrict__ out,
-                       int rows, float eps) {
+layernorm_fixed_kernel(float* __restrict__ x, const T* __restrict__ add, const float* __restrict__ w, const float* __restrict__ bia,
+                       T* __restrict__ out, int rows, float eps) {
     constexpr int D = 128 * NV;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4* xr = reinterpret_cast<float4*>(x + (size_t)row * D);
     float4 v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    if (add) {              // fused residual add (x += add) ahead of the norm: the sum goes back to the fp32 stream
+        float4 a[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) a[i] = Vec4<T>::load(add + (size_t)row * D + 4 * (lane + 32 * i));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x += a[i].x; v[i].y += a[i].y; v[i].z += a[i].z; v[i].w += a[i].w;
+            xr[lane + 32 * i] = v[i];
+        }
+    }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -274,26 +296,27 @@ layernorm_fixed_kernel(const float* __restrict__ x, const float* __restrict__ w,
 }
 
 template <typename T>
-static bool launch_ln_fixed(const float* x, const float* w, const float* b, T* out, int rows, int D, float eps, cudaStream_t s) {
+static bool launch_ln_fixed(float* x, const T* add, const float* w, const float* b, T* out, int rows, int D, float eps, cudaStream_t s) {
     const int blocks = (rows + 3) / 4;
     switch (D) {
-        case 768: layernorm_fixed_kernel<T, 6><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
-        case 1024: layernorm_fixed_kernel<T, 8><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
-        case 1280: layernorm_fixed_kernel<T, 10><<<blocks, 128, 0, s>>>(x, w, b, out, rows, eps); return true;
+        case 768: layernorm_fixed_kernel<T, 6><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
+        case 1024: layernorm_fixed_kernel<T, 8><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
+        case 1280: layernorm_fixed_kernel<T, 10><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
         default: return false;
     }
 }
 
-int layernorm_rows(const float* x, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
+int layernorm_rows(float* x, const void* add, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s) {
     SVB_REQUIRE(D % 4 == 0 && D <= LN_MAXV * 128, "layernorm_rows: D=%d unsupported (multiple of 4, <= %d)", D, LN_MAXV * 128);
     const int blocks = (rows + 7) / 8;
-    ProfScope prof(PC_NORM, 0, (double)rows * D * (4 + (out_bf16 ? 2 : 4)), s);
-    const bool fixed = out_bf16 ? launch_ln_fixed<bf16>(x, w, b, (bf16*)out, rows, D, eps, s)
-                                : launch_ln_fixed<float>(x, w, b, (float*)out, rows, D, eps, s);
+    const int es = out_bf16 ? 2 : 4;
+    ProfScope prof(PC_NORM, 0, (double)rows * D * (4 + es + (add ? 4 + es : 0)), s);
+    const bool fixed = out_bf16 ? launch_ln_fixed<bf16>(x, (const bf16*)add, w, b, (bf16*)out, rows, D, eps, s)
+                                : launch_ln_fixed<float>(x, (const float*)add, w, b, (float*)out, rows, D, eps, s);
     if (!fixed) {
-        if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, w, b, (bf16*)out, rows, D, eps);
-        else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, w, b, (float*)out, rows, D, eps);
+        if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, (const bf16*)add, w, b, (bf16*)out, rows, D, eps);
+        else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, (const float*)add, w, b, (float*)out, rows, D, eps);
     }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -174,7 +174,7 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     // ---- Blocks (image_encoder.py:181-197) ----
     for (int i = 0; i < e->depth; ++i) {
         const std::string p = "blocks." + std::to_string(i) + ".";
-        if ((rc = layernorm_rows(bf.X, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
+        if ((rc = layernorm_rows(bf.X, nullptr, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
             return rc;
         const int ws = e->is_global(i) ? g : e->cfg.window_size;
         const bool tc = h && e->attn_impl_bf16 == 1;
@@ -207,21 +207,23 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
                 if ((rc = attention_simt(ap, h, st))) return rc;
             }
         }
-        {   // proj + shortcut (image_encoder.py:253,194), in place on the fp32 residual stream
+        {   // proj (image_encoder.py:253).  Its output stays in the activation dtype; the shortcut add x = shortcut + x
+            // (:194) is fused into the norm2 kernel below, which is HBM-bound anyway — the fp32 read-modify-write of the
+            // residual stream in this short-K GEMM's epilogue was slower than its MMAs.
             Epilogue ep;
             ep.bias = e->P(p + "attn.proj.bias").f32;
-            ep.resid = bf.X; ep.ldr = D;
-            ep.out = bf.X; ep.ldo = D;
+            ep.out = bf.Xn; ep.out_bf16 = h; ep.ldo = D;
             if ((rc = linear(mode, bf.O, D, e->P(p + "attn.proj.weight"), M, D, D, ep, st))) return rc;
         }
-        if ((rc = layernorm_rows(bf.X, e->P(p + "norm2.weight").f32, e->P(p + "norm2.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
+        // x += proj(attn);  Xn = norm2(x)   (image_encoder.py:194-195).  O is free again and receives the normalised rows.
+        if ((rc = layernorm_rows(bf.X, bf.Xn, e->P(p + "norm2.weight").f32, e->P(p + "norm2.bias").f32, bf.O, h, M, D, e->cfg.ln_eps, st)))
             return rc;
         {   // MLPBlock lin1 + GELU (common.py:25-26)
             Epilogue ep;
             ep.bias = e->P(p + "mlp.lin1.bias").f32;
             ep.act = 1;
             ep.out = bf.Hid; ep.out_bf16 = h; ep.ldo = e->mlp;
-            if ((rc = linear(mode, bf.Xn, D, e->P(p + "mlp.lin1.weight"), M, e->mlp, D, ep, st))) return rc;
+            if ((rc = linear(mode, bf.O, D, e->P(p + "mlp.lin1.weight"), M, e->mlp, D, ep, st))) return rc;
         }
         {   // lin2 + residual (image_encoder.py:195)
             Epilogue ep;
@@ -605,10 +607,10 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
     SVB_REQUIRE(false, "svb_linear: bad mode %d", mode);
 }
 
-int svb_layernorm(const float* x, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim, float eps,
+int svb_layernorm(float* x, const void* add, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim, float eps,
                   svb_stream_t stream) {
     SVB_REQUIRE(x && weight && bias && out, "svb_layernorm: null argument");
-    return layernorm_rows(x, weight, bias, out, out_dtype == SVB_DTYPE_BF16, rows, dim, eps, (cudaStream_t)stream);
+    return layernorm_rows(x, add, weight, bias, out, out_dtype == SVB_DTYPE_BF16, rows, dim, eps, (cudaStream_t)stream);
 }
 
 int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w, const float* qkv_bias,

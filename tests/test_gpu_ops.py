@@ -116,10 +116,20 @@ def test_layernorm(D, out_dtype):
     x = torch.randn(rows, D, device=DEV) * 3 + 0.5
     w, b = torch.randn(D, device=DEV), torch.randn(D, device=DEV)
     out = torch.empty(rows, D, dtype=out_dtype, device=DEV)
-    cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+    cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), None, w.data_ptr(), b.data_ptr(), out.data_ptr(),
                                         cabi.DTYPE_BF16 if out_dtype == torch.bfloat16 else cabi.DTYPE_F32, rows, D, 1e-6,
                                         cabi.stream_ptr()))
     ref = torch.nn.functional.layer_norm(x.double(), (D,), w.double(), b.double(), 1e-6)
+    assert ib.rel_l2(out, ref) < (2e-6 if out_dtype == torch.float32 else 3e-3)
+    # fused shortcut add (image_encoder.py:194): x += add is written back to the fp32 stream, out = LN(x)
+    add = (torch.randn(rows, D, device=DEV) * 2).to(out_dtype)
+    x0 = x.clone()
+    cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), add.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                        cabi.DTYPE_BF16 if out_dtype == torch.bfloat16 else cabi.DTYPE_F32, rows, D, 1e-6,
+                                        cabi.stream_ptr()))
+    xs = x0.double() + add.double()
+    assert ib.rel_l2(x, xs) < 1e-7
+    ref = torch.nn.functional.layer_norm(xs, (D,), w.double(), b.double(), 1e-6)
     assert ib.rel_l2(out, ref) < (2e-6 if out_dtype == torch.float32 else 3e-3)
 
 
