@@ -63,14 +63,19 @@ __device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint3
     }
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3: two comparisons per issue slot
+    return d;
+}
 __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
     float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < 32; e += 4) {
-        m0 = fmaxf(m0, __uint_as_float(v[e]));
-        m1 = fmaxf(m1, __uint_as_float(v[e + 1]));
-        m2 = fmaxf(m2, __uint_as_float(v[e + 2]));
-        m3 = fmaxf(m3, __uint_as_float(v[e + 3]));
+    for (int e = 0; e < 32; e += 8) {
+        m0 = fmax3(m0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        m1 = fmax3(m1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        m2 = fmax3(m2, __uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+        m3 = fmax3(m3, __uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
     }
     return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
@@ -330,7 +335,9 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[C::B_PFULL + i]);                   // phase 0: S_i / O_i columns may be overwritten
 
-        float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        float m_ref = -INFINITY;
+        f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
+        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
 #pragma unroll 1
         for (int j = 0; j < NKT; ++j) {
             ptx::mbar_wait(&bars[C::B_SFULL + i], j & 1);
@@ -377,23 +384,31 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                         for (int e = 0; e < 16; ++e) r2[e] = __float_as_uint(__uint_as_float(r2[e]) * alpha);
                         ptx::tmem_st_x16(o_tmem + 64, r2);
                     }
-                    l0 *= alpha; l1 *= alpha; l2 *= alpha; l3 *= alpha;
+                    const f32x2 al2 = f2_pack(alpha, alpha);
+                    l01 = f2_mul(l01, al2);
+                    l23 = f2_mul(l23, al2);
                 }
                 m_ref = m_new;
             }
-            const float d0 = bh0 - m_ref, d1 = bh1 - m_ref;
+            const f32x2 d0_2 = f2_pack(bh0 - m_ref, bh0 - m_ref), d1_2 = f2_pack(bh1 - m_ref, bh1 - m_ref);
             // ---- pass B: P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
 #define SVB_PASS_B(V, CHUNK)                                                                             \
             {                                                                                            \
                 uint32_t pk[16];                                                                         \
-                const float dd = ((CHUNK) < 2) ? d0 : d1;                                                \
+                const f32x2 dd2 = ((CHUNK) < 2) ? d0_2 : d1_2;                                           \
                 _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
                     const int kw = 32 * ((CHUNK) & 1) + e;                                               \
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(V[e]), scale_log2, bwl[kw]) + dd);         \
-                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 1]), scale_log2, bwl[kw + 1]) + dd); \
-                    const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 2]), scale_log2, bwl[kw + 2]) + dd); \
-                    const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 3]), scale_log2, bwl[kw + 3]) + dd); \
-                    l0 += p0; l1 += p1; l2 += p2; l3 += p3;                                              \
+                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,         \
+                                                    f2_pack(bwl[kw], bwl[kw + 1])), dd2);                \
+                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e + 2]), __uint_as_float(V[e + 3])), sc2,     \
+                                                    f2_pack(bwl[kw + 2], bwl[kw + 3])), dd2);            \
+                    float a0, a1, a2, a3;                                                                \
+                    f2_unpack(x01, a0, a1);                                                              \
+                    f2_unpack(x23, a2, a3);                                                              \
+                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
+                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);                      \
+                    l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
+                    l23 = f2_add(l23, f2_pack(p2, p3));                                                  \
                     pk[e / 2] = pack_bf16x2(p0, p1);                                                     \
                     pk[e / 2 + 1] = pack_bf16x2(p2, p3);                                                 \
                 }                                                                                        \
@@ -418,6 +433,9 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
         // ---- epilogue: O / l at the query's own token position ----
         ptx::mbar_wait(&bars[C::B_PVDONE + i], (NKT - 1) & 1);
         ptx::tc_fence_after();
+        float l0, l1, l2, l3;
+        f2_unpack(l01, l0, l1);
+        f2_unpack(l23, l2, l3);
         const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
         bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD;
         store_row<HD>(dst, o_tmem, inv);
@@ -599,15 +617,19 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
 #pragma unroll
         for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
         // ---- pass B ----
-        float l0 = 0.f, l1 = 0.f;
+        f32x2 l01 = f2_pack(0.f, 0.f);
+        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
 #define SVB_WIN_B(V, CHUNK)                                                                              \
         {                                                                                                \
             uint32_t pk[16];                                                                             \
             _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                          \
                 const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                            \
-                const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(V[e]), scale_log2, bwl[k0 % 14]) + bhm[k0 / 14]);     \
-                const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(V[e + 1]), scale_log2, bwl[k1 % 14]) + bhm[k1 / 14]); \
-                l0 += p0; l1 += p1;                                                                      \
+                const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,               \
+                                              f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
+                float a0, a1;                                                                            \
+                f2_unpack(x, a0, a1);                                                                    \
+                const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                          \
+                l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
                 pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
             }                                                                                            \
             ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
@@ -638,7 +660,7 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
             const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14]);
             const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14]);
             const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14]);
-            l0 += p0 + p2; l1 += p1 + p3;
+            l01 = f2_add(l01, f2_pack(p0 + p2, p1 + p3));
             pk[0] = pack_bf16x2(p0, p1);
             pk[1] = pack_bf16x2(p2, p3);
 #pragma unroll
@@ -651,6 +673,8 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
         // ---- epilogue ----
         ptx::mbar_wait(&bars[C::B_PVDONE], 0);
         ptx::tc_fence_after();
+        float l0, l1;
+        f2_unpack(l01, l0, l1);
         const float inv = 1.0f / (l0 + l1);
         bf16* dst = valid ? out + ((size_t)b * g * g + (size_t)y * g + x) * D + head * HD : nullptr;
         store_row<HD>(dst, o_tmem, inv);
