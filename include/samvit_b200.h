@@ -104,7 +104,13 @@ int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* 
  * Implemented geometry: grid 64, ws 14 or 64, head_dim 64 or 80 (everything build_sam.py:14-44 instantiates). */
 int svb_attention_tc(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
                      svb_stream_t stream);
+/* Same call with per-phase cycle counters of the softmax warp groups (debug aid; `phase_clocks` = 16 device int64, or NULL). */
+int svb_attention_tc_phases(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads,
+                            int head_dim, long long* phase_clocks, svb_stream_t stream);
 int svb_rel_pack_rows(int ws, int grid);
+/* Debug aid: a host-mapped (zero-copy) buffer of 64 uint64 that receives {block, thread, barrier address, parity} records when
+ * an mbarrier wait of the attention kernels times out (the kernel then traps). */
+int svb_attention_debug_buffer(void* mapped_device_ptr);
 int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int head_dim, int is_w, svb_stream_t stream);
 int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int grid, int grid_pad, int row_len,
                       svb_stream_t stream);

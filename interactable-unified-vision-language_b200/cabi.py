@@ -41,7 +41,9 @@ SYMBOLS = {
     "svb_encoder_read_tap": (_i, [_vp, _i, _vp, _i64, _vp]),
     "svb_linear": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp]),
     "svb_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_attention_tc_phases": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "svb_rel_pack_rows": (_i, [_i, _i]),
+    "svb_attention_debug_buffer": (_i, [_vp]),
     "svb_pack_rel_table": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_fill_pad_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "svb_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

@@ -449,6 +449,90 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
     }
 }
 
+// One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
+// the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
+// the reference maximum).  Two passes over TMEM: raw maximum (an upper bound of the row maximum follows from it), then
+// exp2 / sum / pack with packed fp32x2 arithmetic.
+__device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
+    float bmax = bhm[0], wmax = bwl[0];
+#pragma unroll
+    for (int k = 1; k < 14; ++k) { bmax = fmaxf(bmax, bhm[k]); wmax = fmaxf(wmax, bwl[k]); }
+
+    uint32_t va[32], vb[32], vt[4];
+    // ---- pass A: raw maximum over the 196 keys ----
+    float smax = -INFINITY;
+    ptx::tmem_ld_x32(s_tmem, va);
+    ptx::tmem_ld_wait_dep(va);
+#pragma unroll
+    for (int c = 1; c < 6; ++c) {
+        if (c & 1) { ptx::tmem_ld_x32(s_tmem + 32 * c, vb); smax = max32(va, smax); ptx::tmem_ld_wait_dep(vb); }
+        else       { ptx::tmem_ld_x32(s_tmem + 32 * c, va); smax = max32(vb, smax); ptx::tmem_ld_wait_dep(va); }
+    }
+    ptx::tmem_ld_x4(s_tmem + 192, vt);
+    smax = max32(vb, smax);
+    ptx::tmem_ld_wait_dep(vt);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) smax = fmaxf(smax, __uint_as_float(vt[e]));
+    const float m_ref = fmaf(smax, scale_log2, bmax + wmax);   // upper bound of the row maximum (scale > 0)
+#pragma unroll
+    for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
+    // ---- pass B ----
+    f32x2 l01 = f2_pack(0.f, 0.f);
+    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+#define SVB_WIN_B(V, CHUNK)                                                                              \
+    {                                                                                                \
+        uint32_t pk[16];                                                                             \
+        _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                          \
+            const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                            \
+            const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,               \
+                                          f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
+            float a0, a1;                                                                            \
+            f2_unpack(x, a0, a1);                                                                    \
+            const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                          \
+            l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
+            pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
+        }                                                                                            \
+        ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
+    }
+    ptx::tmem_ld_x32(s_tmem, va);
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 32, vb);
+    SVB_WIN_B(va, 0)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 64, va);
+    SVB_WIN_B(vb, 1)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 96, vb);
+    SVB_WIN_B(va, 2)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 128, va);
+    SVB_WIN_B(vb, 3)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 160, vb);
+    SVB_WIN_B(va, 4)
+    ptx::tmem_ld_wait_dep(vb);
+    SVB_WIN_B(vb, 5)
+#undef SVB_WIN_B
+    {
+        // keys 192..195 (vt was loaded in pass A and is still live) + zero columns for keys 196..207
+        uint32_t pk[8];
+        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]) + bhm[192 / 14]);
+        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14]);
+        const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14]);
+        const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14]);
+        l01 = f2_add(l01, f2_pack(p0 + p2, p1 + p3));
+        pk[0] = pack_bf16x2(p0, p1);
+        pk[1] = pack_bf16x2(p2, p3);
+#pragma unroll
+        for (int e = 2; e < 8; ++e) pk[e] = 0u;
+        ptx::tmem_st_x8(s_tmem + 96, pk);
+    }
+    ptx::tmem_st_wait();
+    float l0, l1;
+    f2_unpack(l01, l0, l1);
+    return l0 + l1;
+}
+
 // ================================================================================================================
 //                                      WINDOWED ATTENTION (14 x 14 windows, 196 keys)
 // ================================================================================================================
@@ -592,90 +676,15 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 0
 
-        float bmax = bhm[0], wmax = bwl[0];
-#pragma unroll
-        for (int k = 1; k < 14; ++k) { bmax = fmaxf(bmax, bhm[k]); wmax = fmaxf(wmax, bwl[k]); }
-
         ptx::mbar_wait(&bars[C::B_SFULL], 0);
         ptx::tc_fence_after();
-        uint32_t va[32], vb[32], vt[4];
-        // ---- pass A: raw maximum over the 196 keys ----
-        float smax = -INFINITY;
-        ptx::tmem_ld_x32(s_tmem, va);
-        ptx::tmem_ld_wait_dep(va);
-#pragma unroll
-        for (int c = 1; c < 6; ++c) {
-            if (c & 1) { ptx::tmem_ld_x32(s_tmem + 32 * c, vb); smax = max32(va, smax); ptx::tmem_ld_wait_dep(vb); }
-            else       { ptx::tmem_ld_x32(s_tmem + 32 * c, va); smax = max32(vb, smax); ptx::tmem_ld_wait_dep(va); }
-        }
-        ptx::tmem_ld_x4(s_tmem + 192, vt);
-        smax = max32(vb, smax);
-        ptx::tmem_ld_wait_dep(vt);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) smax = fmaxf(smax, __uint_as_float(vt[e]));
-        const float m_ref = fmaf(smax, scale_log2, bmax + wmax);   // upper bound of the row maximum (scale > 0)
-#pragma unroll
-        for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
-        // ---- pass B ----
-        f32x2 l01 = f2_pack(0.f, 0.f);
-        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
-#define SVB_WIN_B(V, CHUNK)                                                                              \
-        {                                                                                                \
-            uint32_t pk[16];                                                                             \
-            _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                          \
-                const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                            \
-                const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,               \
-                                              f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
-                float a0, a1;                                                                            \
-                f2_unpack(x, a0, a1);                                                                    \
-                const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                          \
-                l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
-                pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
-            }                                                                                            \
-            ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
-        }
-        ptx::tmem_ld_x32(s_tmem, va);
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_x32(s_tmem + 32, vb);
-        SVB_WIN_B(va, 0)
-        ptx::tmem_ld_wait_dep(vb);
-        ptx::tmem_ld_x32(s_tmem + 64, va);
-        SVB_WIN_B(vb, 1)
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_x32(s_tmem + 96, vb);
-        SVB_WIN_B(va, 2)
-        ptx::tmem_ld_wait_dep(vb);
-        ptx::tmem_ld_x32(s_tmem + 128, va);
-        SVB_WIN_B(vb, 3)
-        ptx::tmem_ld_wait_dep(va);
-        ptx::tmem_ld_x32(s_tmem + 160, vb);
-        SVB_WIN_B(va, 4)
-        ptx::tmem_ld_wait_dep(vb);
-        SVB_WIN_B(vb, 5)
-#undef SVB_WIN_B
-        {
-            // keys 192..195 (vt was loaded in pass A and is still live) + zero columns for keys 196..207
-            uint32_t pk[8];
-            const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]) + bhm[192 / 14]);
-            const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14]);
-            const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14]);
-            const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14]);
-            l01 = f2_add(l01, f2_pack(p0 + p2, p1 + p3));
-            pk[0] = pack_bf16x2(p0, p1);
-            pk[1] = pack_bf16x2(p2, p3);
-#pragma unroll
-            for (int e = 2; e < 8; ++e) pk[e] = 0u;
-            ptx::tmem_st_x8(s_tmem + 96, pk);
-        }
-        ptx::tmem_st_wait();
+        const float lsum = window_softmax_tile(s_tmem, bhm, bwl, scale_log2);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 1
         // ---- epilogue ----
         ptx::mbar_wait(&bars[C::B_PVDONE], 0);
         ptx::tc_fence_after();
-        float l0, l1;
-        f2_unpack(l01, l0, l1);
-        const float inv = 1.0f / (l0 + l1);
+        const float inv = 1.0f / lsum;
         bf16* dst = valid ? out + ((size_t)b * g * g + (size_t)y * g + x) * D + head * HD : nullptr;
         store_row<HD>(dst, o_tmem, inv);
     }
@@ -683,6 +692,328 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C::TM_COLS);
+    }
+}
+
+// ================================================================================================================
+//                     WINDOWED ATTENTION, persistent variant (the production kernel for 14 x 14 windows)
+// ================================================================================================================
+// One CTA per SM loops over (image, window, head) items.
+//   * The item's Q / K / V window boxes are prefetched by TMA into a 2-stage ring while the previous item computes.
+//   * Two query tiles per window — window rows 0..8 (126 queries) and 9..13 (70 queries) — each with its own softmax warp group
+//     AND its own MMA issuer thread, so the two chains never wait on each other.
+//   * The rel-pos skew (row t needs entries yi+13-ki / xi+13-kk of ITS OWN 27-entry products) is a register barrel shift.
+//   * The output tile is staged in the (dead) Q buffer in the TMA layout and written with ONE tensor store per tile
+//     (cp.async.bulk.tensor, box = 14 x 9|5 tokens): window_unpartition and the crop to 64 x 64 are the store's coordinates and
+//     its out-of-bounds clipping.  (Row-per-thread stores were LSU-bound: 3000 of 12400 cycles per item.)
+//   * Per group the loop is software-pipelined: after PV(k) the group first hands the rel-pos terms of item k+1 to its issuer,
+//     so S(k+1) runs on the tensor core while the group stores O(k).
+template <int HD> struct WPCfg {
+    static constexpr int TAIL = HD - 64;
+    static constexpr int Q_MAIN = 128 * 128, Q_TAIL = TAIL ? 128 * 32 : 0;   // one query tile (126 / 70 rows used)
+    static constexpr int QT = Q_MAIN + Q_TAIL;
+    static constexpr int K_MAIN = 208 * 128, K_TAIL = TAIL ? 7168 : 0;       // 196 keys (+12 pad rows)
+    static constexpr int KT = K_MAIN + K_TAIL;
+    static constexpr int OFF_K = 2 * QT, OFF_V = OFF_K + KT;
+    static constexpr int STAGE = 2 * QT + 2 * KT;
+    static constexpr int R_MAIN = 64 * 128, R_TAIL = TAIL ? 64 * 32 : 0;
+    static constexpr int OFF_R = 2 * STAGE;
+    static constexpr int OFF_BAR = OFF_R + R_MAIN + R_TAIL;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget");
+    static constexpr int ROWB = 128 + (TAIL ? 32 : 0);
+    static constexpr int QK_TX = (126 + 70 + 196) * ROWB;
+    static constexpr int V_TX = 196 * ROWB;
+    static constexpr int R_TX = 64 * ROWB;
+    static constexpr int B_RFULL = 0, B_QKFULL = 1, B_VFULL = 3, B_EMPTY = 5, B_BIAS = 7, B_BREAD = 9, B_SFULL = 11, B_PFULL = 13,
+                         B_PVDONE = 15, B_COUNT = 17;
+    static constexpr int TM_COLS = 512;                                       // S_i at 208*i; O_i inside S_i at +112
+};
+
+struct WinPMaps {
+    CUtensorMap q0, q1, kv, r;           // loads: boxes (64,14,9,1) / (64,14,5,1) / (64,14,14,1) of the padded qkv; (64,64) of the table
+    CUtensorMap q0t, q1t, kvt, rt;       // their 16-column tails (32B swizzle)
+    CUtensorMap o0, o1, o0t, o1t;        // stores: boxes (64|16,14,9|5,1) of out viewed as [B,64,64,D]
+};
+
+// r[j] <- r[j + sh] for a per-thread shift sh in [0, 13]: four conditional-move stages
+__device__ __forceinline__ void barrel_shift27(float (&r)[27], int sh) {
+#pragma unroll
+    for (int bit = 1; bit <= 8; bit <<= 1) {
+        const bool on = (sh & bit) != 0;
+#pragma unroll
+        for (int j = 0; j + bit < 27; ++j) r[j] = on ? r[j + bit] : r[j];
+    }
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+template <int HD>
+__global__ void __launch_bounds__(352, 1)
+attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
+                              long long* __restrict__ phase_clocks) {
+    using C = WPCfg<HD>;
+    constexpr int WS = 14, NWS = 5;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tmap(&maps.kv);
+        ptx::prefetch_tmap(&maps.q0);
+        ptx::prefetch_tmap(&maps.q1);
+        ptx::prefetch_tmap(&maps.r);
+        ptx::prefetch_tmap(&maps.o0);
+        ptx::prefetch_tmap(&maps.o1);
+        for (int s = 0; s < C::B_COUNT; ++s) {
+            const bool by_threads = (s >= C::B_BREAD && s < C::B_BREAD + 2) || (s >= C::B_PFULL && s < C::B_PFULL + 2);
+            const bool by_tiles = (s >= C::B_EMPTY && s < C::B_EMPTY + 2);            // one release per query tile
+            ptx::mbar_init(&bars[s], by_threads ? 128 : (by_tiles ? 2 : 1));
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    // keys 196..207 of the PV contraction multiply P = 0: their V rows (never written by TMA) must be finite in both stages
+    for (int st = 0; st < 2; ++st) {
+        uint8_t* v = sm + st * C::STAGE + C::OFF_V;
+        for (int i = threadIdx.x; i < 96; i += blockDim.x) *reinterpret_cast<uint4*>(v + 196 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
+        if (HD > 64)
+            for (int i = threadIdx.x; i < 24; i += blockDim.x) *reinterpret_cast<uint4*>(v + C::K_MAIN + 196 * 32 + i * 16) = make_uint4(0, 0, 0, 0);
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // item -> (image, window, head); query tile 1 (window rows 9..13) is entirely padding in the last window row
+    auto decode = [&](int item, int& b, int& wy, int& wx, int& head) {
+        head = item % heads;
+        const int bw = item / heads;
+        const int win = bw % (NWS * NWS);
+        b = bw / (NWS * NWS);
+        wy = win / NWS;
+        wx = win % NWS;
+    };
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[C::B_RFULL], C::R_TX);
+            ptx::tma_load_2d(sm + C::OFF_R, &maps.r, &bars[C::B_RFULL], 0, 0);
+            if (HD > 64) ptx::tma_load_2d(sm + C::OFF_R + C::R_MAIN, &maps.rt, &bars[C::B_RFULL], 64, 0);
+            int it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int st = it & 1;
+                const uint32_t par = ((it >> 1) & 1) ^ 1;
+                int b, wy, wx, head;
+                decode(item, b, wy, wx, head);
+                const int x0 = wx * WS, y0 = wy * WS;
+                uint8_t* q0 = sm + st * C::STAGE;
+                uint8_t* q1 = q0 + C::QT;
+                uint8_t* k = sm + st * C::STAGE + C::OFF_K;
+                uint8_t* v = sm + st * C::STAGE + C::OFF_V;
+                const int cq = head * HD, ck = D + head * HD, cv = 2 * D + head * HD;
+                ptx::mbar_wait(&bars[C::B_EMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_QKFULL + st], C::QK_TX);
+                ptx::tma_load_4d(q0, &maps.q0, &bars[C::B_QKFULL + st], cq, x0, y0, b);
+                ptx::tma_load_4d(q1, &maps.q1, &bars[C::B_QKFULL + st], cq, x0, y0 + 9, b);
+                ptx::tma_load_4d(k, &maps.kv, &bars[C::B_QKFULL + st], ck, x0, y0, b);
+                if (HD > 64) {
+                    ptx::tma_load_4d(q0 + C::Q_MAIN, &maps.q0t, &bars[C::B_QKFULL + st], cq + 64, x0, y0, b);
+                    ptx::tma_load_4d(q1 + C::Q_MAIN, &maps.q1t, &bars[C::B_QKFULL + st], cq + 64, x0, y0 + 9, b);
+                    ptx::tma_load_4d(k + C::K_MAIN, &maps.kvt, &bars[C::B_QKFULL + st], ck + 64, x0, y0, b);
+                }
+                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
+                ptx::tma_load_4d(v, &maps.kv, &bars[C::B_VFULL + st], cv, x0, y0, b);
+                if (HD > 64) ptx::tma_load_4d(v + C::K_MAIN, &maps.kvt, &bars[C::B_VFULL + st], cv + 64, x0, y0, b);
+            }
+        }
+    } else if (warp == 9 || warp == 10) {
+        // ===================== MMA issuers: one per query tile =====================
+        if (lane == 0) {
+            constexpr uint32_t id_r = ptx::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 208, 0, 0);
+            const int i = warp - 9;
+            ptx::mbar_wait(&bars[C::B_RFULL], 0);
+            int it = 0;
+            uint32_t n = 0;                                        // active items of this tile so far (barrier phases)
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int st = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                int b, wy, wx, head;
+                decode(item, b, wy, wx, head);
+                if (i == 1 && wy * WS + 9 >= g) {
+                    // tile 1 is all padding here: just release the stage — but only once THIS use of the stage has begun (its
+                    // loads landed), otherwise the arrival would be counted in the previous use's phase
+                    ptx::mbar_wait(&bars[C::B_QKFULL + st], ph);
+                    ptx::mbar_arrive(&bars[C::B_EMPTY + st]);
+                    continue;
+                }
+                const uint32_t q = base + st * C::STAGE + i * C::QT, k = base + st * C::STAGE + C::OFF_K, v = base + st * C::STAGE + C::OFF_V;
+                ptx::mbar_wait(&bars[C::B_QKFULL + st], ph);
+                ptx::tc_fence_after();
+                // columns [0,64) of S_i: the previous item's P_i there was consumed by its PV (same issuer, in-order tensor pipe);
+                // its O_i (columns 112..191) is only overwritten by the S MMA below, issued after the group has loaded O_i
+                issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
+                ptx::mma_commit(&bars[C::B_BIAS + i]);
+                ptx::mbar_wait(&bars[C::B_BREAD + i], n & 1);      // rel-pos products consumed (and the previous O_i loaded)
+                ptx::tc_fence_after();
+                issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, k, k + C::K_MAIN, id_s);
+                ptx::mma_commit(&bars[C::B_SFULL + i]);
+                ptx::mbar_wait(&bars[C::B_VFULL + st], ph);
+                ptx::mbar_wait(&bars[C::B_PFULL + i], n & 1);      // P_i is in TMEM
+                ptx::tc_fence_after();
+                issue_pv<HD>(tmem + 208 * i + 112, tmem + 208 * i, v, v + C::K_MAIN, 13, false);
+                ptx::mma_commit(&bars[C::B_PVDONE + i]);
+                ++n;
+            }
+        }
+    } else {
+        // ===================== softmax warps: group i = query tile i =====================
+        const int i = warp >> 2, w4 = warp & 3;
+        const int t = w4 * 32 + lane;                              // query row inside the tile
+        const int yi = 9 * i + t / WS, xi = t % WS;                // window coordinates (rows past the tile are discarded)
+        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + 208 * i;
+        const uint32_t o_tmem = s_tmem + 112;
+        const CUtensorMap* omap = i ? &maps.o1 : &maps.o0;
+        const CUtensorMap* omapt = i ? &maps.o1t : &maps.o0t;
+        long long pc[6] = {0, 0, 0, 0, 0, 0};
+        long long tprev = phase_clocks ? clock64() : 0;
+#define SVB_PHASE(k) if (phase_clocks) { const long long tnow = clock64(); pc[k] += tnow - tprev; tprev = tnow; }
+
+        // rel-pos products of the item whose bias MMA is `ph`-th for this tile -> the row's 14 + 14 terms (log2 units)
+        float bhm[14], bwl[14];
+        auto read_bias = [&](uint32_t ph) {
+            ptx::mbar_wait(&bars[C::B_BIAS + i], ph);
+            ptx::tc_fence_after();
+            uint32_t v[32];
+            float rr[27];
+            ptx::tmem_ld_x32(s_tmem, v);
+            ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
+            barrel_shift27(rr, yi < 13 ? yi : 13);
+#pragma unroll
+            for (int kk = 0; kk < 14; ++kk) bhm[kk] = rr[13 - kk];
+            ptx::tmem_ld_x32(s_tmem + 32, v);
+            ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
+            barrel_shift27(rr, xi);
+#pragma unroll
+            for (int kk = 0; kk < 14; ++kk) bwl[kk] = rr[13 - kk];
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars[C::B_BREAD + i]);
+        };
+        auto active = [&](int item) {
+            int b, wy, wx, head;
+            decode(item, b, wy, wx, head);
+            return !(i == 1 && wy * WS + 9 >= g);
+        };
+        // first active item of this group
+        int item = blockIdx.x, it = 0;
+        while (item < num_items && !active(item)) { item += gridDim.x; ++it; }
+        uint32_t n = 0;
+        if (item < num_items) read_bias(0);
+        SVB_PHASE(1)
+        while (item < num_items) {
+            int b, wy, wx, head;
+            decode(item, b, wy, wx, head);
+            const int st = it & 1;
+            const uint32_t ph = n & 1;
+            // ---- softmax over the 196 keys ----
+            ptx::mbar_wait(&bars[C::B_SFULL + i], ph);
+            SVB_PHASE(2)
+            ptx::tc_fence_after();
+            const float lsum = window_softmax_tile(s_tmem, bhm, bwl, scale_log2);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars[C::B_PFULL + i]);
+            SVB_PHASE(3)
+            // next active item of this group
+            int nitem = item + gridDim.x, nit = it + 1;
+            while (nitem < num_items && !active(nitem)) { nitem += gridDim.x; ++nit; }
+            // ---- O(k): TMEM -> normalised bf16 in registers ----
+            ptx::mbar_wait(&bars[C::B_PVDONE + i], ph);
+            SVB_PHASE(4)
+            ptx::tc_fence_after();
+            const float inv = 1.0f / lsum;
+            uint32_t o[HD / 2];
+            {
+                uint32_t v[32];
+#pragma unroll
+                for (int c = 0; c < 64; c += 32) {
+                    ptx::tmem_ld_x32(o_tmem + c, v);
+                    ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[c / 2 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+                }
+                if (HD > 64) {
+                    uint32_t w[16];
+                    ptx::tmem_ld_x16(o_tmem + 64, w);
+                    ptx::tmem_ld_wait_dep(w);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[32 + j] = pack_bf16x2(__uint_as_float(w[2 * j]) * inv, __uint_as_float(w[2 * j + 1]) * inv);
+                }
+            }
+            // ---- hand the next item's rel-pos terms over first: S(k+1) then runs while O(k) is being stored.  Only when the
+            // next item of this tile sits in the OTHER stage: if the tile skips an item, its next one reuses THIS stage, whose
+            // reload waits for the release below (reading its bias first would deadlock). ----
+            const bool early = (nitem < num_items) && (nit == it + 1);
+            if (early) read_bias((n + 1) & 1);
+            SVB_PHASE(1)
+            // ---- O(k) -> the dead Q buffer of this stage in the TMA layout -> one tensor store per tile ----
+            {
+                uint8_t* ob = sm + st * C::STAGE + i * C::QT;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)                        // 128B swizzle: 16-byte piece j of row t at piece j ^ (t & 7)
+                    *reinterpret_cast<uint4*>(ob + t * 128 + ((j ^ (t & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                if (HD > 64) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)                    // 32B swizzle: piece j of row t at piece j ^ ((t >> 2) & 1)
+                        *reinterpret_cast<uint4*>(ob + C::Q_MAIN + t * 32 + ((j ^ ((t >> 2) & 1)) << 4)) =
+                            make_uint4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
+                }
+                ptx::fence_proxy_async_smem();                     // generic writes -> visible to the TMA (async proxy) read
+                if (i == 0) asm volatile("bar.sync 1, 128;" ::: "memory");          // the group's 128 rows are staged
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (t == 0) {
+                    const int x0 = wx * WS, y0 = wy * WS + 9 * i;
+                    tma_store_4d(omap, ob, head * HD, x0, y0, b);  // rows past 64 and columns past 64 are clipped by the TMA
+                    if (HD > 64) tma_store_4d(omapt, ob + C::Q_MAIN, head * HD + 64, x0, y0, b);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has finished reading the stage
+                    ptx::mbar_arrive(&bars[C::B_EMPTY + st]);      // this tile is done with stage st (its MMAs retired before PVDONE)
+                }
+                __syncwarp();                                      // reconverge before the next warp-collective tcgen05 instruction
+            }
+            if (!early && nitem < num_items) read_bias((n + 1) & 1);
+            SVB_PHASE(5)
+            item = nitem;
+            it = nit;
+            ++n;
+        }
+#undef SVB_PHASE
+        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // stores complete before the CTA exits
+        if (phase_clocks && w4 == 0 && lane == 0) {
+            for (int k = 0; k < 6; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)n);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem, C::TM_COLS);
     }
@@ -790,9 +1121,61 @@ int launch_window(const AttnTcParams& p, cudaStream_t stream) {
     return 0;
 }
 
+template <int HD>
+int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
+    using C = WPCfg<HD>;
+    const int D = p.heads * p.hd, gp = 70, g = p.grid;
+    WinPMaps wm;
+    int rc;
+    {
+        const uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)gp, (uint64_t)gp, (uint64_t)p.batch};
+        const uint64_t str[3] = {(uint64_t)3 * D * 2, (uint64_t)gp * 3 * D * 2, (uint64_t)gp * gp * 3 * D * 2};
+        const uint32_t q0[4] = {64, 14, 9, 1}, q1[4] = {64, 14, 5, 1}, kv[4] = {64, 14, 14, 1};
+        const uint32_t q0t[4] = {16, 14, 9, 1}, q1t[4] = {16, 14, 5, 1}, kvt[4] = {16, 14, 14, 1};
+        if ((rc = encode_tmap_nd_bf16(&wm.q0, p.qkv, 4, dims, str, q0, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q1, p.qkv, 4, dims, str, q1, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.kv, p.qkv, 4, dims, str, kv, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q0t, p.qkv, 4, dims, str, q0t, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.q1t, p.qkv, 4, dims, str, q1t, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.kvt, p.qkv, 4, dims, str, kvt, 32))) return rc;
+        const uint64_t rd[2] = {(uint64_t)HD, 64};
+        const uint64_t rs[1] = {(uint64_t)HD * 2};
+        const uint32_t rm[2] = {64, 64}, rt[2] = {16, 64};
+        if ((rc = encode_tmap_nd_bf16(&wm.r, p.rel_pack, 2, rd, rs, rm, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.rt, p.rel_pack, 2, rd, rs, rt, 32))) return rc;
+        // output viewed as [B, 64, 64, D]: the store of a window tile is a box of 14 x (9|5) tokens, clipped at the 64 x 64 edge
+        const uint64_t od[4] = {(uint64_t)D, (uint64_t)g, (uint64_t)g, (uint64_t)p.batch};
+        const uint64_t os[3] = {(uint64_t)D * 2, (uint64_t)g * D * 2, (uint64_t)g * g * D * 2};
+        if ((rc = encode_tmap_nd_bf16(&wm.o0, p.out, 4, od, os, q0, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.o1, p.out, 4, od, os, q1, 128))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.o0t, p.out, 4, od, os, q0t, 32))) return rc;
+        if ((rc = encode_tmap_nd_bf16(&wm.o1t, p.out, 4, od, os, q1t, 32))) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    const float scale_log2 = LOG2E / sqrtf((float)HD);
+    const int items = p.batch * 25 * p.heads;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int grid = items < sms ? items : sms;
+    attn_window_persistent_kernel<HD><<<grid, 352, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 int attention_tc_rel_rows(int ws, int grid) { return ws == grid ? 272 : 64; }
+
+// registers a host-mapped buffer (64 x u64, zeroed) that receives mbarrier-timeout records of the attention kernels
+int attention_tc_set_debug_buffer(void* mapped_device_ptr) {
+    unsigned long long* p = (unsigned long long*)mapped_device_ptr;
+    SVB_CHECK_CUDA(cudaMemcpyToSymbol(ptx::svb_dbg_buf, &p, sizeof(p)));
+    return 0;
+}
 
 int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream) {
     SVB_REQUIRE(L == 27 || L == 127, "pack_rel_table: table length %d is not 27 (14x14 windows) or 127 (64x64 global)", L);
@@ -825,7 +1208,10 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
                    (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
                    (double)p.batch * p.grid * p.grid * 4.0 * D_ * 2, stream);
     if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
-    return p.hd == 64 ? launch_window<64>(p, stream) : launch_window<80>(p, stream);
+    // persistent two-tile kernel by default; SVB_ATTNW_IMPL=1 selects the one-tile-per-CTA kernel (A/B comparisons)
+    static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 2; }();
+    if (impl == 1) return p.hd == 64 ? launch_window<64>(p, stream) : launch_window<80>(p, stream);
+    return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }
 
 }  // namespace svb

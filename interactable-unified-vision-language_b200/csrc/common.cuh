@@ -177,8 +177,10 @@ struct AttnTcParams {
     const bf16* qkv; bf16* out;
     const bf16* rel_pack;
     int batch, grid, ws, heads, hd;
+    long long* phase_clocks = nullptr;   // optional [2][8] device counters: per-phase cycles of the softmax groups (debug)
 };
 int attention_tc_rel_rows(int ws, int grid);
+int attention_tc_set_debug_buffer(void* mapped_device_ptr);
 int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream);
 int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream);
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);

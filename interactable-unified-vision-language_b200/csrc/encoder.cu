@@ -625,6 +625,16 @@ int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* 
     SVB_REQUIRE(false, "svb_attention: impl %d is not available in this build", impl);
 }
 
+int svb_attention_tc_phases(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
+                            long long* phase_clocks, svb_stream_t stream) {
+    SVB_REQUIRE(qkv && out && rel_pack, "svb_attention_tc_phases: null argument");
+    AttnTcParams ap;
+    ap.qkv = (const bf16*)qkv; ap.out = (bf16*)out; ap.rel_pack = (const bf16*)rel_pack;
+    ap.batch = batch; ap.grid = grid; ap.ws = ws; ap.heads = heads; ap.hd = head_dim;
+    ap.phase_clocks = phase_clocks;
+    return attention_tc(ap, (cudaStream_t)stream);
+}
+
 int svb_attention_tc(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
                      svb_stream_t stream) {
     SVB_REQUIRE(qkv && out && rel_pack, "svb_attention_tc: null argument");
@@ -635,6 +645,8 @@ int svb_attention_tc(const void* qkv, void* out, const void* rel_pack, int batch
 }
 
 int svb_rel_pack_rows(int ws, int grid) { return attention_tc_rel_rows(ws, grid); }
+
+int svb_attention_debug_buffer(void* mapped_device_ptr) { return attention_tc_set_debug_buffer(mapped_device_ptr); }
 
 int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int head_dim, int is_w, svb_stream_t stream) {
     SVB_REQUIRE(table && rel_pack, "svb_pack_rel_table: null argument");

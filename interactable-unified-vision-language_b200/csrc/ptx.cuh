@@ -47,12 +47,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Spin on try_wait (which itself suspends the thread for a bounded time).  A protocol bug would otherwise hang the GPU:
-// after ~4 s of SM clocks the kernel traps, which surfaces as a launch failure on the host instead.
+// after ~4 s of SM clocks the kernel traps, which surfaces as a launch failure on the host instead.  If a (host-mapped)
+// debug buffer was registered for this translation unit, the first timeouts leave a record there before the trap:
+// {block, thread, barrier smem address, parity} — readable by the host even though the context is dead afterwards.
+static __device__ unsigned long long* svb_dbg_buf = nullptr;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();
+        if (clock64() - t0 > 8000000000LL) {
+            if (svb_dbg_buf) {
+                const unsigned long long slot = atomicAdd(svb_dbg_buf, 1ULL);
+                if (slot < 63) {
+                    svb_dbg_buf[1 + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 36) |
+                                            ((unsigned long long)(smem_u32(bar) & 0xFFFFFF) << 4) | parity;
+                    __threadfence_system();
+                }
+            }
+            __trap();
+        }
     }
 }
 
