@@ -126,75 +126,116 @@ __global__ void cast_s2d_kernel(const float* __restrict__ x, T* __restrict__ xb,
 // ---------------------------------------------------------------------------------------------------------------
 // GroupNorm(1, C) apply (image_encoder.py:419-446): statistics (sum, sumsq per sample, fp64) were accumulated by the
 // producing GEMM's epilogue.  NHWC rows in, NHWC rows out (T) for the next GEMM.
+// GELU: exact erf for fp32 outputs (validation mode); the packed-fp32x2 A&S 7.1.25 form (|erf error| <= 2.5e-5, below the
+// bf16 rounding of the store) for bf16 outputs, which keeps the kernel HBM-bound instead of issue-bound.
+template <typename T> __device__ __forceinline__ void gelu4(float& a, float& b, float& c, float& d);
+template <> __device__ __forceinline__ void gelu4<float>(float& a, float& b, float& c, float& d) {
+    a = gelu_erf(a); b = gelu_erf(b); c = gelu_erf(c); d = gelu_erf(d);
+}
+template <> __device__ __forceinline__ void gelu4<bf16>(float& a, float& b, float& c, float& d) {
+    gelu_pair(a, b);
+    gelu_pair(c, d);
+}
+__device__ __forceinline__ float2 gn_mean_rstd(const double* __restrict__ stats, int sample, double n, float eps) {
+    const double mu = stats[2 * sample] / n;
+    const double var = fmax(stats[2 * sample + 1] / n - mu * mu, 0.0);
+    return make_float2((float)mu, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 template <typename T>
-__global__ void gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, T* __restrict__ out, long rows, int C, long rows_per_sample,
-                                float eps, int gelu) {
-    const size_t total4 = (size_t)rows * C / 4;
-    const double n = (double)rows_per_sample * C;
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, T* __restrict__ out, long rows, int C, long rows_per_sample, float eps, int gelu,
+                int nsamples) {
+    extern __shared__ float2 ms_s[];                 // (mean, rstd) per sample: the fp64 math runs once per block
+    for (int sidx = threadIdx.x; sidx < nsamples; sidx += blockDim.x)
+        ms_s[sidx] = gn_mean_rstd(stats, sidx, (double)rows_per_sample * C, eps);
+    __syncthreads();
+    const unsigned cpr = (unsigned)C / 4;            // float4 per row
+    const size_t total4 = (size_t)rows * cpr;
+    const size_t per_sample4 = (size_t)rows_per_sample * cpr;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = i * 4;
-        const int c = (int)(e % C);
-        const long row = (long)(e / C);
-        const long sample = row / rows_per_sample;
-        const double mu = stats[2 * sample] / n;
-        const double var = fmax(stats[2 * sample + 1] / n - mu * mu, 0.0);
-        const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float4 v = *reinterpret_cast<const float4*>(x + e);
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
-        float a = (v.x - mean) * rstd * g4.x + b4.x, b = (v.y - mean) * rstd * g4.y + b4.y;
-        float cc = (v.z - mean) * rstd * g4.z + b4.z, d = (v.w - mean) * rstd * g4.w + b4.w;
-        if (gelu) { a = gelu_erf(a); b = gelu_erf(b); cc = gelu_erf(cc); d = gelu_erf(d); }
-        Vec4<T>::store(out + e, a, b, cc, d);
+        const int sample = (int)(i / per_sample4);
+        const unsigned c4 = (unsigned)(i % cpr);
+        const float2 ms = ms_s[sample];
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        float a = (v.x - ms.x) * ms.y * g4.x + b4.x, b = (v.y - ms.x) * ms.y * g4.y + b4.y;
+        float cc = (v.z - ms.x) * ms.y * g4.z + b4.z, d = (v.w - ms.x) * ms.y * g4.w + b4.w;
+        if (gelu) gelu4<T>(a, b, cc, d);
+        Vec4<T>::store(out + i * 4, a, b, cc, d);
     }
 }
 
 // Final stage of every branch: GroupNorm(1,C) + GELU, then NHWC (with `levels` folded 2x2 sub-pixel indexes in the row
 // index) -> NCHW.  Input rows are ordered (b, y, x, s_1, ..., s_levels) with s_l = dy_l*2+dx_l; output pixel
-// Y = y*2^L + sum dy_l 2^(L-l), X likewise.  32x32 (pixel x channel) tiles transposed through shared memory so both
-// the reads (along C) and the writes (along X) are coalesced.
-template <typename T>
+// Y = y*2^L + sum dy_l 2^(L-l), X likewise.  One block = TP output pixels of one output row x 64 channels, transposed
+// through shared memory: 16-byte reads along C (256 B per pixel), 16-byte writes along X (whole 128-byte lines for bf16 at
+// TP = 64).
+template <typename T, int TP>
 __global__ void __launch_bounds__(256)
 gn_apply_nchw_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ out, int B, int g, int levels, int C, float eps, int gelu) {
-    __shared__ float tile[32][33];
+    constexpr int TC = 64;
+    __shared__ float tile[TC][TP + 1];
+    __shared__ float2 ms_s;
     const int Wout = g << levels, Hout = Wout;
-    const int xt = Wout / 32;                       // 32-pixel tiles per output row
-    const int X0 = (blockIdx.x % xt) * 32;
+    const int xt = Wout / TP;
+    const int X0 = (blockIdx.x % xt) * TP;
     const int Y = (blockIdx.x / xt) % Hout;
     const int b = blockIdx.x / (xt * Hout);
-    const int c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const long rows_per_sample = (long)g * g << (2 * levels);
-    const double n = (double)rows_per_sample * C;
-    const double mu = stats[2 * b] / n;
-    const double var = fmax(stats[2 * b + 1] / n - mu * mu, 0.0);
-    const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const int c0 = blockIdx.y * TC;
+    if (threadIdx.x == 0) ms_s = gn_mean_rstd(stats, b, (double)((long)g * g << (2 * levels)) * C, eps);
+    __syncthreads();
+    const float mean = ms_s.x, rstd = ms_s.y;
+    {   // ---- phase 1: 16 threads per pixel (4 channels each), 16 pixels per pass ----
+        const int cq = threadIdx.x & 15, pl = threadIdx.x >> 4;
+        const int c = c0 + 4 * cq;
+        const bool c_ok = c < C;                      // C is a multiple of 4
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
+        if (c_ok) { g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)); b4 = __ldg(reinterpret_cast<const float4*>(beta + c)); }
+        float4 v[TP / 16];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = ty + 8 * k;                   // pixel within the tile
-        const int X = X0 + i;
-        // source row of output pixel (Y, X)
-        long row = ((long)b * g + (Y >> levels)) * g + (X >> levels);
-        for (int l = 1; l <= levels; ++l) {
-            const int sh = levels - l;
-            row = row * 4 + (((Y >> sh) & 1) * 2 + ((X >> sh) & 1));
+        for (int k = 0; k < TP / 16; ++k) {
+            const int X = X0 + pl + 16 * k;
+            long row = ((long)b * g + (Y >> levels)) * g + (X >> levels);
+            for (int l = 1; l <= levels; ++l) {
+                const int sh = levels - l;
+                row = row * 4 + (((Y >> sh) & 1) * 2 + ((X >> sh) & 1));
+            }
+            v[k] = c_ok ? __ldcs(reinterpret_cast<const float4*>(x + row * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const int c = c0 + tx;
-        float v = 0.f;
-        if (c < C) {
-            v = (x[row * C + c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-            if (gelu) v = gelu_erf(v);
+#pragma unroll
+        for (int k = 0; k < TP / 16; ++k) {
+            float a0 = (v[k].x - mean) * rstd * g4.x + b4.x, a1 = (v[k].y - mean) * rstd * g4.y + b4.y;
+            float a2 = (v[k].z - mean) * rstd * g4.z + b4.z, a3 = (v[k].w - mean) * rstd * g4.w + b4.w;
+            if (gelu) gelu4<T>(a0, a1, a2, a3);
+            const int px = pl + 16 * k;
+            tile[4 * cq + 0][px] = a0; tile[4 * cq + 1][px] = a1; tile[4 * cq + 2][px] = a2; tile[4 * cq + 3][px] = a3;
         }
-        tile[i][tx] = v;
     }
     __syncthreads();
+    // ---- phase 2: 16 bytes of consecutive X per thread ----
+    constexpr int EPT = 16 / (int)sizeof(T);          // elements per thread: 8 (bf16) or 4 (fp32)
+    constexpr int TPR = TP / EPT;                     // threads per channel row
+    constexpr int CPP = 256 / TPR;                    // channels per pass
+    const int pg = threadIdx.x % TPR, cl = threadIdx.x / TPR;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int cj = ty + 8 * k;
+    for (int k = 0; k < TC / CPP; ++k) {
+        const int cj = cl + CPP * k;
         const int c = c0 + cj;
-        if (c < C) out[(((size_t)b * C + c) * Hout + Y) * Wout + X0 + tx] = from_float<T>(tile[tx][cj]);
+        if (c >= C) continue;
+        T* dst = out + (((size_t)b * C + c) * Hout + Y) * Wout + X0 + pg * EPT;
+        const float* src = &tile[cj][pg * EPT];
+        if constexpr (sizeof(T) == 2) {
+            uint4 u;
+            u.x = pack_bf16x2(src[0], src[1]); u.y = pack_bf16x2(src[2], src[3]);
+            u.z = pack_bf16x2(src[4], src[5]); u.w = pack_bf16x2(src[6], src[7]);
+            __stcs(reinterpret_cast<uint4*>(dst), u);
+        } else {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(src[0], src[1], src[2], src[3]));
+        }
     }
 }
 
@@ -335,12 +376,17 @@ int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int
 int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,
                     long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s) {
     SVB_REQUIRE(C % 4 == 0, "groupnorm_apply: C=%d must be a multiple of 4", C);
+    SVB_REQUIRE(rows_per_sample > 0 && rows % rows_per_sample == 0, "groupnorm_apply: rows %ld not a multiple of rows_per_sample %ld", rows,
+                rows_per_sample);
+    const int nsamples = (int)(rows / rows_per_sample);
+    SVB_REQUIRE(nsamples <= 4096, "groupnorm_apply: %d samples per call (max 4096)", nsamples);
     const size_t total4 = (size_t)rows * C / 4;
+    const size_t smem = sizeof(float2) * (size_t)nsamples;
     ProfScope prof(PC_NORM, 0, (double)rows * C * (4 + (out_bf16 ? 2 : 4)), s);
     if (out_bf16)
-        gn_apply_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, rows, C, rows_per_sample, eps, gelu);
+        gn_apply_kernel<bf16><<<grid_for(total4, 256), 256, smem, s>>>(x, stats, gamma, beta, (bf16*)out, rows, C, rows_per_sample, eps, gelu, nsamples);
     else
-        gn_apply_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, stats, gamma, beta, (float*)out, rows, C, rows_per_sample, eps, gelu);
+        gn_apply_kernel<float><<<grid_for(total4, 256), 256, smem, s>>>(x, stats, gamma, beta, (float*)out, rows, C, rows_per_sample, eps, gelu, nsamples);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -348,11 +394,18 @@ int groupnorm_apply(const float* x, const double* stats, const float* gamma, con
 int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
                          int B, int g, int levels, int C, float eps, int gelu, cudaStream_t s) {
     const int Wout = g << levels;
-    SVB_REQUIRE(Wout % 32 == 0 && levels >= 0 && levels <= 2, "groupnorm_apply_nchw: grid %d levels %d unsupported", g, levels);
-    dim3 grid((unsigned)((size_t)B * Wout * (Wout / 32)), (C + 31) / 32);
+    SVB_REQUIRE(Wout % 32 == 0 && levels >= 0 && levels <= 2 && C % 4 == 0, "groupnorm_apply_nchw: grid %d levels %d C %d unsupported", g,
+                levels, C);
+    const int TP = (Wout % 64 == 0) ? 64 : 32;
+    dim3 grid((unsigned)((size_t)B * Wout * (Wout / TP)), (C + 63) / 64);
     ProfScope prof(PC_NORM, 0, (double)B * Wout * Wout * C * (4 + (out_dtype == 1 ? 2 : 4)), s);
-    if (out_dtype == 1) gn_apply_nchw_kernel<bf16><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
-    else gn_apply_nchw_kernel<float><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
+    if (out_dtype == 1) {
+        if (TP == 64) gn_apply_nchw_kernel<bf16, 64><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
+        else gn_apply_nchw_kernel<bf16, 32><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
+    } else {
+        if (TP == 64) gn_apply_nchw_kernel<float, 64><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
+        else gn_apply_nchw_kernel<float, 32><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
+    }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -77,6 +77,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, multicast: the box lands at the same CTA-relative offset in every CTA of `mask`, and each destination's share of the
+// completion bytes is credited to the barrier at the same offset in that destination's pair leader.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                                    uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
 __device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -85,8 +94,7 @@ __device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a
         : "memory");
 }
 // arrive (once all previously issued MMAs retired) on the barrier at the same offset in BOTH CTAs of the pair
-__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
-    const uint16_t mask = 3;
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(ptx::smem_u32(bar)), "h"(mask)
                  : "memory");
@@ -100,8 +108,11 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int BN, bool RESID>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// CL = CTAs per cluster: 2 (one pair) or 4 (two pairs on consecutive 256-row blocks of the same BN columns: the weight tile
+// is fetched ONCE from L2 and multicast to both pairs, which cuts the L2->SM bytes per MMA by a quarter — the L2 slices'
+// ~6300 B/clk were the limit of the single-pair kernel, ncu: lts 10 TB/s, tensor pipe 68 %).
+template <int BN, bool RESID, int CL>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
                 Epilogue ep, int dbg) {
     using C = Cfg2<BN>;
@@ -118,11 +129,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const int num_m = (M + 2 * BM_CTA - 1) / (2 * BM_CTA);
+    constexpr int PAIRS = CL / 2;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1;                 // position inside the CTA pair (0 = leader: issues the MMAs)
+    const uint32_t pidx = crank >> 1;                // which pair of the cluster
+    const uint32_t lead = crank & ~1u;               // cluster rank of this pair's leader
+    const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;     // cluster index / number of clusters
+    const int num_m = (M + 2 * BM_CTA * PAIRS - 1) / (2 * BM_CTA * PAIRS);
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
+    const int num_tiles = num_m * num_n;             // cluster tiles of (256 * PAIRS) x BN
     const int num_k = (K + BK - 1) / BK;
 
     if (warp == 0 && lane == 0) {
@@ -130,7 +145,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         ptx::prefetch_tmap(&map_w);
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], PAIRS);             // one tcgen05.commit per pair: the stage is free in every CTA
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
@@ -150,16 +165,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             for (int t = pair; t < num_tiles; t += num_pairs) {
-                const int m0 = (t / num_n) * (2 * BM_CTA) + rank * BM_CTA;
-                const int n0 = (t % num_n) * BN + rank * (BN / 2);
+                const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
+                const int n0 = (t % num_n) * BN + rank * (BN / 2) + pidx * (BN / 2 / PAIRS);
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = tiles + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::A_BYTES;
-                    const uint32_t full_leader = map_to_cta(ptx::smem_u32(&full_bar[stage]), 0);
+                    const uint32_t full_leader = map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
                     if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
                     tma_load_2d_pair(sa, &map_a, full_leader, kb * BK, m0);
-                    tma_load_2d_pair(sb, &map_w, full_leader, kb * BK, n0);
+                    if constexpr (PAIRS == 1) {
+                        tma_load_2d_pair(sb, &map_w, full_leader, kb * BK, n0);
+                    } else {
+                        // this CTA fetches 1/PAIRS of the pair-rank's weight rows and multicasts them to the CTA of the same
+                        // pair-rank in every pair
+                        uint16_t mask = 0;
+#pragma unroll
+                        for (int q = 0; q < PAIRS; ++q) mask |= (uint16_t)(1u << (2 * q + rank));
+                        tma_load_2d_pair_mc(sb + pidx * (C::B_BYTES / PAIRS), &map_w, full_leader, kb * BK, n0, mask);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -185,10 +209,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint64_t db = ptx::make_smem_desc(sb, 0, 1024, ptx::LAYOUT_SW128);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    mma_commit_pair(&empty_bar[stage]);       // frees this stage in both CTAs
+                    mma_commit_pair(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // this pair is done with the stage: tell every CTA
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit_pair(&tmem_full[as]);              // accumulators ready in both CTAs
+                mma_commit_pair(&tmem_full[as], (uint16_t)(3u << lead));   // accumulators ready in both CTAs of this pair
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -203,7 +227,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         int as = 0;
         uint32_t aphase = 0;
         for (int t = pair; t < num_tiles; t += num_pairs) {
-            const int m0 = (t / num_n) * (2 * BM_CTA) + rank * BM_CTA;
+            const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
             const int nt0 = (t % num_n) * BN;
             const int n0 = nt0 + half * (BN / 2);
             const int r0 = m0 + quad * 32;                    // first row of this warp's 32-row slab
@@ -333,7 +357,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tmem_empty[as]), 0));
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tmem_empty[as]), lead));
             if (ep.stats) {
                 s_sum = warp_sum(s_sum);
                 s_sq = warp_sum(s_sq);
@@ -355,28 +379,63 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 }
 
+template <int BN, bool RESID, int CL>
+int launch_gemm2_cl(const CUtensorMap& ma, const CUtensorMap& mw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
+    using C = Cfg2<BN>;
+    auto kern = gemm_tc2_kernel<BN, RESID, CL>;
+    static int max_clusters = 0;                // co-resident clusters of this kernel (GPC sizes decide; <= num_sms / CL)
+    if (!max_clusters) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        cudaLaunchConfig_t qc = {};
+        qc.gridDim = dim3(CL * (num_sms() / CL));
+        qc.blockDim = dim3(NUM_THREADS);
+        qc.dynamicSmemBytes = C::SMEM_BYTES;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        qc.attrs = qa; qc.numAttrs = 1;
+        int n = 0;
+        SVB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &qc));
+        SVB_REQUIRE(n > 0, "gemm_tc2: no cluster of %d CTAs fits on this device", CL);
+        max_clusters = std::min(n, num_sms() / CL);
+        if (getenv("SVB_GEMM2_VERBOSE")) fprintf(stderr, "gemm_tc2<%d,%d,%d>: %d co-resident clusters\n", BN, (int)RESID, CL, max_clusters);
+    }
+    const int tiles = ((M + BM_CTA * CL - 1) / (BM_CTA * CL)) * ((N + BN - 1) / BN);
+    const int clusters = std::min(tiles, max_clusters);
+    static const int dbg = [] { const char* e = getenv("SVB_GEMM2_DBG"); return e ? atoi(e) : 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (ep.out_bf16 ? 2.0 : 4.0) * M * N, stream);
+    SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, M, N, K, ep, dbg));
+    return 0;
+}
+
 template <int BN>
 int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
-    using C = Cfg2<BN>;
+    // SVB_GEMM_CLUSTER = 2 (default): one CTA pair per cluster; 4: two pairs sharing the weight tile by TMA multicast.
+    // Measured on B200 (tools/gemm_bench.py, ViT-H shapes, 8 images): the multicast variant is 8 % faster PER SM (9.6 vs
+    // 8.9 TF/s/SM) but only 33 clusters of 4 are co-resident (132 of 148 SMs: GPCs of 18 SMs hold 4 such clusters), so the
+    // whole GEMM is 4 % slower (1268 vs 1316 TF/s).
+    static const int cl = [] { const char* e = getenv("SVB_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
+    const int pairs = (cl == 4 && M > 2 * BM_CTA) ? 2 : 1;
     CUtensorMap ma, mw;
     int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2, 128);
+    rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2 / pairs, 128);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_set = true;
+    if (pairs == 2) {
+        if (ep.resid) return launch_gemm2_cl<BN, true, 4>(ma, mw, M, N, K, ep, stream);
+        return launch_gemm2_cl<BN, false, 4>(ma, mw, M, N, K, ep, stream);
     }
-    const int tiles = ((M + 2 * BM_CTA - 1) / (2 * BM_CTA)) * ((N + BN - 1) / BN);
-    const int pairs = std::min(tiles, num_sms() / 2);
-    ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + (ep.out_bf16 ? 2.0 : 4.0) * M * N, stream);
-    static const int dbg = [] { const char* e = getenv("SVB_GEMM2_DBG"); return e ? atoi(e) : 0; }();   // bisecting aid: 1 no L2 prefetch, 2 no smem bias, 4 no early residual loads
-    if (ep.resid) gemm_tc2_kernel<BN, true><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep, dbg);
-    else gemm_tc2_kernel<BN, false><<<2 * pairs, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mw, M, N, K, ep, dbg);
-    SVB_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    if (ep.resid) return launch_gemm2_cl<BN, true, 2>(ma, mw, M, N, K, ep, stream);
+    return launch_gemm2_cl<BN, false, 2>(ma, mw, M, N, K, ep, stream);
 }
 
 }  // namespace
