@@ -83,6 +83,20 @@ int svb_encoder_read_tap(svb_encoder_t* enc, int block, float* dst, int64_t nume
 int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats,
                int rows_per_sample, int remap_grid, int remap_grid_pad, svb_stream_t stream);
+/* The same GEMM with the LayerNorm-folding epilogues of the bf16 path: norm1 / norm2
+ * (image_encoder.py:183,195) never run as separate passes.
+ *   producer side (fp32 `out` + `resid` required): `out_bf16_copy` (bf16 [M, ldo2]) receives a rounded copy of the final rows and
+ *     `stat_out` ([M][ceil(N/128)][2] fp32) the partial (sum, sum of squares) of each final row per 128-column slab;
+ *   consumer side: `ln_stats` = such partials of the rows of x (over ln_dim = K columns), A = bf16(x) UN-normalised,
+ *     W / bias / ln_colsum as written by svb_fold_layernorm:  out = act(rstd (A W^T - mu ln_colsum) + bias). */
+int svb_linear_fused(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
+                     const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, const float* ln_stats,
+                     const float* ln_colsum, int ln_dim, float ln_eps, void* out_bf16_copy, int ldo2, float* stat_out,
+                     int remap_grid, int remap_grid_pad, svb_stream_t stream);
+/* Derive the folded operands of `LayerNorm(gamma, beta) -> Linear(W [N,K], bias)` from fp32 masters (device pointers):
+ * Wg bf16 [N,K] = gamma (.) W, colsum [N] = row sums of Wg, bias_f [N] = bias + W beta. */
+int svb_fold_layernorm(const float* W, const float* bias, const float* gamma, const float* beta, void* Wg_bf16, float* colsum,
+                       float* bias_f, int N, int K, svb_stream_t stream);
 /* remap_grid > 0: output row r (token order, grid x grid per image) is stored at the token's row of the window-padded
  * grid_pad x grid_pad layout — window_partition's F.pad (image_encoder.py:271-275) expressed as a store address. */
 /* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype.  With `add` (rows x dim, element

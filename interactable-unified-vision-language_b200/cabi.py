@@ -40,6 +40,8 @@ SYMBOLS = {
     "svb_encoder_enable_taps": (_i, [_vp, _i]),
     "svb_encoder_read_tap": (_i, [_vp, _i, _vp, _i64, _vp]),
     "svb_linear": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp]),
+    "svb_linear_fused": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _f, _vp, _i, _vp, _i, _i, _vp]),
+    "svb_fold_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "svb_attention_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_attention_tc_phases": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "svb_rel_pack_rows": (_i, [_i, _i]),

@@ -45,6 +45,19 @@ struct Epilogue {
     // optional output-row remap (token grid g x g -> padded grid gp x gp, the window_partition padding of
     // image_encoder.py:271-275 expressed as a store address): out row = (r / g^2) * gp^2 + ((r % g^2) / g) * gp + r % g
     int remap_g = 0, remap_gp = 0;
+    // ---- LayerNorm folded into the GEMM (bf16 path; tcgen05 pair kernel only) ----
+    // consumer side: A holds the UN-normalised rows x (bf16), W = bf16(gamma (.) W0), bias = b0 + W0 beta; with the row
+    // statistics mu, rstd of x:  LayerNorm(x) W0^T + b0 = rstd * (x W^T - mu * ln_c) + bias,  ln_c[n] = sum_k W[n, k].
+    // ln_stats = [M][ln_parts] partial (sum, sum of squares) of each row of x over ln_dim columns (written by the producer).
+    const float2* ln_stats = nullptr;
+    const float* ln_c = nullptr;     // [N]
+    int ln_parts = 0, ln_dim = 0;
+    float ln_eps = 0.f;
+    // producer side (fp32 output + residual): a bf16 copy of the final rows (the next GEMM's A operand) and the partial
+    // row statistics of the final rows: stat_out[row][(column / 128)] = (sum, sumsq) over that 128-column slab.
+    void* out2 = nullptr;            // bf16 [M, ldo2]
+    int ldo2 = 0;
+    float2* stat_out = nullptr;      // [M][ceil(N / 128)]
 };
 __host__ __device__ __forceinline__ size_t epilogue_out_row(const Epilogue& ep, int row) {
     if (ep.remap_g == 0) return (size_t)row;
@@ -202,5 +215,10 @@ int pack_cast(const float* src, void* dst, bool dst_bf16, long n, cudaStream_t s
 int pack_convT(const float* w /*Cin,Cout,2,2*/, void* dst /*[4*Cout, Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
 int pack_conv2x2(const float* w /*Cout,Cin,2,2*/, void* dst /*[Cout, 4*Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
 int pack_bias4(const float* b, float* dst, int C, cudaStream_t s);
+// LayerNorm -> Linear fold (see Epilogue::ln_stats): Wg bf16 [N,K], colsum [N], bias_f [N] from the fp32 masters
+int fold_layernorm(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wg, float* colsum, float* bias_f, int N,
+                   int K, cudaStream_t s);
+// true when gemm_bf16_tc dispatches to the CTA-pair kernel (the only one implementing the folded-LayerNorm epilogues)
+bool gemm_bf16_tc_supports_fold();
 
 }  // namespace svb

@@ -272,6 +272,28 @@ __global__ void pack_bias4_kernel(const float* __restrict__ b, float* __restrict
     if (i < 4 * C) d[i] = b[i % C];
 }
 
+// LayerNorm folded into the following Linear (bf16 path):  LN(x) W^T + b = rstd (x Wg^T - mu c) + bf  with
+//   Wg[n,k] = bf16(gamma[k] W[n,k]),  c[n] = sum_k Wg[n,k] (of the ROUNDED values: the mean term then cancels exactly),
+//   bf[n] = b[n] + sum_k beta[k] W[n,k].   One warp per output row n.
+__global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, bf16* __restrict__ Wg, float* __restrict__ c, float* __restrict__ bfold,
+                               int N, int K) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float sc = 0.f, sb = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[(size_t)n * K + k];
+        const bf16 wg = __float2bfloat16_rn(w * gamma[k]);
+        Wg[(size_t)n * K + k] = wg;
+        sc += __bfloat162float(wg);
+        sb = fmaf(beta[k], w, sb);
+    }
+    sc = warp_sum(sc);
+    sb = warp_sum(sb);
+    if (lane == 0) { c[n] = sc; bfold[n] = (bias ? bias[n] : 0.f) + sb; }
+}
+
 inline int grid_for(size_t n, int block) {
     size_t gsz = (n + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -427,6 +449,12 @@ int pack_conv2x2(const float* w, void* dst, bool dst_bf16, int Cin, int Cout, cu
     const long n = (long)4 * Cin * Cout;
     if (dst_bf16) pack_conv2x2_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(w, (bf16*)dst, Cin, Cout);
     else pack_conv2x2_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(w, (float*)dst, Cin, Cout);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int fold_layernorm(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wg, float* colsum, float* bias_f, int N,
+                   int K, cudaStream_t s) {
+    fold_ln_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(W, bias, gamma, beta, Wg, colsum, bias_f, N, K);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

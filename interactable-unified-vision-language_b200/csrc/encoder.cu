@@ -30,6 +30,8 @@ struct Param {
     int a = 0, b = 0;           // kind-specific dims: GEMM_W (N,K); CONVT_W (Cin,Cout); CONV22_W (Cin,Cout); CONVT_B (C)
     float* f32 = nullptr;       // packed fp32 copy (all kinds)
     bf16* b16 = nullptr;        // packed bf16 copy (GEMM operands)
+    float* fold_c = nullptr;    // LayerNorm-fold column sums / folded bias (qkv and lin1 weights, bf16 path): see Epilogue::ln_stats
+    float* fold_b = nullptr;
     bool loaded = false;
 };
 
@@ -56,6 +58,8 @@ struct svb_encoder {
     bool taps_enabled = false;
     float* taps = nullptr;          // [(depth+1)][T*D] fp32, first image of the last chunk
     int attn_impl_bf16 = 0;         // 0: SIMT kernel, 1: tcgen05 kernel
+    bool ln_fold = false;           // bf16 path: norm1 / norm2 folded into the qkv / lin1 GEMMs (no LayerNorm pass over HBM)
+    bool fold_dirty = true;         // a parameter was (re)loaded since the folded weights were last derived
     int grid_pad = 0;               // window-padded token grid (70 for 64 / 14)
     std::vector<bf16*> relpack;     // per block: bf16 rel-pos table block of the tcgen05 attention kernel (attention_tc.cu)
     // host path resources
@@ -98,6 +102,12 @@ int alloc_param_storage(Param& p) {
     return 0;
 }
 
+int alloc_fold_storage(Param& p) {
+    SVB_CHECK_CUDA(cudaMalloc(&p.fold_c, sizeof(float) * p.a));
+    SVB_CHECK_CUDA(cudaMalloc(&p.fold_b, sizeof(float) * p.a));
+    return 0;
+}
+
 struct Buffers {
     void *A0, *Xn, *QKV, *O, *Hid;
     float* X;
@@ -105,6 +115,7 @@ struct Buffers {
     void *Xb, *A32, *Gn, *G2n;
     float *G, *G2, *G3;
     double* stats;
+    float2 *st1, *st2;          // LayerNorm-fold partial row statistics of the residual stream (norm1 / norm2 inputs)
     size_t total;
 };
 
@@ -118,6 +129,9 @@ Buffers plan(const svb_encoder* e, int chunk, int mode, void* base) {
     ar.base = (char*)base;
     b.X = (float*)ar.alloc(M * D * 4);
     b.stats = (double*)ar.alloc(sizeof(double) * 2 * 8 * chunk);
+    const size_t parts = (size_t)(D + 127) / 128;
+    b.st1 = (float2*)ar.alloc(M * parts * sizeof(float2));
+    b.st2 = (float2*)ar.alloc(M * parts * sizeof(float2));
     const size_t mark = ar.off;
     b.A0 = ar.alloc(M * kpe * es);
     b.Xn = ar.alloc(M * D * es);
@@ -157,6 +171,35 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     const int M = B * T;
     const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
     int rc;
+    // bf16 path: norm1 / norm2 are folded into the qkv / lin1 GEMMs.  Every GEMM that writes the fp32 residual stream X
+    // (patch embedding, proj, lin2) also writes bf16(X) and the partial row sums of X; the consuming GEMM normalises in its
+    // epilogue (Epilogue::ln_stats).  The fp32 validation mode keeps the explicit LayerNorm kernels.
+    const bool fold = h && e->ln_fold;
+    const int parts = (D + 127) / 128;
+    if (fold && e->fold_dirty) {
+        for (int i = 0; i < e->depth; ++i) {
+            const std::string p = "blocks." + std::to_string(i) + ".";
+            for (int k = 0; k < 2; ++k) {
+                const Param& W = e->P(p + (k ? "mlp.lin1.weight" : "attn.qkv.weight"));
+                const Param& bW = e->P(p + (k ? "mlp.lin1.bias" : "attn.qkv.bias"));
+                const std::string nk = p + (k ? "norm2." : "norm1.");
+                if ((rc = fold_layernorm(W.f32, bW.f32, e->P(nk + "weight").f32, e->P(nk + "bias").f32, W.b16, W.fold_c, W.fold_b, W.a, W.b, st)))
+                    return rc;
+            }
+        }
+        e->fold_dirty = false;
+    }
+    auto produce = [&](Epilogue& ep, float2* stat) {      // epilogue of a GEMM that writes the residual stream
+        ep.out = bf.X; ep.ldo = D;
+        if (fold) { ep.out2 = bf.Xn; ep.ldo2 = D; ep.stat_out = stat; }
+    };
+    auto consume = [&](Epilogue& ep, const Param& W, const Param& b, const float2* stat) {   // epilogue of qkv / lin1
+        if (fold) {
+            ep.bias = W.fold_b; ep.ln_c = W.fold_c; ep.ln_stats = stat; ep.ln_parts = parts; ep.ln_dim = D; ep.ln_eps = e->cfg.ln_eps;
+        } else {
+            ep.bias = b.f32;
+        }
+    };
     // ---- PatchEmbed (image_encoder.py:402-410) + pos_embed (:109-114), fused in the GEMM epilogue ----
     if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size, e->cfg.patch_size, st))) return rc;
     {
@@ -165,8 +208,7 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         ep.resid = e->P("pos_embed").f32;
         ep.resid_mod = T;
         ep.ldr = D;
-        ep.out = bf.X;
-        ep.ldo = D;
+        produce(ep, bf.st1);
         if ((rc = linear(mode, bf.A0, kpe, e->P("patch_embed.proj.weight"), M, D, kpe, ep, st))) return rc;
     }
     if (e->taps_enabled) SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
@@ -174,21 +216,22 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     // ---- Blocks (image_encoder.py:181-197) ----
     for (int i = 0; i < e->depth; ++i) {
         const std::string p = "blocks." + std::to_string(i) + ".";
-        if ((rc = layernorm_rows(bf.X, nullptr, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D, e->cfg.ln_eps, st)))
+        if (!fold && (rc = layernorm_rows(bf.X, nullptr, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D,
+                                          e->cfg.ln_eps, st)))
             return rc;
         const int ws = e->is_global(i) ? g : e->cfg.window_size;
         const bool tc = h && e->attn_impl_bf16 == 1;
         const bool padded = tc && ws != g;      // windowed blocks of the tcgen05 path keep qkv on the padded 70x70 grid
         {   // qkv (image_encoder.py:242)
             Epilogue ep;
-            ep.bias = e->P(p + "attn.qkv.bias").f32;
+            consume(ep, e->P(p + "attn.qkv.weight"), e->P(p + "attn.qkv.bias"), bf.st1);
             ep.out = bf.QKV;
             ep.out_bf16 = h;
             ep.ldo = 3 * D;
             if (padded) { ep.remap_g = g; ep.remap_gp = e->grid_pad; }
             if ((rc = linear(mode, bf.Xn, D, e->P(p + "attn.qkv.weight"), M, 3 * D, D, ep, st))) return rc;
-            // pad tokens are zero after norm1 (image_encoder.py:183-187,271-275): their qkv rows are the bias
-            if (padded && (rc = fill_pad_rows((bf16*)bf.QKV, ep.bias, B, g, e->grid_pad, 3 * D, st))) return rc;
+            // pad tokens are zero after norm1 (image_encoder.py:183-187,271-275): their qkv rows are the (unfolded) bias
+            if (padded && (rc = fill_pad_rows((bf16*)bf.QKV, e->P(p + "attn.qkv.bias").f32, B, g, e->grid_pad, 3 * D, st))) return rc;
         }
         {   // windowed / global attention with decomposed rel-pos (image_encoder.py:246-253, 258-304, 340-376)
             if (tc) {
@@ -207,29 +250,36 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
                 if ((rc = attention_simt(ap, h, st))) return rc;
             }
         }
-        {   // proj (image_encoder.py:253).  Its output stays in the activation dtype; the shortcut add x = shortcut + x
-            // (:194) is fused into the norm2 kernel below, which is HBM-bound anyway — the fp32 read-modify-write of the
-            // residual stream in this short-K GEMM's epilogue was slower than its MMAs.
+        if (fold) {
+            // proj (image_encoder.py:253) + shortcut add (:194) in place on X; bf16(X) and the row sums for norm2 come with it
+            Epilogue ep;
+            ep.bias = e->P(p + "attn.proj.bias").f32;
+            ep.resid = bf.X; ep.ldr = D;
+            produce(ep, bf.st2);
+            if ((rc = linear(mode, bf.O, D, e->P(p + "attn.proj.weight"), M, D, D, ep, st))) return rc;
+        } else {
+            // proj (image_encoder.py:253).  Its output stays in the activation dtype; the shortcut add x = shortcut + x (:194) is
+            // fused into the norm2 kernel below, which is HBM-bound anyway.
             Epilogue ep;
             ep.bias = e->P(p + "attn.proj.bias").f32;
             ep.out = bf.Xn; ep.out_bf16 = h; ep.ldo = D;
             if ((rc = linear(mode, bf.O, D, e->P(p + "attn.proj.weight"), M, D, D, ep, st))) return rc;
+            // x += proj(attn);  O = norm2(x)   (image_encoder.py:194-195).  O is free again and receives the normalised rows.
+            if ((rc = layernorm_rows(bf.X, bf.Xn, e->P(p + "norm2.weight").f32, e->P(p + "norm2.bias").f32, bf.O, h, M, D, e->cfg.ln_eps, st)))
+                return rc;
         }
-        // x += proj(attn);  Xn = norm2(x)   (image_encoder.py:194-195).  O is free again and receives the normalised rows.
-        if ((rc = layernorm_rows(bf.X, bf.Xn, e->P(p + "norm2.weight").f32, e->P(p + "norm2.bias").f32, bf.O, h, M, D, e->cfg.ln_eps, st)))
-            return rc;
         {   // MLPBlock lin1 + GELU (common.py:25-26)
             Epilogue ep;
-            ep.bias = e->P(p + "mlp.lin1.bias").f32;
+            consume(ep, e->P(p + "mlp.lin1.weight"), e->P(p + "mlp.lin1.bias"), bf.st2);
             ep.act = 1;
             ep.out = bf.Hid; ep.out_bf16 = h; ep.ldo = e->mlp;
-            if ((rc = linear(mode, bf.O, D, e->P(p + "mlp.lin1.weight"), M, e->mlp, D, ep, st))) return rc;
+            if ((rc = linear(mode, fold ? bf.Xn : bf.O, D, e->P(p + "mlp.lin1.weight"), M, e->mlp, D, ep, st))) return rc;
         }
         {   // lin2 + residual (image_encoder.py:195)
             Epilogue ep;
             ep.bias = e->P(p + "mlp.lin2.bias").f32;
             ep.resid = bf.X; ep.ldr = D;
-            ep.out = bf.X; ep.ldo = D;
+            produce(ep, bf.st1);
             if ((rc = linear(mode, bf.Hid, e->mlp, e->P(p + "mlp.lin2.weight"), M, D, e->mlp, ep, st))) return rc;
         }
         if (e->taps_enabled)
@@ -384,6 +434,22 @@ int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
         int rc = alloc_param_storage(kv.second);
         if (rc) { svb_encoder_destroy(e); return rc; }
     }
+    // LayerNorm folding (bf16 path): needs whole 32-column epilogue chunks and the CTA-pair GEMM.  Opt-in with SVB_LN_FOLD=1
+    // until the producer-side epilogue (fp32 read-modify-write + bf16 copy + row sums) is as lean as the streamlined ones:
+    // measured 175 us for proj with it against 83 us + 76 us (proj + norm2 kernel) without.
+    {
+        const char* env = getenv("SVB_LN_FOLD");
+        e->ln_fold = (D % 32 == 0) && gemm_bf16_tc_supports_fold() && (env && atoi(env) == 1);
+        if (e->ln_fold) {
+            for (int i = 0; i < e->depth; ++i) {
+                const std::string b = "blocks." + std::to_string(i) + ".";
+                for (const char* k : {"attn.qkv.weight", "mlp.lin1.weight"}) {
+                    int rc = alloc_fold_storage(e->params[b + k]);
+                    if (rc) { svb_encoder_destroy(e); return rc; }
+                }
+            }
+        }
+    }
     // tcgen05 attention covers the geometry _build_sam instantiates (64x64 grid, 14x14 windows, head_dim 64 / 80);
     // anything else runs the SIMT kernel.  SVB_ATTN_IMPL=0 forces the SIMT kernel (bisecting aid).
     e->grid_pad = ((e->grid + cfg->window_size - 1) / cfg->window_size) * cfg->window_size;
@@ -410,6 +476,8 @@ void svb_encoder_destroy(svb_encoder_t* e) {
     for (auto& kv : e->params) {
         if (kv.second.f32) cudaFree(kv.second.f32);
         if (kv.second.b16) cudaFree(kv.second.b16);
+        if (kv.second.fold_c) cudaFree(kv.second.fold_c);
+        if (kv.second.fold_b) cudaFree(kv.second.fold_b);
     }
     if (e->taps) cudaFree(e->taps);
     for (bf16* r : e->relpack)
@@ -466,6 +534,7 @@ int svb_encoder_load_param(svb_encoder_t* e, const char* key, const float* data,
     }
     if (rc) return rc;
     p.loaded = true;
+    e->fold_dirty = true;       // the folded qkv / lin1 operands are re-derived from the fp32 masters at the next bf16 forward
     return 0;
 }
 
@@ -605,6 +674,36 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
     if (mode == SVB_MODE_BF16) return gemm_bf16_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
     if (mode == SVB_MODE_FP32) return gemm_f32_simt((const float*)A, lda, (const float*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
     SVB_REQUIRE(false, "svb_linear: bad mode %d", mode);
+}
+
+int svb_linear_fused(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
+                     const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, const float* ln_stats,
+                     const float* ln_colsum, int ln_dim, float ln_eps, void* out_bf16_copy, int ldo2, float* stat_out,
+                     int remap_grid, int remap_grid_pad, svb_stream_t stream) {
+    SVB_REQUIRE(A && W && out, "svb_linear_fused: null argument");
+    Epilogue ep;
+    ep.bias = bias;
+    ep.act = act_gelu ? 1 : 0;
+    ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
+    ep.out = out; ep.out_bf16 = out_dtype == SVB_DTYPE_BF16; ep.ldo = ldo;
+    if (ln_stats) {
+        ep.ln_stats = reinterpret_cast<const float2*>(ln_stats); ep.ln_c = ln_colsum; ep.ln_dim = ln_dim; ep.ln_parts = (ln_dim + 127) / 128;
+        ep.ln_eps = ln_eps;
+    }
+    ep.out2 = out_bf16_copy; ep.ldo2 = ldo2;
+    ep.stat_out = reinterpret_cast<float2*>(stat_out);
+    if (remap_grid > 0) {
+        SVB_REQUIRE(remap_grid_pad >= remap_grid && M % (remap_grid * remap_grid) == 0,
+                    "svb_linear_fused: row remap needs M to be a multiple of grid^2 and grid_pad >= grid");
+        ep.remap_g = remap_grid; ep.remap_gp = remap_grid_pad;
+    }
+    return gemm_bf16_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
+}
+
+int svb_fold_layernorm(const float* W, const float* bias, const float* gamma, const float* beta, void* Wg_bf16, float* colsum,
+                       float* bias_f, int N, int K, svb_stream_t stream) {
+    SVB_REQUIRE(W && gamma && beta && Wg_bf16 && colsum && bias_f, "svb_fold_layernorm: null argument");
+    return fold_layernorm(W, bias, gamma, beta, (bf16*)Wg_bf16, colsum, bias_f, N, K, (cudaStream_t)stream);
 }
 
 int svb_layernorm(float* x, const void* add, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim, float eps,

@@ -195,20 +195,28 @@ EncodeTiledFn get_encode_fn() {
 }  // namespace
 
 // 2-D bf16 row-major [rows, inner] with leading dimension ld (elements): box = [box_rows, box_inner], 128B swizzle
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
+                 uint32_t box_rows, int swizzle_bytes);
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
                       uint32_t box_rows, int swizzle_bytes) {
+    return make_tmap_2d(map, ptr, 2, inner, rows, ld, box_inner, box_rows, swizzle_bytes);
+}
+
+// elem_bytes 2 = bf16, 4 = fp32
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
+                 uint32_t box_rows, int swizzle_bytes) {
     EncodeTiledFn fn = get_encode_fn();
     SVB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
     cuuint64_t dims[2] = {inner, rows};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * (cuuint64_t)elem_bytes};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                             : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                   : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SVB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)", (int)r,
                 (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld);
@@ -269,6 +277,12 @@ static int launch_gemm(const bf16* A, int lda, const bf16* W, int ldw, int M, in
 
 int gemm_bf16_tc_pair(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
 
+static int gemm_impl() {
+    static const int impl = [] { const char* e = getenv("SVB_GEMM_IMPL"); return e ? atoi(e) : 2; }();
+    return impl;
+}
+bool gemm_bf16_tc_supports_fold() { return gemm_impl() != 1; }
+
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep,
                  cudaStream_t stream) {
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16_tc: empty problem M=%d N=%d K=%d", M, N, K);
@@ -278,8 +292,16 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     SVB_REQUIRE((ep.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm_bf16_tc: output must be 16-byte aligned");
     SVB_REQUIRE(!ep.stats || (ep.rows_per_sample % 32) == 0, "gemm_bf16_tc: rows_per_sample must be a multiple of 32");
     // CTA-pair kernel (gemm_tc2.cu) by default; SVB_GEMM_IMPL=1 selects the single-CTA kernel below (A/B comparisons)
-    static const int impl = [] { const char* e = getenv("SVB_GEMM_IMPL"); return e ? atoi(e) : 2; }();
-    if (impl != 1) return gemm_bf16_tc_pair(A, lda, W, ldw, M, N, K, ep, stream);
+    const bool fold = ep.ln_stats || ep.out2 || ep.stat_out;
+    if (fold) {
+        SVB_REQUIRE(gemm_impl() != 1, "gemm_bf16_tc: the folded-LayerNorm epilogues need the CTA-pair kernel (unset SVB_GEMM_IMPL)");
+        SVB_REQUIRE(N % 32 == 0, "gemm_bf16_tc: folded-LayerNorm epilogues need N %% 32 == 0 (N = %d)", N);
+        SVB_REQUIRE(!ep.ln_stats || (ep.ln_c && ep.bias && ep.ln_parts > 0 && ep.ln_dim > 0), "gemm_bf16_tc: incomplete LayerNorm-fold arguments");
+        SVB_REQUIRE(!(ep.out2 || ep.stat_out) || (ep.resid && !ep.out_bf16 && ep.remap_g == 0),
+                    "gemm_bf16_tc: the bf16 copy / row statistics outputs need the fp32 residual epilogue");
+        SVB_REQUIRE(!ep.out2 || ((ep.ldo2 % 4) == 0 && (reinterpret_cast<uintptr_t>(ep.out2) & 7) == 0), "gemm_bf16_tc: out2 must be 8-byte aligned");
+    }
+    if (gemm_impl() != 1) return gemm_bf16_tc_pair(A, lda, W, ldw, M, N, K, ep, stream);
     if (N <= 128) return launch_gemm<128>(A, lda, W, ldw, M, N, K, ep, stream);
     return launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);
 }

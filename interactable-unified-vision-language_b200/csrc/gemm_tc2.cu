@@ -27,6 +27,8 @@
 namespace svb {
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
                       uint32_t box_rows, int swizzle_bytes);
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
+                 uint32_t box_rows, int swizzle_bytes);
 int num_sms();
 
 namespace {
@@ -42,7 +44,7 @@ template <int BN> struct Cfg2 {
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 5 : 6;
-    static constexpr int BIAS_BYTES = 2 * BN * 4;                 // per accumulator stage: the tile's BN bias values
+    static constexpr int BIAS_BYTES = 2 * 2 * BN * 4;             // per accumulator stage: the tile's BN bias values + BN LayerNorm-fold column sums
     static constexpr int EPI_BYTES = EPI_WARPS * 4096;            // per epilogue warp: one 32 x 32 fp32 transpose tile
     static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
     static constexpr int OFF_BIAS = OFF_BARS + 256;
@@ -233,10 +235,34 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int r0 = m0 + quad * 32;                    // first row of this warp's 32-row slab
             const int row = r0 + lane;
             const bool row_ok = row < M;
+            if (dbg & 8) {                                    // measurement aid: MMA-only rate (no epilogue work, output not written)
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tmem_empty[as]), lead));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+                continue;
+            }
             // ---- while the MMAs of this tile run: stage the tile's bias in smem, start the residual loads ----
-            float* bs = bias_s + as * BN;
+            float* bs = bias_s + as * 2 * BN;
+            float* cs = bs + BN;
             if (ep.bias) {
                 for (int c = etid; c < BN; c += EPI_WARPS * 32) bs[c] = (nt0 + c < N) ? __ldg(ep.bias + nt0 + c) : 0.f;
+            }
+            // LayerNorm fold (consumer): this row's mu / rstd from the producer's partial sums, the tile's column sums in smem
+            float ln_nmu = 0.f, ln_r = 1.f;
+            if (ep.ln_stats) {
+                for (int c = etid; c < BN; c += EPI_WARPS * 32) cs[c] = (nt0 + c < N) ? __ldg(ep.ln_c + nt0 + c) : 0.f;
+                if (row_ok) {
+                    float s1 = 0.f, s2 = 0.f;
+                    const float2* sp = ep.ln_stats + (size_t)row * ep.ln_parts;
+                    for (int p = 0; p < ep.ln_parts; ++p) { const float2 t = __ldg(sp + p); s1 += t.x; s2 += t.y; }
+                    const float inv = 1.0f / (float)ep.ln_dim;
+                    const float mu = s1 * inv;
+                    ln_r = rsqrtf(fmaxf(s2 * inv - mu * mu, 0.f) + ep.ln_eps);
+                    ln_nmu = -mu;
+                }
             }
             // residual in the COALESCED mapping of the write-out: instruction i covers rows 4i..4i+3, lane -> (row 4i + lane/8,
             // 16-byte piece lane%8); two chunks in flight
@@ -259,6 +285,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // bias visible to all epilogue warps
             const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
+            const uint32_t csm = ptx::smem_u32(cs + half * (BN / 2));
+            float rs_sum = 0.f, rs_sq = 0.f;                  // producer side: this lane's row (r0 + 4 (lane & 7) + (lane >> 3)) statistics
             ptx::mbar_wait(&tmem_full[as], aphase);
             ptx::tc_fence_after();
             float s_sum = 0.f, s_sq = 0.f;
@@ -288,7 +316,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (ep.bias) {
+                if (ep.ln_stats) {                            // v = rstd * (acc - mu * c) + bias'
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b, cc;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cc.x), "=f"(cc.y), "=f"(cc.z), "=f"(cc.w) : "r"(csm + c * 128 + 16 * j));
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bsm + c * 128 + 16 * j));
+                        v[4 * j + 0] = fmaf(ln_r, fmaf(ln_nmu, cc.x, v[4 * j + 0]), b.x);
+                        v[4 * j + 1] = fmaf(ln_r, fmaf(ln_nmu, cc.y, v[4 * j + 1]), b.y);
+                        v[4 * j + 2] = fmaf(ln_r, fmaf(ln_nmu, cc.z, v[4 * j + 2]), b.z);
+                        v[4 * j + 3] = fmaf(ln_r, fmaf(ln_nmu, cc.w, v[4 * j + 3]), b.w);
+                    }
+                } else if (ep.bias) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 b;
@@ -334,6 +373,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                      "f"(v[4 * j + 3]) : "memory");
                     }
                     __syncwarp();
+                    float st_s[RESID ? 8 : 1], st_q[RESID ? 8 : 1];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {             // instruction i: rows 4i..4i+3, 8 lanes (128 B) per row
                         const int rr = 4 * i + (lane >> 3), pc = lane & 7;
@@ -341,12 +381,46 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                                      : "r"(tile_s + rr * 128 + ((pc ^ (rr & 7)) << 4)));
                         const int gr = r0 + rr;
-                        if (gr < M) {
-                            if constexpr (RESID) {
+                        if constexpr (RESID) {
+                            if (gr < M) {
                                 const float4 r = q[c & 1][i];
                                 x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
                             }
+                            st_s[i] = (x.x + x.y) + (x.z + x.w);
+                            st_q[i] = fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+                        }
+                        if (gr < M) {
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + epilogue_out_row(ep, gr) * ep.ldo + col0 + pc * 4) = x;
+                            if constexpr (RESID) {
+                                if (ep.out2) {                // bf16 copy of the final rows: the next GEMM's A operand
+                                    uint2 u;
+                                    u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w);
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out2) + (size_t)gr * ep.ldo2 + col0 + pc * 4) = u;
+                                }
+                            }
+                        }
+                    }
+                    if constexpr (RESID) {
+                        if (ep.stat_out) {
+                            // 8 rows x 8 lanes -> one row per lane: butterfly over the 8 lanes of a row group (7 shuffles per
+                            // quantity); lane with piece index p ends up with row-instruction i = p
+                            const int p = lane & 7;
+                            float a4[4], b4[4], a2[2], b2[2];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float ss = (p & 4) ? st_s[k] : st_s[k + 4], sq = (p & 4) ? st_q[k] : st_q[k + 4];
+                                a4[k] = ((p & 4) ? st_s[k + 4] : st_s[k]) + __shfl_xor_sync(0xffffffffu, ss, 4);
+                                b4[k] = ((p & 4) ? st_q[k + 4] : st_q[k]) + __shfl_xor_sync(0xffffffffu, sq, 4);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const float ss = (p & 2) ? a4[k] : a4[k + 2], sq = (p & 2) ? b4[k] : b4[k + 2];
+                                a2[k] = ((p & 2) ? a4[k + 2] : a4[k]) + __shfl_xor_sync(0xffffffffu, ss, 2);
+                                b2[k] = ((p & 2) ? b4[k + 2] : b4[k]) + __shfl_xor_sync(0xffffffffu, sq, 2);
+                            }
+                            const float ss = (p & 1) ? a2[0] : a2[1], sq = (p & 1) ? b2[0] : b2[1];
+                            rs_sum += ((p & 1) ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, ss, 1);
+                            rs_sq += ((p & 1) ? b2[1] : b2[0]) + __shfl_xor_sync(0xffffffffu, sq, 1);
                         }
                     }
                     __syncwarp();
@@ -358,6 +432,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(map_to_cta(ptx::smem_u32(&tmem_empty[as]), lead));
+            if constexpr (RESID) {
+                if (ep.stat_out && n0 < N) {
+                    const int gr = r0 + 4 * (lane & 7) + (lane >> 3);
+                    if (gr < M) ep.stat_out[(size_t)gr * ((N + 127) / 128) + n0 / 128] = make_float2(rs_sum, rs_sq);
+                }
+            }
             if (ep.stats) {
                 s_sum = warp_sum(s_sum);
                 s_sq = warp_sum(s_sq);
@@ -373,6 +453,312 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     ptx::tc_fence_before();
     cluster_sync_all();                                       // the peer may still be reading our smem / signalling our barriers
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// =====================================================================================================================
+// Streamlined kernel: same TMA / tcgen05 main loop, lean epilogue.
+//
+// Measured on B200 (tools/gemm_bench.py, ViT-H shapes, 8 images): with the epilogue switched off the main loop runs at
+// 1640 TF/s, with the generic epilogue above at 1350 TF/s; ncu of the generic kernel showed 15.6 K SASS instructions,
+// ~2600 executed per warp and tile (row predicates, per-row address / remap arithmetic, constant reloads) and 35 % of the
+// warp stalls on instruction fetch.  Here each epilogue warp does, per 32-column chunk: tcgen05.ld -> packed fp32x2 math
+// with the thread's own row (bias or the folded LayerNorm, GELU, GroupNorm sums) -> 4 or 8 swizzled 16-byte shared stores
+// into a [32 rows x 32 columns] staging box -> ONE lane issues a TMA store (or a TMA f32 reduce-add for the in-place
+// residual `X += ...` of lin2), which also clips the M / N edges.  No per-row address arithmetic, no row predicates,
+// no second pass through registers.
+//   MODE 1: bf16 output (qkv, lin1, proj; neck GEMMs feeding another GEMM)      box 32 x 64 B, 64-byte swizzle
+//   MODE 2: fp32 output (neck GEMMs with GroupNorm statistics)                   box 32 x 128 B, 128-byte swizzle
+//   MODE 3: fp32 reduce-add into the output (out += acc + bias: lin2 residual)   same box, cp.reduce.async.bulk .add.f32
+enum { EPI_BF16 = 1, EPI_F32 = 2, EPI_F32_REDADD = 3 };
+
+template <int BN, int MODE> struct Cfg3 {
+    static constexpr bool OUTF32 = MODE != EPI_BF16;
+    static constexpr int A_BYTES = BM_CTA * BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int CHUNK_BYTES = OUTF32 ? 4096 : 2048;       // one staging box: 32 rows x 32 columns
+    static constexpr int EPI_BYTES = EPI_WARPS * 2 * CHUNK_BYTES;  // two boxes per epilogue warp
+    static constexpr int STAGES = (BN == 256) ? (OUTF32 ? 4 : 5) : 6;
+    static constexpr int BIAS_BYTES = 2 * 2 * BN * 4;
+    static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BIAS = OFF_BARS + 256;
+    static constexpr int OFF_EPI = OFF_BIAS + BIAS_BYTES + (1024 - (256 + BIAS_BYTES) % 1024) % 1024;
+    static constexpr int SMEM_BYTES = OFF_EPI + EPI_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+template <int BN, int CL, int MODE, bool GELU, bool LNF>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_o, int M, int N, int K, Epilogue ep, int dbg) {
+    using C = Cfg3<BN, MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = smem_raw + (base_u32 - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::OFF_BARS);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + C::STAGES;
+    uint64_t* tmem_full = bars + 2 * C::STAGES;
+    uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* bias_s = reinterpret_cast<float*>(tiles + C::OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr int PAIRS = CL / 2;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1, pidx = crank >> 1, lead = crank & ~1u;
+    const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;
+    const int num_m = (M + 2 * BM_CTA * PAIRS - 1) / (2 * BM_CTA * PAIRS);
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&map_a);
+        ptx::prefetch_tmap(&map_w);
+        ptx::prefetch_tmap(&map_o);
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], PAIRS);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 2 * EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    ptx::tc_fence_before();
+    cluster_sync_all();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (every CTA) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
+                const int n0 = (t % num_n) * BN + rank * (BN / 2) + pidx * (BN / 2 / PAIRS);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+                    uint8_t* sb = sa + C::A_BYTES;
+                    const uint32_t full_leader = map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
+                    if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                    tma_load_2d_pair(sa, &map_a, full_leader, kb * BK, m0);
+                    if constexpr (PAIRS == 1) {
+                        tma_load_2d_pair(sb, &map_w, full_leader, kb * BK, n0);
+                    } else {
+                        uint16_t mask = 0;
+#pragma unroll
+                        for (int q = 0; q < PAIRS; ++q) mask |= (uint16_t)(1u << (2 * q + rank));
+                        tma_load_2d_pair_mc(sb + pidx * (C::B_BYTES / PAIRS), &map_w, full_leader, kb * BK, n0, mask);
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (pair leader) =====================
+        if (rank == 0 && lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM_CTA, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                ptx::mbar_wait(&tmem_empty[as], aphase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = base_u32 + stage * C::STAGE_BYTES;
+                    const uint32_t sb = sa + C::A_BYTES;
+                    const uint64_t da = ptx::make_smem_desc(sa, 0, 1024, ptx::LAYOUT_SW128);
+                    const uint64_t db = ptx::make_smem_desc(sb, 0, 1024, ptx::LAYOUT_SW128);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    mma_commit_pair(&empty_bar[stage], (uint16_t)((1u << CL) - 1));
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit_pair(&tmem_full[as], (uint16_t)(3u << lead));
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of every CTA) =====================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 64;
+        const int etid = threadIdx.x - 64;
+        const uint32_t stg = base_u32 + C::OFF_EPI + (warp - 2) * (2 * C::CHUNK_BYTES);
+        // this lane's row of a staging box: 16-byte piece j lives at piece j ^ swz (TMA 64-byte / 128-byte swizzle)
+        const uint32_t srow = stg + lane * (C::OUTF32 ? 128 : 64);
+        const uint32_t swz = C::OUTF32 ? (lane & 7) : ((lane >> 1) & 3);
+        const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * (BN / 2);
+        const uint32_t empty_leader = map_to_cta(ptx::smem_u32(&tmem_empty[0]), lead);
+        const int rps = ep.rows_per_sample;
+        int as = 0;
+        uint32_t aphase = 0;
+        uint32_t sbuf = 0;                                    // staging box in use (alternates per chunk, across tiles)
+        for (int t = pair; t < num_tiles; t += num_pairs) {
+            const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
+            const int nt0 = (t % num_n) * BN;
+            const int n0 = nt0 + half * (BN / 2);
+            const int r0 = m0 + quad * 32;
+            const int row = r0 + lane;
+            const bool row_ok = row < M;
+            // ---- while this tile's MMAs run: stage its bias (and LayerNorm-fold column sums), fetch the row statistics ----
+            float* bs = bias_s + as * 2 * BN;
+            float* cs = bs + BN;
+            for (int c = etid; c < BN; c += EPI_WARPS * 32) bs[c] = (ep.bias && nt0 + c < N) ? __ldg(ep.bias + nt0 + c) : 0.f;
+            float ln_nmu = 0.f, ln_r = 1.f;
+            if constexpr (LNF) {
+                for (int c = etid; c < BN; c += EPI_WARPS * 32) cs[c] = (nt0 + c < N) ? __ldg(ep.ln_c + nt0 + c) : 0.f;
+                if (row_ok) {
+                    float s1 = 0.f, s2 = 0.f;
+                    const float2* sp = ep.ln_stats + (size_t)row * ep.ln_parts;
+                    for (int p = 0; p < ep.ln_parts; ++p) { const float2 q = __ldg(sp + p); s1 += q.x; s2 += q.y; }
+                    const float inv = 1.0f / (float)ep.ln_dim;
+                    const float mu = s1 * inv;
+                    ln_r = rsqrtf(fmaxf(s2 * inv - mu * mu, 0.f) + ep.ln_eps);
+                    ln_nmu = -mu;
+                }
+            }
+            const int orow0 = (int)epilogue_out_row(ep, r0);  // a 32-row slab is contiguous in the (window-padded) output too
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
+            const uint32_t csm = ptx::smem_u32(cs + half * (BN / 2));
+            ptx::mbar_wait(&tmem_full[as], aphase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_lane + as * BN;
+            float s_sum = 0.f, s_sq = 0.f;
+            uint32_t ra[32], rb[32];
+            const bool slab = (r0 < M) && (n0 < N) && !(dbg & 8);
+            bool released = false;
+            if (slab) ptx::tmem_ld_x32(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col0 = n0 + c * 32;
+                if (!slab || col0 >= N) break;
+                uint32_t (&raw)[32] = *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? rb : ra);
+                ptx::tmem_ld_wait_dep(raw);
+                if (c + 1 < NCH && col0 + 32 < N) {
+                    ptx::tmem_ld_x32(taddr + (c + 1) * 32, *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? ra : rb));
+                } else {
+                    // the last TMEM read of this warp has completed: release the accumulator stage before the math / store
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(empty_leader + as * 8);
+                    released = true;
+                }
+                // ---- this thread's row, 32 columns: bias / folded LayerNorm, GroupNorm sums, GELU (packed fp32x2) ----
+                f32x2 v[16];
+                const f32x2 nm2 = f2_pack(ln_nmu, ln_nmu), r2 = f2_pack(ln_r, ln_r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = lds128(bsm + c * 128 + 16 * j);
+                    f32x2 x0 = f2_pack(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]));
+                    f32x2 x1 = f2_pack(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                    if constexpr (LNF) {
+                        const float4 cc = lds128(csm + c * 128 + 16 * j);
+                        x0 = f2_fma(r2, f2_fma(nm2, f2_pack(cc.x, cc.y), x0), f2_pack(b.x, b.y));
+                        x1 = f2_fma(r2, f2_fma(nm2, f2_pack(cc.z, cc.w), x1), f2_pack(b.z, b.w));
+                    } else {
+                        x0 = f2_add(x0, f2_pack(b.x, b.y));
+                        x1 = f2_add(x1, f2_pack(b.z, b.w));
+                    }
+                    v[2 * j] = x0; v[2 * j + 1] = x1;
+                }
+                if (MODE == EPI_F32 && ep.stats && row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a, b;
+                        f2_unpack(v[j], a, b);
+                        s_sum += a + b;
+                        s_sq = fmaf(a, a, fmaf(b, b, s_sq));
+                    }
+                }
+                if constexpr (GELU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a, b;
+                        f2_unpack(v[j], a, b);
+                        gelu_pair(a, b);
+                        v[j] = f2_pack(a, b);
+                    }
+                }
+                // ---- stage the box, hand it to the TMA ----
+                const uint32_t box = stg + sbuf * C::CHUNK_BYTES;
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this box is done
+                __syncwarp();
+                const uint32_t rowa = srow + sbuf * C::CHUNK_BYTES;
+                if constexpr (C::OUTF32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowa + ((j ^ swz) << 4)), "l"(v[2 * j]), "l"(v[2 * j + 1]) : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a0, a1, a2, a3, a4, a5, a6, a7;
+                        f2_unpack(v[4 * j], a0, a1); f2_unpack(v[4 * j + 1], a2, a3);
+                        f2_unpack(v[4 * j + 2], a4, a5); f2_unpack(v[4 * j + 3], a6, a7);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + ((j ^ swz) << 4)), "r"(pack_bf16x2(a0, a1)),
+                                     "r"(pack_bf16x2(a2, a3)), "r"(pack_bf16x2(a4, a5)), "r"(pack_bf16x2(a6, a7)) : "memory");
+                    }
+                }
+                ptx::fence_proxy_async_smem();                // generic-proxy writes -> visible to the TMA read
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (MODE == EPI_F32_REDADD) tma_reduce_add_2d(&map_o, box, col0, orow0);
+                    else tma_store_2d(&map_o, box, col0, orow0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                sbuf ^= 1;
+            }
+            if (!released) {                                  // nothing to read for this slab (outside M / N)
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(empty_leader + as * 8);
+            }
+            if (MODE == EPI_F32 && ep.stats) {
+                s_sum = warp_sum(s_sum);
+                s_sq = warp_sum(s_sq);
+                if (lane == 0 && slab) {
+                    const int sample = r0 / rps;
+                    atomicAdd(ep.stats + 2 * sample, (double)s_sum);
+                    atomicAdd(ep.stats + 2 * sample + 1, (double)s_sq);
+                }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
+    }
+
+    ptx::tc_fence_before();
+    cluster_sync_all();
     if (warp == 1) {
         ptx::tc_fence_after();
         tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
@@ -417,6 +803,75 @@ int launch_gemm2_cl(const CUtensorMap& ma, const CUtensorMap& mw, int M, int N, 
     return 0;
 }
 
+template <int BN, int MODE, bool GELU, bool LNF>
+int launch_gemm2s(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, int M, int N, int K, const Epilogue& ep,
+                  cudaStream_t stream) {
+    using C = Cfg3<BN, MODE>;
+    constexpr int CL = 2;
+    auto kern = gemm_tc2s_kernel<BN, CL, MODE, GELU, LNF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = ((M + BM_CTA * CL - 1) / (BM_CTA * CL)) * ((N + BN - 1) / BN);
+    const int clusters = std::min(tiles, num_sms() / CL);
+    static const int dbg = [] { const char* e = getenv("SVB_GEMM2_DBG"); return e ? atoi(e) : 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const double out_bytes = (MODE == EPI_BF16 ? 2.0 : (MODE == EPI_F32 ? 4.0 : 8.0)) * M * N;
+    ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + out_bytes, stream);
+    SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, M, N, K, ep, dbg));
+    return 0;
+}
+
+// The streamlined kernel covers: bf16 output without residual (bias or folded LayerNorm, optional GELU, optional row remap),
+// fp32 output without residual (optional GroupNorm statistics), and the in-place fp32 residual out += acc + bias.
+// Everything else (broadcast residual of the patch embedding, the LayerNorm-fold producer outputs) runs the generic kernel.
+template <int BN>
+int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
+                           bool* done) {
+    *done = false;
+    static const int off = [] { const char* e = getenv("SVB_GEMM_EPI"); return e ? atoi(e) == 0 : 0; }();   // SVB_GEMM_EPI=0: generic epilogue only
+    if (off || ep.out2 || ep.stat_out) return 0;
+    int mode = 0;
+    if (ep.out_bf16) {
+        if (ep.resid || ep.stats) return 0;
+        mode = EPI_BF16;
+    } else {
+        if (ep.act || ep.ln_stats || ep.remap_g) return 0;
+        if (!ep.resid) mode = EPI_F32;
+        else if (ep.resid == ep.out && ep.ldr == ep.ldo && ep.resid_mod == 0 && !ep.stats) mode = EPI_F32_REDADD;
+        else return 0;
+    }
+    if (ep.remap_g && ((ep.remap_g % 32) != 0 || (M % (ep.remap_g * ep.remap_g)) != 0)) return 0;
+    const int esz = ep.out_bf16 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(ep.out) & 15) != 0 || ((size_t)ep.ldo * esz) % 16 != 0) return 0;
+    CUtensorMap ma, mw, mo;
+    int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2, 128);
+    if (rc) return rc;
+    const uint64_t out_rows = ep.remap_g ? (uint64_t)(M / (ep.remap_g * ep.remap_g)) * ep.remap_gp * ep.remap_gp : (uint64_t)M;
+    rc = make_tmap_2d(&mo, ep.out, esz, (uint64_t)N, out_rows, (uint64_t)ep.ldo, 32, 32, ep.out_bf16 ? 64 : 128);
+    if (rc) return rc;
+    *done = true;
+    const bool lnf = ep.ln_stats != nullptr, gelu = ep.act == 1;
+    if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false>(ma, mw, mo, M, N, K, ep, stream);
+    if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false>(ma, mw, mo, M, N, K, ep, stream);
+    if (gelu && lnf) return launch_gemm2s<BN, EPI_BF16, true, true>(ma, mw, mo, M, N, K, ep, stream);
+    if (gelu) return launch_gemm2s<BN, EPI_BF16, true, false>(ma, mw, mo, M, N, K, ep, stream);
+    if (lnf) return launch_gemm2s<BN, EPI_BF16, false, true>(ma, mw, mo, M, N, K, ep, stream);
+    return launch_gemm2s<BN, EPI_BF16, false, false>(ma, mw, mo, M, N, K, ep, stream);
+}
+
 template <int BN>
 int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
     // SVB_GEMM_CLUSTER = 2 (default): one CTA pair per cluster; 4: two pairs sharing the weight tile by TMA multicast.
@@ -424,6 +879,11 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     // 8.9 TF/s/SM) but only 33 clusters of 4 are co-resident (132 of 148 SMs: GPCs of 18 SMs hold 4 such clusters), so the
     // whole GEMM is 4 % slower (1268 vs 1316 TF/s).
     static const int cl = [] { const char* e = getenv("SVB_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
+    if (cl != 4) {
+        bool done = false;
+        const int rc0 = try_launch_streamlined<BN>(A, lda, W, ldw, M, N, K, ep, stream, &done);
+        if (rc0 || done) return rc0;
+    }
     const int pairs = (cl == 4 && M > 2 * BM_CTA) ? 2 : 1;
     CUtensorMap ma, mw;
     int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
@@ -441,7 +901,8 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
 }  // namespace
 
 int gemm_bf16_tc_pair(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
-    if (N <= 128) return launch_gemm2<128>(A, lda, W, ldw, M, N, K, ep, stream);
+    // (the row-statistics output is laid out in 128-column slabs = one epilogue warp of the BN = 256 tile)
+    if (N <= 128 && !ep.stat_out) return launch_gemm2<128>(A, lda, W, ldw, M, N, K, ep, stream);
     return launch_gemm2<256>(A, lda, W, ldw, M, N, K, ep, stream);
 }
 

@@ -92,6 +92,73 @@ def test_gemm_tcgen05_epilogues(out_dtype):
         assert torch.allclose(stats, s_ref, rtol=1e-5, atol=1e-2), (stats, s_ref)
 
 
+def _linear_fused(A, W, bias, out, gelu=False, resid=None, resid_mod=0, ln=None, out2=None, stat_out=None, remap=(0, 0)):
+    M, K = A.shape
+    N = W.shape[0]
+    ln_stats, ln_c, ln_dim, ln_eps = ln if ln is not None else (None, None, 0, 0.0)
+    rc = cabi.lib().svb_linear_fused(
+        A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, cabi.ptr(bias), int(gelu), cabi.ptr(resid),
+        resid.stride(0) if resid is not None else 0, resid_mod, out.data_ptr(),
+        cabi.DTYPE_BF16 if out.dtype == torch.bfloat16 else cabi.DTYPE_F32, out.stride(0), cabi.ptr(ln_stats), cabi.ptr(ln_c), ln_dim,
+        ln_eps, cabi.ptr(out2), out2.stride(0) if out2 is not None else 0, cabi.ptr(stat_out), remap[0], remap[1], cabi.stream_ptr())
+    cabi.check(rc, "svb_linear_fused")
+    return out
+
+
+@pytest.mark.parametrize("M,D,Kp", [(4096, 1280, 256), (8192, 768, 3072), (1000, 160, 64), (512, 128, 128), (4096, 1024, 1024)])
+def test_gemm_layernorm_fold(M, D, Kp):
+    """norm -> Linear folded into the GEMMs of the bf16 path: the producer GEMM (residual epilogue) emits bf16(x) and partial
+    row sums of x; the consumer GEMM computes act(LayerNorm(x) W^T + b) from the un-normalised bf16 rows.
+    Reference: fp64 LayerNorm + Linear of the fp32 x (image_encoder.py:183,195 + common.py:25)."""
+    g = torch.Generator(device="cpu").manual_seed(M + D + Kp)
+    parts = (D + 127) // 128
+    # ---- producer: x = x0 + A Wp^T + bp ----
+    A = torch.randn(M, Kp, generator=g).to(DEV).bfloat16()
+    Wp = (torch.randn(D, Kp, generator=g) / math.sqrt(Kp)).to(DEV).bfloat16()
+    bp = torch.randn(D, generator=g).to(DEV)
+    x0 = (torch.randn(M, D, generator=g) * 2 + 0.7).to(DEV)
+    x = x0.clone()
+    xb = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    stat = torch.full((M, parts, 2), float("nan"), device=DEV)
+    _linear_fused(A, Wp, bp, x, resid=x, out2=xb, stat_out=stat)
+    torch.cuda.synchronize()
+    ref_x, _ = _ref_linear(A, Wp, bp, resid=x0)
+    assert ib.rel_l2(x, ref_x) < 1e-5
+    assert torch.equal(xb, x.bfloat16())                      # the bf16 copy is the rounded fp32 stream
+    pad = parts * 128 - D
+    xs = torch.nn.functional.pad(x.double(), (0, pad)).reshape(M, parts, 128)
+    s_ref = torch.stack([xs.sum(-1), (xs ** 2).sum(-1)], -1)
+    assert torch.allclose(stat.double(), s_ref, rtol=2e-5, atol=1e-3), (stat[0], s_ref[0])
+    # ---- consumer: y = gelu(LayerNorm(x) W^T + b) ----
+    N = 3 * D
+    W = (torch.randn(N, D, generator=g) / math.sqrt(D)).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(D, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(D, generator=g)).to(DEV)
+    Wg = torch.empty(N, D, dtype=torch.bfloat16, device=DEV)
+    csum, bf = torch.empty(N, device=DEV), torch.empty(N, device=DEV)
+    cabi.check(cabi.lib().svb_fold_layernorm(W.data_ptr(), b.data_ptr(), gamma.data_ptr(), beta.data_ptr(), Wg.data_ptr(), csum.data_ptr(),
+                                             bf.data_ptr(), N, D, cabi.stream_ptr()), "fold")
+    assert torch.equal(Wg, (W * gamma).bfloat16())
+    assert torch.allclose(csum.double(), Wg.double().sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bf.double(), b.double() + W.double() @ beta.double(), rtol=1e-5, atol=1e-5)
+    ln_ref = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-6)
+    for gelu in (False, True):
+        y = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        _linear_fused(xb, Wg, bf, y, gelu=gelu, ln=(stat, csum, D, 1e-6))
+        ref = ln_ref @ W.double().t() + b.double()
+        if gelu:
+            ref = torch.nn.functional.gelu(ref)
+        err = ib.rel_l2(y, ref)
+        # same error class as the unfused path (bf16 rounding of the normalised rows instead of the raw rows)
+        xn = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+        cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), None, gamma.data_ptr(), beta.data_ptr(), xn.data_ptr(), cabi.DTYPE_BF16, M, D,
+                                            1e-6, cabi.stream_ptr()), "ln")
+        y2 = _linear(cabi.MODE_BF16, xn, W.bfloat16(), bias=b, gelu=gelu, out_dtype=torch.bfloat16)
+        err2 = ib.rel_l2(y2, ref)
+        assert err < 6e-3 and err < 1.5 * err2 + 1e-3, (err, err2)
+
+
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (4096, 768, 768), (200, 136, 72), (1024, 128, 320)])
 def test_gemm_fp32_simt(M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
