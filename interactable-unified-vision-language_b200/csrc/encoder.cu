@@ -434,12 +434,11 @@ int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
         int rc = alloc_param_storage(kv.second);
         if (rc) { svb_encoder_destroy(e); return rc; }
     }
-    // LayerNorm folding (bf16 path): needs whole 32-column epilogue chunks and the CTA-pair GEMM.  Opt-in with SVB_LN_FOLD=1
-    // until the producer-side epilogue (fp32 read-modify-write + bf16 copy + row sums) is as lean as the streamlined ones:
-    // measured 175 us for proj with it against 83 us + 76 us (proj + norm2 kernel) without.
+    // LayerNorm folding (bf16 path): needs whole 32-column epilogue chunks and the CTA-pair GEMM.  SVB_LN_FOLD=0 keeps the
+    // explicit LayerNorm kernels (A/B comparisons: 96.0 vs 99.7 ms per 16 ViT-H images on the same box).
     {
         const char* env = getenv("SVB_LN_FOLD");
-        e->ln_fold = (D % 32 == 0) && gemm_bf16_tc_supports_fold() && (env && atoi(env) == 1);
+        e->ln_fold = (D % 32 == 0) && gemm_bf16_tc_supports_fold() && !(env && atoi(env) == 0);
         if (e->ln_fold) {
             for (int i = 0; i < e->depth; ++i) {
                 const std::string b = "blocks." + std::to_string(i) + ".";

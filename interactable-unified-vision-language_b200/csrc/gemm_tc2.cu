@@ -473,16 +473,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 //   MODE 1: bf16 output (qkv, lin1, proj; neck GEMMs feeding another GEMM)      box 32 x 64 B, 64-byte swizzle
 //   MODE 2: fp32 output (neck GEMMs with GroupNorm statistics)                   box 32 x 128 B, 128-byte swizzle
 //   MODE 3: fp32 reduce-add into the output (out += acc + bias: lin2 residual)   same box, cp.reduce.async.bulk .add.f32
-enum { EPI_BF16 = 1, EPI_F32 = 2, EPI_F32_REDADD = 3 };
+//   MODE 4: LayerNorm-fold producer: out = out + acc + bias in place (fp32), plus a bf16 copy of the new rows and their
+//           partial row sums.  The residual box is FETCHED by TMA into the staging box (two boxes per warp, the first two
+//           chunks of a tile prefetched while its MMAs run), each thread adds its own row in place (so the row sums are
+//           thread-local), and both the fp32 box and a bf16 box go back out by TMA store.
+enum { EPI_BF16 = 1, EPI_F32 = 2, EPI_F32_REDADD = 3, EPI_F32_RMW = 4 };
 
-template <int BN, int MODE> struct Cfg3 {
+template <int BN, int MODE, bool ONEBOX = false> struct Cfg3 {
     static constexpr bool OUTF32 = MODE != EPI_BF16;
+    static constexpr int NBOX = ONEBOX ? 1 : 2;
     static constexpr int A_BYTES = BM_CTA * BK * 2;
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int CHUNK_BYTES = OUTF32 ? 4096 : 2048;       // one staging box: 32 rows x 32 columns
-    static constexpr int EPI_BYTES = EPI_WARPS * 2 * CHUNK_BYTES;  // two boxes per epilogue warp
-    static constexpr int STAGES = (BN == 256) ? (OUTF32 ? 4 : 5) : 6;
+    static constexpr int WARP_EPI_BYTES = NBOX * CHUNK_BYTES + (MODE == 4 ? 2048 : 0);   // boxes per epilogue warp (+ one bf16 box)
+    static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
+    static constexpr int STAGES = (BN == 256) ? ((OUTF32 && !ONEBOX) ? 4 : 5) : 6;
     static constexpr int BIAS_BYTES = 2 * 2 * BN * 4;
     static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
     static constexpr int OFF_BIAS = OFF_BARS + 256;
@@ -499,17 +505,22 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
 
-template <int BN, int CL, int MODE, bool GELU, bool LNF>
+template <int BN, int CL, int MODE, bool GELU, bool LNF, bool ONEBOX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_o, int M, int N, int K, Epilogue ep, int dbg) {
-    using C = Cfg3<BN, MODE>;
+                 const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_o2, int M, int N, int K,
+                 Epilogue ep, int dbg) {
+    using C = Cfg3<BN, MODE, ONEBOX>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* tiles = smem_raw + (base_u32 - ptx::smem_u32(smem_raw));
@@ -519,7 +530,9 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tmem_full = bars + 2 * C::STAGES;
     uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* rbar = bars + 2 * C::STAGES + 5;       // MODE 4: [epilogue warp][2] "residual box landed"
     float* bias_s = reinterpret_cast<float*>(tiles + C::OFF_BIAS);
+    static_assert((2 * C::STAGES + 5 + (MODE == 4 ? 2 * EPI_WARPS : 0)) * 8 <= 256, "barrier block overflows");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -536,6 +549,10 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::prefetch_tmap(&map_a);
         ptx::prefetch_tmap(&map_w);
         ptx::prefetch_tmap(&map_o);
+        if constexpr (MODE == EPI_F32_RMW) {
+            ptx::prefetch_tmap(&map_o2);
+            for (int s = 0; s < 2 * EPI_WARPS; ++s) ptx::mbar_init(&rbar[s], 1);
+        }
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], PAIRS);
@@ -613,7 +630,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int half = (warp - 2) >> 2;
         constexpr int NCH = BN / 64;
         const int etid = threadIdx.x - 64;
-        const uint32_t stg = base_u32 + C::OFF_EPI + (warp - 2) * (2 * C::CHUNK_BYTES);
+        const uint32_t stg = base_u32 + C::OFF_EPI + (warp - 2) * C::WARP_EPI_BYTES;
         // this lane's row of a staging box: 16-byte piece j lives at piece j ^ swz (TMA 64-byte / 128-byte swizzle)
         const uint32_t srow = stg + lane * (C::OUTF32 ? 128 : 64);
         const uint32_t swz = C::OUTF32 ? (lane & 7) : ((lane >> 1) & 3);
@@ -623,6 +640,124 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int as = 0;
         uint32_t aphase = 0;
         uint32_t sbuf = 0;                                    // staging box in use (alternates per chunk, across tiles)
+        if constexpr (MODE == EPI_F32_RMW) {
+            uint64_t* mybar = rbar + 2 * (warp - 2);
+            uint8_t* stg_g = tiles + C::OFF_EPI + (warp - 2) * C::WARP_EPI_BYTES;      // generic address of the two fp32 boxes
+            const uint32_t hbox = stg + C::NBOX * C::CHUNK_BYTES;                      // the bf16 box
+            const uint32_t hrow = hbox + lane * 64;
+            const uint32_t hswz = (lane >> 1) & 3;
+            uint32_t rph = 0;                                 // parity bits of the two residual barriers
+            const int parts = (N + 127) / 128;
+            for (int t = pair; t < num_tiles; t += num_pairs) {
+                const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
+                const int nt0 = (t % num_n) * BN;
+                const int n0 = nt0 + half * (BN / 2);
+                const int r0 = m0 + quad * 32;
+                const bool slab = (r0 < M) && (n0 < N) && !(dbg & 8);
+                const int nch = slab ? min(NCH, (N - n0 + 31) / 32) : 0;      // chunks of this slab (N % 32 == 0)
+                // ---- while this tile's MMAs run: fetch the residual boxes of the first two chunks, stage the bias ----
+                if (lane == 0) {
+                    if (nch > 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // last tile's stores have left the boxes
+                        for (int c = 0; c < C::NBOX && c < nch; ++c) {
+                            ptx::mbar_expect_tx(&mybar[c], C::CHUNK_BYTES);
+                            ptx::tma_load_2d(stg_g + c * C::CHUNK_BYTES, &map_o, &mybar[c], n0 + 32 * c, r0);
+                        }
+                    }
+                    if (dbg & 16) {                           // experiment: L2 prefetch of the later chunks / the next tile's rows
+                        for (int c = 2; c < nch; ++c) tma_prefetch_l2_2d(&map_o, n0 + 32 * c, r0);
+                        const int tn = t + num_pairs;
+                        if (tn < num_tiles) {
+                            const int rn = ((tn / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA + quad * 32;
+                            const int nn = (tn % num_n) * BN + half * (BN / 2);
+                            if (rn < M)
+                                for (int c = 0; c < NCH && nn + 32 * c < N; ++c) tma_prefetch_l2_2d(&map_o, nn + 32 * c, rn);
+                        }
+                    }
+                }
+                float* bs = bias_s + as * 2 * BN;
+                for (int c = etid; c < BN; c += EPI_WARPS * 32) bs[c] = (ep.bias && nt0 + c < N) ? __ldg(ep.bias + nt0 + c) : 0.f;
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
+                ptx::mbar_wait(&tmem_full[as], aphase);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_lane + as * BN;
+                f32x2 st_s = f2_pack(0.f, 0.f), st_q = st_s;  // this thread's row: sum / sum of squares (two interleaved lanes)
+                uint32_t ra[32], rb[32];
+                bool released = false;
+                if (nch > 0) ptx::tmem_ld_x32(taddr, ra);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (c >= nch) break;
+                    const int col0 = n0 + c * 32;
+                    uint32_t (&raw)[32] = *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? rb : ra);
+                    ptx::tmem_ld_wait_dep(raw);
+                    if (c + 1 < nch) {
+                        ptx::tmem_ld_x32(taddr + (c + 1) * 32, *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? ra : rb));
+                    } else {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(empty_leader + as * 8);
+                        released = true;
+                    }
+                    const uint32_t b = c % C::NBOX;
+                    ptx::mbar_wait(&mybar[b], (rph >> b) & 1);                 // the residual box of this chunk has landed
+                    rph ^= 1u << b;
+                    const uint32_t rowa = srow + b * C::CHUNK_BYTES;
+                    f32x2 v[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bb = lds128(bsm + c * 128 + 16 * j);
+                        const float4 rr = lds128(rowa + ((j ^ swz) << 4));
+                        f32x2 x0 = f2_pack(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]));
+                        f32x2 x1 = f2_pack(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                        x0 = f2_add(f2_add(x0, f2_pack(bb.x, bb.y)), f2_pack(rr.x, rr.y));
+                        x1 = f2_add(f2_add(x1, f2_pack(bb.z, bb.w)), f2_pack(rr.z, rr.w));
+                        st_s = f2_add(st_s, f2_add(x0, x1));
+                        st_q = f2_fma(x0, x0, f2_fma(x1, x1, st_q));
+                        v[2 * j] = x0; v[2 * j + 1] = x1;
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bf16 box is free again
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowa + ((j ^ swz) << 4)), "l"(v[2 * j]), "l"(v[2 * j + 1]) : "memory");
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a0, a1, a2, a3, a4, a5, a6, a7;
+                        f2_unpack(v[4 * j], a0, a1); f2_unpack(v[4 * j + 1], a2, a3);
+                        f2_unpack(v[4 * j + 2], a4, a5); f2_unpack(v[4 * j + 3], a6, a7);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((j ^ hswz) << 4)), "r"(pack_bf16x2(a0, a1)),
+                                     "r"(pack_bf16x2(a2, a3)), "r"(pack_bf16x2(a4, a5)), "r"(pack_bf16x2(a6, a7)) : "memory");
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_o, stg + b * C::CHUNK_BYTES, col0, r0);
+                        if (ep.out2) tma_store_2d(&map_o2, hbox, col0, r0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        if (c + C::NBOX < nch) {              // refill this box with the residual of chunk c + NBOX
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            ptx::mbar_expect_tx(&mybar[b], C::CHUNK_BYTES);
+                            ptx::tma_load_2d(stg_g + b * C::CHUNK_BYTES, &map_o, &mybar[b], col0 + 32 * C::NBOX, r0);
+                        }
+                    }
+                }
+                if (!released) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(empty_leader + as * 8);
+                }
+                if (ep.stat_out && nch > 0 && r0 + lane < M) {
+                    float s0, s1, q0, q1;
+                    f2_unpack(st_s, s0, s1);
+                    f2_unpack(st_q, q0, q1);
+                    ep.stat_out[(size_t)(r0 + lane) * parts + n0 / 128] = make_float2(s0 + s1, q0 + q1);
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else
         for (int t = pair; t < num_tiles; t += num_pairs) {
             const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
             const int nt0 = (t % num_n) * BN;
@@ -712,7 +847,10 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 // ---- stage the box, hand it to the TMA ----
                 const uint32_t box = stg + sbuf * C::CHUNK_BYTES;
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this box is done
+                if (lane == 0) {                              // the store that last read this box is done
+                    if constexpr (ONEBOX) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
                 __syncwarp();
                 const uint32_t rowa = srow + sbuf * C::CHUNK_BYTES;
                 if constexpr (C::OUTF32) {
@@ -736,7 +874,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     else tma_store_2d(&map_o, box, col0, orow0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                sbuf ^= 1;
+                if constexpr (!ONEBOX) sbuf ^= 1;
             }
             if (!released) {                                  // nothing to read for this slab (outside M / N)
                 ptx::tc_fence_before();
@@ -803,12 +941,12 @@ int launch_gemm2_cl(const CUtensorMap& ma, const CUtensorMap& mw, int M, int N, 
     return 0;
 }
 
-template <int BN, int MODE, bool GELU, bool LNF>
-int launch_gemm2s(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, int M, int N, int K, const Epilogue& ep,
-                  cudaStream_t stream) {
-    using C = Cfg3<BN, MODE>;
+template <int BN, int MODE, bool GELU, bool LNF, bool ONEBOX = false>
+int launch_gemm2s(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mo, const CUtensorMap& mo2, int M, int N, int K,
+                  const Epilogue& ep, cudaStream_t stream) {
+    using C = Cfg3<BN, MODE, ONEBOX>;
     constexpr int CL = 2;
-    auto kern = gemm_tc2s_kernel<BN, CL, MODE, GELU, LNF>;
+    auto kern = gemm_tc2s_kernel<BN, CL, MODE, GELU, LNF, ONEBOX>;
     static bool attr_set = false;
     if (!attr_set) {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -826,9 +964,9 @@ int launch_gemm2s(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMa
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    const double out_bytes = (MODE == EPI_BF16 ? 2.0 : (MODE == EPI_F32 ? 4.0 : 8.0)) * M * N;
+    const double out_bytes = (MODE == EPI_BF16 ? 2.0 : (MODE == EPI_F32 ? 4.0 : (MODE == EPI_F32_REDADD ? 8.0 : 10.0))) * M * N;
     ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + out_bytes, stream);
-    SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, M, N, K, ep, dbg));
+    SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, mo2, M, N, K, ep, dbg));
     return 0;
 }
 
@@ -840,9 +978,16 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
                            bool* done) {
     *done = false;
     static const int off = [] { const char* e = getenv("SVB_GEMM_EPI"); return e ? atoi(e) == 0 : 0; }();   // SVB_GEMM_EPI=0: generic epilogue only
-    if (off || ep.out2 || ep.stat_out) return 0;
+    if (off) return 0;
     int mode = 0;
-    if (ep.out_bf16) {
+    if (ep.out2 || ep.stat_out) {
+        // LayerNorm-fold producer: in-place fp32 residual + bf16 copy + row sums (BN = 256 only: 128-column slabs)
+        if (BN != 256 || ep.out_bf16 || ep.resid != ep.out || ep.ldr != ep.ldo || ep.resid_mod || ep.stats || ep.act || ep.ln_stats ||
+            ep.remap_g || (N % 32) != 0)
+            return 0;
+        if (ep.out2 && ((reinterpret_cast<uintptr_t>(ep.out2) & 15) != 0 || (ep.ldo2 % 8) != 0)) return 0;
+        mode = EPI_F32_RMW;
+    } else if (ep.out_bf16) {
         if (ep.resid || ep.stats) return 0;
         mode = EPI_BF16;
     } else {
@@ -862,14 +1007,35 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     const uint64_t out_rows = ep.remap_g ? (uint64_t)(M / (ep.remap_g * ep.remap_g)) * ep.remap_gp * ep.remap_gp : (uint64_t)M;
     rc = make_tmap_2d(&mo, ep.out, esz, (uint64_t)N, out_rows, (uint64_t)ep.ldo, 32, 32, ep.out_bf16 ? 64 : 128);
     if (rc) return rc;
+    CUtensorMap mo2 = mo;
+    if (mode == EPI_F32_RMW && ep.out2) {
+        rc = make_tmap_2d(&mo2, ep.out2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo2, 32, 32, 64);
+        if (rc) return rc;
+    }
     *done = true;
     const bool lnf = ep.ln_stats != nullptr, gelu = ep.act == 1;
-    if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false>(ma, mw, mo, M, N, K, ep, stream);
-    if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false>(ma, mw, mo, M, N, K, ep, stream);
-    if (gelu && lnf) return launch_gemm2s<BN, EPI_BF16, true, true>(ma, mw, mo, M, N, K, ep, stream);
-    if (gelu) return launch_gemm2s<BN, EPI_BF16, true, false>(ma, mw, mo, M, N, K, ep, stream);
-    if (lnf) return launch_gemm2s<BN, EPI_BF16, false, true>(ma, mw, mo, M, N, K, ep, stream);
-    return launch_gemm2s<BN, EPI_BF16, false, false>(ma, mw, mo, M, N, K, ep, stream);
+    if constexpr (BN == 256) {
+        // producer mode: 5 stages + 1 residual box per warp (default) or 4 stages + 2 boxes.  Measured (interleaved A/B, 8 images):
+        // lin2 351 vs 391 us, proj 133 vs 140 us — the deeper operand ring is worth more than the residual prefetch.
+        // SVB_GEMM_RMW_ONEBOX: 0 never, 1 always (default), 2 when K >= 2048
+        static const int rmw1 = [] { const char* e = getenv("SVB_GEMM_RMW_ONEBOX"); return e ? atoi(e) : 1; }();
+        if (mode == EPI_F32_RMW) {
+            if (rmw1 == 1 || (rmw1 == 2 && K >= 2048)) return launch_gemm2s<BN, EPI_F32_RMW, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+            return launch_gemm2s<BN, EPI_F32_RMW, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
+        }
+    }
+    // fp32 modes: 5 pipeline stages + 1 staging box per warp (default; measured 337 vs 358 us for lin2) or 4 stages + 2 boxes
+    static const int onebox = [] { const char* e = getenv("SVB_GEMM_ONEBOX"); return e ? atoi(e) : 1; }();
+    if (onebox && BN == 256) {
+        if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+        if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    }
+    if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    if (gelu && lnf) return launch_gemm2s<BN, EPI_BF16, true, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    if (gelu) return launch_gemm2s<BN, EPI_BF16, true, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    if (lnf) return launch_gemm2s<BN, EPI_BF16, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    return launch_gemm2s<BN, EPI_BF16, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
 }
 
 template <int BN>

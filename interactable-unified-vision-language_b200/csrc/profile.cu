@@ -4,7 +4,10 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 namespace svb {
@@ -54,15 +57,24 @@ int svb_profile_stop(double* ms, double* flops, double* bytes, int64_t* launches
     std::lock_guard<std::mutex> lk(svb::g_mu);
     svb::g_on = false;
     for (int c = 0; c < svb::PC_COUNT; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+    // SVB_PROF_DETAIL=1: per distinct (category, FLOPs, bytes) — i.e. per GEMM shape / kernel variant — launch count and mean time
+    const bool detail = getenv("SVB_PROF_DETAIL") != nullptr;
+    std::map<std::tuple<int, double, double>, std::pair<int, double>> agg;
     for (auto& r : svb::g_recs) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
             ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat] += 1;
+            if (detail) { auto& a = agg[std::make_tuple(r.cat, r.flops, r.bytes)]; a.first += 1; a.second += t; }
         }
         svb::g_pool.push_back(r.e0);
         svb::g_pool.push_back(r.e1);
     }
     svb::g_recs.clear();
+    for (auto& kv : agg) {
+        const double fl = std::get<1>(kv.first), by = std::get<2>(kv.first), mean = kv.second.second / kv.second.first;
+        fprintf(stderr, "prof cat %d  GFLOP %10.2f  MB %9.2f  n %4d  mean %9.1f us  total %8.2f ms  %7.1f TF/s %7.1f GB/s\n", std::get<0>(kv.first),
+                fl / 1e9, by / 1e6, kv.second.first, mean * 1e3, kv.second.second, fl / mean / 1e9, by / mean / 1e6);
+    }
     return 0;
 }
 int64_t svb_launch_count(void) { return svb::g_launches.load(); }
