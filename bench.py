@@ -39,6 +39,18 @@ def peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def traffic_per_launch(model):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, averaged over the GEMM launches of one
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py from the committed capture); None if absent."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d.get(model, {}).get("gemm_bytes_per_launch_avg")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -141,7 +153,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="vit_h", choices=["vit_b", "vit_l", "vit_h"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
-    ap.add_argument("--chunk", type=int, default=8, help="images per pass through the kernels")
+    ap.add_argument("--chunk", type=int, default=16, help="most images per pass through the kernels (the library splits the batch)")
     ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -263,14 +275,14 @@ def main():
     gemm_tflops = (fl5[0] / (ms5[0] * 1e-3) / 1e12) if ms5[0] > 0 else None
     n_gemm = ln5[0]
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM, all linears + patch-embed + neck convs)",
+        "bound": "tensor", "kernel": "gemm_tc2s_kernel (CTA-pair tcgen05 GEMM: all linears + patch-embed + neck convs)",
         "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
         "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None,
         "frac_of_burst": (gemm_tflops / pk["bf16_burst"]) if gemm_tflops else None,
         "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
         "launches": int(n_gemm), "avg_launch_ms": (ms5[0] / n_gemm) if n_gemm else None,
         "flops_per_launch_avg": (fl5[0] / n_gemm) if n_gemm else None,
-        "traffic": None,
+        "traffic": traffic_per_launch(args.model),
         "profiled_steps": prof_steps, "profiled_ms_per_step": ms_prof_total / prof_steps,
         "step_share": {name: ms5[i] / (ms_prof_total if ms_prof_total else 1) for i, name in
                        enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},

@@ -173,7 +173,7 @@ class ImageEncoderViT(nn.Module):
         # runtime knobs (not part of the reference signature)
         self.precision = "bf16"             # "bf16" (tcgen05) or "fp32" (validation mode)
         self.out_dtype = torch.float32      # dtype of the returned embeddings (float32 or bfloat16)
-        self.max_chunk = 8                  # images per pass through the kernels (bounds the workspace)
+        self.max_chunk = 16                 # most images per pass through the kernels (bounds the workspace, ~0.3 GB per image)
         self._handle: Optional[C.c_void_p] = None
         self._handle_device: Optional[torch.device] = None
         self._weights_sig = None
