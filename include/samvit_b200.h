@@ -67,6 +67,18 @@ size_t svb_encoder_workspace_bytes(const svb_encoder_t* enc, int chunk, int mode
 int svb_encoder_forward(svb_encoder_t* enc, const float* x, int batch, void* res2, void* res3, void* res4, void* res5,
                         int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
 
+/* The same forward fed with what the reference's callers hold BEFORE their eager pre-processing (scope row N2): per image a DEVICE
+ * pointer to a uint8 (C,h,w) tensor, h,w <= img_size.  Replaces `(x - pixel_mean) / pixel_std` + `ImageList.from_tensors(images, 1024)`
+ * (modeling/architectures/xdecoder_model.py:481-484, detectron2 zero padding to the bottom/right) + ImageEncoderViT.forward: the
+ * normalisation and the padding happen inside the patch-embedding loader; no fp32 canvas is materialised.  `images`, `heights`,
+ * `widths`, `pixel_mean`, `pixel_std` are HOST arrays (batch / batch / batch / in_chans / in_chans entries). */
+int svb_encoder_forward_u8(svb_encoder_t* enc, const uint8_t* const* images, const int* heights, const int* widths,
+                           const float* pixel_mean, const float* pixel_std, int batch, void* res2, void* res3, void* res4, void* res5,
+                           int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
+/* The staging step alone: out = patch rows [batch * (img/patch)^2, chans * patch^2] of the normalised, zero-padded canvases. */
+int svb_stage_images_u8(const uint8_t* const* images, const int* heights, const int* widths, int batch, int chans, int img, int patch,
+                        const float* pixel_mean, const float* pixel_std, void* out, int out_dtype, svb_stream_t stream);
+
 /* Same call with HOST buffers (the end-to-end path): copies each chunk's input host->device, runs the forward and
  * copies the four outputs device->host, double-buffered on internal streams; returns after everything completed.
  * Host buffers should be pinned for full PCIe bandwidth. */
@@ -135,6 +147,19 @@ int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma,
                         int64_t rows, int C, int64_t rows_per_sample, float eps, int gelu, svb_stream_t stream);
 int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out,
                              int out_dtype, int batch, int grid, int levels, int C, float eps, int gelu, svb_stream_t stream);
+
+/* ---- scope row N1: the first consumer of res3..res5 (MSDeformAttn pixel decoder) ----
+ * Replaces MSDA.ms_deform_attn_forward, the reference's only native kernel (modeling/vision/encoder/ops/src/cuda/
+ * ms_deform_attn_cuda.cu / ms_deform_im2col_cuda.cuh:242-303), as MSDeformAttnFunction.forward calls it
+ * (ops/functions/ms_deform_attn_func.py:34-40): value (N,S,M,D), sampling_locations (N,Lq,M,L,P,2) in [0,1] (x,y),
+ * attention_weights (N,Lq,M,L,P) -> out (N,Lq,M*D).  `dtype` is the element type of value and out (fp32, or bf16 with fp32
+ * accumulation — the reference kernel is fp32-only); locations and weights are fp32.  `spatial_shapes` ([L][2] = (H,W)) and
+ * `level_start_index` ([L]) are HOST arrays; the levels must tile the S positions.  (The reference's im2col_step batching
+ * argument has no effect on the result and is not needed.) */
+int svb_ms_deform_attn_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                               const float* sampling_locations, const float* attention_weights, void* out, int dtype, int batch,
+                               int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_points,
+                               svb_stream_t stream);
 
 /* ---- measurement helpers (bench.py): launch accounting and a CUDA-event profiler.  Between start and stop every kernel
  * launch of this library is bracketed by events on its launch stream; stop synchronises the device and returns, per

@@ -36,6 +36,8 @@ SYMBOLS = {
     "svb_encoder_missing_params": (_i, [_vp]),
     "svb_encoder_workspace_bytes": (_sz, [_vp, _i, _i]),
     "svb_encoder_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "svb_encoder_forward_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "svb_stage_images_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "svb_encoder_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),
     "svb_encoder_enable_taps": (_i, [_vp, _i]),
     "svb_encoder_read_tap": (_i, [_vp, _i, _vp, _i64, _vp]),
@@ -52,6 +54,7 @@ SYMBOLS = {
     "svb_attention": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _f, _i, _vp]),
+    "svb_ms_deform_attn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_profile_start": (_i, []),
     "svb_profile_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "svb_launch_count": (C.c_int64, []),

@@ -200,6 +200,10 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)
 int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s);
+// uint8 (C,h,w) images -> normalised, zero-padded to img x img, patch rows (the patch-embedding GEMM's A operand); `images`, `hs`,
+// `ws` are HOST arrays (device pointers / sizes per image)
+int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, const float* mean, const float* stdv, void* out, bool out_bf16,
+                   int B, int C, int img, int patch, cudaStream_t s);
 // out = LayerNorm(x [+ add]); when `add` (same element type as out) is given, x += add is written back first (fused residual)
 int layernorm_rows(float* x, const void* add, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s);

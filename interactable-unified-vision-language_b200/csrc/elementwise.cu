@@ -50,6 +50,42 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Input staging fused with the patch im2col (row N2 of the scope table): what the caller of the encoder does per batch —
+// `(x - pixel_mean) / pixel_std` on each uint8 (C,h,w) image, then ImageList.from_tensors(images, 1024): bottom/right zero
+// padding to the 1024 x 1024 canvas (xdecoder_model.py:481-484) — written straight into the patch-embedding GEMM's A operand
+// (rows = patches, cols = (c, ky, kx)).  One thread = 4 consecutive kx of one patch row; the normalised fp32 canvas never exists.
+struct U8Batch {
+    const uint8_t* img[16];
+    int h[16], w[16];
+    float mean[4], std[4];
+};
+template <typename T>
+__global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, int img, int patch) {
+    const int g = img / patch;
+    const int pp = patch * patch;
+    const int K = C * pp;
+    const size_t total4 = (size_t)B * g * g * K / 4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;                      // flat output index (row-major [B*g*g, K]): coalesced stores
+        const int k = (int)(e % K);
+        const size_t row = e / K;
+        const int px = (int)(row % g), py = (int)((row / g) % g), b = (int)(row / ((size_t)g * g));
+        const int c = k / pp, ky = (k % pp) / patch, kx = k % patch;
+        const int y = py * patch + ky, x = px * patch + kx;
+        const int h = bt.h[b], w = bt.w[b];
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y < h) {
+            const uint8_t* src = bt.img[b] + ((size_t)c * h + y) * w + x;
+            const float m = bt.mean[c], sd = bt.std[c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < w) v[j] = __fdiv_rn((float)src[j] - m, sd);
+        }
+        Vec4<T>::store(out + e, v[0], v[1], v[2], v[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (norm1 / norm2, image_encoder.py:166,176; eps 1e-6 from build_sam.py:65).
 // fp32 residual stream in, T out.  One warp per row, row cached in registers, two-pass variance.
 constexpr int LN_MAXV = 16;   // float4 per lane -> D <= 2048
@@ -309,6 +345,30 @@ int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img
     if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img, patch);
     else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img, patch);
     SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, const float* mean, const float* stdv, void* out, bool out_bf16,
+                   int B, int C, int img, int patch, cudaStream_t s) {
+    SVB_REQUIRE(img % patch == 0 && patch % 4 == 0 && C >= 1 && C <= 4, "stage_u8_patch: img %d / patch %d / chans %d unsupported", img, patch, C);
+    const size_t row_elems = (size_t)(img / patch) * (img / patch) * C * patch * patch;
+    for (int b0 = 0; b0 < B; b0 += 16) {
+        const int nb = B - b0 < 16 ? B - b0 : 16;
+        U8Batch bt;
+        for (int i = 0; i < 16; ++i) { bt.img[i] = nullptr; bt.h[i] = 0; bt.w[i] = 0; }
+        for (int i = 0; i < nb; ++i) {
+            SVB_REQUIRE(images[b0 + i] && hs[b0 + i] >= 1 && ws[b0 + i] >= 1 && hs[b0 + i] <= img && ws[b0 + i] <= img,
+                        "stage_u8_patch: image %d is %d x %d; sizes 1..%d are implemented (larger canvases are scope row N3)", b0 + i,
+                        hs[b0 + i], ws[b0 + i], img);
+            bt.img[i] = images[b0 + i]; bt.h[i] = hs[b0 + i]; bt.w[i] = ws[b0 + i];
+        }
+        for (int c = 0; c < 4; ++c) { bt.mean[c] = c < C ? mean[c] : 0.f; bt.std[c] = c < C ? stdv[c] : 1.f; }
+        const size_t total4 = (size_t)nb * row_elems / 4;
+        ProfScope prof(PC_OTHER, 0, (double)nb * C * img * img + (double)total4 * 4 * (out_bf16 ? 2 : 4), s);
+        if (out_bf16) stage_u8_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(bt, (bf16*)out + (size_t)b0 * row_elems, nb, C, img, patch);
+        else stage_u8_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(bt, (float*)out + (size_t)b0 * row_elems, nb, C, img, patch);
+        SVB_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -164,8 +164,17 @@ int linear(int mode, const void* A, int lda, const Param& W, int M, int N, int K
     return gemm_f32_simt((const float*)A, lda, W.f32, K, M, N, K, ep, st);
 }
 
+// raw uint8 input of a chunk (scope row N2): per image a device pointer to (C,h,w) uint8 and its size; normalisation constants
+struct U8Input {
+    const uint8_t* const* images = nullptr;
+    const int* hs = nullptr;
+    const int* ws = nullptr;
+    const float* mean = nullptr;
+    const float* stdv = nullptr;
+};
+
 int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], int out_dtype, int mode, const Buffers& bf,
-                  cudaStream_t st) {
+                  cudaStream_t st, const U8Input* u8 = nullptr) {
     const bool h = (mode == SVB_MODE_BF16);
     const int D = e->D, T = e->T, g = e->grid;
     const int M = B * T;
@@ -201,7 +210,13 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         }
     };
     // ---- PatchEmbed (image_encoder.py:402-410) + pos_embed (:109-114), fused in the GEMM epilogue ----
-    if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size, e->cfg.patch_size, st))) return rc;
+    if (u8) {
+        if ((rc = stage_u8_patch(u8->images, u8->hs, u8->ws, u8->mean, u8->stdv, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size,
+                                 e->cfg.patch_size, st)))
+            return rc;
+    } else if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size, e->cfg.patch_size, st))) {
+        return rc;
+    }
     {
         Epilogue ep;
         ep.bias = e->P("patch_embed.proj.bias").f32;
@@ -612,6 +627,44 @@ int svb_encoder_forward(svb_encoder_t* e, const float* x, int batch, void* res2,
         b0 += B;
     }
     return 0;
+}
+
+int svb_encoder_forward_u8(svb_encoder_t* e, const uint8_t* const* images, const int* heights, const int* widths, const float* pixel_mean,
+                           const float* pixel_std, int batch, void* res2, void* res3, void* res4, void* res5, int out_dtype, int mode,
+                           int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    SVB_REQUIRE(e && images && heights && widths && pixel_mean && pixel_std && res2 && res3 && res4 && res5 && workspace,
+                "svb_encoder_forward_u8: null argument");
+    SVB_REQUIRE(mode == SVB_MODE_BF16 || mode == SVB_MODE_FP32, "svb_encoder_forward_u8: bad mode %d", mode);
+    SVB_REQUIRE(out_dtype == SVB_DTYPE_F32 || out_dtype == SVB_DTYPE_BF16, "svb_encoder_forward_u8: bad out_dtype %d", out_dtype);
+    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward_u8: batch %d / chunk %d must be positive", batch, chunk);
+    const int missing = svb_encoder_missing_params(e);
+    SVB_REQUIRE(missing == 0, "svb_encoder_forward_u8: %d parameters have not been loaded", missing);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    for (int c = 0; c < e->cfg.in_chans; ++c) SVB_REQUIRE(pixel_std[c] != 0.f, "svb_encoder_forward_u8: pixel_std[%d] is zero", c);
+    if (chunk > batch) chunk = batch;
+    const size_t need = plan(e, chunk, mode, nullptr).total;
+    SVB_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    const Buffers bf = plan(e, chunk, mode, workspace);
+    const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
+    char* res[4] = {(char*)res2, (char*)res3, (char*)res4, (char*)res5};
+    int b0 = 0;
+    for (int B : chunk_schedule(e, batch, chunk)) {
+        void* outs[4];
+        for (int k = 0; k < 4; ++k) outs[k] = res[k] + (size_t)b0 * out_elems_per_image(e, k) * osz;
+        U8Input u8;
+        u8.images = images + b0; u8.hs = heights + b0; u8.ws = widths + b0; u8.mean = pixel_mean; u8.stdv = pixel_std;
+        int rc = forward_chunk(e, nullptr, B, outs, out_dtype, mode, bf, (cudaStream_t)stream, &u8);
+        if (rc) return rc;
+        b0 += B;
+    }
+    return 0;
+}
+
+int svb_stage_images_u8(const uint8_t* const* images, const int* heights, const int* widths, int batch, int chans, int img, int patch,
+                        const float* pixel_mean, const float* pixel_std, void* out, int out_dtype, svb_stream_t stream) {
+    SVB_REQUIRE(images && heights && widths && pixel_mean && pixel_std && out, "svb_stage_images_u8: null argument");
+    return stage_u8_patch(images, heights, widths, pixel_mean, pixel_std, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, patch,
+                          (cudaStream_t)stream);
 }
 
 int svb_encoder_forward_host(svb_encoder_t* e, const float* x_host, int batch, void* res2_host, void* res3_host, void* res4_host,

@@ -1,0 +1,163 @@
+// Multi-scale deformable attention, forward sampling core (scope row N1: the first consumer of res3..res5).
+//
+// Restates MSDA.ms_deform_attn_forward — the reference's only native kernel, ms_deformable_im2col_gpu_kernel
+// (modeling/vision/encoder/ops/src/cuda/ms_deform_im2col_cuda.cuh:242-303, bilinear tap :18-69; sm_86 SIMT, fp32 only, one
+// thread per output CHANNEL with scalar loads) — as it is called by MSDeformAttn.forward (ops/modules/ms_deform_attn.py:117-119):
+//   out[n, q, m, :] = sum_{l, p} attn[n, q, m, l, p] * bilinear(value[n, level l, :, m, :], loc[n, q, m, l, p])
+// with grid_sample(align_corners=False, padding_mode='zeros') semantics (ops/functions/ms_deform_attn_func.py:52-72).
+//
+// B200 design: the op is a gather out of `value` (22 MB per 1024^2 image in bf16 at the step1.yaml geometry: 3 levels, 8 heads x 64
+// channels — L2-resident) — bound by L2 -> SM bandwidth, not by math.  One thread owns 16 BYTES of channels (8 bf16 / 4 fp32) of
+// one (n, q, head): the 4 taps of a sample are four 16-byte loads, consecutive threads cover consecutive channels (a 64-channel
+// head = 8 lanes = one 128-byte line per tap), the sampling location / weight loads are warp-broadcast, accumulation is fp32, and
+// bf16 values halve the gather traffic of the reference's fp32-only kernel (which forces the caller to up-cast all levels,
+// transformer_encoder_deform.py:314-345).
+#include "../../include/samvit_b200.h"
+#include "common.cuh"
+
+namespace svb {
+namespace {
+
+constexpr int MSDA_MAX_LEVELS = 8;
+struct MsdaLevels {
+    int h[MSDA_MAX_LEVELS], w[MSDA_MAX_LEVELS], start[MSDA_MAX_LEVELS];
+};
+
+template <typename T> struct Pack16;
+template <> struct Pack16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Pack16<bf16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);               // bf16 -> fp32 is a 16-bit shift
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_forward_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn, T* __restrict__ out,
+                    MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int P) {
+    constexpr int V = Pack16<T>::N;
+    const int groups = D / V;                                     // 16-byte channel groups per head
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % groups);
+        const long unit = idx / groups;                           // (n, q, m) flattened: the reference's `sampling_index`
+        const int m = (int)(unit % M);
+        const long nq = unit / M;
+        const int n = (int)(nq / Q);
+        const float* wp = attn + unit * L * P;
+        const float* lp = loc + unit * L * P * 2;
+        const size_t head_stride = (size_t)M * D;                 // elements between consecutive spatial positions
+        const T* vbase = value + (size_t)n * S * head_stride + (size_t)m * D + (size_t)cg * V;
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.h[l], W = lv.w[l];
+            const T* vl = vbase + (size_t)lv.start[l] * head_stride;
+            for (int p = 0; p < P; ++p) {
+                const float lw_ = __ldg(lp), lh_ = __ldg(lp + 1), wt = __ldg(wp);
+                lp += 2;
+                wp += 1;
+                const float h_im = lh_ * H - 0.5f, w_im = lw_ * W - 0.5f;        // ms_deform_im2col_cuda.cuh:286-287
+                if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
+                    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                    const int h_high = h_low + 1, w_high = w_low + 1;
+                    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                    const float w1 = hh * hw * wt, w2 = hh * lw * wt, w3 = lh * hw * wt, w4 = lh * lw * wt;
+                    float t[V];
+                    if (h_low >= 0 && w_low >= 0) {
+                        Pack16<T>::load(vl + ((size_t)h_low * W + w_low) * head_stride, t);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t[i], acc[i]);
+                    }
+                    if (h_low >= 0 && w_high <= W - 1) {
+                        Pack16<T>::load(vl + ((size_t)h_low * W + w_high) * head_stride, t);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w2, t[i], acc[i]);
+                    }
+                    if (h_high <= H - 1 && w_low >= 0) {
+                        Pack16<T>::load(vl + ((size_t)h_high * W + w_low) * head_stride, t);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w3, t[i], acc[i]);
+                    }
+                    if (h_high <= H - 1 && w_high <= W - 1) {
+                        Pack16<T>::load(vl + ((size_t)h_high * W + w_high) * head_stride, t);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w4, t[i], acc[i]);
+                    }
+                }
+            }
+        }
+        Pack16<T>::store(out + unit * D + (size_t)cg * V, acc);
+    }
+}
+
+}  // namespace
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" int svb_ms_deform_attn_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                                          const float* sampling_locations, const float* attention_weights, void* out, int dtype, int batch,
+                                          int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_points,
+                                          svb_stream_t stream) {
+    SVB_REQUIRE(value && spatial_shapes && level_start_index && sampling_locations && attention_weights && out,
+                "svb_ms_deform_attn_forward: null argument");
+    SVB_REQUIRE(dtype == SVB_DTYPE_F32 || dtype == SVB_DTYPE_BF16, "svb_ms_deform_attn_forward: bad dtype %d", dtype);
+    SVB_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS, "svb_ms_deform_attn_forward: %d levels (1..%d supported)", num_levels,
+                MSDA_MAX_LEVELS);
+    const int vec = dtype == SVB_DTYPE_BF16 ? 8 : 4;
+    SVB_REQUIRE(channels > 0 && channels % vec == 0, "svb_ms_deform_attn_forward: channels per head (%d) must be a multiple of %d", channels, vec);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "svb_ms_deform_attn_forward: value / out must be 16-byte aligned");
+    SVB_REQUIRE(batch >= 0 && num_query >= 0 && num_heads > 0 && num_points > 0 && spatial_size >= 0, "svb_ms_deform_attn_forward: bad sizes");
+    MsdaLevels lv;
+    long covered = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        lv.h[l] = spatial_shapes[2 * l];
+        lv.w[l] = spatial_shapes[2 * l + 1];
+        lv.start[l] = level_start_index[l];
+        SVB_REQUIRE(lv.h[l] > 0 && lv.w[l] > 0 && lv.start[l] >= 0 && (long)lv.start[l] + (long)lv.h[l] * lv.w[l] <= spatial_size,
+                    "svb_ms_deform_attn_forward: level %d (%d x %d at %d) does not fit in %d positions", l, lv.h[l], lv.w[l], lv.start[l],
+                    spatial_size);
+        covered += (long)lv.h[l] * lv.w[l];
+    }
+    SVB_REQUIRE(covered == spatial_size, "svb_ms_deform_attn_forward: the levels cover %ld positions, value has %d", covered, spatial_size);
+    const long total = (long)batch * num_query * num_heads * (channels / vec);
+    if (total == 0) return 0;
+    const long blocks_needed = (total + 255) / 256;
+    const int blocks = (int)(blocks_needed < 148L * 32 ? blocks_needed : 148L * 32);
+    const double bytes = (double)batch * num_query * num_heads *
+                         ((double)num_levels * num_points * (12.0 + 4.0 * channels * (vec == 8 ? 2 : 4)) + (double)channels * (vec == 8 ? 2 : 4));
+    ProfScope prof(PC_OTHER, 0, bytes, (cudaStream_t)stream);
+    if (dtype == SVB_DTYPE_BF16)
+        msda_forward_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)value, sampling_locations, attention_weights, (bf16*)out,
+                                                                             lv, total, spatial_size, num_heads, channels, num_levels,
+                                                                             num_query, num_points);
+    else
+        msda_forward_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)value, sampling_locations, attention_weights,
+                                                                              (float*)out, lv, total, spatial_size, num_heads, channels,
+                                                                              num_levels, num_query, num_points);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

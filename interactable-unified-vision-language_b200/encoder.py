@@ -299,6 +299,46 @@ class ImageEncoderViT(nn.Module):
                 cabi.stream_ptr()), "svb_encoder_forward")
         return {"res2": outs[0], "res3": outs[1], "res4": outs[2], "res5": outs[3]}
 
+    def forward_uint8(self, images, pixel_mean, pixel_std) -> Dict[str, torch.Tensor]:
+        """The forward fed with the callers' raw inputs (scope row N2): ``images`` is a list of uint8 CUDA tensors (C,h,w) with
+        h,w <= img_size; equivalent to ``self(ImageList.from_tensors([(x - pixel_mean) / pixel_std for x in images], 1024).tensor)``
+        (modeling/architectures/xdecoder_model.py:481-484) with the normalisation and the zero padding done inside the
+        patch-embedding loader."""
+        if len(images) == 0:
+            raise ValueError("forward_uint8 needs at least one image")
+        device = images[0].device
+        keep = []
+        for t in images:
+            if not t.is_cuda or t.dtype != torch.uint8 or t.dim() != 3 or t.shape[0] != self.cfg.in_chans:
+                raise ValueError(f"forward_uint8 takes uint8 CUDA tensors of shape ({self.cfg.in_chans},h,w)")
+            if t.shape[1] > self.img_size or t.shape[2] > self.img_size:
+                raise NotImplementedError(f"image {tuple(t.shape[1:])} exceeds the {self.img_size}x{self.img_size} canvas "
+                                          "(larger token grids are a 'next' row)")
+            keep.append(t.contiguous())
+        B = len(keep)
+        mean = [float(v) for v in torch.as_tensor(pixel_mean).flatten().tolist()]
+        std = [float(v) for v in torch.as_tensor(pixel_std).flatten().tolist()]
+        if len(mean) != self.cfg.in_chans or len(std) != self.cfg.in_chans:
+            raise ValueError("pixel_mean / pixel_std must have one entry per channel")
+        with torch.cuda.device(device):
+            self._prepare(device)
+            S, od = self.img_size, self.cfg.fpn_dims
+            outs = [torch.empty(B, od[k], S // s, S // s, dtype=self.out_dtype, device=device) for k, s in enumerate((4, 8, 16, 32))]
+            chunk = max(1, min(int(self.max_chunk), B))
+            mode = self._mode()
+            ws = self._workspace(chunk, mode, device)
+            base = (ws.data_ptr() + 1023) & ~1023
+            ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in keep])
+            hs = (C.c_int * B)(*[int(t.shape[1]) for t in keep])
+            wds = (C.c_int * B)(*[int(t.shape[2]) for t in keep])
+            cm = (C.c_float * len(mean))(*mean)
+            cs = (C.c_float * len(std))(*std)
+            cabi.check(cabi.lib().svb_encoder_forward_u8(
+                self._handle, ptrs, hs, wds, cm, cs, B, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
+                cabi.stream_ptr()), "svb_encoder_forward_u8")
+        return {"res2": outs[0], "res3": outs[1], "res4": outs[2], "res5": outs[3]}
+
     def forward_host(self, x: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None,
                      device: Optional[torch.device] = None) -> Dict[str, torch.Tensor]:
         """End-to-end call with HOST tensors: ``x`` (B,3,S,S) fp32 on the CPU (pinned for full PCIe speed); returns pinned

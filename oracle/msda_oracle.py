@@ -1,0 +1,82 @@
+"""CPU ORACLE for the multi-scale deformable attention forward (scope row N1).  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/`` and tools that check the CUDA kernel may import this file; the product never does.
+
+Two restatements of the same operator:
+  * ``ms_deform_attn_core`` follows the reference's own debug/test implementation ``ms_deform_attn_core_pytorch``
+    (``/root/reference/modeling/vision/encoder/ops/functions/ms_deform_attn_func.py:52-72``): per level an
+    ``F.grid_sample(bilinear, zeros, align_corners=False)`` of the head-major value map, weighted sum over levels x points;
+  * ``ms_deform_attn_loops`` follows the reference's CUDA kernel ``ms_deformable_im2col_gpu_kernel`` and its bilinear tap
+    (``ops/src/cuda/ms_deform_im2col_cuda.cuh:242-303`` and ``:18-69``) with explicit Python loops (small cases only).
+
+Parity pin: ``tests/golden/make_golden_msda.py`` executes the SOURCE TEXT of the reference's ``ms_deform_attn_core_pytorch``
+(the module itself cannot be imported: it requires the compiled ``MultiScaleDeformableAttention`` extension at import time,
+``ms_deform_attn_func.py:21-29``) on seeded inputs — the toy geometry of the reference's ``ops/test.py:24-29`` and larger
+ones with out-of-range sampling locations — and commits inputs + outputs as ``tests/golden/msda_*.npz``;
+``tests/test_oracle.py`` checks both restatements against them.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def ms_deform_attn_core(value, spatial_shapes, sampling_locations, attention_weights):
+    """value (N,S,M,D); spatial_shapes [(H,W)]*L; sampling_locations (N,Lq,M,L,P,2) (x,y) in [0,1];
+    attention_weights (N,Lq,M,L,P)  ->  (N,Lq,M*D).   ms_deform_attn_func.py:52-72."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+    levels = value.split([h * w for h, w in shapes], dim=1)
+    grids = 2 * sampling_locations - 1                                            # :58
+    sampled = []
+    for lid, (h, w) in enumerate(shapes):
+        v = levels[lid].flatten(2).transpose(1, 2).reshape(N * M, D, h, w)        # :62
+        g = grids[:, :, :, lid].transpose(1, 2).flatten(0, 1)                     # :64  (N*M, Lq, P, 2)
+        sampled.append(F.grid_sample(v, g, mode="bilinear", padding_mode="zeros", align_corners=False))   # :66-67
+    aw = attention_weights.transpose(1, 2).reshape(N * M, 1, Lq, L * P)           # :70
+    out = (torch.stack(sampled, dim=-2).flatten(-2) * aw).sum(-1).view(N, M * D, Lq)
+    return out.transpose(1, 2).contiguous()                                       # :72
+
+
+def ms_deform_attn_loops(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    """Explicit-loop form of the CUDA kernel (ms_deform_im2col_cuda.cuh:242-303, bilinear :18-69).  fp64 accumulation."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    v = value.double()
+    out = torch.zeros(N, Lq, M, D, dtype=torch.float64)
+    for n in range(N):
+        for q in range(Lq):
+            for m in range(M):
+                col = torch.zeros(D, dtype=torch.float64)
+                for l in range(L):
+                    H, W = int(spatial_shapes[l][0]), int(spatial_shapes[l][1])
+                    start = int(level_start_index[l])
+                    for p in range(P):
+                        loc_w = float(sampling_locations[n, q, m, l, p, 0])
+                        loc_h = float(sampling_locations[n, q, m, l, p, 1])
+                        wt = float(attention_weights[n, q, m, l, p])
+                        h_im, w_im = loc_h * H - 0.5, loc_w * W - 0.5                       # :286-287
+                        if not (h_im > -1 and w_im > -1 and h_im < H and w_im < W):          # :289
+                            continue
+                        h_low, w_low = math.floor(h_im), math.floor(w_im)                    # :25-26
+                        h_high, w_high = h_low + 1, w_low + 1
+                        lh, lw = h_im - h_low, w_im - w_low
+                        hh, hw = 1 - lh, 1 - lw
+
+                        def tap(y, x):
+                            return v[n, start + y * W + x, m]
+                        val = torch.zeros(D, dtype=torch.float64)
+                        if h_low >= 0 and w_low >= 0:                                        # :40
+                            val += hh * hw * tap(h_low, w_low)
+                        if h_low >= 0 and w_high <= W - 1:                                   # :46
+                            val += hh * lw * tap(h_low, w_high)
+                        if h_high <= H - 1 and w_low >= 0:                                   # :52
+                            val += lh * hw * tap(h_high, w_low)
+                        if h_high <= H - 1 and w_high <= W - 1:                              # :58
+                            val += lh * lw * tap(h_high, w_high)
+                        col += val * wt                                                      # :291
+                out[n, q, m] = col
+    return out.reshape(N, Lq, M * D)

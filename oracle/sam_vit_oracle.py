@@ -29,6 +29,24 @@ Tensor = torch.Tensor
 # ----------------------------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------------------------
+def stage_images(images, pixel_mean, pixel_std, size: int = 1024) -> Tensor:
+    """What the encoder's callers do before calling it (scope row N2; modeling/architectures/xdecoder_model.py:481-484):
+    ``images = [(x - pixel_mean) / pixel_std for x in images]`` on uint8 (C,h,w) tensors, then
+    ``ImageList.from_tensors(images, 1024)`` (detectron2): a (B,C,H,W) canvas whose sides are the batch maxima rounded up to a
+    multiple of ``size``, each image in the top-left corner, zeros elsewhere.  The detectron2 class is absent from the reference
+    tree; its documented semantics (pad_value = 0.0, bottom/right padding) are restated here.  Only canvases of exactly
+    ``size`` x ``size`` reach the encoder in the BASELINE configurations."""
+    mean = torch.as_tensor(pixel_mean, dtype=torch.float32).view(-1, 1, 1)
+    std = torch.as_tensor(pixel_std, dtype=torch.float32).view(-1, 1, 1)
+    norm = [(x.to(torch.float32) - mean) / std for x in images]
+    H = -(-max(t.shape[-2] for t in norm) // size) * size
+    W = -(-max(t.shape[-1] for t in norm) // size) * size
+    out = torch.zeros(len(norm), norm[0].shape[0], H, W, dtype=torch.float32)
+    for i, t in enumerate(norm):
+        out[i, :, : t.shape[-2], : t.shape[-1]] = t
+    return out
+
+
 def patch_embed(x: Tensor, w: Tensor, b: Tensor, patch: int) -> Tensor:
     """Conv2d(k=stride=patch) + NCHW->NHWC (image_encoder.py:402-410) as an im2col GEMM.
     x (B,C,H,W) -> (B,H/p,W/p,D)."""

@@ -120,6 +120,59 @@ def test_batch_chunking_and_output_dtype_and_host_path():
         assert ib.rel_l2(oh[k], outs[8][k]) < 1e-6
 
 
+PIXEL_MEAN, PIXEL_STD = [123.675, 116.280, 103.530], [58.395, 57.120, 57.375]      # configs/step1.yaml:320-321
+
+
+def _u8_images(sizes, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8) for h, w in sizes]
+
+
+def test_uint8_staging_is_exact():
+    """(x - mean) / std + zero padding to the canvas + patch im2col, fp32: bit-exact against the oracle's restatement."""
+    import ctypes as C
+    from iuvl_b200 import cabi
+    from oracle import sam_vit_oracle as orc
+    imgs = _u8_images([(1024, 1024), (700, 1000), (37, 53), (1, 1), (1024, 5), (1021, 1023)])
+    canvas = orc.stage_images(imgs, PIXEL_MEAN, PIXEL_STD, 1024)
+    B = len(imgs)
+    ref = canvas.reshape(B, 3, 64, 16, 64, 16).permute(0, 2, 4, 1, 3, 5).reshape(B * 4096, 768)
+    dev = [t.to(DEV) for t in imgs]
+    ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in dev])
+    hs = (C.c_int * B)(*[t.shape[1] for t in dev])
+    ws = (C.c_int * B)(*[t.shape[2] for t in dev])
+    mean, std = (C.c_float * 3)(*PIXEL_MEAN), (C.c_float * 3)(*PIXEL_STD)
+    out = torch.full((B * 4096, 768), float("nan"), device=DEV)
+    cabi.check(cabi.lib().svb_stage_images_u8(ptrs, hs, ws, B, 3, 1024, 16, mean, std, out.data_ptr(), cabi.DTYPE_F32, cabi.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+    outb = torch.empty(B * 4096, 768, device=DEV, dtype=torch.bfloat16)
+    cabi.check(cabi.lib().svb_stage_images_u8(ptrs, hs, ws, B, 3, 1024, 16, mean, std, outb.data_ptr(), cabi.DTYPE_BF16, cabi.stream_ptr()))
+    assert torch.equal(outb.cpu(), ref.bfloat16())
+
+
+def test_uint8_forward_matches_the_oracle_pipeline():
+    """forward_uint8 == oracle(stage_images(...)) (xdecoder_model.py:481-484 + image_encoder.py:107-120), ragged image sizes."""
+    from oracle import sam_vit_oracle as orc
+    cfg = ib.PRESETS["tiny80"]
+    sd = ib.make_state_dict(cfg, 77, rel_std=0.1)
+    imgs = _u8_images([(1024, 1024), (600, 911), (333, 1024)], seed=3)
+    ref = orc.encoder_forward_cfg(sd, orc.stage_images(imgs, PIXEL_MEAN, PIXEL_STD, 1024), cfg)
+    enc = build_encoder(cfg)
+    enc.load_state_dict(sd)
+    enc.to(DEV)
+    for precision, tol in (("fp32", TOL_FP32), ("bf16", TOL_BF16)):
+        enc.precision = precision
+        with torch.no_grad():
+            out = enc.forward_uint8([t.to(DEV) for t in imgs], PIXEL_MEAN, PIXEL_STD)
+            same = enc(orc.stage_images(imgs, PIXEL_MEAN, PIXEL_STD, 1024).to(DEV))
+        for k in KEYS:
+            assert ib.rel_l2(out[k], ref[k]) < tol, (precision, k, ib.rel_l2(out[k], ref[k]))
+            assert torch.equal(out[k], same[k])            # same arithmetic as the fp32-canvas entry point
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        enc.forward_uint8([torch.zeros(3, 1025, 10, dtype=torch.uint8, device=DEV)], PIXEL_MEAN, PIXEL_STD)
+
+
 def test_weights_resync_after_load_state_dict():
     g, cfg, sd, x, enc = _setup("tiny64_std")
     enc.precision = "fp32"

@@ -96,3 +96,44 @@ def test_pad_tokens_are_real_keys():
     msk = torch.cat(outs_masked, 1) @ sd["blocks.0.attn.proj.weight"].t() + sd["blocks.0.attn.proj.bias"]
     assert ib.rel_l2(got.reshape(196, D)[real], man[real]) < 1e-5
     assert ib.rel_l2(msk[real], man[real]) > 1e-2         # masking pads is a different function
+
+
+def test_stage_images_restates_the_callers_preprocessing():
+    """(x - mean) / std on uint8 CHW tensors + detectron2 ImageList.from_tensors(images, 1024) zero padding
+    (modeling/architectures/xdecoder_model.py:481-484)."""
+    import torch
+    from oracle import sam_vit_oracle as orc
+    g = torch.Generator().manual_seed(0)
+    imgs = [torch.randint(0, 256, (3, 5, 7), generator=g, dtype=torch.uint8), torch.randint(0, 256, (3, 8, 3), generator=g, dtype=torch.uint8)]
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    out = orc.stage_images(imgs, mean, std, size=8)
+    assert out.shape == (2, 3, 8, 8)
+    m, s = torch.tensor(mean).view(3, 1, 1), torch.tensor(std).view(3, 1, 1)
+    assert torch.equal(out[0, :, :5, :7], (imgs[0].float() - m) / s)
+    assert torch.equal(out[1, :, :8, :3], (imgs[1].float() - m) / s)
+    assert out[0, :, 5:, :].abs().sum() == 0 and out[0, :, :, 7:].abs().sum() == 0 and out[1, :, :, 3:].abs().sum() == 0
+    big = orc.stage_images([torch.zeros(3, 9, 2, dtype=torch.uint8)], mean, std, size=8)
+    assert big.shape == (1, 3, 16, 8)          # sides round UP to a multiple of the divisibility
+
+
+@pytest.mark.parametrize("case", ["toy", "small", "heads8"])
+def test_msda_oracle_against_reference_goldens(case):
+    """Both restatements of the multi-scale deformable attention forward against outputs of the reference's own
+    ms_deform_attn_core_pytorch (tests/golden/make_golden_msda.py)."""
+    import numpy as np
+    import torch
+    from oracle import msda_oracle as mo
+    from tests.util import GOLDEN
+    import os
+    z = np.load(os.path.join(GOLDEN, f"msda_{case}.npz"))
+    value, loc, aw = (torch.from_numpy(z[k]).double() for k in ("value", "loc", "aw"))
+    shapes = [tuple(int(v) for v in hw) for hw in z["shapes"]]
+    ref = torch.from_numpy(z["out"])
+    out = mo.ms_deform_attn_core(value, shapes, loc, aw)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+    if case != "heads8":
+        starts = [0]
+        for h, w in shapes[:-1]:
+            starts.append(starts[-1] + h * w)
+        out2 = mo.ms_deform_attn_loops(value, shapes, starts, loc, aw)
+        assert torch.allclose(out2, ref, rtol=1e-9, atol=1e-10), float((out2 - ref).abs().max())
