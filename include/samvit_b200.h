@@ -67,6 +67,19 @@ size_t svb_encoder_workspace_bytes(const svb_encoder_t* enc, int chunk, int mode
 int svb_encoder_forward(svb_encoder_t* enc, const float* x, int batch, void* res2, void* res3, void* res4, void* res5,
                         int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
 
+/* Scope row N3: the forward on canvases other than img_size x img_size (both sides multiples of 32 * patch_size, e.g. the
+ * 1024 x 2048 pads of the reference's COCO evaluation).  Takes the reference's own fallbacks: `interpolate_pos_encoding`
+ * (bicubic pos_embed, image_encoder.py:111-114,124-132) and, in the global-attention blocks, `get_rel_pos`'s linear resize of the
+ * rel_pos tables (:319-330).  x (B,3,img_h,img_w); outputs (B,C_k,img_h/s_k,img_w/s_k).  The attention of such grids runs on the
+ * fp32-math kernel (the tcgen05 attention kernels implement the trained 64 x 64 grid). */
+size_t svb_encoder_workspace_bytes_hw(const svb_encoder_t* enc, int chunk, int mode, int img_h, int img_w);
+int svb_encoder_forward_hw(svb_encoder_t* enc, const float* x, int batch, int img_h, int img_w, void* res2, void* res3, void* res4,
+                           void* res5, int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
+/* The two table fallbacks alone (device pointers, fp32): F.interpolate(pos_embed, mode='bicubic') (h0,w0,dim)->(h1,w1,dim);
+ * F.interpolate(rel_pos, mode='linear') (len0,head_dim)->(len1,head_dim). */
+int svb_resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int dim, svb_stream_t stream);
+int svb_resize_rel_pos(const float* src, float* dst, int len0, int len1, int head_dim, svb_stream_t stream);
+
 /* The same forward fed with what the reference's callers hold BEFORE their eager pre-processing (scope row N2): per image a DEVICE
  * pointer to a uint8 (C,h,w) tensor, h,w <= img_size.  Replaces `(x - pixel_mean) / pixel_std` + `ImageList.from_tensors(images, 1024)`
  * (modeling/architectures/xdecoder_model.py:481-484, detectron2 zero padding to the bottom/right) + ImageEncoderViT.forward: the

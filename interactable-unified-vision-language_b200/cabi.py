@@ -36,6 +36,10 @@ SYMBOLS = {
     "svb_encoder_missing_params": (_i, [_vp]),
     "svb_encoder_workspace_bytes": (_sz, [_vp, _i, _i]),
     "svb_encoder_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "svb_encoder_workspace_bytes_hw": (_sz, [_vp, _i, _i, _i, _i]),
+    "svb_encoder_forward_hw": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "svb_resize_pos_embed": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_resize_rel_pos": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_encoder_forward_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "svb_stage_images_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "svb_encoder_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i]),

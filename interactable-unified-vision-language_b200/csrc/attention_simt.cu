@@ -22,23 +22,27 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 attention_simt_kernel(AttnParams p) {
     extern __shared__ float sm[];
-    const int hd = p.hd, ws = p.ws, g = p.grid, D = p.heads * p.hd;
+    // token grid gh x gw, windows wsh x wsw (the whole grid for global attention)
+    const int hd = p.hd, D = p.heads * p.hd;
+    const int gh = p.grid_h > 0 ? p.grid_h : p.grid, gw = p.grid_h > 0 ? p.grid_w : p.grid;
+    const int wsh = p.grid_h > 0 ? p.ws_h : p.ws, wsw = p.grid_h > 0 ? p.ws_w : p.ws;
     const int hdp = hd + 1;
     float* Qs = sm;                          // [QT][hdp]
     float* Ks = Qs + QT * hdp;               // [KT][hdp]
     float* Vs = Ks + KT * hdp;               // [KT][hd]
     float* Ps = Vs + KT * hd;                // [QT][KT+1]
-    float* Bh = Ps + QT * (KT + 1);          // [QT][ws]
-    float* Bw = Bh + QT * ws;                // [QT][ws]
+    float* Bh = Ps + QT * (KT + 1);          // [QT][wsh]
+    float* Bw = Bh + QT * wsh;               // [QT][wsw]
 
     const int tid = threadIdx.x;
     const int r = tid >> 2, g4 = tid & 3;
     const int head = blockIdx.y;
-    const int nwin_side = (g + ws - 1) / ws;
-    const int nwin = nwin_side * nwin_side;
+    const int nwy = (gh + wsh - 1) / wsh, nwx = (gw + wsw - 1) / wsw;
+    const int nwin = nwy * nwx;
     const int b = blockIdx.z / nwin, win = blockIdx.z % nwin;
-    const int wy = win / nwin_side, wx = win % nwin_side;
-    const int S = ws * ws;
+    const int wy = win / nwx, wx = win % nwx;
+    const int S = wsh * wsw;
+    const size_t ntok = (size_t)gh * gw;
     const int q0 = blockIdx.x * QT;
     const T* qkv = reinterpret_cast<const T*>(p.qkv);
     const size_t ld = (size_t)3 * D;
@@ -50,25 +54,26 @@ attention_simt_kernel(AttnParams p) {
         const int qi = q0 + rr;
         float v = 0.f;
         if (qi < S) {
-            const int y = wy * ws + qi / ws, x = wx * ws + qi % ws;
-            if (y < g && x < g) v = to_float(qkv[((size_t)b * g * g + (size_t)y * g + x) * ld + head * hd + c]);
+            const int y = wy * wsh + qi / wsw, x = wx * wsw + qi % wsw;
+            if (y < gh && x < gw) v = to_float(qkv[((size_t)b * ntok + (size_t)y * gw + x) * ld + head * hd + c]);
         }
         Qs[rr * hdp + c] = v;
     }
     __syncthreads();
     // ---- decomposed rel-pos tables for this query tile ----
-    for (int i = tid; i < QT * 2 * ws; i += NT) {
-        const int rr = i / (2 * ws), j = i % (2 * ws);
+    for (int i = tid; i < QT * (wsh + wsw); i += NT) {
+        const int rr = i / (wsh + wsw), j = i % (wsh + wsw);
         const int qi = q0 + rr;
+        const bool is_w = j >= wsh;
+        const int kk = is_w ? j - wsh : j;
         float acc = 0.f;
         if (qi < S) {
-            const bool is_w = j >= ws;
-            const int kk = is_w ? j - ws : j;
-            const int qpos = is_w ? (qi % ws) : (qi / ws);
-            const float* tab = (is_w ? p.rel_w : p.rel_h) + (size_t)(qpos - kk + ws - 1) * hd;
+            const int qpos = is_w ? (qi % wsw) : (qi / wsw);
+            const float* tab = (is_w ? p.rel_w : p.rel_h) + (size_t)(qpos - kk + (is_w ? wsw : wsh) - 1) * hd;
             for (int c = 0; c < hd; ++c) acc = fmaf(Qs[rr * hdp + c], __ldg(tab + c), acc);
         }
-        (j >= ws ? Bw : Bh)[rr * ws + (j >= ws ? j - ws : j)] = acc;
+        if (is_w) Bw[rr * wsw + kk] = acc;
+        else Bh[rr * wsh + kk] = acc;
     }
 
     float m_run = -INFINITY, l_run = 0.f;
@@ -76,7 +81,7 @@ attention_simt_kernel(AttnParams p) {
 #pragma unroll
     for (int t = 0; t < MAXHD / 4; ++t) o[t] = 0.f;
     const int qi = q0 + r;
-    const int qh = qi / ws, qw = qi % ws;
+    const int qh = qi / wsw, qw = qi % wsw;
 
     for (int k0 = 0; k0 < S; k0 += KT) {
         __syncthreads();    // previous tile fully consumed (also orders the Bh/Bw writes on the first pass)
@@ -85,9 +90,9 @@ attention_simt_kernel(AttnParams p) {
             const int ki = k0 + kr;
             float kv = 0.f, vv = 0.f;
             if (ki < S) {
-                const int y = wy * ws + ki / ws, x = wx * ws + ki % ws;
-                if (y < g && x < g) {
-                    const T* base = qkv + ((size_t)b * g * g + (size_t)y * g + x) * ld + head * hd + c;
+                const int y = wy * wsh + ki / wsw, x = wx * wsw + ki % wsw;
+                if (y < gh && x < gw) {
+                    const T* base = qkv + ((size_t)b * ntok + (size_t)y * gw + x) * ld + head * hd + c;
                     kv = to_float(base[D]);
                     vv = to_float(base[2 * D]);
                 } else {   // pad token: qkv(0) = bias; round through T like a stored activation would be
@@ -109,7 +114,7 @@ attention_simt_kernel(AttnParams p) {
             float acc = 0.f;
             for (int c = 0; c < hd; ++c) acc = fmaf(Qs[r * hdp + c], Ks[kr * hdp + c], acc);
             if (ki < S && qi < S) {
-                acc = acc * scale + Bh[r * ws + ki / ws] + Bw[r * ws + ki % ws];
+                acc = acc * scale + Bh[r * wsh + ki / wsw] + Bw[r * wsw + ki % wsw];
             } else {
                 acc = -INFINITY;
             }
@@ -145,9 +150,9 @@ attention_simt_kernel(AttnParams p) {
         }
     }
     if (qi < S) {
-        const int y = wy * ws + qh, x = wx * ws + qw;
-        if (y < g && x < g) {
-            T* out = reinterpret_cast<T*>(p.out) + ((size_t)b * g * g + (size_t)y * g + x) * D + head * hd;
+        const int y = wy * wsh + qh, x = wx * wsw + qw;
+        if (y < gh && x < gw) {
+            T* out = reinterpret_cast<T*>(p.out) + ((size_t)b * ntok + (size_t)y * gw + x) * D + head * hd;
             const float inv = 1.f / l_run;
 #pragma unroll
             for (int t = 0; t < MAXHD / 4; ++t) {
@@ -162,17 +167,21 @@ attention_simt_kernel(AttnParams p) {
 
 int attention_simt(const AttnParams& p, bool is_bf16, cudaStream_t stream) {
     SVB_REQUIRE(p.hd <= MAXHD && p.hd > 0, "attention_simt: head_dim %d not supported (max %d)", p.hd, MAXHD);
-    SVB_REQUIRE(p.ws > 0 && p.ws <= p.grid, "attention_simt: bad window size %d for grid %d", p.ws, p.grid);
-    const int nwin_side = (p.grid + p.ws - 1) / p.ws;
-    const int S = p.ws * p.ws;
+    const int gh = p.grid_h > 0 ? p.grid_h : p.grid, gw = p.grid_h > 0 ? p.grid_w : p.grid;
+    const int wsh = p.grid_h > 0 ? p.ws_h : p.ws, wsw = p.grid_h > 0 ? p.ws_w : p.ws;
+    SVB_REQUIRE(gh > 0 && gw > 0 && wsh > 0 && wsw > 0 && wsh <= gh && wsw <= gw, "attention_simt: bad window %d x %d for grid %d x %d", wsh,
+                wsw, gh, gw);
+    const int nwin = ((gh + wsh - 1) / wsh) * ((gw + wsw - 1) / wsw);
+    const int S = wsh * wsw;
     const int hdp = p.hd + 1;
     const size_t smem = sizeof(float) * ((size_t)QT * hdp + (size_t)KT * hdp + (size_t)KT * p.hd + (size_t)QT * (KT + 1) +
-                                         2 * (size_t)QT * p.ws);
-    dim3 grid((S + QT - 1) / QT, p.heads, p.batch * nwin_side * nwin_side);
+                                         (size_t)QT * (wsh + wsw));
+    SVB_REQUIRE(smem <= 227 * 1024, "attention_simt: window %d x %d needs %zu bytes of shared memory", wsh, wsw, smem);
+    dim3 grid((S + QT - 1) / QT, p.heads, p.batch * nwin);
     const double D_ = (double)p.heads * p.hd;
-    ProfScope prof(p.ws == p.grid ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
-                   (double)p.batch * nwin_side * nwin_side * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
-                   (double)p.batch * p.grid * p.grid * 4.0 * D_ * (is_bf16 ? 2 : 4), stream);
+    ProfScope prof((wsh == gh && wsw == gw) ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
+                   (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * (double)(wsh + wsw) * D_),
+                   (double)p.batch * gh * gw * 4.0 * D_ * (is_bf16 ? 2 : 4), stream);
     if (is_bf16) {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(attention_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attention_simt_kernel<bf16><<<grid, NT, smem, stream>>>(p);

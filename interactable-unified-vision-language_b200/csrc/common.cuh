@@ -178,7 +178,10 @@ struct AttnParams {
     const float* rel_h;     // [2*ws-1, hd] fp32
     const float* rel_w;     // [2*ws-1, hd] fp32
     const float* qkv_bias;  // [3*D] fp32: pad tokens of edge windows have k = b_k, v = b_v
-    int batch, grid, ws, heads, hd;   // ws == grid -> global attention
+    int batch, grid, ws, heads, hd;   // square form: grid x grid tokens, ws x ws windows; ws == grid -> global attention
+    // general form (scope row N3), used when grid_h > 0: grid_h x grid_w tokens, ws_h x ws_w windows (= the grid for global attention);
+    // rel_h has 2*ws_h-1 rows, rel_w 2*ws_w-1 rows
+    int grid_h = 0, grid_w = 0, ws_h = 0, ws_w = 0;
 };
 // fp32-math SIMT attention with decomposed rel-pos; T = float (validation) or bf16.
 int attention_simt(const AttnParams& p, bool is_bf16, cudaStream_t stream);
@@ -199,7 +202,10 @@ int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cu
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)
-int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s);
+int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s);
+// scope row N3: bicubic resize of pos_embed (image_encoder.py:124-132), linear resize of a rel_pos table (:319-330)
+int resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int D, cudaStream_t s);
+int resize_rel_pos(const float* src, float* dst, int L0, int L1, int hd, cudaStream_t s);
 // uint8 (C,h,w) images -> normalised, zero-padded to img x img, patch rows (the patch-embedding GEMM's A operand); `images`, `hs`,
 // `ws` are HOST arrays (device pointers / sizes per image)
 int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, const float* mean, const float* stdv, void* out, bool out_bf16,
@@ -207,13 +213,13 @@ int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, c
 // out = LayerNorm(x [+ add]); when `add` (same element type as out) is given, x += add is written back first (fused residual)
 int layernorm_rows(float* x, const void* add, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s);
-int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s);
+int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int gh, int gw, int D, cudaStream_t s);
 int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,
                     long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s);
 // final stage: GroupNorm(1,C)+GELU and (pixel-unshuffle) NHWC -> NCHW.  `levels` = number of 2x2 ConvT stages whose
-// sub-pixel index is still folded into the row index (0, 1 or 2); base grid `g` (64 or 32).
+// sub-pixel index is still folded into the row index (0, 1 or 2); base token grid gh x gw.
 int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
-                         int B, int g, int levels, int C, float eps, int gelu, cudaStream_t s);
+                         int B, int gh, int gw, int levels, int C, float eps, int gelu, cudaStream_t s);
 // weight packing
 int pack_cast(const float* src, void* dst, bool dst_bf16, long n, cudaStream_t s);
 int pack_convT(const float* w /*Cin,Cout,2,2*/, void* dst /*[4*Cout, Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);

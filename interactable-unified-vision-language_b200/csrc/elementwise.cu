@@ -32,19 +32,20 @@ template <> struct Vec4<bf16> {
 // im2col for the patch embedding (PatchEmbed, image_encoder.py:379-410): x NCHW fp32 -> rows = patches (b,py,px),
 // cols = (c, ky, kx), matching patch_embed.proj.weight.reshape(D, C*p*p).  One thread = 4 consecutive kx.
 template <typename T>
-__global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int img, int patch) {
-    const int g = img / patch;
+__global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int img_h, int img_w, int patch) {
+    const int gh = img_h / patch, gw = img_w / patch;
     const int K = C * patch * patch;
-    const size_t total4 = (size_t)B * C * img * img / 4;
+    const size_t plane = (size_t)img_h * img_w;
+    const size_t total4 = (size_t)B * C * plane / 4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 4;                      // flat NCHW element index (input-major -> coalesced reads)
-        const int X = (int)(e % img);
-        const int Y = (int)((e / img) % img);
-        const int c = (int)((e / ((size_t)img * img)) % C);
-        const int b = (int)(e / ((size_t)img * img * C));
+        const int X = (int)(e % img_w);
+        const int Y = (int)((e / img_w) % img_h);
+        const int c = (int)((e / plane) % C);
+        const int b = (int)(e / (plane * C));
         const float4 v = *reinterpret_cast<const float4*>(x + e);
         const int px = X / patch, kx = X % patch, py = Y / patch, ky = Y % patch;
-        const size_t row = ((size_t)b * g + py) * g + px;
+        const size_t row = ((size_t)b * gh + py) * gw + px;
         Vec4<T>::store(out + row * K + (size_t)c * patch * patch + ky * patch + kx, v.x, v.y, v.z, v.w);
     }
 }
@@ -61,7 +62,7 @@ struct U8Batch {
 };
 template <typename T>
 __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, int img, int patch) {
-    const int g = img / patch;
+    const int g = img / patch;                       // (square canvases only: larger canvases go through the fp32 entry point)
     const int pp = patch * patch;
     const int K = C * pp;
     const size_t total4 = (size_t)B * g * g * K / 4;
@@ -143,17 +144,17 @@ layernorm_kernel(float* __restrict__ x, const T* __restrict__ add, const float* 
 //   a32 [B*(g/2)^2, 4D] = 2x2 space-to-depth gather     (A operand of the k=2,s=2 conv down_32.0, image_encoder.py:442)
 //        a32[(b,Y,X), (dy*2+dx)*D + c] = x[(b,2Y+dy,2X+dx), c]
 template <typename T>
-__global__ void cast_s2d_kernel(const float* __restrict__ x, T* __restrict__ xb, T* __restrict__ a32, int B, int g, int D) {
-    const size_t total4 = (size_t)B * g * g * D / 4;
-    const int hg = g / 2;
+__global__ void cast_s2d_kernel(const float* __restrict__ x, T* __restrict__ xb, T* __restrict__ a32, int B, int gh, int gw, int D) {
+    const size_t total4 = (size_t)B * gh * gw * D / 4;
+    const int hh = gh / 2, hw = gw / 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 4;
         const int c = (int)(e % D);
         const size_t tok = e / D;
-        const int xx = (int)(tok % g), yy = (int)((tok / g) % g), b = (int)(tok / ((size_t)g * g));
+        const int xx = (int)(tok % gw), yy = (int)((tok / gw) % gh), b = (int)(tok / ((size_t)gh * gw));
         const float4 v = *reinterpret_cast<const float4*>(x + e);
         if (xb) Vec4<T>::store(xb + e, v.x, v.y, v.z, v.w);
-        const size_t row = ((size_t)b * hg + (yy >> 1)) * hg + (xx >> 1);
+        const size_t row = ((size_t)b * hh + (yy >> 1)) * hw + (xx >> 1);
         const int sub = (yy & 1) * 2 + (xx & 1);
         Vec4<T>::store(a32 + row * (size_t)(4 * D) + (size_t)sub * D + c, v.x, v.y, v.z, v.w);
     }
@@ -212,17 +213,17 @@ gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, c
 template <typename T, int TP>
 __global__ void __launch_bounds__(256)
 gn_apply_nchw_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, T* __restrict__ out, int B, int g, int levels, int C, float eps, int gelu) {
+                     const float* __restrict__ beta, T* __restrict__ out, int B, int gh, int g, int levels, int C, float eps, int gelu) {
     constexpr int TC = 64;
     __shared__ float tile[TC][TP + 1];
     __shared__ float2 ms_s;
-    const int Wout = g << levels, Hout = Wout;
+    const int Wout = g << levels, Hout = gh << levels;      // g = token-grid width, gh = its height
     const int xt = Wout / TP;
     const int X0 = (blockIdx.x % xt) * TP;
     const int Y = (blockIdx.x / xt) % Hout;
     const int b = blockIdx.x / (xt * Hout);
     const int c0 = blockIdx.y * TC;
-    if (threadIdx.x == 0) ms_s = gn_mean_rstd(stats, b, (double)((long)g * g << (2 * levels)) * C, eps);
+    if (threadIdx.x == 0) ms_s = gn_mean_rstd(stats, b, (double)((long)gh * g << (2 * levels)) * C, eps);
     __syncthreads();
     const float mean = ms_s.x, rstd = ms_s.y;
     {   // ---- phase 1: 16 threads per pixel (4 channels each), 16 pixels per pass ----
@@ -235,7 +236,7 @@ gn_apply_nchw_kernel(const float* __restrict__ x, const double* __restrict__ sta
 #pragma unroll
         for (int k = 0; k < TP / 16; ++k) {
             const int X = X0 + pl + 16 * k;
-            long row = ((long)b * g + (Y >> levels)) * g + (X >> levels);
+            long row = ((long)b * gh + (Y >> levels)) * g + (X >> levels);
             for (int l = 1; l <= levels; ++l) {
                 const int sh = levels - l;
                 row = row * 4 + (((Y >> sh) & 1) * 2 + ((X >> sh) & 1));
@@ -255,11 +256,8 @@ gn_apply_nchw_kernel(const float* __restrict__ x, const double* __restrict__ sta
     // ---- phase 2: 16 bytes of consecutive X per thread ----
     constexpr int EPT = 16 / (int)sizeof(T);          // elements per thread: 8 (bf16) or 4 (fp32)
     constexpr int TPR = TP / EPT;                     // threads per channel row
-    constexpr int CPP = 256 / TPR;                    // channels per pass
-    const int pg = threadIdx.x % TPR, cl = threadIdx.x / TPR;
-#pragma unroll
-    for (int k = 0; k < TC / CPP; ++k) {
-        const int cj = cl + CPP * k;
+    for (int idx = threadIdx.x; idx < TC * TPR; idx += 256) {
+        const int cj = idx / TPR, pg = idx % TPR;
         const int c = c0 + cj;
         if (c >= C) continue;
         T* dst = out + (((size_t)b * C + c) * Hout + Y) * Wout + X0 + pg * EPT;
@@ -330,6 +328,57 @@ __global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restr
     if (lane == 0) { c[n] = sc; bfold[n] = (bias ? bias[n] : 0.f) + sb; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fallbacks of the reference for token grids other than the one the tables were trained on (scope row N3):
+//   * pos_embed (1,h0,w0,D) -> (1,h1,w1,D), bicubic, align_corners=False, A = -0.75, border taps clamped
+//     (ImageEncoderViT.interpolate_pos_encoding, image_encoder.py:124-132: F.interpolate(..., mode='bicubic'));
+//   * rel_pos table (L0,hd) -> (L1,hd), linear, align_corners=False (get_rel_pos, image_encoder.py:319-330).
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+    const float A = -0.75f;
+    const float x0 = t + 1.f, x3 = 2.f - t, u = 1.f - t;
+    w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+    w[1] = ((A + 2.f) * t - (A + 3.f)) * t * t + 1.f;
+    w[2] = ((A + 2.f) * u - (A + 3.f)) * u * u + 1.f;
+    w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__global__ void bicubic_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int h0, int w0, int h1, int w1, int D) {
+    const float sy = (float)h0 / (float)h1, sx = (float)w0 / (float)w1;
+    const long total = (long)h1 * w1 * D;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % D);
+        const int x = (int)((i / D) % w1), y = (int)(i / ((long)D * w1));
+        const float fy = sy * (y + 0.5f) - 0.5f, fx = sx * (x + 0.5f) - 0.5f;      // no clamp at 0 for cubic (ATen upsample)
+        const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+        float wy[4], wx[4];
+        cubic_coeffs(fy - iy, wy);
+        cubic_coeffs(fx - ix, wx);
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int yy = min(max(iy - 1 + a, 0), h0 - 1);
+            float r = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int xx = min(max(ix - 1 + b, 0), w0 - 1);
+                r += wx[b] * __ldg(src + ((long)yy * w0 + xx) * D + c);
+            }
+            acc += wy[a] * r;
+        }
+        dst[i] = acc;
+    }
+}
+__global__ void linear_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int L0, int L1, int hd) {
+    const float sc = (float)L0 / (float)L1;
+    const int total = L1 * hd;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % hd, j = i / hd;
+        const float f = fmaxf(sc * (j + 0.5f) - 0.5f, 0.f);
+        const int i0 = min((int)f, L0 - 1), i1 = min(i0 + 1, L0 - 1);
+        const float lam = f - i0;
+        dst[i] = (1.f - lam) * __ldg(src + (long)i0 * hd + c) + lam * __ldg(src + (long)i1 * hd + c);
+    }
+}
+
 inline int grid_for(size_t n, int block) {
     size_t gsz = (n + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -338,12 +387,13 @@ inline int grid_for(size_t n, int block) {
 
 }  // namespace
 
-int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img, int patch, cudaStream_t s) {
-    SVB_REQUIRE(img % patch == 0 && patch % 4 == 0, "im2col_patch: img %d / patch %d unsupported", img, patch);
-    const size_t total4 = (size_t)B * C * img * img / 4;
+int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s) {
+    SVB_REQUIRE(img_h % patch == 0 && img_w % patch == 0 && patch % 4 == 0, "im2col_patch: image %d x %d / patch %d unsupported", img_h, img_w,
+                patch);
+    const size_t total4 = (size_t)B * C * img_h * img_w / 4;
     ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * (4 + (out_bf16 ? 2 : 4)), s);
-    if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img, patch);
-    else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img, patch);
+    if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img_h, img_w, patch);
+    else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img_h, img_w, patch);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -445,12 +495,12 @@ int layernorm_rows(float* x, const void* add, const float* w, const float* b, vo
     return 0;
 }
 
-int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int grid, int D, cudaStream_t s) {
-    SVB_REQUIRE(D % 4 == 0 && grid % 2 == 0, "cast_and_space2depth: D=%d grid=%d unsupported", D, grid);
-    const size_t total4 = (size_t)B * grid * grid * D / 4;
+int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int gh, int gw, int D, cudaStream_t s) {
+    SVB_REQUIRE(D % 4 == 0 && gh % 2 == 0 && gw % 2 == 0, "cast_and_space2depth: D=%d grid=%d x %d unsupported", D, gh, gw);
+    const size_t total4 = (size_t)B * gh * gw * D / 4;
     ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * (4 + (out_bf16 ? 2 : 4) * (xb ? 2 : 1)), s);
-    if (out_bf16) cast_s2d_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)xb, (bf16*)a32, B, grid, D);
-    else cast_s2d_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)xb, (float*)a32, B, grid, D);
+    if (out_bf16) cast_s2d_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)xb, (bf16*)a32, B, gh, gw, D);
+    else cast_s2d_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)xb, (float*)a32, B, gh, gw, D);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -474,20 +524,24 @@ int groupnorm_apply(const float* x, const double* stats, const float* gamma, con
 }
 
 int groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
-                         int B, int g, int levels, int C, float eps, int gelu, cudaStream_t s) {
-    const int Wout = g << levels;
-    SVB_REQUIRE(Wout % 32 == 0 && levels >= 0 && levels <= 2 && C % 4 == 0, "groupnorm_apply_nchw: grid %d levels %d C %d unsupported", g,
-                levels, C);
-    const int TP = (Wout % 64 == 0) ? 64 : 32;
-    dim3 grid((unsigned)((size_t)B * Wout * (Wout / TP)), (C + 63) / 64);
-    ProfScope prof(PC_NORM, 0, (double)B * Wout * Wout * C * (4 + (out_dtype == 1 ? 2 : 4)), s);
+                         int B, int gh, int gw, int levels, int C, float eps, int gelu, cudaStream_t s) {
+    const int Wout = gw << levels, Hout = gh << levels;
+    SVB_REQUIRE(Wout % 16 == 0 && levels >= 0 && levels <= 2 && C % 4 == 0, "groupnorm_apply_nchw: grid %d x %d levels %d C %d unsupported", gh,
+                gw, levels, C);
+    const int TP = (Wout % 64 == 0) ? 64 : ((Wout % 32 == 0) ? 32 : 16);
+    dim3 grid((unsigned)((size_t)B * Hout * (Wout / TP)), (C + 63) / 64);
+    ProfScope prof(PC_NORM, 0, (double)B * Hout * Wout * C * (4 + (out_dtype == 1 ? 2 : 4)), s);
+#define SVB_GN_NCHW(TT, TPV) gn_apply_nchw_kernel<TT, TPV><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (TT*)out, B, gh, gw, levels, C, eps, gelu)
     if (out_dtype == 1) {
-        if (TP == 64) gn_apply_nchw_kernel<bf16, 64><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
-        else gn_apply_nchw_kernel<bf16, 32><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (bf16*)out, B, g, levels, C, eps, gelu);
+        if (TP == 64) SVB_GN_NCHW(bf16, 64);
+        else if (TP == 32) SVB_GN_NCHW(bf16, 32);
+        else SVB_GN_NCHW(bf16, 16);
     } else {
-        if (TP == 64) gn_apply_nchw_kernel<float, 64><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
-        else gn_apply_nchw_kernel<float, 32><<<grid, 256, 0, s>>>(x, stats, gamma, beta, (float*)out, B, g, levels, C, eps, gelu);
+        if (TP == 64) SVB_GN_NCHW(float, 64);
+        else if (TP == 32) SVB_GN_NCHW(float, 32);
+        else SVB_GN_NCHW(float, 16);
     }
+#undef SVB_GN_NCHW
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -509,6 +563,21 @@ int pack_conv2x2(const float* w, void* dst, bool dst_bf16, int Cin, int Cout, cu
     const long n = (long)4 * Cin * Cout;
     if (dst_bf16) pack_conv2x2_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(w, (bf16*)dst, Cin, Cout);
     else pack_conv2x2_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(w, (float*)dst, Cin, Cout);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int D, cudaStream_t s) {
+    SVB_REQUIRE(h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0 && D > 0, "resize_pos_embed: bad sizes");
+    const long total = (long)h1 * w1 * D;
+    bicubic_resize_kernel<<<grid_for((size_t)total, 256), 256, 0, s>>>(src, dst, h0, w0, h1, w1, D);
+    count_launch();
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int resize_rel_pos(const float* src, float* dst, int L0, int L1, int hd, cudaStream_t s) {
+    SVB_REQUIRE(L0 > 0 && L1 > 0 && hd > 0, "resize_rel_pos: bad sizes");
+    linear_resize_kernel<<<(L1 * hd + 255) / 256, 256, 0, s>>>(src, dst, L0, L1, hd);
+    count_launch();
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

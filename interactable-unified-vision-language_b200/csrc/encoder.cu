@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace svb {
@@ -62,6 +63,15 @@ struct svb_encoder {
     bool fold_dirty = true;         // a parameter was (re)loaded since the folded weights were last derived
     int grid_pad = 0;               // window-padded token grid (70 for 64 / 14)
     std::vector<bf16*> relpack;     // per block: bf16 rel-pos table block of the tcgen05 attention kernel (attention_tc.cu)
+    // scope row N3: tables resized for token grids other than the trained one (dropped whenever a parameter is reloaded)
+    std::map<std::pair<int, int>, float*> pos_cache;               // (gh, gw) -> bicubic pos_embed [gh*gw, D]
+    std::map<std::tuple<int, int, int>, float*> rel_cache;         // (block, is_w, length) -> linear rel_pos table [length, hd]
+    void drop_resized() {
+        for (auto& kv : pos_cache) cudaFree(kv.second);
+        for (auto& kv : rel_cache) cudaFree(kv.second);
+        pos_cache.clear();
+        rel_cache.clear();
+    }
     // host path resources
     struct HostPath {
         int chunk = 0, mode = -1, out_dtype = -1;
@@ -119,9 +129,11 @@ struct Buffers {
     size_t total;
 };
 
-Buffers plan(const svb_encoder* e, int chunk, int mode, void* base) {
+// T = tokens per image (grid_h * grid_w); 0 = the trained grid
+Buffers plan(const svb_encoder* e, int chunk, int mode, void* base, int T = 0) {
     const size_t es = (mode == SVB_MODE_BF16) ? 2 : 4;
-    const size_t M = (size_t)chunk * e->T;
+    const bool native = (T == 0 || T == e->T);
+    const size_t M = (size_t)chunk * (T ? T : e->T);
     const int D = e->D;
     const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
     Buffers b;
@@ -135,7 +147,7 @@ Buffers plan(const svb_encoder* e, int chunk, int mode, void* base) {
     const size_t mark = ar.off;
     b.A0 = ar.alloc(M * kpe * es);
     b.Xn = ar.alloc(M * D * es);
-    const size_t Mp = (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1) ? (size_t)chunk * e->grid_pad * e->grid_pad : M;
+    const size_t Mp = (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1 && native) ? (size_t)chunk * e->grid_pad * e->grid_pad : M;
     b.QKV = ar.alloc(Mp * 3 * D * es);
     b.O = ar.alloc(M * D * es);
     b.Hid = ar.alloc(M * e->mlp * es);
@@ -173,10 +185,45 @@ struct U8Input {
     const float* stdv = nullptr;
 };
 
+// resized tables of scope row N3 (cached per encoder)
+int resized_pos(svb_encoder* e, int gh, int gw, cudaStream_t st, const float** out) {
+    auto it = e->pos_cache.find({gh, gw});
+    if (it == e->pos_cache.end()) {
+        float* p = nullptr;
+        SVB_CHECK_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)gh * gw * e->D));
+        int rc = resize_pos_embed(e->P("pos_embed").f32, p, e->grid, e->grid, gh, gw, e->D, st);
+        if (rc) { cudaFree(p); return rc; }
+        it = e->pos_cache.emplace(std::make_pair(gh, gw), p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+int resized_rel(svb_encoder* e, int block, bool is_w, int L, cudaStream_t st, const float** out) {
+    const Param& t = e->P("blocks." + std::to_string(block) + (is_w ? ".attn.rel_pos_w" : ".attn.rel_pos_h"));
+    if (t.a == L) { *out = t.f32; return 0; }
+    auto key = std::make_tuple(block, (int)is_w, L);
+    auto it = e->rel_cache.find(key);
+    if (it == e->rel_cache.end()) {
+        float* p = nullptr;
+        SVB_CHECK_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)L * e->hd));
+        int rc = resize_rel_pos(t.f32, p, t.a, L, e->hd, st);
+        if (rc) { cudaFree(p); return rc; }
+        it = e->rel_cache.emplace(key, p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// One pass over B images of img_h x img_w pixels (0 = the trained img_size).  Token grids other than the trained one (scope row
+// N3) take the reference's fallbacks: bicubic pos_embed (image_encoder.py:111-114,124-132), linearly resized rel_pos tables in
+// the global blocks (:319-330); their attention runs on the fp32-math kernel (the tcgen05 kernels implement the 64 x 64 grid).
 int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], int out_dtype, int mode, const Buffers& bf,
-                  cudaStream_t st, const U8Input* u8 = nullptr) {
+                  cudaStream_t st, const U8Input* u8 = nullptr, int img_h = 0, int img_w = 0) {
     const bool h = (mode == SVB_MODE_BF16);
-    const int D = e->D, T = e->T, g = e->grid;
+    if (img_h == 0) { img_h = e->cfg.img_size; img_w = e->cfg.img_size; }
+    const int gh = img_h / e->cfg.patch_size, gw = img_w / e->cfg.patch_size;
+    const bool native = (gh == e->grid && gw == e->grid);
+    const int D = e->D, T = gh * gw, g = e->grid;
     const int M = B * T;
     const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
     int rc;
@@ -214,19 +261,22 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         if ((rc = stage_u8_patch(u8->images, u8->hs, u8->ws, u8->mean, u8->stdv, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size,
                                  e->cfg.patch_size, st)))
             return rc;
-    } else if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size, e->cfg.patch_size, st))) {
+    } else if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, img_h, img_w, e->cfg.patch_size, st))) {
         return rc;
     }
     {
+        const float* pos = e->P("pos_embed").f32;
+        if (!native && (rc = resized_pos(e, gh, gw, st, &pos))) return rc;
         Epilogue ep;
         ep.bias = e->P("patch_embed.proj.bias").f32;
-        ep.resid = e->P("pos_embed").f32;
+        ep.resid = pos;
         ep.resid_mod = T;
         ep.ldr = D;
         produce(ep, bf.st1);
         if ((rc = linear(mode, bf.A0, kpe, e->P("patch_embed.proj.weight"), M, D, kpe, ep, st))) return rc;
     }
-    if (e->taps_enabled) SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
+    const bool taps = e->taps_enabled && native;        // the tap buffer is sized for the trained grid
+    if (taps) SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
 
     // ---- Blocks (image_encoder.py:181-197) ----
     for (int i = 0; i < e->depth; ++i) {
@@ -234,8 +284,9 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         if (!fold && (rc = layernorm_rows(bf.X, nullptr, e->P(p + "norm1.weight").f32, e->P(p + "norm1.bias").f32, bf.Xn, h, M, D,
                                           e->cfg.ln_eps, st)))
             return rc;
-        const int ws = e->is_global(i) ? g : e->cfg.window_size;
-        const bool tc = h && e->attn_impl_bf16 == 1;
+        const bool glob = e->is_global(i);
+        const int ws = glob ? g : e->cfg.window_size;
+        const bool tc = h && e->attn_impl_bf16 == 1 && native;
         const bool padded = tc && ws != g;      // windowed blocks of the tcgen05 path keep qkv on the padded 70x70 grid
         {   // qkv (image_encoder.py:242)
             Epilogue ep;
@@ -262,6 +313,15 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
                 ap.rel_w = e->P(p + "attn.rel_pos_w").f32;
                 ap.qkv_bias = e->P(p + "attn.qkv.bias").f32;
                 ap.batch = B; ap.grid = g; ap.ws = ws; ap.heads = e->heads; ap.hd = e->hd;
+                if (!native) {
+                    ap.grid_h = gh; ap.grid_w = gw;
+                    ap.ws_h = glob ? gh : e->cfg.window_size;
+                    ap.ws_w = glob ? gw : e->cfg.window_size;
+                    if (glob) {     // get_rel_pos resizes the table when its length is not 2 * size - 1 (image_encoder.py:319-330)
+                        if ((rc = resized_rel(e, i, false, 2 * gh - 1, st, &ap.rel_h))) return rc;
+                        if ((rc = resized_rel(e, i, true, 2 * gw - 1, st, &ap.rel_w))) return rc;
+                    }
+                }
                 if ((rc = attention_simt(ap, h, st))) return rc;
             }
         }
@@ -297,14 +357,14 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
             produce(ep, bf.st1);
             if ((rc = linear(mode, bf.Hid, e->mlp, e->P(p + "mlp.lin2.weight"), M, D, e->mlp, ep, st))) return rc;
         }
-        if (e->taps_enabled)
+        if (taps)
             SVB_CHECK_CUDA(cudaMemcpyAsync(e->taps + (size_t)(i + 1) * T * D, bf.X, sizeof(float) * T * D, cudaMemcpyDeviceToDevice, st));
     }
 
     // ---- SimpleFPN neck (image_encoder.py:413-466).  ConvTranspose2d(k=2,s=2) and Conv2d(k=2,s=2) do not overlap, so
     // each is one GEMM; the 2x2 sub-pixel index stays folded in the row index until the final NCHW write. ----
     SVB_CHECK_CUDA(cudaMemsetAsync(bf.stats, 0, sizeof(double) * 2 * 8 * B, st));
-    if ((rc = cast_and_space2depth(bf.X, h ? bf.Xb : nullptr, bf.A32, h, B, g, D, st))) return rc;
+    if ((rc = cast_and_space2depth(bf.X, h ? bf.Xb : nullptr, bf.A32, h, B, gh, gw, D, st))) return rc;
     const void* Xb = h ? bf.Xb : (const void*)bf.X;
     const float geps = e->cfg.gn_eps;
     const int* od = e->cfg.fpn_dims;
@@ -321,7 +381,7 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     // down_16: Conv1x1 -> GN -> GELU  (:435-439)
     if ((rc = gemm_stats(Xb, D, n + "down_16.0.weight", n + "down_16.0.bias", M, od[2], D, bf.G, S(0), T))) return rc;
     if ((rc = groupnorm_apply_nchw(bf.G, S(0), e->P(n + "down_16.1.weight").f32, e->P(n + "down_16.1.bias").f32, outs[2], out_dtype,
-                                   B, g, 0, od[2], geps, 1, st))) return rc;
+                                   B, gh, gw, 0, od[2], geps, 1, st))) return rc;
     // down_8: ConvT -> GN -> Conv1x1 -> GN -> GELU  (:428-434)
     if ((rc = gemm_stats(Xb, D, n + "down_8.0.weight", n + "down_8.0.bias", M, 4 * e->d8, D, bf.G, S(1), T))) return rc;
     if ((rc = groupnorm_apply(bf.G, S(1), e->P(n + "down_8.1.weight").f32, e->P(n + "down_8.1.bias").f32, bf.Gn, h, (long)4 * M, e->d8,
@@ -329,7 +389,7 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     if ((rc = gemm_stats(h ? bf.Gn : bf.Gn, e->d8, n + "down_8.2.weight", n + "down_8.2.bias", 4 * M, od[1], e->d8, bf.G2, S(2), 4 * T)))
         return rc;
     if ((rc = groupnorm_apply_nchw(bf.G2, S(2), e->P(n + "down_8.3.weight").f32, e->P(n + "down_8.3.bias").f32, outs[1], out_dtype, B,
-                                   g, 1, od[1], geps, 1, st))) return rc;
+                                   gh, gw, 1, od[1], geps, 1, st))) return rc;
     // down_4: ConvT -> GN -> GELU -> ConvT -> GN -> Conv1x1 -> GN -> GELU  (:417-426)
     if ((rc = gemm_stats(Xb, D, n + "down_4.0.weight", n + "down_4.0.bias", M, 4 * e->d4, D, bf.G, S(3), T))) return rc;
     if ((rc = groupnorm_apply(bf.G, S(3), e->P(n + "down_4.1.weight").f32, e->P(n + "down_4.1.bias").f32, bf.Gn, h, (long)4 * M, e->d4,
@@ -341,14 +401,14 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     if ((rc = gemm_stats(bf.G2n, e->d4 / 2, n + "down_4.5.weight", n + "down_4.5.bias", 16 * M, od[0], e->d4 / 2, bf.G3, S(5), 16 * T)))
         return rc;
     if ((rc = groupnorm_apply_nchw(bf.G3, S(5), e->P(n + "down_4.6.weight").f32, e->P(n + "down_4.6.bias").f32, outs[0], out_dtype, B,
-                                   g, 2, od[0], geps, 1, st))) return rc;
+                                   gh, gw, 2, od[0], geps, 1, st))) return rc;
     // down_32: Conv(k2,s2) -> GN -> Conv1x1 -> GN -> GELU  (:441-447)
     if ((rc = gemm_stats(bf.A32, 4 * D, n + "down_32.0.weight", n + "down_32.0.bias", M / 4, e->d32, 4 * D, bf.G, S(6), T / 4))) return rc;
     if ((rc = groupnorm_apply(bf.G, S(6), e->P(n + "down_32.1.weight").f32, e->P(n + "down_32.1.bias").f32, bf.Gn, h, (long)M / 4, e->d32,
                               (long)T / 4, geps, 0, st))) return rc;
     if ((rc = gemm_stats(bf.Gn, e->d32, n + "down_32.2.weight", n + "down_32.2.bias", M / 4, od[3], e->d32, bf.G2, S(7), T / 4))) return rc;
     if ((rc = groupnorm_apply_nchw(bf.G2, S(7), e->P(n + "down_32.3.weight").f32, e->P(n + "down_32.3.bias").f32, outs[3], out_dtype, B,
-                                   g / 2, 0, od[3], geps, 1, st))) return rc;
+                                   gh / 2, gw / 2, 0, od[3], geps, 1, st))) return rc;
     return 0;
 }
 
@@ -390,10 +450,10 @@ std::vector<int> chunk_schedule(const svb_encoder* e, int batch, int max_chunk) 
     return out;
 }
 
-size_t out_elems_per_image(const svb_encoder* e, int k) {
-    const int S = e->cfg.img_size;
+size_t out_elems_per_image(const svb_encoder* e, int k, int img_h = 0, int img_w = 0) {
+    if (img_h == 0) { img_h = e->cfg.img_size; img_w = e->cfg.img_size; }
     const int strides[4] = {4, 8, 16, 32};
-    const size_t hw = (size_t)(S / strides[k]) * (S / strides[k]);
+    const size_t hw = (size_t)(img_h / strides[k]) * (img_w / strides[k]);
     return hw * e->cfg.fpn_dims[k];
 }
 
@@ -532,6 +592,7 @@ void svb_encoder_destroy(svb_encoder_t* e) {
         if (kv.second.fold_b) cudaFree(kv.second.fold_b);
     }
     if (e->taps) cudaFree(e->taps);
+    e->drop_resized();
     for (bf16* r : e->relpack)
         if (r) cudaFree(r);
     auto& hp = e->hp;
@@ -587,6 +648,10 @@ int svb_encoder_load_param(svb_encoder_t* e, const char* key, const float* data,
     if (rc) return rc;
     p.loaded = true;
     e->fold_dirty = true;       // the folded qkv / lin1 operands are re-derived from the fp32 masters at the next bf16 forward
+    if (!e->pos_cache.empty() || !e->rel_cache.empty()) {
+        cudaStreamSynchronize((cudaStream_t)stream);   // a forward still reading the resized tables must finish before they are freed
+        e->drop_resized();
+    }
     return 0;
 }
 
@@ -627,6 +692,51 @@ int svb_encoder_forward(svb_encoder_t* e, const float* x, int batch, void* res2,
         b0 += B;
     }
     return 0;
+}
+
+size_t svb_encoder_workspace_bytes_hw(const svb_encoder_t* e, int chunk, int mode, int img_h, int img_w) {
+    if (!e || chunk <= 0 || img_h <= 0 || img_w <= 0) return 0;
+    const int p = e->cfg.patch_size;
+    return plan(e, chunk, mode, nullptr, (img_h / p) * (img_w / p)).total;
+}
+
+int svb_encoder_forward_hw(svb_encoder_t* e, const float* x, int batch, int img_h, int img_w, void* res2, void* res3, void* res4, void* res5,
+                           int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    SVB_REQUIRE(e && x && res2 && res3 && res4 && res5 && workspace, "svb_encoder_forward_hw: null argument");
+    SVB_REQUIRE(mode == SVB_MODE_BF16 || mode == SVB_MODE_FP32, "svb_encoder_forward_hw: bad mode %d", mode);
+    SVB_REQUIRE(out_dtype == SVB_DTYPE_F32 || out_dtype == SVB_DTYPE_BF16, "svb_encoder_forward_hw: bad out_dtype %d", out_dtype);
+    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward_hw: batch %d / chunk %d must be positive", batch, chunk);
+    const int p = e->cfg.patch_size;
+    SVB_REQUIRE(img_h > 0 && img_w > 0 && img_h % (32 * p) == 0 && img_w % (32 * p) == 0,
+                "svb_encoder_forward_hw: image %d x %d: both sides must be multiples of %d (token grid in multiples of 32)", img_h, img_w, 32 * p);
+    const int missing = svb_encoder_missing_params(e);
+    SVB_REQUIRE(missing == 0, "svb_encoder_forward_hw: %d parameters have not been loaded", missing);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
+    if (chunk > batch) chunk = batch;
+    const int T = (img_h / p) * (img_w / p);
+    const size_t need = plan(e, chunk, mode, nullptr, T).total;
+    SVB_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+    const Buffers bf = plan(e, chunk, mode, workspace, T);
+    const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
+    const size_t in_per_img = (size_t)e->cfg.in_chans * img_h * img_w;
+    char* res[4] = {(char*)res2, (char*)res3, (char*)res4, (char*)res5};
+    for (int b0 = 0; b0 < batch; b0 += chunk) {
+        const int B = std::min(chunk, batch - b0);
+        void* outs[4];
+        for (int k = 0; k < 4; ++k) outs[k] = res[k] + (size_t)b0 * out_elems_per_image(e, k, img_h, img_w) * osz;
+        int rc = forward_chunk(e, x + (size_t)b0 * in_per_img, B, outs, out_dtype, mode, bf, (cudaStream_t)stream, nullptr, img_h, img_w);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int svb_resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int dim, svb_stream_t stream) {
+    SVB_REQUIRE(src && dst, "svb_resize_pos_embed: null argument");
+    return resize_pos_embed(src, dst, h0, w0, h1, w1, dim, (cudaStream_t)stream);
+}
+int svb_resize_rel_pos(const float* src, float* dst, int len0, int len1, int head_dim, svb_stream_t stream) {
+    SVB_REQUIRE(src && dst, "svb_resize_rel_pos: null argument");
+    return resize_rel_pos(src, dst, len0, len1, head_dim, (cudaStream_t)stream);
 }
 
 int svb_encoder_forward_u8(svb_encoder_t* e, const uint8_t* const* images, const int* heights, const int* widths, const float* pixel_mean,
@@ -852,7 +962,7 @@ int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int gr
 
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream) {
     SVB_REQUIRE(x && out, "svb_im2col: null argument");
-    return im2col_patch(x, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, patch, (cudaStream_t)stream);
+    return im2col_patch(x, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, img, patch, (cudaStream_t)stream);
 }
 
 int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
@@ -865,7 +975,7 @@ int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma,
 int svb_groupnorm_apply_nchw(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,
                              int batch, int grid, int levels, int C, float eps, int gelu, svb_stream_t stream) {
     SVB_REQUIRE(x && stats && gamma && beta && out, "svb_groupnorm_apply_nchw: null argument");
-    return groupnorm_apply_nchw(x, stats, gamma, beta, out, out_dtype, batch, grid, levels, C, eps, gelu, (cudaStream_t)stream);
+    return groupnorm_apply_nchw(x, stats, gamma, beta, out, out_dtype, batch, grid, grid, levels, C, eps, gelu, (cudaStream_t)stream);
 }
 
 }  // extern "C"

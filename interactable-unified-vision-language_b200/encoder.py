@@ -247,23 +247,29 @@ class ImageEncoderViT(nn.Module):
         torch.cuda.current_stream().synchronize()
         self._weights_sig = sig
 
-    def _workspace(self, chunk: int, mode: int, device: torch.device) -> torch.Tensor:
-        key = (chunk, mode)
+    def _workspace(self, chunk: int, mode: int, device: torch.device, hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        hw = hw or (self.img_size, self.img_size)
+        key = (chunk, mode, hw)
         ws = self._ws.get(key)
         if ws is None or ws.device != device:
-            n = cabi.lib().svb_encoder_workspace_bytes(self._handle, chunk, mode)
+            n = cabi.lib().svb_encoder_workspace_bytes_hw(self._handle, chunk, mode, hw[0], hw[1])
             self._ws.clear()
             ws = torch.empty(n + 1024, dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
 
-    def _check_input(self, x: torch.Tensor) -> None:
+    def _check_input(self, x: torch.Tensor, square_only: bool = False) -> None:
         if x.dim() != 4 or x.shape[1] != self.cfg.in_chans:
             raise ValueError(f"expected (B,{self.cfg.in_chans},H,W), got {tuple(x.shape)}")
-        if x.shape[2] != self.img_size or x.shape[3] != self.img_size:
+        H, W = int(x.shape[2]), int(x.shape[3])
+        if H == self.img_size and W == self.img_size:
+            return
+        unit = 32 * self.cfg.patch_size
+        if square_only or H % unit or W % unit or H <= 0 or W <= 0:
             raise NotImplementedError(
-                f"input {tuple(x.shape[2:])}: only {self.img_size}x{self.img_size} inputs are implemented (the reference's "
-                "bicubic pos_embed / linear rel_pos resize fallback, image_encoder.py:111-114,319-330, is a 'next' row)")
+                f"input {(H, W)}: implemented are {self.img_size}x{self.img_size} and, through forward(), canvases whose sides are "
+                f"multiples of {unit} (the reference's bicubic pos_embed / linear rel_pos resize fallback, "
+                "image_encoder.py:111-114,319-330)")
 
     def _prepare(self, device: torch.device) -> None:
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -283,20 +289,30 @@ class ImageEncoderViT(nn.Module):
             xf = x.detach()
             if xf.dtype != torch.float32 or not xf.is_contiguous():
                 xf = xf.float().contiguous()
-            B = xf.shape[0]
-            S, od = self.img_size, self.cfg.fpn_dims
-            outs = [torch.empty(B, od[k], S // s, S // s, dtype=self.out_dtype, device=device)
+            B, H, W = xf.shape[0], int(xf.shape[2]), int(xf.shape[3])
+            od = self.cfg.fpn_dims
+            outs = [torch.empty(B, od[k], H // s, W // s, dtype=self.out_dtype, device=device)
                     for k, s in enumerate((4, 8, 16, 32))]
             if B == 0:
                 return dict(zip(("res2", "res3", "res4", "res5"), outs))
             chunk = max(1, min(int(self.max_chunk), B))
             mode = self._mode()
-            ws = self._workspace(chunk, mode, device)
-            base = (ws.data_ptr() + 1023) & ~1023
-            cabi.check(cabi.lib().svb_encoder_forward(
-                self._handle, xf.data_ptr(), B, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
-                outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
-                cabi.stream_ptr()), "svb_encoder_forward")
+            if H == self.img_size and W == self.img_size:
+                ws = self._workspace(chunk, mode, device)
+                base = (ws.data_ptr() + 1023) & ~1023
+                cabi.check(cabi.lib().svb_encoder_forward(
+                    self._handle, xf.data_ptr(), B, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                    outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
+                    cabi.stream_ptr()), "svb_encoder_forward")
+            else:
+                # other token grids: the reference's pos_embed / rel_pos resize fallbacks (scope row N3)
+                chunk = max(1, min(chunk, max(1, (4 * self.img_size * self.img_size) // (H * W))))
+                ws = self._workspace(chunk, mode, device, (H, W))
+                base = (ws.data_ptr() + 1023) & ~1023
+                cabi.check(cabi.lib().svb_encoder_forward_hw(
+                    self._handle, xf.data_ptr(), B, H, W, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                    outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
+                    cabi.stream_ptr()), "svb_encoder_forward_hw")
         return {"res2": outs[0], "res3": outs[1], "res4": outs[2], "res5": outs[3]}
 
     def forward_uint8(self, images, pixel_mean, pixel_std) -> Dict[str, torch.Tensor]:
@@ -346,7 +362,7 @@ class ImageEncoderViT(nn.Module):
         library (``svb_encoder_forward_host``).  Synchronous."""
         if x.is_cuda:
             raise ValueError("forward_host takes a CPU tensor")
-        self._check_input(x)
+        self._check_input(x, square_only=True)
         device = device or next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("the encoder parameters must live on a CUDA device")

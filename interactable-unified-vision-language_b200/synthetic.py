@@ -66,11 +66,13 @@ def _uniform(shape, fan_in: int, g: torch.Generator) -> torch.Tensor:
     return (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
 
 
-def make_images(batch: int, cfg: EncoderConfig, seed: int = 0) -> torch.Tensor:
-    """``randn(B,3,S,S)``: the post-normalisation range of real inputs (xdecoder_model.py:333)."""
+def make_images(batch: int, cfg: EncoderConfig, seed: int = 0, hw=None) -> torch.Tensor:
+    """``randn(B,3,S,S)``: the post-normalisation range of real inputs (xdecoder_model.py:333).  ``hw`` overrides the canvas
+    (scope row N3: e.g. the 1024 x 2048 pads of the reference's COCO evaluation)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
-    return torch.randn(batch, cfg.in_chans, cfg.img_size, cfg.img_size, generator=g)
+    h, w = hw if hw else (cfg.img_size, cfg.img_size)
+    return torch.randn(batch, cfg.in_chans, h, w, generator=g)
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:

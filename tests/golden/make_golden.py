@@ -39,6 +39,10 @@ CASES = {
     "vit_l_std": ("vit_l", 1, 0.02, 4096),
     "vit_h_std": ("vit_h", 1, 0.02, 4096),
     "vit_h_stress": ("vit_h", 1, 0.5, 4096),
+    # scope row N3: canvases other than 1024 x 1024 run the reference's bicubic pos_embed / linear rel_pos fallbacks
+    # (image_encoder.py:111-114,124-132,319-330); 5-tuples carry the (H, W) of the input
+    "tiny64_wide": ("tiny64", 1, 0.1, 4096, (1024, 2048)),
+    "tiny80_tall": ("tiny80", 1, 0.1, 4096, (1536, 512)),
 }
 WEIGHT_SEED, IMAGE_SEED = 1234, 0
 
@@ -62,10 +66,11 @@ def sample(t: torch.Tensor, n: int, rs: np.random.RandomState):
 
 
 def run_case(name: str):
-    preset, batch, rel_std, n = CASES[name]
+    preset, batch, rel_std, n = CASES[name][:4]
+    hw = CASES[name][4] if len(CASES[name]) > 4 else None
     cfg = ib.PRESETS[preset]
     sd = ib.make_state_dict(cfg, WEIGHT_SEED, rel_std=rel_std)
-    x = ib.make_images(batch, cfg, IMAGE_SEED)
+    x = ib.make_images(batch, cfg, IMAGE_SEED, hw=hw)
     enc = build_reference(cfg)
     missing = enc.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
@@ -90,7 +95,8 @@ def run_case(name: str):
     rs = np.random.RandomState(12345)
     blob = {"meta_preset": np.array(preset), "meta_batch": np.int64(batch), "meta_rel_std": np.float64(rel_std),
             "meta_weight_seed": np.int64(WEIGHT_SEED), "meta_image_seed": np.int64(IMAGE_SEED),
-            "meta_ref_seconds": np.float64(dt), "meta_torch": np.array(torch.__version__)}
+            "meta_ref_seconds": np.float64(dt), "meta_torch": np.array(torch.__version__),
+            "meta_hw": np.array(hw if hw else (cfg.img_size, cfg.img_size), dtype=np.int64)}
     for k, v in outs.items():
         for kk, vv in sample(torch.cat(v, 0), n, rs).items():
             blob[f"out.{k}.{kk}"] = vv

@@ -21,7 +21,8 @@ def _setup(case):
     g = load_golden(case)
     cfg = ib.PRESETS[str(g["meta_preset"])]
     sd = ib.make_state_dict(cfg, int(g["meta_weight_seed"]), rel_std=float(g["meta_rel_std"]))
-    x = ib.make_images(int(g["meta_batch"]), cfg, int(g["meta_image_seed"]))
+    hw = tuple(int(v) for v in g["meta_hw"]) if "meta_hw" in g else None
+    x = ib.make_images(int(g["meta_batch"]), cfg, int(g["meta_image_seed"]), hw=hw)
     enc = build_encoder(cfg)
     enc.load_state_dict(sd, strict=True)
     enc.to(DEV)
@@ -60,6 +61,37 @@ def test_tiny_bf16(case):
     g, cfg, sd, x, enc = _setup(case)
     # with N(0, 0.5^2) rel-pos tables the bias dominates the logits; bf16 q/k rounding is amplified -> looser bar
     _check(enc, x, g, "bf16", TOL_BF16 if case.endswith("std") else 3e-2)
+
+
+@pytest.mark.parametrize("case", ["tiny64_wide", "tiny80_tall"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_other_canvases_against_reference_goldens(case, precision):
+    """Scope row N3: 1024 x 2048 and 1536 x 512 inputs against goldens of the unmodified reference, which takes its
+    bicubic pos_embed (image_encoder.py:124-132) and linear rel_pos (:319-330) fallbacks on them."""
+    g, cfg, sd, x, enc = _setup(case)
+    out, errs = _check(enc, x, g, precision, TOL_FP32 if precision == "fp32" else TOL_BF16, taps=False)
+    H, W = x.shape[2:]
+    assert tuple(out["res2"].shape) == (1, 128, H // 4, W // 4) and tuple(out["res5"].shape) == (1, 1024, H // 32, W // 32)
+
+
+def test_resize_kernels_match_torch_interpolate():
+    """The two table fallbacks alone against the calls the reference makes: F.interpolate(..., mode='bicubic') on pos_embed
+    (image_encoder.py:124-132) and F.interpolate(..., mode='linear') on a rel_pos table (:321-330)."""
+    import torch.nn.functional as F
+    from iuvl_b200 import cabi
+    g = torch.Generator().manual_seed(3)
+    for (h1, w1) in ((64, 128), (96, 32), (32, 32), (128, 128)):
+        pos = torch.randn(1, 64, 64, 48, generator=g)
+        ref = F.interpolate(pos.permute(0, 3, 1, 2), scale_factor=(h1 / 64, w1 / 64), mode="bicubic").permute(0, 2, 3, 1)
+        src, dst = pos.to(DEV), torch.empty(1, h1, w1, 48, device=DEV)
+        cabi.check(cabi.lib().svb_resize_pos_embed(src.data_ptr(), dst.data_ptr(), 64, 64, h1, w1, 48, cabi.stream_ptr()))
+        assert torch.allclose(dst.cpu(), ref, rtol=1e-5, atol=2e-6), float((dst.cpu() - ref).abs().max())
+    for L1 in (255, 63, 191, 127, 27):
+        tab = torch.randn(127, 80, generator=g)
+        ref = F.interpolate(tab.reshape(1, 127, -1).permute(0, 2, 1), size=L1, mode="linear").reshape(-1, L1).permute(1, 0)
+        src, dst = tab.to(DEV), torch.empty(L1, 80, device=DEV)
+        cabi.check(cabi.lib().svb_resize_rel_pos(src.data_ptr(), dst.data_ptr(), 127, L1, 80, cabi.stream_ptr()))
+        assert torch.allclose(dst.cpu(), ref, rtol=1e-5, atol=2e-6), (L1, float((dst.cpu() - ref).abs().max()))
 
 
 def test_tiny_against_cpu_oracle_full_tensors():
@@ -192,4 +224,4 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError, match="forward pass only"):
         enc(x[:1].to(DEV))                       # grad enabled + requires_grad params
     with torch.no_grad(), pytest.raises(NotImplementedError):
-        enc(torch.zeros(1, 3, 512, 512, device=DEV))
+        enc(torch.zeros(1, 3, 1024, 1000, device=DEV))        # sides must be multiples of 32 patches

@@ -252,7 +252,7 @@ def test_attention_simt_bf16(ws, heads, hd):
 
 
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("levels,g,C", [(0, 64, 512), (1, 64, 256), (2, 64, 128), (0, 32, 1024), (1, 64, 72)])
+@pytest.mark.parametrize("levels,g,C", [(0, 64, 512), (1, 64, 256), (2, 64, 128), (0, 32, 1024), (1, 64, 72), (0, 16, 200)])
 def test_groupnorm_nchw_unshuffle(levels, g, C, out_dtype):
     """GroupNorm(1,C)+GELU on rows ordered (b,y,x,s1,..) -> NCHW; reference builds the NCHW tensor by explicit
     pixel un-shuffle and calls torch group_norm."""

@@ -14,13 +14,15 @@ def _run(case):
     g = load_golden(case)
     cfg = ib.PRESETS[str(g["meta_preset"])]
     sd = ib.make_state_dict(cfg, int(g["meta_weight_seed"]), rel_std=float(g["meta_rel_std"]))
-    x = ib.make_images(int(g["meta_batch"]), cfg, int(g["meta_image_seed"]))
+    hw = tuple(int(v) for v in g["meta_hw"]) if "meta_hw" in g else None
+    x = ib.make_images(int(g["meta_batch"]), cfg, int(g["meta_image_seed"]), hw=hw)
     taps = {}
     out = orc.encoder_forward_cfg(sd, x, cfg, tap=lambda n, t: taps.__setitem__(n, t))
     return g, out, taps
 
 
-@pytest.mark.parametrize("case", ["tiny64_std", "tiny64_stress", "tiny80_std", "tiny80_stress"])
+# *_wide / *_tall: canvases other than 1024 x 1024 -> the reference's bicubic pos_embed / linear rel_pos fallbacks (scope row N3)
+@pytest.mark.parametrize("case", ["tiny64_std", "tiny64_stress", "tiny80_std", "tiny80_stress", "tiny64_wide", "tiny80_tall"])
 def test_oracle_matches_reference_tiny(case):
     g, out, taps = _run(case)
     for k in ("res2", "res3", "res4", "res5"):

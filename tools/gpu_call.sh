@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_msda.py -q -x 2>&1 | tail -5
-timeout 600 python -m pytest tests/test_gpu_encoder.py -q -x -k "uint8" 2>&1 | tail -5
-timeout 300 python tools/msda_bench.py 8 2>&1 | tail -3
-python tools/prof_step.py --batch 8 --steps 2 > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gemm_tc2s -s 150 -c 8 -o gpurun_out/prof_gemm python tools/prof_step.py --batch 8 --steps 2 > gpurun_out/ncu_full.log 2>&1; echo full rc=$?; tail -2 gpurun_out/ncu_full.log
+timeout 600 python -m pytest tests/test_gpu_encoder.py -q -x -k "canvases or resize" 2>&1 | tail -8
+timeout 900 python -m pytest tests -q -x -m gpu > gpurun_out/t_all.log 2>&1; echo all rc=$?; tail -4 gpurun_out/t_all.log
+timeout 600 python bench.py --batch 16 --steps 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_n3.json 2> gpurun_out/bench_n3.err; echo rc=$?; python tools/summarize_bench.py gpurun_out/bench_n3.json
