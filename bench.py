@@ -134,6 +134,52 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_next_rows(torch, cabi, dev, pk):
+    """Kernel-alone CUDA-event timings of scope rows N1 / N2 (not part of `value`): the multi-scale deformable attention forward at
+    the step1.yaml geometry (4 images, bf16 values; an L2 -> SM gather) and the fused uint8 staging of 16 images (HBM-bound)."""
+    import ctypes as C
+    from iuvl_b200.msda import ms_deform_attn_forward
+    out = {}
+    shapes, M, D, P, L, N = [(128, 128), (64, 64), (32, 32)], 8, 64, 4, 3, 4
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, device=dev).bfloat16()
+    loc = (torch.rand(N, S, 1, 1, 1, 2, device=dev) + 0.05 * torch.randn(N, S, M, L, P, 2, device=dev)).contiguous()
+    aw = torch.softmax(torch.randn(N, S, M, L * P, device=dev), -1).reshape(N, S, M, L, P).contiguous()
+    sh, st = torch.tensor(shapes), torch.tensor([0, 128 * 128, 128 * 128 + 64 * 64])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(3):
+            ms_deform_attn_forward(value, sh, st, loc, aw)
+        e0.record()
+        for _ in range(10):
+            ms_deform_attn_forward(value, sh, st, loc, aw)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gather = N * S * M * L * P * 4 * D * 2
+    out["msda_forward"] = {"workload": "4 x (128^2+64^2+32^2) queries, 8 heads x 64 ch, 3 levels x 4 points, bf16", "us_per_launch": ms * 1e3,
+                           "gathered_gbs": gather / ms / 1e6, "bound": "L2->SM gather (value maps are L2-resident)"}
+    B = 16
+    imgs = [torch.randint(0, 256, (3, 1024, 1024), dtype=torch.uint8, device=dev) for _ in range(B)]
+    dst = torch.empty(B * 4096, 768, dtype=torch.bfloat16, device=dev)
+    ptrs = (C.c_void_p * B)(*[t.data_ptr() for t in imgs])
+    hs, wsz = (C.c_int * B)(*([1024] * B)), (C.c_int * B)(*([1024] * B))
+    mean, std = (C.c_float * 3)(123.675, 116.28, 103.53), (C.c_float * 3)(58.395, 57.12, 57.375)
+    lib = cabi.lib()
+    for _ in range(3):
+        cabi.check(lib.svb_stage_images_u8(ptrs, hs, wsz, B, 3, 1024, 16, mean, std, dst.data_ptr(), cabi.DTYPE_BF16, cabi.stream_ptr()))
+    e0.record()
+    for _ in range(10):
+        cabi.check(lib.svb_stage_images_u8(ptrs, hs, wsz, B, 3, 1024, 16, mean, std, dst.data_ptr(), cabi.DTYPE_BF16, cabi.stream_ptr()))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    byts = B * 3 * 1024 * 1024 * (1 + 2)
+    out["stage_u8"] = {"workload": "16 uint8 1024^2 images -> normalised bf16 patch rows", "us_per_launch": ms * 1e3, "gbs": byts / ms / 1e6,
+                       "frac_of_hbm_peak": byts / ms / 1e6 / pk["hbm_gbs"], "bound": "hbm"}
+    return out
+
+
 def workload_config(args, world):
     return {
         "workload": "SAM %s image-encoder forward, batch %d x 3x1024x1024 per GPU (BASELINE.json configs[3] shape), "
@@ -294,6 +340,13 @@ def main():
                        "frac_of_burst": value / world * flops_img / 1e12 / pk["bf16_burst"], "flops_per_image": flops_img},
     }
 
+    # ---------------- the "next" rows of the scope table: kernel-alone timings, for the record ----------------
+    next_rows = None
+    try:
+        next_rows = measure_next_rows(torch, cabi, dev, pk)
+    except Exception as e:  # noqa: BLE001  (never lose the headline line over an extra)
+        next_rows = {"error": str(e)[:200]}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         from oracle import sam_vit_oracle as orc       # the checker, timed as the reported CPU baseline (kind "port")
@@ -310,7 +363,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

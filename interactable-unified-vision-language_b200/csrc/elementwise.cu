@@ -60,29 +60,40 @@ struct U8Batch {
     int h[16], w[16];
     float mean[4], std[4];
 };
-template <typename T>
+template <typename T, int VEC>      // VEC consecutive kx per thread: 16 (one 16-pixel patch row, patch % 16 == 0) or 4
 __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, int img, int patch) {
     const int g = img / patch;                       // (square canvases only: larger canvases go through the fp32 entry point)
     const int pp = patch * patch;
     const int K = C * pp;
-    const size_t total4 = (size_t)B * g * g * K / 4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = i * 4;                      // flat output index (row-major [B*g*g, K]): coalesced stores
+    const size_t totalv = (size_t)B * g * g * K / VEC;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < totalv; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * VEC;                    // flat output index (row-major [B*g*g, K]): coalesced stores
         const int k = (int)(e % K);
         const size_t row = e / K;
         const int px = (int)(row % g), py = (int)((row / g) % g), b = (int)(row / ((size_t)g * g));
         const int c = k / pp, ky = (k % pp) / patch, kx = k % patch;
         const int y = py * patch + ky, x = px * patch + kx;
         const int h = bt.h[b], w = bt.w[b];
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (y < h) {
+        float v[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = 0.f;
+        if (y < h && x < w) {
             const uint8_t* src = bt.img[b] + ((size_t)c * h + y) * w + x;
             const float m = bt.mean[c], sd = bt.std[c];
+            uint8_t px8[VEC];
+            if (x + VEC <= w && (reinterpret_cast<uintptr_t>(src) & (VEC - 1)) == 0) {       // whole vector inside the row and aligned
+                if constexpr (VEC == 16) *reinterpret_cast<uint4*>(px8) = __ldg(reinterpret_cast<const uint4*>(src));
+                else *reinterpret_cast<uint32_t*>(px8) = __ldg(reinterpret_cast<const uint32_t*>(src));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (x + j < w) v[j] = __fdiv_rn((float)src[j] - m, sd);
+                for (int j = 0; j < VEC; ++j) px8[j] = (x + j < w) ? src[j] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                if (x + j < w) v[j] = __fdiv_rn((float)px8[j] - m, sd);
         }
-        Vec4<T>::store(out + e, v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4) Vec4<T>::store(out + e + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
 }
 
@@ -413,10 +424,18 @@ int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, c
             bt.img[i] = images[b0 + i]; bt.h[i] = hs[b0 + i]; bt.w[i] = ws[b0 + i];
         }
         for (int c = 0; c < 4; ++c) { bt.mean[c] = c < C ? mean[c] : 0.f; bt.std[c] = c < C ? stdv[c] : 1.f; }
-        const size_t total4 = (size_t)nb * row_elems / 4;
-        ProfScope prof(PC_OTHER, 0, (double)nb * C * img * img + (double)total4 * 4 * (out_bf16 ? 2 : 4), s);
-        if (out_bf16) stage_u8_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(bt, (bf16*)out + (size_t)b0 * row_elems, nb, C, img, patch);
-        else stage_u8_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(bt, (float*)out + (size_t)b0 * row_elems, nb, C, img, patch);
+        const int vec = (patch % 16 == 0) ? 16 : 4;
+        const size_t totalv = (size_t)nb * row_elems / vec;
+        ProfScope prof(PC_OTHER, 0, (double)nb * C * img * img + (double)nb * row_elems * (out_bf16 ? 2 : 4), s);
+        bf16* ob = (bf16*)out + (size_t)b0 * row_elems;
+        float* of = (float*)out + (size_t)b0 * row_elems;
+        if (vec == 16) {
+            if (out_bf16) stage_u8_kernel<bf16, 16><<<grid_for(totalv, 256), 256, 0, s>>>(bt, ob, nb, C, img, patch);
+            else stage_u8_kernel<float, 16><<<grid_for(totalv, 256), 256, 0, s>>>(bt, of, nb, C, img, patch);
+        } else {
+            if (out_bf16) stage_u8_kernel<bf16, 4><<<grid_for(totalv, 256), 256, 0, s>>>(bt, ob, nb, C, img, patch);
+            else stage_u8_kernel<float, 4><<<grid_for(totalv, 256), 256, 0, s>>>(bt, of, nb, C, img, patch);
+        }
         SVB_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

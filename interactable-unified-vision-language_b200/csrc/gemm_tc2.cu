@@ -488,7 +488,8 @@ template <int BN, int MODE, bool ONEBOX = false> struct Cfg3 {
     static constexpr int CHUNK_BYTES = OUTF32 ? 4096 : 2048;       // one staging box: 32 rows x 32 columns
     static constexpr int WARP_EPI_BYTES = NBOX * CHUNK_BYTES + (MODE == 4 ? 2048 : 0);   // boxes per epilogue warp (+ one bf16 box)
     static constexpr int EPI_BYTES = EPI_WARPS * WARP_EPI_BYTES;
-    static constexpr int STAGES = (BN == 256) ? ((OUTF32 && !ONEBOX) ? 4 : 5) : 6;
+    // BN = 256: fp32 boxes (4 KB) leave room for 4 stages with two boxes per warp or 5 with one; bf16 boxes (2 KB) for 5 / 6
+    static constexpr int STAGES = (BN == 256) ? (OUTF32 ? (ONEBOX ? 5 : 4) : (ONEBOX ? 6 : 5)) : 6;
     static constexpr int BIAS_BYTES = 2 * 2 * BN * 4;
     static constexpr int OFF_BARS = STAGES * STAGE_BYTES;
     static constexpr int OFF_BIAS = OFF_BARS + 256;
@@ -1032,6 +1033,13 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     }
     if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
     if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    // bf16 mode without GELU (qkv, proj): 6 stages + one staging box (measured 218 vs 222 us for qkv); with GELU the longer
+    // epilogue prefers two boxes (lin1 311 vs 314 us).  SVB_GEMM_BF16_ONEBOX=0 keeps 5 stages + two boxes everywhere.
+    static const int bf16_onebox = [] { const char* e = getenv("SVB_GEMM_BF16_ONEBOX"); return e ? atoi(e) : 1; }();
+    if (bf16_onebox && BN == 256 && !gelu) {
+        if (lnf) return launch_gemm2s<BN, EPI_BF16, false, true, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+        return launch_gemm2s<BN, EPI_BF16, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    }
     if (gelu && lnf) return launch_gemm2s<BN, EPI_BF16, true, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
     if (gelu) return launch_gemm2s<BN, EPI_BF16, true, false>(ma, mw, mo, mo2, M, N, K, ep, stream);
     if (lnf) return launch_gemm2s<BN, EPI_BF16, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
