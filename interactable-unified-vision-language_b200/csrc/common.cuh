@@ -53,6 +53,11 @@ struct Epilogue {
     const float* ln_c = nullptr;     // [N]
     int ln_parts = 0, ln_dim = 0;
     float ln_eps = 0.f;
+    // the same fold for GroupNorm(1, C) -> 1x1 conv (SimpleFPN, image_encoder.py:428-447): the statistics are per SAMPLE —
+    // gn_in_stats[sample] = (sum, sumsq) in fp64 over gn_in_rows rows x K channels, accumulated by the producing GEMM (`stats`).
+    // When set it replaces ln_stats as the source of mu / rstd (ln_c, ln_eps and the folded bias are used as above).
+    const double* gn_in_stats = nullptr;
+    int gn_in_rows = 0;
     // producer side (fp32 output + residual): a bf16 copy of the final rows (the next GEMM's A operand) and the partial
     // row statistics of the final rows: stat_out[row][(column / 128)] = (sum, sumsq) over that 128-column slab.
     void* out2 = nullptr;            // bf16 [M, ldo2]

@@ -61,6 +61,7 @@ struct svb_encoder {
     int attn_impl_bf16 = 0;         // 0: SIMT kernel, 1: tcgen05 kernel
     bool ln_fold = false;           // bf16 path: norm1 / norm2 folded into the qkv / lin1 GEMMs (no LayerNorm pass over HBM)
     bool fold_dirty = true;         // a parameter was (re)loaded since the folded weights were last derived
+    bool gn_fold = false;           // bf16 path: GroupNorm(1,C) -> 1x1 conv links of the neck folded the same way (down_8, down_4, down_32)
     int grid_pad = 0;               // window-padded token grid (70 for 64 / 14)
     std::vector<bf16*> relpack;     // per block: bf16 rel-pos table block of the tcgen05 attention kernel (attention_tc.cu)
     // scope row N3: tables resized for token grids other than the trained one (dropped whenever a parameter is reloaded)
@@ -243,6 +244,18 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
                     return rc;
             }
         }
+        if (e->gn_fold) {
+            // GroupNorm(1,C) directly followed by a 1x1 conv (image_encoder.py:430-432, 422-424, 443-445): same algebra, gamma / beta
+            // are per INPUT channel of the conv, the statistics per sample
+            const char* links[3][3] = {{"neck.down_8.2.", "neck.down_8.1.", nullptr}, {"neck.down_4.5.", "neck.down_4.4.", nullptr},
+                                       {"neck.down_32.2.", "neck.down_32.1.", nullptr}};
+            for (auto& l : links) {
+                const Param& W = e->P(std::string(l[0]) + "weight");
+                if ((rc = fold_layernorm(W.f32, e->P(std::string(l[0]) + "bias").f32, e->P(std::string(l[1]) + "weight").f32,
+                                         e->P(std::string(l[1]) + "bias").f32, W.b16, W.fold_c, W.fold_b, W.a, W.b, st)))
+                    return rc;
+            }
+        }
         e->fold_dirty = false;
     }
     auto produce = [&](Epilogue& ep, float2* stat) {      // epilogue of a GEMM that writes the residual stream
@@ -382,31 +395,67 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
     if ((rc = gemm_stats(Xb, D, n + "down_16.0.weight", n + "down_16.0.bias", M, od[2], D, bf.G, S(0), T))) return rc;
     if ((rc = groupnorm_apply_nchw(bf.G, S(0), e->P(n + "down_16.1.weight").f32, e->P(n + "down_16.1.bias").f32, outs[2], out_dtype,
                                    B, gh, gw, 0, od[2], geps, 1, st))) return rc;
+    // GroupNorm -> 1x1 conv links in the folded form (bf16 path): the producer writes the RAW conv output in bf16 (+ its per-sample
+    // sums), the consumer GEMM normalises in its epilogue; no GroupNorm pass, no fp32 intermediate.
+    const bool gfold = fold && e->gn_fold;
+    auto gemm_raw_bf16 = [&](const void* A, int lda, const std::string& wkey, const std::string& bkey, int m, int nn, int k, void* out,
+                             double* stats, int rps) {
+        Epilogue ep;
+        ep.bias = e->P(bkey).f32;
+        ep.out = out; ep.ldo = nn; ep.out_bf16 = 1;
+        ep.stats = stats; ep.rows_per_sample = rps;
+        return linear(mode, A, lda, e->P(wkey), m, nn, k, ep, st);
+    };
+    auto gemm_gnfold = [&](const void* A, int lda, const std::string& wkey, int m, int nn, int k, float* out, const double* in_stats,
+                           int in_rows, double* stats, int rps) {
+        const Param& W = e->P(wkey);
+        Epilogue ep;
+        ep.bias = W.fold_b; ep.ln_c = W.fold_c; ep.ln_eps = geps;
+        ep.gn_in_stats = in_stats; ep.gn_in_rows = in_rows;
+        ep.out = out; ep.ldo = nn;
+        ep.stats = stats; ep.rows_per_sample = rps;
+        return linear(mode, A, lda, W, m, nn, k, ep, st);
+    };
     // down_8: ConvT -> GN -> Conv1x1 -> GN -> GELU  (:428-434)
-    if ((rc = gemm_stats(Xb, D, n + "down_8.0.weight", n + "down_8.0.bias", M, 4 * e->d8, D, bf.G, S(1), T))) return rc;
-    if ((rc = groupnorm_apply(bf.G, S(1), e->P(n + "down_8.1.weight").f32, e->P(n + "down_8.1.bias").f32, bf.Gn, h, (long)4 * M, e->d8,
-                              (long)4 * T, geps, 0, st))) return rc;
-    if ((rc = gemm_stats(h ? bf.Gn : bf.Gn, e->d8, n + "down_8.2.weight", n + "down_8.2.bias", 4 * M, od[1], e->d8, bf.G2, S(2), 4 * T)))
-        return rc;
+    if (gfold) {
+        if ((rc = gemm_raw_bf16(Xb, D, n + "down_8.0.weight", n + "down_8.0.bias", M, 4 * e->d8, D, bf.Gn, S(1), T))) return rc;
+        if ((rc = gemm_gnfold(bf.Gn, e->d8, n + "down_8.2.weight", 4 * M, od[1], e->d8, bf.G2, S(1), 4 * T, S(2), 4 * T))) return rc;
+    } else {
+        if ((rc = gemm_stats(Xb, D, n + "down_8.0.weight", n + "down_8.0.bias", M, 4 * e->d8, D, bf.G, S(1), T))) return rc;
+        if ((rc = groupnorm_apply(bf.G, S(1), e->P(n + "down_8.1.weight").f32, e->P(n + "down_8.1.bias").f32, bf.Gn, h, (long)4 * M, e->d8,
+                                  (long)4 * T, geps, 0, st))) return rc;
+        if ((rc = gemm_stats(bf.Gn, e->d8, n + "down_8.2.weight", n + "down_8.2.bias", 4 * M, od[1], e->d8, bf.G2, S(2), 4 * T))) return rc;
+    }
     if ((rc = groupnorm_apply_nchw(bf.G2, S(2), e->P(n + "down_8.3.weight").f32, e->P(n + "down_8.3.bias").f32, outs[1], out_dtype, B,
                                    gh, gw, 1, od[1], geps, 1, st))) return rc;
     // down_4: ConvT -> GN -> GELU -> ConvT -> GN -> Conv1x1 -> GN -> GELU  (:417-426)
     if ((rc = gemm_stats(Xb, D, n + "down_4.0.weight", n + "down_4.0.bias", M, 4 * e->d4, D, bf.G, S(3), T))) return rc;
     if ((rc = groupnorm_apply(bf.G, S(3), e->P(n + "down_4.1.weight").f32, e->P(n + "down_4.1.bias").f32, bf.Gn, h, (long)4 * M, e->d4,
                               (long)4 * T, geps, 1, st))) return rc;
-    if ((rc = gemm_stats(bf.Gn, e->d4, n + "down_4.3.weight", n + "down_4.3.bias", 4 * M, 4 * (e->d4 / 2), e->d4, bf.G2, S(4), 4 * T)))
-        return rc;
-    if ((rc = groupnorm_apply(bf.G2, S(4), e->P(n + "down_4.4.weight").f32, e->P(n + "down_4.4.bias").f32, bf.G2n, h, (long)16 * M,
-                              e->d4 / 2, (long)16 * T, geps, 0, st))) return rc;
-    if ((rc = gemm_stats(bf.G2n, e->d4 / 2, n + "down_4.5.weight", n + "down_4.5.bias", 16 * M, od[0], e->d4 / 2, bf.G3, S(5), 16 * T)))
-        return rc;
+    if (gfold) {
+        if ((rc = gemm_raw_bf16(bf.Gn, e->d4, n + "down_4.3.weight", n + "down_4.3.bias", 4 * M, 4 * (e->d4 / 2), e->d4, bf.G2n, S(4), 4 * T)))
+            return rc;
+        if ((rc = gemm_gnfold(bf.G2n, e->d4 / 2, n + "down_4.5.weight", 16 * M, od[0], e->d4 / 2, bf.G3, S(4), 16 * T, S(5), 16 * T))) return rc;
+    } else {
+        if ((rc = gemm_stats(bf.Gn, e->d4, n + "down_4.3.weight", n + "down_4.3.bias", 4 * M, 4 * (e->d4 / 2), e->d4, bf.G2, S(4), 4 * T)))
+            return rc;
+        if ((rc = groupnorm_apply(bf.G2, S(4), e->P(n + "down_4.4.weight").f32, e->P(n + "down_4.4.bias").f32, bf.G2n, h, (long)16 * M,
+                                  e->d4 / 2, (long)16 * T, geps, 0, st))) return rc;
+        if ((rc = gemm_stats(bf.G2n, e->d4 / 2, n + "down_4.5.weight", n + "down_4.5.bias", 16 * M, od[0], e->d4 / 2, bf.G3, S(5), 16 * T)))
+            return rc;
+    }
     if ((rc = groupnorm_apply_nchw(bf.G3, S(5), e->P(n + "down_4.6.weight").f32, e->P(n + "down_4.6.bias").f32, outs[0], out_dtype, B,
                                    gh, gw, 2, od[0], geps, 1, st))) return rc;
     // down_32: Conv(k2,s2) -> GN -> Conv1x1 -> GN -> GELU  (:441-447)
-    if ((rc = gemm_stats(bf.A32, 4 * D, n + "down_32.0.weight", n + "down_32.0.bias", M / 4, e->d32, 4 * D, bf.G, S(6), T / 4))) return rc;
-    if ((rc = groupnorm_apply(bf.G, S(6), e->P(n + "down_32.1.weight").f32, e->P(n + "down_32.1.bias").f32, bf.Gn, h, (long)M / 4, e->d32,
-                              (long)T / 4, geps, 0, st))) return rc;
-    if ((rc = gemm_stats(bf.Gn, e->d32, n + "down_32.2.weight", n + "down_32.2.bias", M / 4, od[3], e->d32, bf.G2, S(7), T / 4))) return rc;
+    if (gfold) {
+        if ((rc = gemm_raw_bf16(bf.A32, 4 * D, n + "down_32.0.weight", n + "down_32.0.bias", M / 4, e->d32, 4 * D, bf.Gn, S(6), T / 4))) return rc;
+        if ((rc = gemm_gnfold(bf.Gn, e->d32, n + "down_32.2.weight", M / 4, od[3], e->d32, bf.G2, S(6), T / 4, S(7), T / 4))) return rc;
+    } else {
+        if ((rc = gemm_stats(bf.A32, 4 * D, n + "down_32.0.weight", n + "down_32.0.bias", M / 4, e->d32, 4 * D, bf.G, S(6), T / 4))) return rc;
+        if ((rc = groupnorm_apply(bf.G, S(6), e->P(n + "down_32.1.weight").f32, e->P(n + "down_32.1.bias").f32, bf.Gn, h, (long)M / 4, e->d32,
+                                  (long)T / 4, geps, 0, st))) return rc;
+        if ((rc = gemm_stats(bf.Gn, e->d32, n + "down_32.2.weight", n + "down_32.2.bias", M / 4, od[3], e->d32, bf.G2, S(7), T / 4))) return rc;
+    }
     if ((rc = groupnorm_apply_nchw(bf.G2, S(7), e->P(n + "down_32.3.weight").f32, e->P(n + "down_32.3.bias").f32, outs[3], out_dtype, B,
                                    gh / 2, gw / 2, 0, od[3], geps, 1, st))) return rc;
     return 0;
@@ -552,6 +601,14 @@ int svb_encoder_create(const svb_config_t* cfg, svb_encoder_t** out) {
     {
         const char* env = getenv("SVB_LN_FOLD");
         e->ln_fold = (D % 32 == 0) && gemm_bf16_tc_supports_fold() && !(env && atoi(env) == 0);
+        const char* genv = getenv("SVB_GN_FOLD");
+        e->gn_fold = e->ln_fold && !(genv && atoi(genv) == 0) && (e->d8 % 32 == 0) && ((e->d4 / 2) % 32 == 0) && (e->d32 % 32 == 0);
+        if (e->gn_fold) {
+            for (const char* k : {"neck.down_8.2.weight", "neck.down_4.5.weight", "neck.down_32.2.weight"}) {
+                int rc = alloc_fold_storage(e->params[k]);
+                if (rc) { svb_encoder_destroy(e); return rc; }
+            }
+        }
         if (e->ln_fold) {
             for (int i = 0; i < e->depth; ++i) {
                 const std::string b = "blocks." + std::to_string(i) + ".";

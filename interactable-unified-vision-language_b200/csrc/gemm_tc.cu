@@ -292,11 +292,13 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     SVB_REQUIRE((ep.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0, "gemm_bf16_tc: output must be 16-byte aligned");
     SVB_REQUIRE(!ep.stats || (ep.rows_per_sample % 32) == 0, "gemm_bf16_tc: rows_per_sample must be a multiple of 32");
     // CTA-pair kernel (gemm_tc2.cu) by default; SVB_GEMM_IMPL=1 selects the single-CTA kernel below (A/B comparisons)
-    const bool fold = ep.ln_stats || ep.out2 || ep.stat_out;
+    const bool fold = ep.ln_stats || ep.gn_in_stats || ep.out2 || ep.stat_out;
     if (fold) {
         SVB_REQUIRE(gemm_impl() != 1, "gemm_bf16_tc: the folded-LayerNorm epilogues need the CTA-pair kernel (unset SVB_GEMM_IMPL)");
         SVB_REQUIRE(N % 32 == 0, "gemm_bf16_tc: folded-LayerNorm epilogues need N %% 32 == 0 (N = %d)", N);
         SVB_REQUIRE(!ep.ln_stats || (ep.ln_c && ep.bias && ep.ln_parts > 0 && ep.ln_dim > 0), "gemm_bf16_tc: incomplete LayerNorm-fold arguments");
+        SVB_REQUIRE(!ep.gn_in_stats || (ep.ln_c && ep.bias && ep.gn_in_rows > 0 && !ep.ln_stats && !ep.act && !ep.resid && !ep.remap_g),
+                    "gemm_bf16_tc: incomplete / unsupported GroupNorm-fold arguments");
         SVB_REQUIRE(!(ep.out2 || ep.stat_out) || (ep.resid && !ep.out_bf16 && ep.remap_g == 0),
                     "gemm_bf16_tc: the bf16 copy / row statistics outputs need the fp32 residual epilogue");
         SVB_REQUIRE(!ep.out2 || ((ep.ldo2 % 4) == 0 && (reinterpret_cast<uintptr_t>(ep.out2) & 7) == 0), "gemm_bf16_tc: out2 must be 8-byte aligned");

@@ -774,13 +774,22 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if constexpr (LNF) {
                 for (int c = etid; c < BN; c += EPI_WARPS * 32) cs[c] = (nt0 + c < N) ? __ldg(ep.ln_c + nt0 + c) : 0.f;
                 if (row_ok) {
-                    float s1 = 0.f, s2 = 0.f;
-                    const float2* sp = ep.ln_stats + (size_t)row * ep.ln_parts;
-                    for (int p = 0; p < ep.ln_parts; ++p) { const float2 q = __ldg(sp + p); s1 += q.x; s2 += q.y; }
-                    const float inv = 1.0f / (float)ep.ln_dim;
-                    const float mu = s1 * inv;
-                    ln_r = rsqrtf(fmaxf(s2 * inv - mu * mu, 0.f) + ep.ln_eps);
-                    ln_nmu = -mu;
+                    if (ep.gn_in_stats) {             // GroupNorm(1,C) fold: statistics of the row's SAMPLE (fp64 sums)
+                        const int sample = row / ep.gn_in_rows;
+                        const double n = (double)ep.gn_in_rows * (double)K;
+                        const double mu = ep.gn_in_stats[2 * sample] / n;
+                        const double var = fmax(ep.gn_in_stats[2 * sample + 1] / n - mu * mu, 0.0);
+                        ln_r = (float)(1.0 / sqrt(var + (double)ep.ln_eps));
+                        ln_nmu = -(float)mu;
+                    } else {
+                        float s1 = 0.f, s2 = 0.f;
+                        const float2* sp = ep.ln_stats + (size_t)row * ep.ln_parts;
+                        for (int p = 0; p < ep.ln_parts; ++p) { const float2 q = __ldg(sp + p); s1 += q.x; s2 += q.y; }
+                        const float inv = 1.0f / (float)ep.ln_dim;
+                        const float mu = s1 * inv;
+                        ln_r = rsqrtf(fmaxf(s2 * inv - mu * mu, 0.f) + ep.ln_eps);
+                        ln_nmu = -mu;
+                    }
                 }
             }
             const int orow0 = (int)epilogue_out_row(ep, r0);  // a 32-row slab is contiguous in the (window-padded) output too
@@ -828,7 +837,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     v[2 * j] = x0; v[2 * j + 1] = x1;
                 }
-                if (MODE == EPI_F32 && ep.stats && row_ok) {
+                if ((MODE == EPI_F32 || MODE == EPI_BF16) && ep.stats && row_ok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         float a, b;
@@ -882,7 +891,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(empty_leader + as * 8);
             }
-            if (MODE == EPI_F32 && ep.stats) {
+            if ((MODE == EPI_F32 || MODE == EPI_BF16) && ep.stats) {
                 s_sum = warp_sum(s_sum);
                 s_sq = warp_sum(s_sq);
                 if (lane == 0 && slab) {
@@ -989,10 +998,12 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
         if (ep.out2 && ((reinterpret_cast<uintptr_t>(ep.out2) & 15) != 0 || (ep.ldo2 % 8) != 0)) return 0;
         mode = EPI_F32_RMW;
     } else if (ep.out_bf16) {
-        if (ep.resid || ep.stats) return 0;
+        if (ep.resid) return 0;
+        if (ep.stats && (ep.act || ep.ln_stats || ep.gn_in_stats)) return 0;     // statistics are taken before the activation only
         mode = EPI_BF16;
     } else {
         if (ep.act || ep.ln_stats || ep.remap_g) return 0;
+        if (ep.gn_in_stats && ep.resid) return 0;
         if (!ep.resid) mode = EPI_F32;
         else if (ep.resid == ep.out && ep.ldr == ep.ldo && ep.resid_mod == 0 && !ep.stats) mode = EPI_F32_REDADD;
         else return 0;
@@ -1014,7 +1025,7 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
         if (rc) return rc;
     }
     *done = true;
-    const bool lnf = ep.ln_stats != nullptr, gelu = ep.act == 1;
+    const bool lnf = ep.ln_stats != nullptr || ep.gn_in_stats != nullptr, gelu = ep.act == 1;
     if constexpr (BN == 256) {
         // producer mode: 5 stages + 1 residual box per warp (default) or 4 stages + 2 boxes.  Measured (interleaved A/B, 8 images):
         // lin2 351 vs 391 us, proj 133 vs 140 us — the deeper operand ring is worth more than the residual prefetch.
@@ -1027,6 +1038,10 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     }
     // fp32 modes: 5 pipeline stages + 1 staging box per warp (default; measured 337 vs 358 us for lin2) or 4 stages + 2 boxes
     static const int onebox = [] { const char* e = getenv("SVB_GEMM_ONEBOX"); return e ? atoi(e) : 1; }();
+    if (mode == EPI_F32 && lnf) {                                   // GroupNorm-fold consumer with fp32 output (+ its own statistics)
+        if (BN == 256) return launch_gemm2s<BN, EPI_F32, false, true, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+        return launch_gemm2s<BN, EPI_F32, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
+    }
     if (onebox && BN == 256) {
         if (mode == EPI_F32) return launch_gemm2s<BN, EPI_F32, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
         if (mode == EPI_F32_REDADD) return launch_gemm2s<BN, EPI_F32_REDADD, false, false, true>(ma, mw, mo, mo2, M, N, K, ep, stream);
@@ -1058,6 +1073,7 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
         const int rc0 = try_launch_streamlined<BN>(A, lda, W, ldw, M, N, K, ep, stream, &done);
         if (rc0 || done) return rc0;
     }
+    SVB_REQUIRE(!ep.gn_in_stats, "gemm_tc2: the GroupNorm-fold epilogue exists in the streamlined kernel only (unset SVB_GEMM_EPI / SVB_GEMM_CLUSTER)");
     const int pairs = (cl == 4 && M > 2 * BM_CTA) ? 2 : 1;
     CUtensorMap ma, mw;
     int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
