@@ -45,6 +45,9 @@ struct Epilogue {
     // optional output-row remap (token grid g x g -> padded grid gp x gp, the window_partition padding of
     // image_encoder.py:271-275 expressed as a store address): out row = (r / g^2) * gp^2 + ((r % g^2) / g) * gp + r % g
     int remap_g = 0, remap_gp = 0;
+    // with the remap: also write the PAD rows of the padded grid (= bf16(pad_bias), the qkv bias: pad tokens are zero after norm1,
+    // image_encoder.py:183-187,271-275) from otherwise idle warps of the GEMM, instead of a separate fill_pad_rows launch
+    const float* pad_bias = nullptr;
     // ---- LayerNorm folded into the GEMM (bf16 path; tcgen05 pair kernel only) ----
     // consumer side: A holds the UN-normalised rows x (bf16), W = bf16(gamma (.) W0), bias = b0 + W0 beta; with the row
     // statistics mu, rstd of x:  LayerNorm(x) W0^T + b0 = rstd * (x W^T - mu * ln_c) + bias,  ln_c[n] = sum_k W[n, k].

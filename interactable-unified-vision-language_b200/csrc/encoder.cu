@@ -307,10 +307,14 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
             ep.out = bf.QKV;
             ep.out_bf16 = h;
             ep.ldo = 3 * D;
-            if (padded) { ep.remap_g = g; ep.remap_gp = e->grid_pad; }
+            // pad tokens are zero after norm1 (image_encoder.py:183-187,271-275): their qkv rows are the (unfolded) bias, written by
+            // otherwise idle warps of the same GEMM
+            // SVB_PAD_IN_GEMM=1: idle warps of the qkv GEMM write the pad rows instead of a separate launch — measured neutral
+            // (same-box A/B, 16 images: 170.6 / 167.2 vs 171.6 / 169.7 images/s), so the separate 18 us launch stays the default
+            static const bool pad_in_gemm = [] { const char* v = getenv("SVB_PAD_IN_GEMM"); return v && atoi(v) == 1; }();
+            if (padded) { ep.remap_g = g; ep.remap_gp = e->grid_pad; if (pad_in_gemm) ep.pad_bias = e->P(p + "attn.qkv.bias").f32; }
             if ((rc = linear(mode, bf.Xn, D, e->P(p + "attn.qkv.weight"), M, 3 * D, D, ep, st))) return rc;
-            // pad tokens are zero after norm1 (image_encoder.py:183-187,271-275): their qkv rows are the (unfolded) bias
-            if (padded && (rc = fill_pad_rows((bf16*)bf.QKV, e->P(p + "attn.qkv.bias").f32, B, g, e->grid_pad, 3 * D, st))) return rc;
+            if (padded && !pad_in_gemm && (rc = fill_pad_rows((bf16*)bf.QKV, e->P(p + "attn.qkv.bias").f32, B, g, e->grid_pad, 3 * D, st))) return rc;
         }
         {   // windowed / global attention with decomposed rel-pos (image_encoder.py:246-253, 258-304, 340-376)
             if (tc) {

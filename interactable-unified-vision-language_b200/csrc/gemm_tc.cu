@@ -304,6 +304,10 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
         SVB_REQUIRE(!ep.out2 || ((ep.ldo2 % 4) == 0 && (reinterpret_cast<uintptr_t>(ep.out2) & 7) == 0), "gemm_bf16_tc: out2 must be 8-byte aligned");
     }
     if (gemm_impl() != 1) return gemm_bf16_tc_pair(A, lda, W, ldw, M, N, K, ep, stream);
+    if (ep.pad_bias && ep.remap_g) {       // this kernel does not write the pad rows itself
+        int rc = fill_pad_rows((bf16*)ep.out, ep.pad_bias, M / (ep.remap_g * ep.remap_g), ep.remap_g, ep.remap_gp, ep.ldo, stream);
+        if (rc) return rc;
+    }
     if (N <= 128) return launch_gemm<128>(A, lda, W, ldw, M, N, K, ep, stream);
     return launch_gemm<256>(A, lda, W, ldw, M, N, K, ep, stream);
 }

@@ -624,6 +624,29 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mma_commit_pair(&tmem_full[as], (uint16_t)(3u << lead));
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
+        } else if (rank == 1 && ep.pad_bias && ep.remap_g) {
+            // this warp has nothing to issue in the non-leader CTA: it writes the pad rows of the window-padded output (one slice
+            // per CTA pair).  pad index -> (y, x): first the right-hand strip of the g real rows, then the full bottom rows.
+            const int g = ep.remap_g, gp = ep.remap_gp;
+            const int npad = gp * gp - g * g, strip = g * (gp - g);
+            const int v8 = N / 8;
+            const int rows = (M / (g * g)) * npad;            // pad rows of this pass; one row per iteration and CTA pair,
+            bf16* o = reinterpret_cast<bf16*>(ep.out);        // the index arithmetic once per row, the lanes stride over its columns
+            for (int r = pair; r < rows; r += num_pairs) {
+                const int pi = r % npad, b = r / npad;
+                int y, x;
+                if (pi < strip) { y = pi / (gp - g); x = g + pi % (gp - g); }
+                else { y = g + (pi - strip) / gp; x = (pi - strip) % gp; }
+                bf16* orow = o + (((size_t)b * gp + y) * gp + x) * ep.ldo;
+                for (int c8 = lane; c8 < v8; c8 += 32) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.pad_bias + c8 * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.pad_bias + c8 * 8 + 4));
+                    uint4 u;
+                    u.x = pack_bf16x2(b0.x, b0.y); u.y = pack_bf16x2(b0.z, b0.w);
+                    u.z = pack_bf16x2(b1.x, b1.y); u.w = pack_bf16x2(b1.z, b1.w);
+                    *reinterpret_cast<uint4*>(orow + c8 * 8) = u;
+                }
+            }
         }
     } else {
         // ===================== epilogue (warps 2..9 of every CTA) =====================
@@ -1074,6 +1097,10 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
         if (rc0 || done) return rc0;
     }
     SVB_REQUIRE(!ep.gn_in_stats, "gemm_tc2: the GroupNorm-fold epilogue exists in the streamlined kernel only (unset SVB_GEMM_EPI / SVB_GEMM_CLUSTER)");
+    if (ep.pad_bias && ep.remap_g) {       // the generic kernel does not write the pad rows itself
+        int rc = fill_pad_rows((bf16*)ep.out, ep.pad_bias, M / (ep.remap_g * ep.remap_g), ep.remap_g, ep.remap_gp, ep.ldo, stream);
+        if (rc) return rc;
+    }
     const int pairs = (cl == 4 && M > 2 * BM_CTA) ? 2 : 1;
     CUtensorMap ma, mw;
     int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
