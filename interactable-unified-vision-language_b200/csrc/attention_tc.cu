@@ -1158,8 +1158,9 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     const int items = p.batch * 25 * p.heads;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
     attn_window_persistent_kernel<HD><<<grid, 352, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
     SVB_CHECK_CUDA(cudaGetLastError());

@@ -476,8 +476,9 @@ std::vector<int> chunk_schedule(const svb_encoder* e, int batch, int max_chunk) 
         for (int b0 = 0; b0 < batch; b0 += max_chunk) out.push_back(std::min(max_chunk, batch - b0));
         return out;
     }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long pairs = std::max(1, sms / 2);
     const long D = e->D, mlp = e->mlp;
     const long shp[4][2] = {{3 * D, D}, {D, D}, {mlp, D}, {D, mlp}};

@@ -52,20 +52,24 @@ template <> struct Pack16<bf16> {
     }
 };
 
-template <typename T>
+// PT = number of points when known at compile time (4: the reference's configuration, fully unrolled), 0 = run-time loop.
+// The body is branch-free: taps outside the map get weight 0 and a clamped (always valid) address, so the 4 x PT loads of a
+// level are independent and can all be in flight together (the gather is latency-bound otherwise).
+template <typename T, int PT>
 __global__ void __launch_bounds__(256)
 msda_forward_kernel(const T* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn, T* __restrict__ out,
-                    MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int P) {
+                    const __grid_constant__ MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int P) {
     constexpr int V = Pack16<T>::N;
     const int groups = D / V;                                     // 16-byte channel groups per head
+    const int np = PT ? PT : P;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int cg = (int)(idx % groups);
         const long unit = idx / groups;                           // (n, q, m) flattened: the reference's `sampling_index`
         const int m = (int)(unit % M);
         const long nq = unit / M;
         const int n = (int)(nq / Q);
-        const float* wp = attn + unit * L * P;
-        const float* lp = loc + unit * L * P * 2;
+        const float* wp = attn + unit * L * np;
+        const float2* lp = reinterpret_cast<const float2*>(loc) + unit * L * np;
         const size_t head_stride = (size_t)M * D;                 // elements between consecutive spatial positions
         const T* vbase = value + (size_t)n * S * head_stride + (size_t)m * D + (size_t)cg * V;
         float acc[V];
@@ -74,37 +78,32 @@ msda_forward_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
         for (int l = 0; l < L; ++l) {
             const int H = lv.h[l], W = lv.w[l];
             const T* vl = vbase + (size_t)lv.start[l] * head_stride;
-            for (int p = 0; p < P; ++p) {
-                const float lw_ = __ldg(lp), lh_ = __ldg(lp + 1), wt = __ldg(wp);
-                lp += 2;
-                wp += 1;
-                const float h_im = lh_ * H - 0.5f, w_im = lw_ * W - 0.5f;        // ms_deform_im2col_cuda.cuh:286-287
-                if (h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W) {
-                    const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+#pragma unroll
+            for (int p = 0; p < (PT ? PT : 1); ++p) {
+                for (int pr = 0; pr < (PT ? 1 : np); ++pr) {      // run-time point loop only in the generic instantiation
+                    const float2 xy = __ldg(lp);
+                    const float wt = __ldg(wp);
+                    ++lp;
+                    ++wp;
+                    const float h_im = xy.y * H - 0.5f, w_im = xy.x * W - 0.5f;      // ms_deform_im2col_cuda.cuh:286-287
+                    const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;     // :289
+                    const float hf = floorf(h_im), wf = floorf(w_im);
+                    const int h_low = (int)hf, w_low = (int)wf;
                     const int h_high = h_low + 1, w_high = w_low + 1;
-                    const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-                    const float w1 = hh * hw * wt, w2 = hh * lw * wt, w3 = lh * hw * wt, w4 = lh * lw * wt;
-                    float t[V];
-                    if (h_low >= 0 && w_low >= 0) {
-                        Pack16<T>::load(vl + ((size_t)h_low * W + w_low) * head_stride, t);
+                    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+                    const bool hl = inside && h_low >= 0, hhi = inside && h_high <= H - 1;
+                    const bool wl = w_low >= 0, whi = w_high <= W - 1;
+                    const float w1 = (hl && wl) ? hh * hw * wt : 0.f, w2 = (hl && whi) ? hh * lw * wt : 0.f;
+                    const float w3 = (hhi && wl) ? lh * hw * wt : 0.f, w4 = (hhi && whi) ? lh * lw * wt : 0.f;
+                    const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_high, 0), H - 1);
+                    const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_high, 0), W - 1);
+                    float t1[V], t2[V], t3[V], t4[V];
+                    Pack16<T>::load(vl + ((size_t)y0 * W + x0) * head_stride, t1);
+                    Pack16<T>::load(vl + ((size_t)y0 * W + x1) * head_stride, t2);
+                    Pack16<T>::load(vl + ((size_t)y1 * W + x0) * head_stride, t3);
+                    Pack16<T>::load(vl + ((size_t)y1 * W + x1) * head_stride, t4);
 #pragma unroll
-                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t[i], acc[i]);
-                    }
-                    if (h_low >= 0 && w_high <= W - 1) {
-                        Pack16<T>::load(vl + ((size_t)h_low * W + w_high) * head_stride, t);
-#pragma unroll
-                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w2, t[i], acc[i]);
-                    }
-                    if (h_high <= H - 1 && w_low >= 0) {
-                        Pack16<T>::load(vl + ((size_t)h_high * W + w_low) * head_stride, t);
-#pragma unroll
-                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w3, t[i], acc[i]);
-                    }
-                    if (h_high <= H - 1 && w_high <= W - 1) {
-                        Pack16<T>::load(vl + ((size_t)h_high * W + w_high) * head_stride, t);
-#pragma unroll
-                        for (int i = 0; i < V; ++i) acc[i] = fmaf(w4, t[i], acc[i]);
-                    }
+                    for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t1[i], fmaf(w2, t2[i], fmaf(w3, t3[i], fmaf(w4, t4[i], acc[i]))));
                 }
             }
         }
@@ -150,14 +149,18 @@ extern "C" int svb_ms_deform_attn_forward(const void* value, const int32_t* spat
     const double bytes = (double)batch * num_query * num_heads *
                          ((double)num_levels * num_points * (12.0 + 4.0 * channels * (vec == 8 ? 2 : 4)) + (double)channels * (vec == 8 ? 2 : 4));
     ProfScope prof(PC_OTHER, 0, bytes, (cudaStream_t)stream);
-    if (dtype == SVB_DTYPE_BF16)
-        msda_forward_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)value, sampling_locations, attention_weights, (bf16*)out,
-                                                                             lv, total, spatial_size, num_heads, channels, num_levels,
-                                                                             num_query, num_points);
-    else
-        msda_forward_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)value, sampling_locations, attention_weights,
-                                                                              (float*)out, lv, total, spatial_size, num_heads, channels,
-                                                                              num_levels, num_query, num_points);
+#define SVB_MSDA(TT, PT)                                                                                                         \
+    msda_forward_kernel<TT, PT><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT*)value, sampling_locations, attention_weights, (TT*)out, \
+                                                                           lv, total, spatial_size, num_heads, channels, num_levels,        \
+                                                                           num_query, num_points)
+    if (dtype == SVB_DTYPE_BF16) {
+        if (num_points == 4) SVB_MSDA(bf16, 4);
+        else SVB_MSDA(bf16, 0);
+    } else {
+        if (num_points == 4) SVB_MSDA(float, 4);
+        else SVB_MSDA(float, 0);
+    }
+#undef SVB_MSDA
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
