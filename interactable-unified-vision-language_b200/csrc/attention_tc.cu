@@ -152,7 +152,11 @@ template <int HD, int NST_> struct GCfg {
     static constexpr int TM_S = 0, TM_O = 256, TM_COLS = 512;   // S_i at 128*i (P_i aliases its first 64), O_i at 256 + 128*i
 };
 
-template <int HD, int NST>
+// ONEPASS: from the second key tile on, the softmax reads S from tensor memory ONCE: P = exp2(x - m_ref) with the reference
+// maximum of the previous tiles while the tile's own maximum is tracked alongside; if it exceeds m_ref by more than 2^8, O and the
+// row sum are rescaled at the start of the NEXT tile (P may transiently exceed 2^8, which bf16 / fp32 hold without loss).  The
+// two-pass form (maximum first) remains for the first tile and as the A/B variant.
+template <int HD, int NST, bool ONEPASS>
 // 10 warps are allocated as 12 (warp allocation granularity 4): the register cap is 65536 / 384 = 168 per thread
 __global__ void __launch_bounds__(320, 1)
 attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
@@ -336,6 +340,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
         ptx::mbar_arrive(&bars[C::B_PFULL + i]);                   // phase 0: S_i / O_i columns may be overwritten
 
         float m_ref = -INFINITY;
+        float x_over = 0.f;                                          // ONEPASS: previous tile's maximum exponent relative to m_ref
         f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
         const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
 #pragma unroll 1
@@ -344,25 +349,33 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
             ptx::tc_fence_after();
             const float bh0 = stg[(2 * j) * 32 + lane], bh1 = stg[(2 * j + 1) * 32 + lane];
             uint32_t va[32], vb[32];
-            // ---- pass A: raw maxima of the two key rows ----
-            ptx::tmem_ld_x32(s_tmem, va);
-            ptx::tmem_ld_wait_dep(va);
-            ptx::tmem_ld_x32(s_tmem + 32, vb);
-            float sm0 = max32(va, -INFINITY);
-            ptx::tmem_ld_wait_dep(vb);
-            ptx::tmem_ld_x32(s_tmem + 64, va);
-            sm0 = max32(vb, sm0);
-            ptx::tmem_ld_wait_dep(va);
-            ptx::tmem_ld_x32(s_tmem + 96, vb);
-            float sm1 = max32(va, -INFINITY);
-            ptx::tmem_ld_wait_dep(vb);
-            ptx::tmem_ld_x32(s_tmem, va);                          // first chunk of pass B
-            sm1 = max32(vb, sm1);
-            // upper bound of the row maximum in log2 units (scale > 0)
-            const float mb = fmaxf(fmaf(sm0, scale_log2, bh0), fmaf(sm1, scale_log2, bh1)) + bwmax;
-            const bool need = mb > m_ref + RESCALE_THRESHOLD;      // always true for j == 0
+            float m_new;
+            bool need;
+            if (!ONEPASS || j == 0) {
+                // ---- pass A: raw maxima of the two key rows ----
+                ptx::tmem_ld_x32(s_tmem, va);
+                ptx::tmem_ld_wait_dep(va);
+                ptx::tmem_ld_x32(s_tmem + 32, vb);
+                float sm0 = max32(va, -INFINITY);
+                ptx::tmem_ld_wait_dep(vb);
+                ptx::tmem_ld_x32(s_tmem + 64, va);
+                sm0 = max32(vb, sm0);
+                ptx::tmem_ld_wait_dep(va);
+                ptx::tmem_ld_x32(s_tmem + 96, vb);
+                float sm1 = max32(va, -INFINITY);
+                ptx::tmem_ld_wait_dep(vb);
+                ptx::tmem_ld_x32(s_tmem, va);                      // first chunk of pass B
+                sm1 = max32(vb, sm1);
+                // upper bound of the row maximum in log2 units (scale > 0)
+                const float mb = fmaxf(fmaf(sm0, scale_log2, bh0), fmaf(sm1, scale_log2, bh1)) + bwmax;
+                need = mb > m_ref + RESCALE_THRESHOLD;             // always true for j == 0
+                m_new = need ? mb : m_ref;
+            } else {
+                ptx::tmem_ld_x32(s_tmem, va);                      // first chunk of the single pass
+                need = x_over > RESCALE_THRESHOLD;                 // the previous tile's maximum relative to m_ref
+                m_new = need ? m_ref + x_over : m_ref;
+            }
             if (__any_sync(0xffffffffu, need)) {
-                const float m_new = need ? mb : m_ref;
                 if (j > 0) {
                     const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
                     ptx::mbar_wait(&bars[C::B_PVDONE + i], (j - 1) & 1);   // O_i holds tiles 0..j-1
@@ -390,6 +403,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                 }
                 m_ref = m_new;
             }
+            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
             const f32x2 d0_2 = f2_pack(bh0 - m_ref, bh0 - m_ref), d1_2 = f2_pack(bh1 - m_ref, bh1 - m_ref);
             // ---- pass B: P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
 #define SVB_PASS_B(V, CHUNK)                                                                             \
@@ -405,6 +419,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                     float a0, a1, a2, a3;                                                                \
                     f2_unpack(x01, a0, a1);                                                              \
                     f2_unpack(x23, a2, a3);                                                              \
+                    if (ONEPASS) { xa = fmax3(xa, a0, a1); xb = fmax3(xb, a2, a3); }                      \
                     const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
                     const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);                      \
                     l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
@@ -426,6 +441,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
             ptx::tmem_ld_wait_dep(vb);
             SVB_PASS_B(vb, 3)
 #undef SVB_PASS_B
+            x_over = fmaxf(xa, xb);
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&bars[C::B_PFULL + i]);
@@ -1072,14 +1088,18 @@ int launch_global(const AttnTcParams& p, cudaStream_t stream) {
         if ((rc = encode_tmap_nd_bf16(&m[4], p.rel_pack, 2, rd, rs, hm, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&m[5], p.rel_pack, 2, rd, rs, ht, 32))) return rc;
     }
+    // SVB_ATTNG_ONEPASS=0 selects the two-pass softmax (A/B comparisons)
+    static const bool onepass = [] { const char* e = getenv("SVB_ATTNG_ONEPASS"); return !(e && atoi(e) == 0); }();
     static bool attr_set = false;
     if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     dim3 grid(T / 256, p.heads, p.batch);
-    attn_global_kernel<HD, NST><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
+    if (onepass) attn_global_kernel<HD, NST, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
+    else attn_global_kernel<HD, NST, false><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
