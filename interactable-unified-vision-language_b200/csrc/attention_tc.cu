@@ -1038,25 +1038,28 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
 // ---------------------------------------------------------------------------------------------------------------
 // pad rows of the padded [B, gp, gp, ld] qkv tensor = the qkv bias (pad tokens are zero AFTER norm1, image_encoder.py:183-187,
 // 271-275, so their k / v are b_k / b_v); written once per windowed block before the attention kernel reads it.
-__global__ void fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int B, int g, int gp, int ld) {
-    const int npad = gp * gp - g * g;
+__global__ void __launch_bounds__(256)
+fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int B, int g, int gp, int ld) {
+    // one warp per pad row: the (image, y, x) arithmetic once per row, the lanes stride over its 16-byte pieces
+    const int npad = gp * gp - g * g, strip = g * (gp - g);
     const int v8 = ld / 8;
-    const long total = (long)B * npad * v8;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % v8);
-        const long r = i / v8;
-        const int pi = (int)(r % npad), b = (int)(r / npad);
+    const int rows = B * npad;
+    const int lane = threadIdx.x & 31;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
+        const int pi = r % npad, b = r / npad;
         // pad index -> (y, x): first the right-hand strip of the g real rows, then the full bottom rows
         int y, x;
-        const int strip = g * (gp - g);
         if (pi < strip) { y = pi / (gp - g); x = g + pi % (gp - g); }
         else { y = g + (pi - strip) / gp; x = (pi - strip) % gp; }
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
-        uint4 u;
-        u.x = pack_bf16x2(b0.x, b0.y); u.y = pack_bf16x2(b0.z, b0.w);
-        u.z = pack_bf16x2(b1.x, b1.y); u.w = pack_bf16x2(b1.z, b1.w);
-        *reinterpret_cast<uint4*>(qkv + (((size_t)b * gp + y) * gp + x) * ld + c8 * 8) = u;
+        bf16* orow = qkv + (((size_t)b * gp + y) * gp + x) * ld;
+        for (int c8 = lane; c8 < v8; c8 += 32) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+            uint4 u;
+            u.x = pack_bf16x2(b0.x, b0.y); u.y = pack_bf16x2(b0.z, b0.w);
+            u.z = pack_bf16x2(b1.x, b1.y); u.w = pack_bf16x2(b1.z, b1.w);
+            *reinterpret_cast<uint4*>(orow + c8 * 8) = u;
+        }
     }
 }
 
@@ -1210,7 +1213,8 @@ int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaSt
 int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream) {
     SVB_REQUIRE(ld % 8 == 0, "fill_pad_rows: row length must be a multiple of 8");
     const long total = (long)B * (gp * gp - g * g) * (ld / 8);
-    const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+    const long rows = (long)B * (gp * gp - g * g);
+    const int blocks = (int)std::min<long>((rows + 7) / 8, 148 * 8);
     ProfScope prof(PC_OTHER, 0.0, (double)total * 16.0, stream);
     fill_pad_rows_kernel<<<blocks, 256, 0, stream>>>(qkv, bias, B, g, gp, ld);
     SVB_CHECK_CUDA(cudaGetLastError());
