@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_encoder.py -q -x -k "attention or tiny_bf16 or full_size" 2>&1 | tail -3
-SVB_PROF_DETAIL=1 timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-python tools/summarize_bench.py gpurun_out/bench_default.json
-grep "prof cat 4" gpurun_out/bench_default.err | sort -k12 -n -r | head -4
+python tools/prof_step.py --batch 12 --steps 2 > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python tools/prof_step.py --batch 12 --steps 2 > gpurun_out/ncu_list.log 2>&1; echo list rc=$?
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc2s -s 140 -c 8 -o gpurun_out/prof_gemm python tools/prof_step.py --batch 12 --steps 2 > gpurun_out/ncu_full.log 2>&1; echo full rc=$?; tail -2 gpurun_out/ncu_full.log
