@@ -158,7 +158,25 @@ def measure_next_rows(torch, cabi, dev, pk):
     ms = e0.elapsed_time(e1) / 10
     gather = N * S * M * L * P * 4 * D * 2
     out["msda_forward"] = {"workload": "4 x (128^2+64^2+32^2) queries, 8 heads x 64 ch, 3 levels x 4 points, bf16", "us_per_launch": ms * 1e3,
-                           "gathered_gbs": gather / ms / 1e6, "bound": "L2->SM gather (value maps are L2-resident)"}
+                           "gathered_gbs": gather / ms / 1e6, "bound": "L1/L2->SM gather (value maps are L2-resident)"}
+    # the whole MSDeformAttn module forward (4 GEMMs + the fused softmax / location / gather kernel), d_model 512
+    from iuvl_b200.msda import MSDeformAttn
+    mod = MSDeformAttn(512, 3, 8, 4).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.05)
+        xq = torch.randn(N, S, 512, device=dev).bfloat16()
+        rp = torch.rand(N, S, 3, 2, device=dev)
+        for _ in range(2):
+            mod(xq, rp, xq, sh, st)
+        e0.record()
+        for _ in range(5):
+            mod(xq, rp, xq, sh, st)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["msda_module"] = {"workload": "MSDeformAttn.forward, d_model 512, 4 images x 21504 queries, bf16", "ms_per_layer": ms,
+                          "images_per_s_per_layer": N / ms * 1e3}
     B = 16
     imgs = [torch.randint(0, 256, (3, 1024, 1024), dtype=torch.uint8, device=dev) for _ in range(B)]
     dst = torch.empty(B * 4096, 768, dtype=torch.bfloat16, device=dev)

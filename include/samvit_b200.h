@@ -174,6 +174,16 @@ int svb_ms_deform_attn_forward(const void* value, const int32_t* spatial_shapes,
                                int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_points,
                                svb_stream_t stream);
 
+/* The sampling core with the head of MSDeformAttn.forward (ops/modules/ms_deform_attn.py:97-112) fused in: instead of materialised
+ * sampling_locations / attention_weights it takes `offsets_and_logits` = the fp32 output rows [N*Lq, M*L*P*3] of the module's two
+ * query Linears (M*L*P*2 sampling offsets laid out (M,L,P,2), then M*L*P attention logits laid out (M,L*P)) and
+ * `reference_points` (N,Lq,L,ref_dim), ref_dim 2 (points) or 4 (boxes); the softmax over L*P and the location arithmetic happen
+ * in the kernel. */
+int svb_ms_deform_attn_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                                     const float* reference_points, int ref_dim, const float* offsets_and_logits, void* out, int dtype,
+                                     int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                                     int num_points, svb_stream_t stream);
+
 /* ---- measurement helpers (bench.py): launch accounting and a CUDA-event profiler.  Between start and stop every kernel
  * launch of this library is bracketed by events on its launch stream; stop synchronises the device and returns, per
  * category {0 GEMM, 1 windowed attention, 2 global attention, 3 norms, 4 other}, the summed device milliseconds,

@@ -59,6 +59,7 @@ SYMBOLS = {
     "svb_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _f, _i, _vp]),
     "svb_ms_deform_attn_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "svb_ms_deform_attn_fused_forward": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_profile_start": (_i, []),
     "svb_profile_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "svb_launch_count": (C.c_int64, []),

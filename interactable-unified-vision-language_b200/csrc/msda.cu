@@ -111,6 +111,90 @@ msda_forward_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
     }
 }
 
+// The same gather with the head of MSDeformAttn.forward fused in (ops/modules/ms_deform_attn.py:97-112): instead of materialised
+// sampling_locations / attention_weights tensors it takes `raw` = the output row of the two Linear layers on the query
+// ([N*Lq, M*L*P*3]: M*L*P*2 sampling offsets, then M*L*P attention logits) and the reference points, and computes per
+// (n, q, head) the softmax over the L*P logits (:99) and  loc = ref + offset / (W_l, H_l)  (:102-105; boxes, ref_dim 4: ref_xy +
+// offset / P * ref_wh * 0.5, :106-108) on the fly.  LP = L * P must be <= 32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_fused_kernel(const T* __restrict__ value, const float* __restrict__ raw, const float* __restrict__ ref, T* __restrict__ out,
+                  const __grid_constant__ MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int P, int ref_dim) {
+    constexpr int V = Pack16<T>::N;
+    const int groups = D / V;
+    const int LP = L * P, MLP = M * LP;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % groups);
+        const long unit = idx / groups;
+        const int m = (int)(unit % M);
+        const long nq = unit / M;                                  // n * Q + q
+        const int n = (int)(nq / Q);
+        const float* row = raw + nq * (size_t)(3 * MLP);
+        const float* offp = row + (size_t)m * LP * 2;
+        const float* logp = row + 2 * (size_t)MLP + (size_t)m * LP;
+        const float* rp = ref + nq * (size_t)(L * ref_dim);
+        // softmax over the L*P logits of this head (F.softmax(..., -1), fp32)
+        float mx = -INFINITY;
+        for (int j = 0; j < LP; ++j) mx = fmaxf(mx, __ldg(logp + j));
+        float den = 0.f;
+        for (int j = 0; j < LP; ++j) den += expf(__ldg(logp + j) - mx);
+        const float inv_den = 1.f / den;
+        const size_t head_stride = (size_t)M * D;
+        const T* vbase = value + (size_t)n * S * head_stride + (size_t)m * D + (size_t)cg * V;
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.h[l], W = lv.w[l];
+            const T* vl = vbase + (size_t)lv.start[l] * head_stride;
+            const float rx = __ldg(rp + l * ref_dim), ry = __ldg(rp + l * ref_dim + 1);
+            for (int p = 0; p < P; ++p) {
+                const int j = l * P + p;
+                const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + j);
+                const float wt = expf(__ldg(logp + j) - mx) * inv_den;
+                const float loc_x = ref_dim == 2 ? rx + off.x / (float)W : rx + off.x / (float)P * __ldg(rp + l * ref_dim + 2) * 0.5f;
+                const float loc_y = ref_dim == 2 ? ry + off.y / (float)H : ry + off.y / (float)P * __ldg(rp + l * ref_dim + 3) * 0.5f;
+                const float h_im = loc_y * H - 0.5f, w_im = loc_x * W - 0.5f;
+                const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+                const float hf = floorf(h_im), wf = floorf(w_im);
+                const int h_low = (int)hf, w_low = (int)wf;
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+                const bool hl = inside && h_low >= 0, hhi = inside && h_high <= H - 1;
+                const bool wl = w_low >= 0, whi = w_high <= W - 1;
+                const float w1 = (hl && wl) ? hh * hw * wt : 0.f, w2 = (hl && whi) ? hh * lw * wt : 0.f;
+                const float w3 = (hhi && wl) ? lh * hw * wt : 0.f, w4 = (hhi && whi) ? lh * lw * wt : 0.f;
+                const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_high, 0), H - 1);
+                const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_high, 0), W - 1);
+                float t1[V], t2[V], t3[V], t4[V];
+                Pack16<T>::load(vl + ((size_t)y0 * W + x0) * head_stride, t1);
+                Pack16<T>::load(vl + ((size_t)y0 * W + x1) * head_stride, t2);
+                Pack16<T>::load(vl + ((size_t)y1 * W + x0) * head_stride, t3);
+                Pack16<T>::load(vl + ((size_t)y1 * W + x1) * head_stride, t4);
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t1[i], fmaf(w2, t2[i], fmaf(w3, t3[i], fmaf(w4, t4[i], acc[i]))));
+            }
+        }
+        Pack16<T>::store(out + unit * D + (size_t)cg * V, acc);
+    }
+}
+
+int msda_levels(MsdaLevels& lv, const int32_t* spatial_shapes, const int32_t* level_start_index, int num_levels, int spatial_size,
+                const char* who) {
+    SVB_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS, "%s: %d levels (1..%d supported)", who, num_levels, MSDA_MAX_LEVELS);
+    long covered = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        lv.h[l] = spatial_shapes[2 * l];
+        lv.w[l] = spatial_shapes[2 * l + 1];
+        lv.start[l] = level_start_index[l];
+        SVB_REQUIRE(lv.h[l] > 0 && lv.w[l] > 0 && lv.start[l] >= 0 && (long)lv.start[l] + (long)lv.h[l] * lv.w[l] <= spatial_size,
+                    "%s: level %d (%d x %d at %d) does not fit in %d positions", who, l, lv.h[l], lv.w[l], lv.start[l], spatial_size);
+        covered += (long)lv.h[l] * lv.w[l];
+    }
+    SVB_REQUIRE(covered == spatial_size, "%s: the levels cover %ld positions, value has %d", who, covered, spatial_size);
+    return 0;
+}
+
 }  // namespace
 }  // namespace svb
 
@@ -123,25 +207,16 @@ extern "C" int svb_ms_deform_attn_forward(const void* value, const int32_t* spat
     SVB_REQUIRE(value && spatial_shapes && level_start_index && sampling_locations && attention_weights && out,
                 "svb_ms_deform_attn_forward: null argument");
     SVB_REQUIRE(dtype == SVB_DTYPE_F32 || dtype == SVB_DTYPE_BF16, "svb_ms_deform_attn_forward: bad dtype %d", dtype);
-    SVB_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS, "svb_ms_deform_attn_forward: %d levels (1..%d supported)", num_levels,
-                MSDA_MAX_LEVELS);
     const int vec = dtype == SVB_DTYPE_BF16 ? 8 : 4;
     SVB_REQUIRE(channels > 0 && channels % vec == 0, "svb_ms_deform_attn_forward: channels per head (%d) must be a multiple of %d", channels, vec);
     SVB_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                 "svb_ms_deform_attn_forward: value / out must be 16-byte aligned");
     SVB_REQUIRE(batch >= 0 && num_query >= 0 && num_heads > 0 && num_points > 0 && spatial_size >= 0, "svb_ms_deform_attn_forward: bad sizes");
     MsdaLevels lv;
-    long covered = 0;
-    for (int l = 0; l < num_levels; ++l) {
-        lv.h[l] = spatial_shapes[2 * l];
-        lv.w[l] = spatial_shapes[2 * l + 1];
-        lv.start[l] = level_start_index[l];
-        SVB_REQUIRE(lv.h[l] > 0 && lv.w[l] > 0 && lv.start[l] >= 0 && (long)lv.start[l] + (long)lv.h[l] * lv.w[l] <= spatial_size,
-                    "svb_ms_deform_attn_forward: level %d (%d x %d at %d) does not fit in %d positions", l, lv.h[l], lv.w[l], lv.start[l],
-                    spatial_size);
-        covered += (long)lv.h[l] * lv.w[l];
+    {
+        int rc = msda_levels(lv, spatial_shapes, level_start_index, num_levels, spatial_size, "svb_ms_deform_attn_forward");
+        if (rc) return rc;
     }
-    SVB_REQUIRE(covered == spatial_size, "svb_ms_deform_attn_forward: the levels cover %ld positions, value has %d", covered, spatial_size);
     const long total = (long)batch * num_query * num_heads * (channels / vec);
     if (total == 0) return 0;
     const long blocks_needed = (total + 255) / 256;
@@ -161,6 +236,45 @@ extern "C" int svb_ms_deform_attn_forward(const void* value, const int32_t* spat
         else SVB_MSDA(float, 0);
     }
 #undef SVB_MSDA
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svb_ms_deform_attn_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                                                const float* reference_points, int ref_dim, const float* offsets_and_logits, void* out,
+                                                int dtype, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                                int num_query, int num_points, svb_stream_t stream) {
+    SVB_REQUIRE(value && spatial_shapes && level_start_index && reference_points && offsets_and_logits && out,
+                "svb_ms_deform_attn_fused_forward: null argument");
+    SVB_REQUIRE(dtype == SVB_DTYPE_F32 || dtype == SVB_DTYPE_BF16, "svb_ms_deform_attn_fused_forward: bad dtype %d", dtype);
+    SVB_REQUIRE(ref_dim == 2 || ref_dim == 4, "svb_ms_deform_attn_fused_forward: last dim of reference_points must be 2 or 4, got %d", ref_dim);
+    const int vec = dtype == SVB_DTYPE_BF16 ? 8 : 4;
+    SVB_REQUIRE(channels > 0 && channels % vec == 0, "svb_ms_deform_attn_fused_forward: channels per head (%d) must be a multiple of %d", channels,
+                vec);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(value) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(offsets_and_logits) & 7) == 0, "svb_ms_deform_attn_fused_forward: misaligned pointer");
+    SVB_REQUIRE(batch >= 0 && num_query >= 0 && num_heads > 0 && num_points > 0 && spatial_size >= 0 && ((num_heads * num_levels * num_points) % 2) == 0,
+                "svb_ms_deform_attn_fused_forward: bad sizes");
+    MsdaLevels lv;
+    {
+        int rc = msda_levels(lv, spatial_shapes, level_start_index, num_levels, spatial_size, "svb_ms_deform_attn_fused_forward");
+        if (rc) return rc;
+    }
+    const long total = (long)batch * num_query * num_heads * (channels / vec);
+    if (total == 0) return 0;
+    const long blocks_needed = (total + 255) / 256;
+    const int blocks = (int)(blocks_needed < 148L * 32 ? blocks_needed : 148L * 32);
+    const double bytes = (double)batch * num_query * num_heads *
+                         ((double)num_levels * num_points * (12.0 + 4.0 * channels * (vec == 8 ? 2 : 4)) + (double)channels * (vec == 8 ? 2 : 4));
+    ProfScope prof(PC_OTHER, 0, bytes, (cudaStream_t)stream);
+    if (dtype == SVB_DTYPE_BF16)
+        msda_fused_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)value, offsets_and_logits, reference_points, (bf16*)out, lv,
+                                                                           total, spatial_size, num_heads, channels, num_levels, num_query,
+                                                                           num_points, ref_dim);
+    else
+        msda_fused_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)value, offsets_and_logits, reference_points, (float*)out,
+                                                                            lv, total, spatial_size, num_heads, channels, num_levels,
+                                                                            num_query, num_points, ref_dim);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

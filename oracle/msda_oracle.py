@@ -80,3 +80,28 @@ def ms_deform_attn_loops(value, spatial_shapes, level_start_index, sampling_loca
                         col += val * wt                                                      # :291
                 out[n, q, m] = col
     return out.reshape(N, Lq, M * D)
+
+
+def ms_deform_attn_module(sd, query, reference_points, input_flatten, spatial_shapes, padding_mask, n_heads, n_levels, n_points):
+    """MSDeformAttn.forward (ops/modules/ms_deform_attn.py:82-125) on a plain state_dict ``sd`` with the reference's keys
+    (sampling_offsets / attention_weights / value_proj / output_proj .weight / .bias)."""
+    N, Lq, C = query.shape
+    _, S, _ = input_flatten.shape
+    M, L, P = n_heads, n_levels, n_points
+    shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+    value = input_flatten @ sd["value_proj.weight"].t() + sd["value_proj.bias"]                        # :97
+    if padding_mask is not None:
+        value = value.masked_fill(padding_mask[..., None], 0.0)                                         # :98-99
+    value = value.view(N, S, M, C // M)
+    off = (query @ sd["sampling_offsets.weight"].t() + sd["sampling_offsets.bias"]).view(N, Lq, M, L, P, 2)          # :101
+    aw = (query @ sd["attention_weights.weight"].t() + sd["attention_weights.bias"]).view(N, Lq, M, L * P)           # :102
+    aw = F.softmax(aw, -1).view(N, Lq, M, L, P)                                                                       # :103
+    if reference_points.shape[-1] == 2:                                                                               # :105-108
+        norm = torch.tensor([[w, h] for h, w in shapes], dtype=query.dtype)
+        loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    elif reference_points.shape[-1] == 4:                                                                             # :109-111
+        loc = reference_points[:, :, None, :, None, :2] + off / P * reference_points[:, :, None, :, None, 2:] * 0.5
+    else:
+        raise ValueError("Last dim of reference_points must be 2 or 4")
+    out = ms_deform_attn_core(value, shapes, loc, aw)                                                                 # :117-122
+    return out @ sd["output_proj.weight"].t() + sd["output_proj.bias"]                                                # :124

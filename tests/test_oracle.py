@@ -139,3 +139,20 @@ def test_msda_oracle_against_reference_goldens(case):
             starts.append(starts[-1] + h * w)
         out2 = mo.ms_deform_attn_loops(value, shapes, starts, loc, aw)
         assert torch.allclose(out2, ref, rtol=1e-9, atol=1e-10), float((out2 - ref).abs().max())
+
+
+@pytest.mark.parametrize("case", ["points", "boxes_masked", "heads64"])
+def test_msda_module_oracle_against_reference_goldens(case):
+    """oracle.ms_deform_attn_module against outputs of the UNMODIFIED reference MSDeformAttn module
+    (tests/golden/make_golden_msda_module.py; ops/modules/ms_deform_attn.py:82-125)."""
+    import os
+    import numpy as np
+    from oracle import msda_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"msda_module_{case}.npz"))
+    C, M, P, L = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd.")}
+    mask = torch.from_numpy(z["mask"]) if z["mask"].size else None
+    out = mo.ms_deform_attn_module(sd, torch.from_numpy(z["query"]).double(), torch.from_numpy(z["ref"]).double(),
+                                   torch.from_numpy(z["inp"]).double(), [tuple(int(v) for v in hw) for hw in z["shapes"]], mask, M, L, P)
+    assert torch.allclose(out, torch.from_numpy(z["out"]), rtol=1e-10, atol=1e-11)
