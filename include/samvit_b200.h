@@ -104,7 +104,8 @@ int svb_encoder_enable_taps(svb_encoder_t* enc, int enable);
 int svb_encoder_read_tap(svb_encoder_t* enc, int block, float* dst, int64_t numel, svb_stream_t stream);
 
 /* ---- single operators (the pieces of the forward; exported so each can be checked against the oracle) ---- */
-/* nn.Linear / conv-as-GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  mode BF16: A,W bf16 (tcgen05); FP32: fp32. */
+/* nn.Linear / conv-as-GEMM: C[M,N] = act(A[M,K] W[N,K]^T + bias) + resid.  mode BF16: A,W bf16 (tcgen05); FP32: fp32.
+ * act_gelu: 0 none, 1 exact-erf GELU (nn.GELU()), 2 ReLU (F.relu: the FFN of the deformable encoder layer). */
 int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats,
                int rows_per_sample, int remap_grid, int remap_grid_pad, svb_stream_t stream);
@@ -124,6 +125,9 @@ int svb_fold_layernorm(const float* W, const float* bias, const float* gamma, co
                        float* bias_f, int N, int K, svb_stream_t stream);
 /* remap_grid > 0: output row r (token order, grid x grid per image) is stored at the token's row of the window-padded
  * grid_pad x grid_pad layout — window_partition's F.pad (image_encoder.py:271-275) expressed as a store address. */
+/* out = cast(a [+ b]) elementwise (a, b fp32 device pointers, b may be NULL): `with_pos_embed` + the cast to the GEMM operand type
+ * (transformer_encoder_deform.py:112-114,124). */
+int svb_add_cast(const float* a, const float* b, void* out, int out_dtype, int64_t numel, svb_stream_t stream);
 /* nn.LayerNorm over the last dim (image_encoder.py:166,176): fp32 in, out dtype = out_dtype.  With `add` (rows x dim, element
  * type = out_dtype) the residual add of Block.forward (image_encoder.py:194) is fused in: x += add is written back, then
  * out = LayerNorm(x). */

@@ -54,6 +54,7 @@ SYMBOLS = {
     "svb_attention_debug_buffer": (_i, [_vp]),
     "svb_pack_rel_table": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_fill_pad_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "svb_add_cast": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "svb_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "svb_attention": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

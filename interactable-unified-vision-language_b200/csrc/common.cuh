@@ -233,6 +233,8 @@ int pack_cast(const float* src, void* dst, bool dst_bf16, long n, cudaStream_t s
 int pack_convT(const float* w /*Cin,Cout,2,2*/, void* dst /*[4*Cout, Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
 int pack_conv2x2(const float* w /*Cout,Cin,2,2*/, void* dst /*[Cout, 4*Cin]*/, bool dst_bf16, int Cin, int Cout, cudaStream_t s);
 int pack_bias4(const float* b, float* dst, int C, cudaStream_t s);
+// out = T(a [+ b]) elementwise, fp32 in
+int add_cast(const float* a, const float* b, void* out, bool out_bf16, size_t n, cudaStream_t s);
 // LayerNorm -> Linear fold (see Epilogue::ln_stats): Wg bf16 [N,K], colsum [N], bias_f [N] from the fp32 masters
 int fold_layernorm(const float* W, const float* bias, const float* gamma, const float* beta, bf16* Wg, float* colsum, float* bias_f, int N,
                    int K, cudaStream_t s);

@@ -390,6 +390,20 @@ __global__ void linear_resize_kernel(const float* __restrict__ src, float* __res
     }
 }
 
+// out = T(a [+ b]): the cast of an fp32 stream (optionally plus a positional embedding, `with_pos_embed` of
+// transformer_encoder_deform.py:112-114) to the GEMM operand type
+template <typename T>
+__global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ out, size_t n4) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+        if (b) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(b) + i);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        Vec4<T>::store(out + i * 4, v.x, v.y, v.z, v.w);
+    }
+}
+
 inline int grid_for(size_t n, int block) {
     size_t gsz = (n + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -597,6 +611,14 @@ int resize_rel_pos(const float* src, float* dst, int L0, int L1, int hd, cudaStr
     SVB_REQUIRE(L0 > 0 && L1 > 0 && hd > 0, "resize_rel_pos: bad sizes");
     linear_resize_kernel<<<(L1 * hd + 255) / 256, 256, 0, s>>>(src, dst, L0, L1, hd);
     count_launch();
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int add_cast(const float* a, const float* b, void* out, bool out_bf16, size_t n, cudaStream_t s) {
+    SVB_REQUIRE(n % 4 == 0, "add_cast: element count must be a multiple of 4");
+    ProfScope prof(PC_OTHER, 0, (double)n * (4 + (b ? 4 : 0) + (out_bf16 ? 2 : 4)), s);
+    if (out_bf16) add_cast_kernel<bf16><<<grid_for(n / 4, 256), 256, 0, s>>>(a, b, (bf16*)out, n / 4);
+    else add_cast_kernel<float><<<grid_for(n / 4, 256), 256, 0, s>>>(a, b, (float*)out, n / 4);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

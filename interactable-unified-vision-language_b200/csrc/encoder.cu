@@ -926,7 +926,7 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
     SVB_REQUIRE(A && W && out, "svb_linear: null argument");
     Epilogue ep;
     ep.bias = bias;
-    ep.act = act_gelu ? 1 : 0;
+    ep.act = (act_gelu == 1 || act_gelu == 2) ? act_gelu : 0;     // 1 GELU (erf), 2 ReLU
     ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
     ep.out = out; ep.out_bf16 = out_dtype == SVB_DTYPE_BF16; ep.ldo = ldo;
     ep.stats = gn_stats; ep.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
@@ -947,7 +947,7 @@ int svb_linear_fused(const void* A, int lda, const void* W, int ldw, int M, int 
     SVB_REQUIRE(A && W && out, "svb_linear_fused: null argument");
     Epilogue ep;
     ep.bias = bias;
-    ep.act = act_gelu ? 1 : 0;
+    ep.act = (act_gelu == 1 || act_gelu == 2) ? act_gelu : 0;     // 1 GELU (erf), 2 ReLU
     ep.resid = resid; ep.ldr = ldr; ep.resid_mod = resid_mod;
     ep.out = out; ep.out_bf16 = out_dtype == SVB_DTYPE_BF16; ep.ldo = ldo;
     if (ln_stats) {
@@ -968,6 +968,12 @@ int svb_fold_layernorm(const float* W, const float* bias, const float* gamma, co
                        float* bias_f, int N, int K, svb_stream_t stream) {
     SVB_REQUIRE(W && gamma && beta && Wg_bf16 && colsum && bias_f, "svb_fold_layernorm: null argument");
     return fold_layernorm(W, bias, gamma, beta, (bf16*)Wg_bf16, colsum, bias_f, N, K, (cudaStream_t)stream);
+}
+
+int svb_add_cast(const float* a, const float* b, void* out, int out_dtype, int64_t numel, svb_stream_t stream) {
+    SVB_REQUIRE(a && out && numel >= 0, "svb_add_cast: bad argument");
+    if (numel == 0) return 0;
+    return add_cast(a, b, out, out_dtype == SVB_DTYPE_BF16, (size_t)numel, (cudaStream_t)stream);
 }
 
 int svb_layernorm(float* x, const void* add, const float* weight, const float* bias, void* out, int out_dtype, int rows, int dim, float eps,

@@ -51,6 +51,9 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
         if (ep.act == 1) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
+        } else if (ep.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (ep.resid) {
             const int rr = ep.resid_mod ? (row % ep.resid_mod) : row;
@@ -87,6 +90,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& ep, int row, int 
                 float x = v[j] + (ep.bias ? __ldg(ep.bias + c) : 0.f);
                 if (ep.stats) { s_sum += x; s_sq += x * x; }
                 if (ep.act == 1) x = gelu_fast(x);
+                else if (ep.act == 2) x = fmaxf(x, 0.f);
                 if (ep.resid) x += ep.resid[(size_t)rr * ep.ldr + c];
                 if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out)[orow * ep.ldo + c] = __float2bfloat16_rn(x);
                 else reinterpret_cast<float*>(ep.out)[orow * ep.ldo + c] = x;

@@ -13,6 +13,7 @@ __device__ __forceinline__ void store_out(const Epilogue& ep, int row, int col, 
     if (ep.bias) x += __ldg(ep.bias + col);
     if (ep.stats) { s_sum += x; s_sq += x * x; }
     if (ep.act == 1) x = gelu_erf(x);
+    else if (ep.act == 2) x = fmaxf(x, 0.f);     // ReLU (FFN of the deformable encoder layer)
     if (ep.resid) {
         const int rr = ep.resid_mod ? (row % ep.resid_mod) : row;
         x += ep.resid[(size_t)rr * ep.ldr + col];

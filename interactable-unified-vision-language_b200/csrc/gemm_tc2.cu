@@ -342,6 +342,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (ep.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
+                } else if (ep.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (out_bf16) {
                     // ---- transpose tile [32 rows][64 B]: piece j of row r at physical piece j ^ ((r >> 1) & 3) ----
@@ -877,6 +880,13 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         gelu_pair(a, b);
                         v[j] = f2_pack(a, b);
                     }
+                } else if (ep.act == 2) {                     // ReLU
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a, b;
+                        f2_unpack(v[j], a, b);
+                        v[j] = f2_pack(fmaxf(a, 0.f), fmaxf(b, 0.f));
+                    }
                 }
                 // ---- stage the box, hand it to the TMA ----
                 const uint32_t box = stg + sbuf * C::CHUNK_BYTES;
@@ -1025,7 +1035,8 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
         if (ep.stats && (ep.act || ep.ln_stats || ep.gn_in_stats)) return 0;     // statistics are taken before the activation only
         mode = EPI_BF16;
     } else {
-        if (ep.act || ep.ln_stats || ep.remap_g) return 0;
+        if (ep.act == 1 || ep.ln_stats || ep.remap_g) return 0;          // (ReLU, act == 2, is a run-time branch of every mode)
+        if (ep.act && ep.resid) return 0;
         if (ep.gn_in_stats && ep.resid) return 0;
         if (!ep.resid) mode = EPI_F32;
         else if (ep.resid == ep.out && ep.ldr == ep.ldo && ep.resid_mod == 0 && !ep.stats) mode = EPI_F32_REDADD;

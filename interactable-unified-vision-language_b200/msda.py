@@ -107,12 +107,40 @@ class MSDeformAttn(nn.Module):
             self._packed_sig = sig
         return self._packed
 
+    def _mode(self):
+        if self.precision == "bf16":
+            return cabi.MODE_BF16, torch.bfloat16
+        if self.precision == "fp32":
+            return cabi.MODE_FP32, torch.float32
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+
+    def _core(self, q_in, x_in, reference_points, shapes, starts, input_padding_mask, N, Lq, S):
+        """q_in (N*Lq,C) / x_in (N*S,C) already in the GEMM operand dtype -> fp32 (N*Lq,C).  ms_deform_attn.py:97-124."""
+        mode, adt = self._mode()
+        bf16 = adt == torch.bfloat16
+        dev = q_in.device
+        C = self.d_model
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        D = C // M
+        (wv, bv), (wq, bq), (wo, bo) = self._weights(dev, adt)
+        value = self._linear(mode, x_in, wv, bv, torch.empty(N * S, C, dtype=adt, device=dev))                          # :97
+        if input_padding_mask is not None:
+            value.view(N, S, C).masked_fill_(input_padding_mask[..., None], 0.0)                                         # :98-99
+        raw = self._linear(mode, q_in, wq, bq, torch.empty(N * Lq, 3 * M * L * P, dtype=torch.float32, device=dev))       # :101-102
+        ref = reference_points.detach().to(torch.float32).contiguous()
+        sampled = torch.empty(N * Lq, C, dtype=adt, device=dev)
+        cabi.check(cabi.lib().svb_ms_deform_attn_fused_forward(
+            value.data_ptr(), (ctypes.c_int32 * (2 * L))(*shapes), (ctypes.c_int32 * L)(*starts), ref.data_ptr(), int(ref.shape[-1]),
+            raw.data_ptr(), sampled.data_ptr(), cabi.DTYPE_BF16 if bf16 else cabi.DTYPE_F32, N, S, M, D, L, Lq, P, cabi.stream_ptr()),
+            "svb_ms_deform_attn_fused_forward")                                                                          # :103-122
+        return self._linear(mode, sampled, wo, bo, torch.empty(N * Lq, C, dtype=torch.float32, device=dev))             # :124
+
     @staticmethod
-    def _linear(mode, a, w, b, out):
+    def _linear(mode, a, w, b, out, act=0):
         m, k = a.shape
         n = w.shape[0]
         cabi.check(cabi.lib().svb_linear(
-            mode, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), m, n, k, b.data_ptr(), 0, None, 0, 0, out.data_ptr(),
+            mode, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), m, n, k, b.data_ptr(), act, None, 0, 0, out.data_ptr(),
             cabi.DTYPE_BF16 if out.dtype == torch.bfloat16 else cabi.DTYPE_F32, out.stride(0), None, 0, 0, 0, cabi.stream_ptr()), "svb_linear")
         return out
 
@@ -129,29 +157,203 @@ class MSDeformAttn(nn.Module):
         D = C // M
         shapes = [int(v) for v in input_spatial_shapes.reshape(-1).tolist()]
         starts = [int(v) for v in input_level_start_index.reshape(-1).tolist()]
-        if sum(shapes[2 * i] * shapes[2 * i + 1] for i in range(L)) != S:
+        if len(shapes) != 2 * L or len(starts) != L or sum(shapes[2 * i] * shapes[2 * i + 1] for i in range(L)) != S:
             raise AssertionError("the levels do not cover input_flatten")            # ms_deform_attn.py:95
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
-        bf16 = self.precision == "bf16"
-        if not bf16 and self.precision != "fp32":
-            raise ValueError("precision must be 'bf16' or 'fp32'")
-        mode, adt = (cabi.MODE_BF16, torch.bfloat16) if bf16 else (cabi.MODE_FP32, torch.float32)
+        mode, adt = self._mode()
         dev = query.device
         with torch.cuda.device(dev):
-            (wv, bv), (wq, bq), (wo, bo) = self._weights(dev, adt)
             x_in = input_flatten.detach().reshape(N * S, C).to(adt).contiguous()
             q_in = query.detach().reshape(N * Lq, C).to(adt).contiguous()
-            value = self._linear(mode, x_in, wv, bv, torch.empty(N * S, C, dtype=adt, device=dev))                    # :97
-            if input_padding_mask is not None:
-                value.view(N, S, C).masked_fill_(input_padding_mask[..., None], 0.0)                                     # :98-99
-            raw = self._linear(mode, q_in, wq, bq, torch.empty(N * Lq, 3 * M * L * P, dtype=torch.float32, device=dev))   # :101-102
-            ref = reference_points.detach().to(torch.float32).contiguous()
-            sampled = torch.empty(N * Lq, C, dtype=adt, device=dev)
-            cabi.check(cabi.lib().svb_ms_deform_attn_fused_forward(
-                value.data_ptr(), (ctypes.c_int32 * (2 * L))(*shapes), (ctypes.c_int32 * L)(*starts), ref.data_ptr(), int(ref.shape[-1]),
-                raw.data_ptr(), sampled.data_ptr(), cabi.DTYPE_BF16 if bf16 else cabi.DTYPE_F32, N, S, M, D, L, Lq, P, cabi.stream_ptr()),
-                "svb_ms_deform_attn_fused_forward")                                                                      # :103-122
-            out = self._linear(mode, sampled, wo, bo, torch.empty(N * Lq, C, dtype=torch.float32, device=dev))           # :124
+            out = self._core(q_in, x_in, reference_points, shapes, starts, input_padding_mask, N, Lq, S)
         return out.view(N, Lq, C).to(query.dtype)
 
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The encoder around the module (scope row N1, widened to its caller): transformer_encoder_deform.py:23-161
+import copy  # noqa: E402
+
+
+def _layernorm(x, add, ln, out):
+    """x (rows, dim) fp32, updated in place to x + add when ``add`` is given; out = LayerNorm(x) (fp32)."""
+    rows, dim = x.shape
+    cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), add.data_ptr() if add is not None else None, ln._w32.data_ptr(), ln._b32.data_ptr(),
+                                        out.data_ptr(), cabi.DTYPE_F32, rows, dim, float(ln.eps), cabi.stream_ptr()), "svb_layernorm")
+    return out
+
+
+def _add_cast(a, b, dtype):
+    """cast(a [+ b]) of fp32 (rows, dim) streams to the GEMM operand dtype: ``with_pos_embed`` (:112-114) fused with the cast."""
+    out = torch.empty(a.shape, dtype=dtype, device=a.device)
+    cabi.check(cabi.lib().svb_add_cast(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                       cabi.DTYPE_BF16 if dtype == torch.bfloat16 else cabi.DTYPE_F32, a.numel(), cabi.stream_ptr()), "svb_add_cast")
+    return out
+
+
+class MSDeformAttnTransformerEncoderLayer(nn.Module):
+    """Drop-in for ``MSDeformAttnTransformerEncoderLayer`` (``transformer_encoder_deform.py:91-136``): same constructor, sub-module
+    names (``self_attn``, ``norm1``, ``linear1``, ``linear2``, ``norm2``; the dropouts are identities in the forward-only path) and
+    ``forward`` arguments.  The residual stream stays fp32; ``src + pos`` is fused with the cast to the GEMM operand type, the residual
+    add of the attention output with ``norm1``, the ReLU with ``linear1``'s epilogue and the FFN residual with ``linear2``'s."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("the B200 deformable encoder layer implements activation='relu' (the reference's configuration)")
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self._packed_sig = None
+
+    @property
+    def precision(self):
+        return self.self_attn.precision
+
+    @precision.setter
+    def precision(self, p):
+        self.self_attn.precision = p
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def _prepare(self, device, wdtype):
+        ps = [self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias, self.norm1.weight, self.norm1.bias,
+              self.norm2.weight, self.norm2.bias]
+        sig = (str(device), wdtype) + tuple((p.data_ptr(), p._version) for p in ps)
+        if sig != self._packed_sig:
+            f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()      # noqa: E731
+            self._w1, self._b1 = f(self.linear1.weight).to(wdtype), f(self.linear1.bias)
+            self._w2, self._b2 = f(self.linear2.weight).to(wdtype), f(self.linear2.bias)
+            for ln in (self.norm1, self.norm2):
+                ln._w32, ln._b32 = f(ln.weight), f(ln.bias)
+            self._packed_sig = sig
+
+    def _forward_rows(self, x, pos, reference_points, shapes, starts, padding_mask, N, S):
+        """x (N*S, C) fp32, OVERWRITTEN (it becomes src + attention output); pos (N*S, C) fp32 or None -> new (N*S, C) fp32."""
+        attn = self.self_attn
+        mode, adt = attn._mode()
+        dev = x.device
+        self._prepare(dev, adt)
+        C = x.shape[1]
+        q_in = _add_cast(x, pos, adt) if (pos is not None or adt != torch.float32) else x                       # :125 with_pos_embed
+        x_in = q_in if pos is None else (_add_cast(x, None, adt) if adt != torch.float32 else x)
+        src2 = attn._core(q_in, x_in, reference_points, shapes, starts, padding_mask, N, S, S)                  # :125
+        y = _layernorm(x, src2, self.norm1, torch.empty_like(x))                                                # :126-127
+        yb = _add_cast(y, None, adt) if adt != torch.float32 else y
+        hid = attn._linear(mode, yb, self._w1, self._b1, torch.empty(N * S, self._w1.shape[0], dtype=adt, device=dev), act=2)     # :117 relu(linear1)
+        z = torch.empty(N * S, C, dtype=torch.float32, device=dev)
+        cabi.check(cabi.lib().svb_linear(mode, hid.data_ptr(), hid.stride(0), self._w2.data_ptr(), self._w2.stride(0), N * S, C, hid.shape[1],
+                                         self._b2.data_ptr(), 0, y.data_ptr(), C, 0, z.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0,
+                                         cabi.stream_ptr()), "svb_linear")                                      # :117-118 src + linear2(..)
+        return _layernorm(z, None, self.norm2, y)                                                               # :119
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        if not src.is_cuda:
+            raise RuntimeError("MSDeformAttnTransformerEncoderLayer (B200) has no CPU path: the inputs must be CUDA tensors")
+        if torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("MSDeformAttnTransformerEncoderLayer (B200) implements the forward pass only: call it under torch.no_grad()")
+        N, S, C = src.shape
+        shapes = [int(v) for v in spatial_shapes.reshape(-1).tolist()]
+        starts = [int(v) for v in level_start_index.reshape(-1).tolist()]
+        with torch.cuda.device(src.device):
+            x = src.detach().reshape(N * S, C).to(torch.float32).clone()
+            p = None if pos is None else pos.detach().reshape(N * S, C).to(torch.float32).contiguous()
+            out = self._forward_rows(x, p, reference_points, shapes, starts, padding_mask, N, S)
+        return out.view(N, S, C).to(src.dtype)
+
+
+class MSDeformAttnTransformerEncoder(nn.Module):
+    """``transformer_encoder_deform.py:133-161``: ``num_layers`` clones of the layer over one set of reference points."""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        # :141-153 — pixel centres of every level, normalised by the valid extent, per (image, query, level)
+        pts = []
+        for lvl, (H_, W_) in enumerate(spatial_shapes):
+            H_, W_ = int(H_), int(W_)
+            ys = torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device)
+            ry = ys[:, None].expand(H_, W_).reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * H_)
+            rx = xs[None, :].expand(H_, W_).reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * W_)
+            pts.append(torch.stack((rx, ry), -1))
+        return torch.cat(pts, 1)[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        if not src.is_cuda:
+            raise RuntimeError("MSDeformAttnTransformerEncoder (B200) has no CPU path: the inputs must be CUDA tensors")
+        if torch.is_grad_enabled() and (src.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("MSDeformAttnTransformerEncoder (B200) implements the forward pass only: call it under torch.no_grad()")
+        N, S, C = src.shape
+        shapes_hw = [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+        shapes = [v for hw in shapes_hw for v in hw]
+        starts = [int(v) for v in level_start_index.reshape(-1).tolist()]
+        with torch.cuda.device(src.device):
+            ref = self.get_reference_points(shapes_hw, valid_ratios.to(torch.float32), src.device)
+            x = src.detach().reshape(N * S, C).to(torch.float32).clone()
+            p = None if pos is None else pos.detach().reshape(N * S, C).to(torch.float32).contiguous()
+            for layer in self.layers:
+                x = layer._forward_rows(x, p, ref, shapes, starts, padding_mask, N, S)
+        return x.view(N, S, C).to(src.dtype)
+
+
+class MSDeformAttnTransformerEncoderOnly(nn.Module):
+    """``transformer_encoder_deform.py:23-88``: flattens the feature levels, adds the level embedding to the positional
+    embeddings and runs the encoder.  Returns ``(memory, spatial_shapes, level_start_index)`` like the reference."""
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1, activation="relu",
+                 num_feature_levels=4, enc_n_points=4):
+        super().__init__()
+        self.d_model, self.nhead = d_model, nhead
+        layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels, nhead, enc_n_points)
+        self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # :45-52
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.normal_(self.level_embed)
+
+    @property
+    def precision(self):
+        return self.encoder.layers[0].precision
+
+    @precision.setter
+    def precision(self, p):
+        for layer in self.encoder.layers:
+            layer.precision = p
+
+    def forward(self, srcs, pos_embeds):
+        # :63-88; the masks of the reference are all-False (:64), so valid_ratios == 1 and no value is masked
+        src_flatten, pos_flatten, spatial_shapes = [], [], []
+        for lvl, (src, pos_embed) in enumerate(zip(srcs, pos_embeds)):
+            bs, c, h, w = src.shape
+            spatial_shapes.append((h, w))
+            src_flatten.append(src.detach().flatten(2).transpose(1, 2))
+            pos_flatten.append(pos_embed.detach().flatten(2).transpose(1, 2) + self.level_embed[lvl].detach().view(1, 1, -1))
+        src_flatten = torch.cat(src_flatten, 1)
+        pos_flatten = torch.cat(pos_flatten, 1)
+        dev = src_flatten.device
+        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=dev)
+        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.ones(src_flatten.shape[0], len(srcs), 2, dtype=torch.float32, device=dev)
+        memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, pos_flatten, None)
+        return memory, spatial_shapes, level_start_index

@@ -105,3 +105,36 @@ def ms_deform_attn_module(sd, query, reference_points, input_flatten, spatial_sh
         raise ValueError("Last dim of reference_points must be 2 or 4")
     out = ms_deform_attn_core(value, shapes, loc, aw)                                                                 # :117-122
     return out @ sd["output_proj.weight"].t() + sd["output_proj.bias"]                                                # :124
+
+
+def deform_encoder_only(sd, srcs, pos_embeds, n_heads, n_points, n_layers):
+    """MSDeformAttnTransformerEncoderOnly.forward (transformer_encoder_deform.py:63-88) over the encoder (:155-161) and its layers
+    (:121-131), eval mode (dropouts are identities), on a plain state_dict with the reference's keys.  Pinned by
+    tests/golden/deform_encoder_*.npz (tests/golden/make_golden_deform_encoder.py: the unmodified reference classes)."""
+    L = len(srcs)
+    shapes = [tuple(s.shape[2:]) for s in srcs]
+    src = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)                                                  # :71,79
+    pos = torch.cat([p.flatten(2).transpose(1, 2) + sd["level_embed"][i].view(1, 1, -1) for i, p in enumerate(pos_embeds)], 1)   # :73-75,81
+    N, S, C = src.shape
+    # all-False masks (:64) -> valid_ratios == 1 (:54-61,84); reference points (:141-153)
+    ref = []
+    for h, w in shapes:
+        ys = (torch.arange(h, dtype=src.dtype) + 0.5) / h
+        xs = (torch.arange(w, dtype=src.dtype) + 0.5) / w
+        ref.append(torch.stack((xs[None, :].expand(h, w).reshape(-1), ys[:, None].expand(h, w).reshape(-1)), -1))
+    ref = torch.cat(ref, 0)[None, :, None, :].expand(N, S, L, 2)
+
+    def ln(x, w, b):
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        return (x - mu) / torch.sqrt(var + 1e-5) * w + b
+
+    out = src
+    for i in range(n_layers):
+        pre = f"encoder.layers.{i}."
+        attn_sd = {k[len(pre) + len("self_attn."):]: v for k, v in sd.items() if k.startswith(pre + "self_attn.")}
+        src2 = ms_deform_attn_module(attn_sd, out + pos, ref, out, shapes, None, n_heads, L, n_points)              # :125
+        out = ln(out + src2, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])                                       # :126-127
+        hid = torch.relu(out @ sd[pre + "linear1.weight"].t() + sd[pre + "linear1.bias"])                            # :117
+        out = ln(out + hid @ sd[pre + "linear2.weight"].t() + sd[pre + "linear2.bias"], sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])   # :117-119
+    return out

@@ -131,3 +131,47 @@ def test_msda_module_fused_kernel_equals_unfused_path():
         core = ms_deform_attn_forward(value.contiguous(), torch.tensor(shapes), torch.tensor(_starts(shapes)), loc, aw)
         ref_out = core @ mod.output_proj.weight.t() + mod.output_proj.bias
     assert ib.rel_l2(out, ref_out) < 1e-4, ib.rel_l2(out, ref_out)
+
+
+@pytest.mark.parametrize("case", ["small", "heads64"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_deform_encoder_against_reference_goldens(case, precision, tol):
+    """The drop-in MSDeformAttnTransformerEncoderOnly (per layer: fused pos-add + cast, MSDeformAttn, residual + LayerNorm, ReLU and
+    residual in the FFN GEMMs' epilogues) against outputs of the UNMODIFIED reference classes (transformer_encoder_deform.py:23-161)."""
+    from iuvl_b200.msda import MSDeformAttnTransformerEncoderOnly
+    z = np.load(os.path.join(GOLDEN, f"deform_encoder_{case}.npz"))
+    C, M, NL, F_, P, L = (int(v) for v in z["meta"])
+    mod = MSDeformAttnTransformerEncoderOnly(C, M, NL, F_, 0.1, "relu", L, P)
+    mod.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    mod.to(DEV).eval()
+    mod.precision = precision
+    with torch.no_grad():
+        memory, shapes, starts = mod([torch.from_numpy(z[f"src{i}"]).to(DEV) for i in range(L)],
+                                     [torch.from_numpy(z[f"pos{i}"]).to(DEV) for i in range(L)])
+    assert shapes.cpu().tolist() == z["shapes"].tolist() and starts.cpu().tolist() == z["starts"].tolist()
+    ref = torch.from_numpy(z["memory"])
+    assert tuple(memory.shape) == tuple(ref.shape)
+    err = ib.rel_l2(memory, ref)
+    assert err < tol, (case, precision, err)
+
+
+def test_deform_encoder_layer_matches_composition_of_ops():
+    """One encoder layer in fp32 against the same arithmetic spelled out with torch ops around the drop-in MSDeformAttn."""
+    from iuvl_b200.msda import MSDeformAttnTransformerEncoderLayer
+    g = torch.Generator().manual_seed(5)
+    C, M, P, shapes = 128, 4, 4, [(9, 7), (4, 4)]
+    L, S, N = len(shapes), sum(h * w for h, w in shapes), 2
+    layer = MSDeformAttnTransformerEncoderLayer(C, 256, 0.1, "relu", L, M, P).to(DEV).eval()
+    layer.precision = "fp32"
+    with torch.no_grad():
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.3)
+        layer.self_attn.attention_weights.weight.normal_(0, 0.3)
+        src, pos = torch.randn(N, S, C, generator=g).to(DEV), torch.randn(N, S, C, generator=g).to(DEV)
+        ref = torch.rand(N, S, L, 2, generator=g).to(DEV)
+        ss, st = torch.tensor(shapes), torch.tensor(_starts(shapes))
+        for p_ in (pos, None):
+            out = layer(src, p_, ref, ss, st)
+            a = layer.self_attn(src if p_ is None else src + p_, ref, src, ss, st)
+            y = layer.norm1(src + a)
+            want = layer.norm2(y + layer.linear2(torch.relu(layer.linear1(y))))
+            assert ib.rel_l2(out, want) < 1e-4, ib.rel_l2(out, want)

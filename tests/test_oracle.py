@@ -156,3 +156,37 @@ def test_msda_module_oracle_against_reference_goldens(case):
     out = mo.ms_deform_attn_module(sd, torch.from_numpy(z["query"]).double(), torch.from_numpy(z["ref"]).double(),
                                    torch.from_numpy(z["inp"]).double(), [tuple(int(v) for v in hw) for hw in z["shapes"]], mask, M, L, P)
     assert torch.allclose(out, torch.from_numpy(z["out"]), rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("case", ["small", "heads64"])
+def test_deform_encoder_oracle_against_reference_goldens(case):
+    """oracle.deform_encoder_only against outputs of the UNMODIFIED reference encoder classes
+    (tests/golden/make_golden_deform_encoder.py; transformer_encoder_deform.py:23-161)."""
+    import os
+    import numpy as np
+    from oracle import msda_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"deform_encoder_{case}.npz"))
+    C, M, NL, F_, P, L = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd.")}
+    out = mo.deform_encoder_only(sd, [torch.from_numpy(z[f"src{i}"]).double() for i in range(L)],
+                                 [torch.from_numpy(z[f"pos{i}"]).double() for i in range(L)], M, P, NL)
+    ref = torch.from_numpy(z["memory"]).double()
+    assert float((out - ref).abs().max()) < 1e-5      # the golden is stored in fp32
+
+
+def test_deform_encoder_module_keys_match_reference():
+    """The drop-in encoder's state_dict keys / shapes are the reference's (so its checkpoints load with strict=True)."""
+    import os
+    import numpy as np
+    from iuvl_b200.msda import MSDeformAttnTransformerEncoderOnly
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "deform_encoder_small.npz"))
+    C, M, NL, F_, P, L = (int(v) for v in z["meta"])
+    mod = MSDeformAttnTransformerEncoderOnly(C, M, NL, F_, 0.1, "relu", L, P)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    mod.load_state_dict(sd, strict=True)
+    assert {k: tuple(v.shape) for k, v in mod.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    with pytest.raises(RuntimeError):        # no CPU path
+        with torch.no_grad():
+            mod([torch.from_numpy(z[f"src{i}"]) for i in range(L)], [torch.from_numpy(z[f"pos{i}"]) for i in range(L)])
