@@ -62,6 +62,20 @@ __device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint3
             ptx::mma_f16_ts(o_tmem + 64, p_tmem + 8 * k, ptx::make_smem_desc(v_tail + k * 512, 0, 256, ptx::LAYOUT_SW32), id_tail, acc);
     }
 }
+// The same product as ONE MMA of N = HD per K step: V in two 64-element atoms along N, `atom_stride` bytes apart (the leading-
+// dimension byte offset of an MN-major operand; pinned by tests/test_gpu_probe.py).  Measured (tools/mma_rate.py): a tcgen05.mma
+// with its A operand in TMEM costs >= 44.5 cycles whatever N is, so the N = 64 + N = 16 pair costs 89 cycles per K step against
+// 44.5 for one N = 80 MMA (arithmetic floor 40).
+template <int HD>
+__device__ __forceinline__ void issue_pv_wide(uint32_t o_tmem, uint32_t p_tmem, uint32_t v_main, uint32_t atom_stride, int ksteps,
+                                              bool accumulate) {
+    constexpr uint32_t id = ptx::make_idesc_bf16(128, HD, 0, 1);
+    const uint64_t dv = ptx::make_smem_desc(v_main, HD > 64 ? atom_stride : 0, 1024, ptx::LAYOUT_SW128);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < ksteps) ptx::mma_f16_ts(o_tmem, p_tmem + 8 * k, dv + 128 * k, id, (accumulate || k) ? 1u : 0u);     // 16 keys = 2048 B
+    }
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
@@ -126,11 +140,13 @@ template <int HD, int NST_> struct GCfg {
     static constexpr int TAIL = HD - 64;
     static constexpr int T_MAIN = 128 * 128;                  // 128 rows x 64 bf16, 128B swizzle
     static constexpr int T_TAIL = TAIL ? 128 * 32 : 0;        // 128 rows x 16 bf16, 32B swizzle
-    static constexpr int TILE = T_MAIN + T_TAIL;
+    static constexpr int TILE = T_MAIN + T_TAIL;              // Q and K tiles (K-major operands: main + tail MMAs along K)
+    static constexpr int VTILE = TAIL ? 2 * T_MAIN : T_MAIN;  // V tile (MN-major operand): two 64-column atoms, the second one holds
+                                                              // columns 64..79 (+ 48 columns of whatever follows, never read)
     static constexpr int OFF_Q = 0;                           // 2 query tiles
     static constexpr int OFF_K = 2 * TILE;                    // NST key tiles
     static constexpr int OFF_V = OFF_K + NST * TILE;          // NST value tiles
-    static constexpr int OFF_STG = OFF_V + NST * TILE;        // 8 warps x 8 KB: w-term staging, then the h-term columns
+    static constexpr int OFF_STG = OFF_V + NST * VTILE;       // 8 warps x 8 KB: w-term staging, then the h-term columns
     static constexpr int STG_BYTES = 8 * 8192;
     static constexpr int OFF_RW = OFF_STG;                    // rel tables alias the staging area (dead after the bias MMAs)
     static constexpr int RH_MAIN = 80 * 128;
@@ -141,6 +157,7 @@ template <int HD, int NST_> struct GCfg {
     static constexpr int Q_TX = 2 * (128 * 128 + (TAIL ? 128 * 32 : 0)) + (128 * 128 + (TAIL ? 128 * 32 : 0)) +
                                 (80 * 128 + (TAIL ? 80 * 32 : 0));
     static constexpr int KV_TX = 128 * 128 + (TAIL ? 128 * 32 : 0);
+    static constexpr int V_TX = VTILE;
     static_assert(OFF_RH + RH_MAIN + RH_TAIL <= OFF_STG + STG_BYTES, "rel tables must fit in the staging area");
     static_assert(SMEM <= 232448, "shared memory budget");
     // barrier slots
@@ -156,13 +173,13 @@ template <int HD, int NST_> struct GCfg {
 // maximum of the previous tiles while the tile's own maximum is tracked alongside; if it exceeds m_ref by more than 2^8, O and the
 // row sum are rescaled at the start of the NEXT tile (P may transiently exceed 2^8, which bf16 / fp32 hold without loss).  The
 // two-pass form (maximum first) remains for the first tile and as the A/B variant.
-template <int HD, int NST, bool ONEPASS>
+template <int HD, int NST, bool ONEPASS, bool PH = false>
 // 10 warps are allocated as 12 (warp allocation granularity 4): the register cap is 65536 / 384 = 168 per thread
 __global__ void __launch_bounds__(320, 1)
 attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
-                   bf16* __restrict__ out, int D, int T, float scale_log2) {
+                   bf16* __restrict__ out, int D, int T, float scale_log2, long long* __restrict__ phase_clocks) {
     using C = GCfg<HD, NST>;
     constexpr int NKT = 32;                                     // 4096 keys / 128
     extern __shared__ uint8_t smem_raw[];
@@ -225,9 +242,9 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                 ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
                 if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
                 ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
-                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::KV_TX);
-                ptx::tma_load_2d(sm + C::OFF_V + st * C::TILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_VFULL + st], colv + 64, krow);
+                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
+                ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE + C::T_MAIN, &tm_main, &bars[C::B_VFULL + st], colv + 64, krow);
             }
         }
     } else if (warp == 9) {
@@ -254,16 +271,21 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                 ptx::mma_commit(&bars[C::B_SFULL + i]);
             }
             ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
+            long long ipc[3] = {0, 0, 0};
+            long long itp = PH ? clock64() : 0;
+#define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
             for (int j = 0; j < NKT; ++j) {
                 const int st = j % NST, nst = (j + 1) % NST;
                 const bool more = (j + 1 < NKT);
+                SVB_IPH(2)
                 ptx::mbar_wait(&bars[C::B_VFULL + st], (j / NST) & 1);
                 if (more) ptx::mbar_wait(&bars[C::B_KFULL + nst], ((j + 1) / NST) & 1);
+                SVB_IPH(0)
                 for (int i = 0; i < 2; ++i) {
                     ptx::mbar_wait(&bars[C::B_PFULL + i], (j + 1) & 1);   // P_i(j) is in TMEM
+                    SVB_IPH(1)
                     ptx::tc_fence_after();
-                    issue_pv<HD>(tmem + C::TM_O + 128 * i, tmem + C::TM_S + 128 * i, base + C::OFF_V + st * C::TILE,
-                                 base + C::OFF_V + st * C::TILE + C::T_MAIN, 8, j > 0);
+                    issue_pv_wide<HD>(tmem + C::TM_O + 128 * i, tmem + C::TM_S + 128 * i, base + C::OFF_V + st * C::VTILE, C::T_MAIN, 8, j > 0);
                     ptx::mma_commit(&bars[C::B_PVDONE + i]);
                     if (i == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
                     if (more) {
@@ -274,6 +296,12 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                         if (i == 1) ptx::mma_commit(&bars[C::B_KEMPTY + nst]);
                     }
                 }
+            }
+#undef SVB_IPH
+            if (PH && phase_clocks) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
             }
         }
     } else {
@@ -343,9 +371,14 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
         float x_over = 0.f;                                          // ONEPASS: previous tile's maximum exponent relative to m_ref
         f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
         const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+        long long pc[3] = {0, 0, 0};
+        long long tprev = PH ? clock64() : 0;
+#define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
 #pragma unroll 1
         for (int j = 0; j < NKT; ++j) {
+            SVB_GPH(1)
             ptx::mbar_wait(&bars[C::B_SFULL + i], j & 1);
+            SVB_GPH(0)
             ptx::tc_fence_after();
             const float bh0 = stg[(2 * j) * 32 + lane], bh1 = stg[(2 * j + 1) * 32 + lane];
             uint32_t va[32], vb[32];
@@ -402,6 +435,7 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
                     l23 = f2_mul(l23, al2);
                 }
                 m_ref = m_new;
+                SVB_GPH(2)
             }
             float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
             const f32x2 d0_2 = f2_pack(bh0 - m_ref, bh0 - m_ref), d1_2 = f2_pack(bh1 - m_ref, bh1 - m_ref);
@@ -446,8 +480,395 @@ attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_con
             ptx::tc_fence_before();
             ptx::mbar_arrive(&bars[C::B_PFULL + i]);
         }
+        SVB_GPH(1)
+#undef SVB_GPH
+        if (PH && phase_clocks && w4 == 0 && lane == 0) {
+            for (int k = 0; k < 3; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)NKT);
+        }
         // ---- epilogue: O / l at the query's own token position ----
         ptx::mbar_wait(&bars[C::B_PVDONE + i], (NKT - 1) & 1);
+        ptx::tc_fence_after();
+        float l0, l1, l2, l3;
+        f2_unpack(l01, l0, l1);
+        f2_unpack(l23, l2, l3);
+        const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
+        bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD;
+        store_row<HD>(dst, o_tmem, inv);
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C::TM_COLS);
+    }
+}
+
+// ================================================================================================================
+//                        GLOBAL ATTENTION, half-tile pipeline (64-key S tiles, double-buffered per query tile)
+// ================================================================================================================
+// Measured on the kernel above (tools/dbg_attn_g_phases.py): a softmax group spends 1925 of 4400 cycles per 128-key tile
+// WAITING for S — the chain P(j) -> PV(j) -> QK(j+1) -> S(j+1) is serial per query tile because P(j) aliases S(j).  Here one S
+// tile is one KEY ROW of the image (64 keys, 64 fp32 columns) and every query tile owns two of them: QK(h+2) is issued right
+// after PV(h), while the group is still working on S(h+1), so S is always resident when the group asks for it.  TMEM:
+// 4 x 64 (S) + 2 x 80 (O) = 416 columns (two 128-key S buffers per query tile would need 672).  The K / V ring keeps 128-key
+// TMA tiles; a half tile is a descriptor offset of 64 rows.
+template <int HD, int NST_> struct G2Cfg : GCfg<HD, NST_> {
+    static constexpr int NST = NST_;
+    static constexpr int B_QFULL = 0, B_BIAS = 1, B_BREAD = 3, B_KFULL = 5, B_KEMPTY = B_KFULL + NST, B_VFULL = B_KEMPTY + NST,
+                         B_VEMPTY = B_VFULL + NST, B_SFULL = B_VEMPTY + NST, B_PFULL = B_SFULL + 4, B_PVDONE = B_PFULL + 4,
+                         B_ODONE = B_PVDONE + 2, B_COUNT = B_ODONE + 2;
+    static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
+    // S_i^b at 64*(2i+b) (P_i^b aliases its first 32), O_i at 256 + 80*i, Q_i (bf16 pairs, the A operand of QK) at 416 + 48*i
+    static constexpr int TM_S = 0, TM_O = 256, O_STRIDE = 80, TM_Q = 416, Q_STRIDE = 48, TM_COLS = 512;
+};
+
+// D[128 x N] (+)= Q[128 x HD] (bf16 pairs in TMEM) * B[N x HD]^T (K-major in smem): no shared-memory read of the A operand
+template <int HD>
+__device__ __forceinline__ void issue_qk_ts(uint32_t d_tmem, uint32_t q_tmem, uint32_t b_main, uint32_t b_tail, uint32_t idesc) {
+    const uint64_t db = desc_k128(b_main);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::mma_f16_ts(d_tmem, q_tmem + 8 * k, db + 2 * k, idesc, k ? 1u : 0u);
+    if (HD > 64) ptx::mma_f16_ts(d_tmem, q_tmem + 32, desc_k32(b_tail), idesc, 1u);
+}
+
+template <int HD, int NST, bool PH>
+__global__ void __launch_bounds__(352, 1)
+attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
+                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
+                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
+                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int D, int T, float scale_log2,
+                    long long* __restrict__ phase_clocks, int order) {
+    using C = G2Cfg<HD, NST>;
+    constexpr int NKT = 32;                                     // 128-key TMA tiles
+    constexpr int NH = 64;                                      // 64-key half tiles = key rows of the image
+    constexpr int HALF_MAIN = 64 * 128, HALF_TAIL = 64 * 32;    // byte offset of keys 64.. inside a K / V tile
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * T + pair * 256;
+    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
+
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tmap(&tm_main);
+        ptx::prefetch_tmap(&tm_rw_main);
+        ptx::prefetch_tmap(&tm_rh_main);
+        if (HD > 64) { ptx::prefetch_tmap(&tm_tail); ptx::prefetch_tmap(&tm_rw_tail); ptx::prefetch_tmap(&tm_rh_tail); }
+        ptx::mbar_init(&bars[C::B_QFULL], 1);
+        for (int s = 0; s < NST; ++s) {
+            ptx::mbar_init(&bars[C::B_KFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_KEMPTY + s], 2);             // one release per issuer (query tile)
+            ptx::mbar_init(&bars[C::B_VFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_VEMPTY + s], 2);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars[C::B_BIAS + i], 1);
+            ptx::mbar_init(&bars[C::B_BREAD + i], 128);
+            ptx::mbar_init(&bars[C::B_PVDONE + i], 1);
+            ptx::mbar_init(&bars[C::B_ODONE + i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            ptx::mbar_init(&bars[C::B_SFULL + i], 1);
+            ptx::mbar_init(&bars[C::B_PFULL + i], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===================== TMA producer (as in attn_global_kernel) =====================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::Q_TX);
+            for (int i = 0; i < 2; ++i) {
+                ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE, &tm_main, &bars[C::B_QFULL], colq, row0 + 128 * i);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_QFULL], colq + 64, row0 + 128 * i);
+            }
+            ptx::tma_load_2d(sm + C::OFF_RW, &tm_rw_main, &bars[C::B_QFULL], 0, 144);
+            ptx::tma_load_2d(sm + C::OFF_RH, &tm_rh_main, &bars[C::B_QFULL], 0, 4 * pair);
+            if (HD > 64) {
+                ptx::tma_load_2d(sm + C::OFF_RW + C::T_MAIN, &tm_rw_tail, &bars[C::B_QFULL], 64, 144);
+                ptx::tma_load_2d(sm + C::OFF_RH + C::RH_MAIN, &tm_rh_tail, &bars[C::B_QFULL], 64, 4 * pair);
+            }
+            for (int j = 0; j < NKT; ++j) {
+                const int st = j % NST;
+                const uint32_t par = ((j / NST) & 1) ^ 1;
+                const int krow = b * T + j * 128;
+                ptx::mbar_wait(&bars[C::B_KEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_KFULL + st], C::KV_TX);
+                ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
+                ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
+                ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE + C::T_MAIN, &tm_main, &bars[C::B_VFULL + st], colv + 64, krow);
+            }
+        }
+    } else if (warp == 9 || warp == 10) {
+        // ===================== MMA issuers: one per query tile =====================
+        // (a single issuing thread needs ~40 cycles of scalar work per tcgen05.mma + commit: 52 MMAs + 10 commits per 128 keys
+        // made ONE issuer the bottleneck of this pipeline, 2690 cycles per 128 keys; the two tiles' chains are independent)
+        if (lane == 0) {
+            const int i = warp - 9;
+            constexpr uint32_t id_w = ptx::make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t id_rh = ptx::make_idesc_bf16(128, 80, 0, 0);
+            const uint32_t q_main = base + C::OFF_Q + i * C::TILE, q_tail = q_main + C::T_MAIN;
+            const uint32_t q_tm = tmem + C::TM_Q + C::Q_STRIDE * i;
+            const uint32_t o_tm = tmem + C::TM_O + C::O_STRIDE * i;
+            ptx::mbar_wait(&bars[C::B_QFULL], 0);
+            ptx::tc_fence_after();
+            // decomposed rel-pos products: Q.Rw^T -> both S buffers of the tile (128 columns), Q.Rh[4*pair ..]^T -> O_i columns
+            issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main, q_tail, base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_w);
+            issue_qk<HD>(o_tm, q_main, q_tail, base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
+            ptx::mma_commit(&bars[C::B_BIAS + i]);
+            // S_i(0), S_i(1): the two halves of key tile 0
+            ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
+            ptx::mbar_wait(&bars[C::B_BREAD + i], 0);              // bias products consumed (S_i / O_i columns are free), Q_i is in TMEM
+            ptx::tc_fence_after();
+            for (int hb = 0; hb < 2; ++hb) {
+                issue_qk_ts<HD>(tmem + C::TM_S + 64 * (2 * i + hb), q_tm, base + C::OFF_K + hb * HALF_MAIN,
+                                base + C::OFF_K + C::T_MAIN + hb * HALF_TAIL, id_s);
+                ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
+            }
+            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
+            long long ipc[3] = {0, 0, 0};
+            long long itp = PH ? clock64() : 0;
+#define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
+            for (int h = 0; h < NH; ++h) {
+                const int hb = h & 1, jt = h >> 1, st = jt % NST;
+                const bool more = (h + 2 < NH);
+                const int jt2 = (h + 2) >> 1, st2 = jt2 % NST;
+                SVB_IPH(2)
+                if (hb == 0) {
+                    ptx::mbar_wait(&bars[C::B_VFULL + st], (jt / NST) & 1);
+                    if (more) ptx::mbar_wait(&bars[C::B_KFULL + st2], (jt2 / NST) & 1);
+                }
+                SVB_IPH(0)
+                const uint32_t s_i = tmem + C::TM_S + 64 * (2 * i + hb);
+                ptx::mbar_wait(&bars[C::B_PFULL + 2 * i + hb], jt & 1);      // P_i(h) is in TMEM
+                SVB_IPH(1)
+                ptx::tc_fence_after();
+                issue_pv_wide<HD>(o_tm, s_i, base + C::OFF_V + st * C::VTILE + hb * HALF_MAIN, C::T_MAIN, 4, h > 0);
+                ptx::mma_commit(&bars[C::B_PVDONE + i]);
+                if (h == NH - 1) ptx::mma_commit(&bars[C::B_ODONE + i]);     // O_i is complete
+                if (hb == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
+                if (more) {
+                    // in-order execution of this thread's MMAs: the overwrite of S_i^hb / P_i^hb follows the PV above
+                    issue_qk_ts<HD>(s_i, q_tm, base + C::OFF_K + st2 * C::TILE + hb * HALF_MAIN,
+                                    base + C::OFF_K + st2 * C::TILE + C::T_MAIN + hb * HALF_TAIL, id_s);
+                    ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
+                    if (hb == 1) ptx::mma_commit(&bars[C::B_KEMPTY + st2]);
+                }
+            }
+#undef SVB_IPH
+            if (PH && phase_clocks && i == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
+            }
+        }
+    } else {
+        // ===================== softmax warps: 2 groups of 128 query rows =====================
+        const int i = warp >> 2;                                   // query tile of this warp group
+        const int w4 = warp & 3;                                   // TMEM lane quadrant
+        const int t = w4 * 32 + lane;                              // query row inside the tile
+        const int qr = 2 * i + (t >> 6);                           // grid row of the query inside the CTA (0..3), warp-uniform
+        const int qw = t & 63;                                     // grid column of the query
+        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + C::TM_S + 128 * i;
+        const uint32_t o_tmem = tmem + lane_off + C::TM_O + C::O_STRIDE * i;
+        float* stg = reinterpret_cast<float*>(sm + C::OFF_STG + warp * 8192);   // [64][32] fp32, private to this warp
+
+        // ---- this thread's query row -> TMEM (bf16 pairs, the layout P has): the A operand of every QK product ----
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + 128 * i + t) * (3 * D) + colq);
+            const uint32_t q_tmem = tmem + lane_off + C::TM_Q + C::Q_STRIDE * i;
+            uint32_t qa[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = __ldg(src + c);
+                qa[4 * c] = u.x; qa[4 * c + 1] = u.y; qa[4 * c + 2] = u.z; qa[4 * c + 3] = u.w;
+            }
+            ptx::tmem_st_x32(q_tmem, qa);
+            if (HD > 64) {
+                uint32_t qb[8];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint4 u = __ldg(src + 8 + c);
+                    qb[4 * c] = u.x; qb[4 * c + 1] = u.y; qb[4 * c + 2] = u.z; qb[4 * c + 3] = u.w;
+                }
+                ptx::tmem_st_x8(q_tmem + 32, qb);
+            }
+            ptx::tmem_st_wait();
+        }
+        // ---- rel-pos prologue: w term into registers, h term into this warp's smem column block ----
+        float bwl[64];
+        ptx::mbar_wait(&bars[C::B_BIAS + i], 0);
+        ptx::mbar_wait(&bars[C::B_BIAS + (i ^ 1)], 0);             // the staging area below aliases the tables BOTH tiles' bias MMAs read
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(s_tmem + 64 * p + 32 * hh, v);
+                ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) stg[(32 * hh + e) * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int kw = 0; kw < 64; ++kw) {
+                const int c = qw + 63 - kw;                        // table row qw - kw + 63
+                if ((c >> 6) == p) bwl[kw] = stg[(c & 63) * 32 + lane];
+            }
+            __syncwarp();
+        }
+        float bwmax = bwl[0];
+#pragma unroll
+        for (int kw = 1; kw < 64; ++kw) bwmax = fmaxf(bwmax, bwl[kw]);
+        {
+            // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
+            uint32_t v[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                ptx::tmem_ld_x32(o_tmem + c0, v);
+                ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int kh = qr + 63 - (c0 + e);
+                    if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+                }
+            }
+            uint32_t w[16];
+            ptx::tmem_ld_x16(o_tmem + 64, w);
+            ptx::tmem_ld_wait_dep(w);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int kh = qr + 63 - (64 + e);
+                if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(w[e]) * LOG2E;
+            }
+        }
+        __syncwarp();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_BREAD + i]);                   // S_i / O_i columns may be overwritten
+
+        float m_ref = -INFINITY;
+        float x_over = 0.f;                                          // previous tile's maximum exponent relative to m_ref
+        f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
+        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+        long long pc[5] = {0, 0, 0, 0, 0};
+        long long tprev = PH ? clock64() : 0;
+#define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+            const int hb = h & 1;
+            const uint32_t s_h = s_tmem + 64 * hb;
+            // S(h) sits in the other buffer than P(h-1) and is normally already there: its loads are started BEFORE the hand-over
+            // of P(h-1), so their latency overlaps the store drain (loads and their wait stay in straight-line code: the
+            // destination registers of an in-flight tcgen05.ld must not cross a loop edge, where the compiler may copy them)
+            uint32_t va[32], vb[32];
+            ptx::mbar_wait(&bars[C::B_SFULL + 2 * i + hb], (h >> 1) & 1);
+            SVB_GPH(0)
+            ptx::tc_fence_after();
+            ptx::tmem_ld_x32(s_h, va);
+            ptx::tmem_ld_x32(s_h + 32, vb);
+            if (h > 0) {
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + (hb ^ 1)]);
+            }
+            SVB_GPH(3)
+            const float bh = stg[h * 32 + lane];
+            float m_new;
+            bool need;
+            ptx::tmem_ld_wait_dep(va);
+            ptx::tmem_ld_wait_dep(vb);
+            SVB_GPH(4)
+            if (h == 0) {
+                const float sm0 = max32(vb, max32(va, -INFINITY));
+                m_new = fmaf(sm0, scale_log2, bh) + bwmax;         // upper bound of the row maximum in log2 units (scale > 0)
+                need = true;
+            } else {
+                need = x_over > RESCALE_THRESHOLD;                 // the previous tile's maximum relative to m_ref
+                m_new = need ? m_ref + x_over : m_ref;
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                if (h > 0) {
+                    const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
+                    ptx::mbar_wait(&bars[C::B_PVDONE + i], (h - 1) & 1);   // O_i holds tiles 0..h-1
+                    ptx::tc_fence_after();
+                    uint32_t r[16];
+#pragma unroll
+                    for (int c0 = 0; c0 < HD; c0 += 16) {
+                        ptx::tmem_ld_x16(o_tmem + c0, r);
+                        ptx::tmem_ld_wait_dep(r);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                        ptx::tmem_st_x16(o_tmem + c0, r);
+                    }
+                    const f32x2 al2 = f2_pack(alpha, alpha);
+                    l01 = f2_mul(l01, al2);
+                    l23 = f2_mul(l23, al2);
+                }
+                m_ref = m_new;
+                SVB_GPH(2)
+            }
+            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
+            const f32x2 dd2 = f2_pack(bh - m_ref, bh - m_ref);
+            // ---- P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
+#define SVB_PASS_H(V, CHUNK)                                                                             \
+            {                                                                                            \
+                uint32_t pk[16];                                                                         \
+                _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
+                    const int kw = 32 * (CHUNK) + e;                                                     \
+                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,         \
+                                                    f2_pack(bwl[kw], bwl[kw + 1])), dd2);                \
+                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e + 2]), __uint_as_float(V[e + 3])), sc2,     \
+                                                    f2_pack(bwl[kw + 2], bwl[kw + 3])), dd2);            \
+                    float a0, a1, a2, a3;                                                                \
+                    f2_unpack(x01, a0, a1);                                                              \
+                    f2_unpack(x23, a2, a3);                                                              \
+                    xa = fmax3(xa, a0, a1);                                                              \
+                    xb = fmax3(xb, a2, a3);                                                              \
+                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
+                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);                      \
+                    l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
+                    l23 = f2_add(l23, f2_pack(p2, p3));                                                  \
+                    pk[e / 2] = pack_bf16x2(p0, p1);                                                     \
+                    pk[e / 2 + 1] = pack_bf16x2(p2, p3);                                                 \
+                }                                                                                        \
+                ptx::tmem_st_x16(s_h + 16 * (CHUNK), pk);                                                \
+            }
+            SVB_PASS_H(va, 0)
+            SVB_PASS_H(vb, 1)
+#undef SVB_PASS_H
+            x_over = fmaxf(xa, xb);
+            SVB_GPH(1)
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + 1]);             // P(NH-1)
+        SVB_GPH(3)
+#undef SVB_GPH
+        if (PH && phase_clocks && w4 == 0 && lane == 0) {
+            for (int k = 0; k < 3; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)(NH / 2));
+            if (i == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 7, (unsigned long long)pc[3]); atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 15, (unsigned long long)pc[4]); }
+        }
+        // ---- epilogue: O / l at the query's own token position (its own barrier: the per-tile PVDONE phases may be up to two
+        // ahead of this group here, which a parity wait cannot tell apart) ----
+        ptx::mbar_wait(&bars[C::B_ODONE + i], 0);
         ptx::tc_fence_after();
         float l0, l1, l2, l3;
         f2_unpack(l01, l0, l1);
@@ -1070,9 +1491,8 @@ __global__ void pack_rel_kernel(const float* __restrict__ src, bf16* __restrict_
         dst[(size_t)row_off * hd + i] = __float2bfloat16_rn(src[i]);
 }
 
-template <int HD>
-int launch_global(const AttnTcParams& p, cudaStream_t stream) {
-    constexpr int NST = (HD > 64) ? 2 : 3;
+template <int HD, int NST>
+int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
     using C = GCfg<HD, NST>;
     const int D = p.heads * p.hd, T = p.grid * p.grid;
     CUtensorMap m[6];
@@ -1097,14 +1517,40 @@ int launch_global(const AttnTcParams& p, cudaStream_t stream) {
     if (!attr_set) {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     dim3 grid(T / 256, p.heads, p.batch);
-    if (onepass) attn_global_kernel<HD, NST, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
-    else attn_global_kernel<HD, NST, false><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2);
+    // SVB_ATTNG_IMPL=1 selects the 128-key-tile kernel (A/B comparisons); default: the half-tile pipeline
+    static const int impl = [] { const char* e = getenv("SVB_ATTNG_IMPL"); return e ? atoi(e) : 2; }();
+    if (impl == 2) {
+        static const int order = [] { const char* e = getenv("SVB_ATTNG_ORDER"); return e ? atoi(e) : 1; }();
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+            attr2_set = true;
+        }
+        if (p.phase_clocks)
+            attn_global2_kernel<HD, NST, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, order);
+        else
+            attn_global2_kernel<HD, NST, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
+        SVB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (p.phase_clocks)
+        attn_global_kernel<HD, NST, true, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, p.phase_clocks);
+    else if (onepass) attn_global_kernel<HD, NST, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, nullptr);
+    else attn_global_kernel<HD, NST, false><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, nullptr);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int HD>
+int launch_global(const AttnTcParams& p, cudaStream_t stream) {
+    // K/V ring depth: 3 stages at head_dim 64, 2 at 80 (V tiles of two full atoms; 2 vs 3 stages measured identical)
+    return launch_global_nst<HD, (HD > 64) ? 2 : 3>(p, stream);
 }
 
 template <int HD>

@@ -18,6 +18,7 @@ struct ProbeArgs {
     uint32_t a_lbo, a_sbo, a_kstep; // descriptor byte offsets, per-K=16 start-address advance (bytes)
     uint32_t b_lbo, b_sbo, b_kstep;
     uint32_t idesc;
+    int b_atoms;                    // MN-major B: 64-element atoms along N (1 or 2)
     int a_manual;                   // 1: A written by threads (row-major [128][K] in global, K = 64*n) with manual SW128
                                     // 2: A written by threads into TMEM columns [128, 128 + K/2) as packed bf16 pairs (the P path)
     const bf16* a_gl;
@@ -72,6 +73,8 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             else ptx::tma_load_2d(sA, &map_a, &bar[0], 0, 0);
         }
         ptx::tma_load_2d(sB, &map_b, &bar[0], 0, 0);
+        // MN-major B wider than one 64-element atom: second atom = columns 64.. (out-of-range columns are zero-filled by the TMA)
+        if (pa.b_atoms == 2) ptx::tma_load_2d(sB + pa.K * 128, &map_b, &bar[0], 64, 0);
         ptx::mbar_wait(&bar[0], 0);
         ptx::tc_fence_after();
         const uint32_t a_layout = pa.a_sw == 128 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW32;
@@ -98,6 +101,102 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     __syncthreads();
     if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
+
+// MMA issue-rate microbenchmark (svb_probe_mma_rate): ONE thread issues `reps` tcgen05.mma of one shape back to back (operands:
+// zeroed shared memory / TMEM), commits and waits; out[0] = cycles from the first issue to the completion, out[1] = cycles spent
+// in the issue loop.  variant: 0 SS N=128 K-major B | 1 SS N=64 | 2 TS N=64 K-major B | 3 TS N=64 MN-major B | 4 TS N=16 MN-major
+// SW32 | 5 PV step (3 then 4, counted as one) | 6 TS N=128 K-major B | 7 SS N=208 | 8 TS N=80 as 64+16 K-major.  alt_d != 0: the
+// accumulator alternates between two column ranges (no read-modify-write chain on one range).
+template <int V>
+__global__ void __launch_bounds__(128, 1) probe_rate_kernel(int reps, int alt_d, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 131072);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(sm + 131072 + 64);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 131072 / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    volatile int* stop = reinterpret_cast<volatile int*>(sm + 131072 + 128);
+    if (tid == 0) { for (int b = 0; b < 5; ++b) ptx::mbar_init(&bar[b], 1); *stop = 0; ptx::fence_barrier_init(); }
+    if (warp == 0) ptx::tmem_alloc(slot, 512);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *slot;
+    {
+        uint32_t z[16];
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c0 = 0; c0 < 512; c0 += 16) ptx::tmem_st_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, z);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint32_t sA = base, sB = base + 65536;
+        const uint32_t a_tm = tmem + 448;                    // A operand columns (TS variants)
+        uint64_t da[4], dbk[4], dbm[4], dbt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            da[k] = ptx::make_smem_desc(sA, 0, 1024, ptx::LAYOUT_SW128) + 2 * k;
+            dbk[k] = ptx::make_smem_desc(sB, 0, 1024, ptx::LAYOUT_SW128) + 2 * k;
+            dbm[k] = ptx::make_smem_desc(sB + k * 2048, 0, 1024, ptx::LAYOUT_SW128);
+            dbt[k] = ptx::make_smem_desc(sB + 32768 + k * 512, 0, 256, ptx::LAYOUT_SW32);
+        }
+        const uint32_t d1 = tmem + ((alt_d & 1) ? 224 : 0);
+        const bool commit_each = (alt_d & 2) != 0;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; r += 4) {
+            if (commit_each && r) ptx::mma_commit(&bar[1 + ((r >> 2) & 3)]);      // a commit every 4 (8) MMAs, as the attention issuers do
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t d = (k & 1) ? d1 : tmem;
+                if (V == 0) ptx::mma_f16_ss(d, da[k], dbk[k], ptx::make_idesc_bf16(128, 128, 0, 0), 1u);
+                if (V == 1) ptx::mma_f16_ss(d, da[k], dbk[k], ptx::make_idesc_bf16(128, 64, 0, 0), 1u);
+                if (V == 2) ptx::mma_f16_ts(d, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 64, 0, 0), 1u);
+                if (V == 3) ptx::mma_f16_ts(d, a_tm + 8 * k, dbm[k], ptx::make_idesc_bf16(128, 64, 0, 1), 1u);
+                if (V == 4) ptx::mma_f16_ts(d + 64, a_tm + 8 * k, dbt[k], ptx::make_idesc_bf16(128, 16, 0, 1), 1u);
+                if (V == 5) {
+                    ptx::mma_f16_ts(d, a_tm + 8 * k, dbm[k], ptx::make_idesc_bf16(128, 64, 0, 1), 1u);
+                    ptx::mma_f16_ts(d + 64, a_tm + 8 * k, dbt[k], ptx::make_idesc_bf16(128, 16, 0, 1), 1u);
+                }
+                if (V == 6) ptx::mma_f16_ts(d, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 128, 0, 0), 1u);
+                if (V == 7) ptx::mma_f16_ss(d, da[k], dbk[k], ptx::make_idesc_bf16(128, 208, 0, 0), 1u);
+                if (V == 8) {
+                    ptx::mma_f16_ts(d, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 64, 0, 0), 1u);
+                    ptx::mma_f16_ts(d + 64, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 16, 0, 0), 1u);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        ptx::mma_commit(&bar[0]);
+        ptx::mbar_wait(&bar[0], 0);
+        const long long t2 = clock64();
+        out[0] = t2 - t0;
+        out[1] = t1 - t0;
+        *stop = 1;
+    } else if ((alt_d & 4) && warp > 0) {
+        // background tensor-memory traffic from the other warps (what the softmax groups do): x32 loads + x16 stores on columns
+        // the MMAs do not touch
+        uint32_t v[32], w[16];
+        const uint32_t col = tmem + (static_cast<uint32_t>(warp * 32) << 16) + 300;
+        for (int j = 0; j < 16; ++j) w[j] = 0u;
+        while (*stop == 0) {
+            ptx::tmem_ld_x32(col, v);
+            ptx::tmem_ld_wait_dep(v);
+            ptx::tmem_ld_x32(col + 32, v);
+            ptx::tmem_ld_wait_dep(v);
+            w[0] = v[3];
+            ptx::tmem_st_x16(col, w);
+            ptx::tmem_st_x16(col + 16, w);
+            ptx::tmem_st_wait();
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
 }  // namespace
 }  // namespace svb
 
@@ -113,7 +212,7 @@ extern "C" int svb_probe_mma(const void* a, const void* b, float* out, int K, in
     pa.a_lbo = a_lbo; pa.a_sbo = a_sbo; pa.a_kstep = a_kstep;
     pa.b_lbo = b_lbo; pa.b_sbo = b_sbo; pa.b_kstep = b_kstep;
     pa.idesc = ptx::make_idesc_bf16(128, N, 0, b_mn_major);
-    pa.a_manual = a_manual; pa.a_gl = (const bf16*)a;
+    pa.a_manual = a_manual; pa.a_gl = (const bf16*)a; pa.b_atoms = 1;
     int rc;
     // A: global [128][K] row-major; SW128 -> boxes of 64 columns (one per 64-wide atom), SW32 -> K must be 16
     if (a_sw == 128) rc = make_tmap_2d_bf16(&ma, a, K, 128, K, 64, 128, 128);
@@ -128,13 +227,25 @@ extern "C" int svb_probe_mma(const void* a, const void* b, float* out, int K, in
     } else {             // B global [K][N] (N contiguous): box {N_inner, K rows}
         if (b_sw == 128) rc = make_tmap_2d_bf16(&mb, b, N, K, N, 64, K, 128);
         else rc = make_tmap_2d_bf16(&mb, b, N, K, N, 16, K, 32);
-        pa.b_bytes = K * (b_sw == 128 ? 64 : 16) * 2;
-        SVB_REQUIRE(N == (b_sw == 128 ? 64 : 16), "probe: MN-major B supports a single atom along N");
+        pa.b_atoms = (b_sw == 128 && N > 64) ? 2 : 1;
+        pa.b_bytes = K * (b_sw == 128 ? 64 : 16) * 2 * pa.b_atoms;
+        SVB_REQUIRE(b_sw == 128 ? (N <= 128) : (N == 16), "probe: MN-major B supports up to two 64-element atoms along N (SW128) or N = 16 (SW32)");
     }
     if (rc) return rc;
     const int smem = 131072 + 1024 + 256;
     SVB_CHECK_CUDA(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(ma, mb, pa, out);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream) {
+    SVB_REQUIRE(cycles_out && reps > 0 && reps % 4 == 0 && variant >= 0 && variant <= 8, "probe_mma_rate: bad argument");
+    const int smem = 131072 + 1024 + 256;
+#define SVB_RATE(V) case V: SVB_CHECK_CUDA(cudaFuncSetAttribute(probe_rate_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+                        probe_rate_kernel<V><<<1, 128, smem, (cudaStream_t)stream>>>(reps, alt_d, cycles_out); break;
+    switch (variant) { SVB_RATE(0) SVB_RATE(1) SVB_RATE(2) SVB_RATE(3) SVB_RATE(4) SVB_RATE(5) SVB_RATE(6) SVB_RATE(7) SVB_RATE(8) }
+#undef SVB_RATE
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -63,6 +63,13 @@ def test_descriptor_encodings():
         c4[f"lbo{lbo}_sbo{sbo}_k{kstep}"] = err(run(a2, b4, 128, 16, 128, 32, 1, 1, 0, 1024, 32, lbo, sbo, kstep), ref4)
     report["mn_sw32"] = c4
     report["mn_sw32_tmem_a"] = err(run(a2, b4, 128, 16, 128, 32, 1, 2, 0, 1024, 32, 0, 256, 512), ref4)
+    # 5. MN-major B spanning two 64-element atoms along N (V with head_dim 80 as ONE MMA): LBO = byte stride between the atoms
+    b5 = torch.randn(128, 80, generator=g).bfloat16().to(DEV)
+    ref5 = a2.double() @ b5.double()
+    c5 = {}
+    for lbo in (16384, 1024, 0):
+        c5[f"lbo{lbo}_sbo1024_k2048"] = err(run(a2, b5, 128, 80, 128, 128, 1, 2, 0, 1024, 32, lbo, 1024, 2048), ref5)
+    report["mn_sw128_two_atoms_tmem_a"] = c5
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe_report.json"), "w") as f:
         json.dump(report, f, indent=1)
@@ -75,3 +82,4 @@ def test_descriptor_encodings():
     assert report["mn_sw32_tmem_a"] < 1e-5
     assert report["kmajor_sw32"]["sbo256"] < 1e-5
     assert report["mn_sw32"]["lbo0_sbo256_k512"] < 1e-5
+    assert report["mn_sw128_two_atoms_tmem_a"]["lbo16384_sbo1024_k2048"] < 1e-5
