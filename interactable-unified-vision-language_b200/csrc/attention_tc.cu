@@ -1165,7 +1165,11 @@ template <int HD> struct WPCfg {
     static constexpr int V_TX = 196 * ROWB;
     static constexpr int R_TX = 64 * ROWB;
     static constexpr int B_RFULL = 0, B_QKFULL = 1, B_VFULL = 3, B_EMPTY = 5, B_BIAS = 7, B_BREAD = 9, B_SFULL = 11, B_PFULL = 13,
-                         B_PVDONE = 15, B_COUNT = 17;
+                         B_PVDONE = 15, B_OSTAGED = 17, B_COUNT = 19;
+    // V tile at head_dim 80: FIVE 16-column atoms of the 32B swizzle, V_ATOM bytes apart (an MN-major operand's leading-dimension
+    // byte offset), so that P.V is ONE N = 80 MMA per K step (a tcgen05.mma with A in TMEM costs >= 44.5 cycles whatever N is:
+    // the 64 + 16 pair cost 89).  At head_dim 64: one 64-column atom of the 128B swizzle.
+    static constexpr int V_ATOM = 208 * 32;
     static constexpr int TM_COLS = 512;                                       // S_i at 208*i; O_i inside S_i at +112
 };
 
@@ -1192,7 +1196,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 }
 
 template <int HD>
-__global__ void __launch_bounds__(352, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
                               long long* __restrict__ phase_clocks) {
     using C = WPCfg<HD>;
@@ -1212,7 +1216,8 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         ptx::prefetch_tmap(&maps.o0);
         ptx::prefetch_tmap(&maps.o1);
         for (int s = 0; s < C::B_COUNT; ++s) {
-            const bool by_threads = (s >= C::B_BREAD && s < C::B_BREAD + 2) || (s >= C::B_PFULL && s < C::B_PFULL + 2);
+            const bool by_threads = (s >= C::B_BREAD && s < C::B_BREAD + 2) || (s >= C::B_PFULL && s < C::B_PFULL + 2) ||
+                                    (s >= C::B_OSTAGED && s < C::B_OSTAGED + 2);
             const bool by_tiles = (s >= C::B_EMPTY && s < C::B_EMPTY + 2);            // one release per query tile
             ptx::mbar_init(&bars[s], by_threads ? 128 : (by_tiles ? 2 : 1));
         }
@@ -1222,9 +1227,12 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
     // keys 196..207 of the PV contraction multiply P = 0: their V rows (never written by TMA) must be finite in both stages
     for (int st = 0; st < 2; ++st) {
         uint8_t* v = sm + st * C::STAGE + C::OFF_V;
-        for (int i = threadIdx.x; i < 96; i += blockDim.x) *reinterpret_cast<uint4*>(v + 196 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
-        if (HD > 64)
-            for (int i = threadIdx.x; i < 24; i += blockDim.x) *reinterpret_cast<uint4*>(v + C::K_MAIN + 196 * 32 + i * 16) = make_uint4(0, 0, 0, 0);
+        if (HD > 64) {
+            for (int i = threadIdx.x; i < 5 * 24; i += blockDim.x)
+                *reinterpret_cast<uint4*>(v + (i / 24) * C::V_ATOM + 196 * 32 + (i % 24) * 16) = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int i = threadIdx.x; i < 96; i += blockDim.x) *reinterpret_cast<uint4*>(v + 196 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
+        }
     }
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
@@ -1271,8 +1279,11 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                     ptx::tma_load_4d(k + C::K_MAIN, &maps.kvt, &bars[C::B_QKFULL + st], ck + 64, x0, y0, b);
                 }
                 ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
-                ptx::tma_load_4d(v, &maps.kv, &bars[C::B_VFULL + st], cv, x0, y0, b);
-                if (HD > 64) ptx::tma_load_4d(v + C::K_MAIN, &maps.kvt, &bars[C::B_VFULL + st], cv + 64, x0, y0, b);
+                if (HD > 64) {
+                    for (int a = 0; a < 5; ++a) ptx::tma_load_4d(v + a * C::V_ATOM, &maps.kvt, &bars[C::B_VFULL + st], cv + 16 * a, x0, y0, b);
+                } else {
+                    ptx::tma_load_4d(v, &maps.kv, &bars[C::B_VFULL + st], cv, x0, y0, b);
+                }
             }
         }
     } else if (warp == 9 || warp == 10) {
@@ -1310,10 +1321,43 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                 ptx::mbar_wait(&bars[C::B_VFULL + st], ph);
                 ptx::mbar_wait(&bars[C::B_PFULL + i], n & 1);      // P_i is in TMEM
                 ptx::tc_fence_after();
-                issue_pv<HD>(tmem + 208 * i + 112, tmem + 208 * i, v, v + C::K_MAIN, 13, false);
+                if (HD > 64) {
+                    constexpr uint32_t id_pv = ptx::make_idesc_bf16(128, HD, 0, 1);
+                    const uint64_t dv = ptx::make_smem_desc(v, C::V_ATOM, 256, ptx::LAYOUT_SW32);
+#pragma unroll
+                    for (int kk = 0; kk < 13; ++kk)                // 16 keys = 512 B inside an atom
+                        ptx::mma_f16_ts(tmem + 208 * i + 112, tmem + 208 * i + 8 * kk, dv + 32 * kk, id_pv, kk ? 1u : 0u);
+                } else {
+                    issue_pv<HD>(tmem + 208 * i + 112, tmem + 208 * i, v, v + C::K_MAIN, 13, false);
+                }
                 ptx::mma_commit(&bars[C::B_PVDONE + i]);
                 ++n;
             }
+        }
+    } else if (warp == 11) {
+        // ===================== store warp: O tiles staged by the groups -> ONE tensor store per tile =====================
+        // (the wait for the store to finish reading the stage sat on the critical path of the group's first warp)
+        if (lane == 0) {
+            int it = 0;
+            uint32_t n[2] = {0, 0};
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int st = it & 1;
+                int b, wy, wx, head;
+                decode(item, b, wy, wx, head);
+                for (int i = 0; i < 2; ++i) {
+                    if (i == 1 && wy * WS + 9 >= g) continue;      // released by the issuer
+                    const uint8_t* ob = sm + st * C::STAGE + i * C::QT;
+                    ptx::mbar_wait(&bars[C::B_OSTAGED + i], n[i] & 1);
+                    ++n[i];
+                    const int x0 = wx * WS, y0 = wy * WS + 9 * i;
+                    tma_store_4d(i ? &maps.o1 : &maps.o0, ob, head * HD, x0, y0, b);   // rows / columns past 64 are clipped by the TMA
+                    if (HD > 64) tma_store_4d(i ? &maps.o1t : &maps.o0t, ob + C::Q_MAIN, head * HD + 64, x0, y0, b);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the store has finished reading the stage
+                    ptx::mbar_arrive(&bars[C::B_EMPTY + st]);      // this tile is done with stage st (its MMAs retired before PVDONE)
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                  // stores complete before the CTA exits
         }
     } else {
         // ===================== softmax warps: group i = query tile i =====================
@@ -1334,19 +1378,19 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         auto read_bias = [&](uint32_t ph) {
             ptx::mbar_wait(&bars[C::B_BIAS + i], ph);
             ptx::tc_fence_after();
-            uint32_t v[32];
+            uint32_t v[32], v2[32];
             float rr[27];
-            ptx::tmem_ld_x32(s_tmem, v);
+            ptx::tmem_ld_x32(s_tmem, v);                           // both loads in flight: one tensor-memory round trip
+            ptx::tmem_ld_x32(s_tmem + 32, v2);
             ptx::tmem_ld_wait_dep(v);
+            ptx::tmem_ld_wait_dep(v2);
 #pragma unroll
             for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
             barrel_shift27(rr, yi < 13 ? yi : 13);
 #pragma unroll
             for (int kk = 0; kk < 14; ++kk) bhm[kk] = rr[13 - kk];
-            ptx::tmem_ld_x32(s_tmem + 32, v);
-            ptx::tmem_ld_wait_dep(v);
 #pragma unroll
-            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
+            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v2[j]) * LOG2E;
             barrel_shift27(rr, xi);
 #pragma unroll
             for (int kk = 0; kk < 14; ++kk) bwl[kk] = rr[13 - kk];
@@ -1422,17 +1466,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                             make_uint4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
                 }
                 ptx::fence_proxy_async_smem();                     // generic writes -> visible to the TMA (async proxy) read
-                if (i == 0) asm volatile("bar.sync 1, 128;" ::: "memory");          // the group's 128 rows are staged
-                else asm volatile("bar.sync 2, 128;" ::: "memory");
-                if (t == 0) {
-                    const int x0 = wx * WS, y0 = wy * WS + 9 * i;
-                    tma_store_4d(omap, ob, head * HD, x0, y0, b);  // rows past 64 and columns past 64 are clipped by the TMA
-                    if (HD > 64) tma_store_4d(omapt, ob + C::Q_MAIN, head * HD + 64, x0, y0, b);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has finished reading the stage
-                    ptx::mbar_arrive(&bars[C::B_EMPTY + st]);      // this tile is done with stage st (its MMAs retired before PVDONE)
-                }
-                __syncwarp();                                      // reconverge before the next warp-collective tcgen05 instruction
+                ptx::mbar_arrive(&bars[C::B_OSTAGED + i]);         // the store warp issues the tensor store and releases the stage
             }
             if (!early && nitem < num_items) read_bias((n + 1) & 1);
             SVB_PHASE(5)
@@ -1441,7 +1475,6 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ++n;
         }
 #undef SVB_PHASE
-        if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // stores complete before the CTA exits
         if (phase_clocks && w4 == 0 && lane == 0) {
             for (int k = 0; k < 6; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
             atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)n);
@@ -1631,7 +1664,7 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
-    attn_window_persistent_kernel<HD><<<grid, 352, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    attn_window_persistent_kernel<HD><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

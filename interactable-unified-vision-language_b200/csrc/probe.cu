@@ -74,7 +74,9 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
         ptx::tma_load_2d(sB, &map_b, &bar[0], 0, 0);
         // MN-major B wider than one 64-element atom: second atom = columns 64.. (out-of-range columns are zero-filled by the TMA)
-        if (pa.b_atoms == 2) ptx::tma_load_2d(sB + pa.K * 128, &map_b, &bar[0], 64, 0);
+        if (pa.b_sw == 128 && pa.b_atoms == 2) ptx::tma_load_2d(sB + pa.K * 128, &map_b, &bar[0], 64, 0);
+        // ... or than one 16-element atom of the 32B swizzle: atom a = columns 16a.., K * 32 bytes apart
+        if (pa.b_sw == 32) for (int a = 1; a < pa.b_atoms; ++a) ptx::tma_load_2d(sB + a * pa.K * 32, &map_b, &bar[0], 16 * a, 0);
         ptx::mbar_wait(&bar[0], 0);
         ptx::tc_fence_after();
         const uint32_t a_layout = pa.a_sw == 128 ? ptx::LAYOUT_SW128 : ptx::LAYOUT_SW32;
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(int reps, int alt_d,
                 }
                 if (V == 6) ptx::mma_f16_ts(d, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 128, 0, 0), 1u);
                 if (V == 7) ptx::mma_f16_ss(d, da[k], dbk[k], ptx::make_idesc_bf16(128, 208, 0, 0), 1u);
+                if (V == 9) ptx::mma_f16_ts(d, a_tm + 8 * k, ptx::make_smem_desc(sB + k * 2048, 16384, 1024, ptx::LAYOUT_SW128), ptx::make_idesc_bf16(128, 80, 0, 1), 1u);
+                if (V == 10) ptx::mma_f16_ts(d, a_tm + 8 * k, ptx::make_smem_desc(sB + k * 512, 6656, 256, ptx::LAYOUT_SW32), ptx::make_idesc_bf16(128, 80, 0, 1), 1u);
                 if (V == 8) {
                     ptx::mma_f16_ts(d, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 64, 0, 0), 1u);
                     ptx::mma_f16_ts(d + 64, a_tm + 8 * k, dbk[k], ptx::make_idesc_bf16(128, 16, 0, 0), 1u);
@@ -227,9 +231,9 @@ extern "C" int svb_probe_mma(const void* a, const void* b, float* out, int K, in
     } else {             // B global [K][N] (N contiguous): box {N_inner, K rows}
         if (b_sw == 128) rc = make_tmap_2d_bf16(&mb, b, N, K, N, 64, K, 128);
         else rc = make_tmap_2d_bf16(&mb, b, N, K, N, 16, K, 32);
-        pa.b_atoms = (b_sw == 128 && N > 64) ? 2 : 1;
+        pa.b_atoms = b_sw == 128 ? ((N > 64) ? 2 : 1) : N / 16;
         pa.b_bytes = K * (b_sw == 128 ? 64 : 16) * 2 * pa.b_atoms;
-        SVB_REQUIRE(b_sw == 128 ? (N <= 128) : (N == 16), "probe: MN-major B supports up to two 64-element atoms along N (SW128) or N = 16 (SW32)");
+        SVB_REQUIRE(b_sw == 128 ? (N <= 128) : (N <= 128), "probe: MN-major B supports up to two 64-element atoms (SW128) or eight 16-element atoms (SW32) along N");
     }
     if (rc) return rc;
     const int smem = 131072 + 1024 + 256;
@@ -240,11 +244,11 @@ extern "C" int svb_probe_mma(const void* a, const void* b, float* out, int K, in
 }
 
 extern "C" int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream) {
-    SVB_REQUIRE(cycles_out && reps > 0 && reps % 4 == 0 && variant >= 0 && variant <= 8, "probe_mma_rate: bad argument");
+    SVB_REQUIRE(cycles_out && reps > 0 && reps % 4 == 0 && variant >= 0 && variant <= 10, "probe_mma_rate: bad argument");
     const int smem = 131072 + 1024 + 256;
 #define SVB_RATE(V) case V: SVB_CHECK_CUDA(cudaFuncSetAttribute(probe_rate_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
                         probe_rate_kernel<V><<<1, 128, smem, (cudaStream_t)stream>>>(reps, alt_d, cycles_out); break;
-    switch (variant) { SVB_RATE(0) SVB_RATE(1) SVB_RATE(2) SVB_RATE(3) SVB_RATE(4) SVB_RATE(5) SVB_RATE(6) SVB_RATE(7) SVB_RATE(8) }
+    switch (variant) { SVB_RATE(0) SVB_RATE(1) SVB_RATE(2) SVB_RATE(3) SVB_RATE(4) SVB_RATE(5) SVB_RATE(6) SVB_RATE(7) SVB_RATE(8) SVB_RATE(9) SVB_RATE(10) }
 #undef SVB_RATE
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -70,6 +70,11 @@ def test_descriptor_encodings():
     for lbo in (16384, 1024, 0):
         c5[f"lbo{lbo}_sbo1024_k2048"] = err(run(a2, b5, 128, 80, 128, 128, 1, 2, 0, 1024, 32, lbo, 1024, 2048), ref5)
     report["mn_sw128_two_atoms_tmem_a"] = c5
+    # 6. the same with the 32B swizzle: five 16-element atoms along N, K * 32 bytes apart (no padding columns in shared memory)
+    c6 = {}
+    for lbo in (4096, 256, 0):
+        c6[f"lbo{lbo}_sbo256_k512"] = err(run(a2, b5, 128, 80, 128, 32, 1, 2, 0, 1024, 32, lbo, 256, 512), ref5)
+    report["mn_sw32_five_atoms_tmem_a"] = c6
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe_report.json"), "w") as f:
         json.dump(report, f, indent=1)
@@ -83,3 +88,4 @@ def test_descriptor_encodings():
     assert report["kmajor_sw32"]["sbo256"] < 1e-5
     assert report["mn_sw32"]["lbo0_sbo256_k512"] < 1e-5
     assert report["mn_sw128_two_atoms_tmem_a"]["lbo16384_sbo1024_k2048"] < 1e-5
+    assert report["mn_sw32_five_atoms_tmem_a"]["lbo4096_sbo256_k512"] < 1e-5
