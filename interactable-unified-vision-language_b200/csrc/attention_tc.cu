@@ -77,6 +77,24 @@ __device__ __forceinline__ void issue_pv_wide(uint32_t o_tmem, uint32_t p_tmem, 
     }
 }
 
+// 2^x for a pair of exponents on the FMA / ALU pipes instead of the MUFU (16 ex2 per clock and SM is what bounds both softmax
+// loops): round-to-nearest split x = j + f with |f| <= 0.5 by the 1.5 * 2^23 trick, degree-3 minimax polynomial of 2^f (maximum
+// relative error 7.5e-5, far below the bf16 rounding of P), the exponent added by integer arithmetic.  x is clamped at -120.
+__device__ __forceinline__ void exp2_poly_pair(float a0, float a1, float& p0, float& p1) {
+    const f32x2 x = f2_pack(fmaxf(a0, -120.f), fmaxf(a1, -120.f));
+    const f32x2 t = f2_add(x, f2_pack(12582912.f, 12582912.f));
+    const f32x2 j = f2_add(t, f2_pack(-12582912.f, -12582912.f));
+    const f32x2 f = f2_fma(j, f2_pack(-1.f, -1.f), x);
+    f32x2 q = f2_fma(f2_pack(0.05517163872718811f, 0.05517163872718811f), f, f2_pack(0.2426111251115799f, 0.2426111251115799f));
+    q = f2_fma(q, f, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+    q = f2_fma(q, f, f2_pack(0.9999280571937561f, 0.9999280571937561f));
+    float t0, t1, q0, q1;
+    f2_unpack(t, t0, t1);
+    f2_unpack(q, q0, q1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3: two comparisons per issue slot
@@ -533,7 +551,7 @@ __device__ __forceinline__ void issue_qk_ts(uint32_t d_tmem, uint32_t q_tmem, ui
     if (HD > 64) ptx::mma_f16_ts(d_tmem, q_tmem + 32, desc_k32(b_tail), idesc, 1u);
 }
 
-template <int HD, int NST, bool PH>
+template <int HD, int NST, bool PH, bool POLY>
 __global__ void __launch_bounds__(352, 1)
 attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
                     const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
@@ -842,7 +860,9 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                     xa = fmax3(xa, a0, a1);                                                              \
                     xb = fmax3(xb, a2, a3);                                                              \
                     const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
-                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);                      \
+                    float p2, p3;                                                                        \
+                    if (POLY && ((e >> 2) & 1)) exp2_poly_pair(a2, a3, p2, p3);   /* a quarter of the exponentials */ \
+                    else { p2 = ptx::ex2_approx(a2); p3 = ptx::ex2_approx(a3); }                         \
                     l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
                     l23 = f2_add(l23, f2_pack(p2, p3));                                                  \
                     pk[e / 2] = pack_bf16x2(p0, p1);                                                     \
@@ -890,6 +910,7 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
 // the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
 // the reference maximum).  Two passes over TMEM: raw maximum (an upper bound of the row maximum follows from it), then
 // exp2 / sum / pack with packed fp32x2 arithmetic.
+template <bool POLY>
 __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
     float bmax = bhm[0], wmax = bwl[0];
 #pragma unroll
@@ -925,7 +946,9 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
                                           f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
             float a0, a1;                                                                            \
             f2_unpack(x, a0, a1);                                                                    \
-            const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                          \
+            float p0, p1;                                                                            \
+            if (POLY && ((e >> 1) & 3) == 3) exp2_poly_pair(a0, a1, p0, p1);   /* a quarter of the exponentials */ \
+            else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                             \
             l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
             pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
         }                                                                                            \
@@ -1115,7 +1138,7 @@ attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out,
 
         ptx::mbar_wait(&bars[C::B_SFULL], 0);
         ptx::tc_fence_after();
-        const float lsum = window_softmax_tile(s_tmem, bhm, bwl, scale_log2);
+        const float lsum = window_softmax_tile<false>(s_tmem, bhm, bwl, scale_log2);
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 1
         // ---- epilogue ----
@@ -1195,7 +1218,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                  : "memory");
 }
 
-template <int HD>
+template <int HD, bool POLY>
 __global__ void __launch_bounds__(384, 1)
 attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
                               long long* __restrict__ phase_clocks) {
@@ -1417,7 +1440,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ptx::mbar_wait(&bars[C::B_SFULL + i], ph);
             SVB_PHASE(2)
             ptx::tc_fence_after();
-            const float lsum = window_softmax_tile(s_tmem, bhm, bwl, scale_log2);
+            const float lsum = window_softmax_tile<POLY>(s_tmem, bhm, bwl, scale_log2);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&bars[C::B_PFULL + i]);
             SVB_PHASE(3)
@@ -1524,6 +1547,16 @@ __global__ void pack_rel_kernel(const float* __restrict__ src, bf16* __restrict_
         dst[(size_t)row_off * hd + i] = __float2bfloat16_rn(src[i]);
 }
 
+// A quarter of the softmax exponentials on the FMA pipe (exp2_poly_pair).  Measured: windowed kernel 118.5 -> 114.5 us per 8 images
+// (its two softmax groups are MUFU-bound while they overlap), global kernel 920 -> 947 us (issue / latency-bound: the extra
+// instructions cost more than the MUFU slots they free).  Defaults: on for the windowed kernel (SVB_ATTNW_POLY=0 turns it off),
+// off for the global kernel (SVB_ATTNG_POLY=1 turns it on).
+static bool exp2_poly(bool windowed) {
+    static const bool w = [] { const char* e = getenv("SVB_ATTNW_POLY"); return !(e && atoi(e) == 0); }();
+    static const bool g = [] { const char* e = getenv("SVB_ATTNG_POLY"); return e && atoi(e) != 0; }();
+    return windowed ? w : g;
+}
+
 template <int HD, int NST>
 int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
     using C = GCfg<HD, NST>;
@@ -1561,14 +1594,17 @@ int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
         static const int order = [] { const char* e = getenv("SVB_ATTNG_ORDER"); return e ? atoi(e) : 1; }();
         static bool attr2_set = false;
         if (!attr2_set) {
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
             attr2_set = true;
         }
         if (p.phase_clocks)
-            attn_global2_kernel<HD, NST, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, order);
+            attn_global2_kernel<HD, NST, true, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, order);
+        else if (exp2_poly(false))
+            attn_global2_kernel<HD, NST, false, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
         else
-            attn_global2_kernel<HD, NST, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
+            attn_global2_kernel<HD, NST, false, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
         SVB_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
@@ -1655,7 +1691,8 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
@@ -1664,7 +1701,8 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
-    attn_window_persistent_kernel<HD><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    if (exp2_poly(true)) attn_window_persistent_kernel<HD, true><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    else attn_window_persistent_kernel<HD, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
