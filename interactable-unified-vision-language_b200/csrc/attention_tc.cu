@@ -801,6 +801,8 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             ptx::tc_fence_after();
             ptx::tmem_ld_x32(s_h, va);
             ptx::tmem_ld_x32(s_h + 32, vb);
+            // (deferring this hand-over into the tile's arithmetic, where the stores have long drained, was measured SLOWER — 912 ->
+            // 1083 us per 8 images: the chain PV(h-1) -> QK(h+1) needs the whole tile of slack)
             if (h > 0) {
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
@@ -845,7 +847,7 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
             const f32x2 dd2 = f2_pack(bh - m_ref, bh - m_ref);
             // ---- P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
-#define SVB_PASS_H(V, CHUNK)                                                                             \
+#define SVB_PASS_H(V, CHUNK)                                                                  \
             {                                                                                            \
                 uint32_t pk[16];                                                                         \
                 _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
@@ -1188,7 +1190,7 @@ template <int HD> struct WPCfg {
     static constexpr int V_TX = 196 * ROWB;
     static constexpr int R_TX = 64 * ROWB;
     static constexpr int B_RFULL = 0, B_QKFULL = 1, B_VFULL = 3, B_EMPTY = 5, B_BIAS = 7, B_BREAD = 9, B_SFULL = 11, B_PFULL = 13,
-                         B_PVDONE = 15, B_OSTAGED = 17, B_COUNT = 19;
+                         B_PVDONE = 15, B_OSTAGED = 17, B_COUNT = 21;   // OSTAGED: one per (tile, stage)
     // V tile at head_dim 80: FIVE 16-column atoms of the 32B swizzle, V_ATOM bytes apart (an MN-major operand's leading-dimension
     // byte offset), so that P.V is ONE N = 80 MMA per K step (a tcgen05.mma with A in TMEM costs >= 44.5 cycles whatever N is:
     // the 64 + 16 pair cost 89).  At head_dim 64: one 64-column atom of the 128B swizzle.
@@ -1240,7 +1242,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         ptx::prefetch_tmap(&maps.o1);
         for (int s = 0; s < C::B_COUNT; ++s) {
             const bool by_threads = (s >= C::B_BREAD && s < C::B_BREAD + 2) || (s >= C::B_PFULL && s < C::B_PFULL + 2) ||
-                                    (s >= C::B_OSTAGED && s < C::B_OSTAGED + 2);
+                                    (s >= C::B_OSTAGED && s < C::B_OSTAGED + 4);
             const bool by_tiles = (s >= C::B_EMPTY && s < C::B_EMPTY + 2);            // one release per query tile
             ptx::mbar_init(&bars[s], by_threads ? 128 : (by_tiles ? 2 : 1));
         }
@@ -1361,8 +1363,10 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         // ===================== store warp: O tiles staged by the groups -> ONE tensor store per tile =====================
         // (the wait for the store to finish reading the stage sat on the critical path of the group's first warp)
         if (lane == 0) {
+            // one "staged" barrier per (tile, stage): a group may stage the NEXT item (other stage) before this warp has looked at
+            // the previous one, and a single barrier two phases ahead cannot be told from one that has not moved (parity wait)
             int it = 0;
-            uint32_t n[2] = {0, 0};
+            uint32_t n[4] = {0, 0, 0, 0};
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
                 const int st = it & 1;
                 int b, wy, wx, head;
@@ -1370,8 +1374,8 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                 for (int i = 0; i < 2; ++i) {
                     if (i == 1 && wy * WS + 9 >= g) continue;      // released by the issuer
                     const uint8_t* ob = sm + st * C::STAGE + i * C::QT;
-                    ptx::mbar_wait(&bars[C::B_OSTAGED + i], n[i] & 1);
-                    ++n[i];
+                    ptx::mbar_wait(&bars[C::B_OSTAGED + 2 * i + st], n[2 * i + st] & 1);
+                    ++n[2 * i + st];
                     const int x0 = wx * WS, y0 = wy * WS + 9 * i;
                     tma_store_4d(i ? &maps.o1 : &maps.o0, ob, head * HD, x0, y0, b);   // rows / columns past 64 are clipped by the TMA
                     if (HD > 64) tma_store_4d(i ? &maps.o1t : &maps.o0t, ob + C::Q_MAIN, head * HD + 64, x0, y0, b);
@@ -1390,8 +1394,6 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
         const uint32_t s_tmem = tmem + lane_off + 208 * i;
         const uint32_t o_tmem = s_tmem + 112;
-        const CUtensorMap* omap = i ? &maps.o1 : &maps.o0;
-        const CUtensorMap* omapt = i ? &maps.o1t : &maps.o0t;
         long long pc[6] = {0, 0, 0, 0, 0, 0};
         long long tprev = phase_clocks ? clock64() : 0;
 #define SVB_PHASE(k) if (phase_clocks) { const long long tnow = clock64(); pc[k] += tnow - tprev; tprev = tnow; }
@@ -1489,7 +1491,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                             make_uint4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
                 }
                 ptx::fence_proxy_async_smem();                     // generic writes -> visible to the TMA (async proxy) read
-                ptx::mbar_arrive(&bars[C::B_OSTAGED + i]);         // the store warp issues the tensor store and releases the stage
+                ptx::mbar_arrive(&bars[C::B_OSTAGED + 2 * i + st]); // the store warp issues the tensor store and releases the stage
             }
             if (!early && nitem < num_items) read_bias((n + 1) & 1);
             SVB_PHASE(5)

@@ -379,3 +379,29 @@ def test_attention_tcgen05_is_deterministic(ws, heads, hd, B):
     for _ in range(12):
         again = _attention_tc(qkv, rel_h, rel_w, bias, B, g, ws, heads, hd)
         assert torch.equal(again, first)
+
+
+@pytest.mark.parametrize("ws,B,rel_std,reps", [(14, 12, 0.02, 300), (14, 16, 0.5, 150), (64, 12, 0.5, 60)])
+def test_attention_tcgen05_many_launches_are_bit_identical(ws, B, rel_std, reps):
+    """ViT-H geometry at the pass sizes of the batch schedule, many launches on the same inputs: a barrier-protocol race shows up as
+    a differing output or as a trapped barrier wait (the store warp of the windowed kernel once aliased two phases of one barrier:
+    1 launch in ~20 hung at 12 images)."""
+    lib = cabi.lib()
+    heads, hd, g = 16, 80, 64
+    D = heads * hd
+    gen = torch.Generator().manual_seed(3)
+    pack = (torch.randn(lib.svb_rel_pack_rows(ws, g), hd, generator=gen) * rel_std).bfloat16().to(DEV)
+    shape = (B * g * g, 3 * D) if ws == 64 else (B, 70, 70, 3 * D)
+    qkv = torch.randn(shape, generator=gen).bfloat16().to(DEV)
+    out = torch.empty(B * g * g, D, dtype=torch.bfloat16, device=DEV)
+    ref = None
+    for r in range(reps):
+        out.fill_(0)
+        cabi.check(lib.svb_attention_tc(qkv.data_ptr(), out.data_ptr(), pack.data_ptr(), B, g, ws, heads, hd, cabi.stream_ptr()), "attn")
+        if r % 10 == 0 or r == reps - 1:
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = out.clone()
+                assert torch.isfinite(ref.float()).all()
+            else:
+                assert torch.equal(ref, out), f"launch {r} differs"
