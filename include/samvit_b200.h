@@ -198,6 +198,31 @@ int64_t svb_launch_count(void);   /* kernels launched by this library since it w
 
 /* ---- test hook: one CTA, K/16 tcgen05.mma with caller-supplied smem-descriptor fields; dumps the 128 x N accumulator.
  * Pins the MN-major / 32B-swizzle descriptor encodings the attention kernel relies on (tests/test_gpu_probe.py). ---- */
+/* ---- scope row N1, convolutional part of the pixel decoder (`MSDeformAttnPixelDecoder.forward`,
+ * modeling/vision/encoder/transformer_encoder_deform.py:315-359).  "rows" = [sample][pixel][channel] (NHWC), the layout the GEMM
+ * reads and writes: a 1x1 convolution (`input_proj[i][0]` :209-214, `lateral_conv` :256-258, `mask_features` :238-245) is one
+ * svb_linear on rows, the 3x3 `output_conv` (:259-268) svb_im2col3x3_rows + svb_linear. ---- */
+/* (batch, channels, pixels) NCHW of src_dtype -> rows of dst_dtype; dst_sample_stride = elements between samples (0: dense), so that
+ * the levels of `src_flatten` (:71,79) can be written in place. */
+int svb_nchw_to_rows(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels,
+                     int64_t dst_sample_stride, svb_stream_t stream);
+/* fp32 rows -> fp32 NCHW (`.transpose(1, 2).view(bs, -1, h, w)` :335 and the module's NCHW outputs :359). */
+int svb_rows_to_nchw(const float* src, int64_t src_sample_stride, float* dst, int batch, int channels, int pixels, svb_stream_t stream);
+/* nn.GroupNorm(groups, channels) on fp32 rows (+ optional ReLU): `input_proj[i][1]` (:213), detectron2 `get_norm("GN", C)` =
+ * GroupNorm(32, C) of the lateral / output convs (:253-268).  stats_ws: batch * groups * 2 doubles of scratch. */
+int svb_groupnorm_rows(const float* x, int64_t x_sample_stride, const float* gamma, const float* beta, void* out, int out_dtype,
+                       int64_t out_sample_stride, int batch, int pixels, int channels, int groups, float eps, int relu,
+                       double* stats_ws, svb_stream_t stream);
+/* dst (batch, out_h, out_w, channels) += F.interpolate(src (batch, h, w, channels), size=(out_h, out_w), mode="bilinear",
+ * align_corners=False) (:348). */
+int svb_upsample_add_rows(const float* src, int64_t src_sample_stride, float* dst, int batch, int h, int w, int out_h, int out_w,
+                          int channels, svb_stream_t stream);
+/* im2col of a 3x3 / stride 1 / pad 1 convolution on fp32 rows: dst[b, y, x, (ky, kx, c)] (dst_dtype) — the A operand of `output_conv`. */
+int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, int batch, int h, int w, int channels, svb_stream_t stream);
+/* out = cast(a + b[i mod b_numel]): svb_add_cast with a `b` shared by every sample (the sine position embedding + level embedding,
+ * :73-75). */
+int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream);
+
 /* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
  * completion, [1] = cycles in the issue loop (device pointers). */
 int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);

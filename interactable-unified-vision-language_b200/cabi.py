@@ -64,6 +64,12 @@ SYMBOLS = {
     "svb_profile_start": (_i, []),
     "svb_profile_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "svb_launch_count": (C.c_int64, []),
+    "svb_nchw_to_rows": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i64, _vp]),
+    "svb_rows_to_nchw": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp]),
+    "svb_groupnorm_rows": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "svb_upsample_add_rows": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "svb_im2col3x3_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_add_cast_bcast": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp]),
     "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
     "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),
     "svb_groupnorm_apply_nchw": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),

@@ -187,8 +187,13 @@ def _layernorm(x, add, ln, out):
 def _add_cast(a, b, dtype):
     """cast(a [+ b]) of fp32 (rows, dim) streams to the GEMM operand dtype: ``with_pos_embed`` (:112-114) fused with the cast."""
     out = torch.empty(a.shape, dtype=dtype, device=a.device)
-    cabi.check(cabi.lib().svb_add_cast(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                                       cabi.DTYPE_BF16 if dtype == torch.bfloat16 else cabi.DTYPE_F32, a.numel(), cabi.stream_ptr()), "svb_add_cast")
+    odt = cabi.DTYPE_BF16 if dtype == torch.bfloat16 else cabi.DTYPE_F32
+    if b is not None and b.numel() != a.numel():          # one embedding for every sample of the batch
+        cabi.check(cabi.lib().svb_add_cast_bcast(a.data_ptr(), b.data_ptr(), b.numel(), out.data_ptr(), odt, a.numel(), cabi.stream_ptr()),
+                   "svb_add_cast_bcast")
+    else:
+        cabi.check(cabi.lib().svb_add_cast(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), odt, a.numel(),
+                                           cabi.stream_ptr()), "svb_add_cast")
     return out
 
 

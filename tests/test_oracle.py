@@ -190,3 +190,41 @@ def test_deform_encoder_module_keys_match_reference():
     with pytest.raises(RuntimeError):        # no CPU path
         with torch.no_grad():
             mod([torch.from_numpy(z[f"src{i}"]) for i in range(L)], [torch.from_numpy(z[f"pos{i}"]) for i in range(L)])
+
+
+def _pixel_decoder_case(case):
+    import os
+    import numpy as np
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"pixel_decoder_{case}.npz"))
+    C, MD, M, NL, F_ = (int(v) for v in z["meta"])
+    seed, N, side = (int(v) for v in z["feat_seed"])
+    gf = torch.Generator().manual_seed(seed)
+    feats = {f"res{2 + i}": torch.randn(N, c, side >> i, side >> i, generator=gf) for i, c in enumerate((128, 256, 512, 1024))}
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    return z, (C, MD, M, NL, F_), feats, sd
+
+
+@pytest.mark.parametrize("case", ["small", "wide"])
+def test_pixel_decoder_oracle_against_reference_goldens(case):
+    """oracle.pixel_decoder against outputs of the UNMODIFIED reference MSDeformAttnPixelDecoder
+    (tests/golden/make_golden_pixel_decoder.py; transformer_encoder_deform.py:315-359; the reference ran in fp32)."""
+    from oracle import pixel_decoder_oracle as po
+    import iuvl_b200 as ib
+    z, (C, MD, M, NL, F_), feats, sd = _pixel_decoder_case(case)
+    mask, multi = po.pixel_decoder({k: v.double() for k, v in sd.items()}, {k: v.double() for k, v in feats.items()}, M, NL)
+    assert ib.rel_l2(mask, torch.from_numpy(z["mask_features"])) < 2e-5
+    for i, m in enumerate(multi):
+        assert ib.rel_l2(m, torch.from_numpy(z[f"multi{i}"])) < 2e-5
+
+
+def test_pixel_decoder_module_keys_match_reference():
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    z, (C, MD, M, NL, F_), feats, sd = _pixel_decoder_case("small")
+    mod = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=M, transformer_dim_feedforward=F_, transformer_enc_layers=NL,
+                                   conv_dim=C, mask_dim=MD, norm="GN", transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    mod.load_state_dict(sd, strict=True)
+    assert {k: tuple(v.shape) for k, v in mod.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    with pytest.raises(RuntimeError):        # no CPU path
+        with torch.no_grad():
+            mod(feats)
