@@ -177,6 +177,27 @@ def measure_next_rows(torch, cabi, dev, pk):
     ms = e0.elapsed_time(e1) / 5
     out["msda_module"] = {"workload": "MSDeformAttn.forward, d_model 512, 4 images x 21504 queries, bf16", "ms_per_layer": ms,
                           "images_per_s_per_layer": N / ms * 1e3}
+    del mod, xq
+    # row N1, the whole pixel decoder on the four maps the encoder produces (transformer_encoder_deform.py:315-359; step1.yaml geometry)
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    dec = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024, transformer_enc_layers=6,
+                                   conv_dim=512, mask_dim=512, norm="GN").to(dev).eval()
+    with torch.no_grad():
+        for layer in dec.transformer.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.05)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+        feats = {f"res{2 + i}": torch.randn(N, c, 256 >> i, 256 >> i, device=dev).bfloat16() for i, c in enumerate((128, 256, 512, 1024))}
+        for _ in range(2):
+            dec(feats)
+        e0.record()
+        for _ in range(3):
+            dec(feats)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["pixel_decoder"] = {"workload": "MSDeformAttnPixelDecoder.forward, conv_dim 512, 6 encoder layers, 4 images (res2..res5 of 1024^2 inputs), bf16",
+                            "ms_per_forward": ms, "images_per_s": N / ms * 1e3}
+    del dec, feats
     B = 16
     imgs = [torch.randint(0, 256, (3, 1024, 1024), dtype=torch.uint8, device=dev) for _ in range(B)]
     dst = torch.empty(B * 4096, 768, dtype=torch.bfloat16, device=dev)

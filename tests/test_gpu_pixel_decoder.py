@@ -105,3 +105,37 @@ def test_pixel_decoder_against_reference_goldens(case, precision, tol):
         errs[f"multi{i}"] = ib.rel_l2(m, torch.from_numpy(z[f"multi{i}"]))
     print(case, precision, errs)
     assert max(errs.values()) < tol, errs
+
+
+def test_encoder_feeds_pixel_decoder():
+    """BASELINE config 5 in miniature: the ViT encoder's four maps go straight into the pixel decoder (bf16 hand-over, no `.float()`
+    up-cast of transformer_encoder_deform.py:320,345), against the two CPU oracles chained in fp64."""
+    from oracle import pixel_decoder_oracle as po
+    from oracle import sam_vit_oracle as orc
+    from iuvl_b200.encoder import build_encoder
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    cfg = ib.PRESETS["tiny80"]
+    sd = ib.make_state_dict(cfg, 99, rel_std=0.1)
+    x = ib.make_images(2, cfg, 5)
+    enc = build_encoder(cfg)
+    enc.load_state_dict(sd)
+    enc.to(DEV)
+    torch.manual_seed(11)
+    dec = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=4, transformer_dim_feedforward=128, transformer_enc_layers=2,
+                                   conv_dim=64, mask_dim=32, norm="GN")
+    with torch.no_grad():
+        for layer in dec.transformer.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.2)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.2)
+    dsd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    feats_ref = orc.encoder_forward_cfg(sd, x, cfg)
+    mask_ref, multi_ref = po.pixel_decoder({k: v.double() for k, v in dsd.items()}, {k: v.double() for k, v in feats_ref.items()}, 4, 2)
+    dec.to(DEV).eval()
+    for precision, tol in (("fp32", 2e-4), ("bf16", 3e-2)):
+        enc.precision = precision
+        enc.out_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        dec.precision = precision
+        with torch.no_grad():
+            mask, multi = dec(enc(x.to(DEV)))
+        errs = [ib.rel_l2(mask, mask_ref)] + [ib.rel_l2(a, b) for a, b in zip(multi, multi_ref)]
+        assert max(errs) < tol, (precision, errs)
