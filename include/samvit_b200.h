@@ -223,6 +223,17 @@ int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, int batch, in
  * :73-75). */
 int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream);
 
+/* ---- scope row N4, first slice: the mask branch of `XDecoder.forward_prediction_heads` (modeling/interface/xdecoder.py:429-470).
+ * `mask_embed` (MLP, :458) and the mask logits `einsum("bqc,bchw->bqhw")` (:459) are svb_linear calls. ---- */
+/* x (batch, queries, channels) fp32, in place: the class token (row queries-1) <- sum_j softmax_j(cos(x_cls, x_j)) x_j over the object
+ * tokens j < queries-1 (:440-446). */
+int svb_cls_token_recompute(float* x, int batch, int queries, int channels, svb_stream_t stream);
+/* F.interpolate(src (maps, h, w), size=(out_h, out_w), mode="bicubic", align_corners=False, antialias=True) (:463); tmp: maps * h * out_w
+ * floats of scratch. */
+int svb_resize_bicubic_aa(const float* src, float* tmp, float* dst, int maps, int h, int w, int out_h, int out_w, svb_stream_t stream);
+/* out (batch, heads, per_sample) bool = sigmoid(v (batch, per_sample)) < 0.5, repeated over the heads (:467). */
+int svb_mask_threshold_heads(const float* v, void* out_bool, int batch, int heads, int64_t per_sample, svb_stream_t stream);
+
 /* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
  * completion, [1] = cycles in the issue loop (device pointers). */
 int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);

@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsamvit_b200.so")
-SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu"]
+SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

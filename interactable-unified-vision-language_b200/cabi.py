@@ -70,6 +70,9 @@ SYMBOLS = {
     "svb_upsample_add_rows": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_im2col3x3_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_add_cast_bcast": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp]),
+    "svb_cls_token_recompute": (_i, [_vp, _i, _i, _i, _vp]),
+    "svb_resize_bicubic_aa": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_mask_threshold_heads": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
     "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),
     "svb_groupnorm_apply_nchw": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),

@@ -1,0 +1,106 @@
+"""Mask branch of the X-Decoder prediction heads (scope row N4, first slice), host-side mirror of
+``XDecoder.forward_prediction_heads`` (``/root/reference/modeling/interface/xdecoder.py:429-494``) for the inference path with
+``task_switch['mask']`` on: ``decoder_norm`` -> class-token recompute -> ``mask_embed`` MLP -> mask logits
+``einsum("bqc,bchw->bqhw")`` -> antialiased bicubic resize to the attention-mask size -> ``sigmoid < 0.5`` per head.
+Forward only, CUDA only, no fallback.  The class logits (``lang_encoder.compute_similarity``), boxes and captions belong to the text
+side of the decoder and are not part of this slice.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import cabi
+
+
+class _MLP(nn.Module):
+    """Parameter holder with the key layout of the reference's ``MLP`` (``interface/modules.py:188-201``: ``layers.N.weight/bias``)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+def _odt(t):
+    return cabi.DTYPE_BF16 if t == torch.bfloat16 else cabi.DTYPE_F32
+
+
+class MaskPredictionHead(nn.Module):
+    """``decoder_norm`` and ``mask_embed`` carry the names they have inside ``XDecoder`` (``xdecoder.py:109,133``), so the matching
+    entries of its ``state_dict`` load with ``strict=True``.  ``precision``: "bf16" (tcgen05 GEMMs) or "fp32" (validation mode)."""
+
+    def __init__(self, hidden_dim=512, mask_dim=512, num_queries=101, nheads=8):
+        super().__init__()
+        self.decoder_norm = nn.LayerNorm(hidden_dim)
+        self.mask_embed = _MLP(hidden_dim, hidden_dim, mask_dim, 3)
+        self.num_queries, self.num_heads = num_queries, nheads
+        self.precision = "bf16"
+        self._sig = None
+
+    def _prepare(self, device, wdtype):
+        ps = list(self.parameters())
+        sig = (str(device), wdtype) + tuple((p.data_ptr(), p._version) for p in ps)
+        if sig != self._sig:
+            f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()      # noqa: E731
+            self._ln = (f(self.decoder_norm.weight), f(self.decoder_norm.bias))
+            self._mlp = [(f(l.weight).to(wdtype).contiguous(), f(l.bias)) for l in self.mask_embed.layers]
+            self._sig = sig
+
+    @staticmethod
+    def _linear(mode, a, w, bias, out, act=0):
+        m, k = a.shape
+        cabi.check(cabi.lib().svb_linear(mode, a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), m, w.shape[0], k,
+                                         bias.data_ptr() if bias is not None else None, act, None, 0, 0, out.data_ptr(), _odt(out.dtype),
+                                         out.stride(0), None, 0, 0, 0, cabi.stream_ptr()), "svb_linear")
+        return out
+
+    def forward(self, output, mask_features, attn_mask_target_size):
+        """output (Q, B, C) — the decoder's query states as ``forward_prediction_heads`` receives them; mask_features (B, Cm, H, W) fp32 or
+        bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool}."""
+        if not output.is_cuda:
+            raise RuntimeError("MaskPredictionHead (B200) has no CPU path: the inputs must be CUDA tensors")
+        if torch.is_grad_enabled() and (output.requires_grad or mask_features.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("MaskPredictionHead (B200) implements the forward pass only: call it under torch.no_grad()")
+        Q, B, C = output.shape
+        if Q != self.num_queries:
+            raise ValueError("this slice implements the segmentation path: `output` must hold exactly num_queries rows (no caption tokens)")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        mode, adt = (cabi.MODE_BF16, torch.bfloat16) if self.precision == "bf16" else (cabi.MODE_FP32, torch.float32)
+        dev = output.device
+        lib, st = cabi.lib(), cabi.stream_ptr
+        Bm, Cm, H, W = mask_features.shape
+        oh, ow = int(attn_mask_target_size[0]), int(attn_mask_target_size[1])
+        with torch.cuda.device(dev):
+            self._prepare(dev, adt)
+            x = output.detach().to(torch.float32).transpose(0, 1).contiguous().view(B * Q, C)         # :431 (the transpose, a 200 KB copy)
+            y = torch.empty_like(x)
+            cabi.check(lib.svb_layernorm(x.data_ptr(), None, self._ln[0].data_ptr(), self._ln[1].data_ptr(), y.data_ptr(), cabi.DTYPE_F32,
+                                         B * Q, C, float(self.decoder_norm.eps), st()), "svb_layernorm")               # :430 decoder_norm
+            cabi.check(lib.svb_cls_token_recompute(y.data_ptr(), B, Q, C, st()), "svb_cls_token_recompute")            # :440-450
+            a = y
+            if adt != torch.float32:
+                a = torch.empty(B * Q, C, dtype=adt, device=dev)
+                cabi.check(lib.svb_add_cast(y.data_ptr(), None, a.data_ptr(), _odt(adt), y.numel(), st()), "svb_add_cast")
+            n = len(self._mlp)
+            for i, (w, b) in enumerate(self._mlp):                                                                    # :458 mask_embed
+                last = i == n - 1
+                a = self._linear(mode, a, w, b, torch.empty(B * Q, w.shape[0], dtype=adt, device=dev), act=0 if last else 2)
+            mf = mask_features.detach().contiguous()
+            if mf.dtype not in (torch.float32, torch.bfloat16):
+                mf = mf.float()
+            rows = torch.empty(B * H * W, Cm, dtype=adt, device=dev)
+            cabi.check(lib.svb_nchw_to_rows(mf.data_ptr(), _odt(mf.dtype), rows.data_ptr(), _odt(adt), B, Cm, H * W, 0, st()), "svb_nchw_to_rows")
+            masks = torch.empty(B, Q, H, W, dtype=torch.float32, device=dev)
+            for b in range(B):                                                                                        # :459 "bqc,bchw->bqhw"
+                self._linear(mode, a[b * Q:(b + 1) * Q], rows[b * H * W:(b + 1) * H * W], None, masks[b].view(Q, H * W))
+            tmp = torch.empty(B * Q * H * ow, dtype=torch.float32, device=dev)
+            small = torch.empty(B, Q * oh * ow, dtype=torch.float32, device=dev)
+            cabi.check(lib.svb_resize_bicubic_aa(masks.data_ptr(), tmp.data_ptr(), small.data_ptr(), B * Q, H, W, oh, ow, st()),
+                       "svb_resize_bicubic_aa")                                                                        # :463
+            attn = torch.empty(B * self.num_heads, Q, oh * ow, dtype=torch.bool, device=dev)
+            cabi.check(lib.svb_mask_threshold_heads(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q * oh * ow, st()),
+                       "svb_mask_threshold_heads")                                                                     # :467-470
+        return {"outputs_mask": masks, "attn_mask": attn, "attn_logits": small.view(B, Q, oh, ow)}

@@ -1,0 +1,68 @@
+"""CPU ORACLE for the mask branch of the X-Decoder prediction heads (scope row N4, first slice).  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/`` and tools that check the CUDA path may import this file; the product never does.
+
+``mask_branch`` restates ``XDecoder.forward_prediction_heads`` (``/root/reference/modeling/interface/xdecoder.py:429-470``) for the
+inference path with the mask task on, on a plain state_dict with the reference's keys (``decoder_norm.*``, ``mask_embed.layers.N.*``);
+``resize_bicubic_aa`` writes out what ``F.interpolate(mode="bicubic", align_corners=False, antialias=True)`` (:463) computes — the
+separable antialiased cubic-convolution filter (a = -0.5, support 2 * max(scale, 1), weights normalised per output pixel) — with
+explicit weight matrices.
+
+Parity pin: ``tests/golden/mask_head_*.npz`` = outputs of the UNMODIFIED reference method executed on CPU
+(``tests/golden/make_golden_mask_head.py``); ``tests/test_oracle.py`` checks this file against them and ``resize_bicubic_aa``
+against ``F.interpolate`` itself.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _cubic(x, a=-0.5):
+    x = x.abs()
+    return torch.where(x < 1, ((a + 2) * x - (a + 3)) * x * x + 1, torch.where(x < 2, (((x - 5) * x + 8) * x - 4) * a, torch.zeros_like(x)))
+
+
+def aa_weights(n_in, n_out, dtype=torch.float64):
+    """(n_out, n_in) matrix of the antialiased bicubic filter along one axis."""
+    scale = n_in / n_out
+    support = 2.0 * scale if scale >= 1 else 2.0
+    inv = 1.0 / scale if scale >= 1 else 1.0
+    wm = torch.zeros(n_out, n_in, dtype=dtype)
+    for i in range(n_out):
+        center = scale * (i + 0.5)
+        lo = max(int(center - support + 0.5), 0)
+        hi = min(int(center + support + 0.5), n_in)
+        j = torch.arange(lo, hi, dtype=dtype)
+        w = _cubic((j - center + 0.5) * inv)
+        wm[i, lo:hi] = w / w.sum()
+    return wm
+
+
+def resize_bicubic_aa(x, size):
+    """x (..., H, W) -> (..., size[0], size[1])."""
+    wh = aa_weights(x.shape[-2], size[0], x.dtype)
+    ww = aa_weights(x.shape[-1], size[1], x.dtype)
+    return torch.einsum("oh,...hw,pw->...op", wh, x, ww)
+
+
+def mask_branch(sd, output, mask_features, attn_mask_target_size, num_queries, num_heads):
+    """-> (outputs_mask (B, Q, H, W), attention logits (B, Q, h, w), attn_mask (B * heads, Q, h * w) bool)."""
+    c = output.shape[-1]
+    mu = output.mean(-1, keepdim=True)
+    var = ((output - mu) ** 2).mean(-1, keepdim=True)
+    dec = ((output - mu) / torch.sqrt(var + 1e-5) * sd["decoder_norm.weight"] + sd["decoder_norm.bias"]).transpose(0, 1)       # :430-431
+    nrm = dec / (dec.norm(dim=-1, keepdim=True) + 1e-7)                                                                          # :440
+    obj, cls = nrm[:, :num_queries - 1], nrm[:, num_queries - 1:num_queries]
+    sim = (cls @ obj.transpose(1, 2)).softmax(-1)[:, 0, :, None]                                                                 # :444
+    cls_token = (sim * dec[:, :num_queries - 1]).sum(dim=1, keepdim=True)                                                        # :445
+    dec = torch.cat((dec[:, :num_queries - 1], cls_token), dim=1)                                                                # :450
+    x = dec
+    n = len([k for k in sd if k.startswith("mask_embed.layers.") and k.endswith(".weight")])
+    for i in range(n):                                                                                                           # :458
+        x = x @ sd[f"mask_embed.layers.{i}.weight"].t() + sd[f"mask_embed.layers.{i}.bias"]
+        if i < n - 1:
+            x = torch.relu(x)
+    outputs_mask = torch.einsum("bqc,bchw->bqhw", x, mask_features)                                                              # :459
+    logits = resize_bicubic_aa(outputs_mask, attn_mask_target_size)                                                              # :463
+    attn = (logits.sigmoid().flatten(2).unsqueeze(1).repeat(1, num_heads, 1, 1).flatten(0, 1) < 0.5)                             # :467
+    return outputs_mask, logits, attn

@@ -1,0 +1,74 @@
+"""GPU parity of the mask branch of the X-Decoder prediction heads (scope row N4, first slice): the kernels of csrc/maskhead.cu
+against the torch ops they replace, and the MaskPredictionHead module against outputs of the UNMODIFIED reference method
+(tests/golden/mask_head_*.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import iuvl_b200 as ib
+from iuvl_b200 import cabi
+from tests.util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("shape,size", [((5, 32, 32), (8, 8)), ((3, 48, 40), (12, 10)), ((2, 24, 24), (12, 12)), ((2, 17, 23), (5, 9)),
+                                        ((2, 256, 256), (32, 32))])
+def test_resize_bicubic_aa(shape, size):
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(7)).to(DEV)
+    n, h, w = shape
+    tmp = torch.empty(n * h * size[1], device=DEV)
+    out = torch.empty(n, size[0], size[1], device=DEV)
+    cabi.check(cabi.lib().svb_resize_bicubic_aa(x.data_ptr(), tmp.data_ptr(), out.data_ptr(), n, h, w, size[0], size[1], cabi.stream_ptr()), "resize")
+    want = F.interpolate(x[None].double().cpu(), size=size, mode="bicubic", align_corners=False, antialias=True)[0]
+    assert ib.rel_l2(out, want) < 2e-6
+
+
+def test_cls_token_recompute_and_threshold():
+    g = torch.Generator().manual_seed(9)
+    B, Q, C, NH = 3, 101, 512, 8
+    x = torch.randn(B, Q, C, generator=g)
+    nrm = x / (x.norm(dim=-1, keepdim=True) + 1e-7)
+    sim = (nrm[:, Q - 1:Q] @ nrm[:, :Q - 1].transpose(1, 2)).softmax(-1)[:, 0, :, None]
+    want = torch.cat((x[:, :Q - 1], (sim * x[:, :Q - 1]).sum(dim=1, keepdim=True)), dim=1)          # xdecoder.py:440-450
+    xd = x.to(DEV).contiguous()
+    cabi.check(cabi.lib().svb_cls_token_recompute(xd.data_ptr(), B, Q, C, cabi.stream_ptr()), "cls")
+    assert ib.rel_l2(xd, want) < 1e-6
+    v = torch.randn(B, 77, generator=g).to(DEV)
+    out = torch.empty(B * NH, 77, dtype=torch.bool, device=DEV)
+    cabi.check(cabi.lib().svb_mask_threshold_heads(v.data_ptr(), out.data_ptr(), B, NH, 77, cabi.stream_ptr()), "threshold")
+    assert torch.equal(out, (v.sigmoid().unsqueeze(1).repeat(1, NH, 1).flatten(0, 1) < 0.5))
+
+
+@pytest.mark.parametrize("case", ["small", "odd", "half"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_mask_head_against_reference_goldens(case, precision, tol):
+    """MaskPredictionHead against the UNMODIFIED reference method (xdecoder.py:429-470): mask logits within 1e-4 (fp32 validation mode) /
+    1e-2 (bf16) relative L2; the boolean attention mask may differ only where the resized logit is within the arithmetic's error of 0."""
+    from iuvl_b200.mask_head import MaskPredictionHead
+    z = np.load(os.path.join(GOLDEN, f"mask_head_{case}.npz"))
+    C, MD, Q, NH, th, tw = (int(v) for v in z["meta"])
+    head = MaskPredictionHead(hidden_dim=C, mask_dim=MD, num_queries=Q, nheads=NH)
+    head.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    head.to(DEV).eval()
+    head.precision = precision
+    with torch.no_grad():
+        res = head(torch.from_numpy(z["output"]).to(DEV), torch.from_numpy(z["mask_features"]).to(DEV), (th, tw))
+    ref_mask = torch.from_numpy(z["outputs_mask"])
+    assert tuple(res["outputs_mask"].shape) == tuple(ref_mask.shape)
+    err = ib.rel_l2(res["outputs_mask"], ref_mask)
+    assert err < tol, (case, precision, err)
+    ref_attn = torch.from_numpy(z["attn_mask"])
+    assert res["attn_mask"].dtype == torch.bool and tuple(res["attn_mask"].shape) == tuple(ref_attn.shape)
+    differ = res["attn_mask"].cpu() != ref_attn
+    ref_logits = F.interpolate(ref_mask.double(), size=(th, tw), mode="bicubic", align_corners=False, antialias=True)
+    rep = ref_logits.flatten(2).unsqueeze(1).repeat(1, NH, 1, 1).flatten(0, 1)
+    scale = float(ref_logits.abs().mean())
+    frac = float(differ.float().mean())
+    assert frac < (1e-3 if precision == "fp32" else 2e-2), (case, precision, frac)
+    assert (not differ.any()) or float(rep[differ].abs().max()) < (1e-3 if precision == "fp32" else 0.1) * scale
+    assert ib.rel_l2(res["attn_logits"], ref_logits) < tol

@@ -228,3 +228,35 @@ def test_pixel_decoder_module_keys_match_reference():
     with pytest.raises(RuntimeError):        # no CPU path
         with torch.no_grad():
             mod(feats)
+
+
+@pytest.mark.parametrize("shape,size", [((3, 32, 32), (8, 8)), ((2, 48, 40), (12, 10)), ((1, 24, 24), (12, 12)), ((2, 17, 23), (5, 9))])
+def test_resize_bicubic_aa_oracle_is_f_interpolate(shape, size):
+    """The written-out antialiased bicubic filter against the op the reference calls (xdecoder.py:463)."""
+    import torch.nn.functional as F
+    from oracle import mask_head_oracle as mo
+    x = torch.randn(1, *shape, generator=torch.Generator().manual_seed(7), dtype=torch.float64)
+    want = F.interpolate(x, size=size, mode="bicubic", align_corners=False, antialias=True)
+    got = mo.resize_bicubic_aa(x, size)
+    assert float((got - want).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("case", ["small", "odd", "half"])
+def test_mask_head_oracle_against_reference_goldens(case):
+    """oracle.mask_branch against outputs of the UNMODIFIED reference method XDecoder.forward_prediction_heads
+    (tests/golden/make_golden_mask_head.py; xdecoder.py:429-470; the reference ran in fp32)."""
+    import os
+    import numpy as np
+    import iuvl_b200 as ib
+    from oracle import mask_head_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"mask_head_{case}.npz"))
+    C, MD, Q, NH, th, tw = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd.")}
+    masks, logits, attn = mo.mask_branch(sd, torch.from_numpy(z["output"]).double(), torch.from_numpy(z["mask_features"]).double(), (th, tw), Q, NH)
+    assert ib.rel_l2(masks, torch.from_numpy(z["outputs_mask"])) < 2e-6
+    ref_attn = torch.from_numpy(z["attn_mask"])
+    differ = attn != ref_attn
+    # a bool can only differ where the fp32 reference and the fp64 oracle straddle zero
+    rep = logits.flatten(2).unsqueeze(1).repeat(1, NH, 1, 1).flatten(0, 1)
+    assert float(differ.float().mean()) < 1e-3 and (not differ.any() or float(rep[differ].abs().max()) < 1e-4)
