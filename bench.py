@@ -198,6 +198,23 @@ def measure_next_rows(torch, cabi, dev, pk):
     out["pixel_decoder"] = {"workload": "MSDeformAttnPixelDecoder.forward, conv_dim 512, 6 encoder layers, 4 images (res2..res5 of 1024^2 inputs), bf16",
                             "ms_per_forward": ms, "images_per_s": N / ms * 1e3}
     del dec, feats
+    # row N4 (first slice): the mask branch of the prediction heads, one call as a decoder layer makes it (xdecoder.py:457-470)
+    from iuvl_b200.mask_head import MaskPredictionHead
+    head = MaskPredictionHead(512, 512, 101, 8).to(dev).eval()
+    with torch.no_grad():
+        q = torch.randn(101, N, 512, device=dev)
+        mf = torch.randn(N, 512, 256, 256, device=dev).bfloat16()
+        for _ in range(2):
+            head(q, mf, (64, 64))
+        e0.record()
+        for _ in range(5):
+            head(q, mf, (64, 64))
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["mask_head"] = {"workload": "mask branch of forward_prediction_heads, 101 queries x 512, mask_features 512 x 256^2, 4 images, 64^2 attention mask, bf16",
+                        "ms_per_call": ms}
+    del head, mf
     B = 16
     imgs = [torch.randint(0, 256, (3, 1024, 1024), dtype=torch.uint8, device=dev) for _ in range(B)]
     dst = torch.empty(B * 4096, 768, dtype=torch.bfloat16, device=dev)

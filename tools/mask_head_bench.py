@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Timing of the mask branch of the prediction heads at the step1.yaml geometry: 101 queries, hidden = mask_dim = 512, 8 heads,
+mask_features 512 x 256^2 per image, attention-mask sizes 32^2 / 64^2 / 128^2 (one call per decoder layer, xdecoder.py:296-329)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from iuvl_b200.mask_head import MaskPredictionHead  # noqa: E402
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = "cuda"
+head = MaskPredictionHead(512, 512, 101, 8).to(dev).eval()
+with torch.no_grad():
+    out = torch.randn(101, N, 512, device=dev)
+    mf = torch.randn(N, 512, 256, 256, device=dev).bfloat16()
+    for tgt in ((32, 32), (64, 64), (128, 128)):
+        for _ in range(2):
+            res = head(out, mf, tgt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            res = head(out, mf, tgt)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        fl = 2.0 * N * 101 * 512 * 65536
+        print(f"target {tgt}: {ms:7.3f} ms per call for {N} images; mask-logit GEMMs {fl / 1e9:.0f} GFLOP; outputs_mask {tuple(res['outputs_mask'].shape)}")
