@@ -919,6 +919,398 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     }
 }
 
+// ================================================================================================================
+//          GLOBAL ATTENTION, half-tile pipeline with FOUR softmax warps per scheduler (column-split rows)
+// ================================================================================================================
+template <int HD, int NST_> struct G3Cfg : G2Cfg<HD, NST_> {
+    using B = G2Cfg<HD, NST_>;
+    static constexpr int OFF_XO = B::OFF_BAR + 256;              // exchange area: 4 x 2 x 128 x 2 + 2 x 128 x 2 floats
+    static constexpr int XO_BYTES = (4 * 2 * 128 * 2 + 2 * 128 * 2) * 4;
+    static constexpr int SMEM = OFF_XO + XO_BYTES + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int HD, int NST, bool PH>
+__global__ void __launch_bounds__(608, 1)
+attn_global3_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
+                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
+                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
+                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int D, int T, float scale_log2,
+                    long long* __restrict__ phase_clocks, int order) {
+    using C = G3Cfg<HD, NST>;
+    constexpr int NKT = 32;                                     // 128-key TMA tiles
+    constexpr int NH = 64;                                      // 64-key half tiles = key rows of the image
+    constexpr int HALF_MAIN = 64 * 128, HALF_TAIL = 64 * 32;    // byte offset of keys 64.. inside a K / V tile
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * T + pair * 256;
+    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
+
+    if (warp == 16 && lane == 0) {
+        ptx::prefetch_tmap(&tm_main);
+        ptx::prefetch_tmap(&tm_rw_main);
+        ptx::prefetch_tmap(&tm_rh_main);
+        if (HD > 64) { ptx::prefetch_tmap(&tm_tail); ptx::prefetch_tmap(&tm_rw_tail); ptx::prefetch_tmap(&tm_rh_tail); }
+        ptx::mbar_init(&bars[C::B_QFULL], 1);
+        for (int s = 0; s < NST; ++s) {
+            ptx::mbar_init(&bars[C::B_KFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_KEMPTY + s], 2);             // one release per issuer (query tile)
+            ptx::mbar_init(&bars[C::B_VFULL + s], 1);
+            ptx::mbar_init(&bars[C::B_VEMPTY + s], 2);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&bars[C::B_BIAS + i], 1);
+            ptx::mbar_init(&bars[C::B_BREAD + i], 256);            // both column halves of the 128 rows
+            ptx::mbar_init(&bars[C::B_PVDONE + i], 1);
+            ptx::mbar_init(&bars[C::B_ODONE + i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            ptx::mbar_init(&bars[C::B_SFULL + i], 1);
+            ptx::mbar_init(&bars[C::B_PFULL + i], 256);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 17) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // ===================== TMA producer (as in attn_global_kernel) =====================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::Q_TX);
+            for (int i = 0; i < 2; ++i) {
+                ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE, &tm_main, &bars[C::B_QFULL], colq, row0 + 128 * i);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_QFULL], colq + 64, row0 + 128 * i);
+            }
+            ptx::tma_load_2d(sm + C::OFF_RW, &tm_rw_main, &bars[C::B_QFULL], 0, 144);
+            ptx::tma_load_2d(sm + C::OFF_RH, &tm_rh_main, &bars[C::B_QFULL], 0, 4 * pair);
+            if (HD > 64) {
+                ptx::tma_load_2d(sm + C::OFF_RW + C::T_MAIN, &tm_rw_tail, &bars[C::B_QFULL], 64, 144);
+                ptx::tma_load_2d(sm + C::OFF_RH + C::RH_MAIN, &tm_rh_tail, &bars[C::B_QFULL], 64, 4 * pair);
+            }
+            for (int j = 0; j < NKT; ++j) {
+                const int st = j % NST;
+                const uint32_t par = ((j / NST) & 1) ^ 1;
+                const int krow = b * T + j * 128;
+                ptx::mbar_wait(&bars[C::B_KEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_KFULL + st], C::KV_TX);
+                ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
+                ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
+                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
+                ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
+                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE + C::T_MAIN, &tm_main, &bars[C::B_VFULL + st], colv + 64, krow);
+            }
+        }
+    } else if (warp == 17 || warp == 18) {
+        // ===================== MMA issuers: one per query tile =====================
+        // (a single issuing thread needs ~40 cycles of scalar work per tcgen05.mma + commit: 52 MMAs + 10 commits per 128 keys
+        // made ONE issuer the bottleneck of this pipeline, 2690 cycles per 128 keys; the two tiles' chains are independent)
+        if (lane == 0) {
+            const int i = warp - 17;
+            constexpr uint32_t id_w = ptx::make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 64, 0, 0);
+            constexpr uint32_t id_rh = ptx::make_idesc_bf16(128, 80, 0, 0);
+            const uint32_t q_main = base + C::OFF_Q + i * C::TILE, q_tail = q_main + C::T_MAIN;
+            const uint32_t q_tm = tmem + C::TM_Q + C::Q_STRIDE * i;
+            const uint32_t o_tm = tmem + C::TM_O + C::O_STRIDE * i;
+            ptx::mbar_wait(&bars[C::B_QFULL], 0);
+            ptx::tc_fence_after();
+            // decomposed rel-pos products: Q.Rw^T -> both S buffers of the tile (128 columns), Q.Rh[4*pair ..]^T -> O_i columns
+            issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main, q_tail, base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_w);
+            issue_qk<HD>(o_tm, q_main, q_tail, base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
+            ptx::mma_commit(&bars[C::B_BIAS + i]);
+            // S_i(0), S_i(1): the two halves of key tile 0
+            ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
+            ptx::mbar_wait(&bars[C::B_BREAD + i], 0);              // bias products consumed (S_i / O_i columns are free), Q_i is in TMEM
+            ptx::tc_fence_after();
+            for (int hb = 0; hb < 2; ++hb) {
+                issue_qk_ts<HD>(tmem + C::TM_S + 64 * (2 * i + hb), q_tm, base + C::OFF_K + hb * HALF_MAIN,
+                                base + C::OFF_K + C::T_MAIN + hb * HALF_TAIL, id_s);
+                ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
+            }
+            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
+            long long ipc[3] = {0, 0, 0};
+            long long itp = PH ? clock64() : 0;
+#define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
+            for (int h = 0; h < NH; ++h) {
+                const int hb = h & 1, jt = h >> 1, st = jt % NST;
+                const bool more = (h + 2 < NH);
+                const int jt2 = (h + 2) >> 1, st2 = jt2 % NST;
+                SVB_IPH(2)
+                if (hb == 0) {
+                    ptx::mbar_wait(&bars[C::B_VFULL + st], (jt / NST) & 1);
+                    if (more) ptx::mbar_wait(&bars[C::B_KFULL + st2], (jt2 / NST) & 1);
+                }
+                SVB_IPH(0)
+                const uint32_t s_i = tmem + C::TM_S + 64 * (2 * i + hb);
+                ptx::mbar_wait(&bars[C::B_PFULL + 2 * i + hb], jt & 1);      // P_i(h) is in TMEM
+                SVB_IPH(1)
+                ptx::tc_fence_after();
+                issue_pv_wide<HD>(o_tm, s_i, base + C::OFF_V + st * C::VTILE + hb * HALF_MAIN, C::T_MAIN, 4, h > 0);
+                ptx::mma_commit(&bars[C::B_PVDONE + i]);
+                if (h == NH - 1) ptx::mma_commit(&bars[C::B_ODONE + i]);     // O_i is complete
+                if (hb == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
+                if (more) {
+                    // in-order execution of this thread's MMAs: the overwrite of S_i^hb / P_i^hb follows the PV above
+                    issue_qk_ts<HD>(s_i, q_tm, base + C::OFF_K + st2 * C::TILE + hb * HALF_MAIN,
+                                    base + C::OFF_K + st2 * C::TILE + C::T_MAIN + hb * HALF_TAIL, id_s);
+                    ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
+                    if (hb == 1) ptx::mma_commit(&bars[C::B_KEMPTY + st2]);
+                }
+            }
+#undef SVB_IPH
+            if (PH && phase_clocks && i == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
+                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
+            }
+        }
+    } else {
+        // ===================== softmax warps: 2 query tiles x 2 column halves x 4 lane quadrants =====================
+        // Warps w and w + 8 own the SAME 32 query rows (TMEM lanes) and split every 64-key half tile: `half` 0 takes key columns
+        // 0..31, `half` 1 columns 32..63 — four softmax warps per scheduler instead of two (one warp alone is latency-bound: ~1200
+        // cycles for the 64 exponentials of a row's half tile).  What a row's two threads must agree on is the reference maximum:
+        // each publishes the absolute maximum exponent of its columns per half tile (xo, 4 slots), and the lazy rescale at tile
+        // h uses the values of tile h-2, which are visible through the barrier chain P(h-2) -> QK(h) -> S(h) without any extra
+        // synchronisation; the first tile's bound and the final row sum go through one named barrier per warp pair.
+        const int half = warp >> 3;
+        const int i = (warp >> 2) & 1;                             // query tile
+        const int w4 = warp & 3;                                   // TMEM lane quadrant (= warp id % 4)
+        const int t = w4 * 32 + lane;                              // query row inside the tile
+        const int qr = 2 * i + (t >> 6);                           // grid row of the query inside the CTA (0..3), warp-uniform
+        const int qw = t & 63;                                     // grid column of the query
+        const int kw0 = 32 * half;                                 // first key column of this thread
+        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + C::TM_S + 128 * i;
+        const uint32_t o_tmem = tmem + lane_off + C::TM_O + C::O_STRIDE * i;
+        float* stg = reinterpret_cast<float*>(sm + C::OFF_STG + (warp & 7) * 8192);   // [64][32] fp32, shared by the warp pair
+        float* xo = reinterpret_cast<float*>(sm + C::OFF_XO);     // [4 slots][2 tiles][128 rows][2 halves]
+        float* lx = xo + 4 * 2 * 128 * 2;                          // [2 tiles][128 rows][2 halves]: first-tile bound, then the row sums
+        const int xi = (i * 128 + t) * 2;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 7)) : "memory"); };
+
+        // ---- this row's query -> TMEM (bf16 pairs, the layout P has): the A operand of every QK product ----
+        if (half == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + 128 * i + t) * (3 * D) + colq);
+            const uint32_t q_tmem = tmem + lane_off + C::TM_Q + C::Q_STRIDE * i;
+            uint32_t qa[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = __ldg(src + c);
+                qa[4 * c] = u.x; qa[4 * c + 1] = u.y; qa[4 * c + 2] = u.z; qa[4 * c + 3] = u.w;
+            }
+            ptx::tmem_st_x32(q_tmem, qa);
+            if (HD > 64) {
+                uint32_t qb[8];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint4 u = __ldg(src + 8 + c);
+                    qb[4 * c] = u.x; qb[4 * c + 1] = u.y; qb[4 * c + 2] = u.z; qb[4 * c + 3] = u.w;
+                }
+                ptx::tmem_st_x8(q_tmem + 32, qb);
+            }
+            ptx::tmem_st_wait();
+        }
+        // ---- rel-pos prologue: w term of this thread's 32 key columns into registers (the two halves take turns with the pair's
+        // staging block), h term into the staging block (written by half 0, read by both) ----
+        float bwl[32];
+        ptx::mbar_wait(&bars[C::B_BIAS + i], 0);
+        ptx::mbar_wait(&bars[C::B_BIAS + (i ^ 1)], 0);             // the staging area below aliases the tables BOTH tiles' bias MMAs read
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int turn = 0; turn < 2; ++turn) {
+            if (turn == half) {
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_x32(s_tmem + 64 * p + 32 * hh, v);
+                        ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) stg[(32 * hh + e) * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int kk = 0; kk < 32; ++kk) {
+                        const int c = qw + 63 - (kw0 + kk);            // table row qw - kw + 63
+                        if ((c >> 6) == p) bwl[kk] = stg[(c & 63) * 32 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            pair_sync();
+        }
+        float bwmax = bwl[0];
+#pragma unroll
+        for (int kk = 1; kk < 32; ++kk) bwmax = fmaxf(bwmax, bwl[kk]);
+        if (half == 0) {
+            // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
+            uint32_t v[32];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                ptx::tmem_ld_x32(o_tmem + c0, v);
+                ptx::tmem_ld_wait_dep(v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int kh = qr + 63 - (c0 + e);
+                    if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
+                }
+            }
+            uint32_t w[16];
+            ptx::tmem_ld_x16(o_tmem + 64, w);
+            ptx::tmem_ld_wait_dep(w);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int kh = qr + 63 - (64 + e);
+                if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(w[e]) * LOG2E;
+            }
+        }
+        pair_sync();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_BREAD + i]);                   // S_i / O_i columns may be overwritten
+
+        float m_ref = -INFINITY;
+        f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // partial row sum over this thread's columns
+        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+        long long pc[5] = {0, 0, 0, 0, 0};
+        long long tprev = PH ? clock64() : 0;
+#define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+            const int hb = h & 1;
+            const uint32_t s_h = s_tmem + 64 * hb;
+            uint32_t va[32];
+            ptx::mbar_wait(&bars[C::B_SFULL + 2 * i + hb], (h >> 1) & 1);
+            SVB_GPH(0)
+            ptx::tc_fence_after();
+            ptx::tmem_ld_x32(s_h + kw0, va);
+            if (h > 0) {
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + (hb ^ 1)]);
+            }
+            SVB_GPH(3)
+            const float bh = stg[h * 32 + lane];
+            float m_new = m_ref;
+            bool need = false;
+            if (h >= 2) {
+                // absolute maximum exponent of tile h-2 over BOTH column halves (written before P(h-2) was handed over)
+                const float2 mm = *reinterpret_cast<const float2*>(xo + ((h - 2) & 3) * 512 + xi);
+                const float mx = fmaxf(mm.x, mm.y);
+                need = mx - m_ref > RESCALE_THRESHOLD;
+                m_new = need ? mx : m_ref;
+            }
+            ptx::tmem_ld_wait_dep(va);
+            // P(h) overlays S columns 0..31 — the OTHER half's keys for half 1: nobody stores P before both have loaded their S
+            if (h > 0) pair_sync();
+            SVB_GPH(4)
+            if (h == 0) {
+                // the first tile's reference: an upper bound of the row maximum over both halves, exchanged through the pair barrier
+                lx[xi + half] = fmaf(max32(va, -INFINITY), scale_log2, bh) + bwmax;
+                pair_sync();
+                const float2 bb = *reinterpret_cast<const float2*>(lx + xi);
+                m_ref = fmaxf(bb.x, bb.y);
+            } else if (__any_sync(0xffffffffu, need)) {
+                const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
+                ptx::mbar_wait(&bars[C::B_PVDONE + i], (h - 1) & 1);   // O_i holds tiles 0..h-1
+                ptx::tc_fence_after();
+                uint32_t r[8];
+#pragma unroll
+                for (int c0 = 0; c0 < HD / 2; c0 += 8) {               // this thread's half of the O columns
+                    ptx::tmem_ld_x8(o_tmem + half * (HD / 2) + c0, r);
+                    ptx::tmem_ld_wait_dep(r);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+                    ptx::tmem_st_x8(o_tmem + half * (HD / 2) + c0, r);
+                }
+                const f32x2 al2 = f2_pack(alpha, alpha);
+                l01 = f2_mul(l01, al2);
+                l23 = f2_mul(l23, al2);
+                m_ref = m_new;
+                SVB_GPH(2)
+            }
+            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
+            const f32x2 dd2 = f2_pack(bh - m_ref, bh - m_ref);
+            // ---- P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
+            {
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), sc2, f2_pack(bwl[e], bwl[e + 1])), dd2);
+                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), sc2, f2_pack(bwl[e + 2], bwl[e + 3])), dd2);
+                    float a0, a1, a2, a3;
+                    f2_unpack(x01, a0, a1);
+                    f2_unpack(x23, a2, a3);
+                    xa = fmax3(xa, a0, a1);
+                    xb = fmax3(xb, a2, a3);
+                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
+                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);
+                    l01 = f2_add(l01, f2_pack(p0, p1));
+                    l23 = f2_add(l23, f2_pack(p2, p3));
+                    pk[e / 2] = pack_bf16x2(p0, p1);
+                    pk[e / 2 + 1] = pack_bf16x2(p2, p3);
+                }
+                ptx::tmem_st_x16(s_h + 16 * half, pk);             // keys kw0 .. kw0+31 = P columns 16*half .. +15
+            }
+            xo[(h & 3) * 512 + xi + half] = m_ref + fmaxf(xa, xb);   // published before P(h) is handed over (next iteration)
+            SVB_GPH(1)
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + 1]);             // P(NH-1)
+        SVB_GPH(3)
+#undef SVB_GPH
+        if (PH && phase_clocks && w4 == 0 && lane == 0 && half == 0) {
+            for (int k = 0; k < 3; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)(NH / 2));
+            if (i == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 7, (unsigned long long)pc[3]); atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 15, (unsigned long long)pc[4]); }
+        }
+        // ---- row sum over both halves, then each thread stores its half of the O columns at the query's own token position ----
+        {
+            float l0, l1, l2, l3;
+            f2_unpack(l01, l0, l1);
+            f2_unpack(l23, l2, l3);
+            pair_sync();                                             // the first-tile bounds in lx have been read by both
+            lx[xi + half] = (l0 + l1) + (l2 + l3);
+            pair_sync();
+            const float2 ll = *reinterpret_cast<const float2*>(lx + xi);
+            const float inv = 1.0f / (ll.x + ll.y);
+            ptx::mbar_wait(&bars[C::B_ODONE + i], 0);
+            ptx::tc_fence_after();
+            bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD + half * (HD / 2);
+#pragma unroll
+            for (int c0 = 0; c0 < HD / 2; c0 += 8) {
+                uint32_t r[8];
+                ptx::tmem_ld_x8(o_tmem + half * (HD / 2) + c0, r);
+                ptx::tmem_ld_wait_dep(r);
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+                u.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+                u.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+                u.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+                *reinterpret_cast<uint4*>(dst + c0) = u;
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 17) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, C::TM_COLS);
+    }
+}
+
 // One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
 // the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
 // the reference maximum).  Two passes over TMEM: raw maximum (an upper bound of the row maximum follows from it), then
@@ -1603,6 +1995,21 @@ int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
     dim3 grid(T / 256, p.heads, p.batch);
     // SVB_ATTNG_IMPL=1 selects the 128-key-tile kernel (A/B comparisons); default: the half-tile pipeline
     static const int impl = [] { const char* e = getenv("SVB_ATTNG_IMPL"); return e ? atoi(e) : 2; }();
+    if (impl == 3) {
+        using C3 = G3Cfg<HD, NST>;
+        static bool attr3_set = false;
+        if (!attr3_set) {
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global3_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM));
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global3_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM));
+            attr3_set = true;
+        }
+        if (p.phase_clocks)
+            attn_global3_kernel<HD, NST, true><<<grid, 608, C3::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, 0);
+        else
+            attn_global3_kernel<HD, NST, false><<<grid, 608, C3::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 0);
+        SVB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (impl == 2) {
         static const int order = [] { const char* e = getenv("SVB_ATTNG_ORDER"); return e ? atoi(e) : 1; }();
         static bool attr2_set = false;
