@@ -785,7 +785,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
         float x_over = 0.f;                                          // previous tile's maximum exponent relative to m_ref
         f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
         const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
-        if (order == 2 && i == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
         long long pc[5] = {0, 0, 0, 0, 0};
         long long tprev = PH ? clock64() : 0;
 #define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
@@ -816,12 +815,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             ptx::tmem_ld_wait_dep(va);
             ptx::tmem_ld_wait_dep(vb);
             SVB_GPH(4)
-            // ping-pong (order == 2, A/B): the two groups take turns in the arithmetic below, so that one group's hand-over / wait /
-            // load phases run while the other one has the MUFU to itself (named barriers 1 and 2, 128 + 128 threads)
-            if (order == 2) {
-                if (i == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-                else asm volatile("bar.sync 2, 256;" ::: "memory");
-            }
             if (h == 0) {
                 const float sm0 = max32(vb, max32(va, -INFINITY));
                 m_new = fmaf(sm0, scale_log2, bh) + bwmax;         // upper bound of the row maximum in log2 units (scale > 0)
@@ -883,10 +876,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             SVB_PASS_H(vb, 1)
 #undef SVB_PASS_H
             x_over = fmaxf(xa, xb);
-            if (order == 2 && !(i == 1 && h == NH - 1)) {
-                if (i == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-                else asm volatile("bar.arrive 1, 256;" ::: "memory");
-            }
             SVB_GPH(1)
         }
         ptx::tmem_st_wait();
