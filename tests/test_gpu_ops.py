@@ -405,3 +405,18 @@ def test_attention_tcgen05_many_launches_are_bit_identical(ws, B, rel_std, reps)
                 assert torch.isfinite(ref.float()).all()
             else:
                 assert torch.equal(ref, out), f"launch {r} differs"
+
+
+@pytest.mark.parametrize("env", [{"SVB_ATTNG_IMPL": "1"}, {"SVB_ATTNG_IMPL": "3"}, {"SVB_ATTNW_IMPL": "1"}, {"SVB_ATTNW_POLY": "0", "SVB_ATTNG_POLY": "1"}])
+def test_attention_ab_variants_stay_correct(env):
+    """The measured-and-kept A/B variants of the attention kernels (selected by environment variables that are read once per process)
+    pass the same parity tests as the defaults: 128-key-tile global kernel, four-softmax-warps-per-scheduler global kernel,
+    one-tile-per-CTA windowed kernel, exponentials all on the MUFU / a quarter on the FMA pipe."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-q", "-x", "-k", "test_attention_tcgen05 and not variants and not many_launches"],
+                       cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (env, r.stdout[-1500:], r.stderr[-500:])
