@@ -505,6 +505,8 @@ template <typename T>
 static bool launch_ln_fixed(float* x, const T* add, const float* w, const float* b, T* out, int rows, int D, float eps, cudaStream_t s) {
     const int blocks = (rows + 3) / 4;
     switch (D) {
+        case 256: layernorm_fixed_kernel<T, 2><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;     // deformable encoder widths
+        case 512: layernorm_fixed_kernel<T, 4><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
         case 768: layernorm_fixed_kernel<T, 6><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
         case 1024: layernorm_fixed_kernel<T, 8><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;
         case 1280: layernorm_fixed_kernel<T, 10><<<blocks, 128, 0, s>>>(x, add, w, b, out, rows, eps); return true;

@@ -15,6 +15,15 @@ inline int grid_cap(size_t n, int block) {
     return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+__device__ __forceinline__ void store8(float* p, float4 a, float4 b) { reinterpret_cast<float4*>(p)[0] = a; reinterpret_cast<float4*>(p)[1] = b; }
+__device__ __forceinline__ void store8(bf16* p, float4 a, float4 b) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+
 // ---- NCHW -> rows: 32 x 32 tiles through shared memory (coalesced on both sides); casts to the GEMM operand type ----
 template <typename TI, typename TO>
 __global__ void nchw_to_rows_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C, int HW, long long dst_sample_stride) {
@@ -77,32 +86,32 @@ __global__ void gn_rows_stats_kernel(const float* __restrict__ x, long long samp
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * groups + i], sacc[i]);
 }
-// pass 2: y = (x - mean_g) * rstd_g * gamma_c + beta_c [ReLU]
+// pass 2: y = (x - mean_g) * rstd_g * gamma_c + beta_c [ReLU]; mean / rstd of the sample's groups once per block (shared memory)
 template <typename TO>
 __global__ void gn_rows_apply_kernel(const float* __restrict__ x, long long x_sample_stride, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, TO* __restrict__ out, long long out_sample_stride, int HW, int C,
                                      int groups, float eps, int relu, const double* __restrict__ stats) {
+    extern __shared__ float2 mr[];                         // [groups] (mean, rstd)
     const int b = blockIdx.y, cg = C / groups;
     const double n = (double)HW * cg;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        const double mu = stats[(size_t)b * 2 * groups + 2 * g] / n;
+        const double var = stats[(size_t)b * 2 * groups + 2 * g + 1] / n - mu * mu;
+        mr[g] = make_float2((float)mu, (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps)));
+    }
+    __syncthreads();
     const size_t n4 = (size_t)HW * C / 4;
     const float* xb = x + (size_t)b * x_sample_stride;
     TO* ob = out + (size_t)b * out_sample_stride;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const int c4 = (int)((i * 4) % C);
         const float4 v = __ldg(reinterpret_cast<const float4*>(xb) + i);
-        const float in[4] = {v.x, v.y, v.z, v.w};
-        float y[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c4 + j, g = c / cg;
-            const double mu = stats[(size_t)b * 2 * groups + 2 * g] / n;
-            const double var = stats[(size_t)b * 2 * groups + 2 * g + 1] / n - mu * mu;
-            const float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
-            float t = (in[j] - (float)mu) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-            y[j] = relu ? fmaxf(t, 0.f) : t;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ob[i * 4 + j] = from_float<TO>(y[j]);
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c4)), bt = __ldg(reinterpret_cast<const float4*>(beta + c4));
+        const float2 m0 = mr[c4 / cg], m1 = mr[(c4 + 1) / cg], m2 = mr[(c4 + 2) / cg], m3 = mr[(c4 + 3) / cg];
+        float y0 = (v.x - m0.x) * m0.y * gm.x + bt.x, y1 = (v.y - m1.x) * m1.y * gm.y + bt.y;
+        float y2 = (v.z - m2.x) * m2.y * gm.z + bt.z, y3 = (v.w - m3.x) * m3.y * gm.w + bt.w;
+        if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+        store4(ob + i * 4, y0, y1, y2, y3);
     }
 }
 
@@ -140,21 +149,25 @@ __global__ void upsample_add_rows_kernel(const float* __restrict__ src, long lon
 // ---- im2col of a 3x3 / stride 1 / zero-pad 1 convolution on rows: dst[b, y, x, (ky, kx, c)] = src[b, y+ky-1, x+kx-1, c] ----
 template <typename TO>
 __global__ void im2col3x3_rows_kernel(const float* __restrict__ src, TO* __restrict__ dst, int H, int W, int C) {
-    const int b = blockIdx.y, c4n = C / 4;
-    const size_t total = (size_t)H * W * 9 * c4n;
+    const int b = blockIdx.y, c8n = C / 8;                 // 8 channels per thread: 16-byte stores of the bf16 operand
+    const size_t total = (size_t)H * W * 9 * c8n;
     const float* sb = src + (size_t)b * H * W * C;
     TO* db = dst + (size_t)b * H * W * 9 * C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % c4n);
-        const size_t t = i / c4n;
+        const int c8 = (int)(i % c8n);
+        const size_t t = i / c8n;
         const int tap = (int)(t % 9);
         const size_t p = t / 9;
         const int x = (int)(p % W), y = (int)(p / W);
         const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)sy * W + sx) * C) + c4);
-        TO* o = db + (p * 9 + tap) * C + c4 * 4;
-        o[0] = from_float<TO>(v.x); o[1] = from_float<TO>(v.y); o[2] = from_float<TO>(v.z); o[3] = from_float<TO>(v.w);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+            const float4* q = reinterpret_cast<const float4*>(sb + ((size_t)sy * W + sx) * C) + 2 * c8;
+            v0 = __ldg(q);
+            v1 = __ldg(q + 1);
+        }
+        TO* o = db + (p * 9 + tap) * C + c8 * 8;
+        store8(o, v0, v1);
     }
 }
 
@@ -221,9 +234,9 @@ extern "C" int svb_groupnorm_rows(const float* x, int64_t x_sample_stride, const
     SVB_CHECK_CUDA(cudaGetLastError());
     dim3 g2(grid_cap((size_t)pixels * channels / 4, 256), batch);
     if (out_dtype == SVB_DTYPE_BF16)
-        gn_rows_apply_kernel<bf16><<<g2, 256, 0, s>>>(x, x_sample_stride, gamma, beta, (bf16*)out, out_sample_stride, pixels, channels, groups, eps, relu, stats_ws);
+        gn_rows_apply_kernel<bf16><<<g2, 256, sizeof(float2) * groups, s>>>(x, x_sample_stride, gamma, beta, (bf16*)out, out_sample_stride, pixels, channels, groups, eps, relu, stats_ws);
     else
-        gn_rows_apply_kernel<float><<<g2, 256, 0, s>>>(x, x_sample_stride, gamma, beta, (float*)out, out_sample_stride, pixels, channels, groups, eps, relu, stats_ws);
+        gn_rows_apply_kernel<float><<<g2, 256, sizeof(float2) * groups, s>>>(x, x_sample_stride, gamma, beta, (float*)out, out_sample_stride, pixels, channels, groups, eps, relu, stats_ws);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -242,11 +255,11 @@ extern "C" int svb_upsample_add_rows(const float* src, int64_t src_sample_stride
 }
 
 extern "C" int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, int batch, int h, int w, int channels, svb_stream_t stream) {
-    SVB_REQUIRE(src && dst && batch > 0 && h > 0 && w > 0 && channels % 4 == 0, "svb_im2col3x3_rows: bad argument");
+    SVB_REQUIRE(src && dst && batch > 0 && h > 0 && w > 0 && channels % 8 == 0, "svb_im2col3x3_rows: bad argument (channels must be a multiple of 8)");
     cudaStream_t s = (cudaStream_t)stream;
     const bool ob = dst_dtype == SVB_DTYPE_BF16;
     ProfScope prof(PC_OTHER, 0, (double)batch * h * w * channels * (4 + 9 * (ob ? 2 : 4)), s);
-    dim3 grid(grid_cap((size_t)h * w * 9 * channels / 4, 256), batch);
+    dim3 grid(grid_cap((size_t)h * w * 9 * channels / 8, 256), batch);
     if (ob) im2col3x3_rows_kernel<bf16><<<grid, 256, 0, s>>>(src, (bf16*)dst, h, w, channels);
     else im2col3x3_rows_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, h, w, channels);
     SVB_CHECK_CUDA(cudaGetLastError());

@@ -254,11 +254,11 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         y = _layernorm(x, src2, self.norm1, torch.empty_like(x))                                                # :126-127
         yb = _add_cast(y, None, adt) if adt != torch.float32 else y
         hid = attn._linear(mode, yb, self._w1, self._b1, torch.empty(N * S, self._w1.shape[0], dtype=adt, device=dev), act=2)     # :117 relu(linear1)
-        z = torch.empty(N * S, C, dtype=torch.float32, device=dev)
+        # src + linear2(..) accumulated IN PLACE into y (the GEMM's TMA reduce-add epilogue), then norm2 into the buffer x leaves behind
         cabi.check(cabi.lib().svb_linear(mode, hid.data_ptr(), hid.stride(0), self._w2.data_ptr(), self._w2.stride(0), N * S, C, hid.shape[1],
-                                         self._b2.data_ptr(), 0, y.data_ptr(), C, 0, z.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0,
+                                         self._b2.data_ptr(), 0, y.data_ptr(), C, 0, y.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0,
                                          cabi.stream_ptr()), "svb_linear")                                      # :117-118 src + linear2(..)
-        return _layernorm(z, None, self.norm2, y)                                                               # :119
+        return _layernorm(y, None, self.norm2, x)                                                               # :119
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         if not src.is_cuda:
