@@ -116,13 +116,15 @@ msda_forward_kernel(const T* __restrict__ value, const float* __restrict__ loc, 
 // ([N*Lq, M*L*P*3]: M*L*P*2 sampling offsets, then M*L*P attention logits) and the reference points, and computes per
 // (n, q, head) the softmax over the L*P logits (:99) and  loc = ref + offset / (W_l, H_l)  (:102-105; boxes, ref_dim 4: ref_xy +
 // offset / P * ref_wh * 0.5, :106-108) on the fly.  LP = L * P must be <= 32.
-template <typename T>
+// PT as above (4 points fully unrolled: the 16 loads of a level are in flight together; 0 = run-time loop).
+template <typename T, int PT>
 __global__ void __launch_bounds__(256)
 msda_fused_kernel(const T* __restrict__ value, const float* __restrict__ raw, const float* __restrict__ ref, T* __restrict__ out,
                   const __grid_constant__ MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int P, int ref_dim) {
     constexpr int V = Pack16<T>::N;
     const int groups = D / V;
-    const int LP = L * P, MLP = M * LP;
+    const int np = PT ? PT : P;
+    const int LP = L * np, MLP = M * LP;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int cg = (int)(idx % groups);
         const long unit = idx / groups;
@@ -130,15 +132,14 @@ msda_fused_kernel(const T* __restrict__ value, const float* __restrict__ raw, co
         const long nq = unit / M;                                  // n * Q + q
         const int n = (int)(nq / Q);
         const float* row = raw + nq * (size_t)(3 * MLP);
-        const float* offp = row + (size_t)m * LP * 2;
+        const float2* offp = reinterpret_cast<const float2*>(row + (size_t)m * LP * 2);
         const float* logp = row + 2 * (size_t)MLP + (size_t)m * LP;
         const float* rp = ref + nq * (size_t)(L * ref_dim);
-        // softmax over the L*P logits of this head (F.softmax(..., -1), fp32)
+        // softmax over the L*P logits of this head (F.softmax(..., -1), fp32): maximum, then ONE exponential per logit (the
+        // normalisation is applied to the accumulated sum at the end)
         float mx = -INFINITY;
         for (int j = 0; j < LP; ++j) mx = fmaxf(mx, __ldg(logp + j));
         float den = 0.f;
-        for (int j = 0; j < LP; ++j) den += expf(__ldg(logp + j) - mx);
-        const float inv_den = 1.f / den;
         const size_t head_stride = (size_t)M * D;
         const T* vbase = value + (size_t)n * S * head_stride + (size_t)m * D + (size_t)cg * V;
         float acc[V];
@@ -148,33 +149,40 @@ msda_fused_kernel(const T* __restrict__ value, const float* __restrict__ raw, co
             const int H = lv.h[l], W = lv.w[l];
             const T* vl = vbase + (size_t)lv.start[l] * head_stride;
             const float rx = __ldg(rp + l * ref_dim), ry = __ldg(rp + l * ref_dim + 1);
-            for (int p = 0; p < P; ++p) {
-                const int j = l * P + p;
-                const float2 off = __ldg(reinterpret_cast<const float2*>(offp) + j);
-                const float wt = expf(__ldg(logp + j) - mx) * inv_den;
-                const float loc_x = ref_dim == 2 ? rx + off.x / (float)W : rx + off.x / (float)P * __ldg(rp + l * ref_dim + 2) * 0.5f;
-                const float loc_y = ref_dim == 2 ? ry + off.y / (float)H : ry + off.y / (float)P * __ldg(rp + l * ref_dim + 3) * 0.5f;
-                const float h_im = loc_y * H - 0.5f, w_im = loc_x * W - 0.5f;
-                const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
-                const float hf = floorf(h_im), wf = floorf(w_im);
-                const int h_low = (int)hf, w_low = (int)wf;
-                const int h_high = h_low + 1, w_high = w_low + 1;
-                const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
-                const bool hl = inside && h_low >= 0, hhi = inside && h_high <= H - 1;
-                const bool wl = w_low >= 0, whi = w_high <= W - 1;
-                const float w1 = (hl && wl) ? hh * hw * wt : 0.f, w2 = (hl && whi) ? hh * lw * wt : 0.f;
-                const float w3 = (hhi && wl) ? lh * hw * wt : 0.f, w4 = (hhi && whi) ? lh * lw * wt : 0.f;
-                const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_high, 0), H - 1);
-                const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_high, 0), W - 1);
-                float t1[V], t2[V], t3[V], t4[V];
-                Pack16<T>::load(vl + ((size_t)y0 * W + x0) * head_stride, t1);
-                Pack16<T>::load(vl + ((size_t)y0 * W + x1) * head_stride, t2);
-                Pack16<T>::load(vl + ((size_t)y1 * W + x0) * head_stride, t3);
-                Pack16<T>::load(vl + ((size_t)y1 * W + x1) * head_stride, t4);
 #pragma unroll
-                for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t1[i], fmaf(w2, t2[i], fmaf(w3, t3[i], fmaf(w4, t4[i], acc[i]))));
+            for (int p = 0; p < (PT ? PT : 1); ++p) {
+                for (int pr = 0; pr < (PT ? 1 : np); ++pr) {      // run-time point loop only in the generic instantiation
+                    const int j = l * np + (PT ? p : pr);
+                    const float2 off = __ldg(offp + j);
+                    const float wt = __expf(__ldg(logp + j) - mx);
+                    den += wt;
+                    const float loc_x = ref_dim == 2 ? rx + off.x / (float)W : rx + off.x / (float)np * __ldg(rp + l * ref_dim + 2) * 0.5f;
+                    const float loc_y = ref_dim == 2 ? ry + off.y / (float)H : ry + off.y / (float)np * __ldg(rp + l * ref_dim + 3) * 0.5f;
+                    const float h_im = loc_y * H - 0.5f, w_im = loc_x * W - 0.5f;
+                    const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+                    const float hf = floorf(h_im), wf = floorf(w_im);
+                    const int h_low = (int)hf, w_low = (int)wf;
+                    const int h_high = h_low + 1, w_high = w_low + 1;
+                    const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+                    const bool hl = inside && h_low >= 0, hhi = inside && h_high <= H - 1;
+                    const bool wl = w_low >= 0, whi = w_high <= W - 1;
+                    const float w1 = (hl && wl) ? hh * hw * wt : 0.f, w2 = (hl && whi) ? hh * lw * wt : 0.f;
+                    const float w3 = (hhi && wl) ? lh * hw * wt : 0.f, w4 = (hhi && whi) ? lh * lw * wt : 0.f;
+                    const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_high, 0), H - 1);
+                    const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_high, 0), W - 1);
+                    float t1[V], t2[V], t3[V], t4[V];
+                    Pack16<T>::load(vl + ((size_t)y0 * W + x0) * head_stride, t1);
+                    Pack16<T>::load(vl + ((size_t)y0 * W + x1) * head_stride, t2);
+                    Pack16<T>::load(vl + ((size_t)y1 * W + x0) * head_stride, t3);
+                    Pack16<T>::load(vl + ((size_t)y1 * W + x1) * head_stride, t4);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t1[i], fmaf(w2, t2[i], fmaf(w3, t3[i], fmaf(w4, t4[i], acc[i]))));
+                }
             }
         }
+        const float inv_den = 1.f / den;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] *= inv_den;
         Pack16<T>::store(out + unit * D + (size_t)cg * V, acc);
     }
 }
@@ -267,14 +275,13 @@ extern "C" int svb_ms_deform_attn_fused_forward(const void* value, const int32_t
     const double bytes = (double)batch * num_query * num_heads *
                          ((double)num_levels * num_points * (12.0 + 4.0 * channels * (vec == 8 ? 2 : 4)) + (double)channels * (vec == 8 ? 2 : 4));
     ProfScope prof(PC_OTHER, 0, bytes, (cudaStream_t)stream);
-    if (dtype == SVB_DTYPE_BF16)
-        msda_fused_kernel<bf16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)value, offsets_and_logits, reference_points, (bf16*)out, lv,
-                                                                           total, spatial_size, num_heads, channels, num_levels, num_query,
-                                                                           num_points, ref_dim);
-    else
-        msda_fused_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)value, offsets_and_logits, reference_points, (float*)out,
-                                                                            lv, total, spatial_size, num_heads, channels, num_levels,
-                                                                            num_query, num_points, ref_dim);
+#define SVB_FUSED(TT, PT)                                                                                                   \
+    msda_fused_kernel<TT, PT><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT*)value, offsets_and_logits, reference_points, (TT*)out, lv, \
+                                                                         total, spatial_size, num_heads, channels, num_levels, num_query,  \
+                                                                         num_points, ref_dim)
+    if (dtype == SVB_DTYPE_BF16) { if (num_points == 4) SVB_FUSED(bf16, 4); else SVB_FUSED(bf16, 0); }
+    else { if (num_points == 4) SVB_FUSED(float, 4); else SVB_FUSED(float, 0); }
+#undef SVB_FUSED
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
