@@ -234,6 +234,15 @@ int svb_resize_bicubic_aa(const float* src, float* tmp, float* dst, int maps, in
 /* out (batch, heads, per_sample) bool = sigmoid(v (batch, per_sample)) < 0.5, repeated over the heads (:467). */
 int svb_mask_threshold_heads(const float* v, void* out_bool, int batch, int heads, int64_t per_sample, svb_stream_t stream);
 
+/* ---- scope row N4, second slice: the attention core of `CrossAttentionLayer.forward_post` (modeling/interface/modules.py:95-106), i.e.
+ * nn.MultiheadAttention's softmax((q / sqrt(d)) k^T + mask) v for `queries` <= 128 tokens over `keys` image positions.  q (queries, batch,
+ * heads * 64), k / v (keys, batch, heads * 64) sequence-first as the reference passes them, element type `dtype`; mask_bool
+ * (batch * heads, queries, keys) bytes, non-zero = not allowed (may be NULL); out (queries, batch, heads * 64) of `dtype`.  workspace:
+ * svb_masked_cross_attention_workspace(...) floats.  A row whose keys are all masked yields NaN, as torch does. ---- */
+int64_t svb_masked_cross_attention_workspace(int queries, int keys, int batch, int heads);
+int svb_masked_cross_attention(const void* q, const void* k, const void* v, int dtype, const void* mask_bool, void* out, float* workspace,
+                               int64_t workspace_floats, int queries, int keys, int batch, int heads, int head_dim, svb_stream_t stream);
+
 /* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
  * completion, [1] = cycles in the issue loop (device pointers). */
 int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);

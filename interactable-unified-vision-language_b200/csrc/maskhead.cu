@@ -133,3 +133,128 @@ extern "C" int svb_mask_threshold_heads(const float* v, void* out_bool, int batc
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ================================================================================================================
+// Masked cross-attention core (scope row N4, second slice): the scaled-dot-product attention inside `nn.MultiheadAttention` as
+// `CrossAttentionLayer.forward_post` calls it (/root/reference/modeling/interface/modules.py:95-106): Q <= 128 query tokens
+// attend to HW image positions under a boolean mask (True = not allowed, the `attn_mask` of xdecoder.py:467).  ~100 queries per
+// image make this a small, key-parallel problem (27 GFLOP per layer at 8 images x 128^2 positions): one thread per query with
+// its 64-channel q and output rows in registers, K / V chunks broadcast from shared memory, keys split over blocks
+// (flash-decoding style partial results) and a combine kernel.
+// ================================================================================================================
+namespace svb {
+namespace {
+constexpr int XA_HD = 64, XA_CHUNK = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+xattn_partial_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const uint8_t* __restrict__ mask,
+                     float* __restrict__ part, int Q, int HW, int B, int heads, int keys_per_block, float scale) {
+    __shared__ float sk[XA_CHUNK][XA_HD], sv[XA_CHUNK][XA_HD];
+    const int blk = blockIdx.x, head = blockIdx.y, b = blockIdx.z, t = threadIdx.x;
+    const int C = heads * XA_HD;
+    const int k0 = blk * keys_per_block, k1 = min(HW, k0 + keys_per_block);
+    float qr[XA_HD], o[XA_HD];
+    const bool live = t < Q;
+#pragma unroll
+    for (int d = 0; d < XA_HD; ++d) { qr[d] = live ? to_float(q[((size_t)t * B + b) * C + head * XA_HD + d]) * scale : 0.f; o[d] = 0.f; }
+    float m = -INFINITY, l = 0.f;
+    const uint8_t* mrow = mask ? mask + ((size_t)(b * heads + head) * Q + (live ? t : 0)) * HW : nullptr;
+    for (int c0 = k0; c0 < k1; c0 += XA_CHUNK) {
+        const int nk = min(XA_CHUNK, k1 - c0);
+        __syncthreads();
+        for (int i = t; i < XA_CHUNK * XA_HD; i += 128) {
+            const int kk = i / XA_HD, d = i % XA_HD;
+            const size_t src = ((size_t)(c0 + kk) * B + b) * C + head * XA_HD + d;
+            sk[kk][d] = kk < nk ? to_float(k[src]) : 0.f;
+            sv[kk][d] = kk < nk ? to_float(v[src]) : 0.f;
+        }
+        __syncthreads();
+        if (!live) continue;
+        float s[XA_CHUNK];
+        float cmax = -INFINITY;
+#pragma unroll 4
+        for (int kk = 0; kk < XA_CHUNK; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < XA_HD; ++d) acc = fmaf(qr[d], sk[kk][d], acc);
+            const bool off = kk >= nk || (mrow && mrow[c0 + kk]);
+            s[kk] = off ? -INFINITY : acc;
+            cmax = fmaxf(cmax, s[kk]);
+        }
+        if (cmax == -INFINITY) continue;                   // every key of this chunk is masked for this query
+        const float m_new = fmaxf(m, cmax);
+        const float alpha = __expf(m - m_new);             // 0 when m was -inf
+        l *= alpha;
+#pragma unroll
+        for (int d = 0; d < XA_HD; ++d) o[d] *= alpha;
+        m = m_new;
+#pragma unroll 4
+        for (int kk = 0; kk < XA_CHUNK; ++kk) {
+            const float p = __expf(s[kk] - m);             // exp(-inf) = 0 for masked keys
+            l += p;
+#pragma unroll
+            for (int d = 0; d < XA_HD; ++d) o[d] = fmaf(p, sv[kk][d], o[d]);
+        }
+    }
+    if (live) {
+        float* dst = part + ((((size_t)b * heads + head) * gridDim.x + blk) * Q + t) * (XA_HD + 2);
+        dst[0] = m;
+        dst[1] = l;
+#pragma unroll
+        for (int d = 0; d < XA_HD; ++d) dst[2 + d] = o[d];
+    }
+}
+
+template <typename T>
+__global__ void xattn_combine_kernel(const float* __restrict__ part, T* __restrict__ out, int Q, int B, int heads, int nblk) {
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int t = blockIdx.x * (blockDim.x / XA_HD) + threadIdx.x / XA_HD, d = threadIdx.x % XA_HD;
+    if (t >= Q) return;
+    const float* p0 = part + (((size_t)b * heads + head) * nblk * Q + t) * (XA_HD + 2);
+    const size_t stride = (size_t)Q * (XA_HD + 2);
+    float m = -INFINITY;
+    for (int j = 0; j < nblk; ++j) m = fmaxf(m, p0[j * stride]);
+    float l = 0.f, o = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+        const float w = __expf(p0[j * stride] - m);        // NaN only if every key of the row is masked (m = -inf), as in torch
+        l += w * p0[j * stride + 1];
+        o += w * p0[j * stride + 2 + d];
+    }
+    out[((size_t)t * B + b) * (heads * XA_HD) + head * XA_HD + d] = from_float<T>(o / l);
+}
+}  // namespace
+}  // namespace svb
+
+extern "C" int svb_masked_cross_attention(const void* q, const void* k, const void* v, int dtype, const void* mask_bool, void* out, float* workspace,
+                                          int64_t workspace_floats, int queries, int keys, int batch, int heads, int head_dim, svb_stream_t stream) {
+    SVB_REQUIRE(q && k && v && out && workspace, "svb_masked_cross_attention: null argument");
+    SVB_REQUIRE(head_dim == XA_HD && queries >= 1 && queries <= 128 && keys >= 1 && batch >= 1 && heads >= 1,
+                "svb_masked_cross_attention: head_dim %d (64 supported), %d queries (<= 128)", head_dim, queries);
+    cudaStream_t s = (cudaStream_t)stream;
+    int kpb = 512;
+    while (kpb > XA_CHUNK && (long)((keys + kpb - 1) / kpb) * heads * batch < 296) kpb /= 2;      // at least two blocks per SM where possible
+    const int nblk = (keys + kpb - 1) / kpb;
+    const int64_t need = (int64_t)batch * heads * nblk * queries * (XA_HD + 2);
+    SVB_REQUIRE(workspace_floats >= need, "svb_masked_cross_attention: workspace of %lld floats needed, %lld given", (long long)need,
+                (long long)workspace_floats);
+    ProfScope prof(PC_OTHER, 4.0 * batch * heads * (double)queries * keys * XA_HD, (double)batch * keys * heads * XA_HD * 2 * (dtype == SVB_DTYPE_BF16 ? 2 : 4), s, 2);
+    dim3 g1(nblk, heads, batch);
+    const float scale = 1.0f / sqrtf((float)head_dim);
+    dim3 g2((queries + 3) / 4, heads, batch);
+    if (dtype == SVB_DTYPE_BF16) {
+        xattn_partial_kernel<bf16><<<g1, 128, 0, s>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const uint8_t*)mask_bool, workspace, queries, keys, batch, heads, kpb, scale);
+        SVB_CHECK_CUDA(cudaGetLastError());
+        xattn_combine_kernel<bf16><<<g2, 256, 0, s>>>(workspace, (bf16*)out, queries, batch, heads, nblk);
+    } else {
+        xattn_partial_kernel<float><<<g1, 128, 0, s>>>((const float*)q, (const float*)k, (const float*)v, (const uint8_t*)mask_bool, workspace, queries, keys, batch, heads, kpb, scale);
+        SVB_CHECK_CUDA(cudaGetLastError());
+        xattn_combine_kernel<float><<<g2, 256, 0, s>>>(workspace, (float*)out, queries, batch, heads, nblk);
+    }
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int64_t svb_masked_cross_attention_workspace(int queries, int keys, int batch, int heads) {
+    return (int64_t)batch * heads * ((keys + XA_CHUNK - 1) / XA_CHUNK) * queries * (XA_HD + 2);
+}

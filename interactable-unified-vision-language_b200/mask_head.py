@@ -104,3 +104,91 @@ class MaskPredictionHead(nn.Module):
             cabi.check(lib.svb_mask_threshold_heads(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q * oh * ow, st()),
                        "svb_mask_threshold_heads")                                                                     # :467-470
         return {"outputs_mask": masks, "attn_mask": attn, "attn_logits": small.view(B, Q, oh, ow)}
+
+
+class CrossAttentionLayer(nn.Module):
+    """Drop-in for the reference's ``CrossAttentionLayer`` (``interface/modules.py:72-131``, post-norm path ``forward_post``): same
+    constructor and parameter names (``multihead_attn.in_proj_weight / in_proj_bias / out_proj.*``, ``norm.*`` — an
+    ``nn.MultiheadAttention`` is kept as the parameter holder), same ``forward(tgt, memory, memory_mask, ..., pos, query_pos)``.
+    Forward only, CUDA only.  The three input projections and the output projection run on the GEMM (``svb_linear``), ``tensor + pos``
+    is fused with the cast to the operand type, the masked softmax(QK^T)V is ``svb_masked_cross_attention``, the residual add is fused
+    into the LayerNorm.  Returns ``(tgt, None)``: the head-averaged attention map the reference also returns is not materialised."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        if normalize_before:
+            raise NotImplementedError("the B200 CrossAttentionLayer implements the post-norm path (PRE_NORM: False in step1.yaml)")
+        self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+        self.nhead = nhead
+        self.precision = "bf16"
+        self._sig = None
+        for p in self.parameters():                                                    # :87-90
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def _prepare(self, device, wdtype):
+        ps = list(self.parameters())
+        sig = (str(device), wdtype) + tuple((p.data_ptr(), p._version) for p in ps)
+        if sig != self._sig:
+            f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()      # noqa: E731
+            w, b = f(self.multihead_attn.in_proj_weight), f(self.multihead_attn.in_proj_bias)
+            c = w.shape[1]
+            self._wq, self._wk, self._wv = (w[i * c:(i + 1) * c].to(wdtype).contiguous() for i in range(3))
+            self._bq, self._bk, self._bv = (b[i * c:(i + 1) * c].contiguous() for i in range(3))
+            self._wo, self._bo = f(self.multihead_attn.out_proj.weight).to(wdtype).contiguous(), f(self.multihead_attn.out_proj.bias)
+            self.norm._w32, self.norm._b32 = f(self.norm.weight), f(self.norm.bias)
+            self._sig = sig
+
+    def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
+        """tgt (Q, B, C), memory (HW, B, C), memory_mask (B * heads, Q, HW) bool (True = not allowed), pos / query_pos like memory / tgt."""
+        if not tgt.is_cuda:
+            raise RuntimeError("CrossAttentionLayer (B200) has no CPU path: the inputs must be CUDA tensors")
+        if memory_key_padding_mask is not None:
+            raise NotImplementedError("memory_key_padding_mask is not used by the X-Decoder (xdecoder.py:259-263) and not implemented")
+        if torch.is_grad_enabled() and (tgt.requires_grad or memory.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("CrossAttentionLayer (B200) implements the forward pass only: call it under torch.no_grad()")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        mode, adt = (cabi.MODE_BF16, torch.bfloat16) if self.precision == "bf16" else (cabi.MODE_FP32, torch.float32)
+        Q, B, C = tgt.shape
+        HW = memory.shape[0]
+        h = self.nhead
+        dev = tgt.device
+        lib, st = cabi.lib(), cabi.stream_ptr
+        lin = MaskPredictionHead._linear
+
+        def cast(a, b):
+            out = torch.empty(a.shape, dtype=adt, device=dev)
+            cabi.check(lib.svb_add_cast(a.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(), _odt(adt), a.numel(), st()), "svb_add_cast")
+            return out
+
+        with torch.cuda.device(dev):
+            self._prepare(dev, adt)
+            x = tgt.detach().to(torch.float32).contiguous().view(Q * B, C).clone()
+            mem = memory.detach().to(torch.float32).contiguous().view(HW * B, C)
+            qp = None if query_pos is None else query_pos.detach().to(torch.float32).contiguous().view(Q * B, C)
+            kp = None if pos is None else pos.detach().to(torch.float32).contiguous().view(HW * B, C)
+            q_in = cast(x, qp) if (qp is not None or adt != torch.float32) else x                                  # :100 with_pos_embed(tgt, query_pos)
+            k_in = cast(mem, kp) if (kp is not None or adt != torch.float32) else mem                              # :101 with_pos_embed(memory, pos)
+            v_in = k_in if kp is None else (cast(mem, None) if adt != torch.float32 else mem)                      # :102 value = memory
+            q = lin(mode, q_in, self._wq, self._bq, torch.empty(Q * B, C, dtype=adt, device=dev))
+            k = lin(mode, k_in, self._wk, self._bk, torch.empty(HW * B, C, dtype=adt, device=dev))
+            v = lin(mode, v_in, self._wv, self._bv, torch.empty(HW * B, C, dtype=adt, device=dev))
+            mask = None
+            if memory_mask is not None:
+                if memory_mask.dtype != torch.bool or tuple(memory_mask.shape) != (B * h, Q, HW):
+                    raise ValueError("memory_mask must be a bool tensor of shape (batch * heads, queries, keys)")
+                mask = memory_mask.contiguous()
+            nws = int(lib.svb_masked_cross_attention_workspace(Q, HW, B, h))
+            ws = torch.empty(nws, dtype=torch.float32, device=dev)
+            att = torch.empty(Q * B, C, dtype=adt, device=dev)
+            cabi.check(lib.svb_masked_cross_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), _odt(adt), mask.data_ptr() if mask is not None else None,
+                                                      att.data_ptr(), ws.data_ptr(), nws, Q, HW, B, h, C // h, st()), "svb_masked_cross_attention")
+            tgt2 = lin(mode, att, self._wo, self._bo, torch.empty(Q * B, C, dtype=torch.float32, device=dev))     # out_proj
+            out = torch.empty(Q * B, C, dtype=torch.float32, device=dev)
+            cabi.check(lib.svb_layernorm(x.data_ptr(), tgt2.data_ptr(), self.norm._w32.data_ptr(), self.norm._b32.data_ptr(), out.data_ptr(),
+                                         cabi.DTYPE_F32, Q * B, C, float(self.norm.eps), st()), "svb_layernorm")          # :104-105
+        return out.view(Q, B, C).to(tgt.dtype), None

@@ -66,3 +66,31 @@ def mask_branch(sd, output, mask_features, attn_mask_target_size, num_queries, n
     logits = resize_bicubic_aa(outputs_mask, attn_mask_target_size)                                                              # :463
     attn = (logits.sigmoid().flatten(2).unsqueeze(1).repeat(1, num_heads, 1, 1).flatten(0, 1) < 0.5)                             # :467
     return outputs_mask, logits, attn
+
+
+def cross_attention_layer(sd, tgt, memory, memory_mask, pos, query_pos, n_heads):
+    """CrossAttentionLayer.forward_post (interface/modules.py:95-106) with torch's nn.MultiheadAttention written out (in_proj split in
+    q / k / v, q scaled by head_dim^-0.5, additive -inf mask where memory_mask is True, softmax over the keys, out_proj), eval mode.
+    tgt (Q, B, C), memory (HW, B, C) sequence-first; state_dict keys as the reference's.  Pinned by tests/golden/cross_attn_*.npz."""
+    Q, B, C = tgt.shape
+    HW = memory.shape[0]
+    d = C // n_heads
+    w, b = sd["multihead_attn.in_proj_weight"], sd["multihead_attn.in_proj_bias"]
+    qi = tgt if query_pos is None else tgt + query_pos
+    ki = memory if pos is None else memory + pos
+    q = qi @ w[:C].t() + b[:C]
+    k = ki @ w[C:2 * C].t() + b[C:2 * C]
+    v = memory @ w[2 * C:].t() + b[2 * C:]
+    q = q.reshape(Q, B * n_heads, d).transpose(0, 1) * (d ** -0.5)
+    k = k.reshape(HW, B * n_heads, d).transpose(0, 1)
+    v = v.reshape(HW, B * n_heads, d).transpose(0, 1)
+    s = q @ k.transpose(1, 2)
+    if memory_mask is not None:
+        s = s.masked_fill(memory_mask, float("-inf"))
+    a = torch.softmax(s, -1) @ v                                           # (B * heads, Q, d)
+    a = a.transpose(0, 1).reshape(Q, B, C)
+    tgt2 = a @ sd["multihead_attn.out_proj.weight"].t() + sd["multihead_attn.out_proj.bias"]
+    x = tgt + tgt2
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + 1e-5) * sd["norm.weight"] + sd["norm.bias"]

@@ -72,3 +72,51 @@ def test_mask_head_against_reference_goldens(case, precision, tol):
     assert frac < (1e-3 if precision == "fp32" else 2e-2), (case, precision, frac)
     assert (not differ.any()) or float(rep[differ].abs().max()) < (1e-3 if precision == "fp32" else 0.1) * scale
     assert ib.rel_l2(res["attn_logits"], ref_logits) < tol
+
+
+@pytest.mark.parametrize("Q,HW,B,NH,dtype,masked", [(101, 1024, 2, 8, torch.float32, True), (37, 300, 1, 2, torch.float32, False),
+                                                    (101, 4096, 2, 8, torch.bfloat16, True)])
+def test_masked_cross_attention_core(Q, HW, B, NH, dtype, masked):
+    """svb_masked_cross_attention against softmax((q / sqrt(d)) k^T + mask) v in fp64 (keys split over blocks + combine)."""
+    g = torch.Generator().manual_seed(13)
+    d = 64
+    C = NH * d
+    q, k, v = (torch.randn(n, B, C, generator=g).to(dtype).to(DEV) for n in (Q, HW, HW))
+    mask = None
+    if masked:
+        mask = (torch.rand(B * NH, Q, HW, generator=g) < 0.6)
+        mask[:, :, HW // 2:HW // 2 + 200] = True                 # whole key chunks masked for every query
+        mask = mask.to(DEV)
+    lib = cabi.lib()
+    nws = int(lib.svb_masked_cross_attention_workspace(Q, HW, B, NH))
+    ws = torch.empty(nws, device=DEV)
+    out = torch.empty(Q, B, C, dtype=dtype, device=DEV)
+    cabi.check(lib.svb_masked_cross_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), cabi.DTYPE_BF16 if dtype == torch.bfloat16 else cabi.DTYPE_F32,
+                                              mask.data_ptr() if masked else None, out.data_ptr(), ws.data_ptr(), nws, Q, HW, B, NH, d,
+                                              cabi.stream_ptr()), "xattn")
+    qh = q.double().cpu().reshape(Q, B * NH, d).transpose(0, 1) * d ** -0.5
+    kh, vh = (t.double().cpu().reshape(HW, B * NH, d).transpose(0, 1) for t in (k, v))
+    s = qh @ kh.transpose(1, 2)
+    if masked:
+        s = s.masked_fill(mask.cpu(), float("-inf"))
+    want = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(Q, B, C)
+    assert ib.rel_l2(out, want) < (2e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("case", ["small", "q101", "nomask"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_cross_attention_layer_against_reference_goldens(case, precision, tol):
+    """Drop-in CrossAttentionLayer against the UNMODIFIED reference class (interface/modules.py:72-131), state_dict loaded by its keys."""
+    from iuvl_b200.mask_head import CrossAttentionLayer
+    z = np.load(os.path.join(GOLDEN, f"cross_attn_{case}.npz"))
+    C, NH = (int(v) for v in z["meta"])
+    layer = CrossAttentionLayer(C, NH)
+    layer.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    layer.to(DEV).eval()
+    layer.precision = precision
+    mask = torch.from_numpy(z["mask"]).to(DEV) if z["mask"].size else None
+    with torch.no_grad():
+        out, _ = layer(torch.from_numpy(z["tgt"]).to(DEV), torch.from_numpy(z["memory"]).to(DEV), memory_mask=mask,
+                       pos=torch.from_numpy(z["pos"]).to(DEV), query_pos=torch.from_numpy(z["query_pos"]).to(DEV))
+    err = ib.rel_l2(out, torch.from_numpy(z["out"]))
+    assert err < tol, (case, precision, err)

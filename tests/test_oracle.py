@@ -260,3 +260,21 @@ def test_mask_head_oracle_against_reference_goldens(case):
     # a bool can only differ where the fp32 reference and the fp64 oracle straddle zero
     rep = logits.flatten(2).unsqueeze(1).repeat(1, NH, 1, 1).flatten(0, 1)
     assert float(differ.float().mean()) < 1e-3 and (not differ.any() or float(rep[differ].abs().max()) < 1e-4)
+
+
+@pytest.mark.parametrize("case", ["small", "q101", "nomask"])
+def test_cross_attention_oracle_against_reference_goldens(case):
+    """oracle.cross_attention_layer against outputs of the UNMODIFIED reference CrossAttentionLayer
+    (tests/golden/make_golden_cross_attn.py; interface/modules.py:72-131)."""
+    import os
+    import numpy as np
+    import iuvl_b200 as ib
+    from oracle import mask_head_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"cross_attn_{case}.npz"))
+    C, NH = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd.")}
+    mask = torch.from_numpy(z["mask"]) if z["mask"].size else None
+    out = mo.cross_attention_layer(sd, torch.from_numpy(z["tgt"]).double(), torch.from_numpy(z["memory"]).double(), mask,
+                                   torch.from_numpy(z["pos"]).double(), torch.from_numpy(z["query_pos"]).double(), NH)
+    assert ib.rel_l2(out, torch.from_numpy(z["out"])) < 2e-6
