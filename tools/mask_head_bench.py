@@ -28,3 +28,23 @@ with torch.no_grad():
         ms = e0.elapsed_time(e1) / 5
         fl = 2.0 * N * 101 * 512 * 65536
         print(f"target {tgt}: {ms:7.3f} ms per call for {N} images; mask-logit GEMMs {fl / 1e9:.0f} GFLOP; outputs_mask {tuple(res['outputs_mask'].shape)}")
+
+# the masked cross-attention layer of a decoder layer (interface/modules.py:95-106) at the three memory sizes
+from iuvl_b200.mask_head import CrossAttentionLayer  # noqa: E402
+layer = CrossAttentionLayer(512, 8).to(dev).eval()
+with torch.no_grad():
+    tgt, qpos = torch.randn(101, N, 512, device=dev), torch.randn(101, N, 512, device=dev)
+    for side in (32, 64, 128):
+        hw = side * side
+        mem, pos = torch.randn(hw, N, 512, device=dev), torch.randn(hw, N, 512, device=dev)
+        mask = torch.rand(N * 8, 101, hw, device=dev) < 0.5
+        for _ in range(2):
+            layer(tgt, mem, memory_mask=mask, pos=pos, query_pos=qpos)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            layer(tgt, mem, memory_mask=mask, pos=pos, query_pos=qpos)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"cross-attention layer, memory {side}^2: {e0.elapsed_time(e1) / 5:7.3f} ms per call for {N} images")
