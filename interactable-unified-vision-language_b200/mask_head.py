@@ -118,6 +118,7 @@ class CrossAttentionLayer(nn.Module):
         super().__init__()
         if normalize_before:
             raise NotImplementedError("the B200 CrossAttentionLayer implements the post-norm path (PRE_NORM: False in step1.yaml)")
+        self._mha_name = "multihead_attn"
         self.multihead_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
         self.norm = nn.LayerNorm(d_model)
         self.dropout = nn.Dropout(dropout)
@@ -134,11 +135,12 @@ class CrossAttentionLayer(nn.Module):
         sig = (str(device), wdtype) + tuple((p.data_ptr(), p._version) for p in ps)
         if sig != self._sig:
             f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()      # noqa: E731
-            w, b = f(self.multihead_attn.in_proj_weight), f(self.multihead_attn.in_proj_bias)
+            mha = getattr(self, self._mha_name)
+            w, b = f(mha.in_proj_weight), f(mha.in_proj_bias)
             c = w.shape[1]
             self._wq, self._wk, self._wv = (w[i * c:(i + 1) * c].to(wdtype).contiguous() for i in range(3))
             self._bq, self._bk, self._bv = (b[i * c:(i + 1) * c].contiguous() for i in range(3))
-            self._wo, self._bo = f(self.multihead_attn.out_proj.weight).to(wdtype).contiguous(), f(self.multihead_attn.out_proj.bias)
+            self._wo, self._bo = f(mha.out_proj.weight).to(wdtype).contiguous(), f(mha.out_proj.bias)
             self.norm._w32, self.norm._b32 = f(self.norm.weight), f(self.norm.bias)
             self._sig = sig
 
@@ -192,3 +194,78 @@ class CrossAttentionLayer(nn.Module):
             cabi.check(lib.svb_layernorm(x.data_ptr(), tgt2.data_ptr(), self.norm._w32.data_ptr(), self.norm._b32.data_ptr(), out.data_ptr(),
                                          cabi.DTYPE_F32, Q * B, C, float(self.norm.eps), st()), "svb_layernorm")          # :104-105
         return out.view(Q, B, C).to(tgt.dtype), None
+
+
+class SelfAttentionLayer(CrossAttentionLayer):
+    """Drop-in for the reference's ``SelfAttentionLayer`` (``interface/modules.py:14-69``, post-norm path): ``q = k = tgt + query_pos``,
+    ``value = tgt``, ``attn_mask = tgt_mask`` — the same kernels as the cross-attention layer with the queries as the memory.  The
+    attention parameters live under ``self_attn`` (the reference's own ``MultiheadAttention`` uses torch's parameter names)."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__(d_model, nhead, dropout, activation, normalize_before)
+        self.self_attn = self.multihead_attn
+        del self.multihead_attn
+        self._mha_name = "self_attn"
+
+    def forward(self, tgt, tgt_mask=None, tgt_key_padding_mask=None, query_pos=None):
+        if tgt_key_padding_mask is not None:
+            raise NotImplementedError("tgt_key_padding_mask is not used by the X-Decoder (xdecoder.py:271-275) and not implemented")
+        if tgt_mask is not None and tgt_mask.dtype != torch.bool:
+            raise NotImplementedError("only boolean attention masks (True = not allowed) are implemented")
+        out, _ = super().forward(tgt, tgt, memory_mask=tgt_mask, pos=query_pos, query_pos=query_pos)
+        return out
+
+
+class FFNLayer(nn.Module):
+    """Drop-in for the reference's ``FFNLayer`` (``interface/modules.py:134-174``, post-norm path): ReLU in ``linear1``'s GEMM epilogue, the
+    residual accumulated in place by ``linear2``'s, then the LayerNorm."""
+
+    def __init__(self, d_model, dim_feedforward=2048, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        if normalize_before or activation != "relu":
+            raise NotImplementedError("the B200 FFNLayer implements the post-norm ReLU configuration (step1.yaml)")
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self.normalize_before = normalize_before
+        self.precision = "bf16"
+        self._sig = None
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, tgt):
+        if not tgt.is_cuda:
+            raise RuntimeError("FFNLayer (B200) has no CPU path: the input must be a CUDA tensor")
+        if torch.is_grad_enabled() and (tgt.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("FFNLayer (B200) implements the forward pass only: call it under torch.no_grad()")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        mode, adt = (cabi.MODE_BF16, torch.bfloat16) if self.precision == "bf16" else (cabi.MODE_FP32, torch.float32)
+        dev = tgt.device
+        lib, st = cabi.lib(), cabi.stream_ptr
+        shape = tgt.shape
+        C = shape[-1]
+        with torch.cuda.device(dev):
+            ps = list(self.parameters())
+            sig = (str(dev), adt) + tuple((p.data_ptr(), p._version) for p in ps)
+            if sig != self._sig:
+                f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()      # noqa: E731
+                self._w1, self._b1 = f(self.linear1.weight).to(adt).contiguous(), f(self.linear1.bias)
+                self._w2, self._b2 = f(self.linear2.weight).to(adt).contiguous(), f(self.linear2.bias)
+                self._nw, self._nb = f(self.norm.weight), f(self.norm.bias)
+                self._sig = sig
+            x = tgt.detach().to(torch.float32).contiguous().view(-1, C).clone()
+            rows = x.shape[0]
+            a = x
+            if adt != torch.float32:
+                a = torch.empty(rows, C, dtype=adt, device=dev)
+                cabi.check(lib.svb_add_cast(x.data_ptr(), None, a.data_ptr(), _odt(adt), x.numel(), st()), "svb_add_cast")
+            hid = MaskPredictionHead._linear(mode, a, self._w1, self._b1, torch.empty(rows, self._w1.shape[0], dtype=adt, device=dev), act=2)   # :160
+            cabi.check(lib.svb_linear(mode, hid.data_ptr(), hid.stride(0), self._w2.data_ptr(), self._w2.stride(0), rows, C, hid.shape[1],
+                                      self._b2.data_ptr(), 0, x.data_ptr(), C, 0, x.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0, st()), "svb_linear")   # :160-161
+            out = torch.empty(rows, C, dtype=torch.float32, device=dev)
+            cabi.check(lib.svb_layernorm(x.data_ptr(), None, self._nw.data_ptr(), self._nb.data_ptr(), out.data_ptr(), cabi.DTYPE_F32, rows, C,
+                                         float(self.norm.eps), st()), "svb_layernorm")                                                        # :162
+        return out.view(shape).to(tgt.dtype)

@@ -68,14 +68,14 @@ def mask_branch(sd, output, mask_features, attn_mask_target_size, num_queries, n
     return outputs_mask, logits, attn
 
 
-def cross_attention_layer(sd, tgt, memory, memory_mask, pos, query_pos, n_heads):
+def cross_attention_layer(sd, tgt, memory, memory_mask, pos, query_pos, n_heads, mha="multihead_attn"):
     """CrossAttentionLayer.forward_post (interface/modules.py:95-106) with torch's nn.MultiheadAttention written out (in_proj split in
     q / k / v, q scaled by head_dim^-0.5, additive -inf mask where memory_mask is True, softmax over the keys, out_proj), eval mode.
     tgt (Q, B, C), memory (HW, B, C) sequence-first; state_dict keys as the reference's.  Pinned by tests/golden/cross_attn_*.npz."""
     Q, B, C = tgt.shape
     HW = memory.shape[0]
     d = C // n_heads
-    w, b = sd["multihead_attn.in_proj_weight"], sd["multihead_attn.in_proj_bias"]
+    w, b = sd[mha + ".in_proj_weight"], sd[mha + ".in_proj_bias"]
     qi = tgt if query_pos is None else tgt + query_pos
     ki = memory if pos is None else memory + pos
     q = qi @ w[:C].t() + b[:C]
@@ -89,8 +89,21 @@ def cross_attention_layer(sd, tgt, memory, memory_mask, pos, query_pos, n_heads)
         s = s.masked_fill(memory_mask, float("-inf"))
     a = torch.softmax(s, -1) @ v                                           # (B * heads, Q, d)
     a = a.transpose(0, 1).reshape(Q, B, C)
-    tgt2 = a @ sd["multihead_attn.out_proj.weight"].t() + sd["multihead_attn.out_proj.bias"]
+    tgt2 = a @ sd[mha + ".out_proj.weight"].t() + sd[mha + ".out_proj.bias"]
     x = tgt + tgt2
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + 1e-5) * sd["norm.weight"] + sd["norm.bias"]
+
+
+def self_attention_layer(sd, tgt, tgt_mask, query_pos, n_heads):
+    """SelfAttentionLayer.forward_post (interface/modules.py:37-47): q = k = tgt + query_pos, value = tgt."""
+    return cross_attention_layer(sd, tgt, tgt, tgt_mask, query_pos, query_pos, n_heads, mha="self_attn")
+
+
+def ffn_layer(sd, tgt):
+    """FFNLayer.forward_post (interface/modules.py:159-163)."""
+    x = tgt + torch.relu(tgt @ sd["linear1.weight"].t() + sd["linear1.bias"]) @ sd["linear2.weight"].t() + sd["linear2.bias"]
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + 1e-5) * sd["norm.weight"] + sd["norm.bias"]

@@ -120,3 +120,23 @@ def test_cross_attention_layer_against_reference_goldens(case, precision, tol):
                        pos=torch.from_numpy(z["pos"]).to(DEV), query_pos=torch.from_numpy(z["query_pos"]).to(DEV))
     err = ib.rel_l2(out, torch.from_numpy(z["out"]))
     assert err < tol, (case, precision, err)
+
+
+@pytest.mark.parametrize("case", ["small", "q101"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_self_attention_and_ffn_layers_against_reference_goldens(case, precision, tol):
+    """Drop-in SelfAttentionLayer / FFNLayer against the UNMODIFIED reference classes (interface/modules.py:14-69,134-174)."""
+    from iuvl_b200.mask_head import FFNLayer, SelfAttentionLayer
+    z = np.load(os.path.join(GOLDEN, f"decoder_layers_{case}.npz"))
+    C, NH, FF = (int(v) for v in z["meta"])
+    sa, ffn = SelfAttentionLayer(C, NH), FFNLayer(C, FF)
+    sa.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sa.")}, strict=True)
+    ffn.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("ffn.")}, strict=True)
+    sa.to(DEV).eval()
+    ffn.to(DEV).eval()
+    sa.precision = ffn.precision = precision
+    with torch.no_grad():
+        y = sa(torch.from_numpy(z["tgt"]).to(DEV), tgt_mask=torch.from_numpy(z["mask"]).to(DEV), query_pos=torch.from_numpy(z["query_pos"]).to(DEV))
+        zf = ffn(torch.from_numpy(z["self_out"]).to(DEV))
+    assert ib.rel_l2(y, torch.from_numpy(z["self_out"])) < tol
+    assert ib.rel_l2(zf, torch.from_numpy(z["ffn_out"])) < tol

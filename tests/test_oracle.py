@@ -278,3 +278,21 @@ def test_cross_attention_oracle_against_reference_goldens(case):
     out = mo.cross_attention_layer(sd, torch.from_numpy(z["tgt"]).double(), torch.from_numpy(z["memory"]).double(), mask,
                                    torch.from_numpy(z["pos"]).double(), torch.from_numpy(z["query_pos"]).double(), NH)
     assert ib.rel_l2(out, torch.from_numpy(z["out"])) < 2e-6
+
+
+@pytest.mark.parametrize("case", ["small", "q101"])
+def test_decoder_layer_oracles_against_reference_goldens(case):
+    """oracle.self_attention_layer / ffn_layer against outputs of the UNMODIFIED reference SelfAttentionLayer / FFNLayer
+    (tests/golden/make_golden_decoder_layers.py; interface/modules.py:14-69,134-174)."""
+    import os
+    import numpy as np
+    import iuvl_b200 as ib
+    from oracle import mask_head_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"decoder_layers_{case}.npz"))
+    C, NH, FF = (int(v) for v in z["meta"])
+    sa = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sa.")}
+    ffn = {k[4:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("ffn.")}
+    y = mo.self_attention_layer(sa, torch.from_numpy(z["tgt"]).double(), torch.from_numpy(z["mask"]), torch.from_numpy(z["query_pos"]).double(), NH)
+    assert ib.rel_l2(y, torch.from_numpy(z["self_out"])) < 2e-6
+    assert ib.rel_l2(mo.ffn_layer(ffn, torch.from_numpy(z["self_out"]).double()), torch.from_numpy(z["ffn_out"])) < 2e-6
