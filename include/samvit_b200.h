@@ -243,6 +243,9 @@ int64_t svb_masked_cross_attention_workspace(int queries, int keys, int batch, i
 int svb_masked_cross_attention(const void* q, const void* k, const void* v, int dtype, const void* mask_bool, void* out, float* workspace,
                                int64_t workspace_floats, int queries, int keys, int batch, int heads, int head_dim, svb_stream_t stream);
 
+/* mask (rows, keys) bool, in place: a row whose every entry is set is cleared (xdecoder.py:258). */
+int svb_mask_clear_full_rows(void* mask_bool, int64_t rows, int keys, svb_stream_t stream);
+
 /* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
  * completion, [1] = cycles in the issue loop (device pointers). */
 int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);

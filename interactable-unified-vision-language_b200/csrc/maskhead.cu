@@ -258,3 +258,24 @@ extern "C" int svb_masked_cross_attention(const void* q, const void* k, const vo
 extern "C" int64_t svb_masked_cross_attention_workspace(int queries, int keys, int batch, int heads) {
     return (int64_t)batch * heads * ((keys + XA_CHUNK - 1) / XA_CHUNK) * queries * (XA_HD + 2);
 }
+
+// xdecoder.py:258: attn_mask[where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False — a query whose every key is masked attends to all
+namespace svb {
+namespace {
+__global__ void mask_clear_full_rows_kernel(uint8_t* __restrict__ mask, int keys) {
+    uint8_t* row = mask + (size_t)blockIdx.x * keys;
+    int all = 1;
+    for (int i = threadIdx.x; i < keys; i += blockDim.x) all &= (row[i] != 0);
+    all = __syncthreads_and(all);
+    if (all) for (int i = threadIdx.x; i < keys; i += blockDim.x) row[i] = 0;
+}
+}  // namespace
+}  // namespace svb
+
+extern "C" int svb_mask_clear_full_rows(void* mask_bool, int64_t rows, int keys, svb_stream_t stream) {
+    SVB_REQUIRE(mask_bool && rows > 0 && keys > 0, "svb_mask_clear_full_rows: bad argument");
+    ProfScope prof(PC_OTHER, 0, (double)rows * keys, (cudaStream_t)stream);
+    mask_clear_full_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((uint8_t*)mask_bool, keys);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

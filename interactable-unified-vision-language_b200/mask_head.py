@@ -269,3 +269,107 @@ class FFNLayer(nn.Module):
             cabi.check(lib.svb_layernorm(x.data_ptr(), None, self._nw.data_ptr(), self._nb.data_ptr(), out.data_ptr(), cabi.DTYPE_F32, rows, C,
                                          float(self.norm.eps), st()), "svb_layernorm")                                                        # :162
         return out.view(shape).to(tgt.dtype)
+
+
+class XDecoderMaskPath(nn.Module):
+    """The mask path of ``XDecoder.forward`` (``interface/xdecoder.py:191-329``) for segmentation inference (``task='seg'``, eval mode, no
+    grounding / caption tokens): level prompting of the three feature maps, the learnable queries, then per layer masked cross-attention ->
+    self-attention -> FFN -> mask branch of the prediction heads, whose attention mask feeds the next layer.  Parameters carry the names
+    they have inside ``XDecoder`` (``query_feat``, ``query_embed``, ``level_embed``, ``transformer_{cross,self}_attention_layers.N``,
+    ``transformer_ffn_layers.N``, ``decoder_norm``, ``mask_embed``), so those entries of its ``state_dict`` load with ``strict=True``.
+    Returns ``{"pred_masks": (B, Q, H, W), "aux_masks": [...]}``; class / box / caption outputs belong to the text side and are not built."""
+
+    def __init__(self, hidden_dim=512, mask_dim=512, num_queries=101, nheads=8, dim_feedforward=2048, num_levels=3,
+                 level_indexes=(0, 1, 2, 0, 1, 2, 0, 1, 2)):
+        super().__init__()
+        self.num_queries, self.num_heads, self.num_feature_levels = num_queries, nheads, num_levels
+        self.level_indexes = list(level_indexes)
+        self.num_layers = len(self.level_indexes)
+        self.transformer_self_attention_layers = nn.ModuleList(SelfAttentionLayer(hidden_dim, nheads) for _ in range(self.num_layers))
+        self.transformer_cross_attention_layers = nn.ModuleList(CrossAttentionLayer(hidden_dim, nheads) for _ in range(self.num_layers))
+        self.transformer_ffn_layers = nn.ModuleList(FFNLayer(hidden_dim, dim_feedforward) for _ in range(self.num_layers))
+        self.query_feat = nn.Embedding(num_queries, hidden_dim)
+        self.query_embed = nn.Embedding(num_queries, hidden_dim)
+        self.level_embed = nn.Embedding(num_levels, hidden_dim)
+        self._head = [MaskPredictionHead(hidden_dim, mask_dim, num_queries, nheads)]          # parameters registered below under XDecoder's names
+        self.decoder_norm = self._head[0].decoder_norm
+        self.mask_embed = self._head[0].mask_embed
+        m = torch.zeros(1, num_queries, num_queries, dtype=torch.bool)                      # xdecoder.py:149-153 (object / class queries)
+        m[:, :num_queries - 1, num_queries - 1:] = True
+        m[:, num_queries - 1:, :num_queries - 1] = True
+        self.register_buffer("self_attn_mask", m, persistent=False)
+        self.num_pos_feats, self.temperature, self.scale = hidden_dim // 2, 10000, 2 * 3.141592653589793
+        self._pos_cache = {}
+
+    @property
+    def precision(self):
+        return self._head[0].precision
+
+    @precision.setter
+    def precision(self, p):
+        self._head[0].precision = p
+        for ml in (self.transformer_self_attention_layers, self.transformer_cross_attention_layers, self.transformer_ffn_layers):
+            for layer in ml:
+                layer.precision = p
+
+    def _pos(self, h, w, bs, device):
+        """PositionEmbeddingSine(hidden / 2, normalize=True) of an (h, w) map as (h * w, bs, C) (xdecoder.py:204,208), cached per shape."""
+        key = (h, w, bs)
+        if key not in self._pos_cache:
+            npf = self.num_pos_feats
+            dim_t = torch.arange(npf, dtype=torch.float32, device=device)
+            dim_t = self.temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / npf)
+            y = torch.arange(1, h + 1, dtype=torch.float32, device=device) / (h + 1e-6) * self.scale
+            x = torch.arange(1, w + 1, dtype=torch.float32, device=device) / (w + 1e-6) * self.scale
+            py, px = y[:, None] / dim_t, x[:, None] / dim_t
+            py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)
+            px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)
+            pos = torch.cat((py[:, None, :].expand(h, w, npf), px[None, :, :].expand(h, w, npf)), dim=2).reshape(h * w, 1, 2 * npf)
+            self._pos_cache[key] = pos.expand(h * w, bs, 2 * npf).contiguous()
+        return self._pos_cache[key]
+
+    def forward(self, x, mask_features):
+        """x: three (B, C, H_i, W_i) maps (the pixel decoder's multi_scale_features), mask_features (B, Cm, H, W)."""
+        if len(x) != self.num_feature_levels:
+            raise AssertionError("x must hold num_feature_levels maps")                    # :195
+        if not mask_features.is_cuda:
+            raise RuntimeError("XDecoderMaskPath (B200) has no CPU path: the inputs must be CUDA tensors")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("XDecoderMaskPath (B200) implements the forward pass only: call it under torch.no_grad()")
+        dev = mask_features.device
+        lib, st = cabi.lib(), cabi.stream_ptr
+        head = self._head[0]
+        with torch.cuda.device(dev):
+            bs = x[0].shape[0]
+            src, pos, size_list = [], [], []
+            for i in range(self.num_feature_levels):                                         # :202-209
+                h, w = int(x[i].shape[-2]), int(x[i].shape[-1])
+                size_list.append((h, w))
+                pos.append(self._pos(h, w, bs, dev))
+                rows = torch.empty(bs, h * w, x[i].shape[1], dtype=torch.float32, device=dev)
+                xi = x[i].detach().contiguous()
+                if xi.dtype not in (torch.float32, torch.bfloat16):
+                    xi = xi.float()
+                cabi.check(lib.svb_nchw_to_rows(xi.data_ptr(), _odt(xi.dtype), rows.data_ptr(), cabi.DTYPE_F32, bs, xi.shape[1], h * w, 0, st()),
+                           "svb_nchw_to_rows")
+                # (B, HW, C) -> (HW, B, C) + level embedding: index plumbing of the sequence-first layout the layers take
+                src.append((rows.transpose(0, 1) + self.level_embed.weight[i].detach().float()[None, None, :]).contiguous())
+            query_embed = self.query_embed.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)      # :214-215
+            output = self.query_feat.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)
+            self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
+            masks = []
+            res = head(output, mask_features, size_list[0])                                          # :257
+            masks.append(res["outputs_mask"])
+            attn_mask = res["attn_mask"]
+            for i in range(self.num_layers):
+                lvl = self.level_indexes[i]
+                cabi.check(lib.svb_mask_clear_full_rows(attn_mask.data_ptr(), attn_mask.shape[0] * attn_mask.shape[1], attn_mask.shape[2], st()),
+                           "svb_mask_clear_full_rows")                                                # :267
+                output, _ = self.transformer_cross_attention_layers[i](output, src[lvl], memory_mask=attn_mask, pos=pos[lvl],
+                                                                       query_pos=query_embed)        # :272-277
+                output = self.transformer_self_attention_layers[i](output, tgt_mask=self_mask, query_pos=query_embed)   # :283-287
+                output = self.transformer_ffn_layers[i](output)                                       # :290-292
+                res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels])       # :299
+                attn_mask = res["attn_mask"]
+                masks.append(res["outputs_mask"])
+        return {"pred_masks": masks[-1], "aux_masks": masks[:-1]}

@@ -107,3 +107,37 @@ def ffn_layer(sd, tgt):
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + 1e-5) * sd["norm.weight"] + sd["norm.bias"]
+
+
+def xdecoder_mask_path(sd, x, mask_features, num_queries, num_heads, level_indexes):
+    """XDecoder.forward for task='seg' in eval mode without grounding / caption tokens (interface/xdecoder.py:191-329), mask outputs only:
+    -> list of outputs_mask, one per prediction-head call (the last one is `pred_masks`)."""
+    from . import pixel_decoder_oracle as po
+    hidden = sd["query_feat.weight"].shape[1]
+    src, pos, sizes = [], [], []
+    for i, xi in enumerate(x):                                                                           # :202-209
+        sizes.append(tuple(xi.shape[-2:]))
+        pos.append(po.position_embedding_sine(xi, hidden // 2).flatten(2).permute(2, 0, 1))
+        src.append((xi.flatten(2) + sd["level_embed.weight"][i][None, :, None]).permute(2, 0, 1))
+    bs = src[0].shape[1]
+    query_embed = sd["query_embed.weight"].unsqueeze(1).repeat(1, bs, 1)                                 # :214-215
+    output = sd["query_feat.weight"].unsqueeze(1).repeat(1, bs, 1)
+    q = num_queries
+    sam = torch.zeros(1, q, q, dtype=torch.bool)                                                         # :149-153, :254
+    sam[:, :q - 1, q - 1:] = True
+    sam[:, q - 1:, :q - 1] = True
+    sam = sam.repeat(bs * num_heads, 1, 1)
+    head = {k: v for k, v in sd.items() if k.startswith(("decoder_norm.", "mask_embed."))}
+    masks = []
+    m, _, attn = mask_branch(head, output, mask_features, sizes[0], q, num_heads)                        # :257
+    masks.append(m)
+    for i, lvl in enumerate(level_indexes):
+        attn = attn.clone()
+        attn[torch.where(attn.sum(-1) == attn.shape[-1])] = False                                         # :267
+        sub = lambda pre: {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}                  # noqa: E731
+        output = cross_attention_layer(sub(f"transformer_cross_attention_layers.{i}."), output, src[lvl], attn, pos[lvl], query_embed, num_heads)
+        output = self_attention_layer(sub(f"transformer_self_attention_layers.{i}."), output, sam, query_embed, num_heads)
+        output = ffn_layer(sub(f"transformer_ffn_layers.{i}."), output)
+        m, _, attn = mask_branch(head, output, mask_features, sizes[(i + 1) % len(x)], q, num_heads)     # :299
+        masks.append(m)
+    return masks

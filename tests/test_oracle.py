@@ -296,3 +296,27 @@ def test_decoder_layer_oracles_against_reference_goldens(case):
     y = mo.self_attention_layer(sa, torch.from_numpy(z["tgt"]).double(), torch.from_numpy(z["mask"]), torch.from_numpy(z["query_pos"]).double(), NH)
     assert ib.rel_l2(y, torch.from_numpy(z["self_out"])) < 2e-6
     assert ib.rel_l2(mo.ffn_layer(ffn, torch.from_numpy(z["self_out"]).double()), torch.from_numpy(z["ffn_out"])) < 2e-6
+
+
+def _mask_path_case(case):
+    import os
+    import numpy as np
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"xdecoder_mask_path_{case}.npz"))
+    C, MD, Q, NH, FF, NL = (int(v) for v in z["meta"])
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    x = [torch.from_numpy(z[f"x{i}"]) for i in range(3)]
+    return z, (C, MD, Q, NH, FF, NL), sd, x, torch.from_numpy(z["mask_features"])
+
+
+@pytest.mark.parametrize("case", ["small", "q101"])
+def test_xdecoder_mask_path_oracle_against_reference_goldens(case):
+    """oracle.xdecoder_mask_path against outputs of the UNMODIFIED reference XDecoder.forward (task='seg') executed on a stand-in object
+    (tests/golden/make_golden_xdecoder_mask_path.py; interface/xdecoder.py:191-329).  The attention masks are thresholds of fp32 logits:
+    the fp64 oracle may flip single mask bits, so the comparison allows the small drift that causes in the later layers."""
+    import iuvl_b200 as ib
+    from oracle import mask_head_oracle as mo
+    z, (C, MD, Q, NH, FF, NL), sd, x, mf = _mask_path_case(case)
+    masks = mo.xdecoder_mask_path({k: v.double() for k, v in sd.items()}, [t.double() for t in x], mf.double(), Q, NH, [0, 1, 2, 0, 1, 2, 0, 1, 2][:NL])
+    assert ib.rel_l2(masks[0], torch.from_numpy(z["aux0"]) if "aux0" in z.files else masks[0]) < 1e-5
+    assert ib.rel_l2(masks[-1], torch.from_numpy(z["pred_masks"])) < 2e-3

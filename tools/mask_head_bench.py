@@ -48,3 +48,19 @@ with torch.no_grad():
         e1.record()
         torch.cuda.synchronize()
         print(f"cross-attention layer, memory {side}^2: {e0.elapsed_time(e1) / 5:7.3f} ms per call for {N} images")
+
+# the whole mask path of the X-Decoder predictor (9 layers) on the pixel decoder's outputs
+from iuvl_b200.mask_head import XDecoderMaskPath  # noqa: E402
+path = XDecoderMaskPath(512, 512, 101, 8, 2048).to(dev).eval()
+with torch.no_grad():
+    xs = [torch.randn(N, 512, s, s, device=dev) for s in (32, 64, 128)]
+    for _ in range(2):
+        res = path(xs, mf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        res = path(xs, mf)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"X-Decoder mask path (9 layers, 10 prediction-head calls): {e0.elapsed_time(e1) / 3:7.2f} ms per forward for {N} images; pred_masks {tuple(res['pred_masks'].shape)}")
