@@ -56,7 +56,20 @@ class MaskPredictionHead(nn.Module):
                                          out.stride(0), None, 0, 0, 0, cabi.stream_ptr()), "svb_linear")
         return out
 
-    def forward(self, output, mask_features, attn_mask_target_size):
+    def mask_rows(self, mask_features):
+        """mask_features (B, Cm, H, W) -> (B * H * W, Cm) rows in the GEMM operand type: the layout the mask-logit GEMM reads.  A caller that
+        runs the head several times on the same features (one call per decoder layer) converts once and passes `rows=`."""
+        adt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        mf = mask_features.detach().contiguous()
+        if mf.dtype not in (torch.float32, torch.bfloat16):
+            mf = mf.float()
+        B, Cm, H, W = mf.shape
+        rows = torch.empty(B * H * W, Cm, dtype=adt, device=mf.device)
+        cabi.check(cabi.lib().svb_nchw_to_rows(mf.data_ptr(), _odt(mf.dtype), rows.data_ptr(), _odt(adt), B, Cm, H * W, 0, cabi.stream_ptr()),
+                   "svb_nchw_to_rows")
+        return rows
+
+    def forward(self, output, mask_features, attn_mask_target_size, rows=None):
         """output (Q, B, C) — the decoder's query states as ``forward_prediction_heads`` receives them; mask_features (B, Cm, H, W) fp32 or
         bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool}."""
         if not output.is_cuda:
@@ -88,11 +101,8 @@ class MaskPredictionHead(nn.Module):
             for i, (w, b) in enumerate(self._mlp):                                                                    # :458 mask_embed
                 last = i == n - 1
                 a = self._linear(mode, a, w, b, torch.empty(B * Q, w.shape[0], dtype=adt, device=dev), act=0 if last else 2)
-            mf = mask_features.detach().contiguous()
-            if mf.dtype not in (torch.float32, torch.bfloat16):
-                mf = mf.float()
-            rows = torch.empty(B * H * W, Cm, dtype=adt, device=dev)
-            cabi.check(lib.svb_nchw_to_rows(mf.data_ptr(), _odt(mf.dtype), rows.data_ptr(), _odt(adt), B, Cm, H * W, 0, st()), "svb_nchw_to_rows")
+            if rows is None or rows.dtype != adt:
+                rows = self.mask_rows(mask_features)
             masks = torch.empty(B, Q, H, W, dtype=torch.float32, device=dev)
             for b in range(B):                                                                                        # :459 "bqc,bchw->bqhw"
                 self._linear(mode, a[b * Q:(b + 1) * Q], rows[b * H * W:(b + 1) * H * W], None, masks[b].view(Q, H * W))
@@ -358,7 +368,8 @@ class XDecoderMaskPath(nn.Module):
             output = self.query_feat.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)
             self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
             masks = []
-            res = head(output, mask_features, size_list[0])                                          # :257
+            mrows = head.mask_rows(mask_features)                                                    # once for the ten prediction-head calls
+            res = head(output, mask_features, size_list[0], rows=mrows)                              # :257
             masks.append(res["outputs_mask"])
             attn_mask = res["attn_mask"]
             for i in range(self.num_layers):
@@ -369,7 +380,7 @@ class XDecoderMaskPath(nn.Module):
                                                                        query_pos=query_embed)        # :272-277
                 output = self.transformer_self_attention_layers[i](output, tgt_mask=self_mask, query_pos=query_embed)   # :283-287
                 output = self.transformer_ffn_layers[i](output)                                       # :290-292
-                res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels])       # :299
+                res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels], rows=mrows)   # :299
                 attn_mask = res["attn_mask"]
                 masks.append(res["outputs_mask"])
         return {"pred_masks": masks[-1], "aux_masks": masks[:-1]}

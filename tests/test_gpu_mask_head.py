@@ -165,3 +165,44 @@ def test_xdecoder_mask_path_against_reference_goldens(case, precision, tol):
     err = ib.rel_l2(out["pred_masks"], torch.from_numpy(z["pred_masks"]))
     print(case, precision, err)
     assert err < tol, (case, precision, err)
+
+
+def test_encoder_pixel_decoder_mask_path_chain():
+    """BASELINE config 5 in miniature: ViT encoder -> pixel decoder -> X-Decoder mask path, all on the CUDA path with bf16 hand-overs,
+    against the three CPU oracles chained in fp64 (first prediction: no thresholded mask involved yet; final masks: looser, see above)."""
+    from oracle import mask_head_oracle as mo
+    from oracle import pixel_decoder_oracle as po
+    from oracle import sam_vit_oracle as orc
+    from iuvl_b200.encoder import build_encoder
+    from iuvl_b200.mask_head import XDecoderMaskPath
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    cfg = ib.PRESETS["tiny80"]
+    sd = ib.make_state_dict(cfg, 99, rel_std=0.1)
+    x = ib.make_images(2, cfg, 5)
+    enc = build_encoder(cfg)
+    enc.load_state_dict(sd)
+    enc.to(DEV)
+    torch.manual_seed(21)
+    dec = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=2, transformer_dim_feedforward=128, transformer_enc_layers=1,
+                                   conv_dim=64, mask_dim=64, norm="GN")
+    path = XDecoderMaskPath(64, 64, 11, 1, 128, 3, [0, 1, 2])
+    with torch.no_grad():
+        for layer in dec.transformer.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.2)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.2)
+    dsd = {k: v.detach().clone().double() for k, v in dec.state_dict().items()}
+    psd = {k: v.detach().clone().double() for k, v in path.state_dict().items()}
+    feats = orc.encoder_forward_cfg(sd, x, cfg)
+    mask_ref, multi_ref = po.pixel_decoder(dsd, {k: v.double() for k, v in feats.items()}, 2, 1)
+    masks_ref = mo.xdecoder_mask_path(psd, multi_ref, mask_ref, 11, 1, [0, 1, 2])
+    dec.to(DEV).eval()
+    path.to(DEV).eval()
+    for precision, tol0, tol in (("fp32", 3e-4, 5e-3), ("bf16", 3e-2, 1e-1)):
+        enc.precision = dec.precision = path.precision = precision
+        enc.out_dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        with torch.no_grad():
+            mask, multi = dec(enc(x.to(DEV)))
+            out = path(multi, mask)
+        e0 = ib.rel_l2(out["aux_masks"][0], masks_ref[0])
+        e1 = ib.rel_l2(out["pred_masks"], masks_ref[-1])
+        assert e0 < tol0 and e1 < tol, (precision, e0, e1)
