@@ -214,7 +214,22 @@ def measure_next_rows(torch, cabi, dev, pk):
     ms = e0.elapsed_time(e1) / 5
     out["mask_head"] = {"workload": "mask branch of forward_prediction_heads, 101 queries x 512, mask_features 512 x 256^2, 4 images, 64^2 attention mask, bf16",
                         "ms_per_call": ms}
-    del head, mf
+    # the whole mask path of the predictor (9 layers: masked cross-attention, self-attention, FFN, mask branch; xdecoder.py:191-329)
+    from iuvl_b200.mask_head import XDecoderMaskPath
+    path = XDecoderMaskPath(512, 512, 101, 8, 2048).to(dev).eval()
+    with torch.no_grad():
+        xs = [torch.randn(N, 512, sd_, sd_, device=dev) for sd_ in (32, 64, 128)]
+        for _ in range(2):
+            path(xs, mf)
+        e0.record()
+        for _ in range(3):
+            path(xs, mf)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["xdecoder_mask_path"] = {"workload": "XDecoder.forward mask path (task seg), 9 layers, 101 queries x 512, 4 images, 256^2 masks, bf16",
+                                 "ms_per_forward": ms, "images_per_s": N / ms * 1e3}
+    del head, mf, path, xs
     B = 16
     imgs = [torch.randint(0, 256, (3, 1024, 1024), dtype=torch.uint8, device=dev) for _ in range(B)]
     dst = torch.empty(B * 4096, 768, dtype=torch.bfloat16, device=dev)
