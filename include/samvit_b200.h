@@ -206,6 +206,10 @@ int64_t svb_launch_count(void);   /* kernels launched by this library since it w
  * the levels of `src_flatten` (:71,79) can be written in place. */
 int svb_nchw_to_rows(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels,
                      int64_t dst_sample_stride, svb_stream_t stream);
+/* (batch, channels, pixels) NCHW -> sequence-first (pixels, batch, channels) [+ chan_add per channel, may be NULL]: `x.flatten(2) +
+ * level_embed[i][None, :, None]` -> `.permute(2, 0, 1)` of the X-Decoder (modeling/interface/xdecoder.py:205-209) in one pass. */
+int svb_nchw_to_seq(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels, const float* chan_add,
+                    svb_stream_t stream);
 /* fp32 rows -> fp32 NCHW (`.transpose(1, 2).view(bs, -1, h, w)` :335 and the module's NCHW outputs :359). */
 int svb_rows_to_nchw(const float* src, int64_t src_sample_stride, float* dst, int batch, int channels, int pixels, svb_stream_t stream);
 /* nn.GroupNorm(groups, channels) on fp32 rows (+ optional ReLU): `input_proj[i][1]` (:213), detectron2 `get_norm("GN", C)` =

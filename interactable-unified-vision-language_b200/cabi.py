@@ -65,6 +65,7 @@ SYMBOLS = {
     "svb_profile_stop": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "svb_launch_count": (C.c_int64, []),
     "svb_nchw_to_rows": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i64, _vp]),
+    "svb_nchw_to_seq": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "svb_rows_to_nchw": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp]),
     "svb_groupnorm_rows": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "svb_upsample_add_rows": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -26,7 +26,8 @@ __device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float
 
 // ---- NCHW -> rows: 32 x 32 tiles through shared memory (coalesced on both sides); casts to the GEMM operand type ----
 template <typename TI, typename TO>
-__global__ void nchw_to_rows_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C, int HW, long long dst_sample_stride) {
+__global__ void nchw_to_rows_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int C, int HW, long long dst_sample_stride,
+                                    long long dst_pixel_stride, const float* __restrict__ chan_add) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const TI* s = src + (size_t)b * C * HW;
@@ -38,7 +39,7 @@ __global__ void nchw_to_rows_kernel(const TI* __restrict__ src, TO* __restrict__
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += 8) {
         const int p = p0 + j, c = c0 + threadIdx.x;
-        if (p < HW && c < C) d[(size_t)p * C + c] = from_float<TO>(tile[threadIdx.x][j]);
+        if (p < HW && c < C) d[(size_t)p * dst_pixel_stride + c] = from_float<TO>(tile[threadIdx.x][j] + (chan_add ? __ldg(chan_add + c) : 0.f));
     }
 }
 
@@ -187,20 +188,31 @@ __global__ void add_cast_bcast_kernel(const float* __restrict__ a, const float* 
 
 using namespace svb;
 
+static int nchw_to_rows_launch(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels, int64_t sample_stride,
+                               int64_t pixel_stride, const float* chan_add, cudaStream_t s) {
+    dim3 grid((pixels + 31) / 32, (channels + 31) / 32, batch), block(32, 8);
+    const bool ib = src_dtype == SVB_DTYPE_BF16, ob = dst_dtype == SVB_DTYPE_BF16;
+    ProfScope prof(PC_OTHER, 0, (double)batch * channels * pixels * ((ib ? 2 : 4) + (ob ? 2 : 4)), s);
+    if (ib && ob) nchw_to_rows_kernel<bf16, bf16><<<grid, block, 0, s>>>((const bf16*)src, (bf16*)dst, channels, pixels, sample_stride, pixel_stride, chan_add);
+    else if (ib) nchw_to_rows_kernel<bf16, float><<<grid, block, 0, s>>>((const bf16*)src, (float*)dst, channels, pixels, sample_stride, pixel_stride, chan_add);
+    else if (ob) nchw_to_rows_kernel<float, bf16><<<grid, block, 0, s>>>((const float*)src, (bf16*)dst, channels, pixels, sample_stride, pixel_stride, chan_add);
+    else nchw_to_rows_kernel<float, float><<<grid, block, 0, s>>>((const float*)src, (float*)dst, channels, pixels, sample_stride, pixel_stride, chan_add);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int svb_nchw_to_rows(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels,
                                 int64_t dst_sample_stride, svb_stream_t stream) {
     SVB_REQUIRE(src && dst && batch > 0 && channels > 0 && pixels > 0, "svb_nchw_to_rows: bad argument");
     if (dst_sample_stride <= 0) dst_sample_stride = (int64_t)pixels * channels;
-    cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid((pixels + 31) / 32, (channels + 31) / 32, batch), block(32, 8);
-    const bool ib = src_dtype == SVB_DTYPE_BF16, ob = dst_dtype == SVB_DTYPE_BF16;
-    ProfScope prof(PC_OTHER, 0, (double)batch * channels * pixels * ((ib ? 2 : 4) + (ob ? 2 : 4)), s);
-    if (ib && ob) nchw_to_rows_kernel<bf16, bf16><<<grid, block, 0, s>>>((const bf16*)src, (bf16*)dst, channels, pixels, dst_sample_stride);
-    else if (ib) nchw_to_rows_kernel<bf16, float><<<grid, block, 0, s>>>((const bf16*)src, (float*)dst, channels, pixels, dst_sample_stride);
-    else if (ob) nchw_to_rows_kernel<float, bf16><<<grid, block, 0, s>>>((const float*)src, (bf16*)dst, channels, pixels, dst_sample_stride);
-    else nchw_to_rows_kernel<float, float><<<grid, block, 0, s>>>((const float*)src, (float*)dst, channels, pixels, dst_sample_stride);
-    SVB_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return nchw_to_rows_launch(src, src_dtype, dst, dst_dtype, batch, channels, pixels, dst_sample_stride, channels, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int svb_nchw_to_seq(const void* src, int src_dtype, void* dst, int dst_dtype, int batch, int channels, int pixels, const float* chan_add,
+                               svb_stream_t stream) {
+    SVB_REQUIRE(src && dst && batch > 0 && channels > 0 && pixels > 0, "svb_nchw_to_seq: bad argument");
+    return nchw_to_rows_launch(src, src_dtype, dst, dst_dtype, batch, channels, pixels, channels, (int64_t)batch * channels, chan_add,
+                               (cudaStream_t)stream);
 }
 
 extern "C" int svb_rows_to_nchw(const float* src, int64_t src_sample_stride, float* dst, int batch, int channels, int pixels,

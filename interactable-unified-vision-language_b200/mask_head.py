@@ -356,14 +356,14 @@ class XDecoderMaskPath(nn.Module):
                 h, w = int(x[i].shape[-2]), int(x[i].shape[-1])
                 size_list.append((h, w))
                 pos.append(self._pos(h, w, bs, dev))
-                rows = torch.empty(bs, h * w, x[i].shape[1], dtype=torch.float32, device=dev)
                 xi = x[i].detach().contiguous()
                 if xi.dtype not in (torch.float32, torch.bfloat16):
                     xi = xi.float()
-                cabi.check(lib.svb_nchw_to_rows(xi.data_ptr(), _odt(xi.dtype), rows.data_ptr(), cabi.DTYPE_F32, bs, xi.shape[1], h * w, 0, st()),
-                           "svb_nchw_to_rows")
-                # (B, HW, C) -> (HW, B, C) + level embedding: index plumbing of the sequence-first layout the layers take
-                src.append((rows.transpose(0, 1) + self.level_embed.weight[i].detach().float()[None, None, :]).contiguous())
+                seq = torch.empty(h * w, bs, xi.shape[1], dtype=torch.float32, device=dev)
+                lvl_e = self.level_embed.weight[i].detach().to(device=dev, dtype=torch.float32).contiguous()
+                cabi.check(lib.svb_nchw_to_seq(xi.data_ptr(), _odt(xi.dtype), seq.data_ptr(), cabi.DTYPE_F32, bs, xi.shape[1], h * w,
+                                               lvl_e.data_ptr(), st()), "svb_nchw_to_seq")          # flatten + level embedding + permute(2, 0, 1)
+                src.append(seq)
             query_embed = self.query_embed.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)      # :214-215
             output = self.query_feat.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)
             self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
