@@ -171,30 +171,48 @@ xattn_partial_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
         }
         __syncthreads();
         if (!live) continue;
-        float s[XA_CHUNK];
-        float cmax = -INFINITY;
-#pragma unroll 4
-        for (int kk = 0; kk < XA_CHUNK; ++kk) {
-            float acc = 0.f;
+        // 16 keys at a time, fully unrolled: the scores stay in registers (a 64-entry score array went to local memory)
+#pragma unroll 1
+        for (int k16 = 0; k16 < XA_CHUNK; k16 += 16) {
+            if (k16 >= nk) break;
+            float s[16];
+            float cmax = -INFINITY;
+            uint4 mb = make_uint4(0, 0, 0, 0);
+            if (mrow) {
+                if (((c0 + k16) & 15) == 0 && (HW & 15) == 0) mb = *reinterpret_cast<const uint4*>(mrow + c0 + k16);   // 16 mask bytes at once
+                else {
+                    uint8_t tmpb[16];
 #pragma unroll
-            for (int d = 0; d < XA_HD; ++d) acc = fmaf(qr[d], sk[kk][d], acc);
-            const bool off = kk >= nk || (mrow && mrow[c0 + kk]);
-            s[kk] = off ? -INFINITY : acc;
-            cmax = fmaxf(cmax, s[kk]);
-        }
-        if (cmax == -INFINITY) continue;                   // every key of this chunk is masked for this query
-        const float m_new = fmaxf(m, cmax);
-        const float alpha = __expf(m - m_new);             // 0 when m was -inf
-        l *= alpha;
+                    for (int j = 0; j < 16; ++j) tmpb[j] = (k16 + j < nk) ? mrow[c0 + k16 + j] : 1;
+                    mb = *reinterpret_cast<uint4*>(tmpb);
+                }
+            }
+            const uint32_t mw[4] = {mb.x, mb.y, mb.z, mb.w};
 #pragma unroll
-        for (int d = 0; d < XA_HD; ++d) o[d] *= alpha;
-        m = m_new;
-#pragma unroll 4
-        for (int kk = 0; kk < XA_CHUNK; ++kk) {
-            const float p = __expf(s[kk] - m);             // exp(-inf) = 0 for masked keys
-            l += p;
+            for (int j = 0; j < 16; ++j) {
+                float acc = 0.f;
 #pragma unroll
-            for (int d = 0; d < XA_HD; ++d) o[d] = fmaf(p, sv[kk][d], o[d]);
+                for (int d = 0; d < XA_HD; ++d) acc = fmaf(qr[d], sk[k16 + j][d], acc);
+                const bool off = (k16 + j >= nk) || ((mw[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                s[j] = off ? -INFINITY : acc;
+                cmax = fmaxf(cmax, s[j]);
+            }
+            if (cmax == -INFINITY) continue;               // every key of this group is masked for this query
+            const float m_new = fmaxf(m, cmax);
+            if (m_new > m) {
+                const float alpha = __expf(m - m_new);     // 0 when m was -inf
+                l *= alpha;
+#pragma unroll
+                for (int d = 0; d < XA_HD; ++d) o[d] *= alpha;
+                m = m_new;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float p = __expf(s[j] - m);          // exp(-inf) = 0 for masked keys
+                l += p;
+#pragma unroll
+                for (int d = 0; d < XA_HD; ++d) o[d] = fmaf(p, sv[k16 + j][d], o[d]);
+            }
         }
     }
     if (live) {
