@@ -74,7 +74,8 @@ class MaskPredictionHead(nn.Module):
         bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool}."""
         if not output.is_cuda:
             raise RuntimeError("MaskPredictionHead (B200) has no CPU path: the inputs must be CUDA tensors")
-        if torch.is_grad_enabled() and (output.requires_grad or mask_features.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (output.requires_grad or (torch.is_tensor(mask_features) and mask_features.requires_grad)
+                                        or any(p.requires_grad for p in self.parameters())):
             raise RuntimeError("MaskPredictionHead (B200) implements the forward pass only: call it under torch.no_grad()")
         Q, B, C = output.shape
         if Q != self.num_queries:
@@ -84,7 +85,7 @@ class MaskPredictionHead(nn.Module):
         mode, adt = (cabi.MODE_BF16, torch.bfloat16) if self.precision == "bf16" else (cabi.MODE_FP32, torch.float32)
         dev = output.device
         lib, st = cabi.lib(), cabi.stream_ptr
-        Bm, Cm, H, W = mask_features.shape
+        Bm, Cm, H, W = tuple(mask_features.shape) if torch.is_tensor(mask_features) else tuple(mask_features)   # a shape when `rows` is given
         oh, ow = int(attn_mask_target_size[0]), int(attn_mask_target_size[1])
         with torch.cuda.device(dev):
             self._prepare(dev, adt)
@@ -338,15 +339,20 @@ class XDecoderMaskPath(nn.Module):
             self._pos_cache[key] = pos.expand(h * w, bs, 2 * npf).contiguous()
         return self._pos_cache[key]
 
-    def forward(self, x, mask_features):
-        """x: three (B, C, H_i, W_i) maps (the pixel decoder's multi_scale_features), mask_features (B, Cm, H, W)."""
+    def forward(self, x, mask_features, mask_rows=None, mask_shape=None):
+        """x: three (B, C, H_i, W_i) maps (the pixel decoder's multi_scale_features), mask_features (B, Cm, H, W) — or None with
+        `mask_rows` / `mask_shape` from `MSDeformAttnPixelDecoder.forward(..., rows_out=True)`."""
         if len(x) != self.num_feature_levels:
             raise AssertionError("x must hold num_feature_levels maps")                    # :195
-        if not mask_features.is_cuda:
+        if mask_features is None:
+            if mask_rows is None or mask_shape is None:
+                raise ValueError("mask_features is None: mask_rows and mask_shape are required")
+            mask_features = tuple(mask_shape)
+        if not x[0].is_cuda:
             raise RuntimeError("XDecoderMaskPath (B200) has no CPU path: the inputs must be CUDA tensors")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise RuntimeError("XDecoderMaskPath (B200) implements the forward pass only: call it under torch.no_grad()")
-        dev = mask_features.device
+        dev = x[0].device
         lib, st = cabi.lib(), cabi.stream_ptr
         head = self._head[0]
         with torch.cuda.device(dev):
@@ -368,7 +374,7 @@ class XDecoderMaskPath(nn.Module):
             output = self.query_feat.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)
             self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
             masks = []
-            mrows = head.mask_rows(mask_features)                                                    # once for the ten prediction-head calls
+            mrows = mask_rows if mask_rows is not None else head.mask_rows(mask_features)            # once for the ten prediction-head calls
             res = head(output, mask_features, size_list[0], rows=mrows)                              # :257
             masks.append(res["outputs_mask"])
             attn_mask = res["attn_mask"]

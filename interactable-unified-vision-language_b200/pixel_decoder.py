@@ -158,9 +158,12 @@ class MSDeformAttnPixelDecoder(nn.Module):
                                                  out_stride, B, HW, C, groups, eps, 1 if relu else 0, ws.data_ptr(), cabi.stream_ptr()),
                    "svb_groupnorm_rows")
 
-    def forward(self, features):
+    def forward(self, features, rows_out=False):
         """features: dict res2..res5 of (B, C, H, W) CUDA tensors (fp32 or bf16) -> (mask_features (B, mask_dim, H2, W2) fp32,
-        [three (B, conv_dim, H, W) fp32 maps, lowest resolution first])   (transformer_encoder_deform.py:315-359)."""
+        [three (B, conv_dim, H, W) fp32 maps, lowest resolution first])   (transformer_encoder_deform.py:315-359).
+        rows_out=True (not in the reference): the mask features stay in the layout and type the next GEMM reads — returns
+        (None, multi_scale_features, {"mask_rows": (B * H2 * W2, mask_dim) rows, "mask_shape": (B, mask_dim, H2, W2)}) for
+        ``XDecoderMaskPath.forward(..., mask_rows=, mask_shape=)``, skipping the NCHW round trip of the largest map."""
         x5 = features[self.transformer_in_features[-1]]
         if not x5.is_cuda:
             raise RuntimeError("MSDeformAttnPixelDecoder (B200) has no CPU path: the features must be CUDA tensors")
@@ -239,12 +242,16 @@ class MSDeformAttnPixelDecoder(nn.Module):
             a_in = cur_a if adt == torch.float32 else torch.empty(B * h * w, C, dtype=adt, device=dev)
             if adt != torch.float32:
                 cabi.check(lib.svb_add_cast(cur_a.data_ptr(), None, a_in.data_ptr(), _odt(adt), cur_a.numel(), st()), "svb_add_cast")
-            mrows = self._linear(mode, a_in, wm, bm, torch.empty(B * h * w, self.mask_dim, dtype=torch.float32, device=dev))
-            mask = torch.empty(B, self.mask_dim, h, w, dtype=torch.float32, device=dev)
-            cabi.check(lib.svb_rows_to_nchw(mrows.data_ptr(), 0, mask.data_ptr(), B, self.mask_dim, h * w, st()), "svb_rows_to_nchw")
+            mrows = self._linear(mode, a_in, wm, bm, torch.empty(B * h * w, self.mask_dim, dtype=adt if rows_out else torch.float32, device=dev))
+            mask = None
+            if not rows_out:
+                mask = torch.empty(B, self.mask_dim, h, w, dtype=torch.float32, device=dev)
+                cabi.check(lib.svb_rows_to_nchw(mrows.data_ptr(), 0, mask.data_ptr(), B, self.mask_dim, h * w, st()), "svb_rows_to_nchw")
             multi = []
             for idx, (lh, lw) in enumerate(shapes[:self.maskformer_num_feature_levels]):
                 o = torch.empty(B, C, lh, lw, dtype=torch.float32, device=dev)
                 cabi.check(lib.svb_rows_to_nchw(y[starts[idx]:].data_ptr(), S * C, o.data_ptr(), B, C, lh * lw, st()), "svb_rows_to_nchw")
                 multi.append(o)
+        if rows_out:
+            return mask, multi, {"mask_rows": mrows, "mask_shape": (B, self.mask_dim, h, w)}
         return mask, multi

@@ -206,3 +206,8 @@ def test_encoder_pixel_decoder_mask_path_chain():
         e0 = ib.rel_l2(out["aux_masks"][0], masks_ref[0])
         e1 = ib.rel_l2(out["pred_masks"], masks_ref[-1])
         assert e0 < tol0 and e1 < tol, (precision, e0, e1)
+        # the rows hand-over (no NCHW round trip of the mask features) is the same arithmetic: bit-identical masks
+        with torch.no_grad():
+            _, multi2, extra = dec(enc(x.to(DEV)), rows_out=True)
+            out2 = path(multi2, None, mask_rows=extra["mask_rows"], mask_shape=extra["mask_shape"])
+        assert torch.equal(out2["pred_masks"], out["pred_masks"])

@@ -32,9 +32,9 @@ with torch.no_grad():
         ev[0].record()
         feats = enc(x)
         ev[1].record()
-        mask_features, multi = dec(feats)
+        _, multi, extra = dec(feats, rows_out=True)
         ev[2].record()
-        out = path(multi, mask_features)
+        out = path(multi, None, mask_rows=extra["mask_rows"], mask_shape=extra["mask_shape"])
         ev[3].record()
         torch.cuda.synchronize()
     t = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
