@@ -109,3 +109,47 @@ def test_flops_per_image_match_survey():
     # 0.98682 / 2.92971 / 5.78735 TFLOP
     for k, v in (("vit_b", 0.98682e12), ("vit_l", 2.92971e12), ("vit_h", 5.78735e12)):
         assert abs(ib.PRESETS[k].flops_per_image() / v - 1) < 1e-5
+
+
+def test_decoder_side_drop_ins_load_reference_state_dicts_and_refuse_cpu():
+    """Host logic of the rows N1 / N4 drop-ins without a GPU: the reference's state_dict keys load with strict=True (fixtures written by
+    the unmodified reference classes) and a CPU call raises instead of falling back."""
+    import os
+    import numpy as np
+    import pytest
+    import torch
+    from iuvl_b200.mask_head import CrossAttentionLayer, FFNLayer, MaskPredictionHead, SelfAttentionLayer, XDecoderMaskPath
+    from tests.util import GOLDEN
+
+    def sd_of(z, prefix):
+        return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
+
+    z = np.load(os.path.join(GOLDEN, "cross_attn_small.npz"))
+    C, NH = (int(v) for v in z["meta"])
+    layer = CrossAttentionLayer(C, NH)
+    layer.load_state_dict(sd_of(z, "sd."), strict=True)
+    with pytest.raises(RuntimeError), torch.no_grad():
+        layer(torch.from_numpy(z["tgt"]), torch.from_numpy(z["memory"]))
+    z = np.load(os.path.join(GOLDEN, "decoder_layers_small.npz"))
+    C, NH, FF = (int(v) for v in z["meta"])
+    sa, ffn = SelfAttentionLayer(C, NH), FFNLayer(C, FF)
+    sa.load_state_dict(sd_of(z, "sa."), strict=True)
+    ffn.load_state_dict(sd_of(z, "ffn."), strict=True)
+    with pytest.raises(RuntimeError), torch.no_grad():
+        ffn(torch.from_numpy(z["tgt"]))
+    z = np.load(os.path.join(GOLDEN, "mask_head_small.npz"))
+    C, MD, Q, NH, th, tw = (int(v) for v in z["meta"])
+    head = MaskPredictionHead(C, MD, Q, NH)
+    head.load_state_dict(sd_of(z, "sd."), strict=True)
+    with pytest.raises(RuntimeError), torch.no_grad():
+        head(torch.from_numpy(z["output"]), torch.from_numpy(z["mask_features"]), (th, tw))
+    z = np.load(os.path.join(GOLDEN, "xdecoder_mask_path_small.npz"))
+    C, MD, Q, NH, FF, NL = (int(v) for v in z["meta"])
+    path = XDecoderMaskPath(C, MD, Q, NH, FF, 3, [0, 1, 2, 0, 1, 2, 0, 1, 2][:NL])
+    path.load_state_dict(sd_of(z, "sd."), strict=True)
+    assert set(path.state_dict().keys()) == set(sd_of(z, "sd.").keys())
+    with pytest.raises(RuntimeError), torch.no_grad():
+        path([torch.from_numpy(z[f"x{i}"]) for i in range(3)], torch.from_numpy(z["mask_features"]))
+    # autograd-enabled calls are refused as well (forward only)
+    with pytest.raises(RuntimeError):
+        head(torch.from_numpy(z["x0"]).requires_grad_(), torch.from_numpy(z["mask_features"]), (4, 4))
