@@ -1612,7 +1612,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
                  : "memory");
 }
 
-template <int HD, bool POLY>
+template <int HD, bool POLY, bool PH>
 __global__ void __launch_bounds__(384, 1)
 attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
                               long long* __restrict__ phase_clocks) {
@@ -1787,8 +1787,8 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
         const uint32_t s_tmem = tmem + lane_off + 208 * i;
         const uint32_t o_tmem = s_tmem + 112;
         long long pc[6] = {0, 0, 0, 0, 0, 0};
-        long long tprev = phase_clocks ? clock64() : 0;
-#define SVB_PHASE(k) if (phase_clocks) { const long long tnow = clock64(); pc[k] += tnow - tprev; tprev = tnow; }
+        long long tprev = (PH && phase_clocks) ? clock64() : 0;
+#define SVB_PHASE(k) if (PH && phase_clocks) { const long long tnow = clock64(); pc[k] += tnow - tprev; tprev = tnow; }
 
         // rel-pos products of the item whose bias MMA is `ph`-th for this tile -> the row's 14 + 14 terms (log2 units)
         float bhm[14], bwl[14];
@@ -1892,7 +1892,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ++n;
         }
 #undef SVB_PHASE
-        if (phase_clocks && w4 == 0 && lane == 0) {
+        if (PH && phase_clocks && w4 == 0 && lane == 0) {
             for (int k = 0; k < 6; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
             atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)n);
         }
@@ -2100,8 +2100,9 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
@@ -2110,8 +2111,11 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = items < sms ? items : sms;
-    if (exp2_poly(true)) attn_window_persistent_kernel<HD, true><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
-    else attn_window_persistent_kernel<HD, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    // the phase-clock instrumentation is its own instantiation: dormant run-time branches in the hot loop are not free (the same
+    // lesson as the global kernel's removed ping-pong option)
+    if (p.phase_clocks) attn_window_persistent_kernel<HD, true, true><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
+    else if (exp2_poly(true)) attn_window_persistent_kernel<HD, true, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, nullptr);
+    else attn_window_persistent_kernel<HD, false, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, nullptr);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
