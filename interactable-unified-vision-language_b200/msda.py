@@ -6,9 +6,13 @@ the C ABI (``svb_ms_deform_attn_forward``).  Forward only; CUDA tensors only; no
 """
 from __future__ import annotations
 
+import copy
+import ctypes
 import ctypes as C
+import math
 
 import torch
+from torch import nn
 
 from . import cabi
 
@@ -45,11 +49,6 @@ def ms_deform_attn_forward(value: torch.Tensor, value_spatial_shapes: torch.Tens
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-import ctypes  # noqa: E402
-import math  # noqa: E402
-
-from torch import nn  # noqa: E402
-
 
 class MSDeformAttn(nn.Module):
     """Drop-in for the reference's ``MSDeformAttn`` module (``ops/modules/ms_deform_attn.py:35-125``): same constructor, same
@@ -173,8 +172,6 @@ class MSDeformAttn(nn.Module):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # The encoder around the module (scope row N1, widened to its caller): transformer_encoder_deform.py:23-161
-import copy  # noqa: E402
-
 
 def _layernorm(x, add, ln, out):
     """x (rows, dim) fp32, updated in place to x + add when ``add`` is given; out = LayerNorm(x) (fp32)."""
