@@ -320,3 +320,33 @@ def test_xdecoder_mask_path_oracle_against_reference_goldens(case):
     masks = mo.xdecoder_mask_path({k: v.double() for k, v in sd.items()}, [t.double() for t in x], mf.double(), Q, NH, [0, 1, 2, 0, 1, 2, 0, 1, 2][:NL])
     assert ib.rel_l2(masks[0], torch.from_numpy(z["aux0"]) if "aux0" in z.files else masks[0]) < 1e-5
     assert ib.rel_l2(masks[-1], torch.from_numpy(z["pred_masks"])) < 2e-3
+
+
+def test_mask_head_oracle_properties():
+    """Size-independent properties of the row-N4 oracles: the antialiased filter preserves constants and is the identity at scale 1;
+    an all-False attention mask equals no mask; a fully masked key range leaves the output independent of those keys."""
+    from oracle import mask_head_oracle as mo
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 19, 23, generator=g, dtype=torch.float64)
+    assert float((mo.resize_bicubic_aa(torch.full((1, 17, 31), 2.5, dtype=torch.float64), (5, 7)) - 2.5).abs().max()) < 1e-12
+    assert float((mo.resize_bicubic_aa(x, (19, 23)) - x).abs().max()) < 1e-12
+    for n_in, n_out in ((256, 32), (40, 10), (24, 12), (9, 16)):
+        w = mo.aa_weights(n_in, n_out)
+        assert float((w.sum(1) - 1).abs().max()) < 1e-12
+    C, NH, Q, B, HW = 128, 2, 5, 2, 12
+    sd = {"multihead_attn.in_proj_weight": torch.randn(3 * C, C, generator=g, dtype=torch.float64) * 0.1,
+          "multihead_attn.in_proj_bias": torch.randn(3 * C, generator=g, dtype=torch.float64) * 0.1,
+          "multihead_attn.out_proj.weight": torch.randn(C, C, generator=g, dtype=torch.float64) * 0.1,
+          "multihead_attn.out_proj.bias": torch.randn(C, generator=g, dtype=torch.float64) * 0.1,
+          "norm.weight": torch.ones(C, dtype=torch.float64), "norm.bias": torch.zeros(C, dtype=torch.float64)}
+    tgt, mem = torch.randn(Q, B, C, generator=g, dtype=torch.float64), torch.randn(HW, B, C, generator=g, dtype=torch.float64)
+    none = mo.cross_attention_layer(sd, tgt, mem, None, None, None, NH)
+    allf = mo.cross_attention_layer(sd, tgt, mem, torch.zeros(B * NH, Q, HW, dtype=torch.bool), None, None, NH)
+    assert torch.equal(none, allf)
+    mask = torch.zeros(B * NH, Q, HW, dtype=torch.bool)
+    mask[:, :, 6:] = True
+    mem2 = mem.clone()
+    mem2[6:] = torch.randn(HW - 6, B, C, generator=g, dtype=torch.float64)
+    a = mo.cross_attention_layer(sd, tgt, mem, mask, None, None, NH)
+    b = mo.cross_attention_layer(sd, tgt, mem2, mask, None, None, NH)
+    assert float((a - b).abs().max()) < 1e-12
