@@ -102,32 +102,60 @@ class ClockSampler:
         return out
 
 
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")      # unmodified copy of the reference's sam/ package (git-ignored; made by build())
+
+
+def reference_encoder(model, torch):
+    """The reference's own CPU implementation of the path: `sam.build_sam.sam_model_registry[...]().image_encoder` imported from the
+    UNMODIFIED copy of its `sam/` package under oracle/_ref (`__graft_entry__.build()` copies it from /root/reference when that
+    exists; it travels to the GPU box like the built .so).  Returns (callable(sd, x) -> outputs, kind)."""
+    import iuvl_b200 as ib
+    cfg = ib.PRESETS[model]
+    if os.path.exists(os.path.join(REF_DIR, "sam", "build_sam.py")):
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from sam.build_sam import sam_model_registry          # the reference's public factory (sam/build_sam.py:108-112)
+        enc = sam_model_registry[model](checkpoint=None).image_encoder.eval()
+        state = {"loaded": False}
+
+        def run(sd, x):
+            if not state["loaded"]:
+                enc.load_state_dict(sd, strict=True)
+                state["loaded"] = True
+            with torch.no_grad():
+                return enc(x)
+        return run, "reference"
+    from oracle import sam_vit_oracle as orc                   # the restatement (kind "port") when the copy is absent
+    return (lambda sd, x: orc.encoder_forward_cfg(sd, x, cfg)), "port"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm (oracle port; the reference itself is Python and /root/reference does
-    not exist on the GPU box) on the host CPU with all threads.  Each step = ONE ViT-H image (bounded sample)."""
+    """--impl reference: the reference's own encoder (unmodified sam/ package from oracle/_ref; the oracle port only if that copy
+    is absent) on the host CPU with all threads.  Each step = ONE image of the workload (bounded sample)."""
     if rank != 0:
         return
     import torch
     import iuvl_b200 as ib
-    from oracle import sam_vit_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = ib.PRESETS[args.model]
     sd = ib.make_state_dict(cfg, 1234)
     x = ib.make_images(1, cfg, 0)
+    fwd, kind = reference_encoder(args.model, torch)
     for _ in range(args.warmup):
-        orc.encoder_forward_cfg(sd, x, cfg)
+        fwd(sd, x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.encoder_forward_cfg(sd, x, cfg)
+        fwd(sd, x)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     v = 1.0 / dt
-    sample = f"1 image of the {args.model} workload per step, fp32, torch CPU ops, {torch.get_num_threads()} threads"
+    what = "unmodified reference ImageEncoderViT (oracle/_ref/sam)" if kind == "reference" else "oracle port"
+    sample = f"1 image of the {args.model} workload per step, fp32, {what}, torch CPU ops, {torch.get_num_threads()} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -262,6 +290,68 @@ def workload_config(args, world):
     }
 
 
+def measure_pipeline(torch, ib, enc, dev, n_img, steps, barrier, max_over_ranks, world):
+    """BASELINE config 5 (step1.yaml): uint8 images -> ViT-H encoder -> MSDeformAttn pixel decoder -> X-Decoder mask path
+    (XdecoderHead.forward, modeling/body/xdecoder_head.py:55-58) on this rank's shard of `n_img` images; device-resident
+    (CUDA events, max over ranks) and end to end (pinned host uint8 in, pinned host masks out)."""
+    from iuvl_b200.mask_head import XDecoderMaskPath
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    dec = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024, transformer_enc_layers=6,
+                                   conv_dim=512, mask_dim=512, norm="GN").to(dev).eval()
+    path = XDecoderMaskPath(512, 512, 101, 8, 2048).to(dev).eval()
+    mean, std = [123.675, 116.280, 103.530], [58.395, 57.120, 57.375]                 # configs/step1.yaml:320-321
+    g = torch.Generator().manual_seed(77)
+    host = torch.randint(0, 256, (n_img, 3, 1024, 1024), generator=g, dtype=torch.uint8).pin_memory()
+    x_dev = host.to(dev)
+    old = (enc.out_dtype, enc.max_chunk)
+    enc.out_dtype, enc.max_chunk = torch.bfloat16, 16
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    with torch.no_grad():
+        for layer in dec.transformer.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.05)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+
+        def run(xd):
+            ev[0].record()
+            feats = enc.forward_uint8(list(xd), mean, std)
+            ev[1].record()
+            _, multi, extra = dec(feats, rows_out=True)
+            ev[2].record()
+            out = path(multi, None, mask_rows=extra["mask_rows"], mask_shape=extra["mask_shape"])
+            ev[3].record()
+            return out
+        for _ in range(2):
+            out = run(x_dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = run(x_dev)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        stage = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+        masks_host = torch.empty(out["pred_masks"].shape, dtype=out["pred_masks"].dtype).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            xd = host.to(dev, non_blocking=True)
+            out = run(xd)
+            masks_host.copy_(out["pred_masks"], non_blocking=True)
+            torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / steps)
+    enc.out_dtype, enc.max_chunk = old
+    rec = {"workload": "BASELINE configs[4] (step1.yaml): uint8 1024^2 images -> ViT-H encoder -> MSDeformAttn pixel decoder (conv_dim 512, 6 layers) "
+                       "-> X-Decoder mask path (9 layers, 101 queries), %d images per GPU, bf16 hand-overs" % n_img,
+           "images_per_gpu": n_img, "global_batch": n_img * world, "value": world * n_img / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+           "stage_ms_rank0": {"encoder": stage[0], "pixel_decoder": stage[1], "mask_path": stage[2]},
+           "e2e": {"value": world * n_img / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(host.numel()),
+                   "d2h_bytes_per_step": int(masks_host.numel() * masks_host.element_size())},
+           "pred_masks": list(out["pred_masks"].shape)}
+    del dec, path, x_dev, host
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,6 +364,7 @@ def main():
     ap.add_argument("--out-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling leg, the ViT-B / ViT-L records, the pipeline and the next-row timings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3   # timing rule: at least 3 warm-up steps
@@ -300,13 +391,20 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = ib.PRESETS[args.model]
-    enc = build_encoder(cfg)
-    enc.load_state_dict(ib.make_state_dict(cfg, 1234))
-    enc.to(dev)
-    enc.precision = "bf16"
-    enc.out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
-    enc.max_chunk = args.chunk
+    pk = peaks()
+    out_dtype = torch.bfloat16 if args.out_dtype == "bf16" else torch.float32
+
+    def make_encoder(model):
+        cfg_ = ib.PRESETS[model]
+        enc_ = build_encoder(cfg_)
+        enc_.load_state_dict(ib.make_state_dict(cfg_, 1234))
+        enc_.to(dev)
+        enc_.precision = "bf16"
+        enc_.out_dtype = out_dtype
+        enc_.max_chunk = args.chunk
+        return cfg_, enc_
+
+    cfg, enc = make_encoder(args.model)
     lib = cabi.lib()
 
     B = args.batch
@@ -328,6 +426,38 @@ def main():
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def timed(enc_, x, steps, warmup):
+        """ms per step of `steps` forwards (device-resident input), barrier + synchronize on both sides, max over ranks"""
+        with torch.no_grad():
+            for _ in range(warmup):
+                enc_(x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                enc_(x)
+            e1.record()
+            barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def timed_e2e(enc_, cfg_, xh, steps):
+        """the same metric through the host-buffer C-ABI call: H2D + forward + D2H per step, host clock, max over ranks"""
+        nb = xh.shape[0]
+        out_host = {f"res{k + 2}": torch.empty(nb, cfg_.fpn_dims[k], cfg_.img_size // s_, cfg_.img_size // s_, dtype=enc_.out_dtype).pin_memory()
+                    for k, s_ in enumerate((4, 8, 16, 32))}
+        with torch.no_grad():
+            enc_.forward_host(xh, out_host)          # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                enc_.forward_host(xh, out_host)       # synchronous: returns after the D2H copies completed
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / steps
+        dt = max_over_ranks(dt)
+        return {"value": world * nb / dt, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 4),
+                "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host.values())),
+                "ms_per_step": dt * 1e3, "steps": steps, "timer": "host perf_counter around the synchronous C-ABI call, max over ranks"}
 
     # ---------------- device-resident throughput (`value`): clean timed region, no per-launch events ----------------
     sampler = ClockSampler(local_rank) if rank == 0 else None     # started before the warm-up: nvidia-smi needs time to spin up
@@ -363,40 +493,48 @@ def main():
     value = world * B / (ms_step * 1e-3)
 
     # ---------------- end to end through the host-buffer C-ABI call ----------------
-    e2e = None
-    if not args.no_e2e:
-        out_host = {f"res{k + 2}": torch.empty(B, cfg.fpn_dims[k], cfg.img_size // s, cfg.img_size // s,
-                                               dtype=enc.out_dtype).pin_memory()
-                    for k, s in enumerate((4, 8, 16, 32))}
-        with torch.no_grad():
-            enc.forward_host(x_host, out_host)          # warm-up (allocates the staging buffers)
-            barrier()
-            t0 = time.perf_counter()
-            n_e2e = max(1, min(args.steps, 3))
-            for _ in range(n_e2e):
-                enc.forward_host(x_host, out_host)       # synchronous: returns after the D2H copies completed
-            torch.cuda.synchronize()
-            dt = (time.perf_counter() - t0) / n_e2e
-        dt = max_over_ranks(dt)
-        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
-               "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host.values())),
-               "ms_per_step": dt * 1e3, "steps": n_e2e, "timer": "host perf_counter around the synchronous C-ABI call, max over ranks"}
+    e2e = None if args.no_e2e else timed_e2e(enc, cfg, x_host, max(10, min(args.steps, 20)))
+
+    # ---------------- strong scaling (BASELINE configs[3]: ONE global batch of `batch` images split over the GPUs) ----------------
+    strong = None
+    if not args.no_extras:
+        per = max(1, B // world)
+        if world == 1:
+            strong = {"global_batch": B, "per_gpu_batch": B, "value": value, "ms_per_step": ms_step,
+                      "e2e": e2e["value"] if e2e else None, "note": "identical to the headline at one GPU"}
+        else:
+            ms_s = timed(enc, x_dev[:per], args.steps, 3)
+            e2e_s = None if args.no_e2e else timed_e2e(enc, cfg, x_host[:per], max(10, min(args.steps, 20)))
+            strong = {"global_batch": per * world, "per_gpu_batch": per, "value": world * per / (ms_s * 1e-3), "ms_per_step": ms_s,
+                      "steps": args.steps, "e2e": e2e_s["value"] if e2e_s else None,
+                      "whole_encoder_frac_of_sustained": per / (ms_s * 1e-3) * cfg.flops_per_image() / 1e12 / pk["bf16_sustained"]}
+
+    # ---------------- BASELINE configs[4] as a pipeline record: encoder -> pixel decoder -> mask path, 16 images per GPU ----------------
+    pipeline = None
+    if not args.no_extras and args.model == "vit_h":
+        try:
+            pipeline = measure_pipeline(torch, ib, enc, dev, 16, max(3, min(args.steps, 5)), barrier, max_over_ranks, world)
+        except Exception as e:  # noqa: BLE001  (never lose the headline line over an extra)
+            pipeline = {"error": str(e)[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
     flops_img = cfg.flops_per_image()
     gemm_tflops = (fl5[0] / (ms5[0] * 1e-3) / 1e12) if ms5[0] > 0 else None
     n_gemm = ln5[0]
+    whole_tf = value / world * flops_img / 1e12
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc2s_kernel (CTA-pair tcgen05 GEMM: all linears + patch-embed + neck convs)",
         "achieved": gemm_tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
         "frac": (gemm_tflops / pk["bf16_sustained"]) if gemm_tflops else None,
         "frac_of_burst": (gemm_tflops / pk["bf16_burst"]) if gemm_tflops else None,
-        "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+        # the number the metric asks for: the WHOLE encoder step (all kernels) against the dense bf16 roofline
+        "whole_encoder_tflops": whole_tf, "whole_encoder_frac": whole_tf / pk["bf16_sustained"],
+        "whole_encoder_frac_of_burst": whole_tf / pk["bf16_burst"], "flops_per_image": flops_img,
+        "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step); burst = %.1f" % pk["bf16_burst"],
         "launches": int(n_gemm), "avg_launch_ms": (ms5[0] / n_gemm) if n_gemm else None,
         "flops_per_launch_avg": (fl5[0] / n_gemm) if n_gemm else None,
         "traffic": traffic_per_launch(args.model),
@@ -407,34 +545,67 @@ def main():
                               "tflops": (fl5[i] / (ms5[i] * 1e-3) / 1e12) if ms5[i] > 0 and fl5[i] > 0 else None,
                               "gbs": (by5[i] / (ms5[i] * 1e-3) / 1e9) if ms5[i] > 0 and by5[i] > 0 else None}
                        for i, name in enumerate(("gemm", "attn_windowed", "attn_global", "norms", "other"))},
-        "whole_step": {"tflops": value / world * flops_img / 1e12, "frac_of_sustained": value / world * flops_img / 1e12 / pk["bf16_sustained"],
-                       "frac_of_burst": value / world * flops_img / 1e12 / pk["bf16_burst"], "flops_per_image": flops_img},
+        "whole_step": {"tflops": whole_tf, "frac_of_sustained": whole_tf / pk["bf16_sustained"],
+                       "frac_of_burst": whole_tf / pk["bf16_burst"], "flops_per_image": flops_img},
     }
+
+    # ---------------- BASELINE configs[1] / [2] on this GPU: ViT-B batch 16, ViT-L batch 32 (single-GPU records) ----------------
+    other_configs = None
+    if not args.no_extras and world == 1 and args.model == "vit_h":
+        other_configs = {}
+        del x_dev
+        for model, nb in (("vit_b", 16), ("vit_l", 32)):
+            try:
+                c2, e2 = make_encoder(model)
+                xs = x_host[:nb].to(dev)
+                ms2 = timed(e2, xs, max(5, args.steps), 3)
+                v2 = nb / (ms2 * 1e-3)
+                ee = None if args.no_e2e else timed_e2e(e2, c2, x_host[:nb], 10)
+                other_configs[f"{model}_b{nb}"] = {
+                    "workload": "SAM %s image-encoder forward, batch %d, bf16 (BASELINE.json configs[%d])" % (model, nb, 1 if model == "vit_b" else 2),
+                    "value": v2, "unit": UNIT, "ms_per_step": ms2, "e2e": ee["value"] if ee else None,
+                    "whole_encoder_tflops": v2 * c2.flops_per_image() / 1e12,
+                    "whole_encoder_frac": v2 * c2.flops_per_image() / 1e12 / pk["bf16_sustained"],
+                    "whole_encoder_frac_of_burst": v2 * c2.flops_per_image() / 1e12 / pk["bf16_burst"]}
+                del e2, xs
+            except Exception as e:  # noqa: BLE001
+                other_configs[f"{model}_b{nb}"] = {"error": str(e)[:300]}
 
     # ---------------- the "next" rows of the scope table: kernel-alone timings, for the record ----------------
     next_rows = None
-    try:
-        next_rows = measure_next_rows(torch, cabi, dev, pk)
-    except Exception as e:  # noqa: BLE001  (never lose the headline line over an extra)
-        next_rows = {"error": str(e)[:200]}
+    if not args.no_extras:
+        try:
+            next_rows = measure_next_rows(torch, cabi, dev, pk)
+        except Exception as e:  # noqa: BLE001  (never lose the headline line over an extra)
+            next_rows = {"error": str(e)[:200]}
+        if pipeline is not None:
+            next_rows = dict(next_rows or {})
+            next_rows["pipeline"] = pipeline
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        from oracle import sam_vit_oracle as orc       # the checker, timed as the reported CPU baseline (kind "port")
+        # the reference's own CPU encoder (or the oracle port when oracle/_ref is absent): 1 warm-up pass, median of 3 timed passes
         torch.set_num_threads(os.cpu_count() or 1)
+        fwd, kind = reference_encoder(args.model, torch)
         sd = ib.make_state_dict(cfg, 1234)
         x1 = x_host[:1].clone()
-        t0 = time.perf_counter()
-        orc.encoder_forward_cfg(sd, x1, cfg)
-        dt_cpu = time.perf_counter() - t0
-        cpu_baseline = {"value": 1.0 / dt_cpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"1 image of the same workload ({args.model}, fp32, torch CPU ops), single cold pass of {dt_cpu:.1f} s"}
+        fwd(sd, x1)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fwd(sd, x1)
+            ts.append(time.perf_counter() - t0)
+        dt_cpu = sorted(ts)[1]
+        cpu_baseline = {"value": 1.0 / dt_cpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                        "sample": f"1 image of the same workload ({args.model}, fp32, torch CPU ops), 1 warm-up + median of 3 passes "
+                                  f"({', '.join('%.1f' % t for t in ts)} s)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "next_rows": next_rows,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "strong": strong, "configs": other_configs,
+        "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

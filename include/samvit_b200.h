@@ -23,7 +23,7 @@ typedef void* svb_stream_t; /* cudaStream_t */
 
 enum { SVB_MODE_BF16 = 0,      /* bf16 operands on tcgen05 tensor cores, fp32 accumulate / residual / norms  */
        SVB_MODE_FP32 = 1 };    /* validation mode: fp32 operands, fp32 FMA accumulate (1e-4 rel-L2 bar)       */
-enum { SVB_DTYPE_F32 = 0, SVB_DTYPE_BF16 = 1 };
+enum { SVB_DTYPE_F32 = 0, SVB_DTYPE_BF16 = 1, SVB_DTYPE_F16 = 2 /* inputs only */ };
 
 /* Constructor arguments of ImageEncoderViT (image_encoder.py:18-36) as fixed by _build_sam (build_sam.py:60-73). */
 typedef struct svb_config {
@@ -75,6 +75,13 @@ int svb_encoder_forward(svb_encoder_t* enc, const float* x, int batch, void* res
 size_t svb_encoder_workspace_bytes_hw(const svb_encoder_t* enc, int chunk, int mode, int img_h, int img_w);
 int svb_encoder_forward_hw(svb_encoder_t* enc, const float* x, int batch, int img_h, int img_w, void* res2, void* res3, void* res4,
                            void* res5, int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream);
+/* The same forward for an input tensor of dtype `x_dtype` (SVB_DTYPE_F32 / _BF16 / _F16): the reference's pipeline hands the encoder
+ * fp16 images after cast_batch_to_half (pipeline/XDecoderPipeline.py:93-95); the cast to the GEMM operand type happens in the
+ * patch-embedding loader, no fp32 copy of the batch is made.  img_h x img_w as in svb_encoder_forward_hw (img_size x img_size takes
+ * the same passes as svb_encoder_forward). */
+int svb_encoder_forward_x(svb_encoder_t* enc, const void* x, int x_dtype, int batch, int img_h, int img_w, void* res2, void* res3,
+                          void* res4, void* res5, int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes,
+                          svb_stream_t stream);
 /* The two table fallbacks alone (device pointers, fp32): F.interpolate(pos_embed, mode='bicubic') (h0,w0,dim)->(h1,w1,dim);
  * F.interpolate(rel_pos, mode='linear') (len0,head_dim)->(len1,head_dim). */
 int svb_resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int dim, svb_stream_t stream);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsamvit_b200.so")
 
 MODE_BF16, MODE_FP32 = 0, 1
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 
 
 class SvbConfig(C.Structure):
@@ -38,6 +38,7 @@ SYMBOLS = {
     "svb_encoder_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "svb_encoder_workspace_bytes_hw": (_sz, [_vp, _i, _i, _i, _i]),
     "svb_encoder_forward_hw": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "svb_encoder_forward_x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "svb_resize_pos_embed": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "svb_resize_rel_pos": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_encoder_forward_u8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),

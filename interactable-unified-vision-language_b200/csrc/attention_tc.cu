@@ -187,342 +187,6 @@ template <int HD, int NST_> struct GCfg {
     static constexpr int TM_S = 0, TM_O = 256, TM_COLS = 512;   // S_i at 128*i (P_i aliases its first 64), O_i at 256 + 128*i
 };
 
-// ONEPASS: from the second key tile on, the softmax reads S from tensor memory ONCE: P = exp2(x - m_ref) with the reference
-// maximum of the previous tiles while the tile's own maximum is tracked alongside; if it exceeds m_ref by more than 2^8, O and the
-// row sum are rescaled at the start of the NEXT tile (P may transiently exceed 2^8, which bf16 / fp32 hold without loss).  The
-// two-pass form (maximum first) remains for the first tile and as the A/B variant.
-template <int HD, int NST, bool ONEPASS, bool PH = false>
-// 10 warps are allocated as 12 (warp allocation granularity 4): the register cap is 65536 / 384 = 168 per thread
-__global__ void __launch_bounds__(320, 1)
-attn_global_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
-                   const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
-                   const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
-                   bf16* __restrict__ out, int D, int T, float scale_log2, long long* __restrict__ phase_clocks) {
-    using C = GCfg<HD, NST>;
-    constexpr int NKT = 32;                                     // 4096 keys / 128
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-    const int row0 = b * T + pair * 256;
-    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
-
-    if (warp == 8 && lane == 0) {
-        ptx::prefetch_tmap(&tm_main);
-        ptx::prefetch_tmap(&tm_rw_main);
-        ptx::prefetch_tmap(&tm_rh_main);
-        if (HD > 64) { ptx::prefetch_tmap(&tm_tail); ptx::prefetch_tmap(&tm_rw_tail); ptx::prefetch_tmap(&tm_rh_tail); }
-        ptx::mbar_init(&bars[C::B_QFULL], 1);
-        ptx::mbar_init(&bars[C::B_BIAS], 1);
-        for (int s = 0; s < NST; ++s) {
-            ptx::mbar_init(&bars[C::B_KFULL + s], 1);
-            ptx::mbar_init(&bars[C::B_KEMPTY + s], 1);
-            ptx::mbar_init(&bars[C::B_VFULL + s], 1);
-            ptx::mbar_init(&bars[C::B_VEMPTY + s], 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&bars[C::B_SFULL + i], 1);
-            ptx::mbar_init(&bars[C::B_PFULL + i], 128);
-            ptx::mbar_init(&bars[C::B_PVDONE + i], 1);
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 9) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 8) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::Q_TX);
-            for (int i = 0; i < 2; ++i) {
-                ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE, &tm_main, &bars[C::B_QFULL], colq, row0 + 128 * i);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_QFULL], colq + 64, row0 + 128 * i);
-            }
-            ptx::tma_load_2d(sm + C::OFF_RW, &tm_rw_main, &bars[C::B_QFULL], 0, 144);
-            ptx::tma_load_2d(sm + C::OFF_RH, &tm_rh_main, &bars[C::B_QFULL], 0, 4 * pair);
-            if (HD > 64) {
-                ptx::tma_load_2d(sm + C::OFF_RW + C::T_MAIN, &tm_rw_tail, &bars[C::B_QFULL], 64, 144);
-                ptx::tma_load_2d(sm + C::OFF_RH + C::RH_MAIN, &tm_rh_tail, &bars[C::B_QFULL], 64, 4 * pair);
-            }
-            for (int j = 0; j < NKT; ++j) {
-                const int st = j % NST;
-                const uint32_t par = ((j / NST) & 1) ^ 1;
-                const int krow = b * T + j * 128;
-                ptx::mbar_wait(&bars[C::B_KEMPTY + st], par);
-                ptx::mbar_expect_tx(&bars[C::B_KFULL + st], C::KV_TX);
-                ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
-                ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
-                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
-                ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE + C::T_MAIN, &tm_main, &bars[C::B_VFULL + st], colv + 64, krow);
-            }
-        }
-    } else if (warp == 9) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t id_rh = ptx::make_idesc_bf16(128, 80, 0, 0);
-            const uint32_t q_main[2] = {base + C::OFF_Q, base + C::OFF_Q + C::TILE};
-            const uint32_t q_tail[2] = {q_main[0] + C::T_MAIN, q_main[1] + C::T_MAIN};
-            ptx::mbar_wait(&bars[C::B_QFULL], 0);
-            ptx::tc_fence_after();
-            // decomposed rel-pos products: Q.Rw^T -> S_i columns, Q.Rh[4*pair ..]^T -> O_i columns
-            for (int i = 0; i < 2; ++i)
-                issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_s);
-            for (int i = 0; i < 2; ++i)
-                issue_qk<HD>(tmem + C::TM_O + 128 * i, q_main[i], q_tail[i], base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
-            ptx::mma_commit(&bars[C::B_BIAS]);
-            // S_i(0)
-            ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
-            for (int i = 0; i < 2; ++i) {
-                ptx::mbar_wait(&bars[C::B_PFULL + i], 0);          // bias products consumed: S_i / O_i columns are free
-                ptx::tc_fence_after();
-                issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_K, base + C::OFF_K + C::T_MAIN, id_s);
-                ptx::mma_commit(&bars[C::B_SFULL + i]);
-            }
-            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
-            long long ipc[3] = {0, 0, 0};
-            long long itp = PH ? clock64() : 0;
-#define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
-            for (int j = 0; j < NKT; ++j) {
-                const int st = j % NST, nst = (j + 1) % NST;
-                const bool more = (j + 1 < NKT);
-                SVB_IPH(2)
-                ptx::mbar_wait(&bars[C::B_VFULL + st], (j / NST) & 1);
-                if (more) ptx::mbar_wait(&bars[C::B_KFULL + nst], ((j + 1) / NST) & 1);
-                SVB_IPH(0)
-                for (int i = 0; i < 2; ++i) {
-                    ptx::mbar_wait(&bars[C::B_PFULL + i], (j + 1) & 1);   // P_i(j) is in TMEM
-                    SVB_IPH(1)
-                    ptx::tc_fence_after();
-                    issue_pv_wide<HD>(tmem + C::TM_O + 128 * i, tmem + C::TM_S + 128 * i, base + C::OFF_V + st * C::VTILE, C::T_MAIN, 8, j > 0);
-                    ptx::mma_commit(&bars[C::B_PVDONE + i]);
-                    if (i == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
-                    if (more) {
-                        // in-order execution on the tensor pipe: this overwrite of S_i / P_i follows the PV above
-                        issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main[i], q_tail[i], base + C::OFF_K + nst * C::TILE,
-                                     base + C::OFF_K + nst * C::TILE + C::T_MAIN, id_s);
-                        ptx::mma_commit(&bars[C::B_SFULL + i]);
-                        if (i == 1) ptx::mma_commit(&bars[C::B_KEMPTY + nst]);
-                    }
-                }
-            }
-#undef SVB_IPH
-            if (PH && phase_clocks) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
-            }
-        }
-    } else {
-        // ===================== softmax warps: 2 groups of 128 query rows =====================
-        const int i = warp >> 2;                                   // query tile of this warp group
-        const int w4 = warp & 3;                                   // TMEM lane quadrant
-        const int t = w4 * 32 + lane;                              // query row inside the tile
-        const int qr = 2 * i + (t >> 6);                           // grid row of the query inside the CTA (0..3), warp-uniform
-        const int qw = t & 63;                                     // grid column of the query
-        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
-        const uint32_t s_tmem = tmem + lane_off + C::TM_S + 128 * i;
-        const uint32_t o_tmem = tmem + lane_off + C::TM_O + 128 * i;
-        float* stg = reinterpret_cast<float*>(sm + C::OFF_STG + warp * 8192);   // [64][32] fp32, private to this warp
-
-        // ---- rel-pos prologue: w term into registers, h term into this warp's smem column block ----
-        float bwl[64];
-        ptx::mbar_wait(&bars[C::B_BIAS], 0);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t v[32];
-                ptx::tmem_ld_x32(s_tmem + 64 * p + 32 * h, v);
-                ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) stg[(32 * h + e) * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int kw = 0; kw < 64; ++kw) {
-                const int c = qw + 63 - kw;                        // table row qw - kw + 63
-                if ((c >> 6) == p) bwl[kw] = stg[(c & 63) * 32 + lane];
-            }
-            __syncwarp();
-        }
-        float bwmax = bwl[0];
-#pragma unroll
-        for (int kw = 1; kw < 64; ++kw) bwmax = fmaxf(bwmax, bwl[kw]);
-        {
-            // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
-            uint32_t v[32];
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                ptx::tmem_ld_x32(o_tmem + c0, v);
-                ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int kh = qr + 63 - (c0 + e);
-                    if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
-                }
-            }
-            uint32_t w[16];
-            ptx::tmem_ld_x16(o_tmem + 64, w);
-            ptx::tmem_ld_wait_dep(w);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int kh = qr + 63 - (64 + e);
-                if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(w[e]) * LOG2E;
-            }
-        }
-        __syncwarp();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars[C::B_PFULL + i]);                   // phase 0: S_i / O_i columns may be overwritten
-
-        float m_ref = -INFINITY;
-        float x_over = 0.f;                                          // ONEPASS: previous tile's maximum exponent relative to m_ref
-        f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
-        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
-        long long pc[3] = {0, 0, 0};
-        long long tprev = PH ? clock64() : 0;
-#define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
-#pragma unroll 1
-        for (int j = 0; j < NKT; ++j) {
-            SVB_GPH(1)
-            ptx::mbar_wait(&bars[C::B_SFULL + i], j & 1);
-            SVB_GPH(0)
-            ptx::tc_fence_after();
-            const float bh0 = stg[(2 * j) * 32 + lane], bh1 = stg[(2 * j + 1) * 32 + lane];
-            uint32_t va[32], vb[32];
-            float m_new;
-            bool need;
-            if (!ONEPASS || j == 0) {
-                // ---- pass A: raw maxima of the two key rows ----
-                ptx::tmem_ld_x32(s_tmem, va);
-                ptx::tmem_ld_wait_dep(va);
-                ptx::tmem_ld_x32(s_tmem + 32, vb);
-                float sm0 = max32(va, -INFINITY);
-                ptx::tmem_ld_wait_dep(vb);
-                ptx::tmem_ld_x32(s_tmem + 64, va);
-                sm0 = max32(vb, sm0);
-                ptx::tmem_ld_wait_dep(va);
-                ptx::tmem_ld_x32(s_tmem + 96, vb);
-                float sm1 = max32(va, -INFINITY);
-                ptx::tmem_ld_wait_dep(vb);
-                ptx::tmem_ld_x32(s_tmem, va);                      // first chunk of pass B
-                sm1 = max32(vb, sm1);
-                // upper bound of the row maximum in log2 units (scale > 0)
-                const float mb = fmaxf(fmaf(sm0, scale_log2, bh0), fmaf(sm1, scale_log2, bh1)) + bwmax;
-                need = mb > m_ref + RESCALE_THRESHOLD;             // always true for j == 0
-                m_new = need ? mb : m_ref;
-            } else {
-                ptx::tmem_ld_x32(s_tmem, va);                      // first chunk of the single pass
-                need = x_over > RESCALE_THRESHOLD;                 // the previous tile's maximum relative to m_ref
-                m_new = need ? m_ref + x_over : m_ref;
-            }
-            if (__any_sync(0xffffffffu, need)) {
-                if (j > 0) {
-                    const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
-                    ptx::mbar_wait(&bars[C::B_PVDONE + i], (j - 1) & 1);   // O_i holds tiles 0..j-1
-                    ptx::tc_fence_after();
-                    uint32_t r[32];
-#pragma unroll
-                    for (int c0 = 0; c0 < 64; c0 += 32) {
-                        ptx::tmem_ld_x32(o_tmem + c0, r);
-                        ptx::tmem_ld_wait_dep(r);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                        ptx::tmem_st_x32(o_tmem + c0, r);
-                    }
-                    if (HD > 64) {
-                        uint32_t r2[16];
-                        ptx::tmem_ld_x16(o_tmem + 64, r2);
-                        ptx::tmem_ld_wait_dep(r2);
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) r2[e] = __float_as_uint(__uint_as_float(r2[e]) * alpha);
-                        ptx::tmem_st_x16(o_tmem + 64, r2);
-                    }
-                    const f32x2 al2 = f2_pack(alpha, alpha);
-                    l01 = f2_mul(l01, al2);
-                    l23 = f2_mul(l23, al2);
-                }
-                m_ref = m_new;
-                SVB_GPH(2)
-            }
-            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
-            const f32x2 d0_2 = f2_pack(bh0 - m_ref, bh0 - m_ref), d1_2 = f2_pack(bh1 - m_ref, bh1 - m_ref);
-            // ---- pass B: P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
-#define SVB_PASS_B(V, CHUNK)                                                                             \
-            {                                                                                            \
-                uint32_t pk[16];                                                                         \
-                const f32x2 dd2 = ((CHUNK) < 2) ? d0_2 : d1_2;                                           \
-                _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
-                    const int kw = 32 * ((CHUNK) & 1) + e;                                               \
-                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,         \
-                                                    f2_pack(bwl[kw], bwl[kw + 1])), dd2);                \
-                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e + 2]), __uint_as_float(V[e + 3])), sc2,     \
-                                                    f2_pack(bwl[kw + 2], bwl[kw + 3])), dd2);            \
-                    float a0, a1, a2, a3;                                                                \
-                    f2_unpack(x01, a0, a1);                                                              \
-                    f2_unpack(x23, a2, a3);                                                              \
-                    if (ONEPASS) { xa = fmax3(xa, a0, a1); xb = fmax3(xb, a2, a3); }                      \
-                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
-                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);                      \
-                    l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
-                    l23 = f2_add(l23, f2_pack(p2, p3));                                                  \
-                    pk[e / 2] = pack_bf16x2(p0, p1);                                                     \
-                    pk[e / 2 + 1] = pack_bf16x2(p2, p3);                                                 \
-                }                                                                                        \
-                ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                             \
-            }
-            ptx::tmem_ld_wait_dep(va);
-            ptx::tmem_ld_x32(s_tmem + 32, vb);
-            SVB_PASS_B(va, 0)
-            ptx::tmem_ld_wait_dep(vb);
-            ptx::tmem_ld_x32(s_tmem + 64, va);
-            SVB_PASS_B(vb, 1)
-            ptx::tmem_ld_wait_dep(va);
-            ptx::tmem_ld_x32(s_tmem + 96, vb);
-            SVB_PASS_B(va, 2)
-            ptx::tmem_ld_wait_dep(vb);
-            SVB_PASS_B(vb, 3)
-#undef SVB_PASS_B
-            x_over = fmaxf(xa, xb);
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&bars[C::B_PFULL + i]);
-        }
-        SVB_GPH(1)
-#undef SVB_GPH
-        if (PH && phase_clocks && w4 == 0 && lane == 0) {
-            for (int k = 0; k < 3; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
-            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)NKT);
-        }
-        // ---- epilogue: O / l at the query's own token position ----
-        ptx::mbar_wait(&bars[C::B_PVDONE + i], (NKT - 1) & 1);
-        ptx::tc_fence_after();
-        float l0, l1, l2, l3;
-        f2_unpack(l01, l0, l1);
-        f2_unpack(l23, l2, l3);
-        const float inv = 1.0f / ((l0 + l1) + (l2 + l3));
-        bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD;
-        store_row<HD>(dst, o_tmem, inv);
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem, C::TM_COLS);
-    }
-}
-
 // ================================================================================================================
 //                        GLOBAL ATTENTION, half-tile pipeline (64-key S tiles, double-buffered per query tile)
 // ================================================================================================================
@@ -752,9 +416,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             }
             __syncwarp();
         }
-        float bwmax = bwl[0];
-#pragma unroll
-        for (int kw = 1; kw < 64; ++kw) bwmax = fmaxf(bwmax, bwl[kw]);
         {
             // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
             uint32_t v[32];
@@ -782,7 +443,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
         ptx::mbar_arrive(&bars[C::B_BREAD + i]);                   // S_i / O_i columns may be overwritten
 
         float m_ref = -INFINITY;
-        float x_over = 0.f;                                          // previous tile's maximum exponent relative to m_ref
         f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // row sum, four partial accumulators
         const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
         long long pc[5] = {0, 0, 0, 0, 0};
@@ -815,13 +475,30 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             ptx::tmem_ld_wait_dep(va);
             ptx::tmem_ld_wait_dep(vb);
             SVB_GPH(4)
-            if (h == 0) {
-                const float sm0 = max32(vb, max32(va, -INFINITY));
-                m_new = fmaf(sm0, scale_log2, bh) + bwmax;         // upper bound of the row maximum in log2 units (scale > 0)
-                need = true;
-            } else {
-                need = x_over > RESCALE_THRESHOLD;                 // the previous tile's maximum relative to m_ref
-                m_new = need ? m_ref + x_over : m_ref;
+            // SAFE single pass over tensor memory: the 64 scores are in registers, so the tile's EXACT maximum exponent is known
+            // before the first exponential — pass 1 forms x = s * scale + w term in place and takes its maximum, pass 2 the
+            // exponentials.  The reference maximum moves to it whenever it exceeds the reference by more than 2^8, so P <= 2^8
+            // ALWAYS and no input can overflow exp2, the row sum or O (torch.softmax has no such limit either,
+            // image_encoder.py:246-252); and because the reference is a maximum that was really attained (not a bound built from
+            // the largest bias term), a row cannot underflow as a whole.  Same instruction count as tracking the maximum alongside.
+            f32x2 xa[16], xb[16];
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                xa[e / 2] = f2_fma(f2_pack(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), sc2, f2_pack(bwl[e], bwl[e + 1]));
+                xa[e / 2 + 1] = f2_fma(f2_pack(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), sc2, f2_pack(bwl[e + 2], bwl[e + 3]));
+                xb[e / 2] = f2_fma(f2_pack(__uint_as_float(vb[e]), __uint_as_float(vb[e + 1])), sc2, f2_pack(bwl[32 + e], bwl[33 + e]));
+                xb[e / 2 + 1] = f2_fma(f2_pack(__uint_as_float(vb[e + 2]), __uint_as_float(vb[e + 3])), sc2, f2_pack(bwl[34 + e], bwl[35 + e]));
+                float a0, a1, a2, a3, b0, b1, b2, b3;
+                f2_unpack(xa[e / 2], a0, a1); f2_unpack(xa[e / 2 + 1], a2, a3);
+                f2_unpack(xb[e / 2], b0, b1); f2_unpack(xb[e / 2 + 1], b2, b3);
+                mx0 = fmax3(mx0, a0, a1); mx1 = fmax3(mx1, a2, a3);
+                mx2 = fmax3(mx2, b0, b1); mx3 = fmax3(mx3, b2, b3);
+            }
+            {
+                const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) + bh;     // exact maximum exponent of this tile, log2 units
+                need = (h == 0) || (tmax - m_ref > RESCALE_THRESHOLD);
+                m_new = need ? tmax : m_ref;
             }
             if (__any_sync(0xffffffffu, need)) {
                 if (h > 0) {
@@ -844,23 +521,17 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                 m_ref = m_new;
                 SVB_GPH(2)
             }
-            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
             const f32x2 dd2 = f2_pack(bh - m_ref, bh - m_ref);
-            // ---- P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
-#define SVB_PASS_H(V, CHUNK)                                                                  \
+            // ---- P = exp2(x + h term - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
+#define SVB_PASS_H(X, CHUNK)                                                                  \
             {                                                                                            \
                 uint32_t pk[16];                                                                         \
                 _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                      \
-                    const int kw = 32 * (CHUNK) + e;                                                     \
-                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,         \
-                                                    f2_pack(bwl[kw], bwl[kw + 1])), dd2);                \
-                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e + 2]), __uint_as_float(V[e + 3])), sc2,     \
-                                                    f2_pack(bwl[kw + 2], bwl[kw + 3])), dd2);            \
+                    const f32x2 x01 = f2_add(X[e / 2], dd2);                                             \
+                    const f32x2 x23 = f2_add(X[e / 2 + 1], dd2);                                         \
                     float a0, a1, a2, a3;                                                                \
                     f2_unpack(x01, a0, a1);                                                              \
                     f2_unpack(x23, a2, a3);                                                              \
-                    xa = fmax3(xa, a0, a1);                                                              \
-                    xb = fmax3(xb, a2, a3);                                                              \
                     const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
                     float p2, p3;                                                                        \
                     if (POLY && ((e >> 2) & 1)) exp2_poly_pair(a2, a3, p2, p3);   /* a quarter of the exponentials */ \
@@ -872,10 +543,9 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                 }                                                                                        \
                 ptx::tmem_st_x16(s_h + 16 * (CHUNK), pk);                                                \
             }
-            SVB_PASS_H(va, 0)
-            SVB_PASS_H(vb, 1)
+            SVB_PASS_H(xa, 0)
+            SVB_PASS_H(xb, 1)
 #undef SVB_PASS_H
-            x_over = fmaxf(xa, xb);
             SVB_GPH(1)
         }
         ptx::tmem_st_wait();
@@ -908,429 +578,58 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     }
 }
 
-// ================================================================================================================
-//          GLOBAL ATTENTION, half-tile pipeline with FOUR softmax warps per scheduler (column-split rows)
-// ================================================================================================================
-template <int HD, int NST_> struct G3Cfg : G2Cfg<HD, NST_> {
-    using B = G2Cfg<HD, NST_>;
-    static constexpr int OFF_XO = B::OFF_BAR + 256;              // exchange area: 4 x 2 x 128 x 2 + 2 x 128 x 2 floats
-    static constexpr int XO_BYTES = (4 * 2 * 128 * 2 + 2 * 128 * 2) * 4;
-    static constexpr int SMEM = OFF_XO + XO_BYTES + 1024;
-    static_assert(SMEM <= 232448, "shared memory budget");
-};
-
-template <int HD, int NST, bool PH>
-__global__ void __launch_bounds__(608, 1)
-attn_global3_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
-                    const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
-                    const __grid_constant__ CUtensorMap tm_rh_main, const __grid_constant__ CUtensorMap tm_rh_tail,
-                    const bf16* __restrict__ qkv, bf16* __restrict__ out, int D, int T, float scale_log2,
-                    long long* __restrict__ phase_clocks, int order) {
-    using C = G3Cfg<HD, NST>;
-    constexpr int NKT = 32;                                     // 128-key TMA tiles
-    constexpr int NH = 64;                                      // 64-key half tiles = key rows of the image
-    constexpr int HALF_MAIN = 64 * 128, HALF_TAIL = 64 * 32;    // byte offset of keys 64.. inside a K / V tile
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-    const int row0 = b * T + pair * 256;
-    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
-
-    if (warp == 16 && lane == 0) {
-        ptx::prefetch_tmap(&tm_main);
-        ptx::prefetch_tmap(&tm_rw_main);
-        ptx::prefetch_tmap(&tm_rh_main);
-        if (HD > 64) { ptx::prefetch_tmap(&tm_tail); ptx::prefetch_tmap(&tm_rw_tail); ptx::prefetch_tmap(&tm_rh_tail); }
-        ptx::mbar_init(&bars[C::B_QFULL], 1);
-        for (int s = 0; s < NST; ++s) {
-            ptx::mbar_init(&bars[C::B_KFULL + s], 1);
-            ptx::mbar_init(&bars[C::B_KEMPTY + s], 2);             // one release per issuer (query tile)
-            ptx::mbar_init(&bars[C::B_VFULL + s], 1);
-            ptx::mbar_init(&bars[C::B_VEMPTY + s], 2);
-        }
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(&bars[C::B_BIAS + i], 1);
-            ptx::mbar_init(&bars[C::B_BREAD + i], 256);            // both column halves of the 128 rows
-            ptx::mbar_init(&bars[C::B_PVDONE + i], 1);
-            ptx::mbar_init(&bars[C::B_ODONE + i], 1);
-        }
-        for (int i = 0; i < 4; ++i) {
-            ptx::mbar_init(&bars[C::B_SFULL + i], 1);
-            ptx::mbar_init(&bars[C::B_PFULL + i], 256);
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 17) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 16) {
-        // ===================== TMA producer (as in attn_global_kernel) =====================
-        if (lane == 0) {
-            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::Q_TX);
-            for (int i = 0; i < 2; ++i) {
-                ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE, &tm_main, &bars[C::B_QFULL], colq, row0 + 128 * i);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_Q + i * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_QFULL], colq + 64, row0 + 128 * i);
-            }
-            ptx::tma_load_2d(sm + C::OFF_RW, &tm_rw_main, &bars[C::B_QFULL], 0, 144);
-            ptx::tma_load_2d(sm + C::OFF_RH, &tm_rh_main, &bars[C::B_QFULL], 0, 4 * pair);
-            if (HD > 64) {
-                ptx::tma_load_2d(sm + C::OFF_RW + C::T_MAIN, &tm_rw_tail, &bars[C::B_QFULL], 64, 144);
-                ptx::tma_load_2d(sm + C::OFF_RH + C::RH_MAIN, &tm_rh_tail, &bars[C::B_QFULL], 64, 4 * pair);
-            }
-            for (int j = 0; j < NKT; ++j) {
-                const int st = j % NST;
-                const uint32_t par = ((j / NST) & 1) ^ 1;
-                const int krow = b * T + j * 128;
-                ptx::mbar_wait(&bars[C::B_KEMPTY + st], par);
-                ptx::mbar_expect_tx(&bars[C::B_KFULL + st], C::KV_TX);
-                ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE, &tm_main, &bars[C::B_KFULL + st], colk, krow);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_K + st * C::TILE + C::T_MAIN, &tm_tail, &bars[C::B_KFULL + st], colk + 64, krow);
-                ptx::mbar_wait(&bars[C::B_VEMPTY + st], par);
-                ptx::mbar_expect_tx(&bars[C::B_VFULL + st], C::V_TX);
-                ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE, &tm_main, &bars[C::B_VFULL + st], colv, krow);
-                if (HD > 64) ptx::tma_load_2d(sm + C::OFF_V + st * C::VTILE + C::T_MAIN, &tm_main, &bars[C::B_VFULL + st], colv + 64, krow);
-            }
-        }
-    } else if (warp == 17 || warp == 18) {
-        // ===================== MMA issuers: one per query tile =====================
-        // (a single issuing thread needs ~40 cycles of scalar work per tcgen05.mma + commit: 52 MMAs + 10 commits per 128 keys
-        // made ONE issuer the bottleneck of this pipeline, 2690 cycles per 128 keys; the two tiles' chains are independent)
-        if (lane == 0) {
-            const int i = warp - 17;
-            constexpr uint32_t id_w = ptx::make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 64, 0, 0);
-            constexpr uint32_t id_rh = ptx::make_idesc_bf16(128, 80, 0, 0);
-            const uint32_t q_main = base + C::OFF_Q + i * C::TILE, q_tail = q_main + C::T_MAIN;
-            const uint32_t q_tm = tmem + C::TM_Q + C::Q_STRIDE * i;
-            const uint32_t o_tm = tmem + C::TM_O + C::O_STRIDE * i;
-            ptx::mbar_wait(&bars[C::B_QFULL], 0);
-            ptx::tc_fence_after();
-            // decomposed rel-pos products: Q.Rw^T -> both S buffers of the tile (128 columns), Q.Rh[4*pair ..]^T -> O_i columns
-            issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main, q_tail, base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_w);
-            issue_qk<HD>(o_tm, q_main, q_tail, base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
-            ptx::mma_commit(&bars[C::B_BIAS + i]);
-            // S_i(0), S_i(1): the two halves of key tile 0
-            ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
-            ptx::mbar_wait(&bars[C::B_BREAD + i], 0);              // bias products consumed (S_i / O_i columns are free), Q_i is in TMEM
-            ptx::tc_fence_after();
-            for (int hb = 0; hb < 2; ++hb) {
-                issue_qk_ts<HD>(tmem + C::TM_S + 64 * (2 * i + hb), q_tm, base + C::OFF_K + hb * HALF_MAIN,
-                                base + C::OFF_K + C::T_MAIN + hb * HALF_TAIL, id_s);
-                ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
-            }
-            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
-            long long ipc[3] = {0, 0, 0};
-            long long itp = PH ? clock64() : 0;
-#define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
-            for (int h = 0; h < NH; ++h) {
-                const int hb = h & 1, jt = h >> 1, st = jt % NST;
-                const bool more = (h + 2 < NH);
-                const int jt2 = (h + 2) >> 1, st2 = jt2 % NST;
-                SVB_IPH(2)
-                if (hb == 0) {
-                    ptx::mbar_wait(&bars[C::B_VFULL + st], (jt / NST) & 1);
-                    if (more) ptx::mbar_wait(&bars[C::B_KFULL + st2], (jt2 / NST) & 1);
-                }
-                SVB_IPH(0)
-                const uint32_t s_i = tmem + C::TM_S + 64 * (2 * i + hb);
-                ptx::mbar_wait(&bars[C::B_PFULL + 2 * i + hb], jt & 1);      // P_i(h) is in TMEM
-                SVB_IPH(1)
-                ptx::tc_fence_after();
-                issue_pv_wide<HD>(o_tm, s_i, base + C::OFF_V + st * C::VTILE + hb * HALF_MAIN, C::T_MAIN, 4, h > 0);
-                ptx::mma_commit(&bars[C::B_PVDONE + i]);
-                if (h == NH - 1) ptx::mma_commit(&bars[C::B_ODONE + i]);     // O_i is complete
-                if (hb == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
-                if (more) {
-                    // in-order execution of this thread's MMAs: the overwrite of S_i^hb / P_i^hb follows the PV above
-                    issue_qk_ts<HD>(s_i, q_tm, base + C::OFF_K + st2 * C::TILE + hb * HALF_MAIN,
-                                    base + C::OFF_K + st2 * C::TILE + C::T_MAIN + hb * HALF_TAIL, id_s);
-                    ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
-                    if (hb == 1) ptx::mma_commit(&bars[C::B_KEMPTY + st2]);
-                }
-            }
-#undef SVB_IPH
-            if (PH && phase_clocks && i == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
-                atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
-            }
-        }
-    } else {
-        // ===================== softmax warps: 2 query tiles x 2 column halves x 4 lane quadrants =====================
-        // Warps w and w + 8 own the SAME 32 query rows (TMEM lanes) and split every 64-key half tile: `half` 0 takes key columns
-        // 0..31, `half` 1 columns 32..63 — four softmax warps per scheduler instead of two (one warp alone is latency-bound: ~1200
-        // cycles for the 64 exponentials of a row's half tile).  What a row's two threads must agree on is the reference maximum:
-        // each publishes the absolute maximum exponent of its columns per half tile (xo, 4 slots), and the lazy rescale at tile
-        // h uses the values of tile h-2, which are visible through the barrier chain P(h-2) -> QK(h) -> S(h) without any extra
-        // synchronisation; the first tile's bound and the final row sum go through one named barrier per warp pair.
-        const int half = warp >> 3;
-        const int i = (warp >> 2) & 1;                             // query tile
-        const int w4 = warp & 3;                                   // TMEM lane quadrant (= warp id % 4)
-        const int t = w4 * 32 + lane;                              // query row inside the tile
-        const int qr = 2 * i + (t >> 6);                           // grid row of the query inside the CTA (0..3), warp-uniform
-        const int qw = t & 63;                                     // grid column of the query
-        const int kw0 = 32 * half;                                 // first key column of this thread
-        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
-        const uint32_t s_tmem = tmem + lane_off + C::TM_S + 128 * i;
-        const uint32_t o_tmem = tmem + lane_off + C::TM_O + C::O_STRIDE * i;
-        float* stg = reinterpret_cast<float*>(sm + C::OFF_STG + (warp & 7) * 8192);   // [64][32] fp32, shared by the warp pair
-        float* xo = reinterpret_cast<float*>(sm + C::OFF_XO);     // [4 slots][2 tiles][128 rows][2 halves]
-        float* lx = xo + 4 * 2 * 128 * 2;                          // [2 tiles][128 rows][2 halves]: first-tile bound, then the row sums
-        const int xi = (i * 128 + t) * 2;
-        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 7)) : "memory"); };
-
-        // ---- this row's query -> TMEM (bf16 pairs, the layout P has): the A operand of every QK product ----
-        if (half == 0) {
-            const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + 128 * i + t) * (3 * D) + colq);
-            const uint32_t q_tmem = tmem + lane_off + C::TM_Q + C::Q_STRIDE * i;
-            uint32_t qa[32];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 u = __ldg(src + c);
-                qa[4 * c] = u.x; qa[4 * c + 1] = u.y; qa[4 * c + 2] = u.z; qa[4 * c + 3] = u.w;
-            }
-            ptx::tmem_st_x32(q_tmem, qa);
-            if (HD > 64) {
-                uint32_t qb[8];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const uint4 u = __ldg(src + 8 + c);
-                    qb[4 * c] = u.x; qb[4 * c + 1] = u.y; qb[4 * c + 2] = u.z; qb[4 * c + 3] = u.w;
-                }
-                ptx::tmem_st_x8(q_tmem + 32, qb);
-            }
-            ptx::tmem_st_wait();
-        }
-        // ---- rel-pos prologue: w term of this thread's 32 key columns into registers (the two halves take turns with the pair's
-        // staging block), h term into the staging block (written by half 0, read by both) ----
-        float bwl[32];
-        ptx::mbar_wait(&bars[C::B_BIAS + i], 0);
-        ptx::mbar_wait(&bars[C::B_BIAS + (i ^ 1)], 0);             // the staging area below aliases the tables BOTH tiles' bias MMAs read
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int turn = 0; turn < 2; ++turn) {
-            if (turn == half) {
-#pragma unroll
-                for (int p = 0; p < 2; ++p) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_x32(s_tmem + 64 * p + 32 * hh, v);
-                        ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) stg[(32 * hh + e) * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int kk = 0; kk < 32; ++kk) {
-                        const int c = qw + 63 - (kw0 + kk);            // table row qw - kw + 63
-                        if ((c >> 6) == p) bwl[kk] = stg[(c & 63) * 32 + lane];
-                    }
-                    __syncwarp();
-                }
-            }
-            pair_sync();
-        }
-        float bwmax = bwl[0];
-#pragma unroll
-        for (int kk = 1; kk < 32; ++kk) bwmax = fmaxf(bwmax, bwl[kk]);
-        if (half == 0) {
-            // column c of the h product = Q . Rh[4*pair + c]; key row kh needs table row (4*pair + qr) - kh + 63
-            uint32_t v[32];
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                ptx::tmem_ld_x32(o_tmem + c0, v);
-                ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int kh = qr + 63 - (c0 + e);
-                    if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
-                }
-            }
-            uint32_t w[16];
-            ptx::tmem_ld_x16(o_tmem + 64, w);
-            ptx::tmem_ld_wait_dep(w);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int kh = qr + 63 - (64 + e);
-                if (kh >= 0 && kh < 64) stg[kh * 32 + lane] = __uint_as_float(w[e]) * LOG2E;
-            }
-        }
-        pair_sync();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars[C::B_BREAD + i]);                   // S_i / O_i columns may be overwritten
-
-        float m_ref = -INFINITY;
-        f32x2 l01 = f2_pack(0.f, 0.f), l23 = f2_pack(0.f, 0.f);      // partial row sum over this thread's columns
-        const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
-        long long pc[5] = {0, 0, 0, 0, 0};
-        long long tprev = PH ? clock64() : 0;
-#define SVB_GPH(k) if (PH) { const long long tn = clock64(); pc[k] += tn - tprev; tprev = tn; }
-#pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
-            const int hb = h & 1;
-            const uint32_t s_h = s_tmem + 64 * hb;
-            uint32_t va[32];
-            ptx::mbar_wait(&bars[C::B_SFULL + 2 * i + hb], (h >> 1) & 1);
-            SVB_GPH(0)
-            ptx::tc_fence_after();
-            ptx::tmem_ld_x32(s_h + kw0, va);
-            if (h > 0) {
-                ptx::tmem_st_wait();
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + (hb ^ 1)]);
-            }
-            SVB_GPH(3)
-            const float bh = stg[h * 32 + lane];
-            float m_new = m_ref;
-            bool need = false;
-            if (h >= 2) {
-                // absolute maximum exponent of tile h-2 over BOTH column halves (written before P(h-2) was handed over)
-                const float2 mm = *reinterpret_cast<const float2*>(xo + ((h - 2) & 3) * 512 + xi);
-                const float mx = fmaxf(mm.x, mm.y);
-                need = mx - m_ref > RESCALE_THRESHOLD;
-                m_new = need ? mx : m_ref;
-            }
-            ptx::tmem_ld_wait_dep(va);
-            // P(h) overlays S columns 0..31 — the OTHER half's keys for half 1: nobody stores P before both have loaded their S
-            if (h > 0) pair_sync();
-            SVB_GPH(4)
-            if (h == 0) {
-                // the first tile's reference: an upper bound of the row maximum over both halves, exchanged through the pair barrier
-                lx[xi + half] = fmaf(max32(va, -INFINITY), scale_log2, bh) + bwmax;
-                pair_sync();
-                const float2 bb = *reinterpret_cast<const float2*>(lx + xi);
-                m_ref = fmaxf(bb.x, bb.y);
-            } else if (__any_sync(0xffffffffu, need)) {
-                const float alpha = need ? ptx::ex2_approx(m_ref - m_new) : 1.0f;
-                ptx::mbar_wait(&bars[C::B_PVDONE + i], (h - 1) & 1);   // O_i holds tiles 0..h-1
-                ptx::tc_fence_after();
-                uint32_t r[8];
-#pragma unroll
-                for (int c0 = 0; c0 < HD / 2; c0 += 8) {               // this thread's half of the O columns
-                    ptx::tmem_ld_x8(o_tmem + half * (HD / 2) + c0, r);
-                    ptx::tmem_ld_wait_dep(r);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
-                    ptx::tmem_st_x8(o_tmem + half * (HD / 2) + c0, r);
-                }
-                const f32x2 al2 = f2_pack(alpha, alpha);
-                l01 = f2_mul(l01, al2);
-                l23 = f2_mul(l23, al2);
-                m_ref = m_new;
-                SVB_GPH(2)
-            }
-            float xa = -INFINITY, xb = -INFINITY;                  // maximum of this tile's exponents x = s*scale + bias - m_ref
-            const f32x2 dd2 = f2_pack(bh - m_ref, bh - m_ref);
-            // ---- P = exp2(S*scale + bias - m_ref) -> bf16 -> TMEM (over the consumed S columns) ----
-            {
-                uint32_t pk[16];
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const f32x2 x01 = f2_add(f2_fma(f2_pack(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), sc2, f2_pack(bwl[e], bwl[e + 1])), dd2);
-                    const f32x2 x23 = f2_add(f2_fma(f2_pack(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), sc2, f2_pack(bwl[e + 2], bwl[e + 3])), dd2);
-                    float a0, a1, a2, a3;
-                    f2_unpack(x01, a0, a1);
-                    f2_unpack(x23, a2, a3);
-                    xa = fmax3(xa, a0, a1);
-                    xb = fmax3(xb, a2, a3);
-                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);
-                    const float p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);
-                    l01 = f2_add(l01, f2_pack(p0, p1));
-                    l23 = f2_add(l23, f2_pack(p2, p3));
-                    pk[e / 2] = pack_bf16x2(p0, p1);
-                    pk[e / 2 + 1] = pack_bf16x2(p2, p3);
-                }
-                ptx::tmem_st_x16(s_h + 16 * half, pk);             // keys kw0 .. kw0+31 = P columns 16*half .. +15
-            }
-            xo[(h & 3) * 512 + xi + half] = m_ref + fmaxf(xa, xb);   // published before P(h) is handed over (next iteration)
-            SVB_GPH(1)
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars[C::B_PFULL + 2 * i + 1]);             // P(NH-1)
-        SVB_GPH(3)
-#undef SVB_GPH
-        if (PH && phase_clocks && w4 == 0 && lane == 0 && half == 0) {
-            for (int k = 0; k < 3; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + k, (unsigned long long)pc[k]);
-            atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + i * 8 + 6, (unsigned long long)(NH / 2));
-            if (i == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 7, (unsigned long long)pc[3]); atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 15, (unsigned long long)pc[4]); }
-        }
-        // ---- row sum over both halves, then each thread stores its half of the O columns at the query's own token position ----
-        {
-            float l0, l1, l2, l3;
-            f2_unpack(l01, l0, l1);
-            f2_unpack(l23, l2, l3);
-            pair_sync();                                             // the first-tile bounds in lx have been read by both
-            lx[xi + half] = (l0 + l1) + (l2 + l3);
-            pair_sync();
-            const float2 ll = *reinterpret_cast<const float2*>(lx + xi);
-            const float inv = 1.0f / (ll.x + ll.y);
-            ptx::mbar_wait(&bars[C::B_ODONE + i], 0);
-            ptx::tc_fence_after();
-            bf16* dst = out + (size_t)(row0 + 128 * i + t) * D + head * HD + half * (HD / 2);
-#pragma unroll
-            for (int c0 = 0; c0 < HD / 2; c0 += 8) {
-                uint32_t r[8];
-                ptx::tmem_ld_x8(o_tmem + half * (HD / 2) + c0, r);
-                ptx::tmem_ld_wait_dep(r);
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
-                u.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
-                u.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
-                u.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
-                *reinterpret_cast<uint4*>(dst + c0) = u;
-            }
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 17) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem, C::TM_COLS);
-    }
-}
-
 // One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
 // the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
-// the reference maximum).  Two passes over TMEM: raw maximum (an upper bound of the row maximum follows from it), then
-// exp2 / sum / pack with packed fp32x2 arithmetic.
+// the reference maximum).  Two passes over TMEM: the exact row maximum, then exp2 / sum / pack with packed fp32x2 arithmetic.
 template <bool POLY>
 __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
-    float bmax = bhm[0], wmax = bwl[0];
-#pragma unroll
-    for (int k = 1; k < 14; ++k) { bmax = fmaxf(bmax, bhm[k]); wmax = fmaxf(wmax, bwl[k]); }
-
     uint32_t va[32], vb[32], vt[4];
-    // ---- pass A: raw maximum over the 196 keys ----
-    float smax = -INFINITY;
+    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+    // ---- pass A: the row's EXACT maximum exponent.  Per key row kh the maximum of s * scale + w term (an FMA and half a
+    // three-input maximum per element: the pairs (k, k+1) never straddle a key row, 14 is even), then + h term.  A reference that
+    // was really attained cannot make the whole row underflow, whatever the spread of the bias terms (an upper bound built from
+    // the largest bias terms could: P = exp2(x - bound) flushes to zero once the bound overshoots by ~126). ----
+    float mk[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) mk[k] = -INFINITY;
+#define SVB_WIN_A(V, CHUNK)                                                                              \
+    _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                                  \
+        const int k0 = 32 * (CHUNK) + e;                                                                 \
+        const f32x2 x = f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2, f2_pack(bwl[k0 % 14], bwl[(k0 + 1) % 14])); \
+        float a0, a1;                                                                                    \
+        f2_unpack(x, a0, a1);                                                                            \
+        mk[k0 / 14] = fmax3(mk[k0 / 14], a0, a1);                                                        \
+    }
     ptx::tmem_ld_x32(s_tmem, va);
     ptx::tmem_ld_wait_dep(va);
-#pragma unroll
-    for (int c = 1; c < 6; ++c) {
-        if (c & 1) { ptx::tmem_ld_x32(s_tmem + 32 * c, vb); smax = max32(va, smax); ptx::tmem_ld_wait_dep(vb); }
-        else       { ptx::tmem_ld_x32(s_tmem + 32 * c, va); smax = max32(vb, smax); ptx::tmem_ld_wait_dep(va); }
-    }
+    ptx::tmem_ld_x32(s_tmem + 32, vb);
+    SVB_WIN_A(va, 0)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 64, va);
+    SVB_WIN_A(vb, 1)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 96, vb);
+    SVB_WIN_A(va, 2)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 128, va);
+    SVB_WIN_A(vb, 3)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 160, vb);
+    SVB_WIN_A(va, 4)
+    ptx::tmem_ld_wait_dep(vb);
     ptx::tmem_ld_x4(s_tmem + 192, vt);
-    smax = max32(vb, smax);
+    SVB_WIN_A(vb, 5)
+#undef SVB_WIN_A
     ptx::tmem_ld_wait_dep(vt);
+    mk[13] = fmaxf(mk[13], fmaxf(fmaxf(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]), fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14])),
+                                 fmaxf(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]), fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]))));
+    float m_ref = mk[0] + bhm[0];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) smax = fmaxf(smax, __uint_as_float(vt[e]));
-    const float m_ref = fmaf(smax, scale_log2, bmax + wmax);   // upper bound of the row maximum (scale > 0)
+    for (int k = 1; k < 14; ++k) m_ref = fmaxf(m_ref, mk[k] + bhm[k]);
 #pragma unroll
     for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
     // ---- pass B ----
     f32x2 l01 = f2_pack(0.f, 0.f);
-    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
 #define SVB_WIN_B(V, CHUNK)                                                                              \
     {                                                                                                \
         uint32_t pk[16];                                                                             \
@@ -1385,170 +684,6 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
     float l0, l1;
     f2_unpack(l01, l0, l1);
     return l0 + l1;
-}
-
-// ================================================================================================================
-//                                      WINDOWED ATTENTION (14 x 14 windows, 196 keys)
-// ================================================================================================================
-template <int HD> struct WCfg {
-    static constexpr int TAIL = HD - 64;
-    static constexpr int Q_MAIN = 128 * 128, Q_TAIL = TAIL ? 128 * 32 : 0;
-    static constexpr int K_MAIN = 208 * 128, K_TAIL = TAIL ? 7168 : 0;       // 208 x 32 B rounded up to 1 KB
-    static constexpr int R_MAIN = 64 * 128, R_TAIL = TAIL ? 64 * 32 : 0;     // rel tables: rows 0..26 h, 32..58 w
-    static constexpr int OFF_Q = 0;
-    static constexpr int OFF_K = OFF_Q + Q_MAIN + Q_TAIL;
-    static constexpr int OFF_V = OFF_K + K_MAIN + K_TAIL;
-    static constexpr int OFF_R = OFF_V + K_MAIN + K_TAIL;
-    // The per-warp staging blocks of the rel-pos prologue (4 warps x [32][32] fp32) reuse the rel-table area: the tables are
-    // dead once the bias MMA has committed, and no later TMA write lands there.  (Staging inside the V tile raced with the V
-    // load: generic-proxy accesses followed by an async-proxy write to the same bytes are not ordered by an mbarrier hand-off.)
-    static constexpr int STG_BYTES = 4 * 4096;
-    static constexpr int R_AREA = (R_MAIN + R_TAIL > STG_BYTES) ? (R_MAIN + R_TAIL) : STG_BYTES;
-    static constexpr int OFF_BAR = OFF_R + R_AREA;
-    static constexpr int SMEM = OFF_BAR + 128 + 1024;
-    static_assert(2 * (SMEM + 1024) <= 233472, "two CTAs per SM");
-    static constexpr int QR_TX = 64 * 128 + (TAIL ? 64 * 32 : 0);            // + query rows * (128 + 32)
-    static constexpr int KV_TX = 196 * 128 + (TAIL ? 196 * 32 : 0);
-    static constexpr int B_QFULL = 0, B_BIAS = 1, B_KFULL = 2, B_VFULL = 3, B_SFULL = 4, B_PFULL = 5, B_PVDONE = 6, B_COUNT = 7;
-    static constexpr int TM_S = 0, TM_O = 112, TM_COLS = 256;                // bias product at [0,64), P at [0,104), O at [112,112+HD)
-};
-
-struct WinMaps {
-    CUtensorMap q0_main, q1_main, kv_main, r_main;     // boxes (64,14,9,1) / (64,14,5,1) / (64,14,14,1) / (64,64)
-    CUtensorMap q0_tail, q1_tail, kv_tail, r_tail;     // boxes (16, ...)
-};
-
-template <int HD>
-__global__ void __launch_bounds__(192, 2)
-attn_window_kernel(const __grid_constant__ WinMaps maps, bf16* __restrict__ out, int D, int g, float scale_log2, int dbg) {
-    using C = WCfg<HD>;
-    constexpr int WS = 14, NWS = 5;
-    const int qt = blockIdx.x, head = blockIdx.y;
-    const int b = blockIdx.z / (NWS * NWS), win = blockIdx.z % (NWS * NWS);
-    const int wy = win / NWS, wx = win % NWS;
-    const int yi0 = qt ? 9 : 0;
-    if (wy * WS + yi0 >= g) return;                               // every query row of this tile is padding (cropped later)
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
-    const int qrows = qt ? 70 : 126;
-
-    if (warp == 4 && lane == 0) {
-        ptx::prefetch_tmap(&maps.kv_main);
-        ptx::prefetch_tmap(qt ? &maps.q1_main : &maps.q0_main);
-        ptx::prefetch_tmap(&maps.r_main);
-        for (int s = 0; s < C::B_COUNT; ++s) ptx::mbar_init(&bars[s], s == C::B_PFULL ? 128 : 1);
-        ptx::fence_barrier_init();
-    }
-    if (warp == 5) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            const int x0 = wx * WS, y0 = wy * WS;
-            ptx::mbar_expect_tx(&bars[C::B_QFULL], C::QR_TX + qrows * (128 + (HD > 64 ? 32 : 0)));
-            ptx::tma_load_4d(sm + C::OFF_Q, qt ? &maps.q1_main : &maps.q0_main, &bars[C::B_QFULL], colq, x0, y0 + yi0, b);
-            ptx::tma_load_2d(sm + C::OFF_R, &maps.r_main, &bars[C::B_QFULL], 0, 0);
-            if (HD > 64) {
-                ptx::tma_load_4d(sm + C::OFF_Q + C::Q_MAIN, qt ? &maps.q1_tail : &maps.q0_tail, &bars[C::B_QFULL], colq + 64, x0, y0 + yi0, b);
-                ptx::tma_load_2d(sm + C::OFF_R + C::R_MAIN, &maps.r_tail, &bars[C::B_QFULL], 64, 0);
-            }
-            ptx::mbar_expect_tx(&bars[C::B_KFULL], C::KV_TX);
-            ptx::tma_load_4d(sm + C::OFF_K, &maps.kv_main, &bars[C::B_KFULL], colk, x0, y0, b);
-            if (HD > 64) ptx::tma_load_4d(sm + C::OFF_K + C::K_MAIN, &maps.kv_tail, &bars[C::B_KFULL], colk + 64, x0, y0, b);
-            ptx::mbar_expect_tx(&bars[C::B_VFULL], C::KV_TX);
-            ptx::tma_load_4d(sm + C::OFF_V, &maps.kv_main, &bars[C::B_VFULL], colv, x0, y0, b);
-            if (HD > 64) ptx::tma_load_4d(sm + C::OFF_V + C::K_MAIN, &maps.kv_tail, &bars[C::B_VFULL], colv + 64, x0, y0, b);
-        }
-    } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t id_r = ptx::make_idesc_bf16(128, 64, 0, 0);
-            constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 208, 0, 0);
-            ptx::mbar_wait(&bars[C::B_QFULL], 0);
-            ptx::tc_fence_after();
-            issue_qk<HD>(tmem + C::TM_S, base + C::OFF_Q, base + C::OFF_Q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
-            ptx::mma_commit(&bars[C::B_BIAS]);
-            ptx::mbar_wait(&bars[C::B_KFULL], 0);
-            ptx::mbar_wait(&bars[C::B_PFULL], 0);                  // bias product consumed
-            ptx::tc_fence_after();
-            issue_qk<HD>(tmem + C::TM_S, base + C::OFF_Q, base + C::OFF_Q + C::Q_MAIN, base + C::OFF_K, base + C::OFF_K + C::K_MAIN, id_s);
-            ptx::mma_commit(&bars[C::B_SFULL]);
-            ptx::mbar_wait(&bars[C::B_VFULL], 0);
-            ptx::mbar_wait(&bars[C::B_PFULL], 1);                  // P is in TMEM
-            ptx::tc_fence_after();
-            issue_pv<HD>(tmem + C::TM_O, tmem + C::TM_S, base + C::OFF_V, base + C::OFF_V + C::K_MAIN, 13, false);
-            ptx::mma_commit(&bars[C::B_PVDONE]);
-        }
-    } else {
-        // ===================== softmax warps: 128 query rows =====================
-        const int t = warp * 32 + lane;
-        const int yi = yi0 + t / WS, xi = t % WS;
-        const int y = wy * WS + yi, x = wx * WS + xi;
-        const bool valid = (t < qrows) && (y < g) && (x < g);
-        const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-        const uint32_t s_tmem = tmem + lane_off + C::TM_S;
-        const uint32_t o_tmem = tmem + lane_off + C::TM_O;
-        float* stg = reinterpret_cast<float*>(sm + C::OFF_R + warp * 4096);     // [32][32] fp32, private to this warp
-
-        // keys 196..207 of the PV contraction multiply P = 0: their V rows must be finite
-        if (t < 96) *reinterpret_cast<uint4*>(sm + C::OFF_V + 196 * 128 + t * 16) = make_uint4(0, 0, 0, 0);
-        if (HD > 64 && t < 24) *reinterpret_cast<uint4*>(sm + C::OFF_V + C::K_MAIN + 196 * 32 + t * 16) = make_uint4(0, 0, 0, 0);
-        ptx::fence_proxy_async_smem();
-
-        // ---- rel-pos prologue: both terms into registers through the per-warp staging block ----
-        float bhm[14], bwl[14];
-        ptx::mbar_wait(&bars[C::B_BIAS], 0);
-        ptx::tc_fence_after();
-        const int yc = yi < 18 ? yi : 18;                          // rows beyond the tile hold garbage; keep the reads in bounds
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            uint32_t v[32];
-            ptx::tmem_ld_x32(s_tmem + 32 * p, v);
-            ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) stg[e * 32 + lane] = __uint_as_float(v[e]) * LOG2E;
-            __syncwarp();
-            if (p == 0) {
-#pragma unroll
-                for (int k = 0; k < 14; ++k) bhm[k] = stg[(yc + 13 - k) * 32 + lane];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 14; ++k) bwl[k] = stg[(xi + 13 - k) * 32 + lane];
-            }
-            __syncwarp();
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 0
-
-        ptx::mbar_wait(&bars[C::B_SFULL], 0);
-        ptx::tc_fence_after();
-        const float lsum = window_softmax_tile<false>(s_tmem, bhm, bwl, scale_log2);
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars[C::B_PFULL]);                       // phase 1
-        // ---- epilogue ----
-        ptx::mbar_wait(&bars[C::B_PVDONE], 0);
-        ptx::tc_fence_after();
-        const float inv = 1.0f / lsum;
-        bf16* dst = valid ? out + ((size_t)b * g * g + (size_t)y * g + x) * D + head * HD : nullptr;
-        store_row<HD>(dst, o_tmem, inv);
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem, C::TM_COLS);
-    }
 }
 
 // ================================================================================================================
@@ -1953,7 +1088,7 @@ static bool exp2_poly(bool windowed) {
 
 template <int HD, int NST>
 int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
-    using C = GCfg<HD, NST>;
+    using C = G2Cfg<HD, NST>;
     const int D = p.heads * p.hd, T = p.grid * p.grid;
     CUtensorMap m[6];
     int rc;
@@ -1971,56 +1106,21 @@ int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
         if ((rc = encode_tmap_nd_bf16(&m[4], p.rel_pack, 2, rd, rs, hm, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&m[5], p.rel_pack, 2, rd, rs, ht, 32))) return rc;
     }
-    // SVB_ATTNG_ONEPASS=0 selects the two-pass softmax (A/B comparisons)
-    static const bool onepass = [] { const char* e = getenv("SVB_ATTNG_ONEPASS"); return !(e && atoi(e) == 0); }();
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     dim3 grid(T / 256, p.heads, p.batch);
-    // SVB_ATTNG_IMPL=1 selects the 128-key-tile kernel (A/B comparisons); default: the half-tile pipeline
-    static const int impl = [] { const char* e = getenv("SVB_ATTNG_IMPL"); return e ? atoi(e) : 2; }();
-    if (impl == 3) {
-        using C3 = G3Cfg<HD, NST>;
-        static bool attr3_set = false;
-        if (!attr3_set) {
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global3_kernel<HD, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM));
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global3_kernel<HD, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3::SMEM));
-            attr3_set = true;
-        }
-        if (p.phase_clocks)
-            attn_global3_kernel<HD, NST, true><<<grid, 608, C3::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, 0);
-        else
-            attn_global3_kernel<HD, NST, false><<<grid, 608, C3::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 0);
-        SVB_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    }
-    if (impl == 2) {
-        static const int order = [] { const char* e = getenv("SVB_ATTNG_ORDER"); return e ? atoi(e) : 1; }();
-        static bool attr2_set = false;
-        if (!attr2_set) {
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-            SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-            attr2_set = true;
-        }
-        if (p.phase_clocks)
-            attn_global2_kernel<HD, NST, true, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, order);
-        else if (exp2_poly(false))
-            attn_global2_kernel<HD, NST, false, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
-        else
-            attn_global2_kernel<HD, NST, false, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, order);
-        SVB_CHECK_CUDA(cudaGetLastError());
-        return 0;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr2_set = true;
     }
     if (p.phase_clocks)
-        attn_global_kernel<HD, NST, true, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, p.phase_clocks);
-    else if (onepass) attn_global_kernel<HD, NST, true><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, nullptr);
-    else attn_global_kernel<HD, NST, false><<<grid, 320, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], p.out, D, T, scale_log2, nullptr);
+        attn_global2_kernel<HD, NST, true, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, 1);
+    else if (exp2_poly(false))
+        attn_global2_kernel<HD, NST, false, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 1);
+    else
+        attn_global2_kernel<HD, NST, false, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 1);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -2029,43 +1129,6 @@ template <int HD>
 int launch_global(const AttnTcParams& p, cudaStream_t stream) {
     // K/V ring depth: 3 stages at head_dim 64, 2 at 80 (V tiles of two full atoms; 2 vs 3 stages measured identical)
     return launch_global_nst<HD, (HD > 64) ? 2 : 3>(p, stream);
-}
-
-template <int HD>
-int launch_window(const AttnTcParams& p, cudaStream_t stream) {
-    using C = WCfg<HD>;
-    const int D = p.heads * p.hd, gp = 70;
-    WinMaps wm;
-    int rc;
-    {
-        const uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)gp, (uint64_t)gp, (uint64_t)p.batch};
-        const uint64_t str[3] = {(uint64_t)3 * D * 2, (uint64_t)gp * 3 * D * 2, (uint64_t)gp * gp * 3 * D * 2};
-        const uint32_t q0[4] = {64, 14, 9, 1}, q1[4] = {64, 14, 5, 1}, kv[4] = {64, 14, 14, 1};
-        const uint32_t q0t[4] = {16, 14, 9, 1}, q1t[4] = {16, 14, 5, 1}, kvt[4] = {16, 14, 14, 1};
-        if ((rc = encode_tmap_nd_bf16(&wm.q0_main, p.qkv, 4, dims, str, q0, 128))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.q1_main, p.qkv, 4, dims, str, q1, 128))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.kv_main, p.qkv, 4, dims, str, kv, 128))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.q0_tail, p.qkv, 4, dims, str, q0t, 32))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.q1_tail, p.qkv, 4, dims, str, q1t, 32))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.kv_tail, p.qkv, 4, dims, str, kvt, 32))) return rc;
-        const uint64_t rd[2] = {(uint64_t)HD, 64};
-        const uint64_t rs[1] = {(uint64_t)HD * 2};
-        const uint32_t rm[2] = {64, 64}, rt[2] = {16, 64};
-        if ((rc = encode_tmap_nd_bf16(&wm.r_main, p.rel_pack, 2, rd, rs, rm, 128))) return rc;
-        if ((rc = encode_tmap_nd_bf16(&wm.r_tail, p.rel_pack, 2, rd, rs, rt, 32))) return rc;
-    }
-    const int smem = C::SMEM;
-    const int dbg = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    const float scale_log2 = LOG2E / sqrtf((float)HD);
-    dim3 grid(2, p.heads, p.batch * 25);
-    attn_window_kernel<HD><<<grid, 192, smem, stream>>>(wm, p.out, D, p.grid, scale_log2, dbg);
-    SVB_CHECK_CUDA(cudaGetLastError());
-    return 0;
 }
 
 template <int HD>
@@ -2163,9 +1226,6 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
                    (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
                    (double)p.batch * p.grid * p.grid * 4.0 * D_ * 2, stream);
     if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
-    // persistent two-tile kernel by default; SVB_ATTNW_IMPL=1 selects the one-tile-per-CTA kernel (A/B comparisons)
-    static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 2; }();
-    if (impl == 1) return p.hd == 64 ? launch_window<64>(p, stream) : launch_window<80>(p, stream);
     return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }
 

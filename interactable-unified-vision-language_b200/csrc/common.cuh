@@ -66,6 +66,16 @@ struct Epilogue {
     void* out2 = nullptr;            // bf16 [M, ldo2]
     int ldo2 = 0;
     float2* stat_out = nullptr;      // [M][ceil(N / 128)]
+    // CENTRED form of that hand-over (LayerNorm is invariant under a per-row shift of its input): the bf16 copy and the partial
+    // statistics are taken of  x - c[row],  c[row] = the mean of the row BEFORE this GEMM's update = shift_in[row] + the mean the
+    // previous producer's (already centred) statistics give.  The rounding error of the bf16 operand then scales with the row's
+    // deviation from its previous mean instead of with |x| (a common offset per row costs nothing), and the single-pass variance
+    // sum(y^2)/n - mean(y)^2 no longer cancels.  The consumer is unchanged (it only ever sees y = x - c).  shift_out[row] = c[row].
+    const float2* shift_stats = nullptr;   // [M][shift_parts] statistics of the rows before the update (null: c = shift_in)
+    const float* shift_in = nullptr;       // [M] their shifts (null: zeros); [shift_in_mod] indexed row % shift_in_mod when that is set
+    int shift_in_mod = 0;
+    float* shift_out = nullptr;            // [M] receives c (null: centring off, c = 0)
+    int shift_parts = 0, shift_dim = 0;
 };
 __host__ __device__ __forceinline__ size_t epilogue_out_row(const Epilogue& ep, int row) {
     if (ep.remap_g == 0) return (size_t)row;
@@ -210,9 +220,11 @@ int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cu
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)
-int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s);
+int im2col_patch(const void* x, int x_dtype, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s);
 // scope row N3: bicubic resize of pos_embed (image_encoder.py:124-132), linear resize of a rel_pos table (:319-330)
 int resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int D, cudaStream_t s);
+// out[t] = mean_d(a[t, d]) + mean_d(b[d]): the expected row mean of patch_embed + pos_embed, the first producer's centring shift
+int row_means(const float* a, const float* b, float* out, int rows, int D, cudaStream_t s);
 int resize_rel_pos(const float* src, float* dst, int L0, int L1, int hd, cudaStream_t s);
 // uint8 (C,h,w) images -> normalised, zero-padded to img x img, patch rows (the patch-embedding GEMM's A operand); `images`, `hs`,
 // `ws` are HOST arrays (device pointers / sizes per image)

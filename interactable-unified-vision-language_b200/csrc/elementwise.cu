@@ -1,6 +1,7 @@
 // HBM-bound stages of the encoder: patch im2col, LayerNorm, GroupNorm(1,C) apply (+GELU, + NHWC->NCHW un-shuffle),
 // the neck's cast / 2x2 space-to-depth gather, and the one-time weight packing kernels.
 // All are sized for coalesced 16-byte accesses; their roofline is HBM bandwidth.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace svb {
@@ -31,8 +32,29 @@ template <> struct Vec4<bf16> {
 // ---------------------------------------------------------------------------------------------------------------
 // im2col for the patch embedding (PatchEmbed, image_encoder.py:379-410): x NCHW fp32 -> rows = patches (b,py,px),
 // cols = (c, ky, kx), matching patch_embed.proj.weight.reshape(D, C*p*p).  One thread = 4 consecutive kx.
-template <typename T>
-__global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int C, int img_h, int img_w, int patch) {
+// 4 consecutive input elements of type TI (fp32 / fp16 / bf16: the reference's pipeline feeds fp16 images after
+// cast_batch_to_half, pipeline/XDecoderPipeline.py:93-95) as fp32
+template <typename TI> struct Load4;
+template <> struct Load4<float> {
+    static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+};
+template <> struct Load4<__half> {
+    static __device__ __forceinline__ float4 load(const __half* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <> struct Load4<bf16> {
+    static __device__ __forceinline__ float4 load(const bf16* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+
+template <typename T, typename TI>
+__global__ void im2col_kernel(const TI* __restrict__ x, T* __restrict__ out, int B, int C, int img_h, int img_w, int patch) {
     const int gh = img_h / patch, gw = img_w / patch;
     const int K = C * patch * patch;
     const size_t plane = (size_t)img_h * img_w;
@@ -43,7 +65,7 @@ __global__ void im2col_kernel(const float* __restrict__ x, T* __restrict__ out, 
         const int Y = (int)((e / img_w) % img_h);
         const int c = (int)((e / plane) % C);
         const int b = (int)(e / (plane * C));
-        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        const float4 v = Load4<TI>::load(x + e);
         const int px = X / patch, kx = X % patch, py = Y / patch, ky = Y % patch;
         const size_t row = ((size_t)b * gh + py) * gw + px;
         Vec4<T>::store(out + row * K + (size_t)c * patch * patch + ky * patch + kx, v.x, v.y, v.z, v.w);
@@ -412,13 +434,19 @@ inline int grid_for(size_t n, int block) {
 
 }  // namespace
 
-int im2col_patch(const float* x, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s) {
+// x_dtype: 0 fp32, 1 bf16, 2 fp16 (SVB_DTYPE_*)
+int im2col_patch(const void* x, int x_dtype, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s) {
     SVB_REQUIRE(img_h % patch == 0 && img_w % patch == 0 && patch % 4 == 0, "im2col_patch: image %d x %d / patch %d unsupported", img_h, img_w,
                 patch);
+    SVB_REQUIRE(x_dtype >= 0 && x_dtype <= 2, "im2col_patch: input dtype %d is not fp32 (0) / bf16 (1) / fp16 (2)", x_dtype);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(x) & (x_dtype == 0 ? 15 : 7)) == 0, "im2col_patch: the input must be 16-byte (fp32) / 8-byte (half) aligned");
     const size_t total4 = (size_t)B * C * img_h * img_w / 4;
-    ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * (4 + (out_bf16 ? 2 : 4)), s);
-    if (out_bf16) im2col_kernel<bf16><<<grid_for(total4, 256), 256, 0, s>>>(x, (bf16*)out, B, C, img_h, img_w, patch);
-    else im2col_kernel<float><<<grid_for(total4, 256), 256, 0, s>>>(x, (float*)out, B, C, img_h, img_w, patch);
+    ProfScope prof(PC_OTHER, 0, (double)total4 * 4 * ((x_dtype == 0 ? 4 : 2) + (out_bf16 ? 2 : 4)), s);
+    const int grid = grid_for(total4, 256);
+#define SVB_IM2COL(TO, TI) im2col_kernel<TO, TI><<<grid, 256, 0, s>>>((const TI*)x, (TO*)out, B, C, img_h, img_w, patch)
+    if (out_bf16) { if (x_dtype == 0) SVB_IM2COL(bf16, float); else if (x_dtype == 1) SVB_IM2COL(bf16, bf16); else SVB_IM2COL(bf16, __half); }
+    else { if (x_dtype == 0) SVB_IM2COL(float, float); else if (x_dtype == 1) SVB_IM2COL(float, bf16); else SVB_IM2COL(float, __half); }
+#undef SVB_IM2COL
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -601,6 +629,25 @@ int pack_conv2x2(const float* w, void* dst, bool dst_bf16, int Cin, int Cout, cu
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+namespace {
+__global__ void row_means_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int rows, int D) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s += a[(size_t)row * D + d] + (b ? b[d] : 0.f);
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s / (float)D;
+}
+}  // namespace
+
+int row_means(const float* a, const float* b, float* out, int rows, int D, cudaStream_t s) {
+    ProfScope prof(PC_OTHER, 0, (double)rows * D * 4, s);
+    row_means_kernel<<<(rows + 7) / 8, 256, 0, s>>>(a, b, out, rows, D);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int D, cudaStream_t s) {
     SVB_REQUIRE(h0 > 0 && w0 > 0 && h1 > 0 && w1 > 0 && D > 0, "resize_pos_embed: bad sizes");
     const long total = (long)h1 * w1 * D;

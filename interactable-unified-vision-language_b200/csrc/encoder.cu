@@ -127,6 +127,7 @@ struct Buffers {
     float *G, *G2, *G3;
     double* stats;
     float2 *st1, *st2;          // LayerNorm-fold partial row statistics of the residual stream (norm1 / norm2 inputs)
+    float *c1, *c2;             // their per-row shifts (centred hand-over, Epilogue::shift_out)
     size_t total;
 };
 
@@ -145,6 +146,8 @@ Buffers plan(const svb_encoder* e, int chunk, int mode, void* base, int T = 0) {
     const size_t parts = (size_t)(D + 127) / 128;
     b.st1 = (float2*)ar.alloc(M * parts * sizeof(float2));
     b.st2 = (float2*)ar.alloc(M * parts * sizeof(float2));
+    b.c1 = (float*)ar.alloc(M * sizeof(float));
+    b.c2 = (float*)ar.alloc(M * sizeof(float));
     const size_t mark = ar.off;
     b.A0 = ar.alloc(M * kpe * es);
     b.Xn = ar.alloc(M * D * es);
@@ -218,8 +221,8 @@ int resized_rel(svb_encoder* e, int block, bool is_w, int L, cudaStream_t st, co
 // One pass over B images of img_h x img_w pixels (0 = the trained img_size).  Token grids other than the trained one (scope row
 // N3) take the reference's fallbacks: bicubic pos_embed (image_encoder.py:111-114,124-132), linearly resized rel_pos tables in
 // the global blocks (:319-330); their attention runs on the fp32-math kernel (the tcgen05 kernels implement the 64 x 64 grid).
-int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], int out_dtype, int mode, const Buffers& bf,
-                  cudaStream_t st, const U8Input* u8 = nullptr, int img_h = 0, int img_w = 0) {
+int forward_chunk(svb_encoder* e, const void* x, int B, void* const outs[4], int out_dtype, int mode, const Buffers& bf,
+                  cudaStream_t st, const U8Input* u8 = nullptr, int img_h = 0, int img_w = 0, int x_dtype = SVB_DTYPE_F32) {
     const bool h = (mode == SVB_MODE_BF16);
     if (img_h == 0) { img_h = e->cfg.img_size; img_w = e->cfg.img_size; }
     const int gh = img_h / e->cfg.patch_size, gw = img_w / e->cfg.patch_size;
@@ -258,9 +261,20 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         }
         e->fold_dirty = false;
     }
-    auto produce = [&](Epilogue& ep, float2* stat) {      // epilogue of a GEMM that writes the residual stream
+    // SVB_LN_CENTRE=0 switches the centring of the hand-over off (A/B comparisons; the shifts are then all zero)
+    static const bool centre = [] { const char* v = getenv("SVB_LN_CENTRE"); return !(v && atoi(v) == 0); }();
+    auto produce = [&](Epilogue& ep, float2* stat, bool first = false) {      // epilogue of a GEMM that writes the residual stream
         ep.out = bf.X; ep.ldo = D;
-        if (fold) { ep.out2 = bf.Xn; ep.ldo2 = D; ep.stat_out = stat; }
+        if (fold) {
+            ep.out2 = bf.Xn; ep.ldo2 = D; ep.stat_out = stat;
+            // the statistics / bf16 copy are of x - c[row], c = the row's mean before this update (from the other statistics array)
+            ep.shift_out = (stat == bf.st1) ? bf.c1 : bf.c2;
+            if (!first && centre) {
+                ep.shift_stats = (stat == bf.st1) ? bf.st2 : bf.st1;
+                ep.shift_in = (stat == bf.st1) ? bf.c2 : bf.c1;
+                ep.shift_parts = parts; ep.shift_dim = D;
+            }
+        }
     };
     auto consume = [&](Epilogue& ep, const Param& W, const Param& b, const float2* stat) {   // epilogue of qkv / lin1
         if (fold) {
@@ -274,7 +288,7 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         if ((rc = stage_u8_patch(u8->images, u8->hs, u8->ws, u8->mean, u8->stdv, bf.A0, h, B, e->cfg.in_chans, e->cfg.img_size,
                                  e->cfg.patch_size, st)))
             return rc;
-    } else if ((rc = im2col_patch(x, bf.A0, h, B, e->cfg.in_chans, img_h, img_w, e->cfg.patch_size, st))) {
+    } else if ((rc = im2col_patch(x, x_dtype, bf.A0, h, B, e->cfg.in_chans, img_h, img_w, e->cfg.patch_size, st))) {
         return rc;
     }
     {
@@ -285,7 +299,13 @@ int forward_chunk(svb_encoder* e, const float* x, int B, void* const outs[4], in
         ep.resid = pos;
         ep.resid_mod = T;
         ep.ldr = D;
-        produce(ep, bf.st1);
+        produce(ep, bf.st1, true);
+        if (fold && centre) {
+            // the first producer centres by the mean of what it ADDS to every row of token t: pos_embed[t, :] + the conv bias
+            // (c2 is free until proj of block 0 writes it, and only its first T entries are used here)
+            if ((rc = row_means(pos, e->P("patch_embed.proj.bias").f32, bf.c2, T, D, st))) return rc;
+            ep.shift_in = bf.c2; ep.shift_in_mod = T;
+        }
         if ((rc = linear(mode, bf.A0, kpe, e->P("patch_embed.proj.weight"), M, D, kpe, ep, st))) return rc;
     }
     const bool taps = e->taps_enabled && native;        // the tap buffer is sized for the trained grid
@@ -762,34 +782,47 @@ size_t svb_encoder_workspace_bytes_hw(const svb_encoder_t* e, int chunk, int mod
     return plan(e, chunk, mode, nullptr, (img_h / p) * (img_w / p)).total;
 }
 
-int svb_encoder_forward_hw(svb_encoder_t* e, const float* x, int batch, int img_h, int img_w, void* res2, void* res3, void* res4, void* res5,
-                           int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
-    SVB_REQUIRE(e && x && res2 && res3 && res4 && res5 && workspace, "svb_encoder_forward_hw: null argument");
-    SVB_REQUIRE(mode == SVB_MODE_BF16 || mode == SVB_MODE_FP32, "svb_encoder_forward_hw: bad mode %d", mode);
-    SVB_REQUIRE(out_dtype == SVB_DTYPE_F32 || out_dtype == SVB_DTYPE_BF16, "svb_encoder_forward_hw: bad out_dtype %d", out_dtype);
-    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward_hw: batch %d / chunk %d must be positive", batch, chunk);
+int svb_encoder_forward_x(svb_encoder_t* e, const void* x, int x_dtype, int batch, int img_h, int img_w, void* res2, void* res3, void* res4,
+                          void* res5, int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    SVB_REQUIRE(e && x && res2 && res3 && res4 && res5 && workspace, "svb_encoder_forward_x: null argument");
+    SVB_REQUIRE(mode == SVB_MODE_BF16 || mode == SVB_MODE_FP32, "svb_encoder_forward_x: bad mode %d", mode);
+    SVB_REQUIRE(out_dtype == SVB_DTYPE_F32 || out_dtype == SVB_DTYPE_BF16, "svb_encoder_forward_x: bad out_dtype %d", out_dtype);
+    SVB_REQUIRE(x_dtype == SVB_DTYPE_F32 || x_dtype == SVB_DTYPE_BF16 || x_dtype == SVB_DTYPE_F16, "svb_encoder_forward_x: bad input dtype %d", x_dtype);
+    SVB_REQUIRE(batch > 0 && chunk > 0, "svb_encoder_forward_x: batch %d / chunk %d must be positive", batch, chunk);
     const int p = e->cfg.patch_size;
     SVB_REQUIRE(img_h > 0 && img_w > 0 && img_h % (32 * p) == 0 && img_w % (32 * p) == 0,
-                "svb_encoder_forward_hw: image %d x %d: both sides must be multiples of %d (token grid in multiples of 32)", img_h, img_w, 32 * p);
+                "svb_encoder_forward_x: image %d x %d: both sides must be multiples of %d (token grid in multiples of 32)", img_h, img_w, 32 * p);
     const int missing = svb_encoder_missing_params(e);
-    SVB_REQUIRE(missing == 0, "svb_encoder_forward_hw: %d parameters have not been loaded", missing);
+    SVB_REQUIRE(missing == 0, "svb_encoder_forward_x: %d parameters have not been loaded", missing);
     SVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "workspace must be 1024-byte aligned");
     if (chunk > batch) chunk = batch;
+    const bool native = (img_h == e->cfg.img_size && img_w == e->cfg.img_size);
     const int T = (img_h / p) * (img_w / p);
     const size_t need = plan(e, chunk, mode, nullptr, T).total;
     SVB_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
     const Buffers bf = plan(e, chunk, mode, workspace, T);
     const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
-    const size_t in_per_img = (size_t)e->cfg.in_chans * img_h * img_w;
+    const size_t in_per_img = (size_t)e->cfg.in_chans * img_h * img_w * (x_dtype == SVB_DTYPE_F32 ? 4 : 2);     // bytes
     char* res[4] = {(char*)res2, (char*)res3, (char*)res4, (char*)res5};
-    for (int b0 = 0; b0 < batch; b0 += chunk) {
-        const int B = std::min(chunk, batch - b0);
+    std::vector<int> passes;
+    if (native) passes = chunk_schedule(e, batch, chunk);
+    else for (int b0 = 0; b0 < batch; b0 += chunk) passes.push_back(std::min(chunk, batch - b0));
+    int b0 = 0;
+    for (int B : passes) {
         void* outs[4];
         for (int k = 0; k < 4; ++k) outs[k] = res[k] + (size_t)b0 * out_elems_per_image(e, k, img_h, img_w) * osz;
-        int rc = forward_chunk(e, x + (size_t)b0 * in_per_img, B, outs, out_dtype, mode, bf, (cudaStream_t)stream, nullptr, img_h, img_w);
+        int rc = forward_chunk(e, (const char*)x + (size_t)b0 * in_per_img, B, outs, out_dtype, mode, bf, (cudaStream_t)stream, nullptr, img_h, img_w,
+                               x_dtype);
         if (rc) return rc;
+        b0 += B;
     }
     return 0;
+}
+
+int svb_encoder_forward_hw(svb_encoder_t* e, const float* x, int batch, int img_h, int img_w, void* res2, void* res3, void* res4, void* res5,
+                           int out_dtype, int mode, int chunk, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    return svb_encoder_forward_x(e, x, SVB_DTYPE_F32, batch, img_h, img_w, res2, res3, res4, res5, out_dtype, mode, chunk, workspace, workspace_bytes,
+                                 stream);
 }
 
 int svb_resize_pos_embed(const float* src, float* dst, int h0, int w0, int h1, int w1, int dim, svb_stream_t stream) {
@@ -1030,7 +1063,7 @@ int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int gr
 
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream) {
     SVB_REQUIRE(x && out, "svb_im2col: null argument");
-    return im2col_patch(x, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, img, patch, (cudaStream_t)stream);
+    return im2col_patch(x, SVB_DTYPE_F32, out, out_dtype == SVB_DTYPE_BF16, batch, chans, img, img, patch, (cudaStream_t)stream);
 }
 
 int svb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, int out_dtype,

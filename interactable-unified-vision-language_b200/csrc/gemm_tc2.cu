@@ -279,9 +279,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 }
             };
+            // centred hand-over (Epilogue::shift_out): the shifts of the 8 rows this lane writes out (row 4i + lane / 8)
+            float csh[RESID ? 8 : 1];
             if constexpr (RESID) {
                 load_resid(0, q[0]);
                 if (NCH > 1) load_resid(1, q[1]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    csh[i] = 0.f;
+                    const int gr = r0 + 4 * i + (lane >> 3);
+                    if (ep.shift_out && gr < M && n0 < N) {
+                        float cv = ep.shift_in ? __ldg(ep.shift_in + (ep.shift_in_mod ? gr % ep.shift_in_mod : gr)) : 0.f;
+                        if (ep.shift_stats) {
+                            float s1 = 0.f;
+                            const float2* sp = ep.shift_stats + (size_t)gr * ep.shift_parts;
+                            for (int p = 0; p < ep.shift_parts; ++p) s1 += __ldg(sp + p).x;
+                            cv += s1 / (float)ep.shift_dim;
+                        }
+                        csh[i] = cv;
+                        if (n0 == 0 && (lane & 7) == 0) ep.shift_out[gr] = cv;
+                    }
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // bias visible to all epilogue warps
             const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
@@ -389,11 +407,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 const float4 r = q[c & 1][i];
                                 x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
                             }
+                        }
+                        if (gr < M) {
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + epilogue_out_row(ep, gr) * ep.ldo + col0 + pc * 4) = x;
+                        }
+                        if constexpr (RESID) {                // statistics and bf16 copy of the CENTRED row (Epilogue::shift_out)
+                            x.x -= csh[i]; x.y -= csh[i]; x.z -= csh[i]; x.w -= csh[i];
                             st_s[i] = (x.x + x.y) + (x.z + x.w);
                             st_q[i] = fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
                         }
                         if (gr < M) {
-                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + epilogue_out_row(ep, gr) * ep.ldo + col0 + pc * 4) = x;
                             if constexpr (RESID) {
                                 if (ep.out2) {                // bf16 copy of the final rows: the next GEMM's A operand
                                     uint2 u;
@@ -704,6 +727,20 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 float* bs = bias_s + as * 2 * BN;
                 for (int c = etid; c < BN; c += EPI_WARPS * 32) bs[c] = (ep.bias && nt0 + c < N) ? __ldg(ep.bias + nt0 + c) : 0.f;
+                // centred hand-over (Epilogue::shift_out): this row's shift = its mean before the update
+                float cshift = 0.f;
+                if (ep.shift_out && nch > 0 && r0 + lane < M) {
+                    const int row = r0 + lane;
+                    if (ep.shift_in) cshift = __ldg(ep.shift_in + (ep.shift_in_mod ? row % ep.shift_in_mod : row));
+                    if (ep.shift_stats) {
+                        float s1 = 0.f;
+                        const float2* sp = ep.shift_stats + (size_t)row * ep.shift_parts;
+                        for (int p = 0; p < ep.shift_parts; ++p) s1 += __ldg(sp + p).x;
+                        cshift += s1 / (float)ep.shift_dim;
+                    }
+                    if (n0 == 0) ep.shift_out[row] = cshift;
+                }
+                const f32x2 nc2 = f2_pack(-cshift, -cshift);
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
                 const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
                 ptx::mbar_wait(&tmem_full[as], aphase);
@@ -740,15 +777,17 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         f32x2 x1 = f2_pack(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
                         x0 = f2_add(f2_add(x0, f2_pack(bb.x, bb.y)), f2_pack(rr.x, rr.y));
                         x1 = f2_add(f2_add(x1, f2_pack(bb.z, bb.w)), f2_pack(rr.z, rr.w));
+                        // the fp32 residual stream goes back in place (this thread's own piece of its own row) ...
+                        asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowa + ((j ^ swz) << 4)), "l"(x0), "l"(x1) : "memory");
+                        // ... the statistics and the bf16 copy are taken of the centred row
+                        x0 = f2_add(x0, nc2);
+                        x1 = f2_add(x1, nc2);
                         st_s = f2_add(st_s, f2_add(x0, x1));
                         st_q = f2_fma(x0, x0, f2_fma(x1, x1, st_q));
                         v[2 * j] = x0; v[2 * j + 1] = x1;
                     }
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bf16 box is free again
                     __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowa + ((j ^ swz) << 4)), "l"(v[2 * j]), "l"(v[2 * j + 1]) : "memory");
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float a0, a1, a2, a3, a4, a5, a6, a7;

@@ -177,6 +177,7 @@ class ImageEncoderViT(nn.Module):
         self._handle: Optional[C.c_void_p] = None
         self._handle_device: Optional[torch.device] = None
         self._weights_sig = None
+        self._plist = None
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
@@ -228,12 +229,31 @@ class ImageEncoderViT(nn.Module):
         self._handle, self._handle_device, self._weights_sig = h, device, None
         self._ws.clear()
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() replace the parameter storage without touching the version counters
+        self._weights_sig = None
+        self._plist = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        # also reached when a parent module (Sam, the X-Decoder backbone) loads a checkpoint; covers load_state_dict(assign=True)
+        self._weights_sig = None
+        self._plist = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _sync_weights(self, device: torch.device) -> None:
-        """(Re)pack the parameters into the native encoder whenever they changed (load_state_dict, .to(), optimizer)."""
-        sd = self.state_dict(keep_vars=True)
-        sig = tuple((k, v.data_ptr(), v._version) for k, v in sd.items())
+        """(Re)pack the parameters into the native encoder whenever they changed.  Per forward this is ONE pass over the cached
+        parameter list reading the autograd version counters (in-place updates — load_state_dict's copy_, optimizer steps — bump
+        them; storage swaps go through _apply above): ~30 us for ViT-H's 489 entries, no state_dict() walk."""
+        plist = getattr(self, "_plist", None)
+        if plist is None:
+            plist = self._plist = [v for _, v in self.state_dict(keep_vars=True).items()]
+            self._weights_sig = None
+        sig = [v._version for v in plist]
         if sig == self._weights_sig:
             return
+        sd = self.state_dict(keep_vars=True)
+        self._plist = [v for _, v in sd.items()]
         lib = cabi.lib()
         stream = cabi.stream_ptr()
         keep = []
@@ -245,7 +265,7 @@ class ImageEncoderViT(nn.Module):
             cabi.check(lib.svb_encoder_load_param(self._handle, k.encode(), t.data_ptr(), t.numel(), stream),
                        f"load_param({k})")
         torch.cuda.current_stream().synchronize()
-        self._weights_sig = sig
+        self._weights_sig = [v._version for v in self._plist]
 
     def _workspace(self, chunk: int, mode: int, device: torch.device, hw: Optional[Tuple[int, int]] = None) -> torch.Tensor:
         hw = hw or (self.img_size, self.img_size)
@@ -287,8 +307,13 @@ class ImageEncoderViT(nn.Module):
         with torch.cuda.device(device):
             self._prepare(device)
             xf = x.detach()
-            if xf.dtype != torch.float32 or not xf.is_contiguous():
-                xf = xf.float().contiguous()
+            # fp32 / fp16 / bf16 inputs are read as they are (the reference's pipeline feeds fp16 images, pipeline/XDecoderPipeline.py:
+            # 93-95): the cast to the GEMM operand type happens inside the patch-embedding loader
+            xcode = {torch.float32: cabi.DTYPE_F32, torch.float16: cabi.DTYPE_F16, torch.bfloat16: cabi.DTYPE_BF16}.get(xf.dtype)
+            if xcode is None:
+                raise TypeError(f"ImageEncoderViT (B200): input dtype {xf.dtype} is not float32 / float16 / bfloat16")
+            if not xf.is_contiguous():
+                xf = xf.contiguous()
             B, H, W = xf.shape[0], int(xf.shape[2]), int(xf.shape[3])
             od = self.cfg.fpn_dims
             outs = [torch.empty(B, od[k], H // s, W // s, dtype=self.out_dtype, device=device)
@@ -297,22 +322,22 @@ class ImageEncoderViT(nn.Module):
                 return dict(zip(("res2", "res3", "res4", "res5"), outs))
             chunk = max(1, min(int(self.max_chunk), B))
             mode = self._mode()
-            if H == self.img_size and W == self.img_size:
-                ws = self._workspace(chunk, mode, device)
-                base = (ws.data_ptr() + 1023) & ~1023
+            native = (H == self.img_size and W == self.img_size)
+            if not native:
+                # other token grids: the reference's pos_embed / rel_pos resize fallbacks (scope row N3)
+                chunk = max(1, min(chunk, max(1, (4 * self.img_size * self.img_size) // (H * W))))
+            ws = self._workspace(chunk, mode, device, None if native else (H, W))
+            base = (ws.data_ptr() + 1023) & ~1023
+            if native and xcode == cabi.DTYPE_F32:
                 cabi.check(cabi.lib().svb_encoder_forward(
                     self._handle, xf.data_ptr(), B, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
                     outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
                     cabi.stream_ptr()), "svb_encoder_forward")
             else:
-                # other token grids: the reference's pos_embed / rel_pos resize fallbacks (scope row N3)
-                chunk = max(1, min(chunk, max(1, (4 * self.img_size * self.img_size) // (H * W))))
-                ws = self._workspace(chunk, mode, device, (H, W))
-                base = (ws.data_ptr() + 1023) & ~1023
-                cabi.check(cabi.lib().svb_encoder_forward_hw(
-                    self._handle, xf.data_ptr(), B, H, W, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                cabi.check(cabi.lib().svb_encoder_forward_x(
+                    self._handle, xf.data_ptr(), xcode, B, H, W, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
                     outs[3].data_ptr(), self._out_code(), mode, chunk, base, ws.numel() - (base - ws.data_ptr()),
-                    cabi.stream_ptr()), "svb_encoder_forward_hw")
+                    cabi.stream_ptr()), "svb_encoder_forward_x")
         return {"res2": outs[0], "res3": outs[1], "res4": outs[2], "res5": outs[3]}
 
     def forward_uint8(self, images, pixel_mean, pixel_std) -> Dict[str, torch.Tensor]:

@@ -39,6 +39,11 @@ CASES = {
     "vit_l_std": ("vit_l", 1, 0.02, 4096),
     "vit_h_std": ("vit_h", 1, 0.02, 4096),
     "vit_h_stress": ("vit_h", 1, 0.5, 4096),
+    # three DISTINCT images per model, 16384 samples per output: the parity cases at the benchmarked batch / pass sizes
+    # (ViT-B 16, ViT-L 32, ViT-H 13 and 64 images in passes of 12 / 16) are built from these
+    "vit_b_std3": ("vit_b", 3, 0.02, 16384),
+    "vit_l_std3": ("vit_l", 3, 0.02, 16384),
+    "vit_h_std3": ("vit_h", 3, 0.02, 16384),
     # scope row N3: canvases other than 1024 x 1024 run the reference's bicubic pos_embed / linear rel_pos fallbacks
     # (image_encoder.py:111-114,124-132,319-330); 5-tuples carry the (H, W) of the input
     "tiny64_wide": ("tiny64", 1, 0.1, 4096, (1024, 2048)),

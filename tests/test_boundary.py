@@ -153,3 +153,41 @@ def test_decoder_side_drop_ins_load_reference_state_dicts_and_refuse_cpu():
     # autograd-enabled calls are refused as well (forward only)
     with pytest.raises(RuntimeError):
         head(torch.from_numpy(z["x0"]).requires_grad_(), torch.from_numpy(z["mask_features"]), (4, 4))
+
+
+def test_install_into_reference_builds_the_drop_in():
+    """The drop-in mechanism itself: after install_into_reference() the reference's OWN factory (sam/build_sam.py:108-112,
+    `sam_model_registry['vit_b'](checkpoint=None)`) builds this repo's encoder class with the reference's 209 state_dict keys, and a
+    reference state_dict loads strictly.  Needs the reference package: /root/reference in the build container, else the unmodified
+    copy under oracle/_ref that build() makes."""
+    import importlib
+    import sys
+    roots = [p for p in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")) if os.path.exists(os.path.join(p, "sam", "build_sam.py"))]
+    if not roots:
+        pytest.skip("no copy of the reference's sam package here")
+    sys.path.insert(0, roots[0])
+    try:
+        for m in [m for m in sys.modules if m == "sam" or m.startswith("sam.")]:
+            del sys.modules[m]
+        ref_cls = importlib.import_module("sam.modeling.image_encoder").ImageEncoderViT
+        import torch
+        from iuvl_b200 import encoder as enc_mod
+        torch.manual_seed(0)
+        ref_sd = importlib.import_module("sam.build_sam").sam_model_registry["vit_b"](checkpoint=None).image_encoder.state_dict()
+        enc_mod.install_into_reference()
+        sam = importlib.import_module("sam.build_sam").sam_model_registry["vit_b"](checkpoint=None)
+        e = sam.image_encoder
+        assert type(e) is enc_mod.ImageEncoderViT and type(e) is not ref_cls
+        sd = e.state_dict()
+        assert len(sd) == 209 and list(sd) == list(ref_sd)
+        assert all(tuple(sd[k].shape) == tuple(ref_sd[k].shape) and sd[k].dtype == ref_sd[k].dtype for k in sd)
+        res = e.load_state_dict(ref_sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        # _build_sam marks the encoder parameters trainable through named_parameters() (build_sam.py:101-105)
+        assert all(p.requires_grad for n, p in sam.named_parameters() if n.startswith("image_encoder"))
+        with pytest.raises(RuntimeError):
+            e(torch.zeros(1, 3, 1024, 1024))                 # no CPU path
+    finally:
+        sys.path.remove(roots[0])
+        for m in [m for m in sys.modules if m == "sam" or m.startswith("sam.")]:
+            del sys.modules[m]

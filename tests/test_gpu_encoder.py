@@ -115,12 +115,121 @@ def test_tiny_against_cpu_oracle_full_tensors():
 
 @pytest.mark.parametrize("case,precision", [
     ("vit_b_std", "fp32"), ("vit_b_std", "bf16"), ("vit_b_stress", "fp32"), ("vit_b_stress", "bf16"),
-    ("vit_l_std", "bf16"), ("vit_h_std", "fp32"), ("vit_h_std", "bf16"), ("vit_h_stress", "bf16"),
+    ("vit_l_std", "fp32"), ("vit_l_std", "bf16"), ("vit_h_std", "fp32"), ("vit_h_std", "bf16"), ("vit_h_stress", "fp32"),
+    ("vit_h_stress", "bf16"),
 ])
 def test_full_size_against_reference_goldens(case, precision):
     g, cfg, sd, x, enc = _setup(case)
     tol = TOL_FP32 if precision == "fp32" else (TOL_BF16 if case.endswith("std") else 3e-2)
     _check(enc, x, g, precision, tol)
+
+
+def _positions_check(out, g, perm, tol):
+    """Every position p of a batch built as x[perm[p]] against the reference samples of image perm[p] (the golden holds samples of a
+    3-image reference batch: flat indices into (3, C, H, W)); returns the worst rel-L2 over positions and outputs."""
+    worst = 0.0
+    for k in KEYS:
+        shape = [int(v) for v in g[f"out.{k}.shape"]]
+        per = shape[1] * shape[2] * shape[3]
+        idx = torch.from_numpy(g[f"out.{k}.idx"])
+        val = torch.from_numpy(g[f"out.{k}.val"]).double()
+        img, rest = idx // per, idx % per
+        assert tuple(out[k].shape[1:]) == tuple(shape[1:])
+        flat = out[k].reshape(out[k].shape[0], -1)
+        for p, b in enumerate(perm):
+            sel = img == b
+            got = flat[p][rest[sel].to(flat.device)].double().cpu()
+            err = float((got - val[sel]).norm() / val[sel].norm())
+            assert err < tol, f"{k}: position {p} (image {b}): rel-L2 {err:.3e} >= {tol}"
+            worst = max(worst, err)
+    return worst
+
+
+@pytest.mark.parametrize("case,batch,out_dtype", [
+    ("vit_b_std3", 16, torch.float32),       # BASELINE.json configs[1]: ViT-B, batch 16
+    ("vit_l_std3", 32, torch.float32),       # configs[2]: ViT-L, batch 32
+    ("vit_h_std3", 13, torch.float32),       # a pass size with a ragged last GEMM tile (13 * 4096 rows)
+    ("vit_h_std3", 64, torch.bfloat16),      # configs[3] = the benchmarked step: 64 images, passes of 12+12+12+12+16, bf16 outputs
+])
+def test_benchmarked_batch_sizes_against_reference_goldens(case, batch, out_dtype):
+    """The configurations bench.py measures, checked against the unmodified reference: the batch is built from the three
+    golden images in a shuffled order (max_chunk = 16 as in the bench), EVERY position is compared with the reference's
+    samples of its image, and positions that hold the same image must be bit-identical (different rows of the GEMM tiles,
+    different persistent-grid items of the attention kernels, different passes)."""
+    g, cfg, sd, x3, enc = _setup(case)
+    assert x3.shape[0] == 3
+    gen = torch.Generator().manual_seed(batch)
+    perm = [0, 1, 2] + torch.randint(0, 3, (batch - 3,), generator=gen).tolist()
+    perm = [perm[i] for i in torch.randperm(batch, generator=gen).tolist()]
+    x = x3.to(DEV)[torch.tensor(perm, device=DEV)]
+    enc.precision, enc.max_chunk, enc.out_dtype = "bf16", 16, out_dtype
+    with torch.no_grad():
+        out = enc(x)
+    torch.cuda.synchronize()
+    worst = _positions_check(out, g, perm, TOL_BF16)
+    first = {b: perm.index(b) for b in (0, 1, 2)}
+    for k in KEYS:
+        assert out[k].dtype == out_dtype
+        for p, b in enumerate(perm):
+            assert torch.equal(out[k][p], out[k][first[b]]), f"{k}: positions {p} and {first[b]} hold image {b} but differ"
+    print(f"{case} batch {batch}: worst rel-L2 over positions / outputs = {worst:.3e}")
+
+
+@pytest.mark.parametrize("preset,precision", [("vit_b", "fp32"), ("vit_b", "bf16"), ("vit_l", "bf16"), ("vit_h", "fp32"), ("vit_h", "bf16")])
+def test_full_tensor_against_oracle_on_host(preset, precision):
+    """ALL elements of the four embeddings and of the last block's token stream (not samples) against the oracle run on this
+    box's host cores for one full-size image (the oracle itself is pinned to the reference by tests/test_oracle.py).  Besides the
+    whole-tensor rel-L2: the rel-L2 of every (14 x 14 window, head-width channel slice) cell of the token stream and of every
+    window-aligned spatial tile of the embeddings, and the largest absolute error in units of the tensor's RMS — a wrong
+    edge window, last tile or head slice moves a whole-tensor norm by little and these by a lot."""
+    from oracle import sam_vit_oracle as orc
+    cfg = ib.PRESETS[preset]
+    sd = ib.make_state_dict(cfg, 4242, rel_std=0.05)
+    x = ib.make_images(1, cfg, 17)
+    taps = {}
+    ref = orc.encoder_forward_cfg(sd, x, cfg, tap=lambda n, t: taps.__setitem__(n, t.clone()))
+    enc = build_encoder(cfg)
+    enc.load_state_dict(sd)
+    enc.to(DEV)
+    enc.precision = precision
+    enc.enable_taps(True)
+    with torch.no_grad():
+        out = enc(x.to(DEV))
+    torch.cuda.synchronize()
+    tol = TOL_FP32 if precision == "fp32" else TOL_BF16
+    cell_tol, peak_tol = (3 * tol, 0.15) if precision == "bf16" else (3 * tol, 2e-3)
+
+    def cells(a, b, ty, tx, tc):
+        """rel-L2 per (ty x tx spatial tile, tc channels) cell of two (H, W, C) tensors (ragged last tiles included)"""
+        H, W, Cc = a.shape
+        worst = 0.0
+        for y0 in range(0, H, ty):
+            for x0 in range(0, W, tx):
+                da = (a[y0:y0 + ty, x0:x0 + tx] - b[y0:y0 + ty, x0:x0 + tx]).double()
+                rb = b[y0:y0 + ty, x0:x0 + tx].double()
+                n = -(-Cc // tc)
+                pad = n * tc - Cc
+                if pad:
+                    da = torch.nn.functional.pad(da, (0, pad)); rb = torch.nn.functional.pad(rb, (0, pad))
+                e = da.reshape(-1, n, tc).pow(2).sum((0, 2)).sqrt() / rb.reshape(-1, n, tc).pow(2).sum((0, 2)).sqrt()
+                worst = max(worst, float(e.max()))
+        return worst
+
+    last = enc.read_tap(cfg.depth - 1)[0].cpu()
+    want = taps[f"block{cfg.depth - 1}"][0]
+    assert ib.rel_l2(last, want) < tol
+    w = cells(last, want, cfg.window_size, cfg.window_size, cfg.head_dim)
+    assert w < cell_tol, f"token stream: worst (window, head slice) cell rel-L2 {w:.3e}"
+    for k, stride in zip(KEYS, (4, 8, 16, 32)):
+        a, b = out[k][0].float().cpu().permute(1, 2, 0), ref[k][0].permute(1, 2, 0)
+        assert a.shape == b.shape
+        err = ib.rel_l2(a, b)
+        assert err < tol, (k, err)
+        t = max(1, cfg.window_size * 16 // stride)
+        w = cells(a, b, t, t, 64)
+        assert w < cell_tol, f"{k}: worst window-aligned tile rel-L2 {w:.3e}"
+        peak = float((a - b).abs().max() / b.double().pow(2).mean().sqrt())
+        assert peak < peak_tol, f"{k}: largest absolute error = {peak:.3e} x RMS"
 
 
 def test_batch_chunking_and_output_dtype_and_host_path():
@@ -203,6 +312,74 @@ def test_uint8_forward_matches_the_oracle_pipeline():
             assert torch.equal(out[k], same[k])            # same arithmetic as the fp32-canvas entry point
     with torch.no_grad(), pytest.raises(NotImplementedError):
         enc.forward_uint8([torch.zeros(3, 1025, 10, dtype=torch.uint8, device=DEV)], PIXEL_MEAN, PIXEL_STD)
+
+
+def test_half_precision_inputs_are_read_directly():
+    """The reference's pipeline hands the encoder fp16 images (cast_batch_to_half, pipeline/XDecoderPipeline.py:93-95): fp16 / bf16
+    inputs go through the same patch-embedding loader (svb_encoder_forward_x) and give bit-identical embeddings to the fp32 tensor
+    holding the same values."""
+    g, cfg, sd, x, enc = _setup("tiny64_std")
+    for dt in (torch.float16, torch.bfloat16):
+        xh = x.to(DEV).to(dt)
+        for precision in ("bf16", "fp32"):
+            enc.precision = precision
+            with torch.no_grad():
+                a = enc(xh)
+                b = enc(xh.float())
+            for k in KEYS:
+                assert torch.equal(a[k], b[k]), (dt, precision, k)
+    with torch.no_grad(), pytest.raises(TypeError):
+        enc(x.to(DEV).double())
+
+
+def _offset_case():
+    """tiny80 weights whose residual stream carries a common offset of +40 on every channel of every token from the position
+    embedding to the last block (removed again by the last lin2 bias): |row mean| / row std ~ 40."""
+    cfg = ib.PRESETS["tiny80"]
+    sd = ib.make_state_dict(cfg, 31, rel_std=0.05)
+    sd["pos_embed"] = sd["pos_embed"] + 40.0
+    last = f"blocks.{cfg.depth - 1}.mlp.lin2.bias"
+    sd[last] = sd[last] - 40.0
+    return cfg, sd, ib.make_images(1, cfg, 9)
+
+
+def test_layernorm_fold_survives_a_large_common_offset():
+    """The folded LayerNorm reads bf16(x) instead of bf16(LayerNorm(x)): without care its rounding error grows with |row mean| / row
+    std and the single-pass variance cancels.  The producers therefore hand over the CENTRED row (x minus its mean before the update,
+    Epilogue::shift_out) — LayerNorm is invariant under that shift.  With an offset of 40 standard deviations the bf16 bar must hold;
+    the same run with the centring switched off (SVB_LN_CENTRE=0, in a subprocess) must miss it by a wide margin, which shows that
+    this case has the power to detect the problem."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import sam_vit_oracle as orc
+    cfg, sd, x = _offset_case()
+    ref = orc.encoder_forward_cfg(sd, x, cfg)
+    enc = build_encoder(cfg)
+    enc.load_state_dict(sd)
+    enc.to(DEV)
+    enc.precision = "bf16"
+    with torch.no_grad():
+        out = enc(x.to(DEV))
+    errs = {k: ib.rel_l2(out[k], ref[k]) for k in KEYS}
+    assert max(errs.values()) < TOL_BF16, errs
+    code = ("import json, torch, iuvl_b200 as ib\n"
+            "from iuvl_b200.encoder import build_encoder\n"
+            "from tests.test_gpu_encoder import _offset_case, KEYS\n"
+            "from oracle import sam_vit_oracle as orc\n"
+            "cfg, sd, x = _offset_case()\n"
+            "ref = orc.encoder_forward_cfg(sd, x, cfg)\n"
+            "enc = build_encoder(cfg); enc.load_state_dict(sd); enc.to('cuda'); enc.precision = 'bf16'\n"
+            "with torch.no_grad():\n"
+            "    out = enc(x.to('cuda'))\n"
+            "print('ERRS', json.dumps({k: ib.rel_l2(out[k], ref[k]) for k in KEYS}))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SVB_LN_CENTRE="0", PYTHONPATH=root),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    off = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("ERRS")][0][5:])
+    assert max(off.values()) > 3 * max(errs.values()), (off, errs)
 
 
 def test_weights_resync_after_load_state_dict():
