@@ -39,14 +39,16 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays below 2^8 rel
 __device__ __forceinline__ uint64_t desc_k128(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 1024, ptx::LAYOUT_SW128); }
 __device__ __forceinline__ uint64_t desc_k32(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 256, ptx::LAYOUT_SW32); }
 
+// The issue helpers below are called by ALL lanes of an issuer warp under warp-uniform control flow; one elected lane issues
+// (ptx::mma_f16_*_e: uniform-register operands, no per-MMA waterfall loop).
 // D[128 x N] (+)= A[128 x HD] * B[N x HD]^T, both K-major: 64 columns in a 128B-swizzled tile (+ 16 in a 32B-swizzled tile)
 template <int HD>
 __device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t a_main, uint32_t a_tail, uint32_t b_main, uint32_t b_tail,
                                          uint32_t idesc) {
     const uint64_t da = desc_k128(a_main), db = desc_k128(b_main);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
-    if (HD > 64) ptx::mma_f16_ss(d_tmem, desc_k32(a_tail), desc_k32(b_tail), idesc, 1u);
+    for (int k = 0; k < 4; ++k) ptx::mma_f16_ss_e(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+    if (HD > 64) ptx::mma_f16_ss_e(d_tmem, desc_k32(a_tail), desc_k32(b_tail), idesc, 1u);
 }
 
 // O[128 x HD] (+)= P[128 x 16*ksteps] (bf16 in TMEM, two per column) * V[keys x HD] (MN-major in smem)
@@ -57,9 +59,9 @@ __device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint3
     constexpr uint32_t id_tail = ptx::make_idesc_bf16(128, 16, 0, 1);
     for (int k = 0; k < ksteps; ++k) {
         const uint32_t acc = (accumulate || k) ? 1u : 0u;
-        ptx::mma_f16_ts(o_tmem, p_tmem + 8 * k, ptx::make_smem_desc(v_main + k * 2048, 0, 1024, ptx::LAYOUT_SW128), id_main, acc);
+        ptx::mma_f16_ts_e(o_tmem, p_tmem + 8 * k, ptx::make_smem_desc(v_main + k * 2048, 0, 1024, ptx::LAYOUT_SW128), id_main, acc);
         if (HD > 64)
-            ptx::mma_f16_ts(o_tmem + 64, p_tmem + 8 * k, ptx::make_smem_desc(v_tail + k * 512, 0, 256, ptx::LAYOUT_SW32), id_tail, acc);
+            ptx::mma_f16_ts_e(o_tmem + 64, p_tmem + 8 * k, ptx::make_smem_desc(v_tail + k * 512, 0, 256, ptx::LAYOUT_SW32), id_tail, acc);
     }
 }
 // The same product as ONE MMA of N = HD per K step: V in two 64-element atoms along N, `atom_stride` bytes apart (the leading-
@@ -73,7 +75,7 @@ __device__ __forceinline__ void issue_pv_wide(uint32_t o_tmem, uint32_t p_tmem, 
     const uint64_t dv = ptx::make_smem_desc(v_main, HD > 64 ? atom_stride : 0, 1024, ptx::LAYOUT_SW128);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        if (k < ksteps) ptx::mma_f16_ts(o_tmem, p_tmem + 8 * k, dv + 128 * k, id, (accumulate || k) ? 1u : 0u);     // 16 keys = 2048 B
+        if (k < ksteps) ptx::mma_f16_ts_e(o_tmem, p_tmem + 8 * k, dv + 128 * k, id, (accumulate || k) ? 1u : 0u);     // 16 keys = 2048 B
     }
 }
 
@@ -211,8 +213,8 @@ template <int HD>
 __device__ __forceinline__ void issue_qk_ts(uint32_t d_tmem, uint32_t q_tmem, uint32_t b_main, uint32_t b_tail, uint32_t idesc) {
     const uint64_t db = desc_k128(b_main);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ptx::mma_f16_ts(d_tmem, q_tmem + 8 * k, db + 2 * k, idesc, k ? 1u : 0u);
-    if (HD > 64) ptx::mma_f16_ts(d_tmem, q_tmem + 32, desc_k32(b_tail), idesc, 1u);
+    for (int k = 0; k < 4; ++k) ptx::mma_f16_ts_e(d_tmem, q_tmem + 8 * k, db + 2 * k, idesc, k ? 1u : 0u);
+    if (HD > 64) ptx::mma_f16_ts_e(d_tmem, q_tmem + 32, desc_k32(b_tail), idesc, 1u);
 }
 
 template <int HD, int NST, bool PH, bool POLY>

@@ -120,6 +120,40 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- WARP-UNIFORM issue (the whole warp executes the call, one elected lane issues) ----
+// Inside `if (lane == 0)` every operand of a tcgen05.mma is a per-thread value for the compiler: it moves each of them into a
+// uniform register with R2UR inside a "waterfall" loop (ELECT, 4-5 x R2UR.BROADCAST, PLOP3, UTCHMMA, BRA.U.ANY) — ~14 dependent
+// instructions per MMA, measured as 60-110 cycles of issue per MMA where the tensor pipe needs 44.5.  When the call site is
+// reached by all 32 lanes under warp-uniform control flow (warp index broadcast with __shfl_sync, loop counters and addresses
+// derived from uniform values) the operands live in uniform registers and the MMAs issue back to back (UTCHMMA ... UR, one
+// instruction each).  The election happens inside the asm block, so there is no divergent branch around it.
+__device__ __forceinline__ void mma_f16_ss_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred P, q;\n\telect.sync _|P, 0xffffffff;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "@P tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred P, q;\n\telect.sync _|P, 0xffffffff;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "@P tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, q;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_e(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t"
+        "@P tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t@P mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
