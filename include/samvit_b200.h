@@ -245,6 +245,11 @@ int svb_resize_bicubic_aa(const float* src, float* tmp, float* dst, int maps, in
 /* out (batch, heads, per_sample) bool = sigmoid(v (batch, per_sample)) < 0.5, repeated over the heads (:467). */
 int svb_mask_threshold_heads(const float* v, void* out_bool, int batch, int heads, int64_t per_sample, svb_stream_t stream);
 
+/* The normalisation inside LanguageEncoder.compute_similarity (modeling/language/vlpencoder.py:242,244), which forward_prediction_heads
+ * applies to the class embeddings (xdecoder.py:453-455): out[r, :] = scale * x[r, :] / (|x[r, :]| + eps); x fp32, out of `out_dtype`.
+ * (The class-embedding projection, the similarity against the text embeddings and the box MLP are svb_linear calls.) */
+int svb_l2_normalize_rows(const float* x, void* out, int out_dtype, int rows, int dim, float eps, float scale, svb_stream_t stream);
+
 /* ---- scope row N4, second slice: the attention core of `CrossAttentionLayer.forward_post` (modeling/interface/modules.py:95-106), i.e.
  * nn.MultiheadAttention's softmax((q / sqrt(d)) k^T + mask) v for `queries` <= 128 tokens over `keys` image positions.  q (queries, batch,
  * heads * 64), k / v (keys, batch, heads * 64) sequence-first as the reference passes them, element type `dtype`; mask_bool

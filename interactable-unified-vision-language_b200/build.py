@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsamvit_b200.so")
-SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu"]
+SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "attention_win3.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu", "xattn_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -27,7 +27,10 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    missing = [s for s in srcs if not os.path.exists(s)]
+    if missing:
+        raise FileNotFoundError("CUDA sources listed in build.SOURCES are missing: " + ", ".join(missing))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "samvit_b200.h"))
     objdir = os.path.join(HERE, "build")
@@ -55,6 +58,60 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return OUT
+
+
+SASS_MNEMONICS = ("UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "HMMA", "MUFU.EX2", "R2UR")
+
+
+def sass_summary(out_path: str) -> str:
+    """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native kernel (B200_PROFILING.md: tcgen05.mma = UTC*MMA,
+    tcgen05.ld / st = LDTM / STTM, TMA = UTMALDG / UTMASTG / UTMAREDG) from `cuobjdump -sass` of the built objects, plus registers /
+    spills from the ptxas logs.  Written to profiles/sass_summary.txt by __graft_entry__.build()."""
+    import re
+    objdir = os.path.join(HERE, "build")
+    cuobjdump = os.path.join(os.path.dirname(NVCC), "cuobjdump")
+    cufilt = os.path.join(os.path.dirname(NVCC), "cu++filt")
+    rows = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        if not os.path.exists(obj):
+            continue
+        r = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True)
+        cur, counts = None, {}
+        for line in r.stdout.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                cur = m.group(1)
+                counts[cur] = dict.fromkeys(SASS_MNEMONICS, 0)
+                continue
+            if cur is None:
+                continue
+            for mn in SASS_MNEMONICS:
+                if re.search(r"\b" + re.escape(mn), line):
+                    counts[cur][mn] += 1
+        regs = {}
+        log = os.path.join(objdir, src[:-3] + ".ptxas.log")
+        if os.path.exists(log):
+            txt = open(log).read()
+            for m in re.finditer(r"Function properties for (\S+)\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n"
+                                 r"ptxas info\s+: Used (\d+) registers", txt):
+                regs[m.group(1)] = (int(m.group(5)), int(m.group(3)), int(m.group(4)))
+        names = list(counts)
+        dem = subprocess.run([cufilt] + names, capture_output=True, text=True).stdout.splitlines() if names else []
+        for n, d in zip(names, dem if len(dem) == len(names) else names):
+            d = re.sub(r"\(anonymous namespace\)::", "", d)
+            d = re.sub(r"\((CUtensorMap_st|svb::|const |float|int|void|unsigned|long|double|__nv_bfloat16|bool|char).*$", "", d)[:110]
+            rg = regs.get(n, ("?", "?", "?"))
+            rows.append((src, d, counts[n], rg))
+    lines = ["# Per-kernel SASS evidence (regenerated by __graft_entry__.build(): cuobjdump -sass of the sm_100a objects + ptxas -v logs)",
+             "# columns: " + " ".join(SASS_MNEMONICS) + " | registers, spill stores / loads (bytes)", ""]
+    for src, d, c, rg in rows:
+        lines.append(f"{src:18s} {d}")
+        lines.append("    " + "  ".join(f"{mn}={c[mn]}" for mn in SASS_MNEMONICS if c[mn]) + f"  | regs {rg[0]}, spills {rg[1]}/{rg[2]}")
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    with open(out_path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return out_path
 
 
 if __name__ == "__main__":

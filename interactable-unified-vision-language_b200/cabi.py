@@ -77,6 +77,7 @@ SYMBOLS = {
     "svb_mask_threshold_heads": (_i, [_vp, _vp, _i, _i, _i64, _vp]),
     "svb_masked_cross_attention_workspace": (_i64, [_i, _i, _i, _i]),
     "svb_masked_cross_attention": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "svb_l2_normalize_rows": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "svb_mask_clear_full_rows": (_i, [_vp, _i64, _i, _vp]),
     "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
     "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),

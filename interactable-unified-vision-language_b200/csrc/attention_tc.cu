@@ -21,8 +21,7 @@
 //                  tensor core), 1 TMA warp, 1 MMA warp; K/V tiles of 128 keys through an NST-deep ring.
 // Windowed kernel: CTA = one query tile (9 or 5 window rows) of one (image, window, head); 4 softmax warps + TMA + MMA;
 //                  2 CTAs per SM.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "attention_common.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -32,125 +31,6 @@ int encode_tmap_nd_bf16(CUtensorMap* map, const void* ptr, int rank, const uint6
                         const uint32_t* box, int swizzle_bytes);
 
 namespace {
-
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units: P stays below 2^8 relative to the reference maximum
-
-__device__ __forceinline__ uint64_t desc_k128(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 1024, ptx::LAYOUT_SW128); }
-__device__ __forceinline__ uint64_t desc_k32(uint32_t addr) { return ptx::make_smem_desc(addr, 0, 256, ptx::LAYOUT_SW32); }
-
-// The issue helpers below are called by ALL lanes of an issuer warp under warp-uniform control flow; one elected lane issues
-// (ptx::mma_f16_*_e: uniform-register operands, no per-MMA waterfall loop).
-// D[128 x N] (+)= A[128 x HD] * B[N x HD]^T, both K-major: 64 columns in a 128B-swizzled tile (+ 16 in a 32B-swizzled tile)
-template <int HD>
-__device__ __forceinline__ void issue_qk(uint32_t d_tmem, uint32_t a_main, uint32_t a_tail, uint32_t b_main, uint32_t b_tail,
-                                         uint32_t idesc) {
-    const uint64_t da = desc_k128(a_main), db = desc_k128(b_main);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ptx::mma_f16_ss_e(d_tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
-    if (HD > 64) ptx::mma_f16_ss_e(d_tmem, desc_k32(a_tail), desc_k32(b_tail), idesc, 1u);
-}
-
-// O[128 x HD] (+)= P[128 x 16*ksteps] (bf16 in TMEM, two per column) * V[keys x HD] (MN-major in smem)
-template <int HD>
-__device__ __forceinline__ void issue_pv(uint32_t o_tmem, uint32_t p_tmem, uint32_t v_main, uint32_t v_tail, int ksteps,
-                                         bool accumulate) {
-    constexpr uint32_t id_main = ptx::make_idesc_bf16(128, 64, 0, 1);
-    constexpr uint32_t id_tail = ptx::make_idesc_bf16(128, 16, 0, 1);
-    for (int k = 0; k < ksteps; ++k) {
-        const uint32_t acc = (accumulate || k) ? 1u : 0u;
-        ptx::mma_f16_ts_e(o_tmem, p_tmem + 8 * k, ptx::make_smem_desc(v_main + k * 2048, 0, 1024, ptx::LAYOUT_SW128), id_main, acc);
-        if (HD > 64)
-            ptx::mma_f16_ts_e(o_tmem + 64, p_tmem + 8 * k, ptx::make_smem_desc(v_tail + k * 512, 0, 256, ptx::LAYOUT_SW32), id_tail, acc);
-    }
-}
-// The same product as ONE MMA of N = HD per K step: V in two 64-element atoms along N, `atom_stride` bytes apart (the leading-
-// dimension byte offset of an MN-major operand; pinned by tests/test_gpu_probe.py).  Measured (tools/mma_rate.py): a tcgen05.mma
-// with its A operand in TMEM costs >= 44.5 cycles whatever N is, so the N = 64 + N = 16 pair costs 89 cycles per K step against
-// 44.5 for one N = 80 MMA (arithmetic floor 40).
-template <int HD>
-__device__ __forceinline__ void issue_pv_wide(uint32_t o_tmem, uint32_t p_tmem, uint32_t v_main, uint32_t atom_stride, int ksteps,
-                                              bool accumulate) {
-    constexpr uint32_t id = ptx::make_idesc_bf16(128, HD, 0, 1);
-    const uint64_t dv = ptx::make_smem_desc(v_main, HD > 64 ? atom_stride : 0, 1024, ptx::LAYOUT_SW128);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (k < ksteps) ptx::mma_f16_ts_e(o_tmem, p_tmem + 8 * k, dv + 128 * k, id, (accumulate || k) ? 1u : 0u);     // 16 keys = 2048 B
-    }
-}
-
-// 2^x for a pair of exponents on the FMA / ALU pipes instead of the MUFU (16 ex2 per clock and SM is what bounds both softmax
-// loops): round-to-nearest split x = j + f with |f| <= 0.5 by the 1.5 * 2^23 trick, degree-3 minimax polynomial of 2^f (maximum
-// relative error 7.5e-5, far below the bf16 rounding of P), the exponent added by integer arithmetic.  x is clamped at -120.
-__device__ __forceinline__ void exp2_poly_pair(float a0, float a1, float& p0, float& p1) {
-    const f32x2 x = f2_pack(fmaxf(a0, -120.f), fmaxf(a1, -120.f));
-    const f32x2 t = f2_add(x, f2_pack(12582912.f, 12582912.f));
-    const f32x2 j = f2_add(t, f2_pack(-12582912.f, -12582912.f));
-    const f32x2 f = f2_fma(j, f2_pack(-1.f, -1.f), x);
-    f32x2 q = f2_fma(f2_pack(0.05517163872718811f, 0.05517163872718811f), f, f2_pack(0.2426111251115799f, 0.2426111251115799f));
-    q = f2_fma(q, f, f2_pack(0.6932609677314758f, 0.6932609677314758f));
-    q = f2_fma(q, f, f2_pack(0.9999280571937561f, 0.9999280571937561f));
-    float t0, t1, q0, q1;
-    f2_unpack(t, t0, t1);
-    f2_unpack(q, q0, q1);
-    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
-    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
-}
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3: two comparisons per issue slot
-    return d;
-}
-__device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
-    float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-    for (int e = 0; e < 32; e += 8) {
-        m0 = fmax3(m0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        m1 = fmax3(m1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        m2 = fmax3(m2, __uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-        m3 = fmax3(m3, __uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
-    }
-    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
-
-// write HD normalised outputs of one query row
-template <int HD>
-__device__ __forceinline__ void store_row(bf16* dst, uint32_t o_tmem, float inv) {
-    uint32_t v[32];
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-        ptx::tmem_ld_x32(o_tmem + c, v);
-        ptx::tmem_ld_wait_dep(v);
-        if (dst) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-                u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-                u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-                u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-                reinterpret_cast<uint4*>(dst + c)[j] = u;
-            }
-        }
-    }
-    if (HD > 64) {
-        uint32_t w[16];
-        ptx::tmem_ld_x16(o_tmem + 64, w);
-        ptx::tmem_ld_wait_dep(w);
-        if (dst) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(w[8 * j + 0]) * inv, __uint_as_float(w[8 * j + 1]) * inv);
-                u.y = pack_bf16x2(__uint_as_float(w[8 * j + 2]) * inv, __uint_as_float(w[8 * j + 3]) * inv);
-                u.z = pack_bf16x2(__uint_as_float(w[8 * j + 4]) * inv, __uint_as_float(w[8 * j + 5]) * inv);
-                u.w = pack_bf16x2(__uint_as_float(w[8 * j + 6]) * inv, __uint_as_float(w[8 * j + 7]) * inv);
-                reinterpret_cast<uint4*>(dst + 64)[j] = u;
-            }
-        }
-    }
-}
 
 // ================================================================================================================
 //                                              GLOBAL ATTENTION (64 x 64 keys)
@@ -217,7 +97,7 @@ __device__ __forceinline__ void issue_qk_ts(uint32_t d_tmem, uint32_t q_tmem, ui
     if (HD > 64) ptx::mma_f16_ts_e(d_tmem, q_tmem + 32, desc_k32(b_tail), idesc, 1u);
 }
 
-template <int HD, int NST, bool PH, bool POLY>
+template <int HD, int NST, bool PH, int POLY>
 __global__ void __launch_bounds__(352, 1)
 attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_constant__ CUtensorMap tm_tail,
                     const __grid_constant__ CUtensorMap tm_rw_main, const __grid_constant__ CUtensorMap tm_rw_tail,
@@ -234,7 +114,8 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index as a provably warp-uniform value: the issuer warps' address arithmetic then stays in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int row0 = b * T + pair * 256;
     const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
@@ -299,9 +180,11 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
         }
     } else if (warp == 9 || warp == 10) {
         // ===================== MMA issuers: one per query tile =====================
-        // (a single issuing thread needs ~40 cycles of scalar work per tcgen05.mma + commit: 52 MMAs + 10 commits per 128 keys
-        // made ONE issuer the bottleneck of this pipeline, 2690 cycles per 128 keys; the two tiles' chains are independent)
-        if (lane == 0) {
+        // All 32 lanes run this loop (warp-uniform control flow); every tcgen05.mma / commit is issued by one elected lane inside
+        // the asm block, with operands in uniform registers.  (Under `if (lane == 0)` each MMA cost a ~14-instruction waterfall
+        // loop, 60-110 cycles of issue per MMA for a 44.5-cycle MMA: 52 MMAs + 10 commits per 128 keys made ONE issuer the
+        // bottleneck of this pipeline, and two still spent ~2600 of 4150 cycles per 128 keys issuing.)
+        {
             const int i = warp - 9;
             constexpr uint32_t id_w = ptx::make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 64, 0, 0);
@@ -314,7 +197,7 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             // decomposed rel-pos products: Q.Rw^T -> both S buffers of the tile (128 columns), Q.Rh[4*pair ..]^T -> O_i columns
             issue_qk<HD>(tmem + C::TM_S + 128 * i, q_main, q_tail, base + C::OFF_RW, base + C::OFF_RW + C::T_MAIN, id_w);
             issue_qk<HD>(o_tm, q_main, q_tail, base + C::OFF_RH, base + C::OFF_RH + C::RH_MAIN, id_rh);
-            ptx::mma_commit(&bars[C::B_BIAS + i]);
+            ptx::mma_commit_e(&bars[C::B_BIAS + i]);
             // S_i(0), S_i(1): the two halves of key tile 0
             ptx::mbar_wait(&bars[C::B_KFULL + 0], 0);
             ptx::mbar_wait(&bars[C::B_BREAD + i], 0);              // bias products consumed (S_i / O_i columns are free), Q_i is in TMEM
@@ -322,12 +205,13 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
             for (int hb = 0; hb < 2; ++hb) {
                 issue_qk_ts<HD>(tmem + C::TM_S + 64 * (2 * i + hb), q_tm, base + C::OFF_K + hb * HALF_MAIN,
                                 base + C::OFF_K + C::T_MAIN + hb * HALF_TAIL, id_s);
-                ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
+                ptx::mma_commit_e(&bars[C::B_SFULL + 2 * i + hb]);
             }
-            ptx::mma_commit(&bars[C::B_KEMPTY + 0]);
+            ptx::mma_commit_e(&bars[C::B_KEMPTY + 0]);
             long long ipc[3] = {0, 0, 0};
             long long itp = PH ? clock64() : 0;
 #define SVB_IPH(k) if (PH) { const long long tn = clock64(); ipc[k] += tn - itp; itp = tn; }
+#pragma unroll 1
             for (int h = 0; h < NH; ++h) {
                 const int hb = h & 1, jt = h >> 1, st = jt % NST;
                 const bool more = (h + 2 < NH);
@@ -343,19 +227,19 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                 SVB_IPH(1)
                 ptx::tc_fence_after();
                 issue_pv_wide<HD>(o_tm, s_i, base + C::OFF_V + st * C::VTILE + hb * HALF_MAIN, C::T_MAIN, 4, h > 0);
-                ptx::mma_commit(&bars[C::B_PVDONE + i]);
-                if (h == NH - 1) ptx::mma_commit(&bars[C::B_ODONE + i]);     // O_i is complete
-                if (hb == 1) ptx::mma_commit(&bars[C::B_VEMPTY + st]);
+                ptx::mma_commit_e(&bars[C::B_PVDONE + i]);
+                if (h == NH - 1) ptx::mma_commit_e(&bars[C::B_ODONE + i]);     // O_i is complete
+                if (hb == 1) ptx::mma_commit_e(&bars[C::B_VEMPTY + st]);
                 if (more) {
-                    // in-order execution of this thread's MMAs: the overwrite of S_i^hb / P_i^hb follows the PV above
+                    // in-order execution of this warp's MMAs: the overwrite of S_i^hb / P_i^hb follows the PV above
                     issue_qk_ts<HD>(s_i, q_tm, base + C::OFF_K + st2 * C::TILE + hb * HALF_MAIN,
                                     base + C::OFF_K + st2 * C::TILE + C::T_MAIN + hb * HALF_TAIL, id_s);
-                    ptx::mma_commit(&bars[C::B_SFULL + 2 * i + hb]);
-                    if (hb == 1) ptx::mma_commit(&bars[C::B_KEMPTY + st2]);
+                    ptx::mma_commit_e(&bars[C::B_SFULL + 2 * i + hb]);
+                    if (hb == 1) ptx::mma_commit_e(&bars[C::B_KEMPTY + st2]);
                 }
             }
 #undef SVB_IPH
-            if (PH && phase_clocks && i == 0) {
+            if (PH && phase_clocks && i == 0 && lane == 0) {
                 atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 3, (unsigned long long)ipc[0]);       // wait K / V
                 atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 4, (unsigned long long)ipc[1]);       // wait P
                 atomicAdd(reinterpret_cast<unsigned long long*>(phase_clocks) + 5, (unsigned long long)ipc[2]);       // issue
@@ -534,9 +418,10 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
                     float a0, a1, a2, a3;                                                                \
                     f2_unpack(x01, a0, a1);                                                              \
                     f2_unpack(x23, a2, a3);                                                              \
-                    const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1);                      \
-                    float p2, p3;                                                                        \
-                    if (POLY && ((e >> 2) & 1)) exp2_poly_pair(a2, a3, p2, p3);   /* a quarter of the exponentials */ \
+                    float p0, p1, p2, p3;                                                                \
+                    if (poly_pair(e / 2, POLY)) exp2_poly_pair(a0, a1, p0, p1);   /* POLY of every 8 pairs on the FMA pipe */ \
+                    else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                         \
+                    if (poly_pair(e / 2 + 1, POLY)) exp2_poly_pair(a2, a3, p2, p3);                      \
                     else { p2 = ptx::ex2_approx(a2); p3 = ptx::ex2_approx(a3); }                         \
                     l01 = f2_add(l01, f2_pack(p0, p1));                                                  \
                     l23 = f2_add(l23, f2_pack(p2, p3));                                                  \
@@ -578,114 +463,6 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem, C::TM_COLS);
     }
-}
-
-// One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
-// the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
-// the reference maximum).  Two passes over TMEM: the exact row maximum, then exp2 / sum / pack with packed fp32x2 arithmetic.
-template <bool POLY>
-__device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
-    uint32_t va[32], vb[32], vt[4];
-    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
-    // ---- pass A: the row's EXACT maximum exponent.  Per key row kh the maximum of s * scale + w term (an FMA and half a
-    // three-input maximum per element: the pairs (k, k+1) never straddle a key row, 14 is even), then + h term.  A reference that
-    // was really attained cannot make the whole row underflow, whatever the spread of the bias terms (an upper bound built from
-    // the largest bias terms could: P = exp2(x - bound) flushes to zero once the bound overshoots by ~126). ----
-    float mk[14];
-#pragma unroll
-    for (int k = 0; k < 14; ++k) mk[k] = -INFINITY;
-#define SVB_WIN_A(V, CHUNK)                                                                              \
-    _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                                  \
-        const int k0 = 32 * (CHUNK) + e;                                                                 \
-        const f32x2 x = f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2, f2_pack(bwl[k0 % 14], bwl[(k0 + 1) % 14])); \
-        float a0, a1;                                                                                    \
-        f2_unpack(x, a0, a1);                                                                            \
-        mk[k0 / 14] = fmax3(mk[k0 / 14], a0, a1);                                                        \
-    }
-    ptx::tmem_ld_x32(s_tmem, va);
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 32, vb);
-    SVB_WIN_A(va, 0)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 64, va);
-    SVB_WIN_A(vb, 1)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 96, vb);
-    SVB_WIN_A(va, 2)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 128, va);
-    SVB_WIN_A(vb, 3)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 160, vb);
-    SVB_WIN_A(va, 4)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x4(s_tmem + 192, vt);
-    SVB_WIN_A(vb, 5)
-#undef SVB_WIN_A
-    ptx::tmem_ld_wait_dep(vt);
-    mk[13] = fmaxf(mk[13], fmaxf(fmaxf(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]), fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14])),
-                                 fmaxf(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]), fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]))));
-    float m_ref = mk[0] + bhm[0];
-#pragma unroll
-    for (int k = 1; k < 14; ++k) m_ref = fmaxf(m_ref, mk[k] + bhm[k]);
-#pragma unroll
-    for (int k = 0; k < 14; ++k) bhm[k] -= m_ref;
-    // ---- pass B ----
-    f32x2 l01 = f2_pack(0.f, 0.f);
-#define SVB_WIN_B(V, CHUNK)                                                                              \
-    {                                                                                                \
-        uint32_t pk[16];                                                                             \
-        _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                          \
-            const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                            \
-            const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,               \
-                                          f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
-            float a0, a1;                                                                            \
-            f2_unpack(x, a0, a1);                                                                    \
-            float p0, p1;                                                                            \
-            if (POLY && ((e >> 1) & 3) == 3) exp2_poly_pair(a0, a1, p0, p1);   /* a quarter of the exponentials */ \
-            else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                             \
-            l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
-            pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
-        }                                                                                            \
-        ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
-    }
-    ptx::tmem_ld_x32(s_tmem, va);
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 32, vb);
-    SVB_WIN_B(va, 0)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 64, va);
-    SVB_WIN_B(vb, 1)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 96, vb);
-    SVB_WIN_B(va, 2)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 128, va);
-    SVB_WIN_B(vb, 3)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 160, vb);
-    SVB_WIN_B(va, 4)
-    ptx::tmem_ld_wait_dep(vb);
-    SVB_WIN_B(vb, 5)
-#undef SVB_WIN_B
-    {
-        // keys 192..195 (vt was loaded in pass A and is still live) + zero columns for keys 196..207
-        uint32_t pk[8];
-        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]) + bhm[192 / 14]);
-        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14]);
-        const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14]);
-        const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14]);
-        l01 = f2_add(l01, f2_pack(p0 + p2, p1 + p3));
-        pk[0] = pack_bf16x2(p0, p1);
-        pk[1] = pack_bf16x2(p2, p3);
-#pragma unroll
-        for (int e = 2; e < 8; ++e) pk[e] = 0u;
-        ptx::tmem_st_x8(s_tmem + 96, pk);
-    }
-    ptx::tmem_st_wait();
-    float l0, l1;
-    f2_unpack(l01, l0, l1);
-    return l0 + l1;
 }
 
 // ================================================================================================================
@@ -733,26 +510,10 @@ struct WinPMaps {
     CUtensorMap o0, o1, o0t, o1t;        // stores: boxes (64|16,14,9|5,1) of out viewed as [B,64,64,D]
 };
 
-// r[j] <- r[j + sh] for a per-thread shift sh in [0, 13]: four conditional-move stages
-__device__ __forceinline__ void barrel_shift27(float (&r)[27], int sh) {
-#pragma unroll
-    for (int bit = 1; bit <= 8; bit <<= 1) {
-        const bool on = (sh & bit) != 0;
-#pragma unroll
-        for (int j = 0; j + bit < 27; ++j) r[j] = on ? r[j + bit] : r[j];
-    }
-}
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-
-template <int HD, bool POLY, bool PH>
+template <int HD, int POLY, bool PH>
 __global__ void __launch_bounds__(384, 1)
 attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
-                              long long* __restrict__ phase_clocks) {
+                              long long* __restrict__ phase_clocks, int l2_ahead) {
     using C = WPCfg<HD>;
     constexpr int WS = 14, NWS = 5;
     extern __shared__ uint8_t smem_raw[];
@@ -760,7 +521,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
     uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // provably warp-uniform
 
     if (warp == 8 && lane == 0) {
         ptx::prefetch_tmap(&maps.kv);
@@ -838,17 +599,34 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                 } else {
                     ptx::tma_load_4d(v, &maps.kv, &bars[C::B_VFULL + st], cv, x0, y0, b);
                 }
+                // the kernel moves 48 MB per image and block through a 2-stage ring whose stages free up late: keep HBM -> L2
+                // traffic in flight for the items after the one in the ring (the loads above then hit L2)
+                for (int ahead = 1; ahead <= l2_ahead; ++ahead) {
+                    const int pi = item + (ahead + 0) * gridDim.x;
+                    if (pi < num_items) {
+                        int pb, pwy, pwx, ph_;
+                        decode(pi, pb, pwy, pwx, ph_);
+                        const int px0 = pwx * WS, py0 = pwy * WS;
+                        for (int part = 0; part < 3; ++part) {
+                            const int cc = part * D + ph_ * HD;
+                            ptx::tma_prefetch_l2_4d(&maps.kv, cc, px0, py0, pb);
+                            if (HD > 64) ptx::tma_prefetch_l2_4d(&maps.kvt, cc + 64, px0, py0, pb);
+                        }
+                    }
+                }
             }
         }
     } else if (warp == 9 || warp == 10) {
         // ===================== MMA issuers: one per query tile =====================
-        if (lane == 0) {
+        // all 32 lanes run the loop, one elected lane issues (uniform-register operands: see ptx::mma_f16_ss_e)
+        {
             constexpr uint32_t id_r = ptx::make_idesc_bf16(128, 64, 0, 0);
             constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 208, 0, 0);
             const int i = warp - 9;
             ptx::mbar_wait(&bars[C::B_RFULL], 0);
             int it = 0;
             uint32_t n = 0;                                        // active items of this tile so far (barrier phases)
+#pragma unroll 1
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
                 const int st = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
@@ -858,7 +636,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                     // tile 1 is all padding here: just release the stage — but only once THIS use of the stage has begun (its
                     // loads landed), otherwise the arrival would be counted in the previous use's phase
                     ptx::mbar_wait(&bars[C::B_QKFULL + st], ph);
-                    ptx::mbar_arrive(&bars[C::B_EMPTY + st]);
+                    ptx::mbar_arrive_e(&bars[C::B_EMPTY + st]);
                     continue;
                 }
                 const uint32_t q = base + st * C::STAGE + i * C::QT, k = base + st * C::STAGE + C::OFF_K, v = base + st * C::STAGE + C::OFF_V;
@@ -867,11 +645,11 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                 // columns [0,64) of S_i: the previous item's P_i there was consumed by its PV (same issuer, in-order tensor pipe);
                 // its O_i (columns 112..191) is only overwritten by the S MMA below, issued after the group has loaded O_i
                 issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
-                ptx::mma_commit(&bars[C::B_BIAS + i]);
+                ptx::mma_commit_e(&bars[C::B_BIAS + i]);
                 ptx::mbar_wait(&bars[C::B_BREAD + i], n & 1);      // rel-pos products consumed (and the previous O_i loaded)
                 ptx::tc_fence_after();
                 issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, k, k + C::K_MAIN, id_s);
-                ptx::mma_commit(&bars[C::B_SFULL + i]);
+                ptx::mma_commit_e(&bars[C::B_SFULL + i]);
                 ptx::mbar_wait(&bars[C::B_VFULL + st], ph);
                 ptx::mbar_wait(&bars[C::B_PFULL + i], n & 1);      // P_i is in TMEM
                 ptx::tc_fence_after();
@@ -880,11 +658,11 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                     const uint64_t dv = ptx::make_smem_desc(v, C::V_ATOM, 256, ptx::LAYOUT_SW32);
 #pragma unroll
                     for (int kk = 0; kk < 13; ++kk)                // 16 keys = 512 B inside an atom
-                        ptx::mma_f16_ts(tmem + 208 * i + 112, tmem + 208 * i + 8 * kk, dv + 32 * kk, id_pv, kk ? 1u : 0u);
+                        ptx::mma_f16_ts_e(tmem + 208 * i + 112, tmem + 208 * i + 8 * kk, dv + 32 * kk, id_pv, kk ? 1u : 0u);
                 } else {
                     issue_pv<HD>(tmem + 208 * i + 112, tmem + 208 * i, v, v + C::K_MAIN, 13, false);
                 }
-                ptx::mma_commit(&bars[C::B_PVDONE + i]);
+                ptx::mma_commit_e(&bars[C::B_PVDONE + i]);
                 ++n;
             }
         }
@@ -1071,20 +849,20 @@ fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int
     }
 }
 
-// rel_pos table (L, hd) fp32 -> rows [row_off, row_off + L) of the packed bf16 table
-__global__ void pack_rel_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int L, int hd, int row_off) {
-    const int n = L * hd;
+// rel_pos table (L, hd) fp32 rows [src0, src0 + n) -> rows [row_off, row_off + n) of the packed bf16 table
+__global__ void pack_rel_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int n_rows, int hd, int src0, int row_off) {
+    const int n = n_rows * hd;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        dst[(size_t)row_off * hd + i] = __float2bfloat16_rn(src[i]);
+        dst[(size_t)row_off * hd + i] = __float2bfloat16_rn(src[(size_t)src0 * hd + i]);
 }
 
 // A quarter of the softmax exponentials on the FMA pipe (exp2_poly_pair).  Measured: windowed kernel 118.5 -> 114.5 us per 8 images
 // (its two softmax groups are MUFU-bound while they overlap), global kernel 920 -> 947 us (issue / latency-bound: the extra
 // instructions cost more than the MUFU slots they free).  Defaults: on for the windowed kernel (SVB_ATTNW_POLY=0 turns it off),
 // off for the global kernel (SVB_ATTNG_POLY=1 turns it on).
-static bool exp2_poly(bool windowed) {
-    static const bool w = [] { const char* e = getenv("SVB_ATTNW_POLY"); return !(e && atoi(e) == 0); }();
-    static const bool g = [] { const char* e = getenv("SVB_ATTNG_POLY"); return e && atoi(e) != 0; }();
+static int exp2_poly(bool windowed) {
+    static const int w = [] { const char* e = getenv("SVB_ATTNW_POLY"); return e ? atoi(e) : 2; }();
+    static const int g = [] { const char* e = getenv("SVB_ATTNG_POLY"); return e ? atoi(e) : 2; }();
     return windowed ? w : g;
 }
 
@@ -1110,19 +888,18 @@ int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     dim3 grid(T / 256, p.heads, p.batch);
-    static bool attr2_set = false;
-    if (!attr2_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_global2_kernel<HD, NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr2_set = true;
-    }
-    if (p.phase_clocks)
-        attn_global2_kernel<HD, NST, true, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, p.phase_clocks, 1);
-    else if (exp2_poly(false))
-        attn_global2_kernel<HD, NST, false, true><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 1);
-    else
-        attn_global2_kernel<HD, NST, false, false><<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, nullptr, 1);
+    auto launch = [&](auto kern, long long* clocks) -> int {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        kern<<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, clocks, 1);
+        return 0;
+    };
+    const int k8 = exp2_poly(false);
+    if (p.phase_clocks) rc = launch(attn_global2_kernel<HD, NST, true, 2>, p.phase_clocks);
+    else if (k8 == 2) rc = launch(attn_global2_kernel<HD, NST, false, 2>, nullptr);
+    else if (k8 == 3) rc = launch(attn_global2_kernel<HD, NST, false, 3>, nullptr);
+    else if (k8 == 4) rc = launch(attn_global2_kernel<HD, NST, false, 4>, nullptr);
+    else rc = launch(attn_global2_kernel<HD, NST, false, 0>, nullptr);
+    if (rc) return rc;
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1163,13 +940,6 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
         if ((rc = encode_tmap_nd_bf16(&wm.o0t, p.out, 4, od, os, q0t, 32))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.o1t, p.out, 4, od, os, q1t, 32))) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        SVB_CHECK_CUDA(cudaFuncSetAttribute(attn_window_persistent_kernel<HD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
-    }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
     const int items = p.batch * 25 * p.heads;
     int sms = 148, dev = 0;
@@ -1178,16 +948,31 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     const int grid = items < sms ? items : sms;
     // the phase-clock instrumentation is its own instantiation: dormant run-time branches in the hot loop are not free (the same
     // lesson as the global kernel's removed ping-pong option)
-    if (p.phase_clocks) attn_window_persistent_kernel<HD, true, true><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, p.phase_clocks);
-    else if (exp2_poly(true)) attn_window_persistent_kernel<HD, true, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, nullptr);
-    else attn_window_persistent_kernel<HD, false, false><<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, nullptr);
+    auto launch = [&](auto kern, long long* clocks) -> int {
+        SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        static const int l2_ahead = [] { const char* e = getenv("SVB_ATTNW_L2AHEAD"); return e ? atoi(e) : 1; }();
+        kern<<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, clocks, l2_ahead);
+        return 0;
+    };
+    const int k8 = exp2_poly(true);
+    if (p.phase_clocks) rc = launch(attn_window_persistent_kernel<HD, 2, true>, p.phase_clocks);
+    else if (k8 == 0) rc = launch(attn_window_persistent_kernel<HD, 0, false>, nullptr);
+    else if (k8 == 3) rc = launch(attn_window_persistent_kernel<HD, 3, false>, nullptr);
+    else if (k8 == 4) rc = launch(attn_window_persistent_kernel<HD, 4, false>, nullptr);
+    else rc = launch(attn_window_persistent_kernel<HD, 2, false>, nullptr);
+    if (rc) return rc;
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 }  // namespace
 
-int attention_tc_rel_rows(int ws, int grid) { return ws == grid ? 272 : 64; }
+// Rows of the packed bf16 rel-pos block of one attention module.  Global (64 x 64): rel_pos_h at rows [0,127), rel_pos_w at
+// [144,271).  Windowed (14 x 14): rows [0,27) rel_pos_h and [32,59) rel_pos_w (two-group kernel); rows [64,112) and [112,160) the
+// two 48-row tables of the pipelined kernel (attention_win3.cu): query tile 0 (window rows 0..7) = rel_pos_h[0..20] then
+// rel_pos_w[0..26], query tile 1 (rows 8..13) = rel_pos_h[8..26] then rel_pos_w[0..26] (+ two unused rows).  Unwritten rows must
+// be finite: the block is zero-filled when it is allocated.
+int attention_tc_rel_rows(int ws, int grid) { return ws == grid ? 272 : 160; }
 
 // registers a host-mapped buffer (64 x u64, zeroed) that receives mbarrier-timeout records of the attention kernels
 int attention_tc_set_debug_buffer(void* mapped_device_ptr) {
@@ -1198,9 +983,21 @@ int attention_tc_set_debug_buffer(void* mapped_device_ptr) {
 
 int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream) {
     SVB_REQUIRE(L == 27 || L == 127, "pack_rel_table: table length %d is not 27 (14x14 windows) or 127 (64x64 global)", L);
-    const int row_off = is_w ? (L == 127 ? 144 : 32) : 0;
-    pack_rel_kernel<<<(L * hd + 255) / 256, 256, 0, stream>>>(src, dst, L, hd, row_off);
-    count_launch();
+    auto pack = [&](int n_rows, int src0, int row_off) {
+        pack_rel_kernel<<<(n_rows * hd + 255) / 256, 256, 0, stream>>>(src, dst, n_rows, hd, src0, row_off);
+        count_launch();
+    };
+    if (L == 127) {
+        pack(L, 0, is_w ? 144 : 0);
+    } else if (is_w) {
+        pack(27, 0, 32);
+        pack(27, 0, 64 + 21);          // tile 0 table: rows 21..47
+        pack(27, 0, 112 + 19);         // tile 1 table: rows 19..45
+    } else {
+        pack(27, 0, 0);
+        pack(21, 0, 64);               // tile 0 table: rel_pos_h[0..20]
+        pack(19, 8, 112);              // tile 1 table: rel_pos_h[8..26]
+    }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1228,6 +1025,10 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
                    (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
                    (double)p.batch * p.grid * p.grid * 4.0 * D_ * 2, stream);
     if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
+    // pipelined kernel (attention_win3.cu) by default; SVB_ATTNW_IMPL=2 selects the two-group kernel below (A/B comparisons,
+    // phase clocks)
+    static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 3; }();
+    if (impl == 3) return attention_window3(p, stream);
     return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }
 

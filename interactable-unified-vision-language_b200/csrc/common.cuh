@@ -218,6 +218,12 @@ int attention_tc_set_debug_buffer(void* mapped_device_ptr);
 int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream);
 int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream);
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
+int attention_window3(const AttnTcParams& p, cudaStream_t stream);   // attention_win3.cu
+// tcgen05 masked cross-attention of the X-Decoder layers (xattn_tc.cu)
+int xattn_tc_supported(int dtype_bf16, int queries, int keys, int head_dim, const void* q, const void* k, const void* v, const void* mask,
+                       const void* out, int batch, int heads);
+int xattn_tc_launch(const bf16* q, const bf16* k, const bf16* v, const uint8_t* mask, bf16* out, float* workspace, int64_t workspace_floats,
+                    int queries, int keys, int batch, int heads, cudaStream_t stream);
 
 // elementwise / normalisation kernels (elementwise.cu)
 int im2col_patch(const void* x, int x_dtype, void* out, bool out_bf16, int B, int C, int img_h, int img_w, int patch, cudaStream_t s);

@@ -3,6 +3,7 @@
 // logits are GEMMs: svb_linear), antialiased bicubic resize of the logits to the attention-mask size, threshold + head repeat.
 #include "../../include/samvit_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 namespace svb {
 namespace {
@@ -250,6 +251,11 @@ extern "C" int svb_masked_cross_attention(const void* q, const void* k, const vo
     SVB_REQUIRE(head_dim == XA_HD && queries >= 1 && queries <= 128 && keys >= 1 && batch >= 1 && heads >= 1,
                 "svb_masked_cross_attention: head_dim %d (64 supported), %d queries (<= 128)", head_dim, queries);
     cudaStream_t s = (cudaStream_t)stream;
+    // bf16, keys in multiples of 64: the tcgen05 kernel (xattn_tc.cu).  SVB_XATTN_IMPL=0 forces the fp32-FMA kernel below (A/B, fp32 mode).
+    static const bool tc_off = [] { const char* e = getenv("SVB_XATTN_IMPL"); return e && atoi(e) == 0; }();
+    if (!tc_off && xattn_tc_supported(dtype == SVB_DTYPE_BF16, queries, keys, head_dim, q, k, v, mask_bool, out, batch, heads))
+        return xattn_tc_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, (const uint8_t*)mask_bool, (bf16*)out, workspace, workspace_floats,
+                               queries, keys, batch, heads, s);
     int kpb = 512;
     while (kpb > XA_CHUNK && (long)((keys + kpb - 1) / kpb) * heads * batch < 296) kpb /= 2;      // at least two blocks per SM where possible
     const int nblk = (keys + kpb - 1) / kpb;
@@ -275,6 +281,34 @@ extern "C" int svb_masked_cross_attention(const void* q, const void* k, const vo
 
 extern "C" int64_t svb_masked_cross_attention_workspace(int queries, int keys, int batch, int heads) {
     return (int64_t)batch * heads * ((keys + XA_CHUNK - 1) / XA_CHUNK) * queries * (XA_HD + 2);
+}
+
+// LanguageEncoder.compute_similarity's normalisation (modeling/language/vlpencoder.py:242, 244): out = scale * x / (|x| + eps) per row
+namespace svb {
+namespace {
+template <typename T>
+__global__ void l2_normalize_rows_kernel(const float* __restrict__ x, T* __restrict__ out, int rows, int dim, float eps, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * dim;
+    float s = 0.f;
+    for (int d = lane; d < dim; d += 32) s = fmaf(xr[d], xr[d], s);
+    s = warp_sum(s);
+    const float f = scale / (sqrtf(s) + eps);
+    for (int d = lane; d < dim; d += 32) out[(size_t)row * dim + d] = from_float<T>(xr[d] * f);
+}
+}  // namespace
+}  // namespace svb
+
+extern "C" int svb_l2_normalize_rows(const float* x, void* out, int out_dtype, int rows, int dim, float eps, float scale, svb_stream_t stream) {
+    SVB_REQUIRE(x && out && rows > 0 && dim > 0, "svb_l2_normalize_rows: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_OTHER, 0, (double)rows * dim * (4 + (out_dtype == SVB_DTYPE_BF16 ? 2 : 4)), s);
+    if (out_dtype == SVB_DTYPE_BF16) l2_normalize_rows_kernel<bf16><<<(rows + 7) / 8, 256, 0, s>>>(x, (bf16*)out, rows, dim, eps, scale);
+    else l2_normalize_rows_kernel<float><<<(rows + 7) / 8, 256, 0, s>>>(x, (float*)out, rows, dim, eps, scale);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // xdecoder.py:258: attn_mask[where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False — a query whose every key is masked attends to all

@@ -31,11 +31,21 @@ class MaskPredictionHead(nn.Module):
     """``decoder_norm`` and ``mask_embed`` carry the names they have inside ``XDecoder`` (``xdecoder.py:109,133``), so the matching
     entries of its ``state_dict`` load with ``strict=True``.  ``precision``: "bf16" (tcgen05 GEMMs) or "fp32" (validation mode)."""
 
-    def __init__(self, hidden_dim=512, mask_dim=512, num_queries=101, nheads=8):
+    def __init__(self, hidden_dim=512, mask_dim=512, num_queries=101, nheads=8, dim_proj=None, bbox=False, caption=False):
+        """``dim_proj``: width of the class / caption embedding (``class_embed``, xdecoder.py:135); with it the head also returns
+        ``outputs_class`` (when text embeddings are passed to forward), ``outputs_caption`` (``caption=True``, the reference's
+        task_switch['caption']) and, with ``bbox=True`` (task_switch['bbox']), ``outputs_bbox`` from ``bbox_embed`` (xdecoder.py:139)."""
         super().__init__()
         self.decoder_norm = nn.LayerNorm(hidden_dim)
         self.mask_embed = _MLP(hidden_dim, hidden_dim, mask_dim, 3)
         self.num_queries, self.num_heads = num_queries, nheads
+        self.caption = bool(caption)
+        if dim_proj is not None:
+            self.class_embed = nn.Parameter(torch.empty(hidden_dim, dim_proj))
+            nn.init.trunc_normal_(self.class_embed, std=0.02)                              # xdecoder.py:136
+        else:
+            self.class_embed = None
+        self.bbox_embed = _MLP(hidden_dim, hidden_dim, 4, 3) if bbox else None             # xdecoder.py:139
         self.precision = "bf16"
         self._sig = None
 
@@ -46,6 +56,9 @@ class MaskPredictionHead(nn.Module):
             f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()      # noqa: E731
             self._ln = (f(self.decoder_norm.weight), f(self.decoder_norm.bias))
             self._mlp = [(f(l.weight).to(wdtype).contiguous(), f(l.bias)) for l in self.mask_embed.layers]
+            self._box = [(f(l.weight).to(wdtype).contiguous(), f(l.bias)) for l in self.bbox_embed.layers] if self.bbox_embed is not None else None
+            # x @ class_embed as a GEMM against the [dim_proj, hidden] operand
+            self._cls = f(self.class_embed).t().contiguous().to(wdtype).contiguous() if self.class_embed is not None else None
             self._sig = sig
 
     @staticmethod
@@ -69,9 +82,43 @@ class MaskPredictionHead(nn.Module):
                    "svb_nchw_to_rows")
         return rows
 
-    def forward(self, output, mask_features, attn_mask_target_size, rows=None):
+    def class_box_outputs(self, y, a, B, Q, mode, adt, text_embeddings=None, logit_scale=None):
+        """The outputs of forward_prediction_heads beside the mask (xdecoder.py:452-484) from the decoder rows after the class-token
+        recompute (``y`` fp32, ``a`` in the GEMM operand type): class embeddings (:453), class logits = the language encoder's
+        compute_similarity against ``text_embeddings`` (K, dim_proj) with ``logit_scale`` (vlpencoder.py:239-245), boxes (:478),
+        caption embeddings (:482)."""
+        lib, st, dev = cabi.lib(), cabi.stream_ptr, y.device
+        res = {"outputs_class": None, "outputs_bbox": None, "outputs_caption": None}
+        if self._cls is not None:
+            ce = self._linear(mode, a, self._cls, None, torch.empty(B * Q, self._cls.shape[0], dtype=torch.float32, device=dev))
+            if self.caption:
+                res["outputs_caption"] = ce.view(B, Q, -1)
+            if text_embeddings is not None:
+                K, DP = text_embeddings.shape
+                scale = float(torch.as_tensor(logit_scale).exp()) if logit_scale is not None else 1.0
+                v = torch.empty(B * Q, DP, dtype=adt, device=dev)
+                cabi.check(lib.svb_l2_normalize_rows(ce.data_ptr(), v.data_ptr(), _odt(adt), B * Q, DP, 1e-7, scale, st()), "svb_l2_normalize_rows")
+                t = text_embeddings.detach().to(device=dev, dtype=adt).contiguous()
+                Kp = (K + 7) // 8 * 8                                                    # 16-byte rows for the GEMM's stores
+                logits = torch.empty(B * Q, Kp, dtype=torch.float32, device=dev)
+                self._linear(mode, v, t, None, logits[:, :K] if Kp == K else logits.as_strided((B * Q, K), (Kp, 1)))
+                res["outputs_class"] = logits[:, :K].reshape(B, Q, K) if Kp != K else logits.view(B, Q, K)
+        if self._box is not None:
+            x = a
+            n = len(self._box)
+            for i, (w, b) in enumerate(self._box):
+                last = i == n - 1
+                odt = torch.float32 if last else adt
+                Np = 8 if last else w.shape[0]                                            # the 4 box values live in an 8-wide row
+                buf = torch.empty(B * Q, Np, dtype=odt, device=dev)
+                x = self._linear(mode, x, w, b, buf.as_strided((B * Q, w.shape[0]), (Np, 1)), act=0 if last else 2)
+            res["outputs_bbox"] = x.reshape(B, Q, 4)
+        return res
+
+    def forward(self, output, mask_features, attn_mask_target_size, rows=None, text_embeddings=None, logit_scale=None):
         """output (Q, B, C) — the decoder's query states as ``forward_prediction_heads`` receives them; mask_features (B, Cm, H, W) fp32 or
-        bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool}."""
+        bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool} and, when the
+        head was built with ``dim_proj`` / ``bbox``, "outputs_class" / "outputs_bbox" / "outputs_caption" (see class_box_outputs)."""
         if not output.is_cuda:
             raise RuntimeError("MaskPredictionHead (B200) has no CPU path: the inputs must be CUDA tensors")
         if torch.is_grad_enabled() and (output.requires_grad or (torch.is_tensor(mask_features) and mask_features.requires_grad)
@@ -98,6 +145,7 @@ class MaskPredictionHead(nn.Module):
             if adt != torch.float32:
                 a = torch.empty(B * Q, C, dtype=adt, device=dev)
                 cabi.check(lib.svb_add_cast(y.data_ptr(), None, a.data_ptr(), _odt(adt), y.numel(), st()), "svb_add_cast")
+            extra = self.class_box_outputs(y, a, B, Q, mode, adt, text_embeddings, logit_scale)                      # :452-455, 476-482
             n = len(self._mlp)
             for i, (w, b) in enumerate(self._mlp):                                                                    # :458 mask_embed
                 last = i == n - 1
@@ -114,7 +162,7 @@ class MaskPredictionHead(nn.Module):
             attn = torch.empty(B * self.num_heads, Q, oh * ow, dtype=torch.bool, device=dev)
             cabi.check(lib.svb_mask_threshold_heads(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q * oh * ow, st()),
                        "svb_mask_threshold_heads")                                                                     # :467-470
-        return {"outputs_mask": masks, "attn_mask": attn, "attn_logits": small.view(B, Q, oh, ow)}
+        return {"outputs_mask": masks, "attn_mask": attn, "attn_logits": small.view(B, Q, oh, ow), **extra}
 
 
 class CrossAttentionLayer(nn.Module):

@@ -68,6 +68,37 @@ def mask_branch(sd, output, mask_features, attn_mask_target_size, num_queries, n
     return outputs_mask, logits, attn
 
 
+def decoder_output_rows(sd, output, num_queries):
+    """decoder_norm + transpose + class-token recompute (xdecoder.py:430-450): (Q, B, C) -> (B, Q, C)."""
+    mu = output.mean(-1, keepdim=True)
+    var = ((output - mu) ** 2).mean(-1, keepdim=True)
+    dec = ((output - mu) / torch.sqrt(var + 1e-5) * sd["decoder_norm.weight"] + sd["decoder_norm.bias"]).transpose(0, 1)
+    nrm = dec / (dec.norm(dim=-1, keepdim=True) + 1e-7)
+    obj, cls = nrm[:, :num_queries - 1], nrm[:, num_queries - 1:num_queries]
+    sim = (cls @ obj.transpose(1, 2)).softmax(-1)[:, 0, :, None]
+    cls_token = (sim * dec[:, :num_queries - 1]).sum(dim=1, keepdim=True)
+    return torch.cat((dec[:, :num_queries - 1], cls_token), dim=1)
+
+
+def class_box_branch(sd, output, num_queries, text_embeddings, logit_scale):
+    """The remaining outputs of forward_prediction_heads (xdecoder.py:452-484) for the inference path:
+    class_embed = decoder_output @ class_embed (:453); outputs_class = LanguageEncoder.compute_similarity(class_embed)
+    (modeling/language/vlpencoder.py:239-245: exp(logit_scale) * normalise(v) @ t_emb^T, normalisation with + 1e-7);
+    outputs_bbox = bbox_embed(decoder_output) (a 3-layer ReLU MLP, :478); outputs_caption = class_embed (:482).
+    -> (outputs_class (B, Q, K), outputs_bbox (B, Q, 4), outputs_caption (B, Q, dim_proj)).  Pinned by tests/golden/mask_head_full_*.npz."""
+    dec = decoder_output_rows(sd, output, num_queries)
+    class_embed = dec @ sd["class_embed"]
+    v = class_embed / (class_embed.norm(dim=-1, keepdim=True) + 1e-7)
+    outputs_class = torch.as_tensor(logit_scale).exp() * v @ text_embeddings.unsqueeze(0).transpose(1, 2)
+    x = dec
+    n = len([k for k in sd if k.startswith("bbox_embed.layers.") and k.endswith(".weight")])
+    for i in range(n):
+        x = x @ sd[f"bbox_embed.layers.{i}.weight"].t() + sd[f"bbox_embed.layers.{i}.bias"]
+        if i < n - 1:
+            x = torch.relu(x)
+    return outputs_class, x, class_embed
+
+
 def cross_attention_layer(sd, tgt, memory, memory_mask, pos, query_pos, n_heads, mha="multihead_attn"):
     """CrossAttentionLayer.forward_post (interface/modules.py:95-106) with torch's nn.MultiheadAttention written out (in_proj split in
     q / k / v, q scaled by head_dim^-0.5, additive -inf mask where memory_mask is True, softmax over the keys, out_proj), eval mode.

@@ -74,8 +74,33 @@ def test_mask_head_against_reference_goldens(case, precision, tol):
     assert ib.rel_l2(res["attn_logits"], ref_logits) < tol
 
 
+@pytest.mark.parametrize("case", ["full_small", "full_q101"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_class_box_caption_outputs_against_reference_goldens(case, precision, tol):
+    """The outputs of forward_prediction_heads beside the mask (xdecoder.py:452-484) against the UNMODIFIED reference method run with
+    the reference's own compute_similarity (vlpencoder.py:239-245): class logits against the text embeddings, box MLP, caption
+    embeddings; parameters loaded by the reference's names (class_embed, bbox_embed.layers.N.*)."""
+    from iuvl_b200.mask_head import MaskPredictionHead
+    z = np.load(os.path.join(GOLDEN, f"mask_head_{case}.npz"))
+    C, MD, Q, NH, th, tw, DP, NC = (int(v) for v in z["meta"])
+    head = MaskPredictionHead(hidden_dim=C, mask_dim=MD, num_queries=Q, nheads=NH, dim_proj=DP, bbox=True, caption=True)
+    head.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}, strict=True)
+    head.to(DEV).eval()
+    head.precision = precision
+    with torch.no_grad():
+        res = head(torch.from_numpy(z["output"]).to(DEV), torch.from_numpy(z["mask_features"]).to(DEV), (th, tw),
+                   text_embeddings=torch.from_numpy(z["text_embeddings"]).to(DEV), logit_scale=torch.from_numpy(z["logit_scale"]))
+    for key in ("outputs_class", "outputs_bbox", "outputs_caption", "outputs_mask"):
+        ref = torch.from_numpy(z[key])
+        assert tuple(res[key].shape) == tuple(ref.shape), key
+        err = ib.rel_l2(res[key], ref)
+        assert err < tol, (case, precision, key, err)
+
+
 @pytest.mark.parametrize("Q,HW,B,NH,dtype,masked", [(101, 1024, 2, 8, torch.float32, True), (37, 300, 1, 2, torch.float32, False),
-                                                    (101, 4096, 2, 8, torch.bfloat16, True)])
+                                                    (101, 4096, 2, 8, torch.bfloat16, True), (101, 16384, 2, 8, torch.bfloat16, True),
+                                                    (101, 1024, 16, 8, torch.bfloat16, True), (7, 64, 1, 1, torch.bfloat16, False),
+                                                    (128, 4096, 1, 2, torch.bfloat16, False), (101, 300, 1, 2, torch.bfloat16, True)])
 def test_masked_cross_attention_core(Q, HW, B, NH, dtype, masked):
     """svb_masked_cross_attention against softmax((q / sqrt(d)) k^T + mask) v in fp64 (keys split over blocks + combine)."""
     g = torch.Generator().manual_seed(13)
@@ -86,6 +111,7 @@ def test_masked_cross_attention_core(Q, HW, B, NH, dtype, masked):
     if masked:
         mask = (torch.rand(B * NH, Q, HW, generator=g) < 0.6)
         mask[:, :, HW // 2:HW // 2 + 200] = True                 # whole key chunks masked for every query
+        mask[0, 3, :] = True                                     # one query with EVERY key masked: NaN, as torch (0 / 0)
         mask = mask.to(DEV)
     lib = cabi.lib()
     nws = int(lib.svb_masked_cross_attention_workspace(Q, HW, B, NH))
@@ -100,7 +126,10 @@ def test_masked_cross_attention_core(Q, HW, B, NH, dtype, masked):
     if masked:
         s = s.masked_fill(mask.cpu(), float("-inf"))
     want = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(Q, B, C)
-    assert ib.rel_l2(out, want) < (2e-6 if dtype == torch.float32 else 4e-3)
+    nan = torch.isnan(want)
+    assert torch.equal(torch.isnan(out.float().cpu()), nan) and bool(nan.any()) == bool(masked)
+    got = torch.where(nan, torch.zeros_like(want), out.double().cpu())
+    assert ib.rel_l2(got, torch.where(nan, torch.zeros_like(want), want)) < (2e-6 if dtype == torch.float32 else 4e-3)
 
 
 @pytest.mark.parametrize("case", ["small", "q101", "nomask"])

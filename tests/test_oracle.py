@@ -283,6 +283,25 @@ def test_mask_head_oracle_against_reference_goldens(case):
     assert float(differ.float().mean()) < 1e-3 and (not differ.any() or float(rep[differ].abs().max()) < 1e-4)
 
 
+@pytest.mark.parametrize("case", ["full_small", "full_q101"])
+def test_class_box_oracle_against_reference_goldens(case):
+    """oracle.class_box_branch against the class logits / boxes / caption embeddings of the UNMODIFIED reference method
+    (xdecoder.py:452-484) with the reference's own compute_similarity (vlpencoder.py:239-245)."""
+    import os
+    import numpy as np
+    import iuvl_b200 as ib
+    from oracle import mask_head_oracle as mo
+    from tests.util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, f"mask_head_{case}.npz"))
+    Q = int(z["meta"][2])
+    sd = {k[3:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("sd.")}
+    cls, box, cap = mo.class_box_branch(sd, torch.from_numpy(z["output"]).double(), Q, torch.from_numpy(z["text_embeddings"]).double(),
+                                        float(z["logit_scale"]))
+    assert ib.rel_l2(cls, torch.from_numpy(z["outputs_class"])) < 2e-6
+    assert ib.rel_l2(box, torch.from_numpy(z["outputs_bbox"])) < 2e-6
+    assert ib.rel_l2(cap, torch.from_numpy(z["outputs_caption"])) < 2e-6
+
+
 @pytest.mark.parametrize("case", ["small", "q101", "nomask"])
 def test_cross_attention_oracle_against_reference_goldens(case):
     """oracle.cross_attention_layer against outputs of the UNMODIFIED reference CrossAttentionLayer
