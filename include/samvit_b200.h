@@ -164,6 +164,18 @@ int svb_attention_debug_buffer(void* mapped_device_ptr);
 int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int head_dim, int is_w, svb_stream_t stream);
 int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int grid, int grid_pad, int row_len,
                       svb_stream_t stream);
+/* Scope row N3 on the tensor cores: the same attention cores for token grids other than 64 x 64 (both sides multiples of 32; e.g. the
+ * 64 x 128 grid of the reference's 1024 x 2048 evaluation pads).  Windowed blocks: qkv on the window-padded grid [B, 14 ceil(gh / 14),
+ * 14 ceil(gw / 14), 3D] (pad rows = qkv bias: svb_fill_pad_rows_hw), rel_pack as for svb_attention_tc (ws 14).  Global blocks: qkv in
+ * token order; rel_pos_h / rel_pos_w are the fp32 tables ALREADY resized to 2 gh - 1 / 2 gw - 1 rows (get_rel_pos's linear resize,
+ * image_encoder.py:319-330 = svb_resize_rel_pos); the decomposed terms q . rel_pos[j] are formed per head by the tcgen05 GEMM into the
+ * workspace, then the generic-grid kernel (csrc/attention_ext.cu) runs. */
+int svb_fill_pad_rows_hw(void* qkv_padded, const float* qkv_bias, int batch, int grid_h, int grid_w, int row_len, svb_stream_t stream);
+int svb_attention_window_hw(const void* qkv_padded, void* out, const void* rel_pack, int batch, int grid_h, int grid_w, int heads,
+                            int head_dim, svb_stream_t stream);
+size_t svb_attention_global_hw_workspace(int batch, int grid_h, int grid_w, int heads, int head_dim);
+int svb_attention_global_hw(const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w, int batch, int grid_h, int grid_w,
+                            int heads, int head_dim, void* workspace, size_t workspace_bytes, svb_stream_t stream);
 /* PatchEmbed im2col (image_encoder.py:402-410). */
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream);
 /* GroupNorm(1,C) apply from (sum,sumsq) statistics; NHWC rows -> NHWC rows, or -> NCHW with `levels` folded 2x2 stages. */

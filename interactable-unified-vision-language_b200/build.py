@@ -13,10 +13,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsamvit_b200.so")
-SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "attention_win3.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu", "xattn_tc.cu"]
+SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "attention_ext.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu", "xattn_tc.cu"]
+# measured-and-rejected kernel variants live under csrc/experiments/ and are NOT part of the product library; SVB_BUILD_EXPERIMENTAL=1
+# adds them (and the dispatch hooks guarded by SVB_EXPERIMENTAL_*) for A/B runs
+EXPERIMENTAL = os.environ.get("SVB_BUILD_EXPERIMENTAL", "0") == "1"
+if EXPERIMENTAL:
+    SOURCES = SOURCES + ["experiments/attention_win3.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", CSRC] + (["-DSVB_EXPERIMENTAL_WIN3"] if EXPERIMENTAL else [])
 
 
 def _stale(target: str, deps) -> bool:

@@ -55,6 +55,10 @@ SYMBOLS = {
     "svb_attention_debug_buffer": (_i, [_vp]),
     "svb_pack_rel_table": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "svb_fill_pad_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "svb_fill_pad_rows_hw": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "svb_attention_window_hw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_attention_global_hw_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "svb_attention_global_hw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "svb_add_cast": (_i, [_vp, _vp, _vp, _i, _i64, _vp]),
     "svb_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "svb_attention": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -512,10 +512,11 @@ struct WinPMaps {
 
 template <int HD, int POLY, bool PH>
 __global__ void __launch_bounds__(384, 1)
-attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int heads, int num_items, float scale_log2,
+attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int nwy, int nwx, int heads, int num_items, float scale_log2,
                               long long* __restrict__ phase_clocks, int l2_ahead) {
+    // g = token-grid HEIGHT (the last window row's padding decides whether query tile 1 exists); nwy x nwx windows per image
     using C = WPCfg<HD>;
-    constexpr int WS = 14, NWS = 5;
+    constexpr int WS = 14;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -559,10 +560,10 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
     auto decode = [&](int item, int& b, int& wy, int& wx, int& head) {
         head = item % heads;
         const int bw = item / heads;
-        const int win = bw % (NWS * NWS);
-        b = bw / (NWS * NWS);
-        wy = win / NWS;
-        wx = win % NWS;
+        const int win = bw % (nwy * nwx);
+        b = bw / (nwy * nwx);
+        wy = win / nwx;
+        wx = win % nwx;
     };
 
     if (warp == 8) {
@@ -825,19 +826,19 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
 // pad rows of the padded [B, gp, gp, ld] qkv tensor = the qkv bias (pad tokens are zero AFTER norm1, image_encoder.py:183-187,
 // 271-275, so their k / v are b_k / b_v); written once per windowed block before the attention kernel reads it.
 __global__ void __launch_bounds__(256)
-fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int B, int g, int gp, int ld) {
+fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int B, int gh, int gw, int gph, int gpw, int ld) {
     // one warp per pad row: the (image, y, x) arithmetic once per row, the lanes stride over its 16-byte pieces
-    const int npad = gp * gp - g * g, strip = g * (gp - g);
+    const int npad = gph * gpw - gh * gw, strip = gh * (gpw - gw);
     const int v8 = ld / 8;
     const int rows = B * npad;
     const int lane = threadIdx.x & 31;
     for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8) {
         const int pi = r % npad, b = r / npad;
-        // pad index -> (y, x): first the right-hand strip of the g real rows, then the full bottom rows
+        // pad index -> (y, x): first the right-hand strip of the gh real rows, then the full bottom rows
         int y, x;
-        if (pi < strip) { y = pi / (gp - g); x = g + pi % (gp - g); }
-        else { y = g + (pi - strip) / gp; x = (pi - strip) % gp; }
-        bf16* orow = qkv + (((size_t)b * gp + y) * gp + x) * ld;
+        if (pi < strip) { y = pi / (gpw - gw); x = gw + pi % (gpw - gw); }
+        else { y = gh + (pi - strip) / gpw; x = (pi - strip) % gpw; }
+        bf16* orow = qkv + (((size_t)b * gph + y) * gpw + x) * ld;
         for (int c8 = lane; c8 < v8; c8 += 32) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
@@ -913,12 +914,14 @@ int launch_global(const AttnTcParams& p, cudaStream_t stream) {
 template <int HD>
 int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     using C = WPCfg<HD>;
-    const int D = p.heads * p.hd, gp = 70, g = p.grid;
+    const int D = p.heads * p.hd;
+    const int gh = p.grid_h ? p.grid_h : p.grid, gw = p.grid_w ? p.grid_w : p.grid;
+    const int nwy = (gh + 13) / 14, nwx = (gw + 13) / 14, gph = nwy * 14, gpw = nwx * 14;
     WinPMaps wm;
     int rc;
     {
-        const uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)gp, (uint64_t)gp, (uint64_t)p.batch};
-        const uint64_t str[3] = {(uint64_t)3 * D * 2, (uint64_t)gp * 3 * D * 2, (uint64_t)gp * gp * 3 * D * 2};
+        const uint64_t dims[4] = {(uint64_t)3 * D, (uint64_t)gpw, (uint64_t)gph, (uint64_t)p.batch};
+        const uint64_t str[3] = {(uint64_t)3 * D * 2, (uint64_t)gpw * 3 * D * 2, (uint64_t)gph * gpw * 3 * D * 2};
         const uint32_t q0[4] = {64, 14, 9, 1}, q1[4] = {64, 14, 5, 1}, kv[4] = {64, 14, 14, 1};
         const uint32_t q0t[4] = {16, 14, 9, 1}, q1t[4] = {16, 14, 5, 1}, kvt[4] = {16, 14, 14, 1};
         if ((rc = encode_tmap_nd_bf16(&wm.q0, p.qkv, 4, dims, str, q0, 128))) return rc;
@@ -932,16 +935,16 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
         const uint32_t rm[2] = {64, 64}, rt[2] = {16, 64};
         if ((rc = encode_tmap_nd_bf16(&wm.r, p.rel_pack, 2, rd, rs, rm, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.rt, p.rel_pack, 2, rd, rs, rt, 32))) return rc;
-        // output viewed as [B, 64, 64, D]: the store of a window tile is a box of 14 x (9|5) tokens, clipped at the 64 x 64 edge
-        const uint64_t od[4] = {(uint64_t)D, (uint64_t)g, (uint64_t)g, (uint64_t)p.batch};
-        const uint64_t os[3] = {(uint64_t)D * 2, (uint64_t)g * D * 2, (uint64_t)g * g * D * 2};
+        // output viewed as [B, gh, gw, D]: the store of a window tile is a box of 14 x (9|5) tokens, clipped at the grid's edge
+        const uint64_t od[4] = {(uint64_t)D, (uint64_t)gw, (uint64_t)gh, (uint64_t)p.batch};
+        const uint64_t os[3] = {(uint64_t)D * 2, (uint64_t)gw * D * 2, (uint64_t)gh * gw * D * 2};
         if ((rc = encode_tmap_nd_bf16(&wm.o0, p.out, 4, od, os, q0, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.o1, p.out, 4, od, os, q1, 128))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.o0t, p.out, 4, od, os, q0t, 32))) return rc;
         if ((rc = encode_tmap_nd_bf16(&wm.o1t, p.out, 4, od, os, q1t, 32))) return rc;
     }
     const float scale_log2 = LOG2E / sqrtf((float)HD);
-    const int items = p.batch * 25 * p.heads;
+    const int items = p.batch * nwy * nwx * p.heads;
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -951,7 +954,7 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     auto launch = [&](auto kern, long long* clocks) -> int {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         static const int l2_ahead = [] { const char* e = getenv("SVB_ATTNW_L2AHEAD"); return e ? atoi(e) : 1; }();
-        kern<<<grid, 384, C::SMEM, stream>>>(wm, D, g, p.heads, items, scale_log2, clocks, l2_ahead);
+        kern<<<grid, 384, C::SMEM, stream>>>(wm, D, gh, nwy, nwx, p.heads, items, scale_log2, clocks, l2_ahead);
         return 0;
     };
     const int k8 = exp2_poly(true);
@@ -1002,33 +1005,39 @@ int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaSt
     return 0;
 }
 
-int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream) {
+int fill_pad_rows(bf16* qkv, const float* bias, int B, int gh, int gw, int gph, int gpw, int ld, cudaStream_t stream) {
     SVB_REQUIRE(ld % 8 == 0, "fill_pad_rows: row length must be a multiple of 8");
-    const long total = (long)B * (gp * gp - g * g) * (ld / 8);
-    const long rows = (long)B * (gp * gp - g * g);
+    const long rows = (long)B * (gph * gpw - gh * gw);
+    if (rows == 0) return 0;
+    const long total = rows * (ld / 8);
     const int blocks = (int)std::min<long>((rows + 7) / 8, 148 * 8);
     ProfScope prof(PC_OTHER, 0.0, (double)total * 16.0, stream);
-    fill_pad_rows_kernel<<<blocks, 256, 0, stream>>>(qkv, bias, B, g, gp, ld);
+    fill_pad_rows_kernel<<<blocks, 256, 0, stream>>>(qkv, bias, B, gh, gw, gph, gpw, ld);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
-    SVB_REQUIRE(p.grid == 64, "attention_tc: the tcgen05 kernels implement the 64x64 token grid (img 1024 / patch 16), got %d", p.grid);
-    SVB_REQUIRE(p.ws == 14 || p.ws == 64, "attention_tc: window size %d is not 14 (windowed) or 64 (global)", p.ws);
+    const int gh = p.grid_h ? p.grid_h : p.grid, gw = p.grid_w ? p.grid_w : p.grid;
+    const bool native = (gh == 64 && gw == 64);
+    SVB_REQUIRE(gh > 0 && gw > 0 && gh % 32 == 0 && gw % 32 == 0, "attention_tc: token grid %d x %d: both sides must be multiples of 32", gh, gw);
+    SVB_REQUIRE(p.ws == 14 || (native && p.ws == 64), "attention_tc: window size %d is not 14 (windowed) or the 64 x 64 grid (global; other grids: "
+                "attention_global_ext)", p.ws);
     SVB_REQUIRE(p.hd == 64 || p.hd == 80, "attention_tc: head_dim %d is not 64 or 80", p.hd);
     SVB_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(p.rel_pack) & 15) == 0, "attention_tc: pointers must be 16-byte aligned");
     const double D_ = (double)p.heads * p.hd;
-    const int S = p.ws * p.ws, nwin = p.ws == 64 ? 1 : 25;
-    ProfScope prof(p.ws == p.grid ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
+    const int S = p.ws * p.ws, nwin = p.ws == 64 ? 1 : ((gh + 13) / 14) * ((gw + 13) / 14);
+    ProfScope prof(p.ws == 64 ? PC_ATTN_GLOBAL : PC_ATTN_WIN,
                    (double)p.batch * nwin * (4.0 * S * (double)S * D_ + 2.0 * S * 2.0 * p.ws * D_),
-                   (double)p.batch * p.grid * p.grid * 4.0 * D_ * 2, stream);
+                   (double)p.batch * gh * gw * 4.0 * D_ * 2, stream);
     if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
-    // pipelined kernel (attention_win3.cu) by default; SVB_ATTNW_IMPL=2 selects the two-group kernel below (A/B comparisons,
-    // phase clocks)
-    static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 3; }();
+#ifdef SVB_EXPERIMENTAL_WIN3
+    // experimental builds only (SVB_BUILD_EXPERIMENTAL=1): the helper-group pipeline of csrc/experiments/attention_win3.cu, measured
+    // correct and SLOWER than the two-group kernel below; SVB_ATTNW_IMPL=3 selects it
+    static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 2; }();
     if (impl == 3) return attention_window3(p, stream);
+#endif
     return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }
 

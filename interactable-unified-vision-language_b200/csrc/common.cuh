@@ -44,7 +44,8 @@ struct Epilogue {
     int rows_per_sample = 1;
     // optional output-row remap (token grid g x g -> padded grid gp x gp, the window_partition padding of
     // image_encoder.py:271-275 expressed as a store address): out row = (r / g^2) * gp^2 + ((r % g^2) / g) * gp + r % g
-    int remap_g = 0, remap_gp = 0;
+    int remap_g = 0, remap_gp = 0;   // grid WIDTH / padded width
+    int remap_h = 0, remap_hp = 0;   // grid height / padded height (0: square, = remap_g / remap_gp)
     // with the remap: also write the PAD rows of the padded grid (= bf16(pad_bias), the qkv bias: pad tokens are zero after norm1,
     // image_encoder.py:183-187,271-275) from otherwise idle warps of the GEMM, instead of a separate fill_pad_rows launch
     const float* pad_bias = nullptr;
@@ -77,11 +78,13 @@ struct Epilogue {
     float* shift_out = nullptr;            // [M] receives c (null: centring off, c = 0)
     int shift_parts = 0, shift_dim = 0;
 };
+__host__ __device__ __forceinline__ int epilogue_remap_tokens(const Epilogue& ep) { return ep.remap_g * (ep.remap_h ? ep.remap_h : ep.remap_g); }
+__host__ __device__ __forceinline__ int epilogue_remap_padded(const Epilogue& ep) { return ep.remap_gp * (ep.remap_hp ? ep.remap_hp : ep.remap_gp); }
 __host__ __device__ __forceinline__ size_t epilogue_out_row(const Epilogue& ep, int row) {
     if (ep.remap_g == 0) return (size_t)row;
-    const int t = ep.remap_g * ep.remap_g;
+    const int t = epilogue_remap_tokens(ep);
     const int b = row / t, r = row % t;
-    return (size_t)b * ep.remap_gp * ep.remap_gp + (size_t)(r / ep.remap_g) * ep.remap_gp + (r % ep.remap_g);
+    return (size_t)b * epilogue_remap_padded(ep) + (size_t)(r / ep.remap_g) * ep.remap_gp + (r % ep.remap_g);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -212,13 +215,22 @@ struct AttnTcParams {
     const bf16* rel_pack;
     int batch, grid, ws, heads, hd;
     long long* phase_clocks = nullptr;   // optional [2][8] device counters: per-phase cycles of the softmax groups (debug)
+    // scope row N3: token grids other than the trained one (both sides multiples of 32; 0 = square `grid`).  The windowed kernel only
+    // needs the sizes; the global kernel then takes its rel-pos terms from tables in global memory (see attention_tc.cu):
+    // bias_h [batch * grid_h * grid_w][heads][bias_ld] fp32 = q . rel_pos_h[j] for j < 2 grid_h - 1 (resized table), bias_w likewise.
+    int grid_h = 0, grid_w = 0;
+    const float* bias_h = nullptr;
+    const float* bias_w = nullptr;
+    int bias_ld_h = 0, bias_ld_w = 0;
 };
 int attention_tc_rel_rows(int ws, int grid);
 int attention_tc_set_debug_buffer(void* mapped_device_ptr);
 int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaStream_t stream);
-int fill_pad_rows(bf16* qkv, const float* bias, int B, int g, int gp, int ld, cudaStream_t stream);
+// pad rows of the padded [B, gph, gpw, ld] tensor = bias (gh x gw real tokens per image)
+int fill_pad_rows(bf16* qkv, const float* bias, int B, int gh, int gw, int gph, int gpw, int ld, cudaStream_t stream);
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
-int attention_window3(const AttnTcParams& p, cudaStream_t stream);   // attention_win3.cu
+int attention_window3(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win3.cu
+int attention_global_ext(const AttnTcParams& p, cudaStream_t stream); // attention_ext.cu: global attention on other token grids
 // tcgen05 masked cross-attention of the X-Decoder layers (xattn_tc.cu)
 int xattn_tc_supported(int dtype_bf16, int queries, int keys, int head_dim, const void* q, const void* k, const void* v, const void* mask,
                        const void* out, int batch, int heads);

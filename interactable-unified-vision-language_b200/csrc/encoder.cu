@@ -67,11 +67,14 @@ struct svb_encoder {
     // scope row N3: tables resized for token grids other than the trained one (dropped whenever a parameter is reloaded)
     std::map<std::pair<int, int>, float*> pos_cache;               // (gh, gw) -> bicubic pos_embed [gh*gw, D]
     std::map<std::tuple<int, int, int>, float*> rel_cache;         // (block, is_w, length) -> linear rel_pos table [length, hd]
+    std::map<std::tuple<int, int, int>, bf16*> rel16_cache;        // the same tables as bf16 GEMM operands (tcgen05 path)
     void drop_resized() {
         for (auto& kv : pos_cache) cudaFree(kv.second);
         for (auto& kv : rel_cache) cudaFree(kv.second);
+        for (auto& kv : rel16_cache) cudaFree(kv.second);
         pos_cache.clear();
         rel_cache.clear();
+        rel16_cache.clear();
     }
     // host path resources
     struct HostPath {
@@ -128,14 +131,17 @@ struct Buffers {
     double* stats;
     float2 *st1, *st2;          // LayerNorm-fold partial row statistics of the residual stream (norm1 / norm2 inputs)
     float *c1, *c2;             // their per-row shifts (centred hand-over, Epilogue::shift_out)
+    float *biasH, *biasW;       // row N3: rel-pos term tables of the global blocks on other token grids
     size_t total;
 };
 
-// T = tokens per image (grid_h * grid_w); 0 = the trained grid
-Buffers plan(const svb_encoder* e, int chunk, int mode, void* base, int T = 0) {
+// gh x gw = token grid of the canvas; 0 = the trained grid
+Buffers plan(const svb_encoder* e, int chunk, int mode, void* base, int gh = 0, int gw = 0) {
     const size_t es = (mode == SVB_MODE_BF16) ? 2 : 4;
-    const bool native = (T == 0 || T == e->T);
-    const size_t M = (size_t)chunk * (T ? T : e->T);
+    if (gh == 0) { gh = e->grid; gw = e->grid; }
+    const bool native = (gh == e->grid && gw == e->grid);
+    const int T = gh * gw;
+    const size_t M = (size_t)chunk * T;
     const int D = e->D;
     const int kpe = e->cfg.in_chans * e->cfg.patch_size * e->cfg.patch_size;
     Buffers b;
@@ -151,8 +157,16 @@ Buffers plan(const svb_encoder* e, int chunk, int mode, void* base, int T = 0) {
     const size_t mark = ar.off;
     b.A0 = ar.alloc(M * kpe * es);
     b.Xn = ar.alloc(M * D * es);
-    const size_t Mp = (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1 && native) ? (size_t)chunk * e->grid_pad * e->grid_pad : M;
+    const int ws_ = e->cfg.window_size;
+    const size_t Mp = (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1)
+                          ? (size_t)chunk * (((gh + ws_ - 1) / ws_) * ws_) * (((gw + ws_ - 1) / ws_) * ws_) : M;   // window-padded grid
     b.QKV = ar.alloc(Mp * 3 * D * es);
+    // other token grids on the tcgen05 path (row N3): the rel-pos terms of the global blocks, [M][heads][2 g - 1 rounded up to 8] fp32
+    b.biasH = b.biasW = nullptr;
+    if (mode == SVB_MODE_BF16 && e->attn_impl_bf16 == 1 && !native) {
+        b.biasH = (float*)ar.alloc(M * e->heads * (size_t)((2 * gh - 1 + 7) / 8 * 8) * 4);
+        b.biasW = (float*)ar.alloc(M * e->heads * (size_t)((2 * gw - 1 + 7) / 8 * 8) * 4);
+    }
     b.O = ar.alloc(M * D * es);
     b.Hid = ar.alloc(M * e->mlp * es);
     const size_t trunk_end = ar.off;
@@ -213,6 +227,24 @@ int resized_rel(svb_encoder* e, int block, bool is_w, int L, cudaStream_t st, co
         int rc = resize_rel_pos(t.f32, p, t.a, L, e->hd, st);
         if (rc) { cudaFree(p); return rc; }
         it = e->rel_cache.emplace(key, p).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// the same table as a bf16 GEMM operand [L][hd] (cached per encoder)
+int resized_rel_bf16(svb_encoder* e, int block, bool is_w, int L, cudaStream_t st, const bf16** out) {
+    auto key = std::make_tuple(block, (int)is_w, L);
+    auto it = e->rel16_cache.find(key);
+    if (it == e->rel16_cache.end()) {
+        const float* src = nullptr;
+        int rc = resized_rel(e, block, is_w, L, st, &src);
+        if (rc) return rc;
+        bf16* p = nullptr;
+        SVB_CHECK_CUDA(cudaMalloc(&p, sizeof(bf16) * (size_t)L * e->hd));
+        rc = add_cast(src, nullptr, p, true, (long)L * e->hd, st);
+        if (rc) { cudaFree(p); return rc; }
+        it = e->rel16_cache.emplace(key, p).first;
     }
     *out = it->second;
     return 0;
@@ -319,8 +351,12 @@ int forward_chunk(svb_encoder* e, const void* x, int B, void* const outs[4], int
             return rc;
         const bool glob = e->is_global(i);
         const int ws = glob ? g : e->cfg.window_size;
-        const bool tc = h && e->attn_impl_bf16 == 1 && native;
-        const bool padded = tc && ws != g;      // windowed blocks of the tcgen05 path keep qkv on the padded 70x70 grid
+        // SVB_ATTN_EXT=0: other token grids on the fp32-math kernel as in round 1 (A/B, bisecting)
+        static const bool ext_off = [] { const char* v = getenv("SVB_ATTN_EXT"); return v && atoi(v) == 0; }();
+        const bool tc = h && e->attn_impl_bf16 == 1 && (native || !ext_off);
+        const bool padded = tc && !glob;        // windowed blocks of the tcgen05 path keep qkv on the window-padded grid (70 x 70)
+        const int wsz = e->cfg.window_size;
+        const int gph = ((gh + wsz - 1) / wsz) * wsz, gpw = ((gw + wsz - 1) / wsz) * wsz;
         {   // qkv (image_encoder.py:242)
             Epilogue ep;
             consume(ep, e->P(p + "attn.qkv.weight"), e->P(p + "attn.qkv.bias"), bf.st1);
@@ -332,9 +368,14 @@ int forward_chunk(svb_encoder* e, const void* x, int B, void* const outs[4], int
             // SVB_PAD_IN_GEMM=1: idle warps of the qkv GEMM write the pad rows instead of a separate launch — measured neutral
             // (same-box A/B, 16 images: 170.6 / 167.2 vs 171.6 / 169.7 images/s), so the separate 18 us launch stays the default
             static const bool pad_in_gemm = [] { const char* v = getenv("SVB_PAD_IN_GEMM"); return v && atoi(v) == 1; }();
-            if (padded) { ep.remap_g = g; ep.remap_gp = e->grid_pad; if (pad_in_gemm) ep.pad_bias = e->P(p + "attn.qkv.bias").f32; }
+            if (padded) {
+                ep.remap_g = gw; ep.remap_gp = gpw;
+                if (!native) { ep.remap_h = gh; ep.remap_hp = gph; }
+                else if (pad_in_gemm) ep.pad_bias = e->P(p + "attn.qkv.bias").f32;
+            }
             if ((rc = linear(mode, bf.Xn, D, e->P(p + "attn.qkv.weight"), M, 3 * D, D, ep, st))) return rc;
-            if (padded && !pad_in_gemm && (rc = fill_pad_rows((bf16*)bf.QKV, e->P(p + "attn.qkv.bias").f32, B, g, e->grid_pad, 3 * D, st))) return rc;
+            if (padded && !(native && pad_in_gemm) &&
+                (rc = fill_pad_rows((bf16*)bf.QKV, e->P(p + "attn.qkv.bias").f32, B, gh, gw, gph, gpw, 3 * D, st))) return rc;
         }
         {   // windowed / global attention with decomposed rel-pos (image_encoder.py:246-253, 258-304, 340-376)
             if (tc) {
@@ -342,7 +383,28 @@ int forward_chunk(svb_encoder* e, const void* x, int B, void* const outs[4], int
                 ap.qkv = (const bf16*)bf.QKV; ap.out = (bf16*)bf.O;
                 ap.rel_pack = e->relpack[i];
                 ap.batch = B; ap.grid = g; ap.ws = ws; ap.heads = e->heads; ap.hd = e->hd;
-                if ((rc = attention_tc(ap, st))) return rc;
+                if (!native) { ap.grid_h = gh; ap.grid_w = gw; }
+                if (native || !glob) {
+                    if ((rc = attention_tc(ap, st))) return rc;
+                } else {
+                    // global block on another token grid (row N3): the decomposed rel-pos terms q . rel_pos'[j] of every token and
+                    // head from the linearly resized tables (get_rel_pos, image_encoder.py:319-330) as tcgen05 GEMMs — per head
+                    // [M, hd] x [2 g - 1, hd]^T with fp32 output rows [M][heads][ld] — then the generic-grid attention kernel
+                    const int Lh = 2 * gh - 1, Lw = 2 * gw - 1, ldh = (Lh + 7) / 8 * 8, ldw = (Lw + 7) / 8 * 8;
+                    for (int w = 0; w < 2; ++w) {
+                        const bf16* tab = nullptr;
+                        if ((rc = resized_rel_bf16(e, i, w == 1, w ? Lw : Lh, st, &tab))) return rc;
+                        const int L = w ? Lw : Lh, ld = w ? ldw : ldh;
+                        float* dst = w ? bf.biasW : bf.biasH;
+                        for (int hh = 0; hh < e->heads; ++hh) {
+                            Epilogue ep;
+                            ep.out = dst + (size_t)hh * ld; ep.ldo = e->heads * ld;
+                            if ((rc = gemm_bf16_tc((const bf16*)bf.QKV + (size_t)hh * e->hd, 3 * D, tab, e->hd, M, L, e->hd, ep, st))) return rc;
+                        }
+                    }
+                    ap.bias_h = bf.biasH; ap.bias_w = bf.biasW; ap.bias_ld_h = ldh; ap.bias_ld_w = ldw;
+                    if ((rc = attention_global_ext(ap, st))) return rc;
+                }
             } else {
                 AttnParams ap;
                 ap.qkv = bf.QKV; ap.out = bf.O;
@@ -779,7 +841,7 @@ int svb_encoder_forward(svb_encoder_t* e, const float* x, int batch, void* res2,
 size_t svb_encoder_workspace_bytes_hw(const svb_encoder_t* e, int chunk, int mode, int img_h, int img_w) {
     if (!e || chunk <= 0 || img_h <= 0 || img_w <= 0) return 0;
     const int p = e->cfg.patch_size;
-    return plan(e, chunk, mode, nullptr, (img_h / p) * (img_w / p)).total;
+    return plan(e, chunk, mode, nullptr, img_h / p, img_w / p).total;
 }
 
 int svb_encoder_forward_x(svb_encoder_t* e, const void* x, int x_dtype, int batch, int img_h, int img_w, void* res2, void* res3, void* res4,
@@ -798,9 +860,9 @@ int svb_encoder_forward_x(svb_encoder_t* e, const void* x, int x_dtype, int batc
     if (chunk > batch) chunk = batch;
     const bool native = (img_h == e->cfg.img_size && img_w == e->cfg.img_size);
     const int T = (img_h / p) * (img_w / p);
-    const size_t need = plan(e, chunk, mode, nullptr, T).total;
+    const size_t need = plan(e, chunk, mode, nullptr, img_h / p, img_w / p).total;
     SVB_REQUIRE(workspace_bytes >= need, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
-    const Buffers bf = plan(e, chunk, mode, workspace, T);
+    const Buffers bf = plan(e, chunk, mode, workspace, img_h / p, img_w / p);
     const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
     const size_t in_per_img = (size_t)e->cfg.in_chans * img_h * img_w * (x_dtype == SVB_DTYPE_F32 ? 4 : 2);     // bytes
     char* res[4] = {(char*)res2, (char*)res3, (char*)res4, (char*)res5};
@@ -1027,6 +1089,54 @@ int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* 
     SVB_REQUIRE(false, "svb_attention: impl %d is not available in this build", impl);
 }
 
+int svb_fill_pad_rows_hw(void* qkv_padded, const float* qkv_bias, int batch, int grid_h, int grid_w, int row_len, svb_stream_t stream) {
+    SVB_REQUIRE(qkv_padded && qkv_bias && batch > 0 && grid_h > 0 && grid_w > 0, "svb_fill_pad_rows_hw: bad argument");
+    return fill_pad_rows((bf16*)qkv_padded, qkv_bias, batch, grid_h, grid_w, (grid_h + 13) / 14 * 14, (grid_w + 13) / 14 * 14, row_len, (cudaStream_t)stream);
+}
+
+int svb_attention_window_hw(const void* qkv_padded, void* out, const void* rel_pack, int batch, int grid_h, int grid_w, int heads, int head_dim,
+                            svb_stream_t stream) {
+    SVB_REQUIRE(qkv_padded && out && rel_pack, "svb_attention_window_hw: null argument");
+    AttnTcParams ap;
+    ap.qkv = (const bf16*)qkv_padded; ap.out = (bf16*)out; ap.rel_pack = (const bf16*)rel_pack;
+    ap.batch = batch; ap.grid = 0; ap.grid_h = grid_h; ap.grid_w = grid_w; ap.ws = 14; ap.heads = heads; ap.hd = head_dim;
+    return attention_tc(ap, (cudaStream_t)stream);
+}
+
+size_t svb_attention_global_hw_workspace(int batch, int grid_h, int grid_w, int heads, int head_dim) {
+    const size_t M = (size_t)batch * grid_h * grid_w;
+    const size_t ldh = (2 * grid_h - 1 + 7) / 8 * 8, ldw = (2 * grid_w - 1 + 7) / 8 * 8;
+    return M * heads * (ldh + ldw) * sizeof(float) + (ldh + ldw) * (size_t)head_dim * sizeof(bf16) + 4096;
+}
+
+int svb_attention_global_hw(const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w, int batch, int grid_h, int grid_w,
+                            int heads, int head_dim, void* workspace, size_t workspace_bytes, svb_stream_t stream) {
+    SVB_REQUIRE(qkv && out && rel_pos_h && rel_pos_w && workspace, "svb_attention_global_hw: null argument");
+    SVB_REQUIRE(workspace_bytes >= svb_attention_global_hw_workspace(batch, grid_h, grid_w, heads, head_dim) &&
+                (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "svb_attention_global_hw: workspace too small or not 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = heads * head_dim, M = batch * grid_h * grid_w;
+    const int Lh = 2 * grid_h - 1, Lw = 2 * grid_w - 1, ldh = (Lh + 7) / 8 * 8, ldw = (Lw + 7) / 8 * 8;
+    float* bh = (float*)workspace;
+    float* bw = bh + (size_t)M * heads * ldh;
+    bf16* th = (bf16*)(((uintptr_t)(bw + (size_t)M * heads * ldw) + 255) & ~(uintptr_t)255);
+    bf16* tw = th + (size_t)ldh * head_dim;
+    int rc;
+    if ((rc = add_cast(rel_pos_h, nullptr, th, true, (size_t)Lh * head_dim, st))) return rc;
+    if ((rc = add_cast(rel_pos_w, nullptr, tw, true, (size_t)Lw * head_dim, st))) return rc;
+    for (int w = 0; w < 2; ++w)
+        for (int hh = 0; hh < heads; ++hh) {
+            Epilogue ep;
+            ep.out = (w ? bw : bh) + (size_t)hh * (w ? ldw : ldh); ep.ldo = heads * (w ? ldw : ldh);
+            if ((rc = gemm_bf16_tc((const bf16*)qkv + (size_t)hh * head_dim, 3 * D, w ? tw : th, head_dim, M, w ? Lw : Lh, head_dim, ep, st))) return rc;
+        }
+    AttnTcParams ap;
+    ap.qkv = (const bf16*)qkv; ap.out = (bf16*)out; ap.rel_pack = nullptr;
+    ap.batch = batch; ap.grid = 0; ap.grid_h = grid_h; ap.grid_w = grid_w; ap.ws = 0; ap.heads = heads; ap.hd = head_dim;
+    ap.bias_h = bh; ap.bias_w = bw; ap.bias_ld_h = ldh; ap.bias_ld_w = ldw;
+    return attention_global_ext(ap, st);
+}
+
 int svb_attention_tc_phases(const void* qkv, void* out, const void* rel_pack, int batch, int grid, int ws, int heads, int head_dim,
                             long long* phase_clocks, svb_stream_t stream) {
     SVB_REQUIRE(qkv && out && rel_pack, "svb_attention_tc_phases: null argument");
@@ -1058,7 +1168,7 @@ int svb_pack_rel_table(const float* table, void* rel_pack, int table_len, int he
 int svb_fill_pad_rows(void* qkv_padded, const float* qkv_bias, int batch, int grid, int grid_pad, int row_len, svb_stream_t stream) {
     SVB_REQUIRE(qkv_padded && qkv_bias, "svb_fill_pad_rows: null argument");
     SVB_REQUIRE(grid > 0 && grid_pad >= grid, "svb_fill_pad_rows: bad grid %d / padded grid %d", grid, grid_pad);
-    return fill_pad_rows((bf16*)qkv_padded, qkv_bias, batch, grid, grid_pad, row_len, (cudaStream_t)stream);
+    return fill_pad_rows((bf16*)qkv_padded, qkv_bias, batch, grid, grid, grid_pad, grid_pad, row_len, (cudaStream_t)stream);
 }
 
 int svb_im2col(const float* x, void* out, int out_dtype, int batch, int chans, int img, int patch, svb_stream_t stream) {

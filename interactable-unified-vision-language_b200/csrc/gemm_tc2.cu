@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace svb {
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_inner,
@@ -95,6 +96,22 @@ __device__ __forceinline__ void mma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// warp-uniform issue (all 32 lanes reach the call, one elected lane issues; operands stay in uniform registers — see
+// ptx::mma_f16_ss_e): no per-MMA R2UR waterfall loop in the issuer
+__device__ __forceinline__ void mma_f16_ss_pair_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred P, q;\n\telect.sync _|P, 0xffffffff;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+        "@P tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, q;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_e(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\t"
+        "@P tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n"
+        ::"r"(ptx::smem_u32(bar)), "h"(mask)
+        : "memory");
+}
 // arrive (once all previously issued MMAs retired) on the barrier at the same offset in BOTH CTAs of the pair
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -129,10 +146,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
     float* bias_s = reinterpret_cast<float*>(tiles + C::OFF_BIAS);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // provably warp-uniform (the issuer's operands stay in uniform registers)
     const int lane = threadIdx.x & 31;
     constexpr int PAIRS = CL / 2;
-    const uint32_t crank = cluster_ctarank();
+    const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
     const uint32_t rank = crank & 1;                 // position inside the CTA pair (0 = leader: issues the MMAs)
     const uint32_t pidx = crank >> 1;                // which pair of the cluster
     const uint32_t lead = crank & ~1u;               // cluster rank of this pair's leader
@@ -192,7 +209,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
+            // all lanes run the loop, one elected lane issues (uniform-register operands); SVB_GEMM2_DBG & 32 selects the former
+            // single-thread issue (a per-MMA R2UR waterfall loop) for A/B runs
+            auto issue_loop = [&](auto uniform) {
+            constexpr bool U = decltype(uniform)::value;
             constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM_CTA, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -210,13 +231,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint64_t da = ptx::make_smem_desc(sa, 0, 1024, ptx::LAYOUT_SW128);
                     const uint64_t db = ptx::make_smem_desc(sb, 0, 1024, ptx::LAYOUT_SW128);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    mma_commit_pair(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // this pair is done with the stage: tell every CTA
+                    for (int k = 0; k < BK / UMMA_K; ++k) (U ? mma_f16_ss_pair_e : mma_f16_ss_pair)(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    (U ? mma_commit_pair_e : mma_commit_pair)(&empty_bar[stage], (uint16_t)((1u << CL) - 1));   // this pair is done with the stage: tell every CTA
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit_pair(&tmem_full[as], (uint16_t)(3u << lead));   // accumulators ready in both CTAs of this pair
+                (U ? mma_commit_pair_e : mma_commit_pair)(&tmem_full[as], (uint16_t)(3u << lead));   // accumulators ready in both CTAs of this pair
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
+            };
+            if (dbg & 32) { if (lane == 0) issue_loop(std::false_type{}); }
+            else issue_loop(std::true_type{});
         }
     } else {
         // ===================== epilogue (warps 2..9, both CTAs) =====================
@@ -561,10 +585,10 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* bias_s = reinterpret_cast<float*>(tiles + C::OFF_BIAS);
     static_assert((2 * C::STAGES + 5 + (MODE == 4 ? 2 * EPI_WARPS : 0)) * 8 <= 256, "barrier block overflows");
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // provably warp-uniform (the issuer's operands stay in uniform registers)
     const int lane = threadIdx.x & 31;
     constexpr int PAIRS = CL / 2;
-    const uint32_t crank = cluster_ctarank();
+    const uint32_t crank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
     const uint32_t rank = crank & 1, pidx = crank >> 1, lead = crank & ~1u;
     const int pair = blockIdx.x / CL, num_pairs = gridDim.x / CL;
     const int num_m = (M + 2 * BM_CTA * PAIRS - 1) / (2 * BM_CTA * PAIRS);
@@ -625,7 +649,11 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leader) =====================
-        if (rank == 0 && lane == 0) {
+        if (rank == 0) {
+            // all lanes run the loop, one elected lane issues (uniform-register operands); SVB_GEMM2_DBG & 32 selects the former
+            // single-thread issue (a per-MMA R2UR waterfall loop) for A/B runs
+            auto issue_loop = [&](auto uniform) {
+            constexpr bool U = decltype(uniform)::value;
             constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM_CTA, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -643,14 +671,17 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const uint64_t da = ptx::make_smem_desc(sa, 0, 1024, ptx::LAYOUT_SW128);
                     const uint64_t db = ptx::make_smem_desc(sb, 0, 1024, ptx::LAYOUT_SW128);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    mma_commit_pair(&empty_bar[stage], (uint16_t)((1u << CL) - 1));
+                    for (int k = 0; k < BK / UMMA_K; ++k) (U ? mma_f16_ss_pair_e : mma_f16_ss_pair)(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    (U ? mma_commit_pair_e : mma_commit_pair)(&empty_bar[stage], (uint16_t)((1u << CL) - 1));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                mma_commit_pair(&tmem_full[as], (uint16_t)(3u << lead));
+                (U ? mma_commit_pair_e : mma_commit_pair)(&tmem_full[as], (uint16_t)(3u << lead));
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
-        } else if (rank == 1 && ep.pad_bias && ep.remap_g) {
+            };
+            if (dbg & 32) { if (lane == 0) issue_loop(std::false_type{}); }
+            else issue_loop(std::true_type{});
+        } else if (rank == 1 && ep.pad_bias && ep.remap_g && !ep.remap_h) {      // (square grids only: the SVB_PAD_IN_GEMM experiment)
             // this warp has nothing to issue in the non-leader CTA: it writes the pad rows of the window-padded output (one slice
             // per CTA pair).  pad index -> (y, x): first the right-hand strip of the g real rows, then the full bottom rows.
             const int g = ep.remap_g, gp = ep.remap_gp;
@@ -1081,7 +1112,7 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
         else if (ep.resid == ep.out && ep.ldr == ep.ldo && ep.resid_mod == 0 && !ep.stats) mode = EPI_F32_REDADD;
         else return 0;
     }
-    if (ep.remap_g && ((ep.remap_g % 32) != 0 || (M % (ep.remap_g * ep.remap_g)) != 0)) return 0;
+    if (ep.remap_g && ((ep.remap_g % 32) != 0 || (M % epilogue_remap_tokens(ep)) != 0)) return 0;
     const int esz = ep.out_bf16 ? 2 : 4;
     if ((reinterpret_cast<uintptr_t>(ep.out) & 15) != 0 || ((size_t)ep.ldo * esz) % 16 != 0) return 0;
     CUtensorMap ma, mw, mo;
@@ -1089,7 +1120,7 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2, 128);
     if (rc) return rc;
-    const uint64_t out_rows = ep.remap_g ? (uint64_t)(M / (ep.remap_g * ep.remap_g)) * ep.remap_gp * ep.remap_gp : (uint64_t)M;
+    const uint64_t out_rows = ep.remap_g ? (uint64_t)(M / epilogue_remap_tokens(ep)) * epilogue_remap_padded(ep) : (uint64_t)M;
     rc = make_tmap_2d(&mo, ep.out, esz, (uint64_t)N, out_rows, (uint64_t)ep.ldo, 32, 32, ep.out_bf16 ? 64 : 128);
     if (rc) return rc;
     CUtensorMap mo2 = mo;
@@ -1148,7 +1179,8 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
     }
     SVB_REQUIRE(!ep.gn_in_stats, "gemm_tc2: the GroupNorm-fold epilogue exists in the streamlined kernel only (unset SVB_GEMM_EPI / SVB_GEMM_CLUSTER)");
     if (ep.pad_bias && ep.remap_g) {       // the generic kernel does not write the pad rows itself
-        int rc = fill_pad_rows((bf16*)ep.out, ep.pad_bias, M / (ep.remap_g * ep.remap_g), ep.remap_g, ep.remap_gp, ep.ldo, stream);
+        int rc = fill_pad_rows((bf16*)ep.out, ep.pad_bias, M / epilogue_remap_tokens(ep), ep.remap_h ? ep.remap_h : ep.remap_g, ep.remap_g,
+                               ep.remap_hp ? ep.remap_hp : ep.remap_gp, ep.remap_gp, ep.ldo, stream);
         if (rc) return rc;
     }
     const int pairs = (cl == 4 && M > 2 * BM_CTA) ? 2 : 1;

@@ -336,11 +336,21 @@ class XDecoderMaskPath(nn.Module):
     self-attention -> FFN -> mask branch of the prediction heads, whose attention mask feeds the next layer.  Parameters carry the names
     they have inside ``XDecoder`` (``query_feat``, ``query_embed``, ``level_embed``, ``transformer_{cross,self}_attention_layers.N``,
     ``transformer_ffn_layers.N``, ``decoder_norm``, ``mask_embed``), so those entries of its ``state_dict`` load with ``strict=True``.
-    Returns ``{"pred_masks": (B, Q, H, W), "aux_masks": [...]}``; class / box / caption outputs belong to the text side and are not built."""
+    Returns ``{"pred_masks": (B, Q, H, W), "aux_masks": [...]}`` and — when built with ``dim_proj`` / ``bbox`` / ``caption`` —
+    ``pred_logits`` (class logits against the text embeddings passed to forward: the language encoder itself is out of scope),
+    ``pred_boxes``, ``pred_captions`` and the per-layer ``aux_outputs`` as the reference returns them (:319-327).
+
+    ``in_channels`` / ``enforce_input_project``: the reference inserts a 1x1 ``input_proj`` convolution per level when the pixel
+    decoder's width differs from ``hidden_dim`` or ENFORCE_INPUT_PROJ is set (:120-127); step1.yaml uses 512 / 512 / False, which
+    makes them empty ``nn.Sequential``s — the only configuration implemented here."""
 
     def __init__(self, hidden_dim=512, mask_dim=512, num_queries=101, nheads=8, dim_feedforward=2048, num_levels=3,
-                 level_indexes=(0, 1, 2, 0, 1, 2, 0, 1, 2)):
+                 level_indexes=(0, 1, 2, 0, 1, 2, 0, 1, 2), dim_proj=None, bbox=False, caption=False, in_channels=None,
+                 enforce_input_project=False):
         super().__init__()
+        if enforce_input_project or (in_channels is not None and in_channels != hidden_dim):
+            raise NotImplementedError("XDecoderMaskPath (B200): input_proj convolutions (in_channels != hidden_dim or "
+                                      "ENFORCE_INPUT_PROJ, xdecoder.py:120-127) are not implemented; step1.yaml does not use them")
         self.num_queries, self.num_heads, self.num_feature_levels = num_queries, nheads, num_levels
         self.level_indexes = list(level_indexes)
         self.num_layers = len(self.level_indexes)
@@ -350,15 +360,27 @@ class XDecoderMaskPath(nn.Module):
         self.query_feat = nn.Embedding(num_queries, hidden_dim)
         self.query_embed = nn.Embedding(num_queries, hidden_dim)
         self.level_embed = nn.Embedding(num_levels, hidden_dim)
-        self._head = [MaskPredictionHead(hidden_dim, mask_dim, num_queries, nheads)]          # parameters registered below under XDecoder's names
+        self._head = [MaskPredictionHead(hidden_dim, mask_dim, num_queries, nheads, dim_proj=dim_proj, bbox=bbox, caption=caption)]
+        # parameters registered under XDecoder's names
         self.decoder_norm = self._head[0].decoder_norm
         self.mask_embed = self._head[0].mask_embed
+        if self._head[0].class_embed is not None:
+            self.class_embed = self._head[0].class_embed
+        if self._head[0].bbox_embed is not None:
+            self.bbox_embed = self._head[0].bbox_embed
         m = torch.zeros(1, num_queries, num_queries, dtype=torch.bool)                      # xdecoder.py:149-153 (object / class queries)
         m[:, :num_queries - 1, num_queries - 1:] = True
         m[:, num_queries - 1:, :num_queries - 1] = True
+        # The reference registers its (1, Q + contxt_len, Q + contxt_len) mask persistently (:153); this slice has no caption tokens, so
+        # the buffer is (1, Q, Q), derived from num_queries and not saved.  A reference state_dict's `self_attn_mask` entry is accepted
+        # and ignored on load (see _load_from_state_dict), so strict=True loading of the reference's entries works.
         self.register_buffer("self_attn_mask", m, persistent=False)
         self.num_pos_feats, self.temperature, self.scale = hidden_dim // 2, 10000, 2 * 3.141592653589793
         self._pos_cache = {}
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        state_dict.pop(prefix + "self_attn_mask", None)          # the reference's persistent buffer: rebuilt from num_queries here
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     @property
     def precision(self):
@@ -387,9 +409,10 @@ class XDecoderMaskPath(nn.Module):
             self._pos_cache[key] = pos.expand(h * w, bs, 2 * npf).contiguous()
         return self._pos_cache[key]
 
-    def forward(self, x, mask_features, mask_rows=None, mask_shape=None):
+    def forward(self, x, mask_features, mask_rows=None, mask_shape=None, text_embeddings=None, logit_scale=None):
         """x: three (B, C, H_i, W_i) maps (the pixel decoder's multi_scale_features), mask_features (B, Cm, H, W) — or None with
-        `mask_rows` / `mask_shape` from `MSDeformAttnPixelDecoder.forward(..., rows_out=True)`."""
+        `mask_rows` / `mask_shape` from `MSDeformAttnPixelDecoder.forward(..., rows_out=True)`.  `text_embeddings` (K, dim_proj) /
+        `logit_scale`: what the language encoder holds as `default_text_embeddings` / `logit_scale` (vlpencoder.py:239-245)."""
         if len(x) != self.num_feature_levels:
             raise AssertionError("x must hold num_feature_levels maps")                    # :195
         if mask_features is None:
@@ -421,10 +444,12 @@ class XDecoderMaskPath(nn.Module):
             query_embed = self.query_embed.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)      # :214-215
             output = self.query_feat.weight.detach().float().unsqueeze(1).repeat(1, bs, 1)
             self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
-            masks = []
+            masks, extras = [], []
             mrows = mask_rows if mask_rows is not None else head.mask_rows(mask_features)            # once for the ten prediction-head calls
-            res = head(output, mask_features, size_list[0], rows=mrows)                              # :257
+            kw = dict(rows=mrows, text_embeddings=text_embeddings, logit_scale=logit_scale)
+            res = head(output, mask_features, size_list[0], **kw)                                    # :257
             masks.append(res["outputs_mask"])
+            extras.append(res)
             attn_mask = res["attn_mask"]
             for i in range(self.num_layers):
                 lvl = self.level_indexes[i]
@@ -434,7 +459,14 @@ class XDecoderMaskPath(nn.Module):
                                                                        query_pos=query_embed)        # :272-277
                 output = self.transformer_self_attention_layers[i](output, tgt_mask=self_mask, query_pos=query_embed)   # :283-287
                 output = self.transformer_ffn_layers[i](output)                                       # :290-292
-                res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels], rows=mrows)   # :299
+                res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels], **kw)         # :299
                 attn_mask = res["attn_mask"]
                 masks.append(res["outputs_mask"])
-        return {"pred_masks": masks[-1], "aux_masks": masks[:-1]}
+                extras.append(res)
+        out = {"pred_masks": masks[-1], "aux_masks": masks[:-1]}
+        if head.class_embed is not None or head.bbox_embed is not None:                               # :319-327
+            out.update(pred_logits=extras[-1]["outputs_class"], pred_boxes=extras[-1]["outputs_bbox"],
+                       pred_captions=extras[-1]["outputs_caption"],
+                       aux_outputs=[{"pred_logits": e["outputs_class"], "pred_masks": m, "pred_boxes": e["outputs_bbox"],
+                                     "pred_captions": e["outputs_caption"]} for e, m in zip(extras[:-1], masks[:-1])])
+        return out

@@ -48,6 +48,7 @@ CASES = {
     # (image_encoder.py:111-114,124-132,319-330); 5-tuples carry the (H, W) of the input
     "tiny64_wide": ("tiny64", 1, 0.1, 4096, (1024, 2048)),
     "tiny80_tall": ("tiny80", 1, 0.1, 4096, (1536, 512)),
+    "vit_b_wide": ("vit_b", 1, 0.05, 16384, (1024, 2048)),        # the reference's COCO evaluation canvas (configs/step1.yaml:211-212)
 }
 WEIGHT_SEED, IMAGE_SEED = 1234, 0
 

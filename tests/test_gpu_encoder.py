@@ -63,8 +63,8 @@ def test_tiny_bf16(case):
     _check(enc, x, g, "bf16", TOL_BF16 if case.endswith("std") else 3e-2)
 
 
-@pytest.mark.parametrize("case", ["tiny64_wide", "tiny80_tall"])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case,precision", [("tiny64_wide", "fp32"), ("tiny64_wide", "bf16"), ("tiny80_tall", "fp32"), ("tiny80_tall", "bf16"),
+                                            ("vit_b_wide", "bf16")])
 def test_other_canvases_against_reference_goldens(case, precision):
     """Scope row N3: 1024 x 2048 and 1536 x 512 inputs against goldens of the unmodified reference, which takes its
     bicubic pos_embed (image_encoder.py:124-132) and linear rel_pos (:319-330) fallbacks on them."""

@@ -374,6 +374,79 @@ def test_global_softmax_cannot_overflow(hd):
     assert err < 1e-2, err
 
 
+def _ref_attention_grid(qkv, rel_h, rel_w, qkv_bias, B, gh, gw, ws, heads):
+    """fp64 reference of the attention core on a (gh x gw) token grid: ws = 0 global (tables of 2 gh - 1 / 2 gw - 1 rows), ws = 14
+    windows of the zero-padded-then-biased grid (image_encoder.py:239-304, 340-376)."""
+    from oracle import sam_vit_oracle as orc
+    D = qkv.shape[1] // 3
+    hd = D // heads
+    x = qkv.reshape(B, gh, gw, 3 * D).double()
+    if ws:
+        Hp, Wp = -(-gh // ws) * ws, -(-gw // ws) * ws
+        xp = qkv_bias.double().reshape(1, 1, 1, -1).expand(B, Hp, Wp, 3 * D).clone()
+        xp[:, :gh, :gw] = x
+        wins, pad_hw = orc.window_partition(xp, ws)
+        sh, sw = ws, ws
+    else:
+        wins, sh, sw = x, gh, gw
+    Bp, S = wins.shape[0], sh * sw
+    q, k, v = wins.reshape(Bp, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    scores = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    Rh, Rw = orc.rel_pos_rows(sh, sh, rel_h.double()), orc.rel_pos_rows(sw, sw, rel_w.double())
+    q5 = q.reshape(Bp, heads, sh, sw, hd)
+    bh = torch.einsum("bnhwc,hkc->bnhwk", q5, Rh)
+    bw = torch.einsum("bnhwc,wkc->bnhwk", q5, Rw)
+    scores = (scores.reshape(Bp, heads, sh, sw, sh, sw) + bh[..., :, None] + bw[..., None, :]).reshape(Bp, heads, S, S)
+    out = (torch.softmax(scores, -1) @ v).permute(0, 2, 1, 3).reshape(Bp, sh, sw, D)
+    if ws:
+        out = orc.window_unpartition(out, ws, pad_hw, (gh, gw))
+    return out.reshape(B * gh * gw, D)
+
+
+@pytest.mark.parametrize("gh,gw,heads,hd,B", [(64, 128, 2, 80, 1), (96, 32, 2, 64, 2), (32, 64, 1, 80, 1), (32, 96, 1, 64, 1), (64, 64, 1, 80, 1)])
+def test_attention_tcgen05_other_token_grids(gh, gw, heads, hd, B):
+    """Scope row N3 on the tensor cores: windowed and global attention on token grids other than 64 x 64 (svb_attention_window_hw,
+    svb_attention_global_hw; e.g. the 64 x 128 grid of the reference's 1024 x 2048 evaluation canvas) against the fp64 reference."""
+    lib, st = cabi.lib(), cabi.stream_ptr
+    D = heads * hd
+    gen = torch.Generator(device="cpu").manual_seed(gh * 7 + gw + hd)
+    qkv = torch.randn(B * gh * gw, 3 * D, generator=gen).bfloat16()
+    bias = torch.randn(3 * D, generator=gen)
+    # ---- windowed (14 x 14) ----
+    rel_h, rel_w = torch.randn(27, hd, generator=gen) * 0.3, torch.randn(27, hd, generator=gen) * 0.3
+    ref = _ref_attention_grid(qkv.float(), rel_h.bfloat16().float(), rel_w.bfloat16().float(), bias.bfloat16().float(), B, gh, gw, 14, heads)
+    pack = torch.zeros(lib.svb_rel_pack_rows(14, 64), hd, dtype=torch.bfloat16, device=DEV)
+    rh27, rw27, bias_d = rel_h.to(DEV), rel_w.to(DEV), bias.to(DEV)
+    cabi.check(lib.svb_pack_rel_table(rh27.data_ptr(), pack.data_ptr(), 27, hd, 0, st()), "pack h")
+    cabi.check(lib.svb_pack_rel_table(rw27.data_ptr(), pack.data_ptr(), 27, hd, 1, st()), "pack w")
+    gph, gpw = -(-gh // 14) * 14, -(-gw // 14) * 14
+    src = torch.full((B, gph, gpw, 3 * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    src[:, :gh, :gw] = qkv.to(DEV).reshape(B, gh, gw, 3 * D)
+    cabi.check(lib.svb_fill_pad_rows_hw(src.data_ptr(), bias_d.data_ptr(), B, gh, gw, 3 * D, st()), "fill_pad_rows_hw")
+    out = torch.full((B * gh * gw, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    cabi.check(lib.svb_attention_window_hw(src.data_ptr(), out.data_ptr(), pack.data_ptr(), B, gh, gw, heads, hd, st()), "window_hw")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert ib.rel_l2(out, ref) < 6e-3, ("windowed", ib.rel_l2(out, ref))
+    # ---- global: tables of 2 g - 1 rows (what get_rel_pos's linear resize hands to the bias einsums) ----
+    rel_h, rel_w = torch.randn(2 * gh - 1, hd, generator=gen) * 0.2, torch.randn(2 * gw - 1, hd, generator=gen) * 0.2
+    ref = _ref_attention_grid(qkv.float(), rel_h.bfloat16().float(), rel_w.bfloat16().float(), bias, B, gh, gw, 0, heads)
+    nws = int(lib.svb_attention_global_hw_workspace(B, gh, gw, heads, hd))
+    ws = torch.empty(nws + 256, dtype=torch.uint8, device=DEV)
+    base = (ws.data_ptr() + 255) & ~255
+    out = torch.full((B * gh * gw, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    qd, rhd, rwd = qkv.to(DEV), rel_h.to(DEV), rel_w.to(DEV)          # (kept alive: a temporary's block would be reused by the next one)
+    cabi.check(lib.svb_attention_global_hw(qd.data_ptr(), out.data_ptr(), rhd.data_ptr(), rwd.data_ptr(), B, gh, gw, heads, hd, base, nws, st()),
+               "global_hw")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    err = ib.rel_l2(out, ref)
+    assert err < 6e-3, ("global", err)
+    o3, r3 = out.float().cpu().reshape(-1, heads, hd), ref.float().reshape(-1, heads, hd)
+    for hh in range(heads):
+        assert ib.rel_l2(o3[:, hh], r3[:, hh]) < 8e-3
+
+
 def test_linear_remap_to_padded_grid():
     """qkv GEMM epilogue storing token rows at their position in the window-padded 70x70 grid."""
     g, gp, B, K, N = 64, 70, 2, 64, 256
