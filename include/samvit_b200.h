@@ -215,8 +215,6 @@ int svb_profile_start(void);
 int svb_profile_stop(double* ms5, double* flops5, double* bytes5, int64_t* launches5);
 int64_t svb_launch_count(void);   /* kernels launched by this library since it was loaded */
 
-/* ---- test hook: one CTA, K/16 tcgen05.mma with caller-supplied smem-descriptor fields; dumps the 128 x N accumulator.
- * Pins the MN-major / 32B-swizzle descriptor encodings the attention kernel relies on (tests/test_gpu_probe.py). ---- */
 /* ---- scope row N1, convolutional part of the pixel decoder (`MSDeformAttnPixelDecoder.forward`,
  * modeling/vision/encoder/transformer_encoder_deform.py:315-359).  "rows" = [sample][pixel][channel] (NHWC), the layout the GEMM
  * reads and writes: a 1x1 convolution (`input_proj[i][0]` :209-214, `lateral_conv` :256-258, `mask_features` :238-245) is one
@@ -242,6 +240,12 @@ int svb_upsample_add_rows(const float* src, int64_t src_sample_stride, float* ds
                           int channels, svb_stream_t stream);
 /* im2col of a 3x3 / stride 1 / pad 1 convolution on fp32 rows: dst[b, y, x, (ky, kx, c)] (dst_dtype) — the A operand of `output_conv`. */
 int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, int batch, int h, int w, int channels, svb_stream_t stream);
+/* The 3x3 `output_conv` (:259-268) without an im2col operand (bf16 path): src fp32 rows (batch, h, w, cin) are cast into a zero-padded bf16
+ * map `padded_ws` (batch * (h + 2) * (w + 2) * cin bf16 elements of scratch) and the tcgen05 GEMM reads its A tiles from it with one row
+ * shift per filter tap (implicit GEMM); weight_bf16 [cout, 9 * cin] ordered (ky, kx, c) as for svb_im2col3x3_rows; out fp32 rows
+ * (batch, h, w, cout) = [relu](conv + bias).  w must be a multiple of 128, cin of 64, cout of 32. */
+int svb_conv3x3_rows(const float* src, const void* weight_bf16, const float* bias, float* out, void* padded_ws, int batch, int h, int w,
+                     int cin, int cout, int relu, svb_stream_t stream);
 /* out = cast(a + b[i mod b_numel]): svb_add_cast with a `b` shared by every sample (the sine position embedding + level embedding,
  * :73-75). */
 int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream);
@@ -273,13 +277,6 @@ int svb_masked_cross_attention(const void* q, const void* k, const void* v, int 
 
 /* mask (rows, keys) bool, in place: a row whose every entry is set is cleared (xdecoder.py:258). */
 int svb_mask_clear_full_rows(void* mask_bool, int64_t rows, int keys, svb_stream_t stream);
-
-/* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
- * completion, [1] = cycles in the issue loop (device pointers). */
-int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);
-int svb_probe_mma(const void* a, const void* b, float* out, int K, int N, int a_sw, int b_sw, int b_mn_major, int a_manual,
-                  unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo, unsigned b_kstep,
-                  svb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsamvit_b200.so")
-SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "attention_ext.cu", "elementwise.cu", "profile.cu", "probe.cu", "msda.cu", "pixdec.cu", "maskhead.cu", "xattn_tc.cu"]
+PROBE_OUT = os.path.join(HERE, "libsamvit_probe.so")
+PROBE_SOURCES = ["probe.cu", "probe_support.cu"]
+SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention_simt.cu", "attention_tc.cu", "attention_ext.cu", "elementwise.cu", "profile.cu", "msda.cu", "pixdec.cu", "maskhead.cu", "xattn_tc.cu"]
 # measured-and-rejected kernel variants live under csrc/experiments/ and are NOT part of the product library; SVB_BUILD_EXPERIMENTAL=1
 # adds them (and the dispatch hooks guarded by SVB_EXPERIMENTAL_*) for A/B runs
 EXPERIMENTAL = os.environ.get("SVB_BUILD_EXPERIMENTAL", "0") == "1"
@@ -62,6 +64,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    # the hardware probes (descriptor encodings, MMA issue rate): a SEPARATE library, test / measurement infrastructure only
+    pobjs = [compile_one(os.path.join(CSRC, s)) for s in PROBE_SOURCES]
+    if force or _stale(PROBE_OUT, pobjs):
+        cmd = [NVCC, "-shared", "-o", PROBE_OUT] + pobjs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link (probe library) failed:\n" + r.stdout + r.stderr)
     return OUT
 
 
@@ -77,8 +86,8 @@ def sass_summary(out_path: str) -> str:
     cuobjdump = os.path.join(os.path.dirname(NVCC), "cuobjdump")
     cufilt = os.path.join(os.path.dirname(NVCC), "cu++filt")
     rows = []
-    for src in SOURCES:
-        obj = os.path.join(objdir, src[:-3] + ".o")
+    for src in SOURCES + PROBE_SOURCES:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         if not os.path.exists(obj):
             continue
         r = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True)

@@ -75,6 +75,7 @@ SYMBOLS = {
     "svb_groupnorm_rows": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "svb_upsample_add_rows": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_im2col3x3_rows": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "svb_conv3x3_rows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_add_cast_bcast": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp]),
     "svb_cls_token_recompute": (_i, [_vp, _i, _i, _i, _vp]),
     "svb_resize_bicubic_aa": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -83,12 +84,19 @@ SYMBOLS = {
     "svb_masked_cross_attention": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "svb_l2_normalize_rows": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "svb_mask_clear_full_rows": (_i, [_vp, _i64, _i, _vp]),
-    "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
-    "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),
     "svb_groupnorm_apply_nchw": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
 }
 
+# the separate probe library (include/samvit_b200_probe.h): hardware probes used by tests / tools only
+PROBE_LIB_PATH = os.path.join(HERE, "libsamvit_probe.so")
+PROBE_SYMBOLS = {
+    "svb_probe_last_error": (C.c_char_p, []),
+    "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
+    "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),
+}
+
 _lib: Optional[C.CDLL] = None
+_probe_lib: Optional[C.CDLL] = None
 
 
 class SvbError(RuntimeError):
@@ -109,6 +117,26 @@ def lib() -> C.CDLL:
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def probe_lib() -> C.CDLL:
+    global _probe_lib
+    if _probe_lib is None:
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise SvbError(f"{PROBE_LIB_PATH} is missing: run __graft_entry__.build()")
+        l = C.CDLL(PROBE_LIB_PATH)
+        for name, (res, args) in PROBE_SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probe_lib = l
+    return _probe_lib
+
+
+def check_probe(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = probe_lib().svb_probe_last_error()
+        raise SvbError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
 
 
 def check(rc: int, what: str = "") -> None:

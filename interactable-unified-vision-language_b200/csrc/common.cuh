@@ -72,6 +72,12 @@ struct Epilogue {
     // previous producer's (already centred) statistics give.  The rounding error of the bf16 operand then scales with the row's
     // deviation from its previous mean instead of with |x| (a common offset per row costs nothing), and the single-pass variance
     // sum(y^2)/n - mean(y)^2 no longer cancels.  The consumer is unchanged (it only ever sees y = x - c).  shift_out[row] = c[row].
+    // ---- implicit GEMM of a 3x3 / stride 1 / pad 1 convolution on rows (MSDeformAttnPixelDecoder.output_conv,
+    // transformer_encoder_deform.py:259-268): A is the ZERO-PADDED bf16 map [batch, conv_h + 2, conv_w + 2, conv_c]; K = 9 conv_c is
+    // ordered (ky, kx, c); the K block kb = (tap, channel block) of the output pixels m0.. is the box at padded row
+    // (b (h + 2) + y + ky) (w + 2) + x0 + kx, so the TMA producer shifts rows per tap instead of reading a 9x larger im2col operand.
+    // conv_w must be a multiple of the CTA's 128 rows (a tile never crosses an image row), conv_c of 64. ----
+    int conv_w = 0, conv_h = 0, conv_c = 0;
     const float2* shift_stats = nullptr;   // [M][shift_parts] statistics of the rows before the update (null: c = shift_in)
     const float* shift_in = nullptr;       // [M] their shifts (null: zeros); [shift_in_mod] indexed row % shift_in_mod when that is set
     int shift_in_mod = 0;
@@ -231,6 +237,8 @@ int fill_pad_rows(bf16* qkv, const float* bias, int B, int gh, int gw, int gph, 
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 int attention_window3(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win3.cu
 int attention_global_ext(const AttnTcParams& p, cudaStream_t stream); // attention_ext.cu: global attention on other token grids
+// A = zero-padded bf16 map, see Epilogue::conv_w (gemm_tc2.cu)
+int gemm_conv3x3_bf16_tc(const bf16* padded, const bf16* W, int ldw, int batch, int h, int w, int cin, int cout, const Epilogue& ep, cudaStream_t stream);
 // tcgen05 masked cross-attention of the X-Decoder layers (xattn_tc.cu)
 int xattn_tc_supported(int dtype_bf16, int queries, int keys, int head_dim, const void* q, const void* k, const void* v, const void* mask,
                        const void* out, int batch, int heads);

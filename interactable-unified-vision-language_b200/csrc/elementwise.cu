@@ -59,12 +59,12 @@ __global__ void im2col_kernel(const TI* __restrict__ x, T* __restrict__ out, int
     const int K = C * patch * patch;
     const size_t plane = (size_t)img_h * img_w;
     const size_t total4 = (size_t)B * C * plane / 4;
+    const unsigned plane4 = (unsigned)(plane / 4), w4 = (unsigned)img_w / 4;      // (64-bit divisions per element made this kernel issue-bound)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 4;                      // flat NCHW element index (input-major -> coalesced reads)
-        const int X = (int)(e % img_w);
-        const int Y = (int)((e / img_w) % img_h);
-        const int c = (int)((e / plane) % C);
-        const int b = (int)(e / (plane * C));
+        const unsigned pl = (unsigned)(i / plane4), in4 = (unsigned)(i - (size_t)pl * plane4);   // (image, channel) plane; vector inside it
+        const int Y = (int)(in4 / w4), X = (int)(in4 - (unsigned)Y * w4) * 4;
+        const int c = (int)(pl % (unsigned)C), b = (int)(pl / (unsigned)C);
         const float4 v = Load4<TI>::load(x + e);
         const int px = X / patch, kx = X % patch, py = Y / patch, ky = Y % patch;
         const size_t row = ((size_t)b * gh + py) * gw + px;
@@ -88,6 +88,11 @@ __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, i
     const int pp = patch * patch;
     const int K = C * pp;
     const size_t totalv = (size_t)B * g * g * K / VEC;
+    // (x - mean) / std takes only 256 values per channel: the correctly rounded divisions (bit-exact with the callers' fp32 expression,
+    // ~10 instructions each) are done ONCE per block into a table, the pixels then cost one shared-memory lookup
+    __shared__ float lut[4 * 256];
+    for (int t = threadIdx.x; t < 256 * C && t < 4 * 256; t += blockDim.x) lut[t] = __fdiv_rn((float)(t & 255) - bt.mean[t >> 8], bt.std[t >> 8]);
+    __syncthreads();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < totalv; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * VEC;                    // flat output index (row-major [B*g*g, K]): coalesced stores
         const int k = (int)(e % K);
@@ -101,7 +106,7 @@ __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, i
         for (int j = 0; j < VEC; ++j) v[j] = 0.f;
         if (y < h && x < w) {
             const uint8_t* src = bt.img[b] + ((size_t)c * h + y) * w + x;
-            const float m = bt.mean[c], sd = bt.std[c];
+            const float* tab = lut + 256 * c;
             uint8_t px8[VEC];
             if (x + VEC <= w && (reinterpret_cast<uintptr_t>(src) & (VEC - 1)) == 0) {       // whole vector inside the row and aligned
                 if constexpr (VEC == 16) *reinterpret_cast<uint4*>(px8) = __ldg(reinterpret_cast<const uint4*>(src));
@@ -112,7 +117,7 @@ __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, i
             }
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                if (x + j < w) v[j] = __fdiv_rn((float)px8[j] - m, sd);
+                if (x + j < w) v[j] = tab[px8[j]];
         }
 #pragma unroll
         for (int j = 0; j < VEC; j += 4) Vec4<T>::store(out + e + j, v[j], v[j + 1], v[j + 2], v[j + 3]);

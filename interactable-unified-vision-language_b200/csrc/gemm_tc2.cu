@@ -628,13 +628,25 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int t = pair; t < num_tiles; t += num_pairs) {
                 const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
                 const int n0 = (t % num_n) * BN + rank * (BN / 2) + pidx * (BN / 2 / PAIRS);
+                // implicit 3x3 convolution (Epilogue::conv_w): row of output pixel m0 in the zero-padded map, channel blocks per tap
+                int conv_row0 = 0, conv_cb = 1;
+                if (ep.conv_w) {
+                    const int hw = ep.conv_h * ep.conv_w, img = m0 / hw, rem = m0 % hw;
+                    conv_row0 = (img * (ep.conv_h + 2) + rem / ep.conv_w) * (ep.conv_w + 2) + rem % ep.conv_w;
+                    conv_cb = ep.conv_c / BK;
+                }
                 for (int kb = 0; kb < num_k; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = tiles + stage * C::STAGE_BYTES;
                     uint8_t* sb = sa + C::A_BYTES;
                     const uint32_t full_leader = map_to_cta(ptx::smem_u32(&full_bar[stage]), lead);
                     if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-                    tma_load_2d_pair(sa, &map_a, full_leader, kb * BK, m0);
+                    if (ep.conv_w) {
+                        const int tap = kb / conv_cb;
+                        tma_load_2d_pair(sa, &map_a, full_leader, (kb % conv_cb) * BK, conv_row0 + (tap / 3) * (ep.conv_w + 2) + tap % 3);
+                    } else {
+                        tma_load_2d_pair(sa, &map_a, full_leader, kb * BK, m0);
+                    }
                     if constexpr (PAIRS == 1) {
                         tma_load_2d_pair(sb, &map_w, full_leader, kb * BK, n0);
                     } else {
@@ -1116,7 +1128,14 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     const int esz = ep.out_bf16 ? 2 : 4;
     if ((reinterpret_cast<uintptr_t>(ep.out) & 15) != 0 || ((size_t)ep.ldo * esz) % 16 != 0) return 0;
     CUtensorMap ma, mw, mo;
-    int rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
+    int rc;
+    if (ep.conv_w) {      // implicit 3x3 convolution: A = the zero-padded map [batch (h + 2) (w + 2), conv_c]
+        if (ep.conv_w % BM_CTA || ep.conv_c % BK || K != 9 * ep.conv_c || M % (ep.conv_h * ep.conv_w) || ep.remap_g) return 0;
+        const uint64_t prow = (uint64_t)(M / (ep.conv_h * ep.conv_w)) * (ep.conv_h + 2) * (ep.conv_w + 2);
+        rc = make_tmap_2d_bf16(&ma, A, (uint64_t)ep.conv_c, prow, (uint64_t)lda, BK, BM_CTA, 128);
+    } else {
+        rc = make_tmap_2d_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM_CTA, 128);
+    }
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2, 128);
     if (rc) return rc;
@@ -1203,6 +1222,25 @@ int gemm_bf16_tc_pair(const bf16* A, int lda, const bf16* W, int ldw, int M, int
     // (the row-statistics output is laid out in 128-column slabs = one epilogue warp of the BN = 256 tile)
     if (N <= 128 && !ep.stat_out) return launch_gemm2<128>(A, lda, W, ldw, M, N, K, ep, stream);
     return launch_gemm2<256>(A, lda, W, ldw, M, N, K, ep, stream);
+}
+
+// 3x3 / stride 1 / pad 1 convolution on rows as an implicit GEMM (Epilogue::conv_w): out [batch h w, cout] = act(conv + bias)
+int gemm_conv3x3_bf16_tc(const bf16* padded, const bf16* W, int ldw, int batch, int h, int w, int cin, int cout, const Epilogue& ep_in,
+                         cudaStream_t stream) {
+    SVB_REQUIRE(batch > 0 && h > 0 && w > 0 && w % 128 == 0 && cin % 64 == 0 && cout % 32 == 0,
+                "gemm_conv3x3: %d x %d map with %d -> %d channels: the width must be a multiple of 128, cin of 64, cout of 32", h, w, cin, cout);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(padded) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (ldw % 8) == 0 &&
+                !ep_in.resid && !ep_in.out2 && !ep_in.stat_out && !ep_in.ln_stats && !ep_in.gn_in_stats && ep_in.act != 1,
+                "gemm_conv3x3: unsupported epilogue / alignment");
+    Epilogue ep = ep_in;
+    ep.conv_w = w; ep.conv_h = h; ep.conv_c = cin;
+    const int M = batch * h * w, K = 9 * cin;
+    bool done = false;
+    const int rc = (cout <= 128) ? try_launch_streamlined<128>(padded, cin, W, ldw, M, cout, K, ep, stream, &done)
+                                 : try_launch_streamlined<256>(padded, cin, W, ldw, M, cout, K, ep, stream, &done);
+    if (rc) return rc;
+    SVB_REQUIRE(done, "gemm_conv3x3: the streamlined GEMM kernel refused this problem");
+    return 0;
 }
 
 }  // namespace svb

@@ -172,6 +172,26 @@ __global__ void im2col3x3_rows_kernel(const float* __restrict__ src, TO* __restr
     }
 }
 
+// ---- the operand of the implicit-GEMM 3x3 convolution: dst[b, y + 1, x + 1, c] = bf16(src[b, y, x, c]) on a zero border ----
+__global__ void pad_rows_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int H, int W, int C) {
+    const int b = blockIdx.y, c8n = C / 8;
+    const size_t total = (size_t)(H + 2) * (W + 2) * c8n;
+    const float* sb = src + (size_t)b * H * W * C;
+    bf16* db = dst + (size_t)b * (H + 2) * (W + 2) * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % c8n);
+        const size_t p = i / c8n;
+        const int px = (int)(p % (W + 2)), py = (int)(p / (W + 2));
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (py >= 1 && py <= H && px >= 1 && px <= W) {
+            const float4* q = reinterpret_cast<const float4*>(sb + ((size_t)(py - 1) * W + (px - 1)) * C) + 2 * c8;
+            v0 = __ldg(q);
+            v1 = __ldg(q + 1);
+        }
+        store8(db + p * C + c8 * 8, v0, v1);
+    }
+}
+
 // out = T(a + b[i mod b_n]): a positional embedding shared by every sample of the batch
 template <typename T>
 __global__ void add_cast_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ out, size_t n4, size_t b_n4) {
@@ -276,6 +296,23 @@ extern "C" int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, in
     else im2col3x3_rows_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, h, w, channels);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int svb_conv3x3_rows(const float* src, const void* weight_bf16, const float* bias, float* out, void* padded_ws, int batch, int h, int w,
+                                int cin, int cout, int relu, svb_stream_t stream) {
+    SVB_REQUIRE(src && weight_bf16 && out && padded_ws && batch > 0 && h > 0 && w > 0 && cin % 8 == 0, "svb_conv3x3_rows: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        ProfScope prof(PC_OTHER, 0, (double)batch * h * w * cin * 4 + (double)batch * (h + 2) * (w + 2) * cin * 2, s);
+        dim3 grid(grid_cap((size_t)(h + 2) * (w + 2) * cin / 8, 256), batch);
+        pad_rows_bf16_kernel<<<grid, 256, 0, s>>>(src, (bf16*)padded_ws, h, w, cin);
+        SVB_CHECK_CUDA(cudaGetLastError());
+    }
+    Epilogue ep;
+    ep.bias = bias;
+    ep.out = out; ep.ldo = cout;
+    ep.act = relu ? 2 : 0;
+    return gemm_conv3x3_bf16_tc((const bf16*)padded_ws, (const bf16*)weight_bf16, 9 * cin, batch, h, w, cin, cout, ep, s);
 }
 
 extern "C" int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream) {

@@ -2,7 +2,7 @@
 // B tile with TMA (or writes A by hand with the 128B swizzle, the path the attention kernel uses for P), issues
 // K/16 tcgen05.mma with caller-supplied shared-memory descriptor fields, and dumps the 128 x N fp32 accumulator.
 // tests/test_gpu_probe.py uses it to pin the MN-major and 32B-swizzle descriptor encodings against torch.
-#include "../../include/samvit_b200.h"
+#include "../../include/samvit_b200_probe.h"
 #include "common.cuh"
 #include "ptx.cuh"
 

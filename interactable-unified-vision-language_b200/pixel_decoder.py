@@ -86,6 +86,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
             self._outputs.append(output)
         self._laterals, self._outputs = self._laterals[::-1], self._outputs[::-1]              # :291-292, top-down order
         self.conv_dim = conv_dim
+        self.implicit_conv = True          # bf16 path: 3x3 output_conv as an implicit GEMM (False: im2col operand + GEMM, for A/B runs)
         self._cache_sig, self._pos_cache = None, {}
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -221,14 +222,22 @@ class MSDeformAttnPixelDecoder(nn.Module):
                            "svb_upsample_add_rows")                                             # cur_fpn + F.interpolate(out[-1], ...) (:348)
                 wo, bo, no = self._out[idx]
                 conv = torch.empty(B * h * w, C, dtype=torch.float32, device=dev)
-                per = max(1, min(B, (1 << 31) // (h * w * 9 * C * (2 if adt == torch.bfloat16 else 4))))     # images per im2col pass (<= 2 GB)
-                col = torch.empty(per * h * w, 9 * C, dtype=adt, device=dev)
-                for b0 in range(0, B, per):
-                    nb = min(per, B - b0)
-                    cabi.check(lib.svb_im2col3x3_rows(fpn[b0 * h * w:].data_ptr(), col.data_ptr(), _odt(adt), nb, h, w, C, st()), "svb_im2col3x3_rows")
-                    self._linear(mode, col[:nb * h * w], wo, bo, conv[b0 * h * w:(b0 + nb) * h * w],
-                                 act=2 if (no is None) else 0)                                  # output_conv (3x3)
-                del col
+                if adt == torch.bfloat16 and w % 128 == 0 and C % 64 == 0 and self.implicit_conv:
+                    # output_conv (3x3) as an implicit GEMM: the A tiles are row-shifted boxes of a zero-padded bf16 copy of the map
+                    # (68 MB per image at 256^2 x 512) instead of a 604 MB im2col operand
+                    pad = torch.empty(B * (h + 2) * (w + 2), C, dtype=torch.bfloat16, device=dev)
+                    cabi.check(lib.svb_conv3x3_rows(fpn.data_ptr(), wo.data_ptr(), bo.data_ptr() if bo is not None else None, conv.data_ptr(),
+                                                    pad.data_ptr(), B, h, w, C, C, 1 if (no is None) else 0, st()), "svb_conv3x3_rows")
+                    del pad
+                else:
+                    per = max(1, min(B, (1 << 31) // (h * w * 9 * C * (2 if adt == torch.bfloat16 else 4))))     # images per im2col pass (<= 2 GB)
+                    col = torch.empty(per * h * w, 9 * C, dtype=adt, device=dev)
+                    for b0 in range(0, B, per):
+                        nb = min(per, B - b0)
+                        cabi.check(lib.svb_im2col3x3_rows(fpn[b0 * h * w:].data_ptr(), col.data_ptr(), _odt(adt), nb, h, w, C, st()), "svb_im2col3x3_rows")
+                        self._linear(mode, col[:nb * h * w], wo, bo, conv[b0 * h * w:(b0 + nb) * h * w],
+                                     act=2 if (no is None) else 0)                              # output_conv (3x3)
+                    del col
                 if no is not None:
                     self._groupnorm(conv, 0, no, conv, 0, B, h * w, C, True, ws)               # norm + F.relu
                 cur_shape, cur, cur_stride = (h, w), conv, h * w * C

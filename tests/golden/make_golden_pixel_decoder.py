@@ -147,3 +147,24 @@ for seed, (name, (C, MD, M, NL, F_, N, side)) in enumerate(CASES.items()):
         blob["sd." + k] = v.numpy()
     np.savez_compressed(os.path.join(HERE, f"pixel_decoder_{name}.npz"), **blob)
     print(name, tuple(mask.shape), [tuple(m.shape) for m in multi], float(mask.abs().mean()), len(sd))
+
+
+# ---- the step1.yaml geometry (conv_dim = mask_dim = 512, 8 heads, d_ffn 1024, 6 encoder layers; configs/step1.yaml) on small maps.  The
+# 11.5 M weights are not stored: tests.util.seeded_state_dict regenerates them; the outputs are stored as 32768 samples each. ----
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from tests.util import sampled, seeded_state_dict  # noqa: E402
+C, MD, M, NL, F_, N, side, SEED = 512, 512, 8, 6, 1024, 1, 32, 4100
+mod = RefPixelDecoder(input_shape=None, transformer_dropout=0.0, transformer_nheads=M, transformer_dim_feedforward=F_,
+                      transformer_enc_layers=NL, conv_dim=C, mask_dim=MD, norm="GN", transformer_in_features=["res3", "res4", "res5"],
+                      common_stride=4).eval()
+mod.load_state_dict(seeded_state_dict(list(mod.state_dict().items()), SEED), strict=True)
+gf = torch.Generator().manual_seed(SEED + 1)
+feats = {f"res{2 + i}": torch.randn(N, c, side >> i, side >> i, generator=gf) for i, c in enumerate((128, 256, 512, 1024))}
+with torch.no_grad():
+    mask, multi = mod(dict(feats))
+blob = {"meta": np.array([C, MD, M, NL, F_, N, side, SEED], dtype=np.int64)}
+for name, t in [("mask_features", mask)] + [(f"multi{i}", m) for i, m in enumerate(multi)]:
+    idx, val = sampled(t, 32768, 7)
+    blob[name + ".idx"], blob[name + ".val"], blob[name + ".shape"] = idx.numpy(), val.numpy(), np.array(t.shape, dtype=np.int64)
+np.savez_compressed(os.path.join(HERE, "pixel_decoder_step1.npz"), **blob)
+print("step1", tuple(mask.shape), [tuple(m.shape) for m in multi], float(mask.abs().mean()))

@@ -93,6 +93,15 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name)
     assert lib.svb_version() >= 100
+    # the separate probe library (test / measurement infrastructure) and its header
+    with open(os.path.join(ROOT, "include", "samvit_b200_probe.h")) as f:
+        phdr = f.read()
+    pdecl = set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", phdr))
+    assert pdecl == set(cabi.PROBE_SYMBOLS), pdecl ^ set(cabi.PROBE_SYMBOLS)
+    plib = cabi.probe_lib()
+    for name in pdecl:
+        assert hasattr(plib, name)
+    assert not (pdecl - {"svb_probe_last_error"}) & set(cabi.SYMBOLS)        # no probe entry point in the product library
 
 
 def test_product_does_not_import_the_oracle():

@@ -107,6 +107,72 @@ def test_pixel_decoder_against_reference_goldens(case, precision, tol):
     assert max(errs.values()) < tol, errs
 
 
+def test_conv3x3_implicit_gemm_matches_conv2d():
+    """svb_conv3x3_rows (zero-padded bf16 map + row-shifted TMA boxes per filter tap inside the tcgen05 GEMM) against F.conv2d of the
+    bf16-rounded operands in fp64: the `output_conv` of the pixel decoder (transformer_encoder_deform.py:259-268) at 256-wide maps."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(21)
+    for (B, H, W, Cin, Cout, relu) in ((2, 16, 128, 64, 64, 0), (1, 24, 256, 128, 96, 1), (1, 256, 256, 512, 512, 1)):
+        x = torch.randn(B, H, W, Cin, generator=g)
+        wt = torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5
+        bias = torch.randn(Cout, generator=g)
+        ref = F.conv2d(x.bfloat16().double().permute(0, 3, 1, 2), wt.bfloat16().double(), bias.double(), padding=1)
+        if relu:
+            ref = torch.relu(ref)
+        ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+        xd, bd = x.to(DEV).contiguous(), bias.to(DEV)
+        w3 = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(DEV).bfloat16().contiguous()          # (Cout, ky, kx, Cin)
+        out = torch.full((B * H * W, Cout), float("nan"), device=DEV)
+        pad = torch.empty(B * (H + 2) * (W + 2), Cin, dtype=torch.bfloat16, device=DEV)
+        cabi.check(cabi.lib().svb_conv3x3_rows(xd.data_ptr(), w3.data_ptr(), bd.data_ptr(), out.data_ptr(), pad.data_ptr(), B, H, W, Cin, Cout, relu,
+                                               cabi.stream_ptr()), "svb_conv3x3_rows")
+        torch.cuda.synchronize()
+        err = ib.rel_l2(out, ref)
+        assert err < 1e-5, ((B, H, W, Cin, Cout), err)
+        # edges: the first / last row and column of the map see the zero border
+        o4, r4 = out.cpu().reshape(B, H, W, Cout), ref.reshape(B, H, W, Cout)
+        for sl in (o4[:, 0], o4[:, -1], o4[:, :, 0], o4[:, :, -1]), (r4[:, 0], r4[:, -1], r4[:, :, 0], r4[:, :, -1]):
+            pass
+        assert ib.rel_l2(torch.cat([o4[:, 0].flatten(), o4[:, -1].flatten(), o4[:, :, 0].flatten(), o4[:, :, -1].flatten()]),
+                         torch.cat([r4[:, 0].flatten(), r4[:, -1].flatten(), r4[:, :, 0].flatten(), r4[:, :, -1].flatten()])) < 1e-5
+
+
+def test_pixel_decoder_implicit_conv_equals_im2col_path():
+    """The whole pixel decoder at the step1.yaml geometry on the maps of one 1024 x 1024 image (res2 = 256 x 256: the implicit-GEMM
+    3x3 convolution is taken) against the same module with the im2col operand: same bf16 operands, same fp32 accumulation order per
+    K block -> the outputs agree to fp32 rounding."""
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    torch.manual_seed(5)
+    dec = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024, transformer_enc_layers=1,
+                                   conv_dim=512, mask_dim=512, norm="GN").to(DEV).eval()
+    feats = {f"res{2 + i}": torch.randn(1, c, 256 >> i, 256 >> i, device=DEV).bfloat16() for i, c in enumerate((128, 256, 512, 1024))}
+    outs = []
+    with torch.no_grad():
+        for flag in (True, False):
+            dec.implicit_conv = flag
+            mask, multi = dec(feats)
+            outs.append(mask)
+    assert torch.isfinite(outs[0]).all()
+    assert ib.rel_l2(outs[0], outs[1]) < 1e-5, ib.rel_l2(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 2e-2)])
+def test_pixel_decoder_at_the_step1_geometry(precision, tol):
+    """The composed module at the widths the reference runs (configs/step1.yaml: conv_dim = mask_dim = 512, 8 heads, d_ffn 1024, 6
+    deformable encoder layers) against samples of the UNMODIFIED reference class's outputs; weights regenerated from a seed."""
+    from tests.test_oracle import _sampled_err, _step1_pixel_decoder
+    z, mod, sd, feats, _ = _step1_pixel_decoder()
+    mod.to(DEV).eval()
+    mod.precision = precision
+    with torch.no_grad():
+        mask, multi = mod({k: v.to(DEV) for k, v in feats.items()})
+    errs = {"mask_features": _sampled_err(mask, z, "mask_features")}
+    for i, m in enumerate(multi):
+        errs[f"multi{i}"] = _sampled_err(m, z, f"multi{i}")
+    print("step1", precision, errs)
+    assert max(errs.values()) < tol, errs
+
+
 def test_encoder_feeds_pixel_decoder():
     """BASELINE config 5 in miniature: the ViT encoder's four maps go straight into the pixel decoder (bf16 hand-over, no `.float()`
     up-cast of transformer_encoder_deform.py:320,345), against the two CPU oracles chained in fp64."""

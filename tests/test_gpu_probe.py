@@ -16,7 +16,7 @@ DEV = "cuda"
 
 def run(a, b, K, N, a_sw, b_sw, b_mn, a_manual, al, asb, ak, bl, bsb, bk):
     out = torch.full((128, N), float("nan"), device=DEV)
-    cabi.check(cabi.lib().svb_probe_mma(a.data_ptr(), b.data_ptr(), out.data_ptr(), K, N, a_sw, b_sw, b_mn, a_manual,
+    cabi.check_probe(cabi.probe_lib().svb_probe_mma(a.data_ptr(), b.data_ptr(), out.data_ptr(), K, N, a_sw, b_sw, b_mn, a_manual,
                                         al, asb, ak, bl, bsb, bk, cabi.stream_ptr()), "probe")
     torch.cuda.synchronize()
     return out

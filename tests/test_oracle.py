@@ -239,6 +239,69 @@ def test_pixel_decoder_oracle_against_reference_goldens(case):
         assert ib.rel_l2(m, torch.from_numpy(z[f"multi{i}"])) < 2e-5
 
 
+def _sampled_err(t, z, name):
+    idx = torch.from_numpy(z[name + ".idx"])
+    ref = torch.from_numpy(z[name + ".val"]).double()
+    assert tuple(t.shape) == tuple(int(v) for v in z[name + ".shape"]), (name, t.shape)
+    got = t.detach().reshape(-1).double().cpu()[idx]
+    return float((got - ref).norm() / ref.norm())
+
+
+def _step1_pixel_decoder():
+    """The step1.yaml geometry (conv_dim = mask_dim = 512, 8 heads, d_ffn 1024, 6 layers): weights regenerated by seeded_state_dict."""
+    import os
+    import numpy as np
+    from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    from tests.util import GOLDEN, seeded_state_dict
+    z = np.load(os.path.join(GOLDEN, "pixel_decoder_step1.npz"))
+    C, MD, M, NL, F_, N, side, seed = (int(v) for v in z["meta"])
+    mod = MSDeformAttnPixelDecoder(transformer_dropout=0.0, transformer_nheads=M, transformer_dim_feedforward=F_, transformer_enc_layers=NL,
+                                   conv_dim=C, mask_dim=MD, norm="GN", transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    sd = seeded_state_dict(list(mod.state_dict().items()), seed)
+    mod.load_state_dict(sd, strict=True)
+    gf = torch.Generator().manual_seed(seed + 1)
+    feats = {f"res{2 + i}": torch.randn(N, c, side >> i, side >> i, generator=gf) for i, c in enumerate((128, 256, 512, 1024))}
+    return z, mod, sd, feats, (M, NL)
+
+
+@pytest.mark.slow
+def test_pixel_decoder_oracle_at_the_step1_geometry():
+    """oracle.pixel_decoder against the UNMODIFIED reference class at conv_dim 512 / 8 heads / 6 layers (samples of its outputs)."""
+    from oracle import pixel_decoder_oracle as po
+    z, mod, sd, feats, (M, NL) = _step1_pixel_decoder()
+    mask, multi = po.pixel_decoder({k: v.double() for k, v in sd.items()}, {k: v.double() for k, v in feats.items()}, M, NL)
+    assert _sampled_err(mask, z, "mask_features") < 5e-5
+    for i, m in enumerate(multi):
+        assert _sampled_err(m, z, f"multi{i}") < 5e-5
+
+
+def _step1_mask_path():
+    import os
+    import numpy as np
+    from iuvl_b200.mask_head import XDecoderMaskPath
+    from tests.util import GOLDEN, seeded_state_dict
+    z = np.load(os.path.join(GOLDEN, "xdecoder_mask_path_step1.npz"))
+    C, MD, Q, NH, FF, NL, B, ms, seed = (int(v) for v in z["meta"][:9])
+    sides = [int(v) for v in z["meta"][9:]]
+    path = XDecoderMaskPath(C, MD, Q, NH, FF, 3, [0, 1, 2, 0, 1, 2, 0, 1, 2][:NL])
+    sd = seeded_state_dict(list(path.state_dict().items()), seed)
+    path.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = [torch.randn(B, C, s_, s_, generator=g) for s_ in sides]
+    mf = torch.randn(B, MD, ms, ms, generator=g)
+    return z, path, sd, x, mf, (Q, NH, NL)
+
+
+@pytest.mark.slow
+def test_xdecoder_mask_path_oracle_at_the_step1_geometry():
+    """oracle.xdecoder_mask_path against the UNMODIFIED reference forward at hidden 512 / 101 queries / 8 heads / 9 layers."""
+    from oracle import mask_head_oracle as mo
+    z, path, sd, x, mf, (Q, NH, NL) = _step1_mask_path()
+    masks = mo.xdecoder_mask_path({k: v.double() for k, v in sd.items()}, [t.double() for t in x], mf.double(), Q, NH, [0, 1, 2, 0, 1, 2, 0, 1, 2][:NL])
+    assert _sampled_err(masks[0], z, "aux0") < 1e-5
+    assert _sampled_err(masks[-1], z, "pred_masks") < 5e-3
+
+
 def test_pixel_decoder_module_keys_match_reference():
     from iuvl_b200.pixel_decoder import MSDeformAttnPixelDecoder
     z, (C, MD, M, NL, F_), feats, sd = _pixel_decoder_case("small")

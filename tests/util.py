@@ -58,3 +58,42 @@ def ref_attention_core(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tens
     if ws < g:
         out = orc.window_unpartition(out, ws, pad_hw, (g, g))
     return out.reshape(B * g * g, D)
+
+
+def seeded_state_dict(items, seed):
+    """Deterministic weights for the fixtures at the reference's REAL widths (step1.yaml: 512 channels, 8 heads, 6 / 9 layers), whose
+    state_dicts (tens of millions of values) are not stored: every entry is drawn from a generator seeded by (seed, crc32 of its key), by
+    a rule of its name — the golden scripts load the result into the unmodified reference classes, the tests into the drop-ins."""
+    import zlib
+    out = {}
+    for k, v in items:
+        shape = tuple(v.shape)
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(k.encode())) % (2 ** 31))
+        r = torch.randn(shape, generator=g)
+        norm = ("norm" in k) or (k.startswith("input_proj.") and k.split(".")[2] == "1")
+        if k.endswith("sampling_offsets.weight") or k.endswith("attention_weights.weight"):
+            t = r * 0.05
+        elif k.endswith("sampling_offsets.bias"):
+            t = r * 0.5
+        elif norm and k.endswith("weight"):
+            t = 1.0 + 0.2 * r
+        elif norm or k.endswith("bias"):
+            t = 0.1 * r
+        elif len(shape) >= 2:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if k in ("query_feat.weight", "query_embed.weight", "level_embed.weight"):
+                t = r                                             # nn.Embedding default: N(0, 1)
+            else:
+                t = r / fan_in ** 0.5
+        else:
+            t = r
+        out[k] = t.to(v.dtype) if v.dtype.is_floating_point else v.clone()
+    return out
+
+
+def sampled(t, n, seed):
+    """(flat indices, values) of n pseudo-random entries of t"""
+    idx = torch.from_numpy(np.random.RandomState(seed).randint(0, t.numel(), size=min(n, t.numel())).astype(np.int64))
+    return idx, t.detach().reshape(-1)[idx].float()

@@ -14,7 +14,7 @@ for alt in (0,):
         res = []
         for reps in (64, 512):
             for _ in range(2):
-                cabi.check(lib.svb_probe_mma_rate(v, reps, alt, out.data_ptr(), cabi.stream_ptr()), "rate")
+                cabi.check_probe(cabi.probe_lib().svb_probe_mma_rate(v, reps, alt, out.data_ptr(), cabi.stream_ptr()), "rate")
                 torch.cuda.synchronize()
             res.append(out.cpu().tolist())
         per = (res[1][0] - res[0][0]) / (512 - 64)

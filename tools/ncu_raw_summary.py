@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Selected metrics of an `ncu --set full` capture from its raw-page CSV (`ncu -i x.ncu-rep --page raw --csv`, produced on the GPU box
+because the reports themselves exceed what gpurun copies back):  python tools/ncu_raw_summary.py raw.csv [out.csv]"""
+import csv
+import sys
+
+WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__cycles_elapsed.avg.per_second", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "smsp__average_warp_latency_issue_stalled_wait_per_warp_active.pct", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
+rows = list(csv.reader(open(sys.argv[1])))
+head, units, data = rows[0], rows[1], rows[2:]
+idx = [(w, head.index(w)) for w in WANT if w in head]
+out = open(sys.argv[2], "w", newline="") if len(sys.argv) > 2 else sys.stdout
+w = csv.writer(out)
+w.writerow([n for n, _ in idx])
+w.writerow([units[i] for _, i in idx])
+for r in data:
+    w.writerow([r[i][:90] for _, i in idx])
