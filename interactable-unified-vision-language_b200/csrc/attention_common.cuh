@@ -137,7 +137,8 @@ __device__ __forceinline__ void store_row(bf16* dst, uint32_t o_tmem, float inv)
 // One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
 // the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
 // the reference maximum).  Two passes over TMEM: the exact row maximum, then exp2 / sum / pack with packed fp32x2 arithmetic.
-template <int POLY>
+// KO: knock-out diagnostics of tools/ko_bench (timing only, results wrong): 1 = no maximum pass, 2 = no exponentials, 8 = no P stores
+template <int POLY, int KO = 0>
 __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
     uint32_t va[32], vb[32], vt[4];
     const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
@@ -156,6 +157,7 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
         f2_unpack(x, a0, a1);                                                                            \
         mk[k0 / 14] = fmax3(mk[k0 / 14], a0, a1);                                                        \
     }
+    if constexpr (!(KO & 1)) {
     ptx::tmem_ld_x32(s_tmem, va);
     ptx::tmem_ld_wait_dep(va);
     ptx::tmem_ld_x32(s_tmem + 32, vb);
@@ -175,8 +177,13 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
     ptx::tmem_ld_wait_dep(vb);
     ptx::tmem_ld_x4(s_tmem + 192, vt);
     SVB_WIN_A(vb, 5)
-#undef SVB_WIN_A
     ptx::tmem_ld_wait_dep(vt);
+    } else {
+        ptx::tmem_ld_x4(s_tmem + 192, vt);
+        ptx::tmem_ld_wait_dep(vt);
+        mk[0] = 0.f;
+    }
+#undef SVB_WIN_A
     mk[13] = fmaxf(mk[13], fmaxf(fmaxf(fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]), fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14])),
                                  fmaxf(fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]), fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]))));
     float m_ref = mk[0] + bhm[0];
@@ -196,12 +203,14 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
             float a0, a1;                                                                            \
             f2_unpack(x, a0, a1);                                                                    \
             float p0, p1;                                                                            \
-            if (poly_pair(e / 2, POLY)) exp2_poly_pair(a0, a1, p0, p1);   /* POLY of every 8 pairs on the FMA pipe */ \
+            if constexpr (KO & 2) { p0 = a0; p1 = a1; }                                              \
+            else if (poly_pair(e / 2, POLY)) exp2_poly_pair(a0, a1, p0, p1);   /* POLY of every 8 pairs on the FMA pipe */ \
             else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                             \
             l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
             pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
         }                                                                                            \
-        ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                 \
+        if constexpr (!(KO & 8)) ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                        \
+        else asm volatile("" :: "r"(pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7] ^ pk[8] ^ pk[9] ^ pk[10] ^ pk[11] ^ pk[12] ^ pk[13] ^ pk[14] ^ pk[15])); \
     }
     ptx::tmem_ld_x32(s_tmem, va);
     ptx::tmem_ld_wait_dep(va);

@@ -510,7 +510,7 @@ struct WinPMaps {
     CUtensorMap o0, o1, o0t, o1t;        // stores: boxes (64|16,14,9|5,1) of out viewed as [B,64,64,D]
 };
 
-template <int HD, int POLY, bool PH>
+template <int HD, int POLY, bool PH, int KO = 0>
 __global__ void __launch_bounds__(384, 1)
 attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int nwy, int nwx, int heads, int num_items, float scale_log2,
                               long long* __restrict__ phase_clocks, int l2_ahead) {
@@ -558,6 +558,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
 
     // item -> (image, window, head); query tile 1 (window rows 9..13) is entirely padding in the last window row
     auto decode = [&](int item, int& b, int& wy, int& wx, int& head) {
+        if constexpr (KO & 512) item %= heads;                     // diagnostic: every item is window 0 of image 0 (L2-resident operands)
         head = item % heads;
         const int bw = item / heads;
         const int win = bw % (nwy * nwx);
@@ -645,16 +646,17 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                 ptx::tc_fence_after();
                 // columns [0,64) of S_i: the previous item's P_i there was consumed by its PV (same issuer, in-order tensor pipe);
                 // its O_i (columns 112..191) is only overwritten by the S MMA below, issued after the group has loaded O_i
-                issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
+                if constexpr (!(KO & 256)) issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, base + C::OFF_R, base + C::OFF_R + C::R_MAIN, id_r);
                 ptx::mma_commit_e(&bars[C::B_BIAS + i]);
                 ptx::mbar_wait(&bars[C::B_BREAD + i], n & 1);      // rel-pos products consumed (and the previous O_i loaded)
                 ptx::tc_fence_after();
-                issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, k, k + C::K_MAIN, id_s);
+                if constexpr (!(KO & 128)) issue_qk<HD>(tmem + 208 * i, q, q + C::Q_MAIN, k, k + C::K_MAIN, id_s);
                 ptx::mma_commit_e(&bars[C::B_SFULL + i]);
                 ptx::mbar_wait(&bars[C::B_VFULL + st], ph);
                 ptx::mbar_wait(&bars[C::B_PFULL + i], n & 1);      // P_i is in TMEM
                 ptx::tc_fence_after();
-                if (HD > 64) {
+                if constexpr (KO & 64) {
+                } else if (HD > 64) {
                     constexpr uint32_t id_pv = ptx::make_idesc_bf16(128, HD, 0, 1);
                     const uint64_t dv = ptx::make_smem_desc(v, C::V_ATOM, 256, ptx::LAYOUT_SW32);
 #pragma unroll
@@ -719,12 +721,12 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ptx::tmem_ld_wait_dep(v2);
 #pragma unroll
             for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
-            barrel_shift27(rr, yi < 13 ? yi : 13);
+            if constexpr (!(KO & 4)) barrel_shift27(rr, yi < 13 ? yi : 13);
 #pragma unroll
             for (int kk = 0; kk < 14; ++kk) bhm[kk] = rr[13 - kk];
 #pragma unroll
             for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v2[j]) * LOG2E;
-            barrel_shift27(rr, xi);
+            if constexpr (!(KO & 4)) barrel_shift27(rr, xi);
 #pragma unroll
             for (int kk = 0; kk < 14; ++kk) bwl[kk] = rr[13 - kk];
             ptx::tc_fence_before();
@@ -750,7 +752,8 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ptx::mbar_wait(&bars[C::B_SFULL + i], ph);
             SVB_PHASE(2)
             ptx::tc_fence_after();
-            const float lsum = window_softmax_tile<POLY>(s_tmem, bhm, bwl, scale_log2);
+            float lsum = 1.f;
+            if constexpr (!(KO & 32)) lsum = window_softmax_tile<POLY, KO>(s_tmem, bhm, bwl, scale_log2);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&bars[C::B_PFULL + i]);
             SVB_PHASE(3)
@@ -763,7 +766,10 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             ptx::tc_fence_after();
             const float inv = 1.0f / lsum;
             uint32_t o[HD / 2];
-            {
+            if constexpr (KO & 16) {
+#pragma unroll
+                for (int j = 0; j < HD / 2; ++j) o[j] = __float_as_uint(inv);
+            } else {
                 uint32_t v[32];
 #pragma unroll
                 for (int c = 0; c < 64; c += 32) {
@@ -789,6 +795,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
             // ---- O(k) -> the dead Q buffer of this stage in the TMA layout -> one tensor store per tile ----
             {
                 uint8_t* ob = sm + st * C::STAGE + i * C::QT;
+                if constexpr (!(KO & 16)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)                        // 128B swizzle: 16-byte piece j of row t at piece j ^ (t & 7)
                     *reinterpret_cast<uint4*>(ob + t * 128 + ((j ^ (t & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -797,6 +804,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
                     for (int j = 0; j < 2; ++j)                    // 32B swizzle: piece j of row t at piece j ^ ((t >> 2) & 1)
                         *reinterpret_cast<uint4*>(ob + C::Q_MAIN + t * 32 + ((j ^ ((t >> 2) & 1)) << 4)) =
                             make_uint4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
+                }
                 }
                 ptx::fence_proxy_async_smem();                     // generic writes -> visible to the TMA (async proxy) read
                 ptx::mbar_arrive(&bars[C::B_OSTAGED + 2 * i + st]); // the store warp issues the tensor store and releases the stage
@@ -962,6 +970,24 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
         return 0;
     };
     const int k8 = exp2_poly(true);
+#ifdef SVB_ATTN_KO
+    static const int ko = [] { const char* e = getenv("SVB_ATTNW_KO"); return e ? atoi(e) : 0; }();
+    if (ko && HD == 80) {
+        switch (ko) {
+#define SVB_KO_CASE(K) case K: rc = launch(attn_window_persistent_kernel<HD, 2, false, K>, nullptr); break;
+            SVB_KO_CASE(1) SVB_KO_CASE(2) SVB_KO_CASE(3) SVB_KO_CASE(4) SVB_KO_CASE(8) SVB_KO_CASE(16) SVB_KO_CASE(32) SVB_KO_CASE(64) SVB_KO_CASE(128)
+            SVB_KO_CASE(256) SVB_KO_CASE(448) SVB_KO_CASE(36) SVB_KO_CASE(52) SVB_KO_CASE(500) SVB_KO_CASE(11) SVB_KO_CASE(15) SVB_KO_CASE(31)
+            SVB_KO_CASE(512) SVB_KO_CASE(513) SVB_KO_CASE(514) SVB_KO_CASE(515) SVB_KO_CASE(516) SVB_KO_CASE(520) SVB_KO_CASE(528) SVB_KO_CASE(544)
+            SVB_KO_CASE(576) SVB_KO_CASE(640) SVB_KO_CASE(768) SVB_KO_CASE(960) SVB_KO_CASE(1012) SVB_KO_CASE(523) SVB_KO_CASE(527) SVB_KO_CASE(543)
+            SVB_KO_CASE(548) SVB_KO_CASE(564)
+#undef SVB_KO_CASE
+            default: SVB_REQUIRE(false, "SVB_ATTNW_KO=%d is not compiled", ko);
+        }
+        if (rc) return rc;
+        SVB_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+#endif
     if (p.phase_clocks) rc = launch(attn_window_persistent_kernel<HD, 2, true>, p.phase_clocks);
     else if (k8 == 0) rc = launch(attn_window_persistent_kernel<HD, 0, false>, nullptr);
     else if (k8 == 3) rc = launch(attn_window_persistent_kernel<HD, 3, false>, nullptr);
@@ -1042,6 +1068,7 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
     // correct and SLOWER than the two-group kernel below; SVB_ATTNW_IMPL=3 selects it
     static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 2; }();
     if (impl == 3) return attention_window3(p, stream);
+    if (impl == 5) return attention_window5(p, stream);    // two independent chains per SM (experiments/attention_win5.cu)
 #endif
     return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }
