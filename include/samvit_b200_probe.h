@@ -22,6 +22,9 @@ const char* svb_probe_last_error(void);
 /* MMA issue-rate microbenchmark: cycles_out[0] = cycles for `reps` back-to-back tcgen05.mma of one shape (see probe.cu) incl.
  * completion, [1] = cycles in the issue loop (device pointers). */
 int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* cycles_out, svb_stream_t stream);
+/* TMEM load / store rate microbenchmark: `nwarps` (1..16) warps each issue `reps` tcgen05.ld / st of 32 lanes x 32 columns back to back
+ * (mode 0 / 1: loads, one / two in flight per warp; 2: stores); cycles_out[w] = cycles of warp w (device pointer, 16 entries). */
+int svb_probe_tmem_rate(int nwarps, int reps, int mode, long long* cycles_out, svb_stream_t stream);
 int svb_probe_mma(const void* a, const void* b, float* out, int K, int N, int a_sw, int b_sw, int b_mn_major, int a_manual,
                   unsigned a_lbo, unsigned a_sbo, unsigned a_kstep, unsigned b_lbo, unsigned b_sbo, unsigned b_kstep,
                   svb_stream_t stream);

@@ -20,7 +20,7 @@ SOURCES = ["encoder.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "attention
 # adds them (and the dispatch hooks guarded by SVB_EXPERIMENTAL_*) for A/B runs
 EXPERIMENTAL = os.environ.get("SVB_BUILD_EXPERIMENTAL", "0") == "1"
 if EXPERIMENTAL:
-    SOURCES = SOURCES + ["experiments/attention_win3.cu", "experiments/attention_win5.cu"]
+    SOURCES = SOURCES + ["experiments/attention_win3.cu", "experiments/attention_win5.cu", "experiments/attention_win6.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-I", CSRC] + (["-DSVB_EXPERIMENTAL_WIN3"] if EXPERIMENTAL else []) + (["-DSVB_ATTN_KO"] if os.environ.get("SVB_BUILD_KO", "0") == "1" else [])

@@ -92,6 +92,7 @@ PROBE_LIB_PATH = os.path.join(HERE, "libsamvit_probe.so")
 PROBE_SYMBOLS = {
     "svb_probe_last_error": (C.c_char_p, []),
     "svb_probe_mma_rate": (_i, [_i, _i, _i, _vp, _vp]),
+    "svb_probe_tmem_rate": (_i, [_i, _i, _i, _vp, _vp]),
     "svb_probe_mma": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i] + [C.c_uint] * 6 + [_vp]),
 }
 

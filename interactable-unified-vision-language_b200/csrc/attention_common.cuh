@@ -137,10 +137,15 @@ __device__ __forceinline__ void store_row(bf16* dst, uint32_t o_tmem, float inv)
 // One 128-query x 196-key window tile: S (fp32, TMEM columns [0,196) of s_tmem) -> P (bf16, TMEM columns [0,104)), returns
 // the row sum.  bhm / bwl are the row's rel-pos terms (log2 units) per key row / key column; bhm is consumed (shifted by
 // the reference maximum).  Two passes over TMEM: the exact row maximum, then exp2 / sum / pack with packed fp32x2 arithmetic.
-// KO: knock-out diagnostics of tools/ko_bench (timing only, results wrong): 1 = no maximum pass, 2 = no exponentials, 8 = no P stores
+// KO: knock-out diagnostics (SVB_BUILD_KO=1, tools/call14.sh; timing only, results wrong): 1 = no maximum pass, 2 = no exponentials,
+// 8 = no P stores, 1024 / 2048 = the maximum / exponential pass WITHOUT its TMEM loads (arithmetic on stale registers)
 template <int POLY, int KO = 0>
 __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
     uint32_t va[32], vb[32], vt[4];
+    if constexpr ((KO & 3072) != 0) {               // diagnostics that skip loads: defined register contents
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { va[e] = 0x3f800000u + e; vb[e] = 0x3f000000u + e; }
+    }
     const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
     // ---- pass A: the row's EXACT maximum exponent.  Per key row kh the maximum of s * scale + w term (an FMA and half a
     // three-input maximum per element: the pairs (k, k+1) never straddle a key row, 14 is even), then + h term.  A reference that
@@ -158,23 +163,23 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
         mk[k0 / 14] = fmax3(mk[k0 / 14], a0, a1);                                                        \
     }
     if constexpr (!(KO & 1)) {
-    ptx::tmem_ld_x32(s_tmem, va);
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 32, vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem, va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem + 32, vb);
     SVB_WIN_A(va, 0)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 64, va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem + 64, va);
     SVB_WIN_A(vb, 1)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 96, vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem + 96, vb);
     SVB_WIN_A(va, 2)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 128, va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem + 128, va);
     SVB_WIN_A(vb, 3)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 160, vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_x32(s_tmem + 160, vb);
     SVB_WIN_A(va, 4)
-    ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 1024)) ptx::tmem_ld_wait_dep(vb);
     ptx::tmem_ld_x4(s_tmem + 192, vt);
     SVB_WIN_A(vb, 5)
     ptx::tmem_ld_wait_dep(vt);
@@ -212,23 +217,23 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
         if constexpr (!(KO & 8)) ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                        \
         else asm volatile("" :: "r"(pk[0] ^ pk[1] ^ pk[2] ^ pk[3] ^ pk[4] ^ pk[5] ^ pk[6] ^ pk[7] ^ pk[8] ^ pk[9] ^ pk[10] ^ pk[11] ^ pk[12] ^ pk[13] ^ pk[14] ^ pk[15])); \
     }
-    ptx::tmem_ld_x32(s_tmem, va);
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 32, vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem, va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem + 32, vb);
     SVB_WIN_B(va, 0)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 64, va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem + 64, va);
     SVB_WIN_B(vb, 1)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 96, vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem + 96, vb);
     SVB_WIN_B(va, 2)
-    ptx::tmem_ld_wait_dep(vb);
-    ptx::tmem_ld_x32(s_tmem + 128, va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem + 128, va);
     SVB_WIN_B(vb, 3)
-    ptx::tmem_ld_wait_dep(va);
-    ptx::tmem_ld_x32(s_tmem + 160, vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(va);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_x32(s_tmem + 160, vb);
     SVB_WIN_B(va, 4)
-    ptx::tmem_ld_wait_dep(vb);
+    if constexpr (!(KO & 2048)) ptx::tmem_ld_wait_dep(vb);
     SVB_WIN_B(vb, 5)
 #undef SVB_WIN_B
     {
@@ -245,6 +250,148 @@ __device__ __forceinline__ float window_softmax_tile(uint32_t s_tmem, float (&bh
         for (int e = 2; e < 8; ++e) pk[e] = 0u;
         ptx::tmem_st_x8(s_tmem + 96, pk);
     }
+    ptx::tmem_st_wait();
+    float l0, l1;
+    f2_unpack(l01, l0, l1);
+    return l0 + l1;
+}
+
+// The same tile with ONE pass over tensor memory.  Measured (tools/tmem_rate.py, profiles/r02_attnw_analysis): tcgen05.ld delivers
+// 56 bytes per clock PER SM however many warps issue it (one x32 load of 4 KB = 72 cycles), and the two-pass form above reads 532
+// columns per query row (S twice, the rel-pos products, O) — 8700 cycles per (window, head) item: that, not the MUFU or the issue
+// slots, is what the windowed kernel costs.  Here S is read once: the reference of the exponentials is the exact maximum of the row's
+// FIRST 32 keys (a value that is attained, so the row cannot underflow as a whole); every later chunk's maximum is checked before its
+// exponentials and, if it exceeds the reference by more than 2^64 (never on real activations; tests/test_gpu_ops.py provokes it), the
+// reference moves there and the P columns already written are rescaled in place — P <= 2^64 always, so neither bf16 P, the fp32 row
+// sum nor the fp32 O accumulator can overflow (torch.softmax has no limit either, image_encoder.py:246-252).
+template <int POLY>
+__device__ __forceinline__ float window_softmax_tile_1p(uint32_t s_tmem, float (&bhm)[14], const float (&bwl)[14], float scale_log2) {
+    constexpr float LIMIT = 64.0f;
+    uint32_t va[32], vb[32], vt[4];
+    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+    f32x2 l01 = f2_pack(0.f, 0.f);
+    // maximum of chunk CHUNK's exponents (relative to the current reference, which bhm carries)
+#define SVB_W1_MAX(V, CHUNK, MX)                                                                         \
+    {                                                                                                    \
+        float m0_ = -INFINITY, m1_ = -INFINITY;                                                          \
+        _Pragma("unroll") for (int e = 0; e < 32; e += 4) {                                              \
+            const int k0 = 32 * (CHUNK) + e;                                                             \
+            const f32x2 x0 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,              \
+                                           f2_pack(bwl[k0 % 14], bwl[(k0 + 1) % 14])), f2_pack(bhm[k0 / 14], bhm[(k0 + 1) / 14])); \
+            const f32x2 x1 = f2_add(f2_fma(f2_pack(__uint_as_float(V[e + 2]), __uint_as_float(V[e + 3])), sc2,          \
+                                           f2_pack(bwl[(k0 + 2) % 14], bwl[(k0 + 3) % 14])), f2_pack(bhm[(k0 + 2) / 14], bhm[(k0 + 3) / 14])); \
+            float a0, a1, a2, a3;                                                                        \
+            f2_unpack(x0, a0, a1);                                                                       \
+            f2_unpack(x1, a2, a3);                                                                       \
+            m0_ = fmax3(m0_, a0, a1);                                                                    \
+            m1_ = fmax3(m1_, a2, a3);                                                                    \
+        }                                                                                                \
+        MX = fmaxf(m0_, m1_);                                                                            \
+    }
+    // exp2 / sum / pack / store of chunk CHUNK
+#define SVB_W1_EXP(V, CHUNK)                                                                             \
+    {                                                                                                    \
+        uint32_t pk[16];                                                                                 \
+        _Pragma("unroll") for (int e = 0; e < 32; e += 2) {                                              \
+            const int k0 = 32 * (CHUNK) + e, k1 = k0 + 1;                                                \
+            const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,               \
+                                          f2_pack(bwl[k0 % 14], bwl[k1 % 14])), f2_pack(bhm[k0 / 14], bhm[k1 / 14]));   \
+            float a0, a1;                                                                                \
+            f2_unpack(x, a0, a1);                                                                        \
+            float p0, p1;                                                                                \
+            if (poly_pair(e / 2, POLY)) exp2_poly_pair(a0, a1, p0, p1);   /* POLY of every 8 pairs on the FMA pipe */ \
+            else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                                 \
+            l01 = f2_add(l01, f2_pack(p0, p1));                                                          \
+            pk[e / 2] = pack_bf16x2(p0, p1);                                                             \
+        }                                                                                                \
+        ptx::tmem_st_x16(s_tmem + 16 * (CHUNK), pk);                                                     \
+    }
+    // the reference moves up by the chunk maximum where that exceeds LIMIT: rescale what has been written (chunks 0 .. CHUNK-1)
+#define SVB_W1_CHECK(CHUNK, MX)                                                                          \
+    if (__any_sync(0xffffffffu, MX > LIMIT)) {                                                           \
+        const float delta = MX > LIMIT ? MX : 0.f;                                                       \
+        const float f = ptx::ex2_approx(-delta);                                                         \
+        ptx::tmem_st_wait();                                                                             \
+        _Pragma("unroll 1") for (int c = 0; c < (CHUNK); ++c) {                                          \
+            uint32_t r[16];                                                                              \
+            ptx::tmem_ld_x16(s_tmem + 16 * c, r);                                                        \
+            ptx::tmem_ld_wait_dep(r);                                                                    \
+            _Pragma("unroll") for (int e = 0; e < 16; ++e)                                               \
+                r[e] = pack_bf16x2(__uint_as_float(r[e] << 16) * f, __uint_as_float(r[e] & 0xffff0000u) * f);           \
+            ptx::tmem_st_x16(s_tmem + 16 * c, r);                                                        \
+        }                                                                                                \
+        l01 = f2_mul(l01, f2_pack(f, f));                                                                \
+        _Pragma("unroll") for (int k = 0; k < 14; ++k) bhm[k] -= delta;                                  \
+    }
+    float mx;
+    ptx::tmem_ld_x32(s_tmem, va);
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 32, vb);
+    SVB_W1_MAX(va, 0, mx)                                          // the reference: exact maximum of keys 0..31
+#pragma unroll
+    for (int k = 0; k < 14; ++k) bhm[k] -= mx;
+    SVB_W1_EXP(va, 0)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 64, va);
+    SVB_W1_MAX(vb, 1, mx)
+    SVB_W1_CHECK(1, mx)
+    SVB_W1_EXP(vb, 1)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 96, vb);
+    SVB_W1_MAX(va, 2, mx)
+    SVB_W1_CHECK(2, mx)
+    SVB_W1_EXP(va, 2)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x32(s_tmem + 128, va);
+    SVB_W1_MAX(vb, 3, mx)
+    SVB_W1_CHECK(3, mx)
+    SVB_W1_EXP(vb, 3)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x32(s_tmem + 160, vb);
+    SVB_W1_MAX(va, 4, mx)
+    SVB_W1_CHECK(4, mx)
+    SVB_W1_EXP(va, 4)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x4(s_tmem + 192, vt);
+    SVB_W1_MAX(vb, 5, mx)
+    SVB_W1_CHECK(5, mx)
+    SVB_W1_EXP(vb, 5)
+    ptx::tmem_ld_wait_dep(vt);
+    {
+        // keys 192..195 + zero columns for keys 196..207
+        float a0 = fmaf(__uint_as_float(vt[0]), scale_log2, bwl[192 % 14]) + bhm[192 / 14];
+        float a1 = fmaf(__uint_as_float(vt[1]), scale_log2, bwl[193 % 14]) + bhm[193 / 14];
+        float a2 = fmaf(__uint_as_float(vt[2]), scale_log2, bwl[194 % 14]) + bhm[194 / 14];
+        float a3 = fmaf(__uint_as_float(vt[3]), scale_log2, bwl[195 % 14]) + bhm[195 / 14];
+        mx = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        if (__any_sync(0xffffffffu, mx > LIMIT)) {
+            const float delta = mx > LIMIT ? mx : 0.f;
+            const float f = ptx::ex2_approx(-delta);
+            ptx::tmem_st_wait();
+#pragma unroll 1
+            for (int c = 0; c < 6; ++c) {
+                uint32_t r[16];
+                ptx::tmem_ld_x16(s_tmem + 16 * c, r);
+                ptx::tmem_ld_wait_dep(r);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = pack_bf16x2(__uint_as_float(r[e] << 16) * f, __uint_as_float(r[e] & 0xffff0000u) * f);
+                ptx::tmem_st_x16(s_tmem + 16 * c, r);
+            }
+            l01 = f2_mul(l01, f2_pack(f, f));
+            a0 -= delta; a1 -= delta; a2 -= delta; a3 -= delta;
+        }
+        uint32_t pk[8];
+        const float p0 = ptx::ex2_approx(a0), p1 = ptx::ex2_approx(a1), p2 = ptx::ex2_approx(a2), p3 = ptx::ex2_approx(a3);
+        l01 = f2_add(l01, f2_pack(p0 + p2, p1 + p3));
+        pk[0] = pack_bf16x2(p0, p1);
+        pk[1] = pack_bf16x2(p2, p3);
+#pragma unroll
+        for (int e = 2; e < 8; ++e) pk[e] = 0u;
+        ptx::tmem_st_x8(s_tmem + 96, pk);
+    }
+#undef SVB_W1_MAX
+#undef SVB_W1_EXP
+#undef SVB_W1_CHECK
     ptx::tmem_st_wait();
     float l0, l1;
     f2_unpack(l01, l0, l1);

@@ -979,7 +979,8 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
             SVB_KO_CASE(256) SVB_KO_CASE(448) SVB_KO_CASE(36) SVB_KO_CASE(52) SVB_KO_CASE(500) SVB_KO_CASE(11) SVB_KO_CASE(15) SVB_KO_CASE(31)
             SVB_KO_CASE(512) SVB_KO_CASE(513) SVB_KO_CASE(514) SVB_KO_CASE(515) SVB_KO_CASE(516) SVB_KO_CASE(520) SVB_KO_CASE(528) SVB_KO_CASE(544)
             SVB_KO_CASE(576) SVB_KO_CASE(640) SVB_KO_CASE(768) SVB_KO_CASE(960) SVB_KO_CASE(1012) SVB_KO_CASE(523) SVB_KO_CASE(527) SVB_KO_CASE(543)
-            SVB_KO_CASE(548) SVB_KO_CASE(564)
+            SVB_KO_CASE(548) SVB_KO_CASE(564) SVB_KO_CASE(1536) SVB_KO_CASE(2560) SVB_KO_CASE(3584) SVB_KO_CASE(3592) SVB_KO_CASE(1024) SVB_KO_CASE(2048)
+            SVB_KO_CASE(3072)
 #undef SVB_KO_CASE
             default: SVB_REQUIRE(false, "SVB_ATTNW_KO=%d is not compiled", ko);
         }
@@ -1064,11 +1065,13 @@ int attention_tc(const AttnTcParams& p, cudaStream_t stream) {
                    (double)p.batch * gh * gw * 4.0 * D_ * 2, stream);
     if (p.ws == 64) return p.hd == 64 ? launch_global<64>(p, stream) : launch_global<80>(p, stream);
 #ifdef SVB_EXPERIMENTAL_WIN3
-    // experimental builds only (SVB_BUILD_EXPERIMENTAL=1): the helper-group pipeline of csrc/experiments/attention_win3.cu, measured
-    // correct and SLOWER than the two-group kernel below; SVB_ATTNW_IMPL=3 selects it
+    // experimental builds only (SVB_BUILD_EXPERIMENTAL=1), all measured correct and NOT faster than the two-group kernel below inside the
+    // encoder step (csrc/experiments/, profiles/r02_attnw_analysis): SVB_ATTNW_IMPL = 3 helper-group pipeline, 5 two independent chains
+    // per SM (SVB_ATTNW_ONEPASS=1: S read from TMEM once), 6 split rows with four softmax warps per scheduler
     static const int impl = [] { const char* e = getenv("SVB_ATTNW_IMPL"); return e ? atoi(e) : 2; }();
     if (impl == 3) return attention_window3(p, stream);
-    if (impl == 5) return attention_window5(p, stream);    // two independent chains per SM (experiments/attention_win5.cu)
+    if (impl == 5 && !p.phase_clocks) return attention_window5(p, stream);
+    if (impl == 6 && !p.phase_clocks) return attention_window6(p, stream);
 #endif
     return p.hd == 64 ? launch_window_persistent<64>(p, stream) : launch_window_persistent<80>(p, stream);
 }

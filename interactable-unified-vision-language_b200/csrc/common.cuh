@@ -236,7 +236,8 @@ int pack_rel_table(const float* src, bf16* dst, int L, int hd, bool is_w, cudaSt
 int fill_pad_rows(bf16* qkv, const float* bias, int B, int gh, int gw, int gph, int gpw, int ld, cudaStream_t stream);
 int attention_tc(const AttnTcParams& p, cudaStream_t stream);
 int attention_window3(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win3.cu
-int attention_window5(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win5.cu
+int attention_window5(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win5.cu: two independent chains per SM
+int attention_window6(const AttnTcParams& p, cudaStream_t stream);   // experiments/attention_win6.cu: split-row windowed kernel
 int attention_global_ext(const AttnTcParams& p, cudaStream_t stream); // attention_ext.cu: global attention on other token grids
 // A = zero-padded bf16 map, see Epilogue::conv_w (gemm_tc2.cu)
 int gemm_conv3x3_bf16_tc(const bf16* padded, const bf16* W, int ldw, int batch, int h, int w, int cin, int cout, const Epilogue& ep, cudaStream_t stream);

@@ -1,20 +1,26 @@
-// EXPERIMENT (built only with SVB_BUILD_EXPERIMENTAL=1, selected by SVB_ATTNW_IMPL=5): windowed attention as two INDEPENDENT chains per
-// SM with a piecewise-released ring, optionally (SVB_ATTNW_ONEPASS=1, the default here) with S read from tensor memory ONCE
-// (window_softmax_tile_1p).  Correct (test_attention_tcgen05 and the adversarial test_windowed_softmax_reference_moves_without_overflow
-// green) and measured (tools/call15.sh, call17.sh, call20.sh; profiles/r02_attnw_analysis): per 16 ViT-H images kernel-alone 196 us
-// (two-pass) / 203 us (one-pass) against 207-210 us for the production two-group kernel (attn_window_persistent_kernel,
-// attention_tc.cu), 152 vs 145 us at head_dim 64 — and inside the encoder step, at its power-capped 1.2-1.35 GHz, 34.9-35.7 ms per 64
-// images against 33.9-35.3: NO gain.  With every TMA load / store / prefetch knocked out (diagnostic flags in l2_ahead >> 8) it still
-// takes 187-190 us, and reading S once instead of twice (-36 % of the tcgen05.ld bytes, the port measured at 56 B/clk and SM) changes
-// nothing: per tile the chain bias MMA -> skew -> S MMA -> softmax -> PV MMA -> output with its six mbarrier hand-overs is ~7500
-// cycles long and only two S tiles fit tensor memory, so two chains are all the overlap there is, however they are arranged.
-//
-// Design notes of the kernel:
-//   * chain c owns stage c of the ring, S tile c of tensor memory, a softmax group, an MMA issuer and a load / store thread, and walks
-//     its own items, query tile 0 then query tile 1; the stage is refilled piece by piece as the item lets go of it (Q0 after the
-//     store of O0, K after the last S MMA, V after the last PV, Q1 after the store of O1), so the TMA latency of the next item hides
-//     under the second tile; Q1 is not loaded for windows whose tile 1 lies outside the token grid;
-//   * the warp of tile 1 whose 32 rows are all padding keeps the barrier protocol and skips the arithmetic.
+// EXPERIMENT (built only with SVB_BUILD_EXPERIMENTAL=1, selected by SVB_ATTNW_IMPL=6) — correct (test_attention_tcgen05 green) and
+// measured SLOWER than the kernels it was meant to beat (tools/call18.sh, profiles/r02_attnw_analysis/c18_*): 240 us per 16 ViT-H
+// images (209 with every exponential on the MUFU) against 208 for the two-group kernel, 36.7 against 34.1-35.0 ms per 64 images
+// inside the encoder step.  Doubling the softmax warps cannot help a kernel that is bound by the TMEM read port (56 bytes per clock
+// and SM, tools/tmem_rate.py) — the measurement that led to the one-pass softmax of attention_win5.cu.
+// Windowed attention (14 x 14 windows of the padded token grid) with FOUR softmax warps per scheduler (sm_100a).  Same arithmetic and
+// the same shared-memory / tensor-memory layout as attn_window_persistent_kernel (attention_tc.cu): S = Q K^T and O = P V on tcgen05
+// with fp32 accumulators in TMEM, decomposed rel-pos bias from two extra MMAs against the rel_pos tables skewed in registers,
+// exact-maximum base-2 softmax in fp32 (image_encoder.py:239-304, 340-376).  What the measurements of profiles/r02_attnw_analysis
+// left: the eight softmax warps of that kernel — two per scheduler — issue one instruction per ~3.8 cycles and carry 8100 of its
+// 9070 cycles per item however the two chains are arranged, and the ring adds (TMA latency + that) / 2.  Here
+//   * a query row's 196 keys are split over TWO threads (keys 0..111 = 8 key rows / keys 112..195 = 6 key rows + the 12 zero columns
+//     of the padded contraction; warps w and w + 4 of a chain work on the same 32 rows): 16 softmax warps at 104 registers
+//     (setmaxnreg), four per scheduler.  Each half writes its P over S columns only IT reads: keys 0..111 over the first 56 columns
+//     of the S tile, keys 112..207 into 48 of the 96 tensor-memory columns beside the two S tiles (the PV MMAs of the last six K
+//     steps take their A operand from there).  The two halves exchange the row maximum and the row sum through one shared-memory
+//     word per row and a 64-thread named barrier; each normalises and stages half of the output columns;
+//   * the CTA runs two INDEPENDENT chains (chain c owns stage c of the ring, S tile c of tensor memory, 8 softmax warps, an MMA
+//     issuer and a load / store thread, and walks its own items, query tile 0 then query tile 1), and the stage is refilled piece
+//     by piece as the item lets go of it (Q0 after the store of O0, K after the last S MMA, V after the last PV, Q1 after the
+//     store of O1), so the TMA latency of the next item hides under the second tile;
+//   * the warps of tile 1 whose 32 rows are all padding (rows 96..127 of the 70-row tile) keep the barrier protocol and skip the
+//     arithmetic; Q1 is not loaded for windows whose tile 1 lies outside the token grid.
 #include "attention_common.cuh"
 
 #include <algorithm>
@@ -23,7 +29,7 @@
 namespace svb {
 namespace {
 
-// shared-memory / tensor-map layout (that of attn_window_persistent_kernel, attention_tc.cu)
+// shared-memory / tensor-map layout of the production windowed kernel (attention_tc.cu)
 template <int HD> struct WPCfg {
     static constexpr int TAIL = HD - 64;
     static constexpr int Q_MAIN = 128 * 128, Q_TAIL = TAIL ? 128 * 32 : 0;   // one query tile (126 / 70 rows used)
@@ -35,7 +41,8 @@ template <int HD> struct WPCfg {
     static constexpr int R_MAIN = 64 * 128, R_TAIL = TAIL ? 64 * 32 : 0;
     static constexpr int OFF_R = 2 * STAGE;
     static constexpr int OFF_BAR = OFF_R + R_MAIN + R_TAIL;
-    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static constexpr int OFF_XCH = OFF_BAR + 256;                            // [2 chains][2 halves][128 rows] fp32: row maximum, then row sum
+    static constexpr int SMEM = OFF_XCH + 2048 + 1024;
     static_assert(SMEM <= 232448, "shared memory budget");
     static constexpr int ROWB = 128 + (TAIL ? 32 : 0);
     static constexpr int V_TX = 196 * ROWB;
@@ -50,34 +57,146 @@ struct WinPMaps {
     CUtensorMap o0, o1, o0t, o1t;        // stores: boxes (64|16,14,9|5,1) of out viewed as [B,gh,gw,D]
 };
 
-// The two-group production kernel runs its two query-tile chains in LOCKSTEP on the same
-// item — both in their softmax (MUFU contended, 4200 cycles) and both in their waits (bias MMA -> skew 2000, S 350, PV 1250,
-// output 560: the MUFU idle for half of an item's 8350 cycles) at the same time; and with ALL arithmetic knocked out the launch
-// still takes 153 of 208 us: the 770 MB it moves per 16 images is the floor (5.0 TB/s), so at the power-capped clocks of the whole
-// step (1.32 GHz) the serial chain, not the memory, is what one pays for.  Here the CTA runs TWO chains that share nothing but the
-// SM: chain c owns stage c of the ring, S tile c of tensor memory, a softmax group, an MMA issuer and a load / store thread, and
-// walks its OWN items (chain id = 2 blockIdx + c), query tile 0 then query tile 1 of an item one after the other.  The two chains
-// drift apart by themselves, so one chain's softmax runs beside the other chain's MMAs, skew and output.  Inside a chain the
-// buffers of the stage are refilled piece by piece as the item lets go of them — Q0 when the store of O0 has read it (the output
-// tile is staged in the dead Q buffer), K when S of the last tile has retired, V after the last PV, Q1 after the store of O1 —
-// so the next item's loads run under this item's second tile.  The warp of tile 1 whose 32 rows are all padding (rows 96..127
-// of the 70-row tile) keeps the barrier protocol and skips the arithmetic; Q1 is not loaded for windows whose tile 1 lies outside
-// the token grid.
-template <int HD> struct W5Cfg : WPCfg<HD> {
+// u[j] <- u[j + sh] for j < NOUT, sh in [0, 2^STAGES): conditional-move stages from the high bit down, each only as wide as the later
+// stages still need (entries past the 27 products are never selected: sh + j <= 26 by construction)
+template <int NOUT, int STAGES>
+__device__ __forceinline__ void barrel_pick(float (&u)[27], int sh) {
+#pragma unroll
+    for (int s = STAGES - 1; s >= 0; --s) {
+        const int bit = 1 << s;
+        const bool on = (sh & bit) != 0;
+#pragma unroll
+        for (int j = 0; j < NOUT + bit - 1 && j < 27; ++j) u[j] = on ? (j + bit < 27 ? u[j + bit] : 0.f) : u[j];
+    }
+}
+
+// One half of a query row of a 128-query x 196-key window tile.  HALF 0: keys 0..111 (8 key rows), S columns [0,112) of the tile at
+// s_half, P (bf16 pairs) into 56 columns at p_half.  HALF 1: keys 112..195 (6 key rows) + zeros for keys 196..207, S columns
+// [112,208) at s_half, P into 48 columns at p_half.  bh / bw: the row's rel-pos terms of this half's key rows / of the 14 key columns
+// (log2 units; bh is consumed).  Two passes over TMEM: the exact maximum (exchanged with the partner thread through xch_mine /
+// xch_other and the pair's named barrier), then exp2 / sum / pack.  Returns the half's row sum.
+template <int POLY, int HALF>
+__device__ __forceinline__ float window_softmax_half(uint32_t s_half, uint32_t p_half, float (&bh)[8], const float (&bw)[14],
+                                                     float scale_log2, float* xch_mine, float* xch_other, int pair_bar) {
+    constexpr int NCH = HALF ? 6 : 7, NROWS = HALF ? 6 : 8, REAL = HALF ? 84 : 112;     // 16-column chunks, key rows, real keys
+    uint32_t va[16], vb[16];
+    const f32x2 sc2 = f2_pack(scale_log2, scale_log2);
+    float mk[NROWS];
+#pragma unroll
+    for (int k = 0; k < NROWS; ++k) mk[k] = -INFINITY;
+#define SVB_H_A(V, CHUNK)                                                                                \
+    if ((CHUNK) < NCH) {                                                                                 \
+        _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                              \
+            const int k0 = 16 * (CHUNK) + e;                                                             \
+            if (k0 < REAL) {                                                                             \
+                const f32x2 x = f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2, f2_pack(bw[k0 % 14], bw[(k0 + 1) % 14])); \
+                float a0, a1;                                                                            \
+                f2_unpack(x, a0, a1);                                                                    \
+                mk[k0 / 14] = fmax3(mk[k0 / 14], a0, a1);                                                \
+            }                                                                                            \
+        }                                                                                                \
+    }
+    ptx::tmem_ld_x16(s_half, va);
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 16, vb);
+    SVB_H_A(va, 0)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x16(s_half + 32, va);
+    SVB_H_A(vb, 1)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 48, vb);
+    SVB_H_A(va, 2)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x16(s_half + 64, va);
+    SVB_H_A(vb, 3)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 80, vb);
+    SVB_H_A(va, 4)
+    ptx::tmem_ld_wait_dep(vb);
+    if (NCH > 6) ptx::tmem_ld_x16(s_half + 96, va);
+    SVB_H_A(vb, 5)
+    if (NCH > 6) {
+        ptx::tmem_ld_wait_dep(va);
+        SVB_H_A(va, 6)
+    }
+#undef SVB_H_A
+    float m_half = mk[0] + bh[0];
+#pragma unroll
+    for (int k = 1; k < NROWS; ++k) m_half = fmaxf(m_half, mk[k] + bh[k]);
+    *xch_mine = m_half;
+    ptx::named_bar_sync(pair_bar, 64);
+    const float m_ref = fmaxf(m_half, *xch_other);
+#pragma unroll
+    for (int k = 0; k < NROWS; ++k) bh[k] -= m_ref;
+    // ---- pass B ----
+    f32x2 l01 = f2_pack(0.f, 0.f);
+#define SVB_H_B(V, CHUNK)                                                                                \
+    if ((CHUNK) < NCH) {                                                                                 \
+        uint32_t pk[8];                                                                                  \
+        _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                              \
+            const int k0 = 16 * (CHUNK) + e, k1 = k0 + 1;                                                \
+            if (k0 < REAL) {                                                                             \
+                const f32x2 x = f2_add(f2_fma(f2_pack(__uint_as_float(V[e]), __uint_as_float(V[e + 1])), sc2,           \
+                                              f2_pack(bw[k0 % 14], bw[k1 % 14])), f2_pack(bh[k0 / 14 < NROWS ? k0 / 14 : 0], bh[k1 / 14 < NROWS ? k1 / 14 : 0])); \
+                float a0, a1;                                                                            \
+                f2_unpack(x, a0, a1);                                                                    \
+                float p0, p1;                                                                            \
+                if (poly_pair(e / 2 + 8 * ((CHUNK) & 1), POLY)) exp2_poly_pair(a0, a1, p0, p1);          \
+                else { p0 = ptx::ex2_approx(a0); p1 = ptx::ex2_approx(a1); }                             \
+                l01 = f2_add(l01, f2_pack(p0, p1));                                                      \
+                pk[e / 2] = pack_bf16x2(p0, p1);                                                         \
+            } else {                                                                                     \
+                pk[e / 2] = 0u;                   /* keys 196..207 of the padded contraction */          \
+            }                                                                                            \
+        }                                                                                                \
+        ptx::tmem_st_x8(p_half + 8 * (CHUNK), pk);                                                       \
+    }
+    ptx::tmem_ld_x16(s_half, va);
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 16, vb);
+    SVB_H_B(va, 0)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x16(s_half + 32, va);
+    SVB_H_B(vb, 1)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 48, vb);
+    SVB_H_B(va, 2)
+    ptx::tmem_ld_wait_dep(vb);
+    ptx::tmem_ld_x16(s_half + 64, va);
+    SVB_H_B(vb, 3)
+    ptx::tmem_ld_wait_dep(va);
+    ptx::tmem_ld_x16(s_half + 80, vb);
+    SVB_H_B(va, 4)
+    ptx::tmem_ld_wait_dep(vb);
+    if (NCH > 6) ptx::tmem_ld_x16(s_half + 96, va);
+    SVB_H_B(vb, 5)
+    if (NCH > 6) {
+        ptx::tmem_ld_wait_dep(va);
+        SVB_H_B(va, 6)
+    }
+#undef SVB_H_B
+    ptx::tmem_st_wait();
+    float l0, l1;
+    f2_unpack(l01, l0, l1);
+    return l0 + l1;
+}
+
+template <int HD> struct W6Cfg : WPCfg<HD> {
     using P = WPCfg<HD>;
     // barriers: RFULL, then per chain c at 1 + 10 c
     static constexpr int B_RFULL = 0, B_QF0 = 0, B_QF1 = 1, B_KF = 2, B_VF = 3, B_BIAS = 4, B_BREAD = 5, B_SFULL = 6, B_PFULL = 7, B_PVDONE = 8,
                          B_OSTAGED = 9, B_PER_CHAIN = 10, B_COUNT = 21;
     static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
     static constexpr int Q0_TX = 126 * P::ROWB, Q1_TX = 70 * P::ROWB, K_TX = 196 * P::ROWB;
+    static constexpr int TM_SPARE = 416;         // 48 columns per chain beside the two S tiles: P of keys 112..207
 };
 
-template <int HD, int POLY, bool ONEPASS>
-__global__ void __launch_bounds__(384, 1)
-attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int nwy, int nwx, int heads, int num_items, float scale_log2,
+template <int HD, int POLY>
+__global__ void __launch_bounds__(640, 1)
+attn_window_split_kernel(const __grid_constant__ WinPMaps maps, int D, int g, int nwy, int nwx, int heads, int num_items, float scale_log2,
                           int l2_ahead) {
     // g = token-grid HEIGHT (the last window row's padding decides whether query tile 1 exists); nwy x nwx windows per image
-    using C = W5Cfg<HD>;
+    using C = W6Cfg<HD>;
     constexpr int WS = 14;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,7 +205,7 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // provably warp-uniform
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 16 && lane == 0) {
         ptx::prefetch_tmap(&maps.kv);
         ptx::prefetch_tmap(&maps.q0);
         ptx::prefetch_tmap(&maps.q1);
@@ -96,10 +215,10 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
         ptx::mbar_init(&bars[C::B_RFULL], 1);
         for (int c = 0; c < 2; ++c)
             for (int s = 0; s < C::B_PER_CHAIN; ++s)
-                ptx::mbar_init(&bars[1 + C::B_PER_CHAIN * c + s], (s == C::B_BREAD || s == C::B_PFULL || s == C::B_OSTAGED) ? 128 : 1);
+                ptx::mbar_init(&bars[1 + C::B_PER_CHAIN * c + s], (s == C::B_BREAD || s == C::B_PFULL || s == C::B_OSTAGED) ? 256 : 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 10) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
+    if (warp == 18) ptx::tmem_alloc(tmem_slot, C::TM_COLS);
     // keys 196..207 of the PV contraction multiply P = 0: their V rows (never written by TMA) must be finite in both stages
     for (int st = 0; st < 2; ++st) {
         uint8_t* v = sm + st * C::STAGE + C::OFF_V;
@@ -108,18 +227,6 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
                 *reinterpret_cast<uint4*>(v + (i / 24) * C::V_ATOM + 196 * 32 + (i % 24) * 16) = make_uint4(0, 0, 0, 0);
         } else {
             for (int i = threadIdx.x; i < 96; i += blockDim.x) *reinterpret_cast<uint4*>(v + 196 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
-        }
-    }
-    // query rows the TMA never writes (126, 127 of tile 0; 70..127 of tile 1) take part in the MMAs: defined (zero) values, so that
-    // their scores cannot trip the rescale path of the one-pass softmax
-    for (int st = 0; st < 2; ++st) {
-        uint8_t* q0z = sm + st * C::STAGE;
-        uint8_t* q1z = q0z + C::QT;
-        for (int i = threadIdx.x; i < 2 * 8; i += blockDim.x) *reinterpret_cast<uint4*>(q0z + 126 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 58 * 8; i += blockDim.x) *reinterpret_cast<uint4*>(q1z + 70 * 128 + i * 16) = make_uint4(0, 0, 0, 0);
-        if (HD > 64) {
-            for (int i = threadIdx.x; i < 2 * 2; i += blockDim.x) *reinterpret_cast<uint4*>(q0z + C::Q_MAIN + 126 * 32 + i * 16) = make_uint4(0, 0, 0, 0);
-            for (int i = threadIdx.x; i < 58 * 2; i += blockDim.x) *reinterpret_cast<uint4*>(q1z + C::Q_MAIN + 70 * 32 + i * 16) = make_uint4(0, 0, 0, 0);
         }
     }
     ptx::fence_proxy_async_smem();
@@ -143,9 +250,11 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
     };
     const int stride = 2 * gridDim.x;
 
-    if (warp == 8 || warp == 9) {
+    if (warp >= 16) {
+    ptx::setmaxnreg_dec<56>();                                     // ONE instruction for the whole auxiliary warp group
+    if (warp == 16 || warp == 17) {
         // ===================== load / store thread of chain c =====================
-        const int c = warp - 8;
+        const int c = warp - 16;
         uint64_t* cb = bars + 1 + C::B_PER_CHAIN * c;
         uint8_t* q0 = sm + c * C::STAGE;
         uint8_t* q1 = q0 + C::QT;
@@ -246,11 +355,11 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                     // stores complete before the CTA exits
         }
-    } else if (warp == 10 || warp == 11) {
+    } else {
         // ===================== MMA issuer of chain c (all 32 lanes run the loop, one elected lane issues) =====================
         constexpr uint32_t id_r = ptx::make_idesc_bf16(128, 64, 0, 0);
         constexpr uint32_t id_s = ptx::make_idesc_bf16(128, 208, 0, 0);
-        const int c = warp - 10;
+        const int c = warp - 18;
         uint64_t* cb = bars + 1 + C::B_PER_CHAIN * c;
         const uint32_t s_tm = tmem + 208 * c;
         const uint32_t k = base + c * C::STAGE + C::OFF_K, v = base + c * C::STAGE + C::OFF_V;
@@ -276,51 +385,70 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
                 if (tile == 0) ptx::mbar_wait(&cb[C::B_VF], ni & 1);
                 ptx::mbar_wait(&cb[C::B_PFULL], nt & 1);             // P is in TMEM
                 ptx::tc_fence_after();
+                const uint32_t p_hi = tmem + C::TM_SPARE + 48 * c;  // P of keys 112..207 (the second half's columns)
                 if (HD > 64) {
                     constexpr uint32_t id_pv = ptx::make_idesc_bf16(128, HD, 0, 1);
                     const uint64_t dv = ptx::make_smem_desc(v, C::V_ATOM, 256, ptx::LAYOUT_SW32);
 #pragma unroll
                     for (int kq = 0; kq < 13; ++kq)                  // 16 keys = 512 B inside an atom
-                        ptx::mma_f16_ts_e(s_tm + 112, s_tm + 8 * kq, dv + 32 * kq, id_pv, kq ? 1u : 0u);
+                        ptx::mma_f16_ts_e(s_tm + 112, kq < 7 ? s_tm + 8 * kq : p_hi + 8 * (kq - 7), dv + 32 * kq, id_pv, kq ? 1u : 0u);
                 } else {
-                    issue_pv<HD>(s_tm + 112, s_tm, v, v + C::K_MAIN, 13, false);
+                    issue_pv<HD>(s_tm + 112, s_tm, v, v + C::K_MAIN, 7, false);
+                    issue_pv<HD>(s_tm + 112, p_hi, v + 7 * 2048, v + C::K_MAIN + 7 * 512, 6, true);
                 }
                 ptx::mma_commit_e(&cb[C::B_PVDONE]);
             }
             if (ntiles == 2) ++n1;
         }
+    }
     } else {
-        // ===================== softmax group of chain c: one query row per thread =====================
-        const int c = warp >> 2, w4 = warp & 3;
+        // ===================== softmax warps of chain c: one query row per PAIR of threads =====================
+        ptx::setmaxnreg_inc<104>();
+        const int c = warp >> 3, half = (warp >> 2) & 1, q4 = warp & 3;
         uint64_t* cb = bars + 1 + C::B_PER_CHAIN * c;
-        const int t = w4 * 32 + lane;                              // query row inside the tile
+        const int t = q4 * 32 + lane;                              // query row inside the tile
         const int xi = t % WS, yi0 = t / WS;                       // window coordinates in tile 0 (tile 1: row + 9; rows past the tile are discarded)
-        const uint32_t lane_off = static_cast<uint32_t>(w4 * 32) << 16;
-        const uint32_t s_tmem = tmem + lane_off + 208 * c;
-        const uint32_t o_tmem = s_tmem + 112;
+        const uint32_t lane_off = static_cast<uint32_t>(q4 * 32) << 16;
+        const uint32_t s_tmem = tmem + lane_off + 208 * c;         // S row (columns 0..207), P over its first 104, O at +112
+        // this half's S columns; its P: keys 0..111 over the first 56 S columns, keys 112..207 in the chain's 48 spare columns
+        const uint32_t s_half = s_tmem + 112 * half, p_half = half ? tmem + lane_off + C::TM_SPARE + 48 * c : s_tmem;
+        const uint32_t o_half = s_tmem + 112 + (HD / 2) * half;
+        float* xch_mine = reinterpret_cast<float*>(sm + C::OFF_XCH) + (c * 2 + half) * 128 + t;
+        float* xch_other = reinterpret_cast<float*>(sm + C::OFF_XCH) + (c * 2 + (half ^ 1)) * 128 + t;
+        const int pair_bar = 1 + 4 * c + q4;                       // the two warps that share these 32 rows
 
-        // rel-pos products of the tile whose bias MMA is the `nt`-th of this chain -> the row's 14 + 14 terms (log2 units)
-        float bhm[14], bwl[14];
+        // rel-pos products of the tile whose bias MMA is the `nt`-th of this chain -> this half's 8 / 6 h terms and the 14 w terms
+        float bh[8], bw[14];
         auto read_bias = [&](uint32_t nt, int tile) {
             ptx::mbar_wait(&cb[C::B_BIAS], nt & 1);
             ptx::tc_fence_after();
-            uint32_t v[32], v2[32];
-            float rr[27];
-            ptx::tmem_ld_x32(s_tmem, v);                           // both loads in flight: one tensor-memory round trip
-            ptx::tmem_ld_x32(s_tmem + 32, v2);
-            ptx::tmem_ld_wait_dep(v);
-            ptx::tmem_ld_wait_dep(v2);
+            uint32_t v[32];
+            float u[27];
             const int yi = yi0 + 9 * tile;
+            // the term of key row kh is products[yi + 13 - kh]: key rows 0..7 -> bh[kl] = products[yi + 6 + (7 - kl)], key rows 8..13
+            // -> bh[kl] = products[yi + (5 - kl)]
+            ptx::tmem_ld_x32(s_tmem, v);
+            ptx::tmem_ld_wait_dep(v);
 #pragma unroll
-            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v[j]) * LOG2E;
-            barrel_shift27(rr, yi < 13 ? yi : 13);
+            for (int j = 0; j < 27; ++j) u[j] = __uint_as_float(v[j]) * LOG2E;
+            const int yc = yi < 13 ? yi : 13;
+            if (half) {
+                barrel_pick<6, 4>(u, yc);
 #pragma unroll
-            for (int kq = 0; kq < 14; ++kq) bhm[kq] = rr[13 - kq];
+                for (int kl = 0; kl < 6; ++kl) bh[kl] = u[5 - kl];
+                bh[6] = bh[7] = 0.f;
+            } else {
+                barrel_pick<8, 5>(u, yc + 6);
 #pragma unroll
-            for (int j = 0; j < 27; ++j) rr[j] = __uint_as_float(v2[j]) * LOG2E;
-            barrel_shift27(rr, xi);
+                for (int kl = 0; kl < 8; ++kl) bh[kl] = u[7 - kl];
+            }
+            ptx::tmem_ld_x32(s_tmem + 32, v);
+            ptx::tmem_ld_wait_dep(v);
 #pragma unroll
-            for (int kq = 0; kq < 14; ++kq) bwl[kq] = rr[13 - kq];
+            for (int j = 0; j < 27; ++j) u[j] = __uint_as_float(v[j]) * LOG2E;
+            barrel_pick<14, 4>(u, xi);
+#pragma unroll
+            for (int kk = 0; kk < 14; ++kk) bw[kk] = u[13 - kk];
             ptx::tc_fence_before();
             ptx::mbar_arrive(&cb[C::B_BREAD]);
         };
@@ -341,57 +469,54 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
             // the next tile's Q sits in the OTHER Q buffer: a one-tile item is followed by tile 0 of the next item in THIS buffer,
             // whose reload waits for the store (waiting for its bias first would deadlock)
             const bool more = nitem < num_items, early = more && (ntile != tile);
-            if (w4 == 3 && tile == 1) {
+            if (q4 == 3 && tile == 1) {
                 // rows 96..127 of the 70-row tile 1 are all padding: keep the barrier protocol, skip the arithmetic (the rows of P
-                // and O this warp would have written are never stored)
+                // and O these warps would have written are never stored)
                 ptx::mbar_wait(&cb[C::B_SFULL], nt & 1);
                 ptx::mbar_arrive(&cb[C::B_PFULL]);
                 ptx::mbar_wait(&cb[C::B_PVDONE], nt & 1);
                 ptx::mbar_arrive(&cb[C::B_OSTAGED]);
                 if (more) read_bias(nt + 1, ntile);                // the tile after a tile 1 is a tile 0
             } else {
-                // ---- softmax over the 196 keys ----
+                // ---- softmax over this half's keys ----
                 ptx::mbar_wait(&cb[C::B_SFULL], nt & 1);
                 ptx::tc_fence_after();
-                const float lsum = ONEPASS ? window_softmax_tile_1p<POLY>(s_tmem, bhm, bwl, scale_log2)
-                                           : window_softmax_tile<POLY>(s_tmem, bhm, bwl, scale_log2);
+                const float lmine = half ? window_softmax_half<POLY, 1>(s_half, p_half, bh, bw, scale_log2, xch_mine, xch_other, pair_bar)
+                                         : window_softmax_half<POLY, 0>(s_half, p_half, bh, bw, scale_log2, xch_mine, xch_other, pair_bar);
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&cb[C::B_PFULL]);
-                // ---- O: TMEM -> normalised bf16 in registers ----
+                *xch_other = lmine;                                // the slot only the partner reads (its own maximum, consumed before the barrier inside)
+                // ---- this half's columns of O: TMEM -> normalised bf16 in registers ----
                 ptx::mbar_wait(&cb[C::B_PVDONE], nt & 1);
                 ptx::tc_fence_after();
-                const float inv = 1.0f / lsum;
-                uint32_t o[HD / 2];
+                ptx::named_bar_sync(pair_bar, 64);
+                const float inv = 1.0f / (lmine + *xch_mine);
+                uint32_t o[HD / 4];
                 {
                     uint32_t v[32];
+                    ptx::tmem_ld_x32(o_half, v);
+                    ptx::tmem_ld_wait_dep(v);
 #pragma unroll
-                    for (int cc = 0; cc < 64; cc += 32) {
-                        ptx::tmem_ld_x32(o_tmem + cc, v);
-                        ptx::tmem_ld_wait_dep(v);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[cc / 2 + j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
-                    }
+                    for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
                     if (HD > 64) {
-                        uint32_t w[16];
-                        ptx::tmem_ld_x16(o_tmem + 64, w);
+                        uint32_t w[8];
+                        ptx::tmem_ld_x8(o_half + 32, w);
                         ptx::tmem_ld_wait_dep(w);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[32 + j] = pack_bf16x2(__uint_as_float(w[2 * j]) * inv, __uint_as_float(w[2 * j + 1]) * inv);
+                        for (int j = 0; j < 4; ++j) o[16 + j] = pack_bf16x2(__uint_as_float(w[2 * j]) * inv, __uint_as_float(w[2 * j + 1]) * inv);
                     }
                 }
-                const bool next_dead = w4 == 3 && ntile == 1;
+                const bool next_dead = q4 == 3 && ntile == 1;
                 if (early) { if (next_dead) skip_bias(nt + 1); else read_bias(nt + 1, ntile); }
                 // ---- O -> the dead Q buffer of this tile in the TMA layout -> one tensor store per tile ----
                 {
                     uint8_t* ob = sm + c * C::STAGE + tile * C::QT;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)                    // 128B swizzle: 16-byte piece j of row t at piece j ^ (t & 7)
-                        *reinterpret_cast<uint4*>(ob + t * 128 + ((j ^ (t & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    if (HD > 64) {
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)                // 32B swizzle: piece j of row t at piece j ^ ((t >> 2) & 1)
-                            *reinterpret_cast<uint4*>(ob + C::Q_MAIN + t * 32 + ((j ^ ((t >> 2) & 1)) << 4)) =
-                                make_uint4(o[32 + 4 * j], o[32 + 4 * j + 1], o[32 + 4 * j + 2], o[32 + 4 * j + 3]);
+                    for (int j = 0; j < HD / 16; ++j) {            // this half's 16-byte pieces: global piece g of the row
+                        const int g8 = (HD / 16) * half + j;
+                        const uint4 val = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        if (g8 < 8) *reinterpret_cast<uint4*>(ob + t * 128 + ((g8 ^ (t & 7)) << 4)) = val;          // 128B swizzle
+                        else *reinterpret_cast<uint4*>(ob + C::Q_MAIN + t * 32 + (((g8 - 8) ^ ((t >> 2) & 1)) << 4)) = val;   // 32B swizzle (tail)
                     }
                     ptx::fence_proxy_async_smem();                 // generic writes -> visible to the TMA (async proxy) read
                     ptx::mbar_arrive(&cb[C::B_OSTAGED]);           // the chain's load / store thread issues the tensor store and refills the buffer
@@ -406,18 +531,17 @@ attn_window_chains_kernel(const __grid_constant__ WinPMaps maps, int D, int g, i
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 10) {
+    if (warp == 18) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem, C::TM_COLS);
     }
 }
 
-
 }  // namespace
 
 // same contract as attention_tc() for ws = 14
-int attention_window5(const AttnTcParams& p, cudaStream_t stream) {
-    SVB_REQUIRE(p.hd == 64 || p.hd == 80, "attention_window5: head_dim %d", p.hd);
+int attention_window6(const AttnTcParams& p, cudaStream_t stream) {
+    SVB_REQUIRE(p.hd == 64 || p.hd == 80, "attention_window6: head_dim %d", p.hd);
     auto run = [&](auto hd_tag) -> int {
         constexpr int HD = decltype(hd_tag)::value;
         using C = WPCfg<HD>;
@@ -457,12 +581,10 @@ int attention_window5(const AttnTcParams& p, cudaStream_t stream) {
         static const int poly = [] { const char* e = getenv("SVB_ATTNW_POLY"); return e ? atoi(e) : 2; }();
         auto launch = [&](auto kern) -> int {
             SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-            kern<<<grid, 384, C::SMEM, stream>>>(wm, D, gh, nwy, nwx, p.heads, items, scale_log2, l2_ahead);
+            kern<<<grid, 640, C::SMEM, stream>>>(wm, D, gh, nwy, nwx, p.heads, items, scale_log2, l2_ahead);
             return 0;
         };
-        static const int onepass = [] { const char* e = getenv("SVB_ATTNW_ONEPASS"); return e ? atoi(e) : 1; }();
-        if (onepass) rc = poly ? launch(attn_window_chains_kernel<HD, 2, true>) : launch(attn_window_chains_kernel<HD, 0, true>);
-        else rc = poly ? launch(attn_window_chains_kernel<HD, 2, false>) : launch(attn_window_chains_kernel<HD, 0, false>);
+        rc = poly == 0 ? launch(attn_window_split_kernel<HD, 0>) : poly == 4 ? launch(attn_window_split_kernel<HD, 4>) : launch(attn_window_split_kernel<HD, 2>);
         if (rc) return rc;
         SVB_CHECK_CUDA(cudaGetLastError());
         return 0;

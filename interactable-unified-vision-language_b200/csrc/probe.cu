@@ -201,6 +201,61 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(int reps, int alt_d,
     __syncthreads();
     if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
 }
+
+// TMEM load / store rate microbenchmark (svb_probe_tmem_rate): `nwarps` warps (warp w works on lane quadrant w % 4) each issue `reps`
+// tcgen05.ld (mode 0 / 1: one / two in flight per warp) or tcgen05.st (mode 2) of 32 lanes x 32 columns x 4 bytes back to back;
+// out[w] = cycles of warp w.  Bytes per clock and SM = nwarps * reps * 4096 / max_w out[w].
+__global__ void __launch_bounds__(512, 1) probe_tmem_rate_kernel(int nwarps, int reps, int mode, long long* out) {
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) ptx::tmem_alloc(&slot, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = slot;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    if (warp < 4) {
+        uint32_t z[16];
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c0 = 0; c0 < 512; c0 += 16) ptx::tmem_st_x16(lane_base + c0, z);
+        ptx::tmem_st_wait();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp < nwarps) {
+        uint32_t acc = 0;
+        uint32_t va[32], vb[32];
+        for (int j = 0; j < 32; ++j) { va[j] = j; vb[j] = 2 * j; }
+        const long long t0 = clock64();
+        if (mode == 0) {
+            for (int r = 0; r < reps; ++r) {
+                ptx::tmem_ld_x32(lane_base + ((r * 32) & 255), va);
+                ptx::tmem_ld_wait_dep(va);
+                acc ^= va[r & 31];
+            }
+        } else if (mode == 1) {
+            for (int r = 0; r < reps; r += 2) {
+                ptx::tmem_ld_x32(lane_base + ((r * 32) & 255), va);
+                ptx::tmem_ld_x32(lane_base + 256 + ((r * 32) & 223), vb);
+                ptx::tmem_ld_wait_dep(va);
+                ptx::tmem_ld_wait_dep(vb);
+                acc ^= va[r & 31] ^ vb[r & 31];
+            }
+        } else {
+            for (int r = 0; r < reps; ++r) {
+                va[0] = r;
+                ptx::tmem_st_x32(lane_base + ((warp >> 2) * 128 + (r * 32)) % 480, va);
+            }
+            ptx::tmem_st_wait();
+        }
+        const long long t1 = clock64();
+        if ((tid & 31) == 0) out[warp] = (t1 - t0) + (acc == 0x12345678u ? 1 : 0);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
 }  // namespace
 }  // namespace svb
 
@@ -250,6 +305,13 @@ extern "C" int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* c
                         probe_rate_kernel<V><<<1, 128, smem, (cudaStream_t)stream>>>(reps, alt_d, cycles_out); break;
     switch (variant) { SVB_RATE(0) SVB_RATE(1) SVB_RATE(2) SVB_RATE(3) SVB_RATE(4) SVB_RATE(5) SVB_RATE(6) SVB_RATE(7) SVB_RATE(8) SVB_RATE(9) SVB_RATE(10) }
 #undef SVB_RATE
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svb_probe_tmem_rate(int nwarps, int reps, int mode, long long* cycles_out, svb_stream_t stream) {
+    SVB_REQUIRE(cycles_out && nwarps >= 1 && nwarps <= 16 && reps > 0 && reps % 2 == 0 && mode >= 0 && mode <= 2, "probe_tmem_rate: bad argument");
+    probe_tmem_rate_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(nwarps, reps, mode, cycles_out);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,21 @@
+#!/bin/bash
+# GPU call 18: split-row windowed kernel (SVB_ATTNW_IMPL=6: four softmax warps per scheduler): parity, kernel-alone and in-step timing
+mkdir -p gpurun_out
+T="tests/test_gpu_ops.py -m gpu -x -q -k"
+SVB_ATTNW_IMPL=6 timeout 600 python -m pytest $T "test_attention_tcgen05 and not variants" > gpurun_out/c18_pytest.log 2>&1
+rc=$?; echo "impl 6: pytest exit $rc"; tail -15 gpurun_out/c18_pytest.log | cut -c1-300
+if [ $rc -ne 0 ]; then exit 1; fi
+for rep in 1 2; do
+  for impl in 2 6; do SVB_ATTNW_IMPL=$impl timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'; done
+  SVB_ATTNW_IMPL=6 SVB_ATTNW_POLY=0 timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'
+  SVB_ATTNW_IMPL=6 SVB_ATTNW_POLY=4 timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'
+  SVB_ATTNW_IMPL=6 SVB_ATTNW_L2AHEAD=3841 timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'
+  for impl in 2 6; do B=12 SVB_ATTNW_IMPL=$impl timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'; done
+  for impl in 2 6; do HD=64 HEADS=12 SVB_ATTNW_IMPL=$impl timeout 300 python tools/attn_bench.py 2>&1 | tail -1 | sed 's/, global.*//'; done
+done | tee gpurun_out/c18_attn_ab.txt
+if [ $rc -eq 0 ]; then
+for impl in 2 6 2 6; do
+  SVB_ATTNW_IMPL=$impl timeout 600 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-e2e > gpurun_out/c18_bench_$impl.json 2> gpurun_out/c18_bench_$impl.err; echo "bench impl $impl exit $?"
+  python tools/summarize_bench.py gpurun_out/c18_bench_$impl.json | cut -c1-420
+done
+fi
