@@ -180,7 +180,7 @@ xattn_partial_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
             float cmax = -INFINITY;
             uint4 mb = make_uint4(0, 0, 0, 0);
             if (mrow) {
-                if (((c0 + k16) & 15) == 0 && (HW & 15) == 0) mb = *reinterpret_cast<const uint4*>(mrow + c0 + k16);   // 16 mask bytes at once
+                if ((reinterpret_cast<uintptr_t>(mrow + c0 + k16) & 15) == 0 && k16 + 16 <= nk) mb = *reinterpret_cast<const uint4*>(mrow + c0 + k16);   // 16 mask bytes at once (an aligned address, whatever the view's storage offset)
                 else {
                     uint8_t tmpb[16];
 #pragma unroll
