@@ -7,13 +7,19 @@
 // with grid_sample(align_corners=False, padding_mode='zeros') semantics (ops/functions/ms_deform_attn_func.py:52-72).
 //
 // B200 design: the op is a gather out of `value` (22 MB per 1024^2 image in bf16 at the step1.yaml geometry: 3 levels, 8 heads x 64
-// channels — L2-resident) — bound by L2 -> SM bandwidth, not by math.  One thread owns 16 BYTES of channels (8 bf16 / 4 fp32) of
-// one (n, q, head): the 4 taps of a sample are four 16-byte loads, consecutive threads cover consecutive channels (a 64-channel
-// head = 8 lanes = one 128-byte line per tap), the sampling location / weight loads are warp-broadcast, accumulation is fp32, and
-// bf16 values halve the gather traffic of the reference's fp32-only kernel (which forces the caller to up-cast all levels,
-// transformer_encoder_deform.py:314-345).
+// channels — L2-resident).  One thread owns 16 BYTES of channels (8 bf16 / 4 fp32) of one (n, q, head): the 4 taps of a sample are
+// four 16-byte loads, consecutive threads cover consecutive channels (a 64-channel head = 8 lanes = one 128-byte line per tap),
+// accumulation is fp32, and bf16 values halve the gather traffic of the reference's fp32-only kernel (which forces the caller to
+// up-cast all levels, transformer_encoder_deform.py:314-345).  ncu showed the first form of the kernel bound by INSTRUCTIONS, not by
+// the gather (issue slots 70 % busy, L1 29 %, L2 19 %, L1 / L2 hit rates 49 / 79 %): every lane of a unit repeated the softmax, the
+// sampling-location and the bilinear-weight arithmetic for itself.  msda_fused_shared_kernel shares it (each lane prepares its share
+// of the unit's points into shared memory; the accumulation loop reads a point as two 16-byte broadcasts): 0.85 -> 0.53 ms per
+// MSDeformAttn layer and 10.6-11.2 -> 9.1 ms per pixel-decoder forward for 4 images; the one-lane-does-all kernels remain for head
+// widths that are not a power-of-two number of 16-byte groups.
 #include "../../include/samvit_b200.h"
 #include "common.cuh"
+
+#include <cstdlib>
 
 namespace svb {
 namespace {
@@ -187,6 +193,110 @@ msda_fused_kernel(const T* __restrict__ value, const float* __restrict__ raw, co
     }
 }
 
+// The fused kernel with the per-(query, head) arithmetic SHARED by the unit's lanes.  Measured on msda_fused_kernel (ncu, step1.yaml
+// geometry, profiles/r02_final2/ncu_full_heads.csv): issue slots 70 % busy, L1 29 %, L2 19 % — the gather was bound by instructions,
+// and half of them were the softmax / sampling-location / bilinear-weight arithmetic that each of the 8 (bf16) or 16 (fp32) lanes
+// of a unit repeated for itself.  Here lane c of a unit prepares points c, c + G, ... (weights incl. the un-normalised softmax weight
+// and the four element offsets of the taps) into shared memory, the maximum / denominator of the softmax are reduced with shuffles
+// inside the unit, and the accumulation loop reads a point as two 16-byte broadcasts.  G = lanes per unit (a power of two <= 32).
+// FUSED = false: the plain sampling core (svb_ms_deform_attn_forward) — `raw` = sampling_locations [N, Lq, M, L, P, 2], `ref` =
+// attention_weights [N, Lq, M, L, P] (already normalised), ref_dim unused.
+template <typename T, bool FUSED>
+__global__ void __launch_bounds__(256)
+msda_fused_shared_kernel(const T* __restrict__ value, const float* __restrict__ raw, const float* __restrict__ ref, T* __restrict__ out,
+                         const __grid_constant__ MsdaLevels lv, long total, int S, int M, int D, int L, int Q, int np, int ref_dim) {
+    constexpr int V = Pack16<T>::N;
+    extern __shared__ uint4 msda_pts[];                            // [units per block][LP][2]: (w1..w4), (o1..o4)
+    const int G = D / V;
+    const int LP = L * np, MLP = M * LP;
+    const int lane = threadIdx.x & 31;
+    const int cg = lane & (G - 1);
+    uint4* mine = msda_pts + (size_t)(threadIdx.x / G) * LP * 2;
+    const size_t head_stride = (size_t)M * D;
+    const long first = blockIdx.x * (long)blockDim.x + (threadIdx.x & ~31);          // the warp's first index: uniform loop bounds
+    for (long wbase = first; wbase < total; wbase += (long)gridDim.x * blockDim.x) {
+        const long idx = wbase + lane;
+        const bool valid = idx < total;                            // whole units are valid or not (total is a multiple of G)
+        const long unit = valid ? idx / G : 0;
+        const int m = (int)(unit % M);
+        const long nq = unit / M;                                  // n * Q + q
+        const int n = (int)(nq / Q);
+        const float* row = FUSED ? raw + nq * (size_t)(3 * MLP) : raw + (size_t)unit * LP * 2;
+        const float2* offp = reinterpret_cast<const float2*>(FUSED ? row + (size_t)m * LP * 2 : row);
+        const float* logp = FUSED ? row + 2 * (size_t)MLP + (size_t)m * LP : ref + (size_t)unit * LP;
+        const float* rp = ref + nq * (size_t)(L * ref_dim);
+        // ---- this lane's points: j = cg, cg + G, ... ----
+        float mx = -INFINITY;
+        if (FUSED) {
+            for (int j = cg; j < LP; j += G) mx = fmaxf(mx, __ldg(logp + j));
+            for (int o = 1; o < G; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        float den = 0.f;
+        for (int j = cg; j < LP; j += G) {
+            const int l = j / np;
+            const int H = lv.h[l], W = lv.w[l];
+            const float2 off = __ldg(offp + j);
+            const float wt = FUSED ? __expf(__ldg(logp + j) - mx) : __ldg(logp + j);
+            den += wt;
+            float loc_x = off.x, loc_y = off.y;                   // the sampling location itself when it is materialised
+            if (FUSED) {
+                const float rx = __ldg(rp + l * ref_dim), ry = __ldg(rp + l * ref_dim + 1);
+                loc_x = ref_dim == 2 ? rx + off.x / (float)W : rx + off.x / (float)np * __ldg(rp + l * ref_dim + 2) * 0.5f;
+                loc_y = ref_dim == 2 ? ry + off.y / (float)H : ry + off.y / (float)np * __ldg(rp + l * ref_dim + 3) * 0.5f;
+            }
+            const float h_im = loc_y * H - 0.5f, w_im = loc_x * W - 0.5f;
+            const bool inside = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;
+            const float hf = floorf(h_im), wf = floorf(w_im);
+            const int h_low = (int)hf, w_low = (int)wf;
+            const int h_high = h_low + 1, w_high = w_low + 1;
+            const float lh = h_im - hf, lw = w_im - wf, hh = 1.f - lh, hw = 1.f - lw;
+            const bool hl = inside && h_low >= 0, hhi = inside && h_high <= H - 1;
+            const bool wl = w_low >= 0, whi = w_high <= W - 1;
+            float4 w4;
+            w4.x = (hl && wl) ? hh * hw * wt : 0.f; w4.y = (hl && whi) ? hh * lw * wt : 0.f;
+            w4.z = (hhi && wl) ? lh * hw * wt : 0.f; w4.w = (hhi && whi) ? lh * lw * wt : 0.f;
+            const int y0 = min(max(h_low, 0), H - 1), y1 = min(max(h_high, 0), H - 1);
+            const int x0 = min(max(w_low, 0), W - 1), x1 = min(max(w_high, 0), W - 1);
+            const uint32_t hs = (uint32_t)head_stride, st = (uint32_t)lv.start[l];
+            uint4 o4;                                              // element offsets of the four taps inside this sample's value map
+            o4.x = (st + (uint32_t)(y0 * W + x0)) * hs; o4.y = (st + (uint32_t)(y0 * W + x1)) * hs;
+            o4.z = (st + (uint32_t)(y1 * W + x0)) * hs; o4.w = (st + (uint32_t)(y1 * W + x1)) * hs;
+            if (valid) {
+                mine[2 * j] = make_uint4(__float_as_uint(w4.x), __float_as_uint(w4.y), __float_as_uint(w4.z), __float_as_uint(w4.w));
+                mine[2 * j + 1] = o4;
+            }
+        }
+        if (FUSED) for (int o = 1; o < G; o <<= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+        __syncwarp();
+        // ---- the gather: every lane its 16 bytes of channels ----
+        const T* vb = value + (size_t)n * S * head_stride + (size_t)m * D + (size_t)cg * V;
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        if (valid) {
+#pragma unroll 4
+            for (int j = 0; j < LP; ++j) {
+                const uint4 wq = mine[2 * j], oq = mine[2 * j + 1];
+                float t1[V], t2[V], t3[V], t4[V];
+                Pack16<T>::load(vb + oq.x, t1);
+                Pack16<T>::load(vb + oq.y, t2);
+                Pack16<T>::load(vb + oq.z, t3);
+                Pack16<T>::load(vb + oq.w, t4);
+                const float w1 = __uint_as_float(wq.x), w2 = __uint_as_float(wq.y), w3 = __uint_as_float(wq.z), w4 = __uint_as_float(wq.w);
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[i] = fmaf(w1, t1[i], fmaf(w2, t2[i], fmaf(w3, t3[i], fmaf(w4, t4[i], acc[i]))));
+            }
+            if (FUSED) {
+                const float inv_den = 1.f / den;
+#pragma unroll
+                for (int i = 0; i < V; ++i) acc[i] *= inv_den;
+            }
+            Pack16<T>::store(out + unit * D + (size_t)cg * V, acc);
+        }
+        __syncwarp();                                              // the unit's points are rewritten in the next round
+    }
+}
+
 int msda_levels(MsdaLevels& lv, const int32_t* spatial_shapes, const int32_t* level_start_index, int num_levels, int spatial_size,
                 const char* who) {
     SVB_REQUIRE(num_levels >= 1 && num_levels <= MSDA_MAX_LEVELS, "%s: %d levels (1..%d supported)", who, num_levels, MSDA_MAX_LEVELS);
@@ -236,7 +346,21 @@ extern "C" int svb_ms_deform_attn_forward(const void* value, const int32_t* spat
     msda_forward_kernel<TT, PT><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT*)value, sampling_locations, attention_weights, (TT*)out, \
                                                                            lv, total, spatial_size, num_heads, channels, num_levels,        \
                                                                            num_query, num_points)
-    if (dtype == SVB_DTYPE_BF16) {
+    const int G = channels / vec, LP = num_levels * num_points;
+    static const int shared_on = [] { const char* e = getenv("SVB_MSDA_SHARED"); return e ? atoi(e) : 1; }();
+    const bool can_share = shared_on && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && (size_t)(256 / G) * LP * 2 * sizeof(uint4) <= 48 * 1024 &&
+                           (double)spatial_size * num_heads * channels < 4.0e9 && (reinterpret_cast<uintptr_t>(sampling_locations) & 7) == 0;
+    if (can_share) {
+        const size_t smem = (size_t)(256 / G) * LP * 2 * sizeof(uint4);
+        if (dtype == SVB_DTYPE_BF16)
+            msda_fused_shared_kernel<bf16, false><<<blocks, 256, smem, (cudaStream_t)stream>>>((const bf16*)value, sampling_locations, attention_weights,
+                                                                                           (bf16*)out, lv, total, spatial_size, num_heads, channels,
+                                                                                           num_levels, num_query, num_points, 2);
+        else
+            msda_fused_shared_kernel<float, false><<<blocks, 256, smem, (cudaStream_t)stream>>>((const float*)value, sampling_locations,
+                                                                                            attention_weights, (float*)out, lv, total, spatial_size,
+                                                                                            num_heads, channels, num_levels, num_query, num_points, 2);
+    } else if (dtype == SVB_DTYPE_BF16) {
         if (num_points == 4) SVB_MSDA(bf16, 4);
         else SVB_MSDA(bf16, 0);
     } else {
@@ -279,7 +403,23 @@ extern "C" int svb_ms_deform_attn_fused_forward(const void* value, const int32_t
     msda_fused_kernel<TT, PT><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT*)value, offsets_and_logits, reference_points, (TT*)out, lv, \
                                                                          total, spatial_size, num_heads, channels, num_levels, num_query,  \
                                                                          num_points, ref_dim)
-    if (dtype == SVB_DTYPE_BF16) { if (num_points == 4) SVB_FUSED(bf16, 4); else SVB_FUSED(bf16, 0); }
+    // lanes of a unit share the point arithmetic when they sit inside one warp (channel groups per head a power of two <= 32) and a
+    // sample's value map is addressable with 32-bit element offsets; SVB_MSDA_SHARED=0 keeps the one-lane-does-all kernel for A/B
+    const int G = channels / vec, LP = num_levels * num_points;
+    static const int shared_on = [] { const char* e = getenv("SVB_MSDA_SHARED"); return e ? atoi(e) : 1; }();
+    const bool can_share = shared_on && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && (size_t)(256 / G) * LP * 2 * sizeof(uint4) <= 48 * 1024 &&
+                           (double)spatial_size * num_heads * channels < 4.0e9;
+    if (can_share) {
+        const size_t smem = (size_t)(256 / G) * LP * 2 * sizeof(uint4);
+        if (dtype == SVB_DTYPE_BF16)
+            msda_fused_shared_kernel<bf16, true><<<blocks, 256, smem, (cudaStream_t)stream>>>((const bf16*)value, offsets_and_logits, reference_points, (bf16*)out,
+                                                                                        lv, total, spatial_size, num_heads, channels, num_levels,
+                                                                                        num_query, num_points, ref_dim);
+        else
+            msda_fused_shared_kernel<float, true><<<blocks, 256, smem, (cudaStream_t)stream>>>((const float*)value, offsets_and_logits, reference_points,
+                                                                                         (float*)out, lv, total, spatial_size, num_heads, channels,
+                                                                                         num_levels, num_query, num_points, ref_dim);
+    } else if (dtype == SVB_DTYPE_BF16) { if (num_points == 4) SVB_FUSED(bf16, 4); else SVB_FUSED(bf16, 0); }
     else { if (num_points == 4) SVB_FUSED(float, 4); else SVB_FUSED(float, 0); }
 #undef SVB_FUSED
     SVB_CHECK_CUDA(cudaGetLastError());

@@ -175,3 +175,17 @@ def test_deform_encoder_layer_matches_composition_of_ops():
             y = layer.norm1(src + a)
             want = layer.norm2(y + layer.linear2(torch.relu(layer.linear1(y))))
             assert ib.rel_l2(out, want) < 1e-4, ib.rel_l2(out, want)
+
+
+def test_msda_one_lane_kernel_stays_correct():
+    """The fused kernel's predecessor (every lane of a unit computes the softmax / locations / bilinear weights for itself: the path of
+    head widths that are not a power-of-two number of 16-byte groups, and SVB_MSDA_SHARED=0 for A/B runs) passes the same module tests
+    as the shared-arithmetic kernel; the variable is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, SVB_MSDA_SHARED="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_msda.py", "-q", "-x", "-k", "(module or against_reference or against_oracle) and not one_lane"],
+                       cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-500:])
