@@ -119,8 +119,20 @@ __global__ void stage_u8_kernel(U8Batch bt, T* __restrict__ out, int B, int C, i
             for (int j = 0; j < VEC; ++j)
                 if (x + j < w) v[j] = tab[px8[j]];
         }
+        if constexpr (sizeof(T) == 2 && VEC == 16) {
+            // 32 bytes per thread as two 16-byte stores (four 8-byte stores made every warp store touch each 32-byte sector
+            // four times); streaming: the rows are read next by the patch-embedding GEMM's TMA, not by this SM
 #pragma unroll
-        for (int j = 0; j < VEC; j += 4) Vec4<T>::store(out + e + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < VEC; j += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(out + e + j) = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4) Vec4<T>::store(out + e + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
     }
 }
 

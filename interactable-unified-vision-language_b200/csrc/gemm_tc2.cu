@@ -741,30 +741,36 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t hswz = (lane >> 1) & 3;
             uint32_t rph = 0;                                 // parity bits of the two residual barriers
             const int parts = (N + 127) / 128;
+            // column offset (inside the tile) of this warp's chunk c.  Default: the warp owns one 128-column half.  Interleaved
+            // (SVB_GEMM2_DBG & 64, A/B): the two warps of a lane quadrant take alternate 32-column chunks, so that the boxes they
+            // fetch / store at the same time are 256 contiguous bytes of the fp32 rows (128 of the bf16 copy) instead of 128 (64)
+            const bool ilv = (dbg & 64) != 0 && (N % BN) == 0;     // (whole tiles only: the row-sum slots are per 128-column half)
+            const uint32_t cstep = ilv ? 64u : 32u, cbase = ilv ? half * 32u : half * (BN / 2);
+            const uint32_t tmem_q = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
             for (int t = pair; t < num_tiles; t += num_pairs) {
                 const int m0 = ((t / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA;
                 const int nt0 = (t % num_n) * BN;
-                const int n0 = nt0 + half * (BN / 2);
+                const int n0 = nt0 + (int)cbase;                // first column of this warp's first chunk
                 const int r0 = m0 + quad * 32;
                 const bool slab = (r0 < M) && (n0 < N) && !(dbg & 8);
-                const int nch = slab ? min(NCH, (N - n0 + 31) / 32) : 0;      // chunks of this slab (N % 32 == 0)
+                const int nch = slab ? min(NCH, (N - n0 + (int)cstep - 1) / (int)cstep) : 0;      // chunks of this slab (N % 32 == 0)
                 // ---- while this tile's MMAs run: fetch the residual boxes of the first two chunks, stage the bias ----
                 if (lane == 0) {
                     if (nch > 0) {
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // last tile's stores have left the boxes
                         for (int c = 0; c < C::NBOX && c < nch; ++c) {
                             ptx::mbar_expect_tx(&mybar[c], C::CHUNK_BYTES);
-                            ptx::tma_load_2d(stg_g + c * C::CHUNK_BYTES, &map_o, &mybar[c], n0 + 32 * c, r0);
+                            ptx::tma_load_2d(stg_g + c * C::CHUNK_BYTES, &map_o, &mybar[c], n0 + (int)cstep * c, r0);
                         }
                     }
                     if (dbg & 16) {                           // experiment: L2 prefetch of the later chunks / the next tile's rows
-                        for (int c = 2; c < nch; ++c) tma_prefetch_l2_2d(&map_o, n0 + 32 * c, r0);
+                        for (int c = 2; c < nch; ++c) tma_prefetch_l2_2d(&map_o, n0 + (int)cstep * c, r0);
                         const int tn = t + num_pairs;
                         if (tn < num_tiles) {
                             const int rn = ((tn / num_n) * PAIRS + pidx) * (2 * BM_CTA) + rank * BM_CTA + quad * 32;
-                            const int nn = (tn % num_n) * BN + half * (BN / 2);
+                            const int nn = (tn % num_n) * BN + (int)cbase;
                             if (rn < M)
-                                for (int c = 0; c < NCH && nn + 32 * c < N; ++c) tma_prefetch_l2_2d(&map_o, nn + 32 * c, rn);
+                                for (int c = 0; c < NCH && nn + (int)cstep * c < N; ++c) tma_prefetch_l2_2d(&map_o, nn + (int)cstep * c, rn);
                         }
                     }
                 }
@@ -785,10 +791,10 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
                 const f32x2 nc2 = f2_pack(-cshift, -cshift);
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-                const uint32_t bsm = ptx::smem_u32(bs + half * (BN / 2));
+                const uint32_t bsm = ptx::smem_u32(bs) + cbase * 4;
                 ptx::mbar_wait(&tmem_full[as], aphase);
                 ptx::tc_fence_after();
-                const uint32_t taddr = tmem_lane + as * BN;
+                const uint32_t taddr = tmem_q + as * BN + cbase;
                 f32x2 st_s = f2_pack(0.f, 0.f), st_q = st_s;  // this thread's row: sum / sum of squares (two interleaved lanes)
                 uint32_t ra[32], rb[32];
                 bool released = false;
@@ -796,11 +802,11 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     if (c >= nch) break;
-                    const int col0 = n0 + c * 32;
+                    const int col0 = n0 + c * (int)cstep;
                     uint32_t (&raw)[32] = *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? rb : ra);
                     ptx::tmem_ld_wait_dep(raw);
                     if (c + 1 < nch) {
-                        ptx::tmem_ld_x32(taddr + (c + 1) * 32, *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? ra : rb));
+                        ptx::tmem_ld_x32(taddr + (c + 1) * cstep, *reinterpret_cast<uint32_t (*)[32]>((c & 1) ? ra : rb));
                     } else {
                         ptx::tc_fence_before();
                         __syncwarp();
@@ -814,7 +820,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     f32x2 v[16];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 bb = lds128(bsm + c * 128 + 16 * j);
+                        const float4 bb = lds128(bsm + c * (cstep * 4) + 16 * j);
                         const float4 rr = lds128(rowa + ((j ^ swz) << 4));
                         f32x2 x0 = f2_pack(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]));
                         f32x2 x1 = f2_pack(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
@@ -848,7 +854,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (c + C::NBOX < nch) {              // refill this box with the residual of chunk c + NBOX
                             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                             ptx::mbar_expect_tx(&mybar[b], C::CHUNK_BYTES);
-                            ptx::tma_load_2d(stg_g + b * C::CHUNK_BYTES, &map_o, &mybar[b], col0 + 32 * C::NBOX, r0);
+                            ptx::tma_load_2d(stg_g + b * C::CHUNK_BYTES, &map_o, &mybar[b], col0 + (int)cstep * C::NBOX, r0);
                         }
                     }
                 }
@@ -861,7 +867,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     float s0, s1, q0, q1;
                     f2_unpack(st_s, s0, s1);
                     f2_unpack(st_q, q0, q1);
-                    ep.stat_out[(size_t)(r0 + lane) * parts + n0 / 128] = make_float2(s0 + s1, q0 + q1);
+                    ep.stat_out[(size_t)(r0 + lane) * parts + nt0 / 128 + half] = make_float2(s0 + s1, q0 + q1);
                 }
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }

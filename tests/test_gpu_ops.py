@@ -1,5 +1,6 @@
 """GPU parity of the single operators, called through the C ABI, against fp64 references / the oracle's pieces."""
 import math
+import os
 
 import pytest
 import torch
@@ -128,7 +129,12 @@ def test_gemm_layernorm_fold(M, D, Kp):
     pad = parts * 128 - D
     xs = torch.nn.functional.pad(x.double(), (0, pad)).reshape(M, parts, 128)
     s_ref = torch.stack([xs.sum(-1), (xs ** 2).sum(-1)], -1)
-    assert torch.allclose(stat.double(), s_ref, rtol=2e-5, atol=1e-3), (stat[0], s_ref[0])
+    # (SVB_GEMM2_DBG & 64, an A/B variant, hands the two 128-column slots of a 256-column tile to interleaved chunks: the consumer
+    # only ever sums the slots, so there the check is on the sums per tile)
+    if int(os.environ.get("SVB_GEMM2_DBG", "0")) & 64 and D % 256 == 0:
+        assert torch.allclose(stat.double().reshape(M, parts // 2, 2, 2).sum(2), s_ref.reshape(M, parts // 2, 2, 2).sum(2), rtol=2e-5, atol=1e-3)
+    else:
+        assert torch.allclose(stat.double(), s_ref, rtol=2e-5, atol=1e-3), (stat[0], s_ref[0])
     # ---- consumer: y = gelu(LayerNorm(x) W^T + b) ----
     N = 3 * D
     W = (torch.randn(N, D, generator=g) / math.sqrt(D)).to(DEV)

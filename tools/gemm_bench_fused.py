@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Interleaved A/B timing of the GEMM epilogue variants (svb_linear_fused), ViT-H shapes, 8 images.  The variants are run
+"""Interleaved A/B timing of the GEMM epilogue variants (svb_linear_fused), ViT-H shapes, 8 images (SVB_BENCH_IMAGES=n: n images).  The variants are run
 round-robin (R rounds of `reps` launches each) so that every one sees the same clock / power state of the capped GPU."""
 import math
 import os
@@ -12,7 +12,7 @@ from iuvl_b200 import cabi  # noqa: E402
 
 dev = "cuda"
 lib = cabi.lib()
-D, M = 1280, 8 * 4096
+D, M = 1280, int(os.environ.get("SVB_BENCH_IMAGES", "8")) * 4096
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 only = sys.argv[3] if len(sys.argv) > 3 else ""
