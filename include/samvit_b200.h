@@ -116,6 +116,13 @@ int svb_encoder_read_tap(svb_encoder_t* enc, int block, float* dst, int64_t nume
 int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, double* gn_stats,
                int rows_per_sample, int remap_grid, int remap_grid_pad, svb_stream_t stream);
+/* out_t[n * ldo + m] = sum_k A[m, k] W[n, k] + bias[n]: svb_linear (bf16 operands, fp32 accumulate) with the fp32 result stored
+ * TRANSPOSED.  For products with few W rows and many A rows — the mask logits `torch.einsum("bqc,bchw->bqhw", mask_embed,
+ * mask_features)` of XDecoder.forward_prediction_heads (modeling/interface/xdecoder.py:459): A = the image's mask-feature rows
+ * (h*w, c), W = its 101 mask embeddings (q, c), out_t = outputs_mask[b] (q, h*w) — the long dimension runs along the GEMM's M, so
+ * no tile rows are spent on padding the 101 queries to 256.  tcgen05 path only (M % 4 == 0, ldo % 8 == 0, 16-byte aligned operands). */
+int svb_linear_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, float* out_t, int ldo,
+                  svb_stream_t stream);
 /* The same GEMM with the LayerNorm-folding epilogues of the bf16 path: norm1 / norm2
  * (image_encoder.py:183,195) never run as separate passes.
  *   producer side (fp32 `out` + `resid` required): `out_bf16_copy` (bf16 [M, ldo2]) receives a rounded copy of the final rows and
@@ -246,6 +253,12 @@ int svb_im2col3x3_rows(const float* src, void* dst, int dst_dtype, int batch, in
  * (batch, h, w, cout) = [relu](conv + bias).  w must be a multiple of 128, cin of 64, cout of 32. */
 int svb_conv3x3_rows(const float* src, const void* weight_bf16, const float* bias, float* out, void* padded_ws, int batch, int h, int w,
                      int cin, int cout, int relu, svb_stream_t stream);
+/* Post-norm LayerNorm of the deformable encoder layer in one pass (transformer_encoder_deform.py:126-127 `src = norm1(src + src2)`,
+ * :119 `src = norm2(src + ffn)`, followed by `with_pos_embed` :112-114 of the next layer): y = LayerNorm(x [+ add]) over rows of
+ * `dim` (256 / 512 / 768 / 1024 / 1280); x and add (fp32, may be NULL) are only read.  Outputs, each optional (NULL): out = y (fp32),
+ * out_bf16 = bf16(y), out_q_bf16 = bf16(y + pos[row mod pos_rows]) with pos fp32 (pos_rows x dim). */
+int svb_layernorm_post(const float* x, const float* add, const float* weight, const float* bias, float* out, void* out_bf16,
+                       const float* pos, int pos_rows, void* out_q_bf16, int rows, int dim, float eps, svb_stream_t stream);
 /* out = cast(a + b[i mod b_numel]): svb_add_cast with a `b` shared by every sample (the sine position embedding + level embedding,
  * :73-75). */
 int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream);

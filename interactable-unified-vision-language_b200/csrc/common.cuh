@@ -78,6 +78,10 @@ struct Epilogue {
     // (b (h + 2) + y + ky) (w + 2) + x0 + kx, so the TMA producer shifts rows per tap instead of reading a 9x larger im2col operand.
     // conv_w must be a multiple of the CTA's 128 rows (a tile never crosses an image row), conv_c of 64. ----
     int conv_w = 0, conv_h = 0, conv_c = 0;
+    // ---- transposed fp32 output (streamlined pair kernel, EPI_F32 only): out[n * ldo + m] = acc[m, n] + bias[n].  For C = A W^T with
+    // few W rows and many A rows (the mask logits `einsum("bqc,bchw->bqhw")`, xdecoder.py:459: 101 queries x 65536 positions) the
+    // LONG dimension runs along M — no tile rows wasted on the 101-of-256 queries — and the result still lands query-major. ----
+    int out_t = 0;
     const float2* shift_stats = nullptr;   // [M][shift_parts] statistics of the rows before the update (null: c = shift_in)
     const float* shift_in = nullptr;       // [M] their shifts (null: zeros); [shift_in_mod] indexed row % shift_in_mod when that is set
     int shift_in_mod = 0;
@@ -261,6 +265,8 @@ int stage_u8_patch(const uint8_t* const* images, const int* hs, const int* ws, c
 // out = LayerNorm(x [+ add]); when `add` (same element type as out) is given, x += add is written back first (fused residual)
 int layernorm_rows(float* x, const void* add, const float* w, const float* b, void* out, bool out_bf16, int rows, int D, float eps,
                    cudaStream_t s);
+int layernorm_post_rows(const float* x, const float* add, const float* w, const float* b, float* out, bf16* out_b, const float* pos,
+                        int pos_rows, bf16* out_q, int rows, int D, float eps, cudaStream_t s);
 int cast_and_space2depth(const float* x, void* xb, void* a32, bool out_bf16, int B, int gh, int gw, int D, cudaStream_t s);
 int groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, void* out, bool out_bf16,
                     long rows, int C, long rows_per_sample, float eps, int gelu, cudaStream_t s);

@@ -546,6 +546,61 @@ layernorm_fixed_kernel(float* __restrict__ x, const T* __restrict__ add, const f
     }
 }
 
+// Post-norm LayerNorm of the deformable encoder layers (transformer_encoder_deform.py:126-127, 119), one pass for everything
+// the next GEMMs read:  y = LayerNorm(x [+ add])  ->  out (fp32 residual stream), out_b = bf16(y) (operand of linear1 / value_proj),
+// out_q = bf16(y + pos[row mod pos_rows]) (`with_pos_embed`, :112-114: operand of the sampling-offset / attention-weight Linear).
+// x and add are only read (the pre-norm sum is dead after a post-norm layer).  Replaces LayerNorm + one or two cast passes:
+// 4 [+ 4] bytes read and 4 + 2 [+ 2] written per element instead of 12 [+ 12] read and 6 [+ 10] written.
+template <int NV>
+__global__ void __launch_bounds__(128, 8)
+layernorm_post_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ w, const float* __restrict__ bia,
+                      float* __restrict__ out, bf16* __restrict__ out_b, const float* __restrict__ pos, int pos_rows,
+                      bf16* __restrict__ out_q, int rows, float eps) {
+    constexpr int D = 128 * NV;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __ldcs(xr + lane + 32 * i);
+    if (add) {
+        const float4* ar = reinterpret_cast<const float4*>(add + (size_t)row * D);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 a = __ldcs(ar + lane + 32 * i);
+            v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    const float4* pr = (pos && out_q) ? reinterpret_cast<const float4*>(pos + (size_t)(row % pos_rows) * D) : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w) + idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bia) + idx);
+        const float4 y = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        if (out) reinterpret_cast<float4*>(out + (size_t)row * D)[idx] = y;
+        if (out_b) Vec4<bf16>::store(out_b + (size_t)row * D + 4 * idx, y.x, y.y, y.z, y.w);
+        if (out_q) {
+            float4 q = y;
+            if (pr) { const float4 pp = __ldg(pr + idx); q.x += pp.x; q.y += pp.y; q.z += pp.z; q.w += pp.w; }
+            Vec4<bf16>::store(out_q + (size_t)row * D + 4 * idx, q.x, q.y, q.z, q.w);
+        }
+    }
+}
+
 template <typename T>
 static bool launch_ln_fixed(float* x, const T* add, const float* w, const float* b, T* out, int rows, int D, float eps, cudaStream_t s) {
     const int blocks = (rows + 3) / 4;
@@ -570,6 +625,24 @@ int layernorm_rows(float* x, const void* add, const float* w, const float* b, vo
     if (!fixed) {
         if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, s>>>(x, (const bf16*)add, w, b, (bf16*)out, rows, D, eps);
         else layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, (const float*)add, w, b, (float*)out, rows, D, eps);
+    }
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int layernorm_post_rows(const float* x, const float* add, const float* w, const float* b, float* out, bf16* out_b, const float* pos,
+                        int pos_rows, bf16* out_q, int rows, int D, float eps, cudaStream_t s) {
+    SVB_REQUIRE(D == 256 || D == 512 || D == 768 || D == 1024 || D == 1280, "layernorm_post_rows: width %d (256 / 512 / 768 / 1024 / 1280 are built)", D);
+    SVB_REQUIRE(out || out_b || out_q, "layernorm_post_rows: no output");
+    SVB_REQUIRE(!pos || pos_rows > 0, "layernorm_post_rows: pos needs pos_rows > 0");
+    const int blocks = (rows + 3) / 4;
+    ProfScope prof(PC_NORM, 0, (double)rows * D * (4 + (add ? 4 : 0) + (out ? 4 : 0) + (out_b ? 2 : 0) + (out_q ? 2 : 0)), s);
+    switch (D) {
+        case 256: layernorm_post_kernel<2><<<blocks, 128, 0, s>>>(x, add, w, b, out, out_b, pos, pos_rows, out_q, rows, eps); break;
+        case 512: layernorm_post_kernel<4><<<blocks, 128, 0, s>>>(x, add, w, b, out, out_b, pos, pos_rows, out_q, rows, eps); break;
+        case 768: layernorm_post_kernel<6><<<blocks, 128, 0, s>>>(x, add, w, b, out, out_b, pos, pos_rows, out_q, rows, eps); break;
+        case 1024: layernorm_post_kernel<8><<<blocks, 128, 0, s>>>(x, add, w, b, out, out_b, pos, pos_rows, out_q, rows, eps); break;
+        default: layernorm_post_kernel<10><<<blocks, 128, 0, s>>>(x, add, w, b, out, out_b, pos, pos_rows, out_q, rows, eps); break;
     }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

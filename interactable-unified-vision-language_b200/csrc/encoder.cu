@@ -1035,6 +1035,17 @@ int svb_linear(int mode, const void* A, int lda, const void* W, int ldw, int M, 
     SVB_REQUIRE(false, "svb_linear: bad mode %d", mode);
 }
 
+int svb_linear_nt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, float* out_t, int ldo,
+                  svb_stream_t stream) {
+    SVB_REQUIRE(A && W && out_t, "svb_linear_nt: null argument");
+    SVB_REQUIRE(ldo >= M && (ldo % 8) == 0, "svb_linear_nt: ldo (%d) must be >= M (%d) and a multiple of 8", ldo, M);
+    Epilogue ep;
+    ep.bias = bias;
+    ep.out = out_t; ep.out_bf16 = 0; ep.ldo = ldo;
+    ep.out_t = 1;
+    return gemm_bf16_tc((const bf16*)A, lda, (const bf16*)W, ldw, M, N, K, ep, (cudaStream_t)stream);
+}
+
 int svb_linear_fused(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const float* bias, int act_gelu,
                      const float* resid, int ldr, int resid_mod, void* out, int out_dtype, int ldo, const float* ln_stats,
                      const float* ln_colsum, int ln_dim, float ln_eps, void* out_bf16_copy, int ldo2, float* stat_out,
@@ -1075,6 +1086,16 @@ int svb_layernorm(float* x, const void* add, const float* weight, const float* b
                   svb_stream_t stream) {
     SVB_REQUIRE(x && weight && bias && out, "svb_layernorm: null argument");
     return layernorm_rows(x, add, weight, bias, out, out_dtype == SVB_DTYPE_BF16, rows, dim, eps, (cudaStream_t)stream);
+}
+
+int svb_layernorm_post(const float* x, const float* add, const float* weight, const float* bias, float* out, void* out_bf16,
+                       const float* pos, int pos_rows, void* out_q_bf16, int rows, int dim, float eps, svb_stream_t stream) {
+    SVB_REQUIRE(x && weight && bias, "svb_layernorm_post: null argument");
+    SVB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out) |
+                  reinterpret_cast<uintptr_t>(pos)) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(out_bf16) | reinterpret_cast<uintptr_t>(out_q_bf16)) & 7) == 0,
+                "svb_layernorm_post: the fp32 operands must be 16-byte aligned, the bf16 outputs 8-byte aligned");
+    return layernorm_post_rows(x, add, weight, bias, out, (bf16*)out_bf16, pos, pos_rows, (bf16*)out_q_bf16, rows, dim, eps, (cudaStream_t)stream);
 }
 
 int svb_attention(int impl, int dtype, const void* qkv, void* out, const float* rel_pos_h, const float* rel_pos_w, const float* qkv_bias,

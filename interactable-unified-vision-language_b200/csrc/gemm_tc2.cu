@@ -985,9 +985,23 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 const uint32_t rowa = srow + sbuf * C::CHUNK_BYTES;
                 if constexpr (C::OUTF32) {
+                    if (MODE == EPI_F32 && ep.out_t) {
+                        // transposed box [32 columns][32 rows of the tile]: element (row = lane, column c) goes to box row c, 16-byte
+                        // piece (lane / 4) ^ (c % 8), word lane % 4 — the 32 lanes of one store hit 32 different banks
+                        const uint32_t tb = box + ((lane & 3) << 2);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a, b;
+                            f2_unpack(v[j], a, b);
+                            const uint32_t c0 = 2 * j, c1 = 2 * j + 1;
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + c0 * 128 + ((((uint32_t)lane >> 2) ^ (c0 & 7)) << 4)), "f"(a) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tb + c1 * 128 + ((((uint32_t)lane >> 2) ^ (c1 & 7)) << 4)), "f"(b) : "memory");
+                        }
+                    } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(rowa + ((j ^ swz) << 4)), "l"(v[2 * j]), "l"(v[2 * j + 1]) : "memory");
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -1002,6 +1016,7 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (MODE == EPI_F32_REDADD) tma_reduce_add_2d(&map_o, box, col0, orow0);
+                    else if (MODE == EPI_F32 && ep.out_t) tma_store_2d(&map_o, box, orow0, col0);      // (inner = tile row, outer = column)
                     else tma_store_2d(&map_o, box, col0, orow0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -1111,6 +1126,9 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     static const int off = [] { const char* e = getenv("SVB_GEMM_EPI"); return e ? atoi(e) == 0 : 0; }();   // SVB_GEMM_EPI=0: generic epilogue only
     if (off) return 0;
     int mode = 0;
+    if (ep.out_t && (ep.out_bf16 || ep.resid || ep.stats || ep.act == 1 || ep.ln_stats || ep.gn_in_stats || ep.remap_g || ep.out2 || ep.stat_out ||
+                     ep.conv_w || (M % 4) != 0))
+        return 0;                                                        // (the caller reports the refusal)
     if (ep.out2 || ep.stat_out) {
         // LayerNorm-fold producer: in-place fp32 residual + bf16 copy + row sums (BN = 256 only: 128-column slabs)
         if (BN != 256 || ep.out_bf16 || ep.resid != ep.out || ep.ldr != ep.ldo || ep.resid_mod || ep.stats || ep.act || ep.ln_stats ||
@@ -1146,7 +1164,8 @@ int try_launch_streamlined(const bf16* A, int lda, const bf16* W, int ldw, int M
     rc = make_tmap_2d_bf16(&mw, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, BK, BN / 2, 128);
     if (rc) return rc;
     const uint64_t out_rows = ep.remap_g ? (uint64_t)(M / epilogue_remap_tokens(ep)) * epilogue_remap_padded(ep) : (uint64_t)M;
-    rc = make_tmap_2d(&mo, ep.out, esz, (uint64_t)N, out_rows, (uint64_t)ep.ldo, 32, 32, ep.out_bf16 ? 64 : 128);
+    if (ep.out_t) rc = make_tmap_2d(&mo, ep.out, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 32, 128);      // out^T [N rows][M]
+    else rc = make_tmap_2d(&mo, ep.out, esz, (uint64_t)N, out_rows, (uint64_t)ep.ldo, 32, 32, ep.out_bf16 ? 64 : 128);
     if (rc) return rc;
     CUtensorMap mo2 = mo;
     if (mode == EPI_F32_RMW && ep.out2) {
@@ -1203,6 +1222,7 @@ int launch_gemm2(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, i
         if (rc0 || done) return rc0;
     }
     SVB_REQUIRE(!ep.gn_in_stats, "gemm_tc2: the GroupNorm-fold epilogue exists in the streamlined kernel only (unset SVB_GEMM_EPI / SVB_GEMM_CLUSTER)");
+    SVB_REQUIRE(!ep.out_t, "gemm_tc2: the transposed-output epilogue needs the streamlined kernel, fp32 output without residual / statistics / GELU and M %% 4 == 0");
     if (ep.pad_bias && ep.remap_g) {       // the generic kernel does not write the pad rows itself
         int rc = fill_pad_rows((bf16*)ep.out, ep.pad_bias, M / epilogue_remap_tokens(ep), ep.remap_h ? ep.remap_h : ep.remap_g, ep.remap_g,
                                ep.remap_hp ? ep.remap_hp : ep.remap_gp, ep.remap_gp, ep.ldo, stream);

@@ -81,6 +81,114 @@ __global__ void resize_aa_kernel(const float* __restrict__ src, float* __restric
     }
 }
 
+// The same two passes with the filter taken out of the inner loop (the kernel above evaluates the cubic for every tap of every output
+// element: 33 evaluations per output at the 8x reduction, identical for all rows of a map and all maps; it remains for shapes whose
+// tiles do not fit shared memory).  A block first writes the normalised taps of the output indexes it needs into shared memory
+// (lo / count / weights, as PyTorch's `upsample_bicubic2d_aa` normalises them before the sum), then:
+//   columns (w -> out): a block owns 32 rows of one map, staged once with coalesced 16-byte loads into a padded tile; lane = row,
+//     a warp walks the output columns, so the weights are shared-memory broadcasts and the data reads are conflict-free; the
+//     32 x out results leave through a second padded tile as whole rows;
+//   rows (h -> out): thread = (output row, column) with consecutive lanes on consecutive columns (coalesced, the weights broadcast).
+// Shared by both: taps of output index o along an axis of `in` -> `out` elements.
+__device__ __forceinline__ void aa_taps(int o, int in, float scale, float support, float invscale, int& lo, int& n, float& center) {
+    center = scale * (o + 0.5f);
+    lo = max((int)(center - support + 0.5f), 0);
+    n = min((int)(center + support + 0.5f), in) - lo;
+}
+// table for output indexes [o0, o0 + no): wt[(o - o0) * taps_max + t], lo_s / n_s[o - o0]; call with all threads of the block
+__device__ __forceinline__ void aa_build_table(float* wt, int* lo_s, int* n_s, int o0, int no, int in, int out, int taps_max) {
+    const float scale = (float)in / (float)out;
+    const float support = scale >= 1.f ? 2.f * scale : 2.f, invscale = scale >= 1.f ? 1.f / scale : 1.f;
+    for (int i = threadIdx.x; i < no * taps_max; i += blockDim.x) {
+        const int ol = i / taps_max, t = i - ol * taps_max;
+        int lo, n;
+        float center;
+        aa_taps(o0 + ol, in, scale, support, invscale, lo, n, center);
+        wt[i] = t < n ? cubic_aa((lo + t - center + 0.5f) * invscale) : 0.f;
+        if (t == 0) { lo_s[ol] = lo; n_s[ol] = min(n, taps_max); }
+    }
+    __syncthreads();
+    for (int ol = threadIdx.x; ol < no; ol += blockDim.x) {
+        float wsum = 0.f;
+        for (int t = 0; t < n_s[ol]; ++t) wsum += wt[ol * taps_max + t];
+        const float inv = 1.f / wsum;
+        for (int t = 0; t < n_s[ol]; ++t) wt[ol * taps_max + t] *= inv;
+    }
+    __syncthreads();
+}
+
+constexpr int RA_ROWS = 32;
+__global__ void __launch_bounds__(256)
+resize_aa_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int out, int taps_max) {
+    extern __shared__ float ra_sm[];
+    float* tile = ra_sm;                                   // [32][cols + 1]
+    float* so = tile + RA_ROWS * (cols + 1);               // [32][out + 1]
+    float* wt = so + RA_ROWS * (out + 1);                  // [out][taps_max]
+    int* lo_s = reinterpret_cast<int*>(wt + out * taps_max);
+    int* n_s = lo_s + out;
+    const int m = blockIdx.y, r0 = blockIdx.x * RA_ROWS;
+    const float* s = src + ((size_t)m * rows + r0) * cols;
+    const int nr = min(RA_ROWS, rows - r0);
+    if ((cols & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int c4 = cols >> 2;
+        for (int i = threadIdx.x; i < nr * c4; i += blockDim.x) {
+            const int r = i / c4, c = (i - r * c4) * 4;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(s + (size_t)r * cols + c));
+            float* t = tile + r * (cols + 1) + c;
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nr * cols; i += blockDim.x) {
+            const int r = i / cols, c = i - r * cols;
+            tile[r * (cols + 1) + c] = __ldcs(s + (size_t)r * cols + c);
+        }
+    }
+    aa_build_table(wt, lo_s, n_s, 0, out, cols, out, taps_max);      // (its barriers also cover the tile)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < nr) {
+        const float* trow = tile + lane * (cols + 1);
+        for (int o = warp; o < out; o += 8) {
+            const float* w = wt + o * taps_max;
+            const float* tp = trow + lo_s[o];
+            const int n = n_s[o];
+            float acc = 0.f;
+            for (int t = 0; t < n; ++t) acc = fmaf(w[t], tp[t], acc);
+            so[lane * (out + 1) + o] = acc;
+        }
+    }
+    __syncthreads();
+    float* d = dst + ((size_t)m * rows + r0) * out;
+    for (int i = threadIdx.x; i < nr * out; i += blockDim.x) {
+        const int r = i / out, o = i - r * out;
+        d[i] = so[r * (out + 1) + o];
+    }
+}
+
+constexpr int RA_PER_BLOCK = 2048;                         // outputs per block of the row pass
+__global__ void __launch_bounds__(256)
+resize_aa_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int out, int taps_max) {
+    extern __shared__ float ra_sm[];
+    const int m = blockIdx.y;
+    const int total = out * cols;
+    const int i0 = blockIdx.x * RA_PER_BLOCK, i1 = min(total, i0 + RA_PER_BLOCK);
+    const int o0 = i0 / cols, no = (i1 - 1) / cols - o0 + 1;
+    float* wt = ra_sm;                                     // [no][taps_max]
+    int* lo_s = reinterpret_cast<int*>(wt + no * taps_max);
+    int* n_s = lo_s + no;
+    aa_build_table(wt, lo_s, n_s, o0, no, rows, out, taps_max);
+    const float* s = src + (size_t)m * rows * cols;
+    float* d = dst + (size_t)m * total;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int o = i / cols, c = i - o * cols, ol = o - o0;
+        const float* w = wt + ol * taps_max;
+        const float* sp = s + (size_t)lo_s[ol] * cols + c;
+        const int n = n_s[ol];
+        float acc = 0.f;
+        for (int t = 0; t < n; ++t) acc = fmaf(w[t], __ldg(sp + (size_t)t * cols), acc);
+        d[i] = acc;
+    }
+}
+
 // ---- xdecoder.py:467: (sigmoid(v) < 0.5) == (v < 0), repeated over the heads: out[b, h, :] = v[b, :] < 0 ----
 __global__ void mask_threshold_kernel(const float* __restrict__ v, uint8_t* __restrict__ out, int heads, size_t per_sample) {
     const int b = blockIdx.y;
@@ -116,11 +224,35 @@ extern "C" int svb_resize_bicubic_aa(const float* src, float* tmp, float* dst, i
     cudaStream_t s = (cudaStream_t)stream;
     ProfScope prof(PC_OTHER, 0, (double)maps * ((double)h * w + 2.0 * h * out_w + (double)out_h * out_w) * 4, s, 2);
     // columns first (w -> out_w), then rows (h -> out_h), as the reference's separable CPU kernel orders them
-    dim3 g1(grid_cap((size_t)h * out_w, 256), maps);
-    resize_aa_kernel<false><<<g1, 256, 0, s>>>(src, tmp, h, w, w, out_w);
+    auto taps_of = [](int in, int out) {
+        const float scale = (float)in / (float)out;
+        return (int)ceilf(2.f * (scale >= 1.f ? 2.f * scale : 2.f)) + 2;
+    };
+    static const int legacy = [] { const char* e = getenv("SVB_RESIZE_LEGACY"); return e ? atoi(e) : 0; }();   // 1: the per-tap kernels (A/B)
+    const int t1 = taps_of(w, out_w), t2 = taps_of(h, out_h);
+    const size_t sm1 = sizeof(float) * ((size_t)RA_ROWS * (w + 1) + (size_t)RA_ROWS * (out_w + 1) + (size_t)out_w * t1) + sizeof(int) * 2 * (size_t)out_w;
+    const int no2 = (RA_PER_BLOCK + out_w - 1) / out_w + 1;
+    const size_t sm2 = sizeof(float) * (size_t)no2 * t2 + sizeof(int) * 2 * (size_t)no2;
+    if (!legacy && sm1 <= 96 * 1024 && maps <= 65535) {
+        static bool attr = false;
+        if (!attr) {
+            SVB_CHECK_CUDA(cudaFuncSetAttribute(resize_aa_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr = true;
+        }
+        dim3 g1((h + RA_ROWS - 1) / RA_ROWS, maps);
+        resize_aa_cols_kernel<<<g1, 256, sm1, s>>>(src, tmp, h, w, out_w, t1);
+    } else {
+        dim3 g1(grid_cap((size_t)h * out_w, 256), maps);
+        resize_aa_kernel<false><<<g1, 256, 0, s>>>(src, tmp, h, w, w, out_w);
+    }
     SVB_CHECK_CUDA(cudaGetLastError());
-    dim3 g2(grid_cap((size_t)out_h * out_w, 256), maps);
-    resize_aa_kernel<true><<<g2, 256, 0, s>>>(tmp, dst, h, out_w, h, out_h);
+    if (!legacy && sm2 <= 48 * 1024 && maps <= 65535) {
+        dim3 g2(((size_t)out_h * out_w + RA_PER_BLOCK - 1) / RA_PER_BLOCK, maps);
+        resize_aa_rows_kernel<<<g2, 256, sm2, s>>>(tmp, dst, h, out_w, out_h, t2);
+    } else {
+        dim3 g2(grid_cap((size_t)out_h * out_w, 256), maps);
+        resize_aa_kernel<true><<<g2, 256, 0, s>>>(tmp, dst, h, out_w, h, out_h);
+    }
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -154,7 +154,13 @@ class MaskPredictionHead(nn.Module):
                 rows = self.mask_rows(mask_features)
             masks = torch.empty(B, Q, H, W, dtype=torch.float32, device=dev)
             for b in range(B):                                                                                        # :459 "bqc,bchw->bqhw"
-                self._linear(mode, a[b * Q:(b + 1) * Q], rows[b * H * W:(b + 1) * H * W], None, masks[b].view(Q, H * W))
+                if mode == cabi.MODE_BF16 and (H * W) % 8 == 0:
+                    # positions along the GEMM's M (no tile rows spent on padding 101 queries to 256), result stored query-major
+                    rb, ab = rows[b * H * W:(b + 1) * H * W], a[b * Q:(b + 1) * Q]
+                    cabi.check(lib.svb_linear_nt(rb.data_ptr(), rb.stride(0), ab.data_ptr(), ab.stride(0), H * W, Q, rb.shape[1], None,
+                                                 masks[b].data_ptr(), H * W, st()), "svb_linear_nt")
+                else:
+                    self._linear(mode, a[b * Q:(b + 1) * Q], rows[b * H * W:(b + 1) * H * W], None, masks[b].view(Q, H * W))
             tmp = torch.empty(B * Q * H * ow, dtype=torch.float32, device=dev)
             small = torch.empty(B, Q * oh * ow, dtype=torch.float32, device=dev)
             cabi.check(lib.svb_resize_bicubic_aa(masks.data_ptr(), tmp.data_ptr(), small.data_ptr(), B * Q, H, W, oh, ow, st()),
@@ -203,8 +209,11 @@ class CrossAttentionLayer(nn.Module):
             self.norm._w32, self.norm._b32 = f(self.norm.weight), f(self.norm.bias)
             self._sig = sig
 
-    def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None):
-        """tgt (Q, B, C), memory (HW, B, C), memory_mask (B * heads, Q, HW) bool (True = not allowed), pos / query_pos like memory / tgt."""
+    def forward(self, tgt, memory, memory_mask=None, memory_key_padding_mask=None, pos=None, query_pos=None, memory_operands=None):
+        """tgt (Q, B, C), memory (HW, B, C), memory_mask (B * heads, Q, HW) bool (True = not allowed), pos / query_pos like memory / tgt.
+        ``memory_operands`` (not in the reference's signature): a dict a caller may pass to every layer that reads the SAME memory / pos
+        (the X-Decoder visits each feature level three times, xdecoder.py:262): the first call stores the GEMM operand copies of
+        ``memory + pos`` and ``memory`` in it, the later ones reuse them instead of casting the level again."""
         if not tgt.is_cuda:
             raise RuntimeError("CrossAttentionLayer (B200) has no CPU path: the inputs must be CUDA tensors")
         if memory_key_padding_mask is not None:
@@ -233,8 +242,13 @@ class CrossAttentionLayer(nn.Module):
             qp = None if query_pos is None else query_pos.detach().to(torch.float32).contiguous().view(Q * B, C)
             kp = None if pos is None else pos.detach().to(torch.float32).contiguous().view(HW * B, C)
             q_in = cast(x, qp) if (qp is not None or adt != torch.float32) else x                                  # :100 with_pos_embed(tgt, query_pos)
-            k_in = cast(mem, kp) if (kp is not None or adt != torch.float32) else mem                              # :101 with_pos_embed(memory, pos)
-            v_in = k_in if kp is None else (cast(mem, None) if adt != torch.float32 else mem)                      # :102 value = memory
+            if memory_operands is not None and memory_operands.get("key") == (adt, HW * B, C):
+                k_in, v_in = memory_operands["k_in"], memory_operands["v_in"]
+            else:
+                k_in = cast(mem, kp) if (kp is not None or adt != torch.float32) else mem                          # :101 with_pos_embed(memory, pos)
+                v_in = k_in if kp is None else (cast(mem, None) if adt != torch.float32 else mem)                  # :102 value = memory
+                if memory_operands is not None:
+                    memory_operands.update(key=(adt, HW * B, C), k_in=k_in, v_in=v_in)
             q = lin(mode, q_in, self._wq, self._bq, torch.empty(Q * B, C, dtype=adt, device=dev))
             k = lin(mode, k_in, self._wk, self._bk, torch.empty(HW * B, C, dtype=adt, device=dev))
             v = lin(mode, v_in, self._wv, self._bv, torch.empty(HW * B, C, dtype=adt, device=dev))
@@ -451,12 +465,14 @@ class XDecoderMaskPath(nn.Module):
             masks.append(res["outputs_mask"])
             extras.append(res)
             attn_mask = res["attn_mask"]
+            level_ops = {}                                                                           # operand copies of src[lvl] (+ pos[lvl]), per level
             for i in range(self.num_layers):
                 lvl = self.level_indexes[i]
                 cabi.check(lib.svb_mask_clear_full_rows(attn_mask.data_ptr(), attn_mask.shape[0] * attn_mask.shape[1], attn_mask.shape[2], st()),
                            "svb_mask_clear_full_rows")                                                # :267
                 output, _ = self.transformer_cross_attention_layers[i](output, src[lvl], memory_mask=attn_mask, pos=pos[lvl],
-                                                                       query_pos=query_embed)        # :272-277
+                                                                       query_pos=query_embed,
+                                                                       memory_operands=level_ops.setdefault(lvl, {}))    # :272-277
                 output = self.transformer_self_attention_layers[i](output, tgt_mask=self_mask, query_pos=query_embed)   # :283-287
                 output = self.transformer_ffn_layers[i](output)                                       # :290-292
                 res = head(output, mask_features, size_list[(i + 1) % self.num_feature_levels], **kw)         # :299

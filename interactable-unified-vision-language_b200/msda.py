@@ -113,8 +113,10 @@ class MSDeformAttn(nn.Module):
             return cabi.MODE_FP32, torch.float32
         raise ValueError("precision must be 'bf16' or 'fp32'")
 
-    def _core(self, q_in, x_in, reference_points, shapes, starts, input_padding_mask, N, Lq, S):
-        """q_in (N*Lq,C) / x_in (N*S,C) already in the GEMM operand dtype -> fp32 (N*Lq,C).  ms_deform_attn.py:97-124."""
+    def _core(self, q_in, x_in, reference_points, shapes, starts, input_padding_mask, N, Lq, S, resid=None):
+        """q_in (N*Lq,C) / x_in (N*S,C) already in the GEMM operand dtype -> fp32 (N*Lq,C).  ms_deform_attn.py:97-124.
+        With ``resid`` (fp32 (N*Lq,C)) the output projection accumulates IN PLACE, ``resid += output_proj(...)`` (the caller's
+        ``src + dropout(src2)``, transformer_encoder_deform.py:126, in the GEMM's reduce-add epilogue), and ``resid`` is returned."""
         mode, adt = self._mode()
         bf16 = adt == torch.bfloat16
         dev = q_in.device
@@ -132,6 +134,11 @@ class MSDeformAttn(nn.Module):
             value.data_ptr(), (ctypes.c_int32 * (2 * L))(*shapes), (ctypes.c_int32 * L)(*starts), ref.data_ptr(), int(ref.shape[-1]),
             raw.data_ptr(), sampled.data_ptr(), cabi.DTYPE_BF16 if bf16 else cabi.DTYPE_F32, N, S, M, D, L, Lq, P, cabi.stream_ptr()),
             "svb_ms_deform_attn_fused_forward")                                                                          # :103-122
+        if resid is not None:
+            cabi.check(cabi.lib().svb_linear(mode, sampled.data_ptr(), sampled.stride(0), wo.data_ptr(), wo.stride(0), N * Lq, C, C, bo.data_ptr(), 0,
+                                             resid.data_ptr(), C, 0, resid.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0, cabi.stream_ptr()),
+                       "svb_linear")                                                                                    # :124 (+ :126)
+            return resid
         return self._linear(mode, sampled, wo, bo, torch.empty(N * Lq, C, dtype=torch.float32, device=dev))             # :124
 
     @staticmethod
@@ -178,6 +185,19 @@ def _layernorm(x, add, ln, out):
     rows, dim = x.shape
     cabi.check(cabi.lib().svb_layernorm(x.data_ptr(), add.data_ptr() if add is not None else None, ln._w32.data_ptr(), ln._b32.data_ptr(),
                                         out.data_ptr(), cabi.DTYPE_F32, rows, dim, float(ln.eps), cabi.stream_ptr()), "svb_layernorm")
+    return out
+
+
+_LN_POST_WIDTHS = (256, 512, 768, 1024, 1280)          # the widths svb_layernorm_post is built for
+
+
+def _layernorm_post(x, ln, out, out_b=None, pos=None, out_q=None):
+    """One pass: out = LayerNorm(x) (fp32), out_b = bf16(out), out_q = bf16(out + pos) (pos shared by the batch when it has fewer rows)."""
+    rows, dim = x.shape
+    cabi.check(cabi.lib().svb_layernorm_post(
+        x.data_ptr(), None, ln._w32.data_ptr(), ln._b32.data_ptr(), out.data_ptr(), out_b.data_ptr() if out_b is not None else None,
+        pos.data_ptr() if pos is not None else None, pos.numel() // dim if pos is not None else 0,
+        out_q.data_ptr() if out_q is not None else None, rows, dim, float(ln.eps), cabi.stream_ptr()), "svb_layernorm_post")
     return out
 
 
@@ -238,23 +258,41 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
                 ln._w32, ln._b32 = f(ln.weight), f(ln.bias)
             self._packed_sig = sig
 
-    def _forward_rows(self, x, pos, reference_points, shapes, starts, padding_mask, N, S):
-        """x (N*S, C) fp32, OVERWRITTEN (it becomes src + attention output); pos (N*S, C) fp32 or None -> new (N*S, C) fp32."""
+    def _forward_rows(self, x, pos, reference_points, shapes, starts, padding_mask, N, S, carry=None, last=True):
+        """x (N*S, C) fp32, OVERWRITTEN (src + attention output, then the layer's output); pos fp32, (N*S, C) or (S, C) shared by the
+        batch, or None -> the new (N*S, C) fp32 rows (in x's storage).  ``carry``: a dict the encoder loops hand from layer to layer —
+        in the bf16 path the norm2 pass of a layer that is not the ``last`` also writes the next layer's GEMM operands (bf16(src) and
+        bf16(src + pos)), so the two cast passes at the top of the next layer disappear."""
         attn = self.self_attn
         mode, adt = attn._mode()
+        bf16 = adt == torch.bfloat16
         dev = x.device
         self._prepare(dev, adt)
         C = x.shape[1]
-        q_in = _add_cast(x, pos, adt) if (pos is not None or adt != torch.float32) else x                       # :125 with_pos_embed
-        x_in = q_in if pos is None else (_add_cast(x, None, adt) if adt != torch.float32 else x)
-        src2 = attn._core(q_in, x_in, reference_points, shapes, starts, padding_mask, N, S, S)                  # :125
-        y = _layernorm(x, src2, self.norm1, torch.empty_like(x))                                                # :126-127
-        yb = _add_cast(y, None, adt) if adt != torch.float32 else y
+        if carry is not None and carry.get("x") is x:
+            q_in, x_in = carry["q_in"], carry["x_in"]
+        else:
+            q_in = _add_cast(x, pos, adt) if (pos is not None or bf16) else x                                   # :125 with_pos_embed
+            x_in = q_in if pos is None else (_add_cast(x, None, adt) if bf16 else x)
+        attn._core(q_in, x_in, reference_points, shapes, starts, padding_mask, N, S, S, resid=x)                # :125-126 x = src + src2
+        fused = bf16 and C in _LN_POST_WIDTHS                  # (other widths: LayerNorm + separate cast passes)
+        if fused:                                                                                               # :127 norm1 (+ linear1's operand)
+            yb = torch.empty(x.shape, dtype=adt, device=dev)
+            y = _layernorm_post(x, self.norm1, torch.empty_like(x), yb)
+        else:
+            y = _layernorm(x, None, self.norm1, torch.empty_like(x))
+            yb = _add_cast(y, None, adt) if bf16 else y
         hid = attn._linear(mode, yb, self._w1, self._b1, torch.empty(N * S, self._w1.shape[0], dtype=adt, device=dev), act=2)     # :117 relu(linear1)
         # src + linear2(..) accumulated IN PLACE into y (the GEMM's TMA reduce-add epilogue), then norm2 into the buffer x leaves behind
         cabi.check(cabi.lib().svb_linear(mode, hid.data_ptr(), hid.stride(0), self._w2.data_ptr(), self._w2.stride(0), N * S, C, hid.shape[1],
                                          self._b2.data_ptr(), 0, y.data_ptr(), C, 0, y.data_ptr(), cabi.DTYPE_F32, C, None, 0, 0, 0,
                                          cabi.stream_ptr()), "svb_linear")                                      # :117-118 src + linear2(..)
+        if fused and carry is not None and not last:                                                             # :119 norm2 (+ the next layer's operands)
+            nx = torch.empty(x.shape, dtype=adt, device=dev)
+            nq = torch.empty(x.shape, dtype=adt, device=dev) if pos is not None else None
+            _layernorm_post(y, self.norm2, x, nx, pos, nq)
+            carry.update(x=x, x_in=nx, q_in=nq if nq is not None else nx)
+            return x
         return _layernorm(y, None, self.norm2, x)                                                               # :119
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
@@ -306,8 +344,9 @@ class MSDeformAttnTransformerEncoder(nn.Module):
             ref = self.get_reference_points(shapes_hw, valid_ratios.to(torch.float32), src.device)
             x = src.detach().reshape(N * S, C).to(torch.float32).clone()
             p = None if pos is None else pos.detach().reshape(N * S, C).to(torch.float32).contiguous()
-            for layer in self.layers:
-                x = layer._forward_rows(x, p, ref, shapes, starts, padding_mask, N, S)
+            carry = {}
+            for i, layer in enumerate(self.layers):
+                x = layer._forward_rows(x, p, ref, shapes, starts, padding_mask, N, S, carry, i + 1 == len(self.layers))
         return x.view(N, S, C).to(src.dtype)
 
 

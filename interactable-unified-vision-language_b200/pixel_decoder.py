@@ -202,8 +202,9 @@ class MSDeformAttnPixelDecoder(nn.Module):
             ref = MSDeformAttnTransformerEncoder.get_reference_points(shapes, torch.ones(B, len(shapes), 2, dtype=torch.float32, device=dev), dev)
             flat_shapes = [v for hw in shapes for v in hw]
             y = src
-            for layer in self.transformer.encoder.layers:
-                y = layer._forward_rows(y, pos, ref, flat_shapes, starts, None, B, S)
+            carry, layers = {}, self.transformer.encoder.layers
+            for i, layer in enumerate(layers):
+                y = layer._forward_rows(y, pos, ref, flat_shapes, starts, None, B, S, carry, i + 1 == len(layers))
             # ---- extra FPN level(s) on the high-resolution features (:341-351) ----
             cur_shape, cur, cur_stride = shapes[-1], y[starts[-1]:], S * C                     # out[-1]: the finest transformer level
             for idx, f in enumerate(self.in_features[:self.num_fpn_levels][::-1]):

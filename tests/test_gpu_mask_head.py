@@ -17,7 +17,8 @@ DEV = "cuda"
 
 
 @pytest.mark.parametrize("shape,size", [((5, 32, 32), (8, 8)), ((3, 48, 40), (12, 10)), ((2, 24, 24), (12, 12)), ((2, 17, 23), (5, 9)),
-                                        ((2, 256, 256), (32, 32))])
+                                        ((2, 256, 256), (32, 32)), ((3, 256, 256), (64, 64)), ((2, 256, 256), (128, 128)),
+                                        ((2, 100, 60), (25, 30)), ((2, 40, 36), (80, 72)), ((1, 64, 64), (64, 64)), ((1, 8, 1000), (8, 125))])
 def test_resize_bicubic_aa(shape, size):
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(7)).to(DEV)
     n, h, w = shape

@@ -189,3 +189,38 @@ def test_msda_one_lane_kernel_stays_correct():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_msda.py", "-q", "-x", "-k", "(module or against_reference or against_oracle) and not one_lane"],
                        cwd=root, env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-500:])
+
+
+@pytest.mark.parametrize("rows,dim,pos_rows", [(1000, 512, 250), (777, 256, 777), (64, 1280, 0)])
+def test_layernorm_post_outputs(rows, dim, pos_rows):
+    """svb_layernorm_post: LayerNorm(x [+ add]) once, three outputs (fp32, bf16, bf16 of the sum with a position embedding shared by
+    the batch) — the post-norm pairs of the deformable encoder layer (transformer_encoder_deform.py:126-127, 119, 112-114)."""
+    from iuvl_b200 import cabi
+    g = torch.Generator().manual_seed(rows + dim)
+    x = (torch.randn(rows, dim, generator=g) * 1.7 + 0.3).to(DEV)
+    add = torch.randn(rows, dim, generator=g).to(DEV)
+    w, b = (1 + 0.2 * torch.randn(dim, generator=g)).to(DEV), (0.2 * torch.randn(dim, generator=g)).to(DEV)
+    pos = torch.randn(pos_rows, dim, generator=g).to(DEV) if pos_rows else None
+    x0, add0 = x.clone(), add.clone()
+    for use_add in (False, True):
+        out = torch.full((rows, dim), float("nan"), device=DEV)
+        ob = torch.full((rows, dim), float("nan"), dtype=torch.bfloat16, device=DEV)
+        oq = torch.full((rows, dim), float("nan"), dtype=torch.bfloat16, device=DEV) if pos_rows else None
+        cabi.check(cabi.lib().svb_layernorm_post(x.data_ptr(), add.data_ptr() if use_add else None, w.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                                 ob.data_ptr(), cabi.ptr(pos), pos_rows, cabi.ptr(oq), rows, dim, 1e-5, cabi.stream_ptr()), "ln_post")
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.layer_norm((x0 + add0 if use_add else x0).double(), (dim,), w.double(), b.double(), 1e-5)
+        assert ib.rel_l2(out, ref) < 2e-6
+        assert torch.equal(ob, out.bfloat16())
+        if pos_rows:
+            idx = torch.arange(rows, device=DEV) % pos_rows
+            assert torch.equal(oq, (out + pos[idx]).bfloat16())
+        assert torch.equal(x, x0) and torch.equal(add, add0)          # the inputs are only read
+    only_b = torch.empty(rows, dim, dtype=torch.bfloat16, device=DEV)           # outputs are optional one by one
+    cabi.check(cabi.lib().svb_layernorm_post(x.data_ptr(), add.data_ptr(), w.data_ptr(), b.data_ptr(), None, only_b.data_ptr(), None, 0, None, rows,
+                                             dim, 1e-5, cabi.stream_ptr()), "ln_post")
+    assert torch.equal(only_b, ob)
+    assert cabi.lib().svb_layernorm_post(x.data_ptr(), None, w.data_ptr(), b.data_ptr(), None, None, None, 0, None, rows, dim, 1e-5,
+                                         cabi.stream_ptr()) != 0          # no output requested
+    assert cabi.lib().svb_layernorm_post(x.data_ptr(), None, w.data_ptr(), b.data_ptr(), out.data_ptr(), None, None, 0, None, rows, 200, 1e-5,
+                                         cabi.stream_ptr()) != 0          # a width that is not built

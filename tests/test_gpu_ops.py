@@ -560,3 +560,24 @@ def test_attention_ab_variants_stay_correct(env):
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_ops.py", "-q", "-x", "-k", "(test_attention_tcgen05 or test_windowed_softmax) and not variants and not many_launches"],
                        cwd=root, env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (env, r.stdout[-1500:], r.stderr[-500:])
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(4096, 101, 512, False), (65536, 101, 512, False), (1000, 37, 64, True), (520, 128, 192, True),
+                                         (8192, 256, 128, True)])
+def test_linear_nt_transposed_store(M, N, K, bias):
+    """svb_linear_nt: out_t[n, m] = sum_k A[m, k] W[n, k] + bias[n] — the mask-logit einsum (xdecoder.py:459) with the positions along
+    the GEMM's M and the fp32 result stored query-major.  Against the fp64 product of the same bf16 operands, and against svb_linear
+    with the operands swapped (the path it replaces)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV).bfloat16()
+    b = torch.randn(N, generator=g).to(DEV) if bias else None
+    out = torch.full((N, M), float("nan"), device=DEV)
+    cabi.check(cabi.lib().svb_linear_nt(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, cabi.ptr(b), out.data_ptr(), M,
+                                         cabi.stream_ptr()), "svb_linear_nt")
+    torch.cuda.synchronize()
+    ref = W.double() @ A.double().t() + (b.double()[:, None] if bias else 0)
+    assert torch.isfinite(out).all()
+    assert ib.rel_l2(out, ref) < 1e-5
+    swapped = _linear(cabi.MODE_BF16, W, A, out_dtype=torch.float32)             # (N, M) = W A^T, no bias
+    assert ib.rel_l2(out - (b[:, None] if bias else 0), swapped) < 1e-6
