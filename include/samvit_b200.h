@@ -259,6 +259,15 @@ int svb_conv3x3_rows(const float* src, const void* weight_bf16, const float* bia
  * out_bf16 = bf16(y), out_q_bf16 = bf16(y + pos[row mod pos_rows]) with pos fp32 (pos_rows x dim). */
 int svb_layernorm_post(const float* x, const float* add, const float* weight, const float* bias, float* out, void* out_bf16,
                        const float* pos, int pos_rows, void* out_q_bf16, int rows, int dim, float eps, svb_stream_t stream);
+/* One FPN level between its lateral convolution and the output of its 3x3 `output_conv` (transformer_encoder_deform.py:346-349), bf16
+ * path: out (batch*h*w, cout) fp32 = act(conv3x3(GroupNorm(lateral) + F.interpolate(cur, (h, w), "bilinear")) + bias).  lateral
+ * (batch*h*w, cin) fp32 = the raw lateral convolution; gn_gamma / gn_beta NULL: no norm; cur (batch, cur_h, cur_w, cin) fp32 rows with
+ * `cur_sample_stride` elements between samples (<= 0: dense); padded_ws: batch*(h+2)*(w+2)*cin bf16; stats_ws: batch*groups*2 doubles.
+ * The GroupNorm apply, the upsample-add and the zero-padded bf16 operand of the implicit GEMM are ONE pass (svb_groupnorm_rows +
+ * svb_upsample_add_rows + svb_conv3x3_rows compute the same thing through two fp32 maps). */
+int svb_fpn_conv3x3_rows(const float* lateral, const float* gn_gamma, const float* gn_beta, int gn_groups, float gn_eps, const float* cur,
+                         int64_t cur_sample_stride, int cur_h, int cur_w, const void* weight_bf16, const float* bias, float* out,
+                         void* padded_ws, double* stats_ws, int batch, int h, int w, int cin, int cout, int relu, svb_stream_t stream);
 /* out = cast(a + b[i mod b_numel]): svb_add_cast with a `b` shared by every sample (the sine position embedding + level embedding,
  * :73-75). */
 int svb_add_cast_bcast(const float* a, const float* b, int64_t b_numel, void* out, int out_dtype, int64_t numel, svb_stream_t stream);

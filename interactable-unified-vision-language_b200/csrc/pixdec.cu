@@ -192,6 +192,71 @@ __global__ void pad_rows_bf16_kernel(const float* __restrict__ src, bf16* __rest
     }
 }
 
+// ---- one pass for what sits between the lateral convolution and the 3x3 output convolution of an FPN level
+// (transformer_encoder_deform.py:346-349): dst[b, y + 1, x + 1, c] = bf16(GroupNorm(lat)[b, y, x, c] + bilinear(cur[b])(y, x)[c]) on a
+// zero border — GroupNorm apply, `cur_fpn + F.interpolate(out[-1], ..., "bilinear")` and the zero-padded bf16 operand of the
+// implicit-GEMM convolution, without the two fp32 maps in between (at 256^2 x 512 channels: 1.6 GB moved per 8 images instead of 5.9).
+__global__ void fpn_gn_up_pad_kernel(const float* __restrict__ lat, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const double* __restrict__ stats, int groups, float eps, const float* __restrict__ cur,
+                                     long long cur_sample_stride, int H, int W, bf16* __restrict__ dst, int OH, int OW, int C) {
+    extern __shared__ float2 mr[];                         // [groups] (mean, rstd); unused without a norm
+    const int b = blockIdx.y, c8n = C / 8, cg = stats ? C / groups : C;
+    if (stats) {
+        const double n = (double)OH * OW * cg;
+        for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+            const double mu = stats[(size_t)b * 2 * groups + 2 * g] / n;
+            const double var = stats[(size_t)b * 2 * groups + 2 * g + 1] / n - mu * mu;
+            mr[g] = make_float2((float)mu, (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps)));
+        }
+        __syncthreads();
+    }
+    const size_t total = (size_t)(OH + 2) * (OW + 2) * c8n;
+    const float sh = (float)H / OH, sw = (float)W / OW;
+    const float* lb = lat + (size_t)b * OH * OW * C;
+    const float* sb = cur + (size_t)b * cur_sample_stride;
+    bf16* db = dst + (size_t)b * (OH + 2) * (OW + 2) * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % c8n);
+        const size_t p = i / c8n;
+        const int px = (int)(p % (OW + 2)), py = (int)(p / (OW + 2));
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (py >= 1 && py <= OH && px >= 1 && px <= OW) {
+            const int oy = py - 1, ox = px - 1, c0 = c8 * 8;
+            const float4* q = reinterpret_cast<const float4*>(lb + ((size_t)oy * OW + ox) * C + c0);
+            const float4 l0 = __ldcs(q), l1 = __ldcs(q + 1);
+            v[0] = l0.x; v[1] = l0.y; v[2] = l0.z; v[3] = l0.w; v[4] = l1.x; v[5] = l1.y; v[6] = l1.z; v[7] = l1.w;
+            if (stats) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 m = mr[(c0 + j) / cg];
+                    v[j] = (v[j] - m.x) * m.y * gm[j] + bt[j];
+                }
+            }
+            const float fy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+            const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+            const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+            const float ly = fy - y0, lx = fx - x0;
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+            const float4* pa = reinterpret_cast<const float4*>(sb + ((size_t)y0 * W + x0) * C + c0);
+            const float4* pb = reinterpret_cast<const float4*>(sb + ((size_t)y0 * W + x1) * C + c0);
+            const float4* pc = reinterpret_cast<const float4*>(sb + ((size_t)y1 * W + x0) * C + c0);
+            const float4* pd = reinterpret_cast<const float4*>(sb + ((size_t)y1 * W + x1) * C + c0);
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+                const float4 a = __ldg(pa + hq), bq = __ldg(pb + hq), c = __ldg(pc + hq), d = __ldg(pd + hq);
+                v[4 * hq + 0] += w00 * a.x + w01 * bq.x + w10 * c.x + w11 * d.x;
+                v[4 * hq + 1] += w00 * a.y + w01 * bq.y + w10 * c.y + w11 * d.y;
+                v[4 * hq + 2] += w00 * a.z + w01 * bq.z + w10 * c.z + w11 * d.z;
+                v[4 * hq + 3] += w00 * a.w + w01 * bq.w + w10 * c.w + w11 * d.w;
+            }
+        }
+        store8(db + p * C + c8 * 8, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+    }
+}
+
 // out = T(a + b[i mod b_n]): a positional embedding shared by every sample of the batch
 template <typename T>
 __global__ void add_cast_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, T* __restrict__ out, size_t n4, size_t b_n4) {
@@ -306,6 +371,44 @@ extern "C" int svb_conv3x3_rows(const float* src, const void* weight_bf16, const
         ProfScope prof(PC_OTHER, 0, (double)batch * h * w * cin * 4 + (double)batch * (h + 2) * (w + 2) * cin * 2, s);
         dim3 grid(grid_cap((size_t)(h + 2) * (w + 2) * cin / 8, 256), batch);
         pad_rows_bf16_kernel<<<grid, 256, 0, s>>>(src, (bf16*)padded_ws, h, w, cin);
+        SVB_CHECK_CUDA(cudaGetLastError());
+    }
+    Epilogue ep;
+    ep.bias = bias;
+    ep.out = out; ep.ldo = cout;
+    ep.act = relu ? 2 : 0;
+    return gemm_conv3x3_bf16_tc((const bf16*)padded_ws, (const bf16*)weight_bf16, 9 * cin, batch, h, w, cin, cout, ep, s);
+}
+
+extern "C" int svb_fpn_conv3x3_rows(const float* lateral, const float* gn_gamma, const float* gn_beta, int gn_groups, float gn_eps,
+                                    const float* cur, int64_t cur_sample_stride, int cur_h, int cur_w, const void* weight_bf16, const float* bias,
+                                    float* out, void* padded_ws, double* stats_ws, int batch, int h, int w, int cin, int cout, int relu,
+                                    svb_stream_t stream) {
+    SVB_REQUIRE(lateral && cur && weight_bf16 && out && padded_ws && batch > 0 && h > 0 && w > 0 && cur_h > 0 && cur_w > 0 && cin % 8 == 0,
+                "svb_fpn_conv3x3_rows: bad argument");
+    SVB_REQUIRE(((reinterpret_cast<uintptr_t>(lateral) | reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(padded_ws)) & 15) == 0,
+                "svb_fpn_conv3x3_rows: 16-byte aligned operands");
+    if (cur_sample_stride <= 0) cur_sample_stride = (int64_t)cur_h * cur_w * cin;
+    SVB_REQUIRE(cur_sample_stride % 4 == 0, "svb_fpn_conv3x3_rows: sample stride must be a multiple of 4 elements");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool norm = gn_gamma != nullptr;
+    if (norm) {
+        SVB_REQUIRE(gn_beta && stats_ws && gn_groups > 0 && cin % gn_groups == 0 && (cin / gn_groups) % 2 == 0 && gn_groups <= 1024,
+                    "svb_fpn_conv3x3_rows: channels %d / groups %d unsupported", cin, gn_groups);
+        ProfScope prof(PC_NORM, 0, (double)batch * h * w * cin * 4, s);
+        SVB_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * gn_groups * batch, s));
+        const int rpb = 64, pixels = h * w;
+        dim3 g1((pixels + rpb - 1) / rpb, batch);
+        const int threads = cin / 4 >= 256 ? 256 : (cin / 4 >= 32 ? ((cin / 4 + 31) / 32) * 32 : 32);
+        gn_rows_stats_kernel<<<g1, threads, sizeof(double) * 2 * gn_groups, s>>>(lateral, (long long)pixels * cin, pixels, cin, gn_groups, rpb, stats_ws);
+        SVB_CHECK_CUDA(cudaGetLastError());
+    }
+    {
+        ProfScope prof(PC_OTHER, 0, (double)batch * h * w * cin * 4 + (double)batch * cur_h * cur_w * cin * 4 + (double)batch * (h + 2) * (w + 2) * cin * 2, s);
+        dim3 grid(grid_cap((size_t)(h + 2) * (w + 2) * cin / 8, 256), batch);
+        fpn_gn_up_pad_kernel<<<grid, 256, sizeof(float2) * (norm ? gn_groups : 1), s>>>(lateral, gn_gamma, gn_beta, norm ? stats_ws : nullptr, gn_groups,
+                                                                                      gn_eps, cur, cur_sample_stride, cur_h, cur_w, (bf16*)padded_ws,
+                                                                                      h, w, cin);
         SVB_CHECK_CUDA(cudaGetLastError());
     }
     Epilogue ep;

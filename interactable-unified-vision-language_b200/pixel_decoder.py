@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 from torch import nn
@@ -87,6 +88,7 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self._laterals, self._outputs = self._laterals[::-1], self._outputs[::-1]              # :291-292, top-down order
         self.conv_dim = conv_dim
         self.implicit_conv = True          # bf16 path: 3x3 output_conv as an implicit GEMM (False: im2col operand + GEMM, for A/B runs)
+        self.fuse_fpn = os.environ.get("SVB_FPN_FUSE", "1") != "0"   # bf16 path: the passes around output_conv fused (False: one kernel per reference op, A/B)
         self._cache_sig, self._pos_cache = None, {}
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -217,30 +219,51 @@ class MSDeformAttnPixelDecoder(nn.Module):
                 wl, bl, nl = self._lat[idx]
                 fpn = self._linear(mode, rows, wl, bl, torch.empty(B * h * w, C, dtype=torch.float32, device=dev))      # lateral_conv
                 del rows
-                if nl is not None:
-                    self._groupnorm(fpn, 0, nl, fpn, 0, B, h * w, C, False, ws)
-                cabi.check(lib.svb_upsample_add_rows(cur.data_ptr(), cur_stride, fpn.data_ptr(), B, cur_shape[0], cur_shape[1], h, w, C, st()),
-                           "svb_upsample_add_rows")                                             # cur_fpn + F.interpolate(out[-1], ...) (:348)
                 wo, bo, no = self._out[idx]
                 conv = torch.empty(B * h * w, C, dtype=torch.float32, device=dev)
-                if adt == torch.bfloat16 and w % 128 == 0 and C % 64 == 0 and self.implicit_conv:
-                    # output_conv (3x3) as an implicit GEMM: the A tiles are row-shifted boxes of a zero-padded bf16 copy of the map
-                    # (68 MB per image at 256^2 x 512) instead of a 604 MB im2col operand
+                implicit = adt == torch.bfloat16 and w % 128 == 0 and C % 64 == 0 and self.implicit_conv
+                if implicit and self.fuse_fpn:
+                    # GroupNorm apply + `cur_fpn + F.interpolate(out[-1], ...)` (:348) + the zero-padded bf16 operand of the implicit-GEMM
+                    # output_conv in ONE pass over the level (the two fp32 maps in between never exist)
                     pad = torch.empty(B * (h + 2) * (w + 2), C, dtype=torch.bfloat16, device=dev)
-                    cabi.check(lib.svb_conv3x3_rows(fpn.data_ptr(), wo.data_ptr(), bo.data_ptr() if bo is not None else None, conv.data_ptr(),
-                                                    pad.data_ptr(), B, h, w, C, C, 1 if (no is None) else 0, st()), "svb_conv3x3_rows")
+                    gwl, gbl, ggl, gel = nl if nl is not None else (None, None, 0, 0.0)
+                    cabi.check(lib.svb_fpn_conv3x3_rows(fpn.data_ptr(), gwl.data_ptr() if gwl is not None else None,
+                                                        gbl.data_ptr() if gbl is not None else None, ggl, gel, cur.data_ptr(), cur_stride,
+                                                        cur_shape[0], cur_shape[1], wo.data_ptr(), bo.data_ptr() if bo is not None else None,
+                                                        conv.data_ptr(), pad.data_ptr(), ws.data_ptr(), B, h, w, C, C, 1 if (no is None) else 0, st()),
+                               "svb_fpn_conv3x3_rows")
                     del pad
                 else:
-                    per = max(1, min(B, (1 << 31) // (h * w * 9 * C * (2 if adt == torch.bfloat16 else 4))))     # images per im2col pass (<= 2 GB)
-                    col = torch.empty(per * h * w, 9 * C, dtype=adt, device=dev)
-                    for b0 in range(0, B, per):
-                        nb = min(per, B - b0)
-                        cabi.check(lib.svb_im2col3x3_rows(fpn[b0 * h * w:].data_ptr(), col.data_ptr(), _odt(adt), nb, h, w, C, st()), "svb_im2col3x3_rows")
-                        self._linear(mode, col[:nb * h * w], wo, bo, conv[b0 * h * w:(b0 + nb) * h * w],
-                                     act=2 if (no is None) else 0)                              # output_conv (3x3)
-                    del col
+                    if nl is not None:
+                        self._groupnorm(fpn, 0, nl, fpn, 0, B, h * w, C, False, ws)
+                    cabi.check(lib.svb_upsample_add_rows(cur.data_ptr(), cur_stride, fpn.data_ptr(), B, cur_shape[0], cur_shape[1], h, w, C, st()),
+                               "svb_upsample_add_rows")                                         # cur_fpn + F.interpolate(out[-1], ...) (:348)
+                    if implicit:
+                        # output_conv (3x3) as an implicit GEMM: the A tiles are row-shifted boxes of a zero-padded bf16 copy of the map
+                        # (68 MB per image at 256^2 x 512) instead of a 604 MB im2col operand
+                        pad = torch.empty(B * (h + 2) * (w + 2), C, dtype=torch.bfloat16, device=dev)
+                        cabi.check(lib.svb_conv3x3_rows(fpn.data_ptr(), wo.data_ptr(), bo.data_ptr() if bo is not None else None, conv.data_ptr(),
+                                                        pad.data_ptr(), B, h, w, C, C, 1 if (no is None) else 0, st()), "svb_conv3x3_rows")
+                        del pad
+                    else:
+                        per = max(1, min(B, (1 << 31) // (h * w * 9 * C * (2 if adt == torch.bfloat16 else 4))))     # images per im2col pass (<= 2 GB)
+                        col = torch.empty(per * h * w, 9 * C, dtype=adt, device=dev)
+                        for b0 in range(0, B, per):
+                            nb = min(per, B - b0)
+                            cabi.check(lib.svb_im2col3x3_rows(fpn[b0 * h * w:].data_ptr(), col.data_ptr(), _odt(adt), nb, h, w, C, st()), "svb_im2col3x3_rows")
+                            self._linear(mode, col[:nb * h * w], wo, bo, conv[b0 * h * w:(b0 + nb) * h * w],
+                                         act=2 if (no is None) else 0)                          # output_conv (3x3)
+                        del col
+                del fpn
+                last_lvl = idx + 1 == self.num_fpn_levels
+                cur_b = None
                 if no is not None:
-                    self._groupnorm(conv, 0, no, conv, 0, B, h * w, C, True, ws)               # norm + F.relu
+                    if last_lvl and adt == torch.bfloat16 and self.fuse_fpn:
+                        # the last level's map is read by the mask_features convolution only: norm + F.relu write its bf16 operand directly
+                        cur_b = torch.empty(B * h * w, C, dtype=adt, device=dev)
+                        self._groupnorm(conv, 0, no, cur_b, 0, B, h * w, C, True, ws)
+                    else:
+                        self._groupnorm(conv, 0, no, conv, 0, B, h * w, C, True, ws)           # norm + F.relu
                 cur_shape, cur, cur_stride = (h, w), conv, h * w * C
             # ---- outputs (:353-359) ----
             h, w = cur_shape
@@ -249,9 +272,12 @@ class MSDeformAttnPixelDecoder(nn.Module):
             if cur_a is None:        # no FPN level: the finest transformer level itself, gathered densely
                 cur_a = torch.empty(B * h * w, C, dtype=torch.float32, device=dev)
                 cur_a.view(B, h * w, C).copy_(y.view(B, S, C)[:, starts[-1]:starts[-1] + h * w])
-            a_in = cur_a if adt == torch.float32 else torch.empty(B * h * w, C, dtype=adt, device=dev)
-            if adt != torch.float32:
-                cabi.check(lib.svb_add_cast(cur_a.data_ptr(), None, a_in.data_ptr(), _odt(adt), cur_a.numel(), st()), "svb_add_cast")
+            if self.num_fpn_levels > 0 and cur_b is not None:
+                a_in = cur_b
+            else:
+                a_in = cur_a if adt == torch.float32 else torch.empty(B * h * w, C, dtype=adt, device=dev)
+                if adt != torch.float32:
+                    cabi.check(lib.svb_add_cast(cur_a.data_ptr(), None, a_in.data_ptr(), _odt(adt), cur_a.numel(), st()), "svb_add_cast")
             mrows = self._linear(mode, a_in, wm, bm, torch.empty(B * h * w, self.mask_dim, dtype=adt if rows_out else torch.float32, device=dev))
             mask = None
             if not rows_out:
