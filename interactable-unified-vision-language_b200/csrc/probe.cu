@@ -242,12 +242,31 @@ __global__ void __launch_bounds__(512, 1) probe_tmem_rate_kernel(int nwarps, int
                 ptx::tmem_ld_wait_dep(vb);
                 acc ^= va[r & 31] ^ vb[r & 31];
             }
-        } else {
+        } else if (mode == 2) {
             for (int r = 0; r < reps; ++r) {
                 va[0] = r;
                 ptx::tmem_st_x32(lane_base + ((warp >> 2) * 128 + (r * 32)) % 480, va);
             }
             ptx::tmem_st_wait();
+        } else {
+            // the other load shapes, 4 KB per instruction as well (32 registers per thread): 16 lanes x 256 / 128 / 64 bits, repeated
+            // along the columns 8 / 16 / 32 times — is the 56 B/clk of the 32x32b shape a property of the shape or of the port?
+#define SVB_LD_SHAPE(SHAPE)                                                                                                             \
+            for (int r = 0; r < reps; ++r) {                                                                                           \
+                asm volatile("tcgen05.ld.sync.aligned." SHAPE ".b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "    \
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                  \
+                             : "=r"(va[0]), "=r"(va[1]), "=r"(va[2]), "=r"(va[3]), "=r"(va[4]), "=r"(va[5]), "=r"(va[6]), "=r"(va[7]),    \
+                               "=r"(va[8]), "=r"(va[9]), "=r"(va[10]), "=r"(va[11]), "=r"(va[12]), "=r"(va[13]), "=r"(va[14]), "=r"(va[15]), \
+                               "=r"(va[16]), "=r"(va[17]), "=r"(va[18]), "=r"(va[19]), "=r"(va[20]), "=r"(va[21]), "=r"(va[22]), "=r"(va[23]), \
+                               "=r"(va[24]), "=r"(va[25]), "=r"(va[26]), "=r"(va[27]), "=r"(va[28]), "=r"(va[29]), "=r"(va[30]), "=r"(va[31]) \
+                             : "r"(lane_base + ((r * 64) & 255)) : "memory");                                                          \
+                ptx::tmem_ld_wait_dep(va);                                                                                              \
+                acc ^= va[r & 31];                                                                                                      \
+            }
+            if (mode == 3) { SVB_LD_SHAPE("16x256b.x8") }
+            else if (mode == 4) { SVB_LD_SHAPE("16x128b.x16") }
+            else { SVB_LD_SHAPE("16x64b.x32") }
+#undef SVB_LD_SHAPE
         }
         const long long t1 = clock64();
         if ((tid & 31) == 0) out[warp] = (t1 - t0) + (acc == 0x12345678u ? 1 : 0);
@@ -310,7 +329,7 @@ extern "C" int svb_probe_mma_rate(int variant, int reps, int alt_d, long long* c
 }
 
 extern "C" int svb_probe_tmem_rate(int nwarps, int reps, int mode, long long* cycles_out, svb_stream_t stream) {
-    SVB_REQUIRE(cycles_out && nwarps >= 1 && nwarps <= 16 && reps > 0 && reps % 2 == 0 && mode >= 0 && mode <= 2, "probe_tmem_rate: bad argument");
+    SVB_REQUIRE(cycles_out && nwarps >= 1 && nwarps <= 16 && reps > 0 && reps % 2 == 0 && mode >= 0 && mode <= 5, "probe_tmem_rate: bad argument");
     probe_tmem_rate_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(nwarps, reps, mode, cycles_out);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;

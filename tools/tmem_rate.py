@@ -6,7 +6,7 @@ from iuvl_b200 import cabi
 lib = cabi.probe_lib(); st = cabi.stream_ptr
 out = torch.zeros(16, dtype=torch.int64, device="cuda")
 reps = 2000
-for mode, name in ((0, "ld, one in flight"), (1, "ld, two in flight"), (2, "st")):
+for mode, name in ((0, "ld, one in flight"), (1, "ld, two in flight"), (2, "st"), (3, "ld 16x256b.x8"), (4, "ld 16x128b.x16"), (5, "ld 16x64b.x32")):
     for nw in (1, 2, 4, 8, 12, 16):
         out.zero_()
         cabi.check_probe(lib.svb_probe_tmem_rate(nw, reps, mode, out.data_ptr(), st()), "tmem_rate")
