@@ -118,6 +118,9 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int pair = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int row0 = b * T + pair * 256;
+    // the proj GEMM behind this kernel is launched with programmatic stream serialization: let its CTAs become resident as ours exit
+    // (it waits for this grid's completion before it reads `out`)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int colq = head * HD, colk = D + head * HD, colv = 2 * D + head * HD;
 
     if (warp == 8 && lane == 0) {
@@ -149,6 +152,7 @@ attn_global2_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // dependent launch: the set-up above overlapped the qkv GEMM's tail
 
     if (warp == 8) {
         // ===================== TMA producer (as in attn_global_kernel) =====================
@@ -523,6 +527,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::B_COUNT);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;    // provably warp-uniform
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // (see attn_global2_kernel: the proj GEMM is a dependent launch)
 
     if (warp == 8 && lane == 0) {
         ptx::prefetch_tmap(&maps.kv);
@@ -555,6 +560,7 @@ attn_window_persistent_kernel(const __grid_constant__ WinPMaps maps, int D, int 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // dependent launch: the set-up above overlapped the previous kernel's tail
 
     // item -> (image, window, head); query tile 1 (window rows 9..13) is entirely padding in the last window row
     auto decode = [&](int item, int& b, int& wy, int& wx, int& head) {
@@ -848,6 +854,9 @@ fill_pad_rows_kernel(bf16* __restrict__ qkv, const float* __restrict__ bias, int
         brow[c8] = u;
     }
     __syncthreads();
+    // dependent launch (the bias row above overlapped the qkv GEMM's tail); the attention kernel behind this one is one as well
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int npad = gph * gpw - gh * gw, strip = gh * (gpw - gw);
     const int rows = B * npad;
     const int lane = threadIdx.x & 31;
@@ -903,7 +912,13 @@ int launch_global_nst(const AttnTcParams& p, cudaStream_t stream) {
     dim3 grid(T / 256, p.heads, p.batch);
     auto launch = [&](auto kern, long long* clocks) -> int {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        kern<<<grid, 352, C::SMEM, stream>>>(m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, clocks, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(352); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled(2) ? 1 : 0;
+        SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], (const bf16*)p.qkv, p.out, D, T, scale_log2, clocks, 1));
         return 0;
     };
     const int k8 = exp2_poly(false);
@@ -966,7 +981,13 @@ int launch_window_persistent(const AttnTcParams& p, cudaStream_t stream) {
     auto launch = [&](auto kern, long long* clocks) -> int {
         SVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         static const int l2_ahead = [] { const char* e = getenv("SVB_ATTNW_L2AHEAD"); return e ? atoi(e) : 1; }();
-        kern<<<grid, 384, C::SMEM, stream>>>(wm, D, gh, nwy, nwx, p.heads, items, scale_log2, clocks, l2_ahead);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled(2) ? 1 : 0;
+        SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, wm, D, gh, nwy, nwx, p.heads, items, scale_log2, clocks, l2_ahead));
         return 0;
     };
     const int k8 = exp2_poly(true);
@@ -1044,8 +1065,13 @@ int fill_pad_rows(bf16* qkv, const float* bias, int B, int gh, int gw, int gph, 
     const int blocks = (int)std::min<long>((rows + 7) / 8, 148 * 8);
     ProfScope prof(PC_OTHER, 0.0, (double)total * 16.0, stream);
     SVB_REQUIRE(ld * 2 <= 48 * 1024, "fill_pad_rows: row length %d too large", ld);
-    fill_pad_rows_kernel<<<blocks, 256, (size_t)ld * 2, stream>>>(qkv, bias, B, gh, gw, gph, gpw, ld);
-    SVB_CHECK_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = (size_t)ld * 2; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled(4) ? 1 : 0;
+    SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fill_pad_rows_kernel, qkv, bias, B, gh, gw, gph, gpw, ld));
     return 0;
 }
 

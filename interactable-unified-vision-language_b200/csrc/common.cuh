@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace svb {
 
@@ -186,6 +187,16 @@ enum ProfCat { PC_GEMM = 0, PC_ATTN_WIN = 1, PC_ATTN_GLOBAL = 2, PC_NORM = 3, PC
 void count_launch(int n = 1);
 void prof_begin(int cat, double flops, double bytes, cudaStream_t st);
 void prof_end(cudaStream_t st);
+// SVB_PDL (bit mask, A/B): which kernels of the encoder are launched with programmatic stream serialization (their set-up overlaps the
+// previous kernel's tail; griddepcontrol.wait orders every memory access behind it): 1 the GEMMs, 2 the attention kernels, 4 the
+// pad-row kernel; 0 = plain stream order.  Measured inside the ViT-H step (64 images, alternating runs on one box, profiles/r02_pdl):
+// 0: 347.8 / 349.0 ms, 1: 345.4 / 346.8, 3: 345.2 / 346.3, 7: 349.5 / 348.9 (the small pad-row kernel as a dependent launch gives
+// the whole gain back) -> default 3.
+inline bool pdl_enabled(int which = 1) {
+    static const int v = [] { const char* e = getenv("SVB_PDL"); return e ? atoi(e) : 3; }();
+    return (v & which) != 0;
+}
+
 struct ProfScope {
     cudaStream_t st;
     ProfScope(int cat, double flops, double bytes, cudaStream_t s, int launches = 1) : st(s) {

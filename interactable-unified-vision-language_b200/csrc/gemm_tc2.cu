@@ -619,6 +619,11 @@ gemm_tc2s_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: this grid may have been made resident while the previous kernel of the stream was still
+    // draining (its CTAs' set-up above overlaps that tail); everything below reads what that kernel wrote.  The trigger lets the
+    // NEXT kernel do the same with this one (it still waits for this grid's completion before it touches memory).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -1106,10 +1111,14 @@ int launch_gemm2s(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMa
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    // SVB_PDL=0: plain stream order (A/B).  Default: programmatic stream serialization — the grid is scheduled as soon as the previous
+    // kernel's CTAs have triggered / exited and blocks in griddepcontrol.wait until that kernel has completed
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const double out_bytes = (MODE == EPI_BF16 ? 2.0 : (MODE == EPI_F32 ? 4.0 : (MODE == EPI_F32_REDADD ? 8.0 : 10.0))) * M * N;
     ProfScope prof(PC_GEMM, 2.0 * M * N * K, 2.0 * ((double)M * K + (double)N * K) + out_bytes, stream);
     SVB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mw, mo, mo2, M, N, K, ep, dbg));
