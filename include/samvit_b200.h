@@ -104,6 +104,11 @@ int svb_stage_images_u8(const uint8_t* const* images, const int* heights, const 
  * Host buffers should be pinned for full PCIe bandwidth. */
 int svb_encoder_forward_host(svb_encoder_t* enc, const float* x_host, int batch, void* res2_host, void* res3_host,
                              void* res4_host, void* res5_host, int out_dtype, int mode, int chunk);
+/* The passes (images per pass through the kernels) svb_encoder_forward (host_path = 0) / svb_encoder_forward_host (host_path = 1) split
+ * `batch` into for a given `chunk`: a dynamic programme over the wave quantisation of the block GEMMs; the host path also charges the
+ * upload of the first pass and the download of the last one (the only copies its pipeline exposes).  Writes the sizes to passes[] and
+ * returns 1000 + their number (error codes stay below 1000). */
+int svb_encoder_pass_schedule(svb_encoder_t* e, int batch, int chunk, int host_path, int out_dtype, int* passes, int max_passes);
 
 /* Token stream (B*T, D) fp32 after the patch embedding (block = -1) or after block `block` of the LAST forward's
  * last chunk, copied into `dst` (device).  Only valid when taps were enabled; used by the parity tests to bisect. */

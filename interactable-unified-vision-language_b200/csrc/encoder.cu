@@ -593,6 +593,65 @@ size_t out_elems_per_image(const svb_encoder* e, int k, int img_h = 0, int img_w
     return hw * e->cfg.fpn_dims[k];
 }
 
+// The host path (svb_encoder_forward_host) pipelines H2D -> compute -> D2H over the passes, so only the FIRST pass's upload and the
+// LAST pass's download are exposed.  Same dynamic programme as chunk_schedule with those two terms added (one cost unit = one
+// 256 x 256 tile over one unit of K on a CTA pair, ~7.45 ns at 1.3 PFLOP/s; the four block GEMMs x depth x 1.4 for the rest of the
+// block; PCIe at ~50 GB/s): ViT-H, 64 images: 5 x 12 + 4 instead of 16 + 4 x 12 (measured end to end 175.1 -> 175.9 images/s); ViT-B,
+// 16 images: 4 + 8 + 4 instead of one pass, whose copies nothing overlapped (511.9 -> 664.8 images/s).  SVB_HOST_SCHEDULE=0 keeps the
+// device schedule (A/B).
+std::vector<int> chunk_schedule_host(const svb_encoder* e, int batch, int max_chunk, double in_bytes_per_image, double out_bytes_per_image) {
+    static const int on = [] { const char* v = getenv("SVB_HOST_SCHEDULE"); return v ? atoi(v) : 1; }();
+    static const int fixed = [] { const char* v = getenv("SVB_FIXED_CHUNKS"); return v ? atoi(v) : 0; }();
+    if (!on || fixed || batch < 2) return chunk_schedule(e, batch, max_chunk);
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long pairs = std::max(1, sms / 2);
+    const long D = e->D, mlp = e->mlp;
+    const long shp[4][2] = {{3 * D, D}, {D, D}, {mlp, D}, {D, mlp}};
+    auto cost = [&](int B) {
+        double c = 0;
+        for (auto& nk : shp) {
+            const long tiles = (((long)B * e->T + 255) / 256) * ((nk[0] + 255) / 256);
+            c += (double)nk[1] * (double)((tiles + pairs - 1) / pairs);
+        }
+        return c;
+    };
+    const int cmax = std::min(max_chunk, batch);
+    const int cmin = std::min(4, cmax);                                // first / last pass: at least 4 images where the chunk allows (smaller passes leave SMs idle in the attention kernels)
+    const double unit_s = 7.45e-9 * (double)e->depth * 1.4;            // seconds per cost unit (whole pass)
+    const double per_pass = 6.0 * e->depth * 4e-6 / unit_s;            // ~6 launches per block, ~4 us of fill / drain each
+    const double h2d_units = in_bytes_per_image / 50e9 / unit_s, d2h_units = out_bytes_per_image / 50e9 / unit_s;
+    // best[n] = cheapest way to run n images in the MIDDLE of the sequence (no exposure)
+    std::vector<double> best(batch + 1, 1e300);
+    std::vector<int> pick(batch + 1, 0);
+    best[0] = 0;
+    for (int n = 1; n <= batch; ++n)
+        for (int c = 1; c <= std::min(cmax, n); ++c) {
+            const double v = best[n - c] + cost(c) + per_pass;
+            if (v < best[n]) { best[n] = v; pick[n] = c; }
+        }
+    double top = 1e300;
+    int bf = 0, bl = 0;
+    for (int f = cmin; f <= cmax; ++f)
+        for (int l = 0; l <= cmax && f + l <= batch; ++l) {           // l = 0: a single pass (first == last)
+            if (l == 0 ? f != batch : l < cmin) continue;
+            if (cmin == 4 && ((f % 4 && f != batch) || l % 4)) continue;      // end passes in whole groups of 4 images (the sizes the parity tests and the A/B runs cover)
+            const int mid = batch - f - l;
+            const double v = cost(f) + per_pass + (l ? cost(l) + per_pass : 0.0) + best[mid] + h2d_units * f + d2h_units * (l ? l : f);
+            if (v < top) { top = v; bf = f; bl = l; }
+        }
+    if (bf <= 0) return chunk_schedule(e, batch, max_chunk);           // (no candidate: cannot happen for batch >= 1, chunk >= 1)
+    std::vector<int> out;
+    out.push_back(bf);
+    std::vector<int> midv;
+    for (int n = batch - bf - bl; n > 0; n -= pick[n]) midv.push_back(pick[n]);
+    std::sort(midv.begin(), midv.end(), [](int a, int b) { return a > b; });
+    out.insert(out.end(), midv.begin(), midv.end());
+    if (bl) out.push_back(bl);
+    return out;
+}
+
 }  // namespace
 
 extern "C" {
@@ -973,7 +1032,9 @@ int svb_encoder_forward_host(svb_encoder_t* e, const float* x_host, int batch, v
     const Buffers bf = plan(e, chunk, mode, hp.ws);
     char* res[4] = {(char*)res2_host, (char*)res3_host, (char*)res4_host, (char*)res5_host};
     int it = 0, b0 = 0;
-    for (int B : chunk_schedule(e, batch, chunk)) {
+    double out_bytes_per_image = 0;
+    for (int k = 0; k < 4; ++k) out_bytes_per_image += (double)osz * out_elems_per_image(e, k);
+    for (int B : chunk_schedule_host(e, batch, chunk, sizeof(float) * (double)in_per_img, out_bytes_per_image)) {
         const int s = it & 1;
         // H2D of this chunk may start once the compute that last read xin[s] (two chunks ago) has finished
         if (it >= 2) SVB_CHECK_CUDA(cudaStreamWaitEvent(hp.s_in, hp.comp_done[s], 0));
@@ -997,6 +1058,22 @@ int svb_encoder_forward_host(svb_encoder_t* e, const float* x_host, int batch, v
     SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_comp));
     SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_out));
     return 0;
+}
+
+int svb_encoder_pass_schedule(svb_encoder_t* e, int batch, int chunk, int host_path, int out_dtype, int* passes, int max_passes) {
+    SVB_REQUIRE(e && passes && batch > 0 && chunk > 0 && max_passes > 0, "svb_encoder_pass_schedule: bad argument");
+    std::vector<int> sch;
+    if (host_path) {
+        const size_t osz = out_dtype == SVB_DTYPE_BF16 ? 2 : 4;
+        double out_bytes = 0;
+        for (int k = 0; k < 4; ++k) out_bytes += (double)osz * out_elems_per_image(e, k);
+        sch = chunk_schedule_host(e, batch, std::min(chunk, batch), sizeof(float) * (double)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size, out_bytes);
+    } else {
+        sch = chunk_schedule(e, batch, chunk);
+    }
+    SVB_REQUIRE((int)sch.size() <= max_passes, "svb_encoder_pass_schedule: %d passes do not fit %d slots", (int)sch.size(), max_passes);
+    for (size_t i = 0; i < sch.size(); ++i) passes[i] = sch[i];
+    return (int)sch.size() + 1000;        // 1000 + number of passes (0 would read as "ok, nothing written"; errors are 1..)
 }
 
 int svb_encoder_enable_taps(svb_encoder_t* e, int enable) {

@@ -380,6 +380,20 @@ class ImageEncoderViT(nn.Module):
                 cabi.stream_ptr()), "svb_encoder_forward_u8")
         return {"res2": outs[0], "res3": outs[1], "res4": outs[2], "res5": outs[3]}
 
+    def pass_schedule(self, batch: int, host_path: bool = False):
+        """Images per pass through the kernels for a batch of ``batch`` images (``max_chunk`` as set): what ``forward`` (device tensors) or
+        ``forward_host`` (host tensors: the first upload / last download are charged too) will run."""
+        import ctypes
+        device = next(self.parameters()).device
+        with torch.cuda.device(device):
+            self._ensure_handle(device)
+            buf = (ctypes.c_int * 256)()
+            odt = cabi.DTYPE_BF16 if self.out_dtype == torch.bfloat16 else cabi.DTYPE_F32
+            rc = cabi.lib().svb_encoder_pass_schedule(self._handle, int(batch), int(self.max_chunk), int(bool(host_path)), odt, buf, 256)
+            if rc < 1000:
+                cabi.check(rc, "svb_encoder_pass_schedule")
+            return [int(buf[i]) for i in range(rc - 1000)]
+
     def forward_host(self, x: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None,
                      device: Optional[torch.device] = None) -> Dict[str, torch.Tensor]:
         """End-to-end call with HOST tensors: ``x`` (B,3,S,S) fp32 on the CPU (pinned for full PCIe speed); returns pinned

@@ -402,3 +402,21 @@ def test_errors_are_loud():
         enc(x[:1].to(DEV))                       # grad enabled + requires_grad params
     with torch.no_grad(), pytest.raises(NotImplementedError):
         enc(torch.zeros(1, 3, 1024, 1000, device=DEV))        # sides must be multiples of 32 patches
+
+
+def test_pass_schedules_cover_the_batch():
+    """The pass schedules of the device and the host entry points: every image once, no pass above max_chunk; the host schedule keeps
+    its first and last pass (the exposed upload / download) no larger than the device schedule's largest pass."""
+    cfg = ib.PRESETS["vit_h"]
+    enc = build_encoder(cfg).to(DEV)                      # (no weights needed: the schedule depends on the geometry only)
+    enc.out_dtype = torch.bfloat16
+    for chunk in (8, 16):
+        enc.max_chunk = chunk
+        for batch in (1, 3, 8, 13, 16, 33, 64):
+            dev_s, host_s = enc.pass_schedule(batch), enc.pass_schedule(batch, host_path=True)
+            for sch in (dev_s, host_s):
+                assert sum(sch) == batch and all(1 <= c <= chunk for c in sch), (batch, chunk, sch)
+            assert host_s[0] <= max(dev_s) and host_s[-1] <= max(dev_s)
+    enc.max_chunk = 16
+    assert enc.pass_schedule(64) == [16, 12, 12, 12, 12]
+    print("host schedule of 64 ViT-H images:", enc.pass_schedule(64, host_path=True))
