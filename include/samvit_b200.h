@@ -293,6 +293,11 @@ int svb_mask_threshold_heads(const float* v, void* out_bool, int batch, int head
  * (The class-embedding projection, the similarity against the text embeddings and the box MLP are svb_linear calls.) */
 int svb_l2_normalize_rows(const float* x, void* out, int out_dtype, int rows, int dim, float eps, float scale, svb_stream_t stream);
 
+/* svb_mask_threshold_heads with the first statement of the next decoder layer folded in (xdecoder.py:467 + :267): v (batch, queries,
+ * keys) logits -> out (batch * heads, queries, keys) bool = sigmoid(v) < 0.5 repeated over the heads, except that a row whose EVERY key
+ * would be masked is written all-False (`attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False`). */
+int svb_mask_threshold_heads_clear(const float* v, void* out_bool, int batch, int heads, int queries, int keys, svb_stream_t stream);
+
 /* ---- scope row N4, second slice: the attention core of `CrossAttentionLayer.forward_post` (modeling/interface/modules.py:95-106), i.e.
  * nn.MultiheadAttention's softmax((q / sqrt(d)) k^T + mask) v for `queries` <= 128 tokens over `keys` image positions.  q (queries, batch,
  * heads * 64), k / v (keys, batch, heads * 64) sequence-first as the reference passes them, element type `dtype`; mask_bool

@@ -80,6 +80,7 @@ SYMBOLS = {
     "svb_linear_nt": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "svb_fpn_conv3x3_rows": (_i, [_vp, _vp, _vp, _i, _f, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "svb_encoder_pass_schedule": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
+    "svb_mask_threshold_heads_clear": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "svb_layernorm_post": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _f, _vp]),
     "svb_cls_token_recompute": (_i, [_vp, _i, _i, _i, _vp]),
     "svb_resize_bicubic_aa": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -199,6 +199,41 @@ __global__ void mask_threshold_kernel(const float* __restrict__ v, uint8_t* __re
     }
 }
 
+// The same with xdecoder.py:267 folded in (`attn_mask[torch.where(attn_mask.sum(-1) == attn_mask.shape[-1])] = False` at the top of the
+// next decoder layer): one block per (image, query) row; a row whose every key is masked is written as all-False.  The threshold
+// kernel above + svb_mask_clear_full_rows write the 8 per-head copies and read them back; here the row's logits are read twice (the
+// second time out of L1 / L2) and the copies written once.
+__global__ void __launch_bounds__(256)
+mask_threshold_clear_kernel(const float* __restrict__ v, uint8_t* __restrict__ out, int heads, int queries, int keys) {
+    __shared__ int any_open;
+    const int b = blockIdx.y, q = blockIdx.x;
+    const float* row = v + ((size_t)b * queries + q) * keys;
+    if (threadIdx.x == 0) any_open = 0;
+    __syncthreads();
+    int open = 0;
+    for (int i = threadIdx.x; i < keys; i += blockDim.x) open |= (__ldg(row + i) < 0.f) ? 0 : 1;      // (NaN counts as open, as `<` does)
+    if (__any_sync(0xffffffffu, open) && (threadIdx.x & 31) == 0) atomicOr(&any_open, 1);
+    __syncthreads();
+    const bool full = any_open == 0;
+    const bool vec = (keys & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    if (vec) {
+        for (int i = threadIdx.x * 16; i < keys; i += blockDim.x * 16) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (!full) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j >> 2] |= (uint32_t)(__ldg(row + i + j) < 0.f ? 1 : 0) << (8 * (j & 3));
+            }
+            const uint4 u = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int h = 0; h < heads; ++h) *reinterpret_cast<uint4*>(out + (((size_t)b * heads + h) * queries + q) * keys + i) = u;
+        }
+    } else {
+        for (int i = threadIdx.x; i < keys; i += blockDim.x) {
+            const uint8_t bit = (!full && __ldg(row + i) < 0.f) ? 1 : 0;
+            for (int h = 0; h < heads; ++h) out[(((size_t)b * heads + h) * queries + q) * keys + i] = bit;
+        }
+    }
+}
+
 inline int grid_cap(size_t n, int block) {
     size_t g = (n + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -263,6 +298,16 @@ extern "C" int svb_mask_threshold_heads(const float* v, void* out_bool, int batc
     ProfScope prof(PC_OTHER, 0, (double)batch * per_sample * (4 + heads), s);
     dim3 grid(grid_cap((size_t)per_sample, 256), batch);
     mask_threshold_kernel<<<grid, 256, 0, s>>>(v, (uint8_t*)out_bool, heads, (size_t)per_sample);
+    SVB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int svb_mask_threshold_heads_clear(const float* v, void* out_bool, int batch, int heads, int queries, int keys, svb_stream_t stream) {
+    SVB_REQUIRE(v && out_bool && batch > 0 && heads > 0 && queries > 0 && keys > 0 && batch <= 65535, "svb_mask_threshold_heads_clear: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_OTHER, 0, (double)batch * queries * keys * (4 + heads), s);
+    dim3 grid(queries, batch);
+    mask_threshold_clear_kernel<<<grid, 256, 0, s>>>(v, (uint8_t*)out_bool, heads, queries, keys);
     SVB_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -7,6 +7,8 @@ side of the decoder and are not part of this slice.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -115,8 +117,10 @@ class MaskPredictionHead(nn.Module):
             res["outputs_bbox"] = x.reshape(B, Q, 4)
         return res
 
-    def forward(self, output, mask_features, attn_mask_target_size, rows=None, text_embeddings=None, logit_scale=None):
-        """output (Q, B, C) — the decoder's query states as ``forward_prediction_heads`` receives them; mask_features (B, Cm, H, W) fp32 or
+    def forward(self, output, mask_features, attn_mask_target_size, rows=None, text_embeddings=None, logit_scale=None, clear_full_rows=False):
+        """``clear_full_rows`` (not in the reference's signature): also apply the first statement of the NEXT decoder layer to the
+        attention mask (xdecoder.py:267: rows whose every key is masked are cleared) while it is written.
+        output (Q, B, C) — the decoder's query states as ``forward_prediction_heads`` receives them; mask_features (B, Cm, H, W) fp32 or
         bf16; attn_mask_target_size (h, w)  ->  {"outputs_mask": (B, Q, H, W) fp32, "attn_mask": (B * heads, Q, h * w) bool} and, when the
         head was built with ``dim_proj`` / ``bbox``, "outputs_class" / "outputs_bbox" / "outputs_caption" (see class_box_outputs)."""
         if not output.is_cuda:
@@ -166,8 +170,12 @@ class MaskPredictionHead(nn.Module):
             cabi.check(lib.svb_resize_bicubic_aa(masks.data_ptr(), tmp.data_ptr(), small.data_ptr(), B * Q, H, W, oh, ow, st()),
                        "svb_resize_bicubic_aa")                                                                        # :463
             attn = torch.empty(B * self.num_heads, Q, oh * ow, dtype=torch.bool, device=dev)
-            cabi.check(lib.svb_mask_threshold_heads(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q * oh * ow, st()),
-                       "svb_mask_threshold_heads")                                                                     # :467-470
+            if clear_full_rows:
+                cabi.check(lib.svb_mask_threshold_heads_clear(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q, oh * ow, st()),
+                           "svb_mask_threshold_heads_clear")                                                           # :467-470 + :267
+            else:
+                cabi.check(lib.svb_mask_threshold_heads(small.data_ptr(), attn.data_ptr(), B, self.num_heads, Q * oh * ow, st()),
+                           "svb_mask_threshold_heads")                                                                 # :467-470
         return {"outputs_mask": masks, "attn_mask": attn, "attn_logits": small.view(B, Q, oh, ow), **extra}
 
 
@@ -368,6 +376,7 @@ class XDecoderMaskPath(nn.Module):
         self.num_queries, self.num_heads, self.num_feature_levels = num_queries, nheads, num_levels
         self.level_indexes = list(level_indexes)
         self.num_layers = len(self.level_indexes)
+        self.fuse_mask_clear = os.environ.get("SVB_MASK_CLEAR_FUSE", "1") != "0"      # (0: separate svb_mask_clear_full_rows pass per layer, A/B)
         self.transformer_self_attention_layers = nn.ModuleList(SelfAttentionLayer(hidden_dim, nheads) for _ in range(self.num_layers))
         self.transformer_cross_attention_layers = nn.ModuleList(CrossAttentionLayer(hidden_dim, nheads) for _ in range(self.num_layers))
         self.transformer_ffn_layers = nn.ModuleList(FFNLayer(hidden_dim, dim_feedforward) for _ in range(self.num_layers))
@@ -460,7 +469,8 @@ class XDecoderMaskPath(nn.Module):
             self_mask = self.self_attn_mask.to(dev).repeat(bs * self.num_heads, 1, 1).contiguous()    # :254
             masks, extras = [], []
             mrows = mask_rows if mask_rows is not None else head.mask_rows(mask_features)            # once for the ten prediction-head calls
-            kw = dict(rows=mrows, text_embeddings=text_embeddings, logit_scale=logit_scale)
+            # the clearing of fully masked rows (:267, first statement of every layer) is applied while the mask is written
+            kw = dict(rows=mrows, text_embeddings=text_embeddings, logit_scale=logit_scale, clear_full_rows=self.fuse_mask_clear)
             res = head(output, mask_features, size_list[0], **kw)                                    # :257
             masks.append(res["outputs_mask"])
             extras.append(res)
@@ -468,8 +478,9 @@ class XDecoderMaskPath(nn.Module):
             level_ops = {}                                                                           # operand copies of src[lvl] (+ pos[lvl]), per level
             for i in range(self.num_layers):
                 lvl = self.level_indexes[i]
-                cabi.check(lib.svb_mask_clear_full_rows(attn_mask.data_ptr(), attn_mask.shape[0] * attn_mask.shape[1], attn_mask.shape[2], st()),
-                           "svb_mask_clear_full_rows")                                                # :267
+                if not self.fuse_mask_clear:
+                    cabi.check(lib.svb_mask_clear_full_rows(attn_mask.data_ptr(), attn_mask.shape[0] * attn_mask.shape[1], attn_mask.shape[2], st()),
+                               "svb_mask_clear_full_rows")                                            # :267
                 output, _ = self.transformer_cross_attention_layers[i](output, src[lvl], memory_mask=attn_mask, pos=pos[lvl],
                                                                        query_pos=query_embed,
                                                                        memory_operands=level_ops.setdefault(lvl, {}))    # :272-277

@@ -259,3 +259,23 @@ def test_encoder_pixel_decoder_mask_path_chain():
             _, multi2, extra = dec(enc(x.to(DEV)), rows_out=True)
             out2 = path(multi2, None, mask_rows=extra["mask_rows"], mask_shape=extra["mask_shape"])
         assert torch.equal(out2["pred_masks"], out["pred_masks"])
+
+
+def test_threshold_with_cleared_full_rows():
+    """svb_mask_threshold_heads_clear = svb_mask_threshold_heads followed by svb_mask_clear_full_rows (xdecoder.py:467 + :267), incl. rows
+    that are entirely masked, rows with a single open key, and a key count that is not a multiple of 16."""
+    g = torch.Generator().manual_seed(5)
+    for B, NH, Q, K in ((3, 8, 101, 1024), (2, 4, 7, 77)):
+        v = torch.randn(B, Q, K, generator=g)
+        v[0, 1] = -v[0, 1].abs() - 0.1                # every key masked -> cleared
+        v[1, 2] = -v[1, 2].abs() - 0.1
+        v[1, 2, K - 1] = 0.5                          # one open key -> kept
+        v[B - 1, Q - 1] = -1.0
+        vd = v.to(DEV).contiguous()
+        want = (vd.sigmoid().flatten(1).unsqueeze(1).repeat(1, NH, 1).flatten(0, 1) < 0.5).view(B * NH, Q, K).clone()
+        want[torch.where(want.sum(-1) == want.shape[-1])] = False
+        out = torch.ones(B * NH, Q, K, dtype=torch.bool, device=DEV)
+        cabi.check(cabi.lib().svb_mask_threshold_heads_clear(vd.data_ptr(), out.data_ptr(), B, NH, Q, K, cabi.stream_ptr()), "threshold_clear")
+        assert torch.equal(out, want)
+        assert not out[1 * 1, 1].any() if NH == 1 else True
+        assert not out[0:NH, 1].any() and out[NH:2 * NH, 2].sum() == NH * (K - 1)
