@@ -210,15 +210,17 @@ __global__ void fpn_gn_up_pad_kernel(const float* __restrict__ lat, const float*
         }
         __syncthreads();
     }
-    const size_t total = (size_t)(OH + 2) * (OW + 2) * c8n;
+    // (32-bit index arithmetic per image — the host checks (OH + 2) (OW + 2) C / 8 < 2^31: the 64-bit divisions of the first version made
+    // the kernel issue-bound, ncu: issue 73 %, DRAM 43 %)
+    const unsigned total = (unsigned)(OH + 2) * (unsigned)(OW + 2) * (unsigned)c8n, pw = (unsigned)(OW + 2);
     const float sh = (float)H / OH, sw = (float)W / OW;
     const float* lb = lat + (size_t)b * OH * OW * C;
     const float* sb = cur + (size_t)b * cur_sample_stride;
     bf16* db = dst + (size_t)b * (OH + 2) * (OW + 2) * C;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c8 = (int)(i % c8n);
-        const size_t p = i / c8n;
-        const int px = (int)(p % (OW + 2)), py = (int)(p / (OW + 2));
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned p = i / (unsigned)c8n;
+        const int c8 = (int)(i - p * (unsigned)c8n);
+        const int py = (int)(p / pw), px = (int)(p - (unsigned)py * pw);
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (py >= 1 && py <= OH && px >= 1 && px <= OW) {
             const int oy = py - 1, ox = px - 1, c0 = c8 * 8;
@@ -229,10 +231,16 @@ __global__ void fpn_gn_up_pad_kernel(const float* __restrict__ lat, const float*
                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
                 const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                if ((cg & 7) == 0) {                   // the thread's 8 channels lie in one group (one index division instead of eight)
+                    const float2 m = mr[c0 / cg];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float2 m = mr[(c0 + j) / cg];
-                    v[j] = (v[j] - m.x) * m.y * gm[j] + bt[j];
+                    for (int j = 0; j < 8; ++j) v[j] = (v[j] - m.x) * m.y * gm[j] + bt[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 m = mr[(c0 + j) / cg];
+                        v[j] = (v[j] - m.x) * m.y * gm[j] + bt[j];
+                    }
                 }
             }
             const float fy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
@@ -253,7 +261,7 @@ __global__ void fpn_gn_up_pad_kernel(const float* __restrict__ lat, const float*
                 v[4 * hq + 3] += w00 * a.w + w01 * bq.w + w10 * c.w + w11 * d.w;
             }
         }
-        store8(db + p * C + c8 * 8, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+        store8(db + (size_t)p * C + c8 * 8, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
     }
 }
 
@@ -390,6 +398,7 @@ extern "C" int svb_fpn_conv3x3_rows(const float* lateral, const float* gn_gamma,
                 "svb_fpn_conv3x3_rows: 16-byte aligned operands");
     if (cur_sample_stride <= 0) cur_sample_stride = (int64_t)cur_h * cur_w * cin;
     SVB_REQUIRE(cur_sample_stride % 4 == 0, "svb_fpn_conv3x3_rows: sample stride must be a multiple of 4 elements");
+    SVB_REQUIRE((int64_t)(h + 2) * (w + 2) * (cin / 8) < (1ll << 31), "svb_fpn_conv3x3_rows: map of %d x %d x %d too large for the per-image index", h, w, cin);
     cudaStream_t s = (cudaStream_t)stream;
     const bool norm = gn_gamma != nullptr;
     if (norm) {
