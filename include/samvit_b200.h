@@ -109,6 +109,10 @@ int svb_encoder_forward_host(svb_encoder_t* enc, const float* x_host, int batch,
  * upload of the first pass and the download of the last one (the only copies its pipeline exposes).  Writes the sizes to passes[] and
  * returns 1000 + their number (error codes stay below 1000). */
 int svb_encoder_pass_schedule(svb_encoder_t* e, int batch, int chunk, int host_path, int out_dtype, int* passes, int max_passes);
+/* The same schedules from the geometry alone (no encoder handle, no device: host logic that the CPU tests exercise): embed_dim /
+ * mlp_dim / depth of the blocks, tokens per image, SMs of the device, bytes per image the host path uploads / downloads. */
+int svb_pass_schedule_model(int embed_dim, int mlp_dim, int depth, int tokens, int sms, int batch, int chunk, int host_path,
+                            double in_bytes_per_image, double out_bytes_per_image, int* passes, int max_passes);
 
 /* Token stream (B*T, D) fp32 after the patch embedding (block = -1) or after block `block` of the LAST forward's
  * last chunk, copied into `dst` (device).  Only valid when taps were enabled; used by the parity tests to bisect. */

@@ -26,7 +26,7 @@ class SvbConfig(C.Structure):
 
 
 # every symbol include/samvit_b200.h declares: name -> (restype, argtypes)
-_vp, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+_vp, _i, _i64, _sz, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float, C.c_double
 SYMBOLS = {
     "svb_last_error": (C.c_char_p, []),
     "svb_version": (_i, []),
@@ -79,6 +79,7 @@ SYMBOLS = {
     "svb_add_cast_bcast": (_i, [_vp, _vp, _i64, _vp, _i, _i64, _vp]),
     "svb_linear_nt": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "svb_fpn_conv3x3_rows": (_i, [_vp, _vp, _vp, _i, _f, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "svb_pass_schedule_model": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _d, _d, _vp, _i]),
     "svb_encoder_pass_schedule": (_i, [_vp, _i, _i, _i, _i, _vp, _i]),
     "svb_mask_threshold_heads_clear": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "svb_layernorm_post": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _f, _vp]),

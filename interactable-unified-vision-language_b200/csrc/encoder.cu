@@ -551,23 +551,32 @@ int forward_chunk(svb_encoder* e, const void* x, int B, void* const outs[4], int
 // ceil(B*T/256) x ceil(N/256) tiles on num_sms/2 CTA pairs, so a pass costs ceil(tiles / pairs) rounds per GEMM: e.g. for ViT-H
 // 8 images fill 97.9 % of the rounds' slots, 12 images 99.8 %, 13 images 96.4 %.  Dynamic programme over the batch with that
 // cost (weighted by K, the work per tile) plus a small per-pass charge.
-std::vector<int> chunk_schedule(const svb_encoder* e, int batch, int max_chunk) {
+struct SchedGeom {          // what the schedules depend on (no device state: svb_pass_schedule_model runs them on a CPU-only host)
+    long D, mlp, T;
+    int depth, sms;
+};
+int device_sms() {
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    else cudaGetLastError();
+    return sms > 0 ? sms : 148;
+}
+SchedGeom geom_of(const svb_encoder* e) { return SchedGeom{e->D, e->mlp, e->T, e->depth, device_sms()}; }
+
+std::vector<int> chunk_schedule(const SchedGeom& gq, int batch, int max_chunk) {
     static const int fixed = [] { const char* v = getenv("SVB_FIXED_CHUNKS"); return v ? atoi(v) : 0; }();   // 1: equal passes of max_chunk
     std::vector<int> out;
     if (fixed || max_chunk >= batch) {
         for (int b0 = 0; b0 < batch; b0 += max_chunk) out.push_back(std::min(max_chunk, batch - b0));
         return out;
     }
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long pairs = std::max(1, sms / 2);
-    const long D = e->D, mlp = e->mlp;
+    const long pairs = std::max(1, gq.sms / 2);
+    const long D = gq.D, mlp = gq.mlp;
     const long shp[4][2] = {{3 * D, D}, {D, D}, {mlp, D}, {D, mlp}};
     auto cost = [&](int B) {
         double c = 0;
         for (auto& nk : shp) {
-            const long tiles = (((long)B * e->T + 255) / 256) * ((nk[0] + 255) / 256);
+            const long tiles = (((long)B * gq.T + 255) / 256) * ((nk[0] + 255) / 256);
             c += (double)nk[1] * (double)((tiles + pairs - 1) / pairs);
         }
         return c;
@@ -585,6 +594,7 @@ std::vector<int> chunk_schedule(const svb_encoder* e, int batch, int max_chunk) 
     std::sort(out.begin(), out.end(), [](int a, int b) { return a > b; });
     return out;
 }
+std::vector<int> chunk_schedule(const svb_encoder* e, int batch, int max_chunk) { return chunk_schedule(geom_of(e), batch, max_chunk); }
 
 size_t out_elems_per_image(const svb_encoder* e, int k, int img_h = 0, int img_w = 0) {
     if (img_h == 0) { img_h = e->cfg.img_size; img_w = e->cfg.img_size; }
@@ -599,28 +609,25 @@ size_t out_elems_per_image(const svb_encoder* e, int k, int img_h = 0, int img_w
 // block; PCIe at ~50 GB/s): ViT-H, 64 images: 5 x 12 + 4 instead of 16 + 4 x 12 (measured end to end 175.1 -> 175.9 images/s); ViT-B,
 // 16 images: 4 + 8 + 4 instead of one pass, whose copies nothing overlapped (511.9 -> 664.8 images/s).  SVB_HOST_SCHEDULE=0 keeps the
 // device schedule (A/B).
-std::vector<int> chunk_schedule_host(const svb_encoder* e, int batch, int max_chunk, double in_bytes_per_image, double out_bytes_per_image) {
+std::vector<int> chunk_schedule_host(const SchedGeom& gq, int batch, int max_chunk, double in_bytes_per_image, double out_bytes_per_image) {
     static const int on = [] { const char* v = getenv("SVB_HOST_SCHEDULE"); return v ? atoi(v) : 1; }();
     static const int fixed = [] { const char* v = getenv("SVB_FIXED_CHUNKS"); return v ? atoi(v) : 0; }();
-    if (!on || fixed || batch < 2) return chunk_schedule(e, batch, max_chunk);
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long pairs = std::max(1, sms / 2);
-    const long D = e->D, mlp = e->mlp;
+    if (!on || fixed || batch < 2) return chunk_schedule(gq, batch, max_chunk);
+    const long pairs = std::max(1, gq.sms / 2);
+    const long D = gq.D, mlp = gq.mlp;
     const long shp[4][2] = {{3 * D, D}, {D, D}, {mlp, D}, {D, mlp}};
     auto cost = [&](int B) {
         double c = 0;
         for (auto& nk : shp) {
-            const long tiles = (((long)B * e->T + 255) / 256) * ((nk[0] + 255) / 256);
+            const long tiles = (((long)B * gq.T + 255) / 256) * ((nk[0] + 255) / 256);
             c += (double)nk[1] * (double)((tiles + pairs - 1) / pairs);
         }
         return c;
     };
     const int cmax = std::min(max_chunk, batch);
     const int cmin = std::min(4, cmax);                                // first / last pass: at least 4 images where the chunk allows (smaller passes leave SMs idle in the attention kernels)
-    const double unit_s = 7.45e-9 * (double)e->depth * 1.4;            // seconds per cost unit (whole pass)
-    const double per_pass = 6.0 * e->depth * 4e-6 / unit_s;            // ~6 launches per block, ~4 us of fill / drain each
+    const double unit_s = 7.45e-9 * (double)gq.depth * 1.4;            // seconds per cost unit (whole pass)
+    const double per_pass = 6.0 * gq.depth * 4e-6 / unit_s;            // ~6 launches per block, ~4 us of fill / drain each
     const double h2d_units = in_bytes_per_image / 50e9 / unit_s, d2h_units = out_bytes_per_image / 50e9 / unit_s;
     // best[n] = cheapest way to run n images in the MIDDLE of the sequence (no exposure)
     std::vector<double> best(batch + 1, 1e300);
@@ -641,7 +648,7 @@ std::vector<int> chunk_schedule_host(const svb_encoder* e, int batch, int max_ch
             const double v = cost(f) + per_pass + (l ? cost(l) + per_pass : 0.0) + best[mid] + h2d_units * f + d2h_units * (l ? l : f);
             if (v < top) { top = v; bf = f; bl = l; }
         }
-    if (bf <= 0) return chunk_schedule(e, batch, max_chunk);           // (no candidate: cannot happen for batch >= 1, chunk >= 1)
+    if (bf <= 0) return chunk_schedule(gq, batch, max_chunk);          // (no candidate, e.g. 3 images in passes of 2: the device schedule)
     std::vector<int> out;
     out.push_back(bf);
     std::vector<int> midv;
@@ -650,6 +657,9 @@ std::vector<int> chunk_schedule_host(const svb_encoder* e, int batch, int max_ch
     out.insert(out.end(), midv.begin(), midv.end());
     if (bl) out.push_back(bl);
     return out;
+}
+std::vector<int> chunk_schedule_host(const svb_encoder* e, int batch, int max_chunk, double in_bytes_per_image, double out_bytes_per_image) {
+    return chunk_schedule_host(geom_of(e), batch, max_chunk, in_bytes_per_image, out_bytes_per_image);
 }
 
 }  // namespace
@@ -1058,6 +1068,18 @@ int svb_encoder_forward_host(svb_encoder_t* e, const float* x_host, int batch, v
     SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_comp));
     SVB_CHECK_CUDA(cudaStreamSynchronize(hp.s_out));
     return 0;
+}
+
+int svb_pass_schedule_model(int embed_dim, int mlp_dim, int depth, int tokens, int sms, int batch, int chunk, int host_path,
+                            double in_bytes_per_image, double out_bytes_per_image, int* passes, int max_passes) {
+    SVB_REQUIRE(passes && embed_dim > 0 && mlp_dim > 0 && depth > 0 && tokens > 0 && sms > 1 && batch > 0 && chunk > 0 && max_passes > 0,
+                "svb_pass_schedule_model: bad argument");
+    const SchedGeom gq{embed_dim, mlp_dim, tokens, depth, sms};
+    const std::vector<int> sch = host_path ? chunk_schedule_host(gq, batch, std::min(chunk, batch), in_bytes_per_image, out_bytes_per_image)
+                                           : chunk_schedule(gq, batch, chunk);
+    SVB_REQUIRE((int)sch.size() <= max_passes, "svb_pass_schedule_model: %d passes do not fit %d slots", (int)sch.size(), max_passes);
+    for (size_t i = 0; i < sch.size(); ++i) passes[i] = sch[i];
+    return (int)sch.size() + 1000;
 }
 
 int svb_encoder_pass_schedule(svb_encoder_t* e, int batch, int chunk, int host_path, int out_dtype, int* passes, int max_passes) {
