@@ -34,6 +34,7 @@ def test_device_schedule_follows_the_wave_quantisation():
     assert schedule("vit_h", 64, 16, False) == [16, 12, 12, 12, 12]
     assert schedule("vit_h", 16, 16, False) == [16] and schedule("vit_b", 16, 16, False) == [16]      # fits the chunk: one pass
     assert schedule("vit_h", 64, 8, False) == [8] * 8
+    assert schedule("vit_l", 32, 16, False) == [16, 16]       # (not 15 + 15 + 2: a pass has a fixed cost)
 
 
 def test_host_schedule_keeps_the_exposed_copies_small():
