@@ -453,3 +453,24 @@ def test_mask_head_oracle_properties():
     a = mo.cross_attention_layer(sd, tgt, mem, mask, None, None, NH)
     b = mo.cross_attention_layer(sd, tgt, mem2, mask, None, None, NH)
     assert float((a - b).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("g,ws", [(20, 14), (16, 16)])
+def test_key_bias_is_invisible_and_value_bias_folds_out(g, ws):
+    """The identity behind DESIGN.md's next step 4 (image_encoder.py:239-255 with the pad tokens of :183-187, 271-275): a constant added
+    to every key row shifts all scores of a query by the same amount (invisible to the softmax) and a constant added to every value
+    row comes out of the attention unchanged.  So with qkv = x W^T + b, the attention of the biased rows — pad tokens' rows equal to b —
+    equals the attention of the rows with the K and V parts of the bias REMOVED (pad rows: b_q | 0 | 0), plus b_v."""
+    from tests.util import ref_attention_core
+    gen = torch.Generator().manual_seed(g * 100 + ws)
+    B, heads, hd = 2, 3, 8
+    D = heads * hd
+    raw = torch.randn(B * g * g, 3 * D, generator=gen, dtype=torch.float64)
+    bias = torch.randn(3 * D, generator=gen, dtype=torch.float64)
+    rel_h = torch.randn(2 * ws - 1, hd, generator=gen, dtype=torch.float64) * 0.5
+    rel_w = torch.randn(2 * ws - 1, hd, generator=gen, dtype=torch.float64) * 0.5
+    full = ref_attention_core(raw + bias, rel_h, rel_w, bias, B, g, ws, heads)
+    bias_q_only = bias.clone()
+    bias_q_only[D:] = 0
+    reduced = ref_attention_core(raw + bias_q_only, rel_h, rel_w, bias_q_only, B, g, ws, heads)
+    assert torch.allclose(full, reduced + bias[2 * D:], rtol=1e-10, atol=1e-10)
