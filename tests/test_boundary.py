@@ -200,3 +200,48 @@ def test_install_into_reference_builds_the_drop_in():
         sys.path.remove(roots[0])
         for m in [m for m in sys.modules if m == "sam" or m.startswith("sam.")]:
             del sys.modules[m]
+
+
+def _header_prototypes(path):
+    """name -> list of C parameter declarations, from the (comment-stripped) header text."""
+    with open(path) as f:
+        txt = re.sub(r"/\*.*?\*/", " ", f.read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(svb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        params = " ".join(m.group(2).split())
+        protos[m.group(1)] = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+    return protos
+
+
+def _kind(cdecl):
+    if "*" in cdecl or "svb_stream_t" in cdecl:
+        return "ptr"
+    if re.search(r"\b(float|double)\b", cdecl):
+        return "real"
+    return "int"
+
+
+def test_ctypes_prototypes_agree_with_the_header():
+    """Every binding in cabi.SYMBOLS has as many arguments as the declaration in include/samvit_b200.h, of the same kind (pointer /
+    integer / floating point) in the same order: a slip here corrupts arguments silently at call time."""
+    import ctypes as C
+    protos = _header_prototypes(os.path.join(ROOT, "include", "samvit_b200.h"))
+    assert set(protos) == set(cabi.SYMBOLS)
+    ptr_types = (C.c_void_p, C.c_char_p)
+    for name, (_, argtypes) in cabi.SYMBOLS.items():
+        params = protos[name]
+        assert len(params) == len(argtypes), (name, params, argtypes)
+        for p, a in zip(params, argtypes):
+            if a in ptr_types or (isinstance(a, type) and issubclass(a, C._Pointer)):
+                want = "ptr"
+            elif a in (C.c_float, C.c_double):
+                want = "real"
+            else:
+                want = "int"
+            assert _kind(p) == want, (name, p, a)
+        # float vs double must match exactly (a float passed where a double is read is garbage)
+        for p, a in zip(params, argtypes):
+            if a is C.c_double:
+                assert re.search(r"\bdouble\b", p) and "*" not in p, (name, p)
+            if a is C.c_float:
+                assert re.search(r"\bfloat\b", p) and "*" not in p, (name, p)
